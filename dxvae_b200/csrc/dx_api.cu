@@ -1,0 +1,181 @@
+// C ABI (include/dxvae_b200.h) and the composite entry points.
+#include <stdarg.h>
+
+#include "../../include/dxvae_b200.h"
+#include "dx_engine.h"
+
+namespace dx {
+
+long long g_launches = 0;
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+struct TrainWs { EncWs e; DecWs d; float *mu, *sd, *dmu, *dsd; };
+
+static TrainWs carve_train(Arena& ar, int64_t B) {
+  TrainWs t;
+  t.e = carve_enc(ar, B, true);
+  t.d = carve_dec(ar, B, true);
+  t.mu = ar.take<float>((size_t)B * Z); t.sd = ar.take<float>((size_t)B * Z);
+  t.dmu = ar.take<float>((size_t)B * Z); t.dsd = ar.take<float>((size_t)B * Z);
+  return t;
+}
+
+size_t workspace_bytes(int op, int64_t B) {
+  Arena ar(nullptr, (size_t)-1);
+  switch (op) {
+    case DXVAE_OP_ENCODE: carve_enc(ar, B, false); break;
+    case DXVAE_OP_DECODE: carve_dec(ar, B, false); break;
+    case DXVAE_OP_TRAIN: carve_train(ar, B); break;
+    case DXVAE_OP_SCHEDULE: ar.take<int32_t>((size_t)36 * ((B + 1023) / 1024)); break;
+    default: return 0;
+  }
+  return ar.off + 256;
+}
+
+// model.py:369-372 forward (= encode + loss) and model.py:385 backward, one call.
+int elbo_step(dx_stream_t st, const float* weights, const Batch& bt, const float* eps, LossW lw, float* loss5,
+              float* mu_out, float* std_out, float* grads, void* ws, size_t ws_bytes) {
+  const int B = (int)bt.B;
+  Arena ar(ws, ws_bytes);
+  TrainWs t = carve_train(ar, bt.B);
+  DX_CHECK(!ar.overflow, "elbo_step: workspace too small (%zu < %zu bytes)", ws_bytes, ar.off);
+  Weights W(weights);
+  encode_fwd_impl(st, W, bt, t.e, t.mu, t.sd, true);
+  reparameterize(st, (int64_t)B * Z, t.mu, t.sd, eps, t.d.z);
+  zero_async(st, t.d.rowloss, sizeof(float) * 4 * (size_t)B);
+  DecIO io{true, &bt, lw, nullptr, nullptr};
+  decode_fwd_impl(st, W, B, t.d.z, t.d, io);
+  kld_rows(st, B, t.mu, t.sd, lw, t.d.rowloss);
+  loss_reduce(st, B, t.d.rowloss, loss5);
+  if (mu_out) copy_async(st, mu_out, t.mu, sizeof(float) * (size_t)B * Z);
+  if (std_out) copy_async(st, std_out, t.sd, sizeof(float) * (size_t)B * Z);
+  if (grads) {
+    Weights G(grads);
+    decode_bwd_impl(st, W, G, B, t.d.z, t.d, bt, lw);
+    latent_bwd(st, B, t.mu, t.sd, eps, t.d.dz, lw, t.dmu, t.dsd);
+    encode_bwd_impl(st, W, G, bt, t.e, t.dmu, t.dsd, t.sd);
+  }
+  return check_launch("elbo_step");
+}
+
+int decode_greedy(dx_stream_t st, const float* weights, int64_t B64, const float* z, float* Xg, float* Pg,
+                  uint64_t* adj, float* margins, void* ws, size_t ws_bytes) {
+  const int B = (int)B64;
+  Arena ar(ws, ws_bytes);
+  DecWs w = carve_dec(ar, B64, false);
+  DX_CHECK(!ar.overflow, "decode_greedy: workspace too small (%zu < %zu bytes)", ws_bytes, ar.off);
+  Weights W(weights);
+  zero_async(st, adj, sizeof(uint64_t) * (size_t)B);
+  if (margins) foreach (st, B, [=] DX_HD(int64_t i) { margins[i] = 3.0e38f; });
+  DecIO io{false, nullptr, LossW{0, 0, 0, 0}, adj, margins};
+  decode_fwd_impl(st, W, B, z, w, io);
+  unpack_graphs(st, B, w.Xd, w.Pn, Xg, Pg);
+  return check_launch("decode_greedy");
+}
+
+}  // namespace dx
+
+// =============================================================================================
+using namespace dx;
+#define DX_ST(s) ((dx_stream_t)(s))
+#define DX_BATCH_OK(B) DX_CHECK((B) > 0 && (int64_t)7 * (B) < (1ll << 31), "batch size %lld out of range", (long long)(B))
+
+extern "C" {
+
+int dxvae_abi_version(void) { return DXVAE_ABI_VERSION; }
+const char* dxvae_last_error(void) { return g_err; }
+long long dxvae_launch_count(void) { return g_launches; }
+
+int64_t dxvae_param_blob_floats(void) { return param_blob_floats(); }
+int64_t dxvae_param_count(void) {
+  int64_t n = 0;
+  for (int k = 0; k < P_COUNT; ++k) n += param_numel(k);
+  return n;
+}
+int dxvae_param_entry(int k, dxvae_param_entry_t* out) {
+  DX_CHECK(k >= 0 && k < P_COUNT && out, "param_entry: index %d out of range", k);
+  out->name = kParams[k].name; out->offset = offsets().o[k]; out->rows = kParams[k].rows; out->cols = kParams[k].cols;
+  return 0;
+}
+
+int dxvae_batch_build_host(int64_t B, const int32_t* edge_ptr_host, const int8_t* src_host, const int8_t* dst_host,
+                           uint64_t* adj_host, int32_t* indptr_host, int32_t* indices_host, uint8_t* eflags_host,
+                           uint8_t* level_host, int32_t* level_ptr_host, int32_t* level_rows_host, int32_t* n_levels) {
+  return batch_build_host(B, edge_ptr_host, src_host, dst_host, adj_host, indptr_host, indices_host, eflags_host,
+                          level_host, level_ptr_host, level_rows_host, n_levels);
+}
+int dxvae_batch_schedule(int64_t B, const uint64_t* adj, uint8_t* level, int32_t* level_ptr, int32_t* level_rows,
+                         int32_t* level_ptr_host, void* workspace, size_t workspace_bytes, void* stream) {
+  return batch_schedule(DX_ST(stream), B, adj, level, level_ptr, level_rows, level_ptr_host, workspace,
+                        workspace_bytes);
+}
+int dxvae_pack_graphs(int64_t B, const float* Xg, const float* Pg, float* Xn, int32_t* cls, void* stream) {
+  DX_CHECK(B > 0, "pack_graphs: empty batch");
+  return pack_graphs(DX_ST(stream), B, Xg, Pg, Xn, cls);
+}
+int dxvae_unpack_graphs(int64_t B, const float* Xn, const float* Pn, float* Xg, float* Pg, void* stream) {
+  DX_CHECK(B > 0, "unpack_graphs: empty batch");
+  return unpack_graphs(DX_ST(stream), B, Xn, Pn, Xg, Pg);
+}
+int dxvae_voices_to_graphs(int64_t B, const uint8_t* voices, float* Xn, int32_t* cls, uint64_t* adj, float* Xg,
+                           float* Pg, void* stream) {
+  DX_CHECK(B > 0, "voices_to_graphs: empty batch");
+  return voices_to_graphs(DX_ST(stream), B, voices, Xn, cls, adj, Xg, Pg);
+}
+int dxvae_pack_syx(int64_t B, const float* Pg, uint8_t* voices, void* stream) {
+  DX_CHECK(B > 0, "pack_syx: empty batch");
+  return pack_syx(DX_ST(stream), B, Pg, voices);
+}
+size_t dxvae_workspace_bytes(int op, int64_t B) { return workspace_bytes(op, B); }
+
+int dxvae_encode_fwd(const float* weights, int64_t B, const float* Xn, const uint64_t* adj, int32_t n_levels,
+                     const int32_t* level_ptr_host, const int32_t* level_rows, float* mu, float* std_, void* workspace,
+                     size_t workspace_bytes, int keep, void* stream) {
+  DX_BATCH_OK(B);
+  DX_CHECK(n_levels >= 1 && n_levels <= 6, "encode_fwd: n_levels=%d", n_levels);
+  Batch bt{B, Xn, nullptr, adj, n_levels, level_ptr_host, level_rows};
+  return encode_fwd(DX_ST(stream), weights, bt, mu, std_, workspace, workspace_bytes, keep);
+}
+int dxvae_reparameterize(int64_t n, const float* mu, const float* std_, const float* eps, float* z, void* stream) {
+  return reparameterize(DX_ST(stream), n, mu, std_, eps, z);
+}
+int dxvae_decode_greedy(const float* weights, int64_t B, const float* z, float* Xg, float* Pg, uint64_t* adj,
+                        float* margins, void* workspace, size_t workspace_bytes, void* stream) {
+  DX_BATCH_OK(B);
+  return decode_greedy(DX_ST(stream), weights, B, z, Xg, Pg, adj, margins, workspace, workspace_bytes);
+}
+int dxvae_elbo_step(const float* weights, int64_t B, const float* Xn, const int32_t* cls, const uint64_t* adj,
+                    int32_t n_levels, const int32_t* level_ptr_host, const int32_t* level_rows, const float* eps,
+                    float w_env, float w_frq, float w_kld, float inv_batch, float* loss5, float* mu_out,
+                    float* std_out, float* grads, void* workspace, size_t workspace_bytes, void* stream) {
+  DX_BATCH_OK(B);
+  DX_CHECK(n_levels >= 1 && n_levels <= 6, "elbo_step: n_levels=%d", n_levels);
+  Batch bt{B, Xn, cls, adj, n_levels, level_ptr_host, level_rows};
+  LossW lw{w_env, w_frq, w_kld, inv_batch};
+  return elbo_step(DX_ST(stream), weights, bt, eps, lw, loss5, mu_out, std_out, grads, workspace, workspace_bytes);
+}
+int dxvae_adamw_step(int64_t n, float* weights, const float* grads, float* exp_avg, float* exp_avg_sq, float lr,
+                     float beta1, float beta2, float eps, float weight_decay, int64_t step, float grad_scale,
+                     void* stream) {
+  DX_CHECK(n > 0 && step >= 1, "adamw_step: bad arguments");
+  return adamw_step(DX_ST(stream), n, weights, grads, exp_avg, exp_avg_sq, lr, beta1, beta2, eps, weight_decay, step,
+                    grad_scale);
+}
+int dxvae_test_gemm(int variant, int64_t M, int64_t N, int64_t K, const float* A, int64_t lda, const float* Bm,
+                    int64_t ldb, float* C, int64_t ldc, const float* bias, int act, int accumulate, void* stream) {
+  // variant 0: y = act(x W^T + b) ; 1: dx (+)= dy W ; 2: dW += dy^T x
+  if (variant == 0) linear_fwd(DX_ST(stream), (int)M, (int)N, (int)K, A, lda, Bm, ldb, bias, C, ldc, act);
+  else if (variant == 1) linear_dgrad(DX_ST(stream), (int)M, (int)N, (int)K, A, lda, Bm, ldb, C, ldc, accumulate);
+  else if (variant == 2) linear_wgrad(DX_ST(stream), (int)M, (int)N, (int)K, A, lda, Bm, ldb, C, ldc);
+  else { set_error("test_gemm: unknown variant %d", variant); return 1; }
+  return check_launch("test_gemm");
+}
+
+}  // extern "C"

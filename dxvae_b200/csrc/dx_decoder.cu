@@ -1,0 +1,509 @@
+// Autoregressive decoder: greedy generation (model.py:214-253, quantisers :87-149) and the
+// teacher-forced ELBO of model.py:270-367 with its hand-written backward (model.py:385).
+//
+// Both walk the same 34-propagate schedule (root, then per operator vi: P1, self-loop
+// decision, P2, and one re-propagate per lower node vj).  Exact re-arrangements used here
+// (DESIGN.md "decoder schedule"):
+//   * x W_ih^T of node vi is computed once and reused by all (2+vi) propagates;
+//   * P1/P2 have H_in = 0, so the combiner needs no hidden product and both share the
+//     looper's hidden product;
+//   * a finished node's gate/mapper projections (Pg,Pm) and its half of the edge-MLP first
+//     layer (Q = h_j W_e0[:,512:]^T + b) are computed once and reused by every later node;
+//   * the aggregated input of node vi is kept as a running sum, one message added per step
+//     (same left-to-right order as the reference's slot sum).
+#include "dx_engine.h"
+#include "dx_tables.h"
+
+namespace dx {
+
+DecWs carve_dec(Arena& ar, int64_t B, bool train) {
+  DecWs w{};
+  const size_t b = (size_t)B;
+  w.z = ar.take<float>(b * Z); w.Hinit = ar.take<float>(b * H); w.Hd = ar.take<float>(7 * b * H);
+  w.Pg = ar.take<float>(6 * b * 2 * H); w.Pm = ar.take<float>(6 * b * 2 * H); w.Q = ar.take<float>(6 * b * 4 * H);
+  w.gh = ar.take<float>(b * G3); w.ghl0 = ar.take<float>(b * G3); w.Hrun = ar.take<float>(b * H);
+  auto per_node = [&](float** arr, size_t cols, bool need) {
+    float* shared = need ? nullptr : ar.take<float>(b * cols);
+    for (int v = 0; v < 7; ++v) arr[v] = need ? ar.take<float>(b * cols) : shared;
+  };
+  auto per_step = [&](float** arr, size_t cols, bool need) {
+    float* shared = need ? nullptr : ar.take<float>(b * cols);
+    for (int t = 0; t < NSTEP; ++t) arr[t] = need ? ar.take<float>(b * cols) : shared;
+  };
+  per_node(w.A1, 2 * H, train); per_node(w.A2, 2 * H, train); per_node(w.L, LD_L, train);
+  per_node(w.gxc, G3, train); per_node(w.gxl, G3, train); per_node(w.Hc0, H, train);
+  per_node(w.Hi_p1, H, train); per_node(w.Hi_p2, H, train); per_node(w.ES1, 2 * H, train); per_node(w.ls, 1, train);
+  per_step(w.E1, 4 * H, train); per_step(w.l2, 2, train); per_step(w.Hin, H, train); per_step(w.Hc, H, train);
+  per_step(w.Hi, H, train);
+  if (train) {
+    w.g_root = ar.take<float>(b * 4 * H);
+    per_node(w.dL, LD_L, true); per_node(w.g_c0, 4 * H, true); per_node(w.g_p1, 4 * H, true);
+    per_node(w.g_p2, 4 * H, true); per_node(w.dls, 1, true);
+    per_step(w.dl2, 2, true); per_step(w.g_c, 4 * H, true); per_step(w.g_l, 4 * H, true);
+    w.rowloss = ar.take<float>(4 * b);
+    w.dHd = ar.take<float>(7 * b * H); w.dPg = ar.take<float>(6 * b * 2 * H); w.dPm = ar.take<float>(6 * b * 2 * H);
+    w.dQ = ar.take<float>(6 * b * 4 * H); w.dgb = ar.take<float>(6 * b * H);
+    w.dHi = ar.take<float>(b * H); w.dHc = ar.take<float>(b * H); w.dHin = ar.take<float>(b * H);
+    w.dHrun = ar.take<float>(b * H); w.dHc0 = ar.take<float>(b * H);
+    w.dgx = ar.take<float>(b * G3); w.dgxs = ar.take<float>(b * G3); w.dgh = ar.take<float>(b * G3);
+    w.dE1 = ar.take<float>(b * 4 * H); w.dA1 = ar.take<float>(b * 2 * H); w.dA2 = ar.take<float>(b * 2 * H);
+    w.dES1 = ar.take<float>(b * 2 * H); w.dHinit = ar.take<float>(b * H); w.dz = ar.take<float>(b * Z);
+  } else {
+    w.Xd = ar.take<float>(7 * b * XP); w.Pn = ar.take<float>(7 * b * XP);
+  }
+  return w;
+}
+
+// ---- numerically stable pieces shared by the loss heads ---------------------------------
+DX_HD DX_INLINE float bce_logits(float x, float t) {  // BCEWithLogitsLoss, reduction='none'
+  return fmaxf(x, 0.f) - x * t + log1pf(expf(-fabsf(x)));
+}
+
+// ---- loss heads (thread per graph): value into rowloss[k][b] (+=), gradient of the logits ----
+// node 0: model.py:303-308
+static void loss_x0(dx_stream_t st, int B, const float* L0, const float* X0, const int32_t* cls, LossW lw,
+                    float* rowloss, float* dL) {
+  foreach (st, B, [=] DX_HD(int64_t b) {
+    const float* l = L0 + b * LD_L; const float* x = X0 + b * XP; float* d = dL + b * LD_L;
+    const float ib = lw.inv_batch;
+    float acc = 0.f;
+    for (int c = 0; c < 15; ++c) {
+      const float w = c < 8 ? lw.w_env : (c == 8 ? lw.w_frq : 1.f);
+      const float df = l[c] * w - x[c] * w;
+      acc += df * df; d[c] = 2.f * df * w * ib;
+    }
+    for (int c = 15; c < 17; ++c) { acc += bce_logits(l[c], x[c]); d[c] = (sigmoidf_(l[c]) - x[c]) * ib; }
+    for (int seg = 0; seg < 2; ++seg) {
+      const int lo = seg == 0 ? 17 : 23, n = seg == 0 ? 6 : 32;
+      const int tgt = cls[(int64_t)seg * B + b];
+      float mx = l[lo];
+      for (int c = 1; c < n; ++c) mx = fmaxf(mx, l[lo + c]);
+      float se = 0.f;
+      for (int c = 0; c < n; ++c) se += expf(l[lo + c] - mx);
+      const float lse = mx + logf(se);
+      acc += lse - l[lo + tgt];
+      for (int c = 0; c < n; ++c) d[lo + c] = (expf(l[lo + c] - lse) - (c == tgt ? 1.f : 0.f)) * ib;
+    }
+    for (int c = 55; c < LD_L; ++c) d[c] = 0.f;
+    rowloss[b] += acc * ib;  // slot 0: loss_X0
+  });
+}
+// operator vi: model.py:323-328
+static void loss_xi(dx_stream_t st, int B, int vi, const float* Li, const float* Xi, const int32_t* cls, LossW lw,
+                    float* rowloss, float* dL) {
+  foreach (st, B, [=] DX_HD(int64_t b) {
+    const float* l = Li + b * LD_L; const float* x = Xi + b * XP; float* d = dL + b * LD_L;
+    const float ib = lw.inv_batch;
+    float acc = 0.f;
+    for (int c = 0; c < 18; ++c) {
+      const float w = c < 9 ? lw.w_env : (c == 9 ? lw.w_frq : 1.f);
+      const float df = l[c] * w - x[c] * w;
+      acc += df * df; d[c] = 2.f * df * w * ib;
+    }
+    acc += bce_logits(l[18], x[18]); d[18] = (sigmoidf_(l[18]) - x[18]) * ib;
+    for (int seg = 0; seg < 2; ++seg) {
+      const int lo = 19 + 4 * seg;
+      const int tgt = cls[(int64_t)(2 + 6 * seg + (vi - 1)) * B + b];
+      float mx = l[lo];
+      for (int c = 1; c < 4; ++c) mx = fmaxf(mx, l[lo + c]);
+      float se = 0.f;
+      for (int c = 0; c < 4; ++c) se += expf(l[lo + c] - mx);
+      const float lse = mx + logf(se);
+      acc += lse - l[lo + tgt];
+      for (int c = 0; c < 4; ++c) d[lo + c] = (expf(l[lo + c] - lse) - (c == tgt ? 1.f : 0.f)) * ib;
+    }
+    for (int c = 27; c < LD_L; ++c) d[c] = 0.f;
+    rowloss[(int64_t)B + b] += acc * ib;  // slot 1: loss_Xi
+  });
+}
+// edge heads: model.py:339 (self loop, n=1: target A[vi,vi]) and :363 (n=2: A[vj,vi], A[vi,vj])
+static void loss_edge(dx_stream_t st, int B, int vi, int vj, const float* lg, int n, const uint64_t* adj, LossW lw,
+                      float* rowloss, float* dlg) {
+  foreach (st, B, [=] DX_HD(int64_t b) {
+    const uint64_t A = adj[b];
+    float acc = 0.f;
+    for (int c = 0; c < n; ++c) {
+      const float t = (n == 1) ? (float)abit(A, vi, vi) : (c == 0 ? (float)abit(A, vj, vi) : (float)abit(A, vi, vj));
+      const float x = lg[b * n + c];
+      acc += bce_logits(x, t);
+      dlg[b * n + c] = (sigmoidf_(x) - t) * lw.inv_batch;
+    }
+    rowloss[(int64_t)2 * B + b] += acc * lw.inv_batch;  // slot 2: loss_E
+  });
+}
+// KL(N(0,1) || N(mu,std)) per graph (model.py:365) and the latent gradients.
+//   dmu = dz + w*mu/std^2/B ; dstd = dz*eps + w*(1/std - (1+mu^2)/std^3)/B        (dz may be NULL)
+void kld_rows(dx_stream_t st, int B, const float* mu, const float* sd, LossW lw, float* rowloss) {
+  foreach (st, B, [=] DX_HD(int64_t b) {
+    float acc = 0.f;
+    for (int k = 0; k < Z; ++k) {
+      const float m = mu[b * Z + k], s = sd[b * Z + k];
+      const float vr = (1.f / s) * (1.f / s), t1 = (m / s) * (m / s);
+      acc += 0.5f * (vr + t1 - 1.f - logf(vr));
+    }
+    rowloss[(int64_t)3 * B + b] = acc * lw.inv_batch * lw.w_kld;  // slot 3: kld * w_kld
+  });
+}
+void latent_bwd(dx_stream_t st, int B, const float* mu, const float* sd, const float* eps, const float* dz,
+                       LossW lw, float* dmu, float* dsd) {
+  foreach (st, (int64_t)B * Z, [=] DX_HD(int64_t i) {
+    const float m = mu[i], s = sd[i], g = dz[i];
+    const float k = lw.w_kld * lw.inv_batch;
+    dmu[i] = g + k * m / (s * s);
+    dsd[i] = g * eps[i] + k * (1.f / s - (1.f + m * m) / (s * s * s));
+  });
+}
+// loss5 = (sum, x0, xi, e, kld_w): deterministic two-level sum over the B rows of each slot.
+#ifndef DX_EMU
+__global__ void __launch_bounds__(1024) k_loss_reduce(int B, const float* __restrict__ rowloss, float* __restrict__ out) {
+  __shared__ double red[32];
+  __shared__ double tot[4];
+  for (int k = 0; k < 4; ++k) {
+    double s = 0.0;
+    for (int i = threadIdx.x; i < B; i += blockDim.x) s += (double)rowloss[(int64_t)k * B + i];
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+      double v = red[threadIdx.x];
+      for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+      if (threadIdx.x == 0) tot[k] = v;
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    out[0] = (float)(tot[0] + tot[1] + tot[2] + tot[3]);
+    out[1] = (float)tot[0]; out[2] = (float)tot[1]; out[3] = (float)tot[2]; out[4] = (float)tot[3];
+  }
+}
+void loss_reduce(dx_stream_t st, int B, const float* rowloss, float* out) {
+  k_loss_reduce<<<1, 1024, 0, st>>>(B, rowloss, out);
+  ++g_launches;
+}
+#else
+void loss_reduce(dx_stream_t, int B, const float* rowloss, float* out) {
+  double t[4];
+  for (int k = 0; k < 4; ++k) { t[k] = 0; for (int i = 0; i < B; ++i) t[k] += rowloss[(int64_t)k * B + i]; }
+  out[0] = (float)(t[0] + t[1] + t[2] + t[3]);
+  for (int k = 0; k < 4; ++k) out[1 + k] = (float)t[k];
+}
+#endif
+
+// ---- quantisers (greedy decode), thread per graph -----------------------------------------
+DX_HD DX_INLINE float tab_f(const uint32_t* t, int i) {
+  union { uint32_t u; float f; } c; c.u = t[i]; return c.f;
+}
+#ifndef DX_EMU
+__constant__ uint32_t c_tab32[32];
+__constant__ uint32_t c_tab100[100];
+#define DX_TAB32 c_tab32
+#define DX_TAB100 c_tab100
+static void upload_tables() {
+  static bool done = false;  // per process; the tables are immutable constants
+  if (done) return;
+  cudaMemcpyToSymbol(c_tab32, kLogTab32, sizeof(kLogTab32));
+  cudaMemcpyToSymbol(c_tab100, kLogTab100, sizeof(kLogTab100));
+  done = true;
+}
+#else
+#define DX_TAB32 kLogTab32
+#define DX_TAB100 kLogTab100
+static void upload_tables() {}
+#endif
+
+DX_HD DX_INLINE void q_lin(float x, float scale, float* xo, float* po) {   // model.py:87-91
+  float p = rintf(x * scale);
+  p = fminf(fmaxf(p, 0.f), scale);
+  *po = p; *xo = p / scale;
+}
+DX_HD DX_INLINE float q_round_log(float x, float scale) {                  // model.py:93-96
+  float p = rintf(expf(x * logf(scale + 1.f)) - 1.f);
+  return fminf(fmaxf(p, 0.f), scale);
+}
+DX_HD DX_INLINE int argmax_n(const float* l, int n) {
+  int best = 0; float bv = l[0];
+  for (int c = 1; c < n; ++c) if (l[c] > bv) { bv = l[c]; best = c; }
+  return best;
+}
+// _reg_x0, model.py:109-125.  Writes node-major X row (32 wide, zero padded) and params row (32 wide).
+static void reg_x0(dx_stream_t st, int B, const float* L0, float* Xd, float* Pn) {
+  foreach (st, B, [=] DX_HD(int64_t b) {
+    const float* l = L0 + b * LD_L; float* x = Xd + b * XP; float* p = Pn + b * XP;
+    for (int c = 0; c < XP; ++c) { x[c] = 0.f; p[c] = 0.f; }
+    for (int c = 0; c < 15; ++c) {
+      const float sc = c == 8 ? 48.f : (c >= 13 ? 7.f : 99.f);
+      q_lin(l[c], sc, &x[c], &p[c]);
+    }
+    for (int c = 15; c < 17; ++c) { const float v = rintf(sigmoidf_(l[c])); x[c] = v; p[c] = v; }
+    const int lfw = argmax_n(l + 17, 6);
+    x[17 + lfw] = 1.f; p[17] = (float)lfw;
+    p[18] = (float)argmax_n(l + 23, 32);
+  });
+}
+// _reg_xi, model.py:127-149 (incl. the 23:26 argmax quirk and the per-mode fc/ff quantiser)
+static void reg_xi(dx_stream_t st, int B, const float* Li, float* Xd, float* Pn) {
+  foreach (st, B, [=] DX_HD(int64_t b) {
+    const float* l = Li + b * LD_L; float* x = Xd + b * XP; float* p = Pn + b * XP;
+    for (int c = 0; c < XP; ++c) { x[c] = 0.f; p[c] = 0.f; }
+    for (int c = 0; c < 9; ++c) q_lin(l[c], 99.f, &x[c], &p[c]);
+    q_lin(l[11], 14.f, &x[11], &p[11]);
+    for (int c = 12; c < 15; ++c) q_lin(l[c], 99.f, &x[c], &p[c]);
+    q_lin(l[15], 3.f, &x[15], &p[15]);
+    q_lin(l[16], 7.f, &x[16], &p[16]); q_lin(l[17], 7.f, &x[17], &p[17]);
+    const float mode = rintf(sigmoidf_(l[18]));
+    x[18] = mode; p[18] = mode;
+    const int lc = argmax_n(l + 19, 4); x[19 + lc] = 1.f; p[19] = (float)lc;
+    const int rc = argmax_n(l + 23, 3); x[23 + rc] = 1.f; p[20] = (float)rc;
+    if (mode == 0.f) {
+      const float pc = q_round_log(l[9], 31.f), pf = q_round_log(l[10], 99.f);
+      p[9] = pc; x[9] = tab_f(DX_TAB32, (int)pc);
+      p[10] = pf; x[10] = tab_f(DX_TAB100, (int)pf);
+    } else {
+      q_lin(l[9], 3.f, &x[9], &p[9]); q_lin(l[10], 99.f, &x[10], &p[10]);
+    }
+  });
+}
+// edge decisions (model.py:236-239, 245-250): sigmoid(logit) > 0.5 ; sets adjacency bits, tracks margins
+static void decide_edges(dx_stream_t st, int B, int vi, int vj, const float* lg, int n, uint64_t* adj, float* margins) {
+  foreach (st, B, [=] DX_HD(int64_t b) {
+    uint64_t A = adj[b];
+    float mg = margins ? margins[b] : 0.f;
+    for (int c = 0; c < n; ++c) {
+      const float x = lg[b * n + c];
+      const bool on = sigmoidf_(x) > 0.5f;
+      int s, d;
+      if (n == 1) { s = vi; d = vi; } else if (c == 0) { s = vj; d = vi; } else { s = vi; d = vj; }
+      if (on) A |= (1ull << (s * 7 + d));
+      mg = fminf(mg, fabsf(x));
+    }
+    adj[b] = A;
+    if (margins) margins[b] = mg;
+  });
+}
+
+// =============================================================================================
+// forward
+// =============================================================================================
+
+static void mlp3_fwd(dx_stream_t st, const Weights& W, int B, int w0, const float* hin, int nout, float* A1, float* A2,
+                     float* L) {
+  linear_fwd(st, B, 2 * H, H, hin, H, W[w0], H, W[w0 + 1], A1, 2 * H, ACT_RELU);
+  linear_fwd(st, B, 2 * H, 2 * H, A1, 2 * H, W[w0 + 2], 2 * H, W[w0 + 3], A2, 2 * H, ACT_RELU);
+  linear_fwd(st, B, nout, 2 * H, A2, 2 * H, W[w0 + 4], 2 * H, W[w0 + 5], L, LD_L);
+}
+
+static void node_projections(dx_stream_t st, const Weights& W, int B, int v, const DecWs& w) {
+  const float* h = w.Hd + (size_t)v * B * H;
+  linear_fwd(st, B, 2 * H, H, h, H, W[P_G_W], H, nullptr, w.Pg + (size_t)v * B * 2 * H, 2 * H);
+  linear_fwd(st, B, 2 * H, H, h, H, W[P_M_W], H, nullptr, w.Pm + (size_t)v * B * 2 * H, 2 * H);
+  // Hj half of h_to_edge.0 (columns 512..1023 of the (2048,1024) weight) + its bias
+  linear_fwd(st, B, 4 * H, H, h, H, W[P_E_W0] + H, 2 * H, W[P_E_B0], w.Q + (size_t)v * B * 4 * H, 4 * H);
+}
+
+void decode_fwd_impl(dx_stream_t st, const Weights& W, int B, const float* z, const DecWs& w, const DecIO& io) {
+  const bool train = io.train;
+  const uint64_t* adj = train ? io.bt->adj : io.adj_out;
+  const float* Xsrc = train ? io.bt->Xn : w.Xd;   // node-major (7,B,32)
+  upload_tables();
+
+  linear_fwd(st, B, H, Z, z, Z, W[P_ZH_W], Z, W[P_ZH_B], w.Hinit, H, ACT_TANH);
+  mlp3_fwd(st, W, B, P_X0_W0, w.Hinit, SX0 + 32, w.A1[0], w.A2[0], w.L[0]);
+  if (train) loss_x0(st, B, w.L[0], Xsrc, io.bt->cls, io.lw, w.rowloss, w.dL[0]);
+  else reg_x0(st, B, w.L[0], w.Xd, w.Pn);
+  // root: h_0 = GRU_root(x0[:23], H_init)
+  linear_fwd(st, B, G3, SX0, Xsrc, XP, W[P_RD_WIH], SX0, nullptr, w.gxc[0], G3);
+  linear_fwd(st, B, G3, H, w.Hinit, H, W[P_RD_WHH], H, nullptr, w.gh, G3);
+  {
+    RowMap rm{B, B, nullptr, 0};
+    CellFwd c{rm, w.gxc[0], w.gh, W[P_RD_BIH], W[P_RD_BHH], w.Hinit, 0, w.Hd, 0, train ? w.g_root : nullptr, 0, S_ONE, adj};
+    cell_fwd(st, c);
+  }
+  node_projections(st, W, B, 0, w);
+
+  int t = 0;
+  for (int vi = 1; vi < NN; ++vi) {
+    const float* hprev_node = w.Hd + (size_t)(vi - 1) * B * H;
+    float* Xi = const_cast<float*>(Xsrc) + (size_t)vi * B * XP;
+    RowMap rm{B, B, nullptr, vi * B};
+    mlp3_fwd(st, W, B, P_X_W0, hprev_node, SX, w.A1[vi], w.A2[vi], w.L[vi]);
+    if (train) loss_xi(st, B, vi, w.L[vi], Xi, io.bt->cls, io.lw, w.rowloss, w.dL[vi]);
+    else reg_xi(st, B, w.L[vi], w.Xd + (size_t)vi * B * XP, w.Pn + (size_t)vi * B * XP);
+    linear_fwd(st, B, G3, SX, Xi, XP, W[P_CD_WIH], SX, nullptr, w.gxc[vi], G3);
+    linear_fwd(st, B, G3, SX, Xi, XP, W[P_LD_WIH], SX, nullptr, w.gxl[vi], G3);
+    // P1 (model.py:234/320): no edges yet -> H_in = 0, x_loop = 0
+    CellFwd c0{rm, w.gxc[vi], nullptr, W[P_CD_BIH], W[P_CD_BHH], nullptr, 0, w.Hc0[vi], 0, train ? w.g_c0[vi] : nullptr, 0,
+               S_ONE, adj};
+    cell_fwd(st, c0);
+    linear_fwd(st, B, G3, H, w.Hc0[vi], H, W[P_LD_WHH], H, nullptr, w.ghl0, G3);
+    CellFwd p1{rm, w.gxl[vi], w.ghl0, W[P_LD_BIH], W[P_LD_BHH], w.Hc0[vi], 0, w.Hi_p1[vi], 0, train ? w.g_p1[vi] : nullptr,
+               0, S_ZERO, adj};
+    cell_fwd(st, p1);
+    // self-loop head (model.py:236/331)
+    linear_fwd(st, B, 2 * H, H, w.Hi_p1[vi], H, W[P_ES_W0], H, W[P_ES_B0], w.ES1[vi], 2 * H, ACT_RELU);
+    linear_fwd(st, B, 1, 2 * H, w.ES1[vi], 2 * H, W[P_ES_W2], 2 * H, W[P_ES_B2], w.ls[vi], 1);
+    if (train) loss_edge(st, B, vi, vi, w.ls[vi], 1, adj, io.lw, w.rowloss, w.dls[vi]);
+    else decide_edges(st, B, vi, vi, w.ls[vi], 1, io.adj_out, io.margins);
+    // P2 (model.py:240/337): same H_in = 0, x_loop = s*x
+    CellFwd p2{rm, w.gxl[vi], w.ghl0, W[P_LD_BIH], W[P_LD_BHH], w.Hc0[vi], 0, w.Hi_p2[vi], 0, train ? w.g_p2[vi] : nullptr,
+               0, S_SELF, adj};
+    cell_fwd(st, p2);
+    zero_async(st, w.Hrun, sizeof(float) * (size_t)B * H);
+    const float* Hi_prev = w.Hi_p2[vi];
+    for (int vj = vi - 1; vj >= 0; --vj, ++t) {
+      // edge head on cat[Hi, Hj] (model.py:245/350): first layer split into Hi half + cached Hj half
+      linear_fwd(st, B, 4 * H, H, Hi_prev, H, W[P_E_W0], 2 * H, nullptr, w.E1[t], 4 * H, ACT_RELU, nullptr, nullptr,
+                 w.Q + (size_t)vj * B * 4 * H, 4 * H);
+      linear_fwd(st, B, 2, 4 * H, w.E1[t], 4 * H, W[P_E_W2], 4 * H, W[P_E_B2], w.l2[t], 2);
+      if (train) loss_edge(st, B, vi, vj, w.l2[t], 2, adj, io.lw, w.rowloss, w.dl2[t]);
+      else decide_edges(st, B, vi, vj, w.l2[t], 2, io.adj_out, io.margins);
+      // add the message of vj to the running aggregate, then re-propagate (model.py:251/358)
+      MsgFwd mf{rm, w.Pg, w.Pm, W[P_G_B], adj, w.Hrun, 0, vj, vj, 1};
+      msg_fwd(st, mf);
+      if (train) copy_async(st, w.Hin[t], w.Hrun, sizeof(float) * (size_t)B * H);
+      const float* Hin_t = train ? w.Hin[t] : w.Hrun;
+      linear_fwd(st, B, G3, H, Hin_t, H, W[P_CD_WHH], H, nullptr, w.gh, G3);
+      CellFwd cc{rm, w.gxc[vi], w.gh, W[P_CD_BIH], W[P_CD_BHH], Hin_t, 0, w.Hc[t], 0, train ? w.g_c[t] : nullptr, 0, S_ONE,
+                 adj};
+      cell_fwd(st, cc);
+      linear_fwd(st, B, G3, H, w.Hc[t], H, W[P_LD_WHH], H, nullptr, w.gh, G3);
+      float* Hi_out = (vj == 0) ? w.Hd + (size_t)vi * B * H : w.Hi[t];
+      CellFwd cl{rm, w.gxl[vi], w.gh, W[P_LD_BIH], W[P_LD_BHH], w.Hc[t], 0, Hi_out, 0, train ? w.g_l[t] : nullptr, 0, S_SELF,
+                 adj};
+      cell_fwd(st, cl);
+      Hi_prev = Hi_out;
+    }
+    if (vi < NN - 1) node_projections(st, W, B, vi, w);
+  }
+}
+
+// =============================================================================================
+// backward (teacher-forced loss only)
+// =============================================================================================
+static void mlp3_bwd(dx_stream_t st, const Weights& W, const Weights& G, int B, int w0, const float* hin, int nout,
+                     const float* A1, const float* A2, const float* dL, const DecWs& w, float* dhin) {
+  linear_wgrad(st, B, nout, 2 * H, dL, LD_L, A2, 2 * H, G[w0 + 4], 2 * H);
+  colsum_accum(st, B, nout, dL, LD_L, G[w0 + 5]);
+  linear_dgrad(st, B, nout, 2 * H, dL, LD_L, W[w0 + 4], 2 * H, w.dA2, 2 * H, ACC_STORE);
+  relu_mask(st, (int64_t)B * 2 * H / 4, w.dA2, A2);
+  linear_wgrad(st, B, 2 * H, 2 * H, w.dA2, 2 * H, A1, 2 * H, G[w0 + 2], 2 * H);
+  colsum_accum(st, B, 2 * H, w.dA2, 2 * H, G[w0 + 3]);
+  linear_dgrad(st, B, 2 * H, 2 * H, w.dA2, 2 * H, W[w0 + 2], 2 * H, w.dA1, 2 * H, ACC_STORE);
+  relu_mask(st, (int64_t)B * 2 * H / 4, w.dA1, A1);
+  linear_wgrad(st, B, 2 * H, H, w.dA1, 2 * H, hin, H, G[w0], H);
+  colsum_accum(st, B, 2 * H, w.dA1, 2 * H, G[w0 + 1]);
+  linear_dgrad(st, B, 2 * H, H, w.dA1, 2 * H, W[w0], H, dhin, H, ACC_ADD);
+}
+
+// looper cell backward for one propagate: dHi -> (dHc += ..., weight grads)
+static void looper_bwd(dx_stream_t st, const Weights& W, const Weights& G, int B, int vi, const RowMap& rm,
+                       const float* dHi, const float* gates, const float* Hc, int smode, const uint64_t* adj,
+                       const float* Xi, const DecWs& w, float* dHc, bool dHc_accum) {
+  // dHc (+)= dHi*z + dgh W_hh
+  float* direct = dHc_accum ? w.dHin : dHc;  // dHin is free scratch at this point
+  CellBwd cb{rm, dHi, 0, gates, 0, Hc, 0, w.dgx, smode == S_SELF ? w.dgxs : nullptr, w.dgh, direct, smode, adj};
+  cell_bwd(st, cb);
+  if (dHc_accum) add_inplace(st, (int64_t)B * H / 4, dHc, direct);
+  linear_dgrad(st, B, G3, H, w.dgh, G3, W[P_LD_WHH], H, dHc, H, ACC_ADD);
+  linear_wgrad(st, B, G3, H, w.dgh, G3, Hc, H, G[P_LD_WHH], H);
+  colsum_accum(st, B, G3, w.dgh, G3, G[P_LD_BHH]);
+  colsum_accum(st, B, G3, w.dgx, G3, G[P_LD_BIH]);
+  if (smode == S_SELF) linear_wgrad(st, B, G3, SX, w.dgxs, G3, Xi, XP, G[P_LD_WIH], SX);
+  else if (smode == S_ONE) linear_wgrad(st, B, G3, SX, w.dgx, G3, Xi, XP, G[P_LD_WIH], SX);
+  (void)vi;
+}
+
+void decode_bwd_impl(dx_stream_t st, const Weights& W, const Weights& G, int B, const float* z, const DecWs& w,
+                     const Batch& bt, LossW lw) {
+  const uint64_t* adj = bt.adj;
+  const size_t bH = (size_t)B * H;
+  zero_async(st, w.dHd, sizeof(float) * 7 * bH);
+  zero_async(st, w.dPg, sizeof(float) * 6 * (size_t)B * 2 * H);
+  zero_async(st, w.dPm, sizeof(float) * 6 * (size_t)B * 2 * H);
+  zero_async(st, w.dQ, sizeof(float) * 6 * (size_t)B * 4 * H);
+  zero_async(st, w.dgb, sizeof(float) * 6 * bH);
+
+  int t_end = NSTEP;  // steps of node vi occupy [t_end - vi, t_end)
+  for (int vi = NN - 1; vi >= 1; --vi) {
+    const float* Xi = bt.Xn + (size_t)vi * B * XP;
+    RowMap rm{B, B, nullptr, vi * B};
+    const int t0 = t_end - vi;       // step index of vj = vi-1 ; vj = 0 is t_end-1
+    copy_async(st, w.dHi, w.dHd + (size_t)vi * bH, sizeof(float) * bH);
+    zero_async(st, w.dHrun, sizeof(float) * bH);
+    for (int vj = 0; vj < vi; ++vj) {
+      const int t = t0 + (vi - 1 - vj);
+      // looper then combiner of this propagate
+      looper_bwd(st, W, G, B, vi, rm, w.dHi, w.g_l[t], w.Hc[t], S_SELF, adj, Xi, w, w.dHc, false);
+      CellBwd cc{rm, w.dHc, 0, w.g_c[t], 0, w.Hin[t], 0, w.dgx, nullptr, w.dgh, w.dHin, S_ONE, adj};
+      cell_bwd(st, cc);
+      linear_dgrad(st, B, G3, H, w.dgh, G3, W[P_CD_WHH], H, w.dHin, H, ACC_ADD);
+      linear_wgrad(st, B, G3, H, w.dgh, G3, w.Hin[t], H, G[P_CD_WHH], H);
+      linear_wgrad(st, B, G3, SX, w.dgx, G3, Xi, XP, G[P_CD_WIH], SX);
+      colsum_accum(st, B, G3, w.dgh, G3, G[P_CD_BHH]);
+      colsum_accum(st, B, G3, w.dgx, G3, G[P_CD_BIH]);
+      add_inplace(st, (int64_t)bH / 4, w.dHrun, w.dHin);
+      // message of vj was part of this and every later aggregate of node vi
+      RowMap rs{B, B, nullptr, vj * B};
+      MsgBwd mb{rs, w.Pg, w.Pm, W[P_G_B], adj, w.dHrun, 0, w.dPg, w.dPm, w.dgb, 1, vi, vi, 1};
+      msg_bwd(st, mb);
+      // edge head of this step read the PREVIOUS Hi (step t-1, or P2 when vj = vi-1)
+      const float* Hi_prev = (vj == vi - 1) ? w.Hi_p2[vi] : w.Hi[t - 1];
+      linear_wgrad(st, B, 2, 4 * H, w.dl2[t], 2, w.E1[t], 4 * H, G[P_E_W2], 4 * H);
+      colsum_accum(st, B, 2, w.dl2[t], 2, G[P_E_B2]);
+      relu_head_bwd(st, B, 4 * H, 2, w.E1[t], w.dl2[t], 2, W[P_E_W2], w.dE1, w.dQ + (size_t)vj * B * 4 * H);
+      linear_wgrad(st, B, 4 * H, H, w.dE1, 4 * H, Hi_prev, H, G[P_E_W0], 2 * H);
+      linear_dgrad(st, B, 4 * H, H, w.dE1, 4 * H, W[P_E_W0], 2 * H, w.dHi, H, ACC_STORE);
+    }
+    // dHi now holds the gradient of Hi_p2.  P2 and P1 share Hc0.
+    looper_bwd(st, W, G, B, vi, rm, w.dHi, w.g_p2[vi], w.Hc0[vi], S_SELF, adj, Xi, w, w.dHc0, false);
+    // self-loop head consumed Hi_p1
+    linear_wgrad(st, B, 1, 2 * H, w.dls[vi], 1, w.ES1[vi], 2 * H, G[P_ES_W2], 2 * H);
+    colsum_accum(st, B, 1, w.dls[vi], 1, G[P_ES_B2]);
+    relu_head_bwd(st, B, 2 * H, 1, w.ES1[vi], w.dls[vi], 1, W[P_ES_W2], w.dES1, nullptr);
+    linear_wgrad(st, B, 2 * H, H, w.dES1, 2 * H, w.Hi_p1[vi], H, G[P_ES_W0], H);
+    colsum_accum(st, B, 2 * H, w.dES1, 2 * H, G[P_ES_B0]);
+    linear_dgrad(st, B, 2 * H, H, w.dES1, 2 * H, W[P_ES_W0], H, w.dHi, H, ACC_STORE);
+    looper_bwd(st, W, G, B, vi, rm, w.dHi, w.g_p1[vi], w.Hc0[vi], S_ZERO, adj, Xi, w, w.dHc0, true);
+    // combiner with H_in = 0: only input weights / biases receive gradient
+    CellBwd c0{rm, w.dHc0, 0, w.g_c0[vi], 0, nullptr, 0, w.dgx, nullptr, w.dgh, nullptr, S_ONE, adj};
+    cell_bwd(st, c0);
+    linear_wgrad(st, B, G3, SX, w.dgx, G3, Xi, XP, G[P_CD_WIH], SX);
+    colsum_accum(st, B, G3, w.dgh, G3, G[P_CD_BHH]);
+    colsum_accum(st, B, G3, w.dgx, G3, G[P_CD_BIH]);
+    // parameter head of node vi read h_{vi-1}
+    float* dprev = w.dHd + (size_t)(vi - 1) * bH;
+    const float* hprev = w.Hd + (size_t)(vi - 1) * bH;
+    mlp3_bwd(st, W, G, B, P_X_W0, hprev, SX, w.A1[vi], w.A2[vi], w.dL[vi], w, dprev);
+    // every consumer of node vi-1 is done: fold its projection gradients into dh_{vi-1}
+    const int j = vi - 1;
+    const float* dPg = w.dPg + (size_t)j * B * 2 * H; const float* dPm = w.dPm + (size_t)j * B * 2 * H;
+    const float* dQ = w.dQ + (size_t)j * B * 4 * H;
+    linear_dgrad(st, B, 2 * H, H, dPg, 2 * H, W[P_G_W], H, dprev, H, ACC_ADD);
+    linear_dgrad(st, B, 2 * H, H, dPm, 2 * H, W[P_M_W], H, dprev, H, ACC_ADD);
+    linear_dgrad(st, B, 4 * H, H, dQ, 4 * H, W[P_E_W0] + H, 2 * H, dprev, H, ACC_ADD);
+    linear_wgrad(st, B, 2 * H, H, dPg, 2 * H, hprev, H, G[P_G_W], H);
+    linear_wgrad(st, B, 2 * H, H, dPm, 2 * H, hprev, H, G[P_M_W], H);
+    linear_wgrad(st, B, 4 * H, H, dQ, 4 * H, hprev, H, G[P_E_W0] + H, 2 * H);
+    colsum_accum(st, B, 4 * H, dQ, 4 * H, G[P_E_B0]);
+    colsum_accum(st, B, H, w.dgb + (size_t)j * bH, H, G[P_G_B]);
+    t_end = t0;
+  }
+  // root cell: h_0 = GRU_root(x0, H_init)
+  {
+    RowMap rm{B, B, nullptr, 0};
+    CellBwd cr{rm, w.dHd, 0, w.g_root, 0, w.Hinit, 0, w.dgx, nullptr, w.dgh, w.dHinit, S_ONE, adj};
+    cell_bwd(st, cr);
+    linear_dgrad(st, B, G3, H, w.dgh, G3, W[P_RD_WHH], H, w.dHinit, H, ACC_ADD);
+    linear_wgrad(st, B, G3, H, w.dgh, G3, w.Hinit, H, G[P_RD_WHH], H);
+    linear_wgrad(st, B, G3, SX0, w.dgx, G3, bt.Xn, XP, G[P_RD_WIH], SX0);
+    colsum_accum(st, B, G3, w.dgh, G3, G[P_RD_BHH]);
+    colsum_accum(st, B, G3, w.dgx, G3, G[P_RD_BIH]);
+  }
+  mlp3_bwd(st, W, G, B, P_X0_W0, w.Hinit, SX0 + 32, w.A1[0], w.A2[0], w.dL[0], w, w.dHinit);
+  tanh_bwd(st, (int64_t)bH, w.dHinit, w.Hinit);
+  linear_wgrad(st, B, H, Z, w.dHinit, H, z, Z, G[P_ZH_W], Z);
+  colsum_accum(st, B, H, w.dHinit, H, G[P_ZH_B]);
+  linear_dgrad(st, B, H, Z, w.dHinit, H, W[P_ZH_W], Z, w.dz, Z, ACC_STORE);
+  (void)lw;
+}
+
+}  // namespace dx

@@ -1,0 +1,96 @@
+// Host-side orchestration of the hot path (internal API behind the C ABI).
+#pragma once
+#include "dx_gemm.h"
+#include "dx_kernels.h"
+
+namespace dx {
+
+struct Weights {  // pointers into the flat blob (weights or gradients: same layout)
+  float* p[P_COUNT];
+  explicit Weights(const float* blob) {
+    const Offsets& o = offsets();
+    for (int k = 0; k < P_COUNT; ++k) p[k] = const_cast<float*>(blob) + o.o[k];
+  }
+  float* operator[](int k) const { return p[k]; }
+};
+
+struct Batch {       // what the batcher produces (device pointers except level_ptr)
+  int64_t B;
+  const float* Xn;   // (7,B,32)
+  const int32_t* cls;  // (14,B)   (may be null for encode-only)
+  const uint64_t* adj;  // (B)
+  int n_levels;
+  const int32_t* level_ptr;   // HOST, n_levels+1
+  const int32_t* level_rows;  // device, 6B
+};
+
+struct LossW { float w_env, w_frq, w_kld, inv_batch; };
+
+
+// ---- workspaces (carved from the caller's buffer; see DESIGN.md "HBM layout") ------------
+struct EncWs {
+  float *Hin, *Hc, *Hv, *gc, *gl, *Pg, *Pm, *gxc, *gxl, *gh;
+  float *dH, *dHin, *dPg, *dPm, *dgb, *dgx, *dgxs, *dgh, *dHc, *dsraw;
+};
+constexpr int LD_L = 64;  // leading dimension of logit buffers (55 / 27 columns used)
+constexpr int NSTEP = 21;
+
+struct DecWs {
+  float *z, *Hinit, *Hd, *Pg, *Pm, *Q, *g_root;
+  float *A1[7], *A2[7], *L[7], *dL[7];
+  float *gxc[7], *gxl[7], *Hc0[7], *g_c0[7], *g_p1[7], *Hi_p1[7], *g_p2[7], *Hi_p2[7], *ES1[7], *ls[7], *dls[7];
+  float *E1[NSTEP], *l2[NSTEP], *dl2[NSTEP], *Hin[NSTEP], *g_c[NSTEP], *Hc[NSTEP], *g_l[NSTEP], *Hi[NSTEP];
+  float *gh, *ghl0, *Hrun, *rowloss;
+  // greedy only
+  float *Xd, *Pn;
+  // backward temporaries
+  float *dHd, *dPg, *dPm, *dQ, *dgb, *dHi, *dHc, *dHin, *dHrun, *dHc0, *dgx, *dgxs, *dgh, *dE1, *dA1, *dA2, *dES1,
+      *dHinit, *dz;
+};
+
+struct DecIO {
+  bool train;
+  const Batch* bt;        // train: teacher-forcing inputs
+  LossW lw;
+  uint64_t* adj_out;      // greedy: adjacency being built
+  float* margins;         // greedy, optional
+};
+
+EncWs carve_enc(Arena& ar, int64_t B, bool train);
+DecWs carve_dec(Arena& ar, int64_t B, bool train);
+void encode_fwd_impl(dx_stream_t st, const Weights& W, const Batch& bt, const EncWs& w, float* mu, float* sd, bool train);
+void encode_bwd_impl(dx_stream_t st, const Weights& W, const Weights& G, const Batch& bt, const EncWs& w,
+                     const float* dmu, const float* dstd, const float* sd);
+void decode_fwd_impl(dx_stream_t st, const Weights& W, int B, const float* z, const DecWs& w, const DecIO& io);
+void decode_bwd_impl(dx_stream_t st, const Weights& W, const Weights& G, int B, const float* z, const DecWs& w,
+                     const Batch& bt, LossW lw);
+void kld_rows(dx_stream_t st, int B, const float* mu, const float* sd, LossW lw, float* rowloss);
+void latent_bwd(dx_stream_t st, int B, const float* mu, const float* sd, const float* eps, const float* dz, LossW lw,
+                float* dmu, float* dsd);
+void loss_reduce(dx_stream_t st, int B, const float* rowloss, float* out);
+
+size_t workspace_bytes(int op, int64_t B);
+
+int encode_fwd(dx_stream_t st, const float* weights, const Batch& bt, float* mu, float* std_, void* ws, size_t ws_bytes,
+               int keep);
+int elbo_step(dx_stream_t st, const float* weights, const Batch& bt, const float* eps, LossW lw, float* loss5,
+              float* mu_out, float* std_out, float* grads, void* ws, size_t ws_bytes);
+int decode_greedy(dx_stream_t st, const float* weights, int64_t B, const float* z, float* Xg, float* Pg, uint64_t* adj,
+                  float* margins, void* ws, size_t ws_bytes);
+
+// batcher / data-format kernels (dx_data.cu)
+int batch_build_host(int64_t B, const int32_t* edge_ptr, const int8_t* src, const int8_t* dst, uint64_t* adj,
+                     int32_t* indptr, int32_t* indices, uint8_t* eflags, uint8_t* level, int32_t* level_ptr,
+                     int32_t* level_rows, int32_t* n_levels);
+int batch_schedule(dx_stream_t st, int64_t B, const uint64_t* adj, uint8_t* level, int32_t* level_ptr,
+                   int32_t* level_rows, int32_t* level_ptr_host, void* ws, size_t ws_bytes);
+int pack_graphs(dx_stream_t st, int64_t B, const float* Xg, const float* Pg, float* Xn, int32_t* cls);
+int unpack_graphs(dx_stream_t st, int64_t B, const float* Xn, const float* Pn, float* Xg, float* Pg);
+int voices_to_graphs(dx_stream_t st, int64_t B, const uint8_t* voices, float* Xn, int32_t* cls, uint64_t* adj,
+                     float* Xg, float* Pg);
+int pack_syx(dx_stream_t st, int64_t B, const float* Pg, uint8_t* voices);
+int adamw_step(dx_stream_t st, int64_t n, float* w, const float* g, float* m, float* v, float lr, float b1, float b2,
+               float eps, float wd, int64_t step, float gscale);
+int reparameterize(dx_stream_t st, int64_t n, const float* mu, const float* sd, const float* eps, float* z);
+
+}  // namespace dx

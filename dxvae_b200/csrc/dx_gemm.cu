@@ -1,0 +1,340 @@
+// FP32 SIMT GEMM for sm_100a (see dx_gemm.h for the operand forms).
+//
+// Tiling: CTA tile BM x BN x 16, 256 threads as 16x16, each thread a TM x TN register
+// micro-tile split into 4x4 blocks so operand reads from shared memory are 128-bit and
+// conflict-free; global -> register -> shared double buffering with one barrier per
+// k-tile.  Shared tiles are stored reduction-major (As[k][m], Bs[k][n]) whatever the
+// memory form, so forward / dgrad / wgrad share the inner loop.
+// Roofline: FP32 FFMA pipe (148 SMs x 128 lanes x 2 flop x f_SM); operands come from
+// L2 (weights <= 8 MB per product, activations streamed once).
+#include "dx_gemm.h"
+
+namespace dx {
+
+#ifndef DX_EMU
+
+namespace {
+
+constexpr int BK = 16;
+
+__device__ __forceinline__ float apply_act(float v, int act) {
+  if (act == ACT_RELU) return v > 0.f ? v : 0.f;
+  if (act == ACT_TANH) return tanhf(v);
+  if (act == ACT_SOFTPLUS) return softplusf_(v);
+  return v;
+}
+
+// Loads 4 consecutive floats p[0..3]; element c is valid iff c < nvalid.
+__device__ __forceinline__ float4 ld4(const float* p, int nvalid, bool vec) {
+  float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (nvalid >= 4 && vec) {
+    v = __ldg(reinterpret_cast<const float4*>(p));
+  } else {
+    if (nvalid > 0) v.x = __ldg(p);
+    if (nvalid > 1) v.y = __ldg(p + 1);
+    if (nvalid > 2) v.z = __ldg(p + 2);
+    if (nvalid > 3) v.w = __ldg(p + 3);
+  }
+  return v;
+}
+
+template <int BM, int BN, int TM, int TN, bool AKC, bool BKC>
+__global__ void __launch_bounds__(256, (BM >= 128 ? 2 : 3)) k_gemm(const GemmP p, const int k_chunk, const bool vecA, const bool vecB,
+                                              const bool vecC) {
+  static_assert((BM / TM) * (BN / TN) == 256, "256 threads");
+  static_assert(TM % 4 == 0 && TN % 4 == 0, "4x4 sub-blocks");
+  constexpr int LA = BM * BK / 4 / 256;  // float4 loads per thread for the A tile
+  constexpr int LB = BN * BK / 4 / 256;
+  static_assert(LA >= 1 && LB >= 1, "tile too small");
+  __shared__ __align__(16) float As[2][BK][BM + 4];
+  __shared__ __align__(16) float Bs[2][BK][BN + 4];
+
+  const int tid = threadIdx.x;
+  const int tx = tid & 15, ty = tid >> 4;
+  const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+  const int kbeg = blockIdx.z * k_chunk;
+  const int kend = min(p.K, kbeg + k_chunk);
+  if (kbeg >= kend) return;
+
+  // ---- per-thread load coordinates -------------------------------------------------
+  // KC form  : tile element (i, r): thread covers row i, 4 consecutive r.
+  // !KC form : thread covers reduction row r, 4 consecutive i.
+  int a_i[LA], a_r[LA]; const float* a_ptr[LA];
+#pragma unroll
+  for (int l = 0; l < LA; ++l) {
+    const int f = tid + l * 256;
+    if (AKC) {
+      a_i[l] = f % BM; a_r[l] = (f / BM) * 4;
+      const int gi = m0 + a_i[l];
+      const int64_t row = (gi < p.M) ? (p.a_idx ? p.a_idx[gi] : gi) : 0;
+      a_ptr[l] = p.A + row * p.lda;
+    } else {
+      a_i[l] = (f % (BM / 4)) * 4; a_r[l] = f / (BM / 4);
+      a_ptr[l] = p.A;
+    }
+  }
+  int b_j[LB], b_r[LB]; const float* b_ptr[LB];
+#pragma unroll
+  for (int l = 0; l < LB; ++l) {
+    const int f = tid + l * 256;
+    if (BKC) {
+      b_j[l] = f % BN; b_r[l] = (f / BN) * 4;
+      const int gj = n0 + b_j[l];
+      b_ptr[l] = p.B + (int64_t)(gj < p.N ? gj : 0) * p.ldb;
+    } else {
+      b_j[l] = (f % (BN / 4)) * 4; b_r[l] = f / (BN / 4);
+      b_ptr[l] = p.B;
+    }
+  }
+
+  float4 ra[LA], rb[LB];
+  auto gload = [&](int k0) {
+#pragma unroll
+    for (int l = 0; l < LA; ++l) {
+      if (AKC) {
+        const int gi = m0 + a_i[l], gr = k0 + a_r[l];
+        const int nv = (gi < p.M) ? (kend - gr) : 0;
+        ra[l] = ld4(a_ptr[l] + gr, nv, vecA);
+      } else {
+        const int gr = k0 + a_r[l], gi = m0 + a_i[l];
+        int nv = 0; const float* src = p.A;
+        if (gr < kend) {
+          const int64_t row = p.a_idx ? p.a_idx[gr] : gr;
+          src = p.A + row * p.lda + gi; nv = p.M - gi;
+        }
+        ra[l] = ld4(src, nv, vecA);
+      }
+    }
+#pragma unroll
+    for (int l = 0; l < LB; ++l) {
+      if (BKC) {
+        const int gj = n0 + b_j[l], gr = k0 + b_r[l];
+        const int nv = (gj < p.N) ? (kend - gr) : 0;
+        rb[l] = ld4(b_ptr[l] + gr, nv, vecB);
+      } else {
+        const int gr = k0 + b_r[l], gj = n0 + b_j[l];
+        int nv = 0; const float* src = p.B;
+        if (gr < kend) {
+          const int64_t row = p.b_idx ? p.b_idx[gr] : gr;
+          src = p.B + row * p.ldb + gj; nv = p.N - gj;
+        }
+        rb[l] = ld4(src, nv, vecB);
+      }
+    }
+  };
+  auto sstore = [&](int buf) {
+#pragma unroll
+    for (int l = 0; l < LA; ++l) {
+      if (AKC) {
+        As[buf][a_r[l] + 0][a_i[l]] = ra[l].x; As[buf][a_r[l] + 1][a_i[l]] = ra[l].y;
+        As[buf][a_r[l] + 2][a_i[l]] = ra[l].z; As[buf][a_r[l] + 3][a_i[l]] = ra[l].w;
+      } else {
+        *reinterpret_cast<float4*>(&As[buf][a_r[l]][a_i[l]]) = ra[l];
+      }
+    }
+#pragma unroll
+    for (int l = 0; l < LB; ++l) {
+      if (BKC) {
+        Bs[buf][b_r[l] + 0][b_j[l]] = rb[l].x; Bs[buf][b_r[l] + 1][b_j[l]] = rb[l].y;
+        Bs[buf][b_r[l] + 2][b_j[l]] = rb[l].z; Bs[buf][b_r[l] + 3][b_j[l]] = rb[l].w;
+      } else {
+        *reinterpret_cast<float4*>(&Bs[buf][b_r[l]][b_j[l]]) = rb[l];
+      }
+    }
+  };
+
+  float acc[TM][TN];
+#pragma unroll
+  for (int i = 0; i < TM; ++i)
+#pragma unroll
+    for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
+
+  constexpr int GM = TM / 4, GN = TN / 4;        // 4-wide groups per thread
+  constexpr int SM_ = BM / GM, SN_ = BN / GN;    // group stride inside the tile
+
+  gload(kbeg);
+  sstore(0);
+  __syncthreads();
+  int buf = 0;
+  for (int k0 = kbeg; k0 < kend; k0 += BK) {
+    const bool more = (k0 + BK) < kend;
+    if (more) gload(k0 + BK);
+#pragma unroll
+    for (int kk = 0; kk < BK; ++kk) {
+      float a[TM], b[TN];
+#pragma unroll
+      for (int g = 0; g < GM; ++g) {
+        const float4 v = *reinterpret_cast<const float4*>(&As[buf][kk][g * SM_ + ty * 4]);
+        a[g * 4 + 0] = v.x; a[g * 4 + 1] = v.y; a[g * 4 + 2] = v.z; a[g * 4 + 3] = v.w;
+      }
+#pragma unroll
+      for (int g = 0; g < GN; ++g) {
+        const float4 v = *reinterpret_cast<const float4*>(&Bs[buf][kk][g * SN_ + tx * 4]);
+        b[g * 4 + 0] = v.x; b[g * 4 + 1] = v.y; b[g * 4 + 2] = v.z; b[g * 4 + 3] = v.w;
+      }
+#pragma unroll
+      for (int i = 0; i < TM; ++i)
+#pragma unroll
+        for (int j = 0; j < TN; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    }
+    if (more) {
+      sstore(buf ^ 1);
+      __syncthreads();
+      buf ^= 1;
+    }
+  }
+
+  // ---- epilogue ----------------------------------------------------------------------
+#pragma unroll
+  for (int i = 0; i < TM; ++i) {
+    const int gi = m0 + (i / 4) * SM_ + ty * 4 + (i % 4);
+    if (gi >= p.M) continue;
+    const int64_t crow = p.c_idx ? p.c_idx[gi] : gi;
+    float* crow_p = p.C + crow * p.ldc;
+    const float* arow_p = p.add ? p.add + (int64_t)gi * p.ldadd : nullptr;
+#pragma unroll
+    for (int g = 0; g < GN; ++g) {
+      const int gj = n0 + g * SN_ + tx * 4;
+      if (gj >= p.N) continue;
+      float v[4];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        float t = acc[i][g * 4 + c];
+        if (gj + c < p.N) {
+          if (p.bias) t += __ldg(p.bias + gj + c);
+          if (arow_p) t += __ldg(arow_p + gj + c);
+          t = apply_act(t, p.act);
+        }
+        v[c] = t;
+      }
+      if (p.accum == ACC_ATOMIC) {
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+          if (gj + c < p.N) atomicAdd(crow_p + gj + c, v[c]);
+      } else if (vecC && gj + 3 < p.N) {
+        float4* dst = reinterpret_cast<float4*>(crow_p + gj);
+        float4 o = make_float4(v[0], v[1], v[2], v[3]);
+        if (p.accum == ACC_ADD) { const float4 old = *dst; o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w; }
+        *dst = o;
+      } else {
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+          if (gj + c < p.N) {
+            if (p.accum == ACC_ADD) crow_p[gj + c] += v[c]; else crow_p[gj + c] = v[c];
+          }
+      }
+    }
+  }
+}
+
+inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+template <int BM, int BN, int TM, int TN>
+void launch_tile(dx_stream_t s, const GemmP& p) {
+  const int gm = (p.M + BM - 1) / BM, gn = (p.N + BN - 1) / BN;
+  int splits = 1;
+  if (p.accum == ACC_ATOMIC) {
+    const int tiles = gm * gn;
+    const int want = (148 * 4 + tiles - 1) / tiles;          // ~2 waves of 2 CTAs/SM
+    const int maxs = (p.K + BK * 8 - 1) / (BK * 8);           // >= 128 reduction rows per split
+    splits = want < 1 ? 1 : (want > maxs ? maxs : want);
+    if (splits < 1) splits = 1;
+  }
+  int k_chunk = (p.K + splits - 1) / splits;
+  k_chunk = (k_chunk + BK - 1) / BK * BK;
+  splits = (p.K + k_chunk - 1) / k_chunk;
+  const bool vecA = aligned16(p.A) && (p.lda % 4 == 0);
+  const bool vecB = aligned16(p.B) && (p.ldb % 4 == 0);
+  const bool vecC = aligned16(p.C) && (p.ldc % 4 == 0);
+  dim3 grid(gn, gm, splits);
+  if (p.a_kc && p.b_kc) k_gemm<BM, BN, TM, TN, true, true><<<grid, 256, 0, s>>>(p, k_chunk, vecA, vecB, vecC);
+  else if (p.a_kc && !p.b_kc) k_gemm<BM, BN, TM, TN, true, false><<<grid, 256, 0, s>>>(p, k_chunk, vecA, vecB, vecC);
+  else if (!p.a_kc && !p.b_kc) k_gemm<BM, BN, TM, TN, false, false><<<grid, 256, 0, s>>>(p, k_chunk, vecA, vecB, vecC);
+  else k_gemm<BM, BN, TM, TN, false, true><<<grid, 256, 0, s>>>(p, k_chunk, vecA, vecB, vecC);
+  ++g_launches;
+}
+
+__global__ void __launch_bounds__(256) k_colsum(int M, int N, const float* __restrict__ dy, int64_t ld,
+                                                float* __restrict__ db, const int* __restrict__ idx, int rows_per) {
+  // block (x: 64 columns as 64 threads) x (4 row lanes); grid.y splits the rows
+  __shared__ float red[4][64];
+  const int c = blockIdx.x * 64 + (threadIdx.x & 63);
+  const int lane_r = threadIdx.x >> 6;
+  const int r0 = blockIdx.y * rows_per, r1 = min(M, r0 + rows_per);
+  float s = 0.f;
+  if (c < N)
+    for (int r = r0 + lane_r; r < r1; r += 4) {
+      const int64_t row = idx ? idx[r] : r;
+      s += __ldg(dy + row * ld + c);
+    }
+  red[lane_r][threadIdx.x & 63] = s;
+  __syncthreads();
+  if (lane_r == 0 && c < N) {
+    s = red[0][threadIdx.x] + red[1][threadIdx.x] + red[2][threadIdx.x] + red[3][threadIdx.x];
+    atomicAdd(db + c, s);
+  }
+}
+
+}  // namespace
+
+void gemm(dx_stream_t s, const GemmP& p) {
+  if (p.M <= 0 || p.N <= 0 || p.K <= 0) return;
+  // Large tile when both output extents fill it; otherwise 64x64 so small batches
+  // (B=128) and narrow heads (N=27/55/2/1) still spread over the SMs.
+  const bool big = (p.M >= 512 && p.N >= 96);
+  if (big) launch_tile<128, 128, 8, 8>(s, p);
+  else launch_tile<64, 64, 4, 4>(s, p);
+}
+
+void colsum_accum(dx_stream_t s, int M, int N, const float* dy, int64_t lddy, float* db, const int* dy_idx) {
+  if (M <= 0 || N <= 0) return;
+  const int gx = (N + 63) / 64;
+  int gy = (148 * 8 + gx - 1) / gx;
+  const int maxy = (M + 63) / 64;
+  if (gy > maxy) gy = maxy;
+  if (gy < 1) gy = 1;
+  const int rows_per = (M + gy - 1) / gy;
+  gy = (M + rows_per - 1) / rows_per;
+  k_colsum<<<dim3(gx, gy), 256, 0, s>>>(M, N, dy, lddy, db, dy_idx, rows_per);
+  ++g_launches;
+}
+
+#else  // ------------------------------ DX_EMU: naive host loops (tests only) ----------
+
+void gemm(dx_stream_t, const GemmP& p) {
+  for (int i = 0; i < p.M; ++i) {
+    const int64_t crow = p.c_idx ? p.c_idx[i] : i;
+    for (int j = 0; j < p.N; ++j) {
+      float acc = 0.f;
+      for (int r = 0; r < p.K; ++r) {
+        float a, b;
+        if (p.a_kc) a = p.A[(int64_t)(p.a_idx ? p.a_idx[i] : i) * p.lda + r];
+        else a = p.A[(int64_t)(p.a_idx ? p.a_idx[r] : r) * p.lda + i];
+        if (p.b_kc) b = p.B[(int64_t)j * p.ldb + r];
+        else b = p.B[(int64_t)(p.b_idx ? p.b_idx[r] : r) * p.ldb + j];
+        acc = fmaf(a, b, acc);
+      }
+      if (p.bias) acc += p.bias[j];
+      if (p.add) acc += p.add[(int64_t)i * p.ldadd + j];
+      if (p.act == ACT_RELU) acc = acc > 0.f ? acc : 0.f;
+      else if (p.act == ACT_TANH) acc = tanhf(acc);
+      else if (p.act == ACT_SOFTPLUS) acc = softplusf_(acc);
+      float* dst = p.C + crow * p.ldc + j;
+      if (p.accum == ACC_STORE) *dst = acc; else *dst += acc;
+    }
+  }
+  ++g_launches;
+}
+
+void colsum_accum(dx_stream_t, int M, int N, const float* dy, int64_t lddy, float* db, const int* dy_idx) {
+  for (int j = 0; j < N; ++j) {
+    float s = 0.f;
+    for (int r = 0; r < M; ++r) s += dy[(int64_t)(dy_idx ? dy_idx[r] : r) * lddy + j];
+    db[j] += s;
+  }
+  ++g_launches;
+}
+
+#endif
+
+}  // namespace dx

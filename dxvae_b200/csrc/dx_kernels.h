@@ -1,0 +1,245 @@
+// Element-wise kernels of the hot path: GRU cell (fwd/bwd), gated-sum message
+// aggregation with feedback-edge handling (fwd/bwd), loss heads, quantisers.
+// Every kernel is a per-element functor launched through dx::foreach, so the same
+// code runs on the GPU (grid-stride, 128-bit loads, coalesced along the hidden
+// dimension) and, in tests/emu builds, serially on the CPU.
+//
+// Row addressing.  Node-major buffers hold one row per (node v, graph b):
+// global row r = v*B + b.  A launch covers M rows; compact index m in [0,M):
+//     r = rows ? rows[m] : row_base + m ;  b = r % B ;  v = r / B
+// Buffers flagged "global" are indexed by r, the others by m.
+#pragma once
+#include "dx_rt.h"
+
+namespace dx {
+
+DX_HD DX_INLINE int abit(uint64_t a, int s, int d) { return (int)((a >> (s * 7 + d)) & 1ull); }
+DX_HD DX_INLINE float4 ld4f(const float* p) { return *reinterpret_cast<const float4*>(p); }
+DX_HD DX_INLINE void st4f(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
+DX_HD DX_INLINE float4 f4zero() { return make_float4(0.f, 0.f, 0.f, 0.f); }
+
+struct RowMap {
+  int M; int B; const int* rows; int row_base;
+  DX_HD DX_INLINE int r(int m) const { return rows ? rows[m] : row_base + m; }
+};
+
+enum { S_ONE = 0, S_ZERO = 1, S_SELF = 2 };  // x multiplier of the GRU input: 1, 0, or the node's self-loop flag
+
+// ------------------------------------------------------------------------------------
+// GRU cell forward (torch.nn.GRUCell, gate order r,z,n — model.py:186,192,193)
+//   gx, gh: raw products x W_ih^T and h W_hh^T (no bias), compact [M,1536]; gh==NULL means h=0
+//   r = sig((s*gx_r+b_ir)+(gh_r+b_hr)); z likewise; n = tanh((s*gx_n+b_in) + r*(gh_n+b_hn))
+//   h' = (1-z)*n + z*h
+// gates (optional) receives r,z,n,nh=(gh_n+b_hn) as [.,2048] for the backward pass.
+// ------------------------------------------------------------------------------------
+struct CellFwd {
+  RowMap rm; const float* gx; const float* gh; const float* bih; const float* bhh;
+  const float* hprev; int hprev_global; float* hout; int hout_global; float* gates; int gates_global;
+  int smode; const uint64_t* adj;
+};
+
+inline void cell_fwd(dx_stream_t st, const CellFwd& a) {
+  foreach (st, (int64_t)a.rm.M * (H / 4), [=] DX_HD(int64_t idx) {
+    const int m = (int)(idx / (H / 4)), n = (int)(idx % (H / 4)) * 4;
+    const int r = a.rm.r(m);
+    float s = 1.f;
+    if (a.smode == S_ZERO) s = 0.f;
+    else if (a.smode == S_SELF) { const int b = r % a.rm.B, v = r / a.rm.B; s = (float)abit(a.adj[b], v, v); }
+    const float* gx = a.gx + (int64_t)m * G3 + n;
+    const float4 xr = ld4f(gx), xz = ld4f(gx + H), xn = ld4f(gx + 2 * H);
+    float4 hr = f4zero(), hz = f4zero(), hn = f4zero(), hp = f4zero();
+    if (a.gh) { const float* gh = a.gh + (int64_t)m * G3 + n; hr = ld4f(gh); hz = ld4f(gh + H); hn = ld4f(gh + 2 * H); }
+    if (a.hprev) hp = ld4f(a.hprev + (int64_t)(a.hprev_global ? r : m) * H + n);
+    const float4 bir = ld4f(a.bih + n), biz = ld4f(a.bih + H + n), bin = ld4f(a.bih + 2 * H + n);
+    const float4 bhr = ld4f(a.bhh + n), bhz = ld4f(a.bhh + H + n), bhn = ld4f(a.bhh + 2 * H + n);
+    float4 R, Zg, Ng, NH, O;
+#define DX_CELL(c)                                                      \
+    {                                                                   \
+      const float rr = sigmoidf_((s * xr.c + bir.c) + (hr.c + bhr.c));  \
+      const float zz = sigmoidf_((s * xz.c + biz.c) + (hz.c + bhz.c));  \
+      const float nh = hn.c + bhn.c;                                    \
+      const float nn = tanhf((s * xn.c + bin.c) + rr * nh);             \
+      R.c = rr; Zg.c = zz; Ng.c = nn; NH.c = nh;                        \
+      O.c = (1.f - zz) * nn + zz * hp.c;                                \
+    }
+    DX_CELL(x) DX_CELL(y) DX_CELL(z) DX_CELL(w)
+#undef DX_CELL
+    st4f(a.hout + (int64_t)(a.hout_global ? r : m) * H + n, O);
+    if (a.gates) {
+      float* g = a.gates + (int64_t)(a.gates_global ? r : m) * (4 * H) + n;
+      st4f(g, R); st4f(g + H, Zg); st4f(g + 2 * H, Ng); st4f(g + 3 * H, NH);
+    }
+  });
+}
+
+// GRU cell backward.  dh: gradient of h' ; outputs (compact [M,.]):
+//   dgx  = [da_r, da_z, da_n]          (bias_ih gradient = column sums)
+//   dgxs = s * dgx  (optional)         (weight_ih gradient uses the masked form)
+//   dgh  = [da_r, da_z, da_n * r]      (bias_hh / weight_hh gradient, and dh_prev += dgh W_hh)
+//   dhp  = dh * z                      (direct path to h_prev)
+struct CellBwd {
+  RowMap rm; const float* dh; int dh_global; const float* gates; int gates_global; const float* hprev;
+  int hprev_global; float* dgx; float* dgxs; float* dgh; float* dhp; int smode; const uint64_t* adj;
+  int dhp_global = 0;
+};
+
+inline void cell_bwd(dx_stream_t st, const CellBwd& a) {
+  foreach (st, (int64_t)a.rm.M * (H / 4), [=] DX_HD(int64_t idx) {
+    const int m = (int)(idx / (H / 4)), n = (int)(idx % (H / 4)) * 4;
+    const int r = a.rm.r(m);
+    float s = 1.f;
+    if (a.smode == S_ZERO) s = 0.f;
+    else if (a.smode == S_SELF) { const int b = r % a.rm.B, v = r / a.rm.B; s = (float)abit(a.adj[b], v, v); }
+    const float4 d = ld4f(a.dh + (int64_t)(a.dh_global ? r : m) * H + n);
+    const float* g = a.gates + (int64_t)(a.gates_global ? r : m) * (4 * H) + n;
+    const float4 R = ld4f(g), Zg = ld4f(g + H), Ng = ld4f(g + 2 * H), NH = ld4f(g + 3 * H);
+    float4 hp = f4zero();
+    if (a.hprev) hp = ld4f(a.hprev + (int64_t)(a.hprev_global ? r : m) * H + n);
+    float4 ar, az, an, anr, dp;
+#define DX_CELLB(c)                                            \
+    {                                                          \
+      const float dn = d.c * (1.f - Zg.c);                     \
+      const float dz = d.c * (hp.c - Ng.c);                    \
+      const float dan = dn * (1.f - Ng.c * Ng.c);              \
+      const float dr = dan * NH.c;                             \
+      ar.c = dr * R.c * (1.f - R.c);                           \
+      az.c = dz * Zg.c * (1.f - Zg.c);                         \
+      an.c = dan; anr.c = dan * R.c; dp.c = d.c * Zg.c;        \
+    }
+    DX_CELLB(x) DX_CELLB(y) DX_CELLB(z) DX_CELLB(w)
+#undef DX_CELLB
+    float* o = a.dgx + (int64_t)m * G3 + n;
+    st4f(o, ar); st4f(o + H, az); st4f(o + 2 * H, an);
+    if (a.dgxs) {
+      float* os = a.dgxs + (int64_t)m * G3 + n;
+      st4f(os, make_float4(s * ar.x, s * ar.y, s * ar.z, s * ar.w));
+      st4f(os + H, make_float4(s * az.x, s * az.y, s * az.z, s * az.w));
+      st4f(os + 2 * H, make_float4(s * an.x, s * an.y, s * an.z, s * an.w));
+    }
+    float* oh = a.dgh + (int64_t)m * G3 + n;
+    st4f(oh, ar); st4f(oh + H, az); st4f(oh + 2 * H, anr);
+    if (a.dhp) st4f(a.dhp + (int64_t)(a.dhp_global ? r : m) * H + n, dp);
+  });
+}
+
+// ------------------------------------------------------------------------------------
+// Gated-sum neighbour aggregation (model.py:163-181) on pre-projected neighbour states.
+//   Pg[x-row, 2n..2n+1] = (W_g[n,:512] h_x, W_g[n,512:] h_x)   ("in" half, "out" half)
+//   Pm likewise for the bias-free mapper.
+//   message x->v:  i=[x->v], o=[v->x] ;  m = sig(i*Pg_in + o*Pg_out + b_g) * (i*Pm_in + o*Pm_out)
+//   (i=o=0 gives exactly 0 in the reference because the mapper has no bias: skipped.)
+// Forward: target rows (RowMap), neighbours x = x_lo..x_hi in steps of +1 (encode: v+1..6,
+// decode step: x_lo=x_hi=vj).  x_lo<0 means "v+1".  accum=1 adds to the existing Hin.
+// P buffers are global-row ([7B,1024]); hin is global (hin_global) or compact.
+// ------------------------------------------------------------------------------------
+struct MsgFwd {
+  RowMap rm; const float* Pg; const float* Pm; const float* bg; const uint64_t* adj; float* hin; int hin_global;
+  int x_lo, x_hi; int accum;
+};
+
+inline void msg_fwd(dx_stream_t st, const MsgFwd& a) {
+  foreach (st, (int64_t)a.rm.M * (H / 2), [=] DX_HD(int64_t idx) {
+    const int m = (int)(idx / (H / 2)), n = (int)(idx % (H / 2)) * 2;
+    const int r = a.rm.r(m);
+    const int b = r % a.rm.B, v = r / a.rm.B;
+    const uint64_t A = a.adj[b];
+    float* out = a.hin + (int64_t)(a.hin_global ? r : m) * H + n;
+    float acc0 = a.accum ? out[0] : 0.f, acc1 = a.accum ? out[1] : 0.f;
+    const int lo = a.x_lo < 0 ? v + 1 : a.x_lo, hi = a.x_lo < 0 ? NN - 1 : a.x_hi;
+    const float bg0 = a.bg[n], bg1 = a.bg[n + 1];
+    for (int x = lo; x <= hi; ++x) {
+      const float fi = (float)abit(A, x, v), fo = (float)abit(A, v, x);
+      if (fi == 0.f && fo == 0.f) continue;
+      const int64_t xr = (int64_t)x * a.rm.B + b;
+      const float4 g = ld4f(a.Pg + xr * (2 * H) + 2 * n);
+      const float4 p = ld4f(a.Pm + xr * (2 * H) + 2 * n);
+      acc0 += sigmoidf_((fi * g.x + fo * g.y) + bg0) * (fi * p.x + fo * p.y);
+      acc1 += sigmoidf_((fi * g.z + fo * g.w) + bg1) * (fi * p.z + fo * p.w);
+    }
+    out[0] = acc0; out[1] = acc1;
+  });
+}
+
+// Backward, from the SOURCE row's perspective (no atomics, deterministic):
+// source rows (RowMap) x; targets v = v_lo..v_hi (encode: 0..x-1 when v_lo<0).
+// dhin row of target v: (v*dh_vstride + b).  Writes/accumulates dPg, dPm ([.,1024]) and the
+// gate-bias row gradient dgb ([.,512]) at the source row (global r or compact m).
+struct MsgBwd {
+  RowMap rm; const float* Pg; const float* Pm; const float* bg; const uint64_t* adj; const float* dhin;
+  int64_t dh_vstride; float* dPg; float* dPm; float* dgb; int out_global; int v_lo, v_hi; int accum;
+};
+
+inline void msg_bwd(dx_stream_t st, const MsgBwd& a) {
+  foreach (st, (int64_t)a.rm.M * (H / 2), [=] DX_HD(int64_t idx) {
+    const int m = (int)(idx / (H / 2)), n = (int)(idx % (H / 2)) * 2;
+    const int r = a.rm.r(m);
+    const int b = r % a.rm.B, x = r / a.rm.B;
+    const uint64_t A = a.adj[b];
+    const int64_t o = a.out_global ? r : m;
+    float4 dg = f4zero(), dp = f4zero(); float db0 = 0.f, db1 = 0.f;
+    if (a.accum) { dg = ld4f(a.dPg + o * (2 * H) + 2 * n); dp = ld4f(a.dPm + o * (2 * H) + 2 * n);
+                   db0 = a.dgb[o * H + n]; db1 = a.dgb[o * H + n + 1]; }
+    const int lo = a.v_lo < 0 ? 0 : a.v_lo, hi = a.v_lo < 0 ? x - 1 : a.v_hi;
+    const float4 g = ld4f(a.Pg + (int64_t)r * (2 * H) + 2 * n);
+    const float4 p = ld4f(a.Pm + (int64_t)r * (2 * H) + 2 * n);
+    const float bg0 = a.bg[n], bg1 = a.bg[n + 1];
+    for (int v = lo; v <= hi; ++v) {
+      const float fi = (float)abit(A, x, v), fo = (float)abit(A, v, x);
+      if (fi == 0.f && fo == 0.f) continue;
+      const float* dh = a.dhin + ((int64_t)v * a.dh_vstride + b) * H + n;
+      const float s0 = sigmoidf_((fi * g.x + fo * g.y) + bg0), c0 = fi * p.x + fo * p.y;
+      const float s1 = sigmoidf_((fi * g.z + fo * g.w) + bg1), c1 = fi * p.z + fo * p.w;
+      const float da0 = dh[0] * c0 * s0 * (1.f - s0), dc0 = dh[0] * s0;
+      const float da1 = dh[1] * c1 * s1 * (1.f - s1), dc1 = dh[1] * s1;
+      dg.x += fi * da0; dg.y += fo * da0; dg.z += fi * da1; dg.w += fo * da1;
+      dp.x += fi * dc0; dp.y += fo * dc0; dp.z += fi * dc1; dp.w += fo * dc1;
+      db0 += da0; db1 += da1;
+    }
+    st4f(a.dPg + o * (2 * H) + 2 * n, dg); st4f(a.dPm + o * (2 * H) + 2 * n, dp);
+    a.dgb[o * H + n] = db0; a.dgb[o * H + n + 1] = db1;
+  });
+}
+
+// ------------------------------------------------------------------------------------
+// small generic element-wise helpers
+// ------------------------------------------------------------------------------------
+// y[i] (+)= x[i]
+inline void add_inplace(dx_stream_t st, int64_t n4, float* y, const float* x) {
+  foreach (st, n4, [=] DX_HD(int64_t i) {
+    float4 a = ld4f(y + 4 * i); const float4 b = ld4f(x + 4 * i);
+    a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w; st4f(y + 4 * i, a);
+  });
+}
+// dpre[m,j] = (act[m,j] > 0) * sum_c dl[m,c] * W2[c,j]   (backward of  l = relu-act . W2^T, C = 1 or 2 outputs)
+// optionally also acc[m,j] += dpre[m,j]
+inline void relu_head_bwd(dx_stream_t st, int M, int N, int C, const float* act, const float* dl, int lddl,
+                          const float* W2, float* dpre, float* acc) {
+  foreach (st, (int64_t)M * (N / 4), [=] DX_HD(int64_t idx) {
+    const int m = (int)(idx / (N / 4)), j = (int)(idx % (N / 4)) * 4;
+    const float4 a = ld4f(act + (int64_t)m * N + j);
+    float4 g = f4zero();
+    for (int c = 0; c < C; ++c) {
+      const float d = dl[(int64_t)m * lddl + c];
+      const float4 w = ld4f(W2 + (int64_t)c * N + j);
+      g.x += d * w.x; g.y += d * w.y; g.z += d * w.z; g.w += d * w.w;
+    }
+    g.x = a.x > 0.f ? g.x : 0.f; g.y = a.y > 0.f ? g.y : 0.f; g.z = a.z > 0.f ? g.z : 0.f; g.w = a.w > 0.f ? g.w : 0.f;
+    st4f(dpre + (int64_t)m * N + j, g);
+    if (acc) { float4 q = ld4f(acc + (int64_t)m * N + j); q.x += g.x; q.y += g.y; q.z += g.z; q.w += g.w;
+               st4f(acc + (int64_t)m * N + j, q); }
+  });
+}
+// d[m,j] *= (act[m,j] > 0)
+inline void relu_mask(dx_stream_t st, int64_t n4, float* d, const float* act) {
+  foreach (st, n4, [=] DX_HD(int64_t i) {
+    float4 g = ld4f(d + 4 * i); const float4 a = ld4f(act + 4 * i);
+    g.x = a.x > 0.f ? g.x : 0.f; g.y = a.y > 0.f ? g.y : 0.f; g.z = a.z > 0.f ? g.z : 0.f; g.w = a.w > 0.f ? g.w : 0.f;
+    st4f(d + 4 * i, g);
+  });
+}
+// d[i] *= (1 - y[i]^2)      (tanh backward, y = tanh output)
+inline void tanh_bwd(dx_stream_t st, int64_t n, float* d, const float* y) {
+  foreach (st, n, [=] DX_HD(int64_t i) { d[i] *= (1.f - y[i] * y[i]); });
+}
+
+}  // namespace dx

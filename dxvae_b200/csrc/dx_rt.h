@@ -1,0 +1,63 @@
+// Thin runtime layer: element-wise launch, memset, launch counting.
+// GPU build: real kernels.  DX_EMU build (tests only): serial CPU loops.
+#pragma once
+#include "dx_common.h"
+
+namespace dx {
+
+extern long long g_launches;  // kernels launched by this library (bench.py reports it)
+
+#ifndef DX_EMU
+template <class F>
+__global__ void __launch_bounds__(256) k_foreach(F f, int64_t n) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) f(i);
+}
+// Grid sized in whole waves of the 148 SMs (8 resident 256-thread CTAs each).
+template <class F>
+inline void foreach (dx_stream_t s, int64_t n, F f) {
+  if (n <= 0) return;
+  int64_t blocks = (n + 255) / 256;
+  const int64_t cap = 148 * 8;
+  if (blocks > cap) blocks = cap;
+  k_foreach<<<(unsigned)blocks, 256, 0, s>>>(f, n);
+  ++g_launches;
+}
+inline void zero_async(dx_stream_t s, void* p, size_t bytes) {
+  if (bytes) cudaMemsetAsync(p, 0, bytes, s);
+}
+inline void copy_async(dx_stream_t s, void* dst, const void* src, size_t bytes) {
+  if (bytes) cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, s);
+}
+inline int check_launch(const char* what) {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) { set_error("%s: CUDA error %s", what, cudaGetErrorString(e)); return 1; }
+  return 0;
+}
+#else
+template <class F>
+inline void foreach (dx_stream_t, int64_t n, F f) {
+  for (int64_t i = 0; i < n; ++i) f(i);
+  ++g_launches;
+}
+inline void zero_async(dx_stream_t, void* p, size_t bytes) { if (bytes) memset(p, 0, bytes); }
+inline void copy_async(dx_stream_t, void* dst, const void* src, size_t bytes) { if (bytes) memcpy(dst, src, bytes); }
+inline int check_launch(const char*) { return 0; }
+#endif
+
+// ---- math shared by host-emulation and device ------------------------------------
+DX_HD DX_INLINE float sigmoidf_(float x) { return 1.0f / (1.0f + expf(-x)); }
+DX_HD DX_INLINE float softplusf_(float x) { return x > 20.0f ? x : log1pf(expf(x)); }  // nn.Softplus(beta=1, threshold=20)
+
+// ---- bump allocator over the caller's workspace -----------------------------------
+struct Arena {
+  char* base; size_t cap; size_t off; bool overflow;
+  Arena(void* p, size_t bytes) : base((char*)p), cap(bytes), off(0), overflow(false) {}
+  template <class T> T* take(size_t count) {
+    size_t bytes = align_up(count * sizeof(T));
+    if (off + bytes > cap) { overflow = true; off += bytes; return (T*)base; }
+    T* r = (T*)(base + off); off += bytes; return r;
+  }
+};
+
+}  // namespace dx

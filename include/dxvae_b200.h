@@ -1,0 +1,151 @@
+/* dxvae_b200 — C ABI of the B200-native DX-VAE hot path.
+ *
+ * The reference (HotzingTone/DX-VAE) has no FFI of its own: its hot path is the
+ * Python class DXVAE (model.py:10-391) calling stock torch ops on lists of DGL
+ * graphs.  This header is the boundary the new build introduces UNDER that class:
+ * the Python mirror dxvae_b200/model.py binds these entry points with ctypes and
+ * keeps the reference's method surface (encode / reparameterize / decode / loss /
+ * forward / train).  Each entry point cites the reference code it replaces.
+ *
+ * Conventions
+ *   - plain pointers + explicit sizes; every pointer is a DEVICE pointer unless the
+ *     name ends in _host; the caller (torch) owns all buffers, workspace included;
+ *   - `stream` is a cudaStream_t passed as void*; all work is enqueued on it and
+ *     nothing synchronises unless stated;
+ *   - return 0 = ok, non-zero = error; dxvae_last_error() gives the message
+ *     (thread-local).  Nothing throws across the ABI.  No hidden global state.
+ *   - model constants are fixed (7 nodes, X 27, X0 23, H 512, Z 128): kernels are
+ *     specialised on them.
+ *
+ * Layouts (B = graphs in the batch)
+ *   weights  flat fp32 blob, dxvae_param_blob_floats() long; tensor k of the 53
+ *            state_dict tensors (App. E order, model.py:24-72) lives at
+ *            dxvae_param_entry(k).offset, row-major, each offset 64-float aligned.
+ *   Xg       (B,7,27) fp32   graph-major node features  = stack of g.ndata['X']
+ *   Pg       (B,7,21) fp32   graph-major raw parameters = stack of g.ndata['params']
+ *   Xn       (7,B,32) fp32   node-major, zero padded to 32 columns (what kernels read)
+ *   cls      (14,B)  int32   class labels: row0 lfw, row1 alg, rows 2..7 lc(op1..6),
+ *                            rows 8..13 rc(op1..6)            (model.py:307-308,327-328)
+ *   adj      (B)     uint64  bit (src*7+dst) set iff edge src->dst
+ */
+#ifndef DXVAE_B200_H
+#define DXVAE_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DXVAE_ABI_VERSION 1
+#define DXVAE_N_NODES 7
+#define DXVAE_N_PARAMS 21
+#define DXVAE_SIZE_X 27
+#define DXVAE_SIZE_X0 23
+#define DXVAE_SIZE_H 512
+#define DXVAE_SIZE_Z 128
+#define DXVAE_XPAD 32
+#define DXVAE_N_TENSORS 53
+
+int dxvae_abi_version(void);
+const char* dxvae_last_error(void);
+/* number of kernels this library has launched in this process (bench.py's gpu_launches) */
+long long dxvae_launch_count(void);
+
+/* ---- parameter blob (state_dict of model.py:24-72) ------------- */
+typedef struct {
+  const char* name;  /* state_dict key, e.g. "combin_encode.weight_ih" */
+  int64_t offset;    /* in floats, into the flat blob */
+  int32_t rows;      /* 2-D: rows; 1-D: length */
+  int32_t cols;      /* 2-D: cols; 1-D: 0 */
+} dxvae_param_entry_t;
+
+int64_t dxvae_param_blob_floats(void);                 /* padded length of the blob */
+int64_t dxvae_param_count(void);                       /* 12,083,541 real parameters */
+int dxvae_param_entry(int k, dxvae_param_entry_t* out); /* k in [0,53) */
+
+/* ---- batcher (replaces the per-graph DGL queries of model.py:164-177,189-191,
+ *      272-280 and the graph construction of dxdata.py:174-312) ------------------- */
+
+/* Host batcher: COO edge lists -> adjacency masks, CSR by destination over flat node
+ * ids b*7+v (sources ascending), per-edge feedback marks (0 forward src>dst, 1 back
+ * edge src<dst, 2 self-loop), encode level per node and the level schedule (operator
+ * rows v*B+b grouped by level, ascending).  All pointers are HOST pointers.
+ * edge_ptr has B+1 entries; indices/eflags need edge_ptr[B] entries; level_ptr needs 8;
+ * level_rows needs 6*B.  *n_levels receives the number of operator levels. */
+int dxvae_batch_build_host(int64_t B, const int32_t* edge_ptr_host, const int8_t* src_host, const int8_t* dst_host,
+                           uint64_t* adj_host, int32_t* indptr_host, int32_t* indices_host, uint8_t* eflags_host,
+                           uint8_t* level_host, int32_t* level_ptr_host, int32_t* level_rows_host,
+                           int32_t* n_levels);
+
+/* Device level schedule from adjacency masks (same outputs as the host batcher's
+ * level / level_ptr / level_rows).  level_ptr (8 ints) is written on the device AND
+ * copied to level_ptr_host (pinned or pageable) — this call synchronises the stream. */
+int dxvae_batch_schedule(int64_t B, const uint64_t* adj, uint8_t* level, int32_t* level_ptr, int32_t* level_rows,
+                         int32_t* level_ptr_host, void* workspace, size_t workspace_bytes, void* stream);
+
+/* Graph-major reference tensors -> what the kernels read. */
+int dxvae_pack_graphs(int64_t B, const float* Xg, const float* Pg, float* Xn, int32_t* cls, void* stream);
+/* Node-major decode outputs -> graph-major (B,7,27) / (B,7,21). */
+int dxvae_unpack_graphs(int64_t B, const float* Xn, const float* Pn, float* Xg, float* Pg, void* stream);
+
+/* dxdata.py:174-312 (_make_graph) on the device: packed 128-byte DX7 voices ->
+ * Xn, cls, adj (from the 32-entry DX_ALGO table, dxdata.py:140-171) and, when Pg is
+ * non-NULL, the graph-major params (B,7,21). */
+int dxvae_voices_to_graphs(int64_t B, const uint8_t* voices, float* Xn, int32_t* cls, uint64_t* adj, float* Xg,
+                           float* Pg, void* stream);
+/* dxdata.py:341-397 (graph_to_syx): params (B,7,21) fp32 -> B*128 packed voice bytes
+ * (header/name/trailer bytes are added by the host wrapper). */
+int dxvae_pack_syx(int64_t B, const float* Pg, uint8_t* voices, void* stream);
+
+/* ---- workspace sizes ------------------------------------------------------------ */
+enum { DXVAE_OP_ENCODE = 0, DXVAE_OP_DECODE = 1, DXVAE_OP_TRAIN = 2, DXVAE_OP_SCHEDULE = 3 };
+size_t dxvae_workspace_bytes(int op, int64_t B);
+
+/* ---- encode (model.py:200-212; _propagate :151-198 with encode=True) ------------- *
+ * level_ptr_host (n_levels+1 ints, HOST) and level_rows (DEVICE) come from the batcher.
+ * Outputs mu, std (B,128).  With keep=1 the workspace retains what encode_bwd needs
+ * (workspace must then be the DXVAE_OP_TRAIN one). */
+int dxvae_encode_fwd(const float* weights, int64_t B, const float* Xn, const uint64_t* adj, int32_t n_levels,
+                     const int32_t* level_ptr_host, const int32_t* level_rows, float* mu, float* std_,
+                     void* workspace, size_t workspace_bytes, int keep, void* stream);
+
+/* ---- reparameterise (model.py:284, Normal.rsample): z = mu + std*eps -------------- */
+int dxvae_reparameterize(int64_t n, const float* mu, const float* std_, const float* eps, float* z, void* stream);
+
+/* ---- greedy decode (model.py:214-253, quantisers :87-149) ------------------------ *
+ * z (B,128) -> Xg (B,7,27), Pg (B,7,21), adj (B).  logits_out (optional, may be NULL):
+ * (B,34) fp32 decision logits [6 self-loop | 21 x (in,out) ... ] is NOT provided; use
+ * margins (B) = min |logit| over the 48 edge decisions of each graph, for tie-aware
+ * parity checks. */
+int dxvae_decode_greedy(const float* weights, int64_t B, const float* z, float* Xg, float* Pg, uint64_t* adj,
+                        float* margins, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- teacher-forced ELBO (model.py:270-367) + backward (model.py:385) ------------ *
+ * One call = encode_fwd + loss_fwd (+ backward of both when grads != NULL).
+ * eps (B,128) is the injected N(0,1) noise.  loss5 (5 floats, device) receives
+ * (total, loss_X0, loss_Xi, loss_E, kld*w_kld) of model.py:367 over the B graphs
+ * scaled by loss_scale... see below.  `inv_batch` is 1/(global batch): every term is a
+ * batch mean (model.py:303-365), so data-parallel ranks pass 1/(B*world) and sum
+ * loss5 / grads across ranks.  grads: flat blob, same layout as weights, ACCUMULATED
+ * into (caller zeroes it). */
+int dxvae_elbo_step(const float* weights, int64_t B, const float* Xn, const int32_t* cls, const uint64_t* adj,
+                    int32_t n_levels, const int32_t* level_ptr_host, const int32_t* level_rows, const float* eps,
+                    float w_env, float w_frq, float w_kld, float inv_batch, float* loss5, float* mu_out,
+                    float* std_out, float* grads, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- optimiser (model.py:375,386: torch.optim.AdamW defaults) -------------------- */
+int dxvae_adamw_step(int64_t n, float* weights, const float* grads, float* exp_avg, float* exp_avg_sq, float lr,
+                     float beta1, float beta2, float eps, float weight_decay, int64_t step, float grad_scale,
+                     void* stream);
+
+/* ---- low-level pieces exported for unit tests ------------------------------------ *
+ * C[M,N] = act(A[M,K] * W[N,K]^T + bias)  (act: 0 none, 1 relu, 2 tanh, 4 softplus) */
+int dxvae_test_gemm(int variant, int64_t M, int64_t N, int64_t K, const float* A, int64_t lda, const float* Bm,
+                    int64_t ldb, float* C, int64_t ldc, const float* bias, int act, int accumulate, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DXVAE_B200_H */

@@ -1,0 +1,104 @@
+"""Host orchestration + element-wise kernels, executed through the CPU emulation build
+(tests/emu) and compared with the oracle.  No GPU needed: this is what keeps the level
+schedule, buffer carving and the hand-written gradient chain honest in the build
+container.  The GPU parity tests (test_gpu_*.py) repeat the comparisons on the real
+CUDA library."""
+import numpy as np
+import pytest
+import torch
+
+import dxvae_oracle as O
+from dxvae_b200.params import unflatten
+from tests import util
+from tests.emu.emu import Emu
+
+
+@pytest.fixture(scope="module")
+def setup():
+    # back-edge algorithms (3: 4->6, 5: 5->6), 8/9-edge ones (18, 20), depth-5 (0) and flat (31)
+    idx = util.pick_by_alg([3, 5, 18, 20, 0, 31])
+    X, P, E, A = util.dataset_graphs(idx)
+    o = O.make_weights(0, 3.0)
+    return idx, X, P, E, A, o, Emu(o.state_dict())
+
+
+def test_batcher_matches_set_logic(setup):
+    _, X, P, E, A, o, emu = setup
+    for edges in (E, util.random_edge_lists(40, 0.25, 1), util.random_edge_lists(8, 0.0, 2),
+                  util.random_edge_lists(8, 1.0, 3)):
+        bt = emu.batch(None, None, edges)
+        ob = O.batch_oracle(edges)
+        for k in ("adj", "indptr", "indices", "eflags", "level", "level_rows"):
+            assert np.array_equal(bt[k], ob[k]), k
+        n = len(ob["level_ptr"])
+        assert bt["n_levels"] == n - 1
+        assert np.array_equal(bt["level_ptr"][:n], ob["level_ptr"])
+
+
+def test_encode_matches_oracle(setup):
+    _, X, P, E, A, o, emu = setup
+    mu, sd = emu.encode(emu.batch(X.numpy(), P.numpy(), E))
+    mu_o, sd_o = o.encode(X, A)
+    assert np.abs(mu - mu_o.detach().numpy()).max() < 1e-5
+    assert np.abs(sd - sd_o.detach().numpy()).max() < 1e-5
+
+
+def test_encode_arbitrary_topology(setup):
+    _, X, P, _, _, o, emu = setup
+    E = util.random_edge_lists(len(X), 0.3, 7)      # multi back-edges, self loops everywhere, node-0 loops
+    mu, sd = emu.encode(emu.batch(X.numpy(), P.numpy(), E))
+    mu_o, sd_o = o.encode(X, util.adj_dense(E))
+    assert np.abs(mu - mu_o.detach().numpy()).max() < 1e-5
+    assert np.abs(sd - sd_o.detach().numpy()).max() < 1e-5
+
+
+@pytest.mark.parametrize("w", [(2, 5, 0.01), (3, 6, 0.002)])
+def test_elbo_and_gradients_match_oracle(setup, w):
+    _, X, P, E, A, o, emu = setup
+    torch.manual_seed(1234)
+    eps = torch.randn(len(X), 128)
+    loss5, mu, sd, g = emu.elbo(emu.batch(X.numpy(), P.numpy(), E), eps.numpy(), w)
+    mu_o, sd_o = o.encode(X, A)
+    lo = o.loss(mu_o, sd_o, X, P, A, eps, *w)
+    for a, b in zip(loss5, lo):
+        assert abs(a - b.item()) <= 1e-5 * abs(b.item()) + 1e-7
+    o.zero_grad()
+    lo[0].backward()
+    gv = unflatten(g, emu.table)
+    for n, p in o.named_parameters():
+        ref = p.grad.numpy()
+        rel = np.abs(ref - gv[n]).max() / (np.abs(ref).max() + 1e-30)
+        assert rel < 1e-4, (n, rel)
+
+
+def test_elbo_arbitrary_topology_gradients(setup):
+    _, X, P, _, _, o, emu = setup
+    E = util.random_edge_lists(len(X), 0.35, 11)
+    A = util.adj_dense(E)
+    torch.manual_seed(5)
+    eps = torch.randn(len(X), 128)
+    loss5, mu, sd, g = emu.elbo(emu.batch(X.numpy(), P.numpy(), E), eps.numpy())
+    mu_o, sd_o = o.encode(X, A)
+    lo = o.loss(mu_o, sd_o, X, P, A, eps)
+    assert abs(loss5[0] - lo[0].item()) <= 1e-5 * abs(lo[0].item())
+    o.zero_grad()
+    lo[0].backward()
+    gv = unflatten(g, emu.table)
+    for n, p in o.named_parameters():
+        ref = p.grad.numpy()
+        assert np.abs(ref - gv[n]).max() / (np.abs(ref).max() + 1e-30) < 1e-4, n
+
+
+def test_greedy_decode_matches_oracle(setup):
+    _, X, P, E, A, o, emu = setup
+    torch.manual_seed(4321)
+    z = torch.randn(12, 128)
+    Xd, Pd, adj, mg = emu.decode(z.numpy())
+    Xo, Po, Ao, m = o.decode(z, return_margins=True)
+    lg = torch.cat([l.flatten(1) for l in m["edge"] + m["self"]], 1).abs().min(1).values.numpy()
+    assert np.allclose(mg, lg, rtol=1e-3, atol=1e-6)
+    ok = lg > 1e-4                                   # tie-aware: skip graphs with a decision on the threshold
+    assert ok.sum() >= 10
+    assert np.array_equal(util.adj_from_masks(adj)[ok], Ao.numpy()[ok])
+    assert np.array_equal(Pd.astype(np.int32)[ok], Po.numpy().astype(np.int32)[ok])
+    assert np.abs(Xd - Xo.numpy())[ok].max() <= 1e-6
