@@ -17,6 +17,8 @@ SIGNATURES = {
     "dxvae_abi_version": (C.c_int, []),
     "dxvae_last_error": (C.c_char_p, []),
     "dxvae_launch_count": (C.c_longlong, []),
+    "dxvae_prof_begin": (None, [C.c_int]),
+    "dxvae_prof_end": (None, [P, P, P]),
     "dxvae_param_blob_floats": (I64, []),
     "dxvae_param_count": (I64, []),
     "dxvae_param_entry": (C.c_int, [C.c_int, C.POINTER(ParamEntry)]),
@@ -31,11 +33,13 @@ SIGNATURES = {
     "dxvae_reparameterize": (C.c_int, [I64, P, P, P, P, P]),
     "dxvae_decode_greedy": (C.c_int, [P, I64, P, P, P, P, P, P, SZ, P]),
     "dxvae_elbo_step": (C.c_int, [P, I64, P, P, P, I32, P, P, P, F, F, F, F, P, P, P, P, P, SZ, P]),
+    "dxvae_loss_step": (C.c_int, [P, I64, P, P, P, P, P, P, F, F, F, F, P, P, P, P, P, SZ, P]),
+    "dxvae_encode_bwd": (C.c_int, [P, I64, P, P, I32, P, P, P, P, P, P, P, SZ, P]),
     "dxvae_adamw_step": (C.c_int, [I64, P, P, P, P, F, F, F, F, F, I64, F, P]),
     "dxvae_test_gemm": (C.c_int, [C.c_int, I64, I64, I64, P, I64, P, I64, P, I64, P, C.c_int, C.c_int, P]),
 }
 
-OP_ENCODE, OP_DECODE, OP_TRAIN, OP_SCHEDULE = 0, 1, 2, 3
+OP_ENCODE, OP_DECODE, OP_TRAIN, OP_SCHEDULE, OP_ENCODE_TRAIN, OP_LOSS = 0, 1, 2, 3, 4, 5
 
 
 def bind(lib):

@@ -34,6 +34,8 @@ size_t workspace_bytes(int op, int64_t B) {
     case DXVAE_OP_DECODE: carve_dec(ar, B, false); break;
     case DXVAE_OP_TRAIN: carve_train(ar, B); break;
     case DXVAE_OP_SCHEDULE: ar.take<int32_t>((size_t)36 * ((B + 1023) / 1024)); break;
+    case DXVAE_OP_ENCODE_TRAIN: carve_enc(ar, B, true); break;
+    case DXVAE_OP_LOSS: carve_dec(ar, B, true); break;
     default: return 0;
   }
   return ar.off + 256;
@@ -65,6 +67,40 @@ int elbo_step(dx_stream_t st, const float* weights, const Batch& bt, const float
   return check_launch("elbo_step");
 }
 
+// Split form of elbo_step for callers that hold q(z|G) between the two halves
+// (DXVAE.encode(...) followed by DXVAE.loss(q, ...), model.py:370-371).
+int loss_step(dx_stream_t st, const float* weights, const Batch& bt, const float* mu, const float* sd, const float* eps,
+              LossW lw, float* loss5, float* grads, float* dmu, float* dsd, void* ws, size_t ws_bytes) {
+  const int B = (int)bt.B;
+  Arena ar(ws, ws_bytes);
+  DecWs d = carve_dec(ar, bt.B, true);
+  DX_CHECK(!ar.overflow, "loss_step: workspace too small (%zu < %zu bytes)", ws_bytes, ar.off);
+  Weights W(weights);
+  reparameterize(st, (int64_t)B * Z, mu, sd, eps, d.z);
+  zero_async(st, d.rowloss, sizeof(float) * 4 * (size_t)B);
+  DecIO io{true, &bt, lw, nullptr, nullptr};
+  decode_fwd_impl(st, W, B, d.z, d, io);
+  kld_rows(st, B, mu, sd, lw, d.rowloss);
+  loss_reduce(st, B, d.rowloss, loss5);
+  if (grads) {
+    DX_CHECK(dmu && dsd, "loss_step: dmu/dstd required with grads");
+    Weights G(grads);
+    decode_bwd_impl(st, W, G, B, d.z, d, bt, lw);
+    latent_bwd(st, B, mu, sd, eps, d.dz, lw, dmu, dsd);
+  }
+  return check_launch("loss_step");
+}
+
+int encode_bwd(dx_stream_t st, const float* weights, const Batch& bt, const float* sd, const float* dmu,
+               const float* dsd, float* grads, void* ws, size_t ws_bytes) {
+  Arena ar(ws, ws_bytes);
+  EncWs e = carve_enc(ar, bt.B, true);
+  DX_CHECK(!ar.overflow, "encode_bwd: workspace too small (%zu < %zu bytes)", ws_bytes, ar.off);
+  Weights W(weights), G(grads);
+  encode_bwd_impl(st, W, G, bt, e, dmu, dsd, sd);
+  return check_launch("encode_bwd");
+}
+
 int decode_greedy(dx_stream_t st, const float* weights, int64_t B64, const float* z, float* Xg, float* Pg,
                   uint64_t* adj, float* margins, void* ws, size_t ws_bytes) {
   const int B = (int)B64;
@@ -92,6 +128,8 @@ extern "C" {
 int dxvae_abi_version(void) { return DXVAE_ABI_VERSION; }
 const char* dxvae_last_error(void) { return g_err; }
 long long dxvae_launch_count(void) { return g_launches; }
+void dxvae_prof_begin(int max_launches) { prof_begin(max_launches); }
+void dxvae_prof_end(double* ms, double* flops, long long* n) { prof_end(ms, flops, n); }
 
 int64_t dxvae_param_blob_floats(void) { return param_blob_floats(); }
 int64_t dxvae_param_count(void) {
@@ -160,6 +198,23 @@ int dxvae_elbo_step(const float* weights, int64_t B, const float* Xn, const int3
   Batch bt{B, Xn, cls, adj, n_levels, level_ptr_host, level_rows};
   LossW lw{w_env, w_frq, w_kld, inv_batch};
   return elbo_step(DX_ST(stream), weights, bt, eps, lw, loss5, mu_out, std_out, grads, workspace, workspace_bytes);
+}
+int dxvae_loss_step(const float* weights, int64_t B, const float* Xn, const int32_t* cls, const uint64_t* adj,
+                    const float* mu, const float* std_, const float* eps, float w_env, float w_frq, float w_kld,
+                    float inv_batch, float* loss5, float* grads, float* dmu, float* dstd, void* workspace,
+                    size_t workspace_bytes, void* stream) {
+  DX_BATCH_OK(B);
+  Batch bt{B, Xn, cls, adj, 0, nullptr, nullptr};
+  LossW lw{w_env, w_frq, w_kld, inv_batch};
+  return loss_step(DX_ST(stream), weights, bt, mu, std_, eps, lw, loss5, grads, dmu, dstd, workspace, workspace_bytes);
+}
+int dxvae_encode_bwd(const float* weights, int64_t B, const float* Xn, const uint64_t* adj, int32_t n_levels,
+                     const int32_t* level_ptr_host, const int32_t* level_rows, const float* std_, const float* dmu,
+                     const float* dstd, float* grads, void* workspace, size_t workspace_bytes, void* stream) {
+  DX_BATCH_OK(B);
+  DX_CHECK(n_levels >= 1 && n_levels <= 6, "encode_bwd: n_levels=%d", n_levels);
+  Batch bt{B, Xn, nullptr, adj, n_levels, level_ptr_host, level_rows};
+  return encode_bwd(DX_ST(stream), weights, bt, std_, dmu, dstd, grads, workspace, workspace_bytes);
 }
 int dxvae_adamw_step(int64_t n, float* weights, const float* grads, float* exp_avg, float* exp_avg_sq, float lr,
                      float beta1, float beta2, float eps, float weight_decay, int64_t step, float grad_scale,

@@ -229,6 +229,16 @@ __global__ void __launch_bounds__(256, (BM >= 128 ? 2 : 3)) k_gemm(const GemmP p
 
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
+// ---- optional per-launch timing of the GEMM family (bench.py roofline) ----------------------
+// CUDA events are recorded on the launching stream around each GEMM while enabled; the pairs
+// are resolved in prof_end().  Class 0 = 128x128 tile kernels, class 1 = 64x64.
+struct ProfState {
+  bool on = false;
+  int cap = 0, used = 0;
+  cudaEvent_t* e0 = nullptr; cudaEvent_t* e1 = nullptr;
+  double* flops = nullptr; int* cls = nullptr;
+} g_prof;
+
 template <int BM, int BN, int TM, int TN>
 void launch_tile(dx_stream_t s, const GemmP& p) {
   const int gm = (p.M + BM - 1) / BM, gn = (p.N + BN - 1) / BN;
@@ -247,10 +257,18 @@ void launch_tile(dx_stream_t s, const GemmP& p) {
   const bool vecB = aligned16(p.B) && (p.ldb % 4 == 0);
   const bool vecC = aligned16(p.C) && (p.ldc % 4 == 0);
   dim3 grid(gn, gm, splits);
+  int slot = -1;
+  if (g_prof.on && g_prof.used < g_prof.cap) {
+    slot = g_prof.used++;
+    g_prof.flops[slot] = 2.0 * p.M * (double)p.N * p.K;
+    g_prof.cls[slot] = BM >= 128 ? 0 : 1;
+    cudaEventRecord(g_prof.e0[slot], s);
+  }
   if (p.a_kc && p.b_kc) k_gemm<BM, BN, TM, TN, true, true><<<grid, 256, 0, s>>>(p, k_chunk, vecA, vecB, vecC);
   else if (p.a_kc && !p.b_kc) k_gemm<BM, BN, TM, TN, true, false><<<grid, 256, 0, s>>>(p, k_chunk, vecA, vecB, vecC);
   else if (!p.a_kc && !p.b_kc) k_gemm<BM, BN, TM, TN, false, false><<<grid, 256, 0, s>>>(p, k_chunk, vecA, vecB, vecC);
   else k_gemm<BM, BN, TM, TN, false, true><<<grid, 256, 0, s>>>(p, k_chunk, vecA, vecB, vecC);
+  if (slot >= 0) cudaEventRecord(g_prof.e1[slot], s);
   ++g_launches;
 }
 
@@ -276,6 +294,32 @@ __global__ void __launch_bounds__(256) k_colsum(int M, int N, const float* __res
 }
 
 }  // namespace
+
+void prof_begin(int max_launches) {
+  prof_end(nullptr, nullptr, nullptr);
+  g_prof.cap = max_launches; g_prof.used = 0;
+  g_prof.e0 = new cudaEvent_t[max_launches]; g_prof.e1 = new cudaEvent_t[max_launches];
+  g_prof.flops = new double[max_launches]; g_prof.cls = new int[max_launches];
+  for (int i = 0; i < max_launches; ++i) { cudaEventCreate(&g_prof.e0[i]); cudaEventCreate(&g_prof.e1[i]); }
+  g_prof.on = true;
+}
+// ms[2], flops[2], n[2]: totals per tile class.  Synchronises the device.
+void prof_end(double* ms, double* flops, long long* n) {
+  if (!g_prof.e0) return;
+  g_prof.on = false;
+  cudaDeviceSynchronize();
+  double tms[2] = {0, 0}, tfl[2] = {0, 0}; long long tn[2] = {0, 0};
+  for (int i = 0; i < g_prof.used; ++i) {
+    float t = 0.f;
+    if (cudaEventElapsedTime(&t, g_prof.e0[i], g_prof.e1[i]) == cudaSuccess) {
+      tms[g_prof.cls[i]] += t; tfl[g_prof.cls[i]] += g_prof.flops[i]; tn[g_prof.cls[i]]++;
+    }
+  }
+  for (int i = 0; i < g_prof.cap; ++i) { cudaEventDestroy(g_prof.e0[i]); cudaEventDestroy(g_prof.e1[i]); }
+  delete[] g_prof.e0; delete[] g_prof.e1; delete[] g_prof.flops; delete[] g_prof.cls;
+  g_prof = ProfState();
+  for (int c = 0; c < 2; ++c) { if (ms) ms[c] = tms[c]; if (flops) flops[c] = tfl[c]; if (n) n[c] = tn[c]; }
+}
 
 void gemm(dx_stream_t s, const GemmP& p) {
   if (p.M <= 0 || p.N <= 0 || p.K <= 0) return;
@@ -324,6 +368,11 @@ void gemm(dx_stream_t, const GemmP& p) {
     }
   }
   ++g_launches;
+}
+
+void prof_begin(int) {}
+void prof_end(double* ms, double* flops, long long* n) {
+  for (int c = 0; c < 2; ++c) { if (ms) ms[c] = 0; if (flops) flops[c] = 0; if (n) n[c] = 0; }
 }
 
 void colsum_accum(dx_stream_t, int M, int N, const float* dy, int64_t lddy, float* db, const int* dy_idx) {

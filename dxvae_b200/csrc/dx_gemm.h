@@ -31,6 +31,8 @@ struct GemmP {
 };
 
 void gemm(dx_stream_t s, const GemmP& p);
+void prof_begin(int max_launches);
+void prof_end(double* ms, double* flops, long long* n);
 
 // y[M,N] = act(x[M,K] W[N,K]^T + bias)
 inline void linear_fwd(dx_stream_t s, int M, int N, int K, const float* x, int64_t ldx, const float* W, int64_t ldw,

@@ -1,0 +1,400 @@
+"""DXVAE — host-side mirror of the reference class (model.py:10-391) over the CUDA library.
+
+Same constructor, same public methods (encode / decode / encode_decode / generate / loss /
+forward / train, plus the `reparameterize` seam for injected noise), same 53-tensor
+state_dict, same graph format in and out.  All arithmetic happens in hand-written sm_100a
+kernels behind the C ABI of include/dxvae_b200.h; torch is used for device memory, streams,
+autograd plumbing and torch.distributed.  There is no CPU path: compute methods raise
+without the CUDA extension or without a GPU.
+"""
+import ctypes
+import random
+
+import numpy as np
+import torch
+import torch.nn as nn
+from torch.distributions.normal import Normal
+
+from . import _abi, _lib
+from .dxdata import DXGraphBatch
+from .params import param_table
+
+_FIXED = dict(n_nodes=7, n_params=21, size_X=27, size_X0=23, size_H=512, size_Z=128)
+
+
+class _DevBatch:
+    """Device-resident batch in kernel layout (see include/dxvae_b200.h)."""
+    __slots__ = ("B", "Xn", "cls", "adj", "n_levels", "level_ptr", "level_rows", "level", "csr")
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+class DXVAE(nn.Module):
+    def __init__(self, n_nodes=7, n_params=21, size_X=27, size_X0=23, size_H=512, size_Z=128, checkpoint=None):
+        super().__init__()
+        given = dict(n_nodes=n_nodes, n_params=n_params, size_X=size_X, size_X0=size_X0, size_H=size_H, size_Z=size_Z)
+        if given != _FIXED:
+            raise ValueError("dxvae_b200 kernels are specialised on %r; got %r" % (_FIXED, given))
+        self.device = "cuda" if torch.cuda.is_available() else "cpu"     # model.py:13
+        self.n_nodes, self.n_params, self.size_X, self.size_Z = n_nodes, n_params, size_X, size_Z
+        self.zero_X0 = torch.zeros(size_X0, device=self.device)
+        self.zero_H = torch.zeros(size_H, device=self.device)
+        self.hidden = None
+        self.p_dist = Normal(0., 1.)
+        H, Z, X, X0 = size_H, size_Z, size_X, size_X0
+        # Parameter containers only (never called): identical registration order to
+        # model.py:24-72, hence identical state_dict keys and identical seeded init.
+        self.combin_encode = nn.GRUCell(X, H)
+        self.loop_encode = nn.GRUCell(X, H)
+        self.root_encode = nn.GRUCell(X0, H)
+        self.h_to_mu = nn.Linear(H, Z)
+        self.h_to_std = nn.Sequential(nn.Linear(H, Z), nn.Softplus())
+        self.combin_decode = nn.GRUCell(X, H)
+        self.loop_decode = nn.GRUCell(X, H)
+        self.root_decode = nn.GRUCell(X0, H)
+        self.z_to_h = nn.Sequential(nn.Linear(Z, H), nn.Tanh())
+        self.h_to_x0 = nn.Sequential(nn.Linear(H, 2 * H), nn.ReLU(), nn.Linear(2 * H, 2 * H), nn.ReLU(),
+                                     nn.Linear(2 * H, X0 + 32))
+        self.h_to_x = nn.Sequential(nn.Linear(H, 2 * H), nn.ReLU(), nn.Linear(2 * H, 2 * H), nn.ReLU(),
+                                    nn.Linear(2 * H, X))
+        self.h_to_edge_self = nn.Sequential(nn.Linear(H, 2 * H), nn.ReLU(), nn.Linear(2 * H, 1))
+        self.h_to_edge = nn.Sequential(nn.Linear(2 * H, 4 * H), nn.ReLU(), nn.Linear(4 * H, 2))
+        self.gate = nn.Sequential(nn.Linear(2 * H, H), nn.Sigmoid())
+        self.mapper = nn.Sequential(nn.Linear(2 * H, H, bias=False))
+        self._flat = None           # fp32 blob all parameters are views of (device)
+        self._table = None
+        self._ws = {}
+        self.max_chunk = 32768      # graphs per kernel pass for encode / decode
+        self.verbose = True
+        self.last_margins = None
+        if checkpoint is not None:
+            self.load_state_dict(torch.load(checkpoint, map_location=self.device))
+
+    # ------------------------------------------------------------------ plumbing
+    def _ensure_flat(self):
+        """Parameters live as views of one flat CUDA blob laid out per dxvae_param_entry()."""
+        L = _lib.require_cuda()
+        if self._table is None:
+            self._table = param_table(L)
+            self._total = int(L.dxvae_param_blob_floats())
+        named = dict(self.named_parameters())
+        ok = self._flat is not None and self._flat.is_cuda
+        if ok:
+            base = self._flat.data_ptr()
+            ok = all(named[n].data_ptr() == base + 4 * off for n, off, _ in self._table)
+        if not ok:
+            flat = torch.zeros(self._total, dtype=torch.float32, device="cuda")
+            for n, off, shape in self._table:
+                p = named[n]
+                k = p.numel()
+                flat[off:off + k].copy_(p.data.reshape(-1))
+                p.data = flat[off:off + k].view(shape)
+                p.grad = None
+            self._flat = flat
+            self.device = "cuda"
+        return L
+
+    def _workspace(self, op, B, fresh=False):
+        L = _lib.lib()
+        n = int(L.dxvae_workspace_bytes(op, B))
+        if fresh:
+            return torch.empty(n, dtype=torch.uint8, device="cuda")
+        key = (op,)
+        ws = self._ws.get(key)
+        if ws is None or ws.numel() < n:
+            self._ws[key] = None
+            ws = torch.empty(n, dtype=torch.uint8, device="cuda")
+            self._ws[key] = ws
+        return ws
+
+    def _prepare(self, G, need_cls=True, host_batcher=None):
+        """list of graphs / DXGraphBatch -> _DevBatch (the batcher).
+
+        Host lists go through the C++ host batcher (flat CSR + level schedule + feedback
+        marks); device-resident batches through the device scheduler."""
+        L = _lib.require_cuda()
+        gb = DXGraphBatch.from_graphs(G)
+        B = len(gb)
+        if B == 0:
+            raise ValueError("empty batch")
+        st = _stream()
+        d = _DevBatch()
+        d.B = B
+        Xg = gb.X.to("cuda", torch.float32, non_blocking=True).contiguous()
+        Pg = gb.params.to("cuda", torch.float32, non_blocking=True).contiguous()
+        d.Xn = torch.empty(7, B, 32, device="cuda")
+        d.cls = torch.empty(14, B, dtype=torch.int32, device="cuda")
+        _lib.check(L.dxvae_pack_graphs(B, Xg.data_ptr(), Pg.data_ptr(), d.Xn.data_ptr(), d.cls.data_ptr(), st),
+                   "dxvae_pack_graphs")
+        use_host = (not gb.adj.is_cuda) if host_batcher is None else host_batcher
+        d.level_ptr = np.zeros(8, np.int32)
+        d.csr = None
+        if use_host:
+            edges = gb.edge_lists()
+            eptr = np.zeros(B + 1, np.int32)
+            eptr[1:] = np.cumsum([len(e[0]) for e in edges])
+            src = np.fromiter((s for e in edges for s in e[0]), np.int8, count=int(eptr[-1]))
+            dst = np.fromiter((t for e in edges for t in e[1]), np.int8, count=int(eptr[-1]))
+            ne = max(1, int(eptr[-1]))
+            adj = np.zeros(B, np.uint64); indptr = np.zeros(7 * B + 1, np.int32)
+            indices = np.zeros(ne, np.int32); eflags = np.zeros(ne, np.uint8)
+            level = np.zeros((B, 7), np.uint8); rows = np.zeros(6 * B, np.int32)
+            nl = _abi.I32(0)
+            pv = lambda a: a.ctypes.data
+            _lib.check(L.dxvae_batch_build_host(B, pv(eptr), pv(src), pv(dst), pv(adj), pv(indptr), pv(indices),
+                                                pv(eflags), pv(level), pv(d.level_ptr), pv(rows), ctypes.byref(nl)),
+                       "dxvae_batch_build_host")
+            d.n_levels = int(nl.value)
+            d.adj = torch.from_numpy(adj.view(np.int64)).to("cuda")
+            d.level_rows = torch.from_numpy(rows).to("cuda")
+            d.level = level
+            d.csr = (indptr, indices[:int(eptr[-1])], eflags[:int(eptr[-1])])
+        else:
+            d.adj = gb.adj.to("cuda", torch.int64).contiguous()
+            self._schedule(d)
+        return d
+
+    def _schedule(self, d):
+        L = _lib.lib()
+        B = d.B
+        d.level = torch.empty(B, 7, dtype=torch.uint8, device="cuda")
+        d.level_rows = torch.empty(6 * B, dtype=torch.int32, device="cuda")
+        lp_dev = torch.empty(8, dtype=torch.int32, device="cuda")
+        ws = self._workspace(_abi.OP_SCHEDULE, B)
+        _lib.check(L.dxvae_batch_schedule(B, d.adj.data_ptr(), d.level.data_ptr(), lp_dev.data_ptr(),
+                                          d.level_rows.data_ptr(), d.level_ptr.ctypes.data, ws.data_ptr(), ws.numel(),
+                                          _stream()), "dxvae_batch_schedule")
+        nz = [l for l in range(7) if d.level_ptr[l + 1] > d.level_ptr[l]]
+        d.n_levels = (max(nz) + 1) if nz else 1
+
+    def _params_tuple(self):
+        return tuple(dict(self.named_parameters())[n] for n, _, _ in self._table)
+
+    def _grad_views(self, gflat, scale=None):
+        out = []
+        for _, off, shape in self._table:
+            k = int(np.prod(shape))
+            g = gflat[off:off + k].view(shape)
+            out.append(g if scale is None else g * scale)
+        return tuple(out)
+
+    # ------------------------------------------------------------------ encode
+    def encode(self, G):
+        """model.py:200-212.  Returns Normal(mu, std) over the batch (device tensors).  With
+        autograd enabled the result is differentiable w.r.t. the encoder parameters."""
+        L = self._ensure_flat()
+        gb = DXGraphBatch.from_graphs(G)
+        B = len(gb)
+        self.hidden = B                                   # model.py:201 sizes the scratch state here
+        if torch.is_grad_enabled() and B <= self.max_chunk:
+            d = self._prepare(gb, need_cls=True)
+            mu, sd = _EncodeFn.apply(self, d, *self._params_tuple())
+            q = Normal(mu, sd, validate_args=False)
+            q._dx_batch = d
+            return q
+        mu = torch.empty(B, 128, device="cuda"); sd = torch.empty(B, 128, device="cuda")
+        for lo in range(0, B, self.max_chunk):
+            hi = min(B, lo + self.max_chunk)
+            d = self._prepare(gb[lo:hi], need_cls=False)
+            ws = self._workspace(_abi.OP_ENCODE, d.B)
+            _lib.check(L.dxvae_encode_fwd(self._flat.data_ptr(), d.B, d.Xn.data_ptr(), d.adj.data_ptr(), d.n_levels,
+                                          d.level_ptr.ctypes.data, d.level_rows.data_ptr(), mu[lo:hi].data_ptr(),
+                                          sd[lo:hi].data_ptr(), ws.data_ptr(), ws.numel(), 0, _stream()),
+                       "dxvae_encode_fwd")
+        return Normal(mu, sd, validate_args=False)
+
+    # ------------------------------------------------------------------ reparameterize
+    def reparameterize(self, q_dist, eps=None):
+        """z = mu + std * eps (what q_dist.rsample() computes, model.py:284).  eps=None draws
+        from torch's global generator exactly as Normal.rsample does on this device."""
+        L = _lib.require_cuda()
+        mu, sd = (q_dist.loc, q_dist.scale) if isinstance(q_dist, Normal) else q_dist
+        mu = mu.detach().contiguous(); sd = sd.detach().contiguous()
+        if eps is None:
+            eps = torch.empty_like(mu).normal_()
+        eps = eps.to(mu.device, torch.float32).contiguous()
+        z = torch.empty_like(mu)
+        _lib.check(L.dxvae_reparameterize(mu.numel(), mu.data_ptr(), sd.data_ptr(), eps.data_ptr(), z.data_ptr(),
+                                          _stream()), "dxvae_reparameterize")
+        return z
+
+    # ------------------------------------------------------------------ decode
+    @torch.no_grad()
+    def decode(self, z):
+        """model.py:214-253: greedy generation.  Returns a DXGraphBatch (list-like of graphs with
+        ndata['X'], ndata['params'], edges() in the reference's insertion order)."""
+        L = self._ensure_flat()
+        z = torch.as_tensor(z).to("cuda", torch.float32).contiguous()
+        B = z.shape[0]
+        Xg = torch.empty(B, 7, 27, device="cuda"); Pg = torch.empty(B, 7, 21, device="cuda")
+        adj = torch.empty(B, dtype=torch.int64, device="cuda"); mg = torch.empty(B, device="cuda")
+        for lo in range(0, B, self.max_chunk):
+            hi = min(B, lo + self.max_chunk)
+            ws = self._workspace(_abi.OP_DECODE, hi - lo)
+            _lib.check(L.dxvae_decode_greedy(self._flat.data_ptr(), hi - lo, z[lo:hi].data_ptr(), Xg[lo:hi].data_ptr(),
+                                             Pg[lo:hi].data_ptr(), adj[lo:hi].data_ptr(), mg[lo:hi].data_ptr(),
+                                             ws.data_ptr(), ws.numel(), _stream()), "dxvae_decode_greedy")
+        self.last_margins = mg
+        return DXGraphBatch(Xg, Pg, adj)
+
+    def encode_decode(self, G_true, stochastic=False):
+        """model.py:255-262."""
+        with torch.no_grad():
+            q_dist = self.encode(G_true)
+            z = q_dist.sample() if stochastic else q_dist.loc
+        return self.decode(z)
+
+    def generate(self, n):
+        """model.py:264-268 (prior sample drawn on the CPU generator, as the reference does)."""
+        self.hidden = n
+        sample = self.p_dist.sample((n, self.size_Z)).to("cuda")
+        return self.decode(sample)
+
+    # ------------------------------------------------------------------ loss / forward
+    def loss(self, q_dist, G_true, w_env=2, w_frq=5, w_kld=0.01, eps=None):
+        """model.py:270-367.  `eps` injects the reparameterisation noise; None draws it the way
+        q_dist.rsample() would (the reference always samples: App. C.1)."""
+        self._ensure_flat()
+        d = getattr(q_dist, "_dx_batch", None)
+        if d is None or d.B != len(G_true):
+            d = self._prepare(G_true, need_cls=True)
+        mu, sd = q_dist.loc, q_dist.scale
+        if eps is None:
+            eps = torch.empty(mu.shape, device="cuda").normal_()
+        eps = torch.as_tensor(eps).to("cuda", torch.float32).contiguous()
+        out = _LossFn.apply(self, d, eps, (float(w_env), float(w_frq), float(w_kld)), mu, sd, *self._params_tuple())
+        total, rest = out[0], out[1]
+        return total, rest[0], rest[1], rest[2], rest[3]
+
+    def forward(self, G_true, w_env=2, w_frq=5, w_kld=0.01, eps=None):
+        """model.py:369-372: encode + loss, fused into one native call (dxvae_elbo_step)."""
+        self._ensure_flat()
+        d = self._prepare(G_true, need_cls=True)
+        self.hidden = d.B
+        if eps is None:
+            eps = torch.empty(d.B, 128, device="cuda").normal_()
+        eps = torch.as_tensor(eps).to("cuda", torch.float32).contiguous()
+        out = _ElboFn.apply(self, d, eps, (float(w_env), float(w_frq), float(w_kld)), *self._params_tuple())
+        total, rest = out[0], out[1]
+        return total, rest[0], rest[1], rest[2], rest[3]
+
+    def elbo_step(self, d, eps, w, grads=None, inv_batch=None, mu_out=None, std_out=None):
+        """Raw fused step on a prepared batch: returns loss5 (device tensor of 5); accumulates
+        into `grads` (flat blob) when given."""
+        L = _lib.lib()
+        loss5 = torch.empty(5, device="cuda")
+        ws = self._workspace(_abi.OP_TRAIN, d.B)
+        _lib.check(L.dxvae_elbo_step(
+            self._flat.data_ptr(), d.B, d.Xn.data_ptr(), d.cls.data_ptr(), d.adj.data_ptr(), d.n_levels,
+            d.level_ptr.ctypes.data, d.level_rows.data_ptr(), eps.data_ptr(), w[0], w[1], w[2],
+            (1.0 / d.B) if inv_batch is None else inv_batch, loss5.data_ptr(),
+            None if mu_out is None else mu_out.data_ptr(), None if std_out is None else std_out.data_ptr(),
+            None if grads is None else grads.data_ptr(), ws.data_ptr(), ws.numel(), _stream()), "dxvae_elbo_step")
+        return loss5
+
+    # ------------------------------------------------------------------ train
+    def train(self, G_true, epochs, size_batch=32, lr=0.001, checkpoint=None, w_env=2, w_frq=5, w_kld=0.01):
+        """model.py:374-391: AdamW(lr), epochs+1 passes, in-place shuffle with Python's `random`,
+        drop-last batching, checkpoint per epoch.  (Shadows nn.Module.train as the reference
+        does.)  Under torch.distributed every global batch is sharded in equal contiguous
+        slices across ranks and the flat gradient is all-reduced (sum) over NCCL."""
+        from .train import Trainer
+        t = Trainer(self, lr=lr, w=(float(w_env), float(w_frq), float(w_kld)))
+        n_samples = len(G_true)
+        n_iters = int(n_samples / size_batch)
+        data = t.upload(G_true)
+        order = list(range(n_samples))
+        for epoch in range(epochs + 1):
+            if self.verbose:
+                print(f'Epoch: {epoch}')
+            perm = list(range(n_samples))
+            random.shuffle(perm)                      # same RNG consumption as random.shuffle(G_true)
+            order = [order[i] for i in perm]
+            if isinstance(G_true, list):
+                G_true[:] = [G_true[i] for i in perm]  # the reference shuffles the caller's list in place
+            for i in range(n_iters):
+                idx = order[i * size_batch:(i + 1) * size_batch]
+                loss5 = t.step(data, idx)
+                if self.verbose:
+                    l = loss5.tolist()
+                    print(f'batch: {i}\tloss: {l[0]:.4f}\tx0: {l[1]:.4f}\txi: {l[2]:.4f}\te: {l[3]:.4f}\tkld: {l[4]:.4f}')
+            if checkpoint is not None:
+                torch.save(self.state_dict(), checkpoint)
+                if self.verbose:
+                    print(f'\nCheckpoint [{checkpoint}] saved\n')
+        if self.verbose:
+            print('Finished Training')
+
+
+# =============================================================================================
+# autograd glue: gradients are produced by the native backward kernels, never by autograd
+# =============================================================================================
+class _ElboFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, model, d, eps, w, *params):
+        need = any(p.requires_grad for p in params) and torch.is_grad_enabled()
+        g = torch.zeros(model._total, device="cuda") if need else None
+        loss5 = model.elbo_step(d, eps, w, grads=g)
+        ctx.model, ctx.g = model, g
+        total, rest = loss5[0].clone(), loss5[1:].clone()
+        ctx.mark_non_differentiable(rest)
+        return total, rest
+
+    @staticmethod
+    def backward(ctx, gtotal, _grest):
+        grads = ctx.model._grad_views(ctx.g, gtotal)
+        return (None, None, None, None) + grads
+
+
+class _EncodeFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, model, d, *params):
+        L = _lib.lib()
+        ws = model._workspace(_abi.OP_ENCODE_TRAIN, d.B, fresh=True)
+        mu = torch.empty(d.B, 128, device="cuda"); sd = torch.empty(d.B, 128, device="cuda")
+        _lib.check(L.dxvae_encode_fwd(model._flat.data_ptr(), d.B, d.Xn.data_ptr(), d.adj.data_ptr(), d.n_levels,
+                                      d.level_ptr.ctypes.data, d.level_rows.data_ptr(), mu.data_ptr(), sd.data_ptr(),
+                                      ws.data_ptr(), ws.numel(), 1, _stream()), "dxvae_encode_fwd")
+        ctx.model, ctx.d, ctx.ws, ctx.sd = model, d, ws, sd
+        return mu, sd
+
+    @staticmethod
+    def backward(ctx, dmu, dsd):
+        model, d = ctx.model, ctx.d
+        L = _lib.lib()
+        g = torch.zeros(model._total, device="cuda")
+        dmu = torch.zeros(d.B, 128, device="cuda") if dmu is None else dmu.contiguous()
+        dsd = torch.zeros(d.B, 128, device="cuda") if dsd is None else dsd.contiguous()
+        _lib.check(L.dxvae_encode_bwd(model._flat.data_ptr(), d.B, d.Xn.data_ptr(), d.adj.data_ptr(), d.n_levels,
+                                      d.level_ptr.ctypes.data, d.level_rows.data_ptr(), ctx.sd.data_ptr(),
+                                      dmu.data_ptr(), dsd.data_ptr(), g.data_ptr(), ctx.ws.data_ptr(), ctx.ws.numel(),
+                                      _stream()), "dxvae_encode_bwd")
+        return (None, None) + model._grad_views(g)
+
+
+class _LossFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, model, d, eps, w, mu, sd, *params):
+        L = _lib.lib()
+        mu = mu.detach().contiguous(); sd = sd.detach().contiguous()
+        need = torch.is_grad_enabled()
+        g = torch.zeros(model._total, device="cuda") if need else None
+        dmu = torch.empty(d.B, 128, device="cuda") if need else None
+        dsd = torch.empty(d.B, 128, device="cuda") if need else None
+        loss5 = torch.empty(5, device="cuda")
+        ws = model._workspace(_abi.OP_LOSS, d.B)
+        _lib.check(L.dxvae_loss_step(
+            model._flat.data_ptr(), d.B, d.Xn.data_ptr(), d.cls.data_ptr(), d.adj.data_ptr(), mu.data_ptr(),
+            sd.data_ptr(), eps.data_ptr(), w[0], w[1], w[2], 1.0 / d.B, loss5.data_ptr(),
+            None if g is None else g.data_ptr(), None if dmu is None else dmu.data_ptr(),
+            None if dsd is None else dsd.data_ptr(), ws.data_ptr(), ws.numel(), _stream()), "dxvae_loss_step")
+        ctx.model, ctx.g, ctx.dmu, ctx.dsd = model, g, dmu, dsd
+        total, rest = loss5[0].clone(), loss5[1:].clone()
+        ctx.mark_non_differentiable(rest)
+        return total, rest
+
+    @staticmethod
+    def backward(ctx, gtotal, _grest):
+        return (None, None, None, None, ctx.dmu * gtotal, ctx.dsd * gtotal) + ctx.model._grad_views(ctx.g, gtotal)

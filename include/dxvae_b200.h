@@ -52,6 +52,10 @@ int dxvae_abi_version(void);
 const char* dxvae_last_error(void);
 /* number of kernels this library has launched in this process (bench.py's gpu_launches) */
 long long dxvae_launch_count(void);
+/* per-launch CUDA-event timing of the GEMM kernel family (bench.py roofline): totals per tile
+ * class (0: 128x128 tiles, 1: 64x64) of device ms, executed flops (2MNK) and launches. */
+void dxvae_prof_begin(int max_launches);
+void dxvae_prof_end(double* ms2, double* flops2, long long* n2);
 
 /* ---- parameter blob (state_dict of model.py:24-72) ------------- */
 typedef struct {
@@ -100,7 +104,8 @@ int dxvae_voices_to_graphs(int64_t B, const uint8_t* voices, float* Xn, int32_t*
 int dxvae_pack_syx(int64_t B, const float* Pg, uint8_t* voices, void* stream);
 
 /* ---- workspace sizes ------------------------------------------------------------ */
-enum { DXVAE_OP_ENCODE = 0, DXVAE_OP_DECODE = 1, DXVAE_OP_TRAIN = 2, DXVAE_OP_SCHEDULE = 3 };
+enum { DXVAE_OP_ENCODE = 0, DXVAE_OP_DECODE = 1, DXVAE_OP_TRAIN = 2, DXVAE_OP_SCHEDULE = 3,
+       DXVAE_OP_ENCODE_TRAIN = 4, DXVAE_OP_LOSS = 5 };
 size_t dxvae_workspace_bytes(int op, int64_t B);
 
 /* ---- encode (model.py:200-212; _propagate :151-198 with encode=True) ------------- *
@@ -134,6 +139,19 @@ int dxvae_elbo_step(const float* weights, int64_t B, const float* Xn, const int3
                     int32_t n_levels, const int32_t* level_ptr_host, const int32_t* level_rows, const float* eps,
                     float w_env, float w_frq, float w_kld, float inv_batch, float* loss5, float* mu_out,
                     float* std_out, float* grads, void* workspace, size_t workspace_bytes, void* stream);
+
+/* Split form of dxvae_elbo_step, for DXVAE.encode(G) followed by DXVAE.loss(q, G)
+ * (model.py:370-371).  encode_fwd(keep=1, workspace of DXVAE_OP_ENCODE_TRAIN) leaves the
+ * encoder's activations in its workspace; loss_step (workspace DXVAE_OP_LOSS) consumes
+ * mu/std and returns the loss terms, decoder gradients (accumulated into grads) and
+ * dL/dmu, dL/dstd; encode_bwd then finishes the chain from the SAME encoder workspace. */
+int dxvae_loss_step(const float* weights, int64_t B, const float* Xn, const int32_t* cls, const uint64_t* adj,
+                    const float* mu, const float* std_, const float* eps, float w_env, float w_frq, float w_kld,
+                    float inv_batch, float* loss5, float* grads, float* dmu, float* dstd, void* workspace,
+                    size_t workspace_bytes, void* stream);
+int dxvae_encode_bwd(const float* weights, int64_t B, const float* Xn, const uint64_t* adj, int32_t n_levels,
+                     const int32_t* level_ptr_host, const int32_t* level_rows, const float* std_, const float* dmu,
+                     const float* dstd, float* grads, void* workspace, size_t workspace_bytes, void* stream);
 
 /* ---- optimiser (model.py:375,386: torch.optim.AdamW defaults) -------------------- */
 int dxvae_adamw_step(int64_t n, float* weights, const float* grads, float* exp_avg, float* exp_avg_sq, float lr,

@@ -1,0 +1,347 @@
+"""GPU parity tests: the CUDA library, called through the C ABI / the DXVAE mirror, against
+the CPU oracle (oracle/dxvae_oracle.py) and against the golden fixtures generated from the
+UNMODIFIED reference (tests/golden, oracle/make_golden.py).
+
+Tolerances (fp32 path; SURVEY §8c, from the reference's own fp32-vs-fp64 noise floor):
+  latents |d| <= 1e-5 abs; each loss term rel <= 1e-5; gradients max-norm-relative <= 1e-4 per
+  tensor; decoded params / topology exact on graphs whose decision margins exceed 1e-4
+  (tie-aware); decoded X <= 1e-6 abs; batcher / data-format outputs bit-exact."""
+import ctypes
+import hashlib
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import dxvae_oracle as O
+from tests import util
+
+pytestmark = pytest.mark.gpu
+
+TOL_LAT, TOL_LOSS, TOL_GRAD, MARGIN = 1e-5, 1e-5, 1e-4, 1e-4
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from dxvae_b200 import _lib
+    return _lib.require_cuda()
+
+
+@pytest.fixture(scope="module")
+def golden():
+    return np.load(os.path.join(util.GOLDEN, "model_golden.npz"))
+
+
+def make_model(seed, gain):
+    from dxvae_b200 import DXVAE
+    o = O.make_weights(seed, gain)
+    m = DXVAE()
+    m.load_state_dict(o.state_dict())
+    m.verbose = False
+    return m, o
+
+
+def st():
+    return torch.cuda.current_stream().cuda_stream
+
+
+# --------------------------------------------------------------------------- GEMM
+@pytest.mark.parametrize("M,N,K", [(128, 1536, 512), (1000, 1536, 27), (513, 55, 1024), (300, 2, 2048), (77, 1, 1024),
+                                   (4096, 2048, 512), (2048, 1024, 1024), (64, 512, 128), (1, 27, 1024)])
+def test_gemm_forward(lib, M, N, K):
+    from dxvae_b200 import _lib
+    g = torch.Generator().manual_seed(M * 7 + N)
+    lda = 32 if K == 27 else K
+    A = torch.randn(M, lda, generator=g).cuda(); W = torch.randn(N, K, generator=g).cuda()
+    b = torch.randn(N, generator=g).cuda()
+    for act, fn in ((0, lambda t: t), (1, torch.relu), (2, torch.tanh), (4, torch.nn.functional.softplus)):
+        C = torch.empty(M, N, device="cuda")
+        _lib.check(lib.dxvae_test_gemm(0, M, N, K, A.data_ptr(), lda, W.data_ptr(), K, C.data_ptr(), N, b.data_ptr(),
+                                       act, 0, st()), "gemm")
+        ref = fn(A[:, :K].double() @ W.double().t() + b.double())
+        err = (C.double() - ref).abs().max().item()
+        assert err <= 2e-4 * max(1.0, ref.abs().max().item()), (act, err)
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 1536, 512), (1000, 55, 1024), (4096, 2048, 512), (333, 2, 2048)])
+def test_gemm_dgrad_wgrad(lib, M, N, K):
+    from dxvae_b200 import _lib
+    g = torch.Generator().manual_seed(M + N + K)
+    dY = torch.randn(M, N, generator=g).cuda(); W = torch.randn(N, K, generator=g).cuda()
+    X = torch.randn(M, K, generator=g).cuda()
+    dX = torch.zeros(M, K, device="cuda")
+    _lib.check(lib.dxvae_test_gemm(1, M, N, K, dY.data_ptr(), N, W.data_ptr(), K, dX.data_ptr(), K, None, 0, 0, st()), "dgrad")
+    ref = dY.double() @ W.double()
+    assert (dX.double() - ref).abs().max().item() <= 2e-4 * ref.abs().max().item()
+    _lib.check(lib.dxvae_test_gemm(1, M, N, K, dY.data_ptr(), N, W.data_ptr(), K, dX.data_ptr(), K, None, 0, 1, st()), "dgrad+")
+    assert (dX.double() - 2 * ref).abs().max().item() <= 4e-4 * ref.abs().max().item()
+    dW = torch.zeros(N, K, device="cuda")
+    _lib.check(lib.dxvae_test_gemm(2, M, N, K, dY.data_ptr(), N, X.data_ptr(), K, dW.data_ptr(), K, None, 0, 0, st()), "wgrad")
+    refw = dY.double().t() @ X.double()
+    assert (dW.double() - refw).abs().max().item() <= 2e-4 * refw.abs().max().item()
+
+
+# --------------------------------------------------------------------------- batcher / data formats
+def test_device_schedule_matches_set_logic(lib):
+    from dxvae_b200 import DXVAE
+    from dxvae_b200.dxdata import DXGraphBatch, mask_from_edges
+    m = DXVAE()
+    for n, p, seed in ((5000, 0.2, 1), (1, 0.5, 2), (1025, 0.0, 3), (3000, 1.0, 4), (2048, 0.08, 5)):
+        E = util.random_edge_lists(n, p, seed)
+        ob = O.batch_oracle(E)
+        adj = torch.tensor([mask_from_edges(*e) for e in E], dtype=torch.int64, device="cuda")
+        d = type("D", (), {})()
+        d.B, d.adj, d.level_ptr = n, adj, np.zeros(8, np.int32)
+        m._schedule(d)
+        assert np.array_equal(d.level.cpu().numpy(), ob["level"])
+        assert d.n_levels == len(ob["level_ptr"]) - 1
+        assert np.array_equal(d.level_ptr[:d.n_levels + 1], ob["level_ptr"])
+        assert np.array_equal(d.level_rows.cpu().numpy(), ob["level_rows"])
+
+
+def test_host_batcher_matches_set_logic(lib):
+    from dxvae_b200 import DXVAE
+    from dxvae_b200.dxdata import DXGraph
+    E = util.random_edge_lists(200, 0.2, 9)
+    G = [DXGraph(torch.zeros(7, 27), torch.zeros(7, 21), *e) for e in E]
+    d = DXVAE()._prepare(G)
+    ob = O.batch_oracle(E)
+    assert np.array_equal(d.adj.cpu().numpy().view(np.uint64), ob["adj"])
+    assert np.array_equal(d.csr[0], ob["indptr"]) and np.array_equal(d.csr[1], ob["indices"])
+    assert np.array_equal(d.csr[2], ob["eflags"]) and np.array_equal(d.level, ob["level"])
+    assert np.array_equal(d.level_rows.cpu().numpy(), ob["level_rows"])
+
+
+def test_make_graph_matches_dataset_bin_bit_exact(lib):
+    """dxdata.py:_make_graph on the device == DX_data/DXDataset.bin (golden: SHA-256 of the
+    bin's X / params tensors + its edge lists, written by oracle/make_golden.py)."""
+    from dxvae_b200.dxdata import voices_to_batch
+    v = util.voices()
+    gb = voices_to_batch(v["voices"]).cpu()
+    assert hashlib.sha256(gb.X.numpy().tobytes()).hexdigest() == str(v["X_sha256"])
+    assert hashlib.sha256(gb.params.numpy().tobytes()).hexdigest() == str(v["params_sha256"])
+    assert np.array_equal(gb.X[:64].numpy().view(np.uint32), v["X_first64"].view(np.uint32))
+    ptr, es, ed = v["edge_ptr"], v["edge_src"], v["edge_dst"]
+    A = util.adj_from_masks(gb.adj.numpy().view(np.uint64))
+    for i in range(1024):
+        ref = np.zeros((7, 7), np.uint8)
+        ref[es[ptr[i]:ptr[i + 1]], ed[ptr[i]:ptr[i + 1]]] = 1
+        assert np.array_equal(A[i], ref), i
+
+
+def test_graph_to_syx_matches_reference_file(lib):
+    """dxdata.py:graph_to_syx layout pinned by the reference's generated/gen_patch.syx."""
+    from dxvae_b200.dxdata import graph_to_syx_bytes, read_syx, voices_to_batch
+    path = os.path.join(util.GOLDEN, "gen_patch.syx")
+    gb = voices_to_batch(read_syx(path))
+    assert graph_to_syx_bytes(gb) == open(path, "rb").read()
+    # round trip on every dataset voice: pack(make_graph(v)) reproduces the legal bits of v
+    v = util.voices()["voices"]
+    gb = voices_to_batch(v)
+    out = np.frombuffer(graph_to_syx_bytes(gb)[6:-2], np.uint8).reshape(-1, 128)
+    gb2 = voices_to_batch(out)
+    assert torch.equal(gb.params, gb2.params) and torch.equal(gb.X, gb2.X)
+
+
+# --------------------------------------------------------------------------- encode
+def _encode_cases():
+    idx = list(range(0, 1024, 16))
+    X, P, E, A = util.dataset_graphs(idx)
+    return idx, X, P, E, A
+
+
+def _graphs(X, P, E):
+    from dxvae_b200.dxdata import DXGraph
+    return [DXGraph(X[i], P[i], *E[i]) for i in range(len(E))]
+
+
+@pytest.mark.parametrize("tag,gain", [("init", 1.0), ("stress", 3.0)])
+def test_encode_matches_oracle_and_reference_golden(lib, golden, tag, gain):
+    idx, X, P, E, A = _encode_cases()
+    assert list(golden["subset"]) == idx
+    m, o = make_model(0, gain)
+    with torch.no_grad():
+        q = m.encode(_graphs(X, P, E))
+        mu_o, sd_o = o.encode(X, A)
+    mu, sd = q.loc.cpu(), q.scale.cpu()
+    assert (mu - mu_o).abs().max() <= TOL_LAT and (sd - sd_o).abs().max() <= TOL_LAT
+    assert np.abs(mu.numpy() - golden[tag + "_mu"]).max() <= TOL_LAT
+    assert np.abs(sd.numpy() - golden[tag + "_std"]).max() <= TOL_LAT
+
+
+def test_encode_arbitrary_topologies_and_batch_paths(lib):
+    m, o = make_model(1, 3.0)
+    n = 700
+    idx = list(np.random.default_rng(0).integers(0, 1024, n))
+    X, P, _, _ = util.dataset_graphs(idx)
+    E = util.random_edge_lists(n, 0.3, 21)
+    with torch.no_grad():
+        mu_o, sd_o = o.encode(X, util.adj_dense(E))
+        q = m.encode(_graphs(X, P, E))                       # host batcher path
+        from dxvae_b200.dxdata import DXGraphBatch
+        gb = DXGraphBatch.from_graphs(_graphs(X, P, E))
+        gbd = DXGraphBatch(gb.X.cuda(), gb.params.cuda(), gb.adj.cuda())
+        m.max_chunk = 256                                     # chunked, device scheduler path
+        q2 = m.encode(gbd)
+    assert (q.loc.cpu() - mu_o).abs().max() <= TOL_LAT and (q.scale.cpu() - sd_o).abs().max() <= TOL_LAT
+    assert torch.equal(q.loc, q2.loc) and torch.equal(q.scale, q2.scale)
+
+
+# --------------------------------------------------------------------------- ELBO + gradients
+def _check_grads(m, o, scale=1.0):
+    worst = 0.0
+    named = dict(m.named_parameters())
+    for n, p in o.named_parameters():
+        ref = p.grad
+        got = named[n].grad.cpu() * scale
+        rel = (ref - got).abs().max().item() / (ref.abs().max().item() + 1e-30)
+        worst = max(worst, rel)
+        assert rel <= TOL_GRAD, (n, rel)
+    return worst
+
+
+@pytest.mark.parametrize("tag,gain", [("init", 1.0), ("stress", 3.0)])
+def test_elbo_forward_backward_matches_oracle_and_reference_golden(lib, golden, tag, gain):
+    idx, X, P, E, A = _encode_cases()
+    m, o = make_model(0, gain)
+    G = _graphs(X, P, E)
+    eps = torch.from_numpy(golden[tag + "_eps"])
+    for w, key in (((2, 5, 0.01), "_loss_w2"), ((3, 6, 0.002), "_loss_w3")):
+        m.zero_grad(); o.zero_grad()
+        out = m.forward(G, *w, eps=eps)
+        mu_o, sd_o = o.encode(X, A)
+        lo = o.loss(mu_o, sd_o, X, P, A, eps, *w)
+        for a, b, c in zip(out, lo, golden[tag + key]):
+            assert abs(a.item() - b.item()) <= TOL_LOSS * abs(b.item()) + 1e-7
+            assert abs(a.item() - c) <= TOL_LOSS * abs(c) + 1e-7        # the reference's own numbers
+    out[0].backward(); lo[0].backward()
+    _check_grads(m, o)
+    # gradient fingerprints of the reference run (sampled entries, norms)
+    named = dict(m.named_parameters())
+    for k, n in enumerate(golden[tag + "_grad_names"]):
+        g = named[str(n)].grad.cpu().flatten()
+        vals = g[torch.from_numpy(golden[tag + "_grad_idx"][k])].numpy()
+        ref = golden[tag + "_grad_vals"][k]
+        scale = np.abs(g.numpy()).max() + 1e-30
+        assert np.abs(vals - ref).max() / scale <= TOL_GRAD, n
+        assert abs(g.double().norm().item() - golden[tag + "_grad_norms"][k]) <= 1e-4 * golden[tag + "_grad_norms"][k] + 1e-12
+
+
+def test_split_encode_then_loss_equals_fused_forward(lib):
+    idx = util.pick_by_alg([3, 5, 18, 20, 0, 31, 7, 16])
+    X, P, E, A = util.dataset_graphs(idx)
+    m, o = make_model(2, 3.0)
+    G = _graphs(X, P, E)
+    torch.manual_seed(3)
+    eps = torch.randn(len(G), 128)
+    m.zero_grad()
+    total, *_ = m.forward(G, eps=eps)
+    total.backward()
+    g1 = {n: p.grad.clone() for n, p in m.named_parameters()}
+    m.zero_grad()
+    q = m.encode(G)
+    total2, *_ = m.loss(q, G, eps=eps)
+    total2.backward()
+    assert abs(total.item() - total2.item()) <= 1e-6 * abs(total.item())
+    for n, p in m.named_parameters():
+        ref = g1[n]
+        assert (p.grad - ref).abs().max().item() <= 1e-5 * (ref.abs().max().item() + 1e-30), n
+    # and against the oracle on arbitrary topologies
+    E2 = util.random_edge_lists(len(idx), 0.35, 5)
+    A2 = util.adj_dense(E2)
+    G2 = _graphs(X, P, E2)
+    m.zero_grad(); o.zero_grad()
+    out = m.forward(G2, eps=eps)
+    mu_o, sd_o = o.encode(X, A2)
+    lo = o.loss(mu_o, sd_o, X, P, A2, eps)
+    assert abs(out[0].item() - lo[0].item()) <= TOL_LOSS * abs(lo[0].item())
+    out[0].backward(); lo[0].backward()
+    _check_grads(m, o)
+
+
+def test_adamw_kernel_matches_torch_optimizer(lib):
+    """Same gradients in -> same weights out as torch.optim.AdamW (model.py:375 defaults)."""
+    from dxvae_b200 import _lib
+    g = torch.Generator().manual_seed(0)
+    n = 100003
+    w0 = torch.randn(n, generator=g)
+    p = torch.nn.Parameter(w0.clone())
+    opt = torch.optim.AdamW([p], lr=1e-3)
+    w = w0.clone().cuda(); m = torch.zeros(n, device="cuda"); v = torch.zeros(n, device="cuda")
+    for step in range(1, 6):
+        gr = torch.randn(n, generator=g) * (10.0 ** float(torch.randint(-6, 1, (1,), generator=g)))
+        p.grad = gr.clone()
+        opt.step()
+        gd = gr.cuda()
+        _lib.check(lib.dxvae_adamw_step(n, w.data_ptr(), gd.data_ptr(), m.data_ptr(), v.data_ptr(), 1e-3, 0.9, 0.999,
+                                        1e-8, 0.01, step, 1.0, st()), "adamw")
+        assert (w.cpu() - p.data).abs().max().item() <= 2e-6
+
+
+def test_trainer_trajectory_matches_oracle(lib):
+    from dxvae_b200.train import Trainer
+    idx = list(range(0, 1024, 8))
+    X, P, E, A = util.dataset_graphs(idx)
+    m, o = make_model(0, 1.0)
+    t = Trainer(m, lr=1e-3, w=(2, 5, 0.01))
+    data = t.upload(_graphs(X, P, E))
+    opt = torch.optim.AdamW(o.parameters(), lr=1e-3)
+    torch.manual_seed(11)
+    first = None
+    for step in range(4):
+        eps = torch.randn(len(idx), 128)
+        loss5 = t.step(data, list(range(len(idx))), eps=eps)
+        opt.zero_grad()
+        mu_o, sd_o = o.encode(X, A)
+        lo = o.loss(mu_o, sd_o, X, P, A, eps)
+        lo[0].backward()
+        opt.step()
+        assert abs(loss5[0].item() - lo[0].item()) <= 2e-3 * abs(lo[0].item()), step
+        first = first if first is not None else loss5[0].item()
+    assert loss5[0].item() < first
+
+
+# --------------------------------------------------------------------------- greedy decode
+@pytest.mark.parametrize("tag,gain", [("init", 1.0), ("stress", 3.0)])
+def test_decode_matches_oracle_and_reference_golden(lib, golden, tag, gain):
+    m, o = make_model(0, gain)
+    for zt in ("mu", "prior"):
+        z = torch.from_numpy(golden["%s_dec_%s_z" % (tag, zt)])
+        gb = m.decode(z)
+        Xo, Po, Ao, mg = o.decode(z, return_margins=True)
+        ok = golden["%s_dec_%s_minmargin" % (tag, zt)] > MARGIN          # tie-aware
+        assert ok.sum() >= 0.8 * len(ok)
+        A = util.adj_from_masks(gb.adj.cpu().numpy().view(np.uint64))
+        Pd = gb.params.cpu().numpy().astype(np.int32)
+        assert np.array_equal(A[ok], golden["%s_dec_%s_adj" % (tag, zt)][ok])             # reference topology
+        assert np.array_equal(Pd[ok], golden["%s_dec_%s_params" % (tag, zt)].astype(np.int32)[ok])
+        assert np.abs(gb.X.cpu().numpy() - golden["%s_dec_%s_X" % (tag, zt)])[ok].max() <= 1e-6
+        assert np.array_equal(A[ok], Ao.numpy()[ok])
+        # edge insertion order of the returned graph objects (model.py:237-250)
+        g0 = gb[int(np.nonzero(ok)[0][0])]
+        s, d = g0.edges()
+        assert (s.tolist(), d.tolist()) == O.edges_from_adj(A[int(np.nonzero(ok)[0][0])].tolist())
+        assert np.allclose(m.last_margins.cpu().numpy()[ok],
+                           golden["%s_dec_%s_minmargin" % (tag, zt)][ok], rtol=1e-2, atol=1e-5)
+
+
+def test_decode_large_batch_properties(lib):
+    """Full-size style checks that need no oracle: chunking invariance, legal parameter ranges,
+    decode -> .syx -> _make_graph round trip."""
+    from dxvae_b200.dxdata import graph_to_syx_bytes, voices_to_batch
+    m, _ = make_model(0, 3.0)
+    g = torch.Generator().manual_seed(0)
+    z = torch.randn(20000, 128, generator=g)
+    m.max_chunk = 32768
+    a = m.decode(z)
+    m.max_chunk = 4096
+    b = m.decode(z)
+    assert torch.equal(a.params, b.params) and torch.equal(a.adj, b.adj) and torch.equal(a.X, b.X)
+    P = a.params.cpu().numpy()
+    assert P.min() >= 0 and P[:, 1:, 0:9].max() <= 99 and P[:, 0, 18].max() <= 31 and P[:, 1:, 20].max() <= 2
+    voices = np.frombuffer(graph_to_syx_bytes(a)[6:-2], np.uint8).reshape(-1, 128)
+    back = voices_to_batch(voices)
+    # fc in fixed mode is stored mod 4 by _make_graph but the quantiser already emits 0..3: exact round trip
+    assert torch.equal(back.params.cpu(), a.params.cpu().abs())
+    assert np.abs(back.X.cpu().numpy() - a.X.cpu().numpy()).max() <= 1e-6
