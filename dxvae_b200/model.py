@@ -264,7 +264,9 @@ class DXVAE(nn.Module):
         if eps is None:
             eps = torch.empty(mu.shape, device="cuda").normal_()
         eps = torch.as_tensor(eps).to("cuda", torch.float32).contiguous()
-        out = _LossFn.apply(self, d, eps, (float(w_env), float(w_frq), float(w_kld)), mu, sd, *self._params_tuple())
+        need = torch.is_grad_enabled()
+        out = _LossFn.apply(self, d, eps, (float(w_env), float(w_frq), float(w_kld), need), mu, sd,
+                            *self._params_tuple())
         total, rest = out[0], out[1]
         return total, rest[0], rest[1], rest[2], rest[3]
 
@@ -276,7 +278,8 @@ class DXVAE(nn.Module):
         if eps is None:
             eps = torch.empty(d.B, 128, device="cuda").normal_()
         eps = torch.as_tensor(eps).to("cuda", torch.float32).contiguous()
-        out = _ElboFn.apply(self, d, eps, (float(w_env), float(w_frq), float(w_kld)), *self._params_tuple())
+        need = torch.is_grad_enabled()
+        out = _ElboFn.apply(self, d, eps, (float(w_env), float(w_frq), float(w_kld), need), *self._params_tuple())
         total, rest = out[0], out[1]
         return total, rest[0], rest[1], rest[2], rest[3]
 
@@ -334,7 +337,7 @@ class DXVAE(nn.Module):
 class _ElboFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, model, d, eps, w, *params):
-        need = any(p.requires_grad for p in params) and torch.is_grad_enabled()
+        need = w[3] and any(p.requires_grad for p in params)   # grad mode is off inside forward(): flag from caller
         g = torch.zeros(model._total, device="cuda") if need else None
         loss5 = model.elbo_step(d, eps, w, grads=g)
         ctx.model, ctx.g = model, g
@@ -379,7 +382,7 @@ class _LossFn(torch.autograd.Function):
     def forward(ctx, model, d, eps, w, mu, sd, *params):
         L = _lib.lib()
         mu = mu.detach().contiguous(); sd = sd.detach().contiguous()
-        need = torch.is_grad_enabled()
+        need = w[3]
         g = torch.zeros(model._total, device="cuda") if need else None
         dmu = torch.empty(d.B, 128, device="cuda") if need else None
         dsd = torch.empty(d.B, 128, device="cuda") if need else None
