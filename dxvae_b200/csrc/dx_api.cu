@@ -43,8 +43,9 @@ size_t workspace_bytes(int op, int64_t B) {
 
 // model.py:369-372 forward (= encode + loss) and model.py:385 backward, one call.
 int elbo_step(dx_stream_t st, const float* weights, const Batch& bt, const float* eps, LossW lw, float* loss5,
-              float* mu_out, float* std_out, float* grads, void* ws, size_t ws_bytes) {
+              float* mu_out, float* std_out, float* grads, void* ws, size_t ws_bytes, int precision) {
   const int B = (int)bt.B;
+  PrecisionScope prec(precision);
   Arena ar(ws, ws_bytes);
   TrainWs t = carve_train(ar, bt.B);
   DX_CHECK(!ar.overflow, "elbo_step: workspace too small (%zu < %zu bytes)", ws_bytes, ar.off);
@@ -70,8 +71,9 @@ int elbo_step(dx_stream_t st, const float* weights, const Batch& bt, const float
 // Split form of elbo_step for callers that hold q(z|G) between the two halves
 // (DXVAE.encode(...) followed by DXVAE.loss(q, ...), model.py:370-371).
 int loss_step(dx_stream_t st, const float* weights, const Batch& bt, const float* mu, const float* sd, const float* eps,
-              LossW lw, float* loss5, float* grads, float* dmu, float* dsd, void* ws, size_t ws_bytes) {
+              LossW lw, float* loss5, float* grads, float* dmu, float* dsd, void* ws, size_t ws_bytes, int precision) {
   const int B = (int)bt.B;
+  PrecisionScope prec(precision);
   Arena ar(ws, ws_bytes);
   DecWs d = carve_dec(ar, bt.B, true);
   DX_CHECK(!ar.overflow, "loss_step: workspace too small (%zu < %zu bytes)", ws_bytes, ar.off);
@@ -92,7 +94,8 @@ int loss_step(dx_stream_t st, const float* weights, const Batch& bt, const float
 }
 
 int encode_bwd(dx_stream_t st, const float* weights, const Batch& bt, const float* sd, const float* dmu,
-               const float* dsd, float* grads, void* ws, size_t ws_bytes) {
+               const float* dsd, float* grads, void* ws, size_t ws_bytes, int precision) {
+  PrecisionScope prec(precision);
   Arena ar(ws, ws_bytes);
   EncWs e = carve_enc(ar, bt.B, true);
   DX_CHECK(!ar.overflow, "encode_bwd: workspace too small (%zu < %zu bytes)", ws_bytes, ar.off);
@@ -175,10 +178,12 @@ size_t dxvae_workspace_bytes(int op, int64_t B) { return workspace_bytes(op, B);
 
 int dxvae_encode_fwd(const float* weights, int64_t B, const float* Xn, const uint64_t* adj, int32_t n_levels,
                      const int32_t* level_ptr_host, const int32_t* level_rows, float* mu, float* std_, void* workspace,
-                     size_t workspace_bytes, int keep, void* stream) {
+                     size_t workspace_bytes, int keep, int precision, void* stream) {
   DX_BATCH_OK(B);
   DX_CHECK(n_levels >= 1 && n_levels <= 6, "encode_fwd: n_levels=%d", n_levels);
+  DX_CHECK(precision == PREC_FP32 || precision == PREC_TF32, "encode_fwd: unknown precision %d", precision);
   Batch bt{B, Xn, nullptr, adj, n_levels, level_ptr_host, level_rows};
+  PrecisionScope prec(precision);
   return encode_fwd(DX_ST(stream), weights, bt, mu, std_, workspace, workspace_bytes, keep);
 }
 int dxvae_reparameterize(int64_t n, const float* mu, const float* std_, const float* eps, float* z, void* stream) {
@@ -192,29 +197,34 @@ int dxvae_decode_greedy(const float* weights, int64_t B, const float* z, float* 
 int dxvae_elbo_step(const float* weights, int64_t B, const float* Xn, const int32_t* cls, const uint64_t* adj,
                     int32_t n_levels, const int32_t* level_ptr_host, const int32_t* level_rows, const float* eps,
                     float w_env, float w_frq, float w_kld, float inv_batch, float* loss5, float* mu_out,
-                    float* std_out, float* grads, void* workspace, size_t workspace_bytes, void* stream) {
+                    float* std_out, float* grads, void* workspace, size_t workspace_bytes, int precision,
+                    void* stream) {
   DX_BATCH_OK(B);
   DX_CHECK(n_levels >= 1 && n_levels <= 6, "elbo_step: n_levels=%d", n_levels);
+  DX_CHECK(precision == PREC_FP32 || precision == PREC_TF32, "elbo_step: unknown precision %d", precision);
   Batch bt{B, Xn, cls, adj, n_levels, level_ptr_host, level_rows};
   LossW lw{w_env, w_frq, w_kld, inv_batch};
-  return elbo_step(DX_ST(stream), weights, bt, eps, lw, loss5, mu_out, std_out, grads, workspace, workspace_bytes);
+  return elbo_step(DX_ST(stream), weights, bt, eps, lw, loss5, mu_out, std_out, grads, workspace, workspace_bytes,
+                   precision);
 }
 int dxvae_loss_step(const float* weights, int64_t B, const float* Xn, const int32_t* cls, const uint64_t* adj,
                     const float* mu, const float* std_, const float* eps, float w_env, float w_frq, float w_kld,
                     float inv_batch, float* loss5, float* grads, float* dmu, float* dstd, void* workspace,
-                    size_t workspace_bytes, void* stream) {
+                    size_t workspace_bytes, int precision, void* stream) {
   DX_BATCH_OK(B);
   Batch bt{B, Xn, cls, adj, 0, nullptr, nullptr};
   LossW lw{w_env, w_frq, w_kld, inv_batch};
-  return loss_step(DX_ST(stream), weights, bt, mu, std_, eps, lw, loss5, grads, dmu, dstd, workspace, workspace_bytes);
+  return loss_step(DX_ST(stream), weights, bt, mu, std_, eps, lw, loss5, grads, dmu, dstd, workspace, workspace_bytes,
+                   precision);
 }
 int dxvae_encode_bwd(const float* weights, int64_t B, const float* Xn, const uint64_t* adj, int32_t n_levels,
                      const int32_t* level_ptr_host, const int32_t* level_rows, const float* std_, const float* dmu,
-                     const float* dstd, float* grads, void* workspace, size_t workspace_bytes, void* stream) {
+                     const float* dstd, float* grads, void* workspace, size_t workspace_bytes, int precision,
+                     void* stream) {
   DX_BATCH_OK(B);
   DX_CHECK(n_levels >= 1 && n_levels <= 6, "encode_bwd: n_levels=%d", n_levels);
   Batch bt{B, Xn, nullptr, adj, n_levels, level_ptr_host, level_rows};
-  return encode_bwd(DX_ST(stream), weights, bt, std_, dmu, dstd, grads, workspace, workspace_bytes);
+  return encode_bwd(DX_ST(stream), weights, bt, std_, dmu, dstd, grads, workspace, workspace_bytes, precision);
 }
 int dxvae_adamw_step(int64_t n, float* weights, const float* grads, float* exp_avg, float* exp_avg_sq, float lr,
                      float beta1, float beta2, float eps, float weight_decay, int64_t step, float grad_scale,
@@ -225,7 +235,9 @@ int dxvae_adamw_step(int64_t n, float* weights, const float* grads, float* exp_a
 }
 int dxvae_test_gemm(int variant, int64_t M, int64_t N, int64_t K, const float* A, int64_t lda, const float* Bm,
                     int64_t ldb, float* C, int64_t ldc, const float* bias, int act, int accumulate, void* stream) {
-  // variant 0: y = act(x W^T + b) ; 1: dx (+)= dy W ; 2: dW += dy^T x
+  // variant 0: y = act(x W^T + b) ; 1: dx (+)= dy W ; 2: dW += dy^T x ; +16: tcgen05 TF32 path
+  PrecisionScope prec((variant & 16) ? PREC_TF32 : PREC_FP32);
+  variant &= 15;
   if (variant == 0) linear_fwd(DX_ST(stream), (int)M, (int)N, (int)K, A, lda, Bm, ldb, bias, C, ldc, act);
   else if (variant == 1) linear_dgrad(DX_ST(stream), (int)M, (int)N, (int)K, A, lda, Bm, ldb, C, ldc, accumulate);
   else if (variant == 2) linear_wgrad(DX_ST(stream), (int)M, (int)N, (int)K, A, lda, Bm, ldb, C, ldc);

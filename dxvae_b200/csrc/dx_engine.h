@@ -74,7 +74,7 @@ size_t workspace_bytes(int op, int64_t B);
 int encode_fwd(dx_stream_t st, const float* weights, const Batch& bt, float* mu, float* std_, void* ws, size_t ws_bytes,
                int keep);
 int elbo_step(dx_stream_t st, const float* weights, const Batch& bt, const float* eps, LossW lw, float* loss5,
-              float* mu_out, float* std_out, float* grads, void* ws, size_t ws_bytes);
+              float* mu_out, float* std_out, float* grads, void* ws, size_t ws_bytes, int precision);
 int decode_greedy(dx_stream_t st, const float* weights, int64_t B, const float* z, float* Xg, float* Pg, uint64_t* adj,
                   float* margins, void* ws, size_t ws_bytes);
 

@@ -231,7 +231,7 @@ inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 
 
 // ---- optional per-launch timing of the GEMM family (bench.py roofline) ----------------------
 // CUDA events are recorded on the launching stream around each GEMM while enabled; the pairs
-// are resolved in prof_end().  Class 0 = 128x128 tile kernels, class 1 = 64x64.
+// are resolved in prof_end().  Class 0 = FP32 128x128 tile kernels, 1 = FP32 64x64, 2 = tcgen05 TF32.
 struct ProfState {
   bool on = false;
   int cap = 0, used = 0;
@@ -257,18 +257,10 @@ void launch_tile(dx_stream_t s, const GemmP& p) {
   const bool vecB = aligned16(p.B) && (p.ldb % 4 == 0);
   const bool vecC = aligned16(p.C) && (p.ldc % 4 == 0);
   dim3 grid(gn, gm, splits);
-  int slot = -1;
-  if (g_prof.on && g_prof.used < g_prof.cap) {
-    slot = g_prof.used++;
-    g_prof.flops[slot] = 2.0 * p.M * (double)p.N * p.K;
-    g_prof.cls[slot] = BM >= 128 ? 0 : 1;
-    cudaEventRecord(g_prof.e0[slot], s);
-  }
   if (p.a_kc && p.b_kc) k_gemm<BM, BN, TM, TN, true, true><<<grid, 256, 0, s>>>(p, k_chunk, vecA, vecB, vecC);
   else if (p.a_kc && !p.b_kc) k_gemm<BM, BN, TM, TN, true, false><<<grid, 256, 0, s>>>(p, k_chunk, vecA, vecB, vecC);
   else if (!p.a_kc && !p.b_kc) k_gemm<BM, BN, TM, TN, false, false><<<grid, 256, 0, s>>>(p, k_chunk, vecA, vecB, vecC);
   else k_gemm<BM, BN, TM, TN, false, true><<<grid, 256, 0, s>>>(p, k_chunk, vecA, vecB, vecC);
-  if (slot >= 0) cudaEventRecord(g_prof.e1[slot], s);
   ++g_launches;
 }
 
@@ -303,12 +295,13 @@ void prof_begin(int max_launches) {
   for (int i = 0; i < max_launches; ++i) { cudaEventCreate(&g_prof.e0[i]); cudaEventCreate(&g_prof.e1[i]); }
   g_prof.on = true;
 }
-// ms[2], flops[2], n[2]: totals per tile class.  Synchronises the device.
+// ms[3], flops[3], n[3]: totals per kernel class.  Synchronises the device.
 void prof_end(double* ms, double* flops, long long* n) {
+  for (int c = 0; c < 3; ++c) { if (ms) ms[c] = 0; if (flops) flops[c] = 0; if (n) n[c] = 0; }
   if (!g_prof.e0) return;
   g_prof.on = false;
   cudaDeviceSynchronize();
-  double tms[2] = {0, 0}, tfl[2] = {0, 0}; long long tn[2] = {0, 0};
+  double tms[3] = {0, 0, 0}, tfl[3] = {0, 0, 0}; long long tn[3] = {0, 0, 0};
   for (int i = 0; i < g_prof.used; ++i) {
     float t = 0.f;
     if (cudaEventElapsedTime(&t, g_prof.e0[i], g_prof.e1[i]) == cudaSuccess) {
@@ -318,16 +311,29 @@ void prof_end(double* ms, double* flops, long long* n) {
   for (int i = 0; i < g_prof.cap; ++i) { cudaEventDestroy(g_prof.e0[i]); cudaEventDestroy(g_prof.e1[i]); }
   delete[] g_prof.e0; delete[] g_prof.e1; delete[] g_prof.flops; delete[] g_prof.cls;
   g_prof = ProfState();
-  for (int c = 0; c < 2; ++c) { if (ms) ms[c] = tms[c]; if (flops) flops[c] = tfl[c]; if (n) n[c] = tn[c]; }
+  for (int c = 0; c < 3; ++c) { if (ms) ms[c] = tms[c]; if (flops) flops[c] = tfl[c]; if (n) n[c] = tn[c]; }
 }
+
+thread_local int g_precision = PREC_FP32;
+void set_precision(int prec) { g_precision = prec; }
+int get_precision() { return g_precision; }
 
 void gemm(dx_stream_t s, const GemmP& p) {
   if (p.M <= 0 || p.N <= 0 || p.K <= 0) return;
+  int slot = -1;
+  if (g_prof.on && g_prof.used < g_prof.cap) {
+    slot = g_prof.used++;
+    g_prof.flops[slot] = 2.0 * p.M * (double)p.N * p.K;
+    cudaEventRecord(g_prof.e0[slot], s);
+  }
+  int cls;
   // Large tile when both output extents fill it; otherwise 64x64 so small batches
   // (B=128) and narrow heads (N=27/55/2/1) still spread over the SMs.
   const bool big = (p.M >= 512 && p.N >= 96);
-  if (big) launch_tile<128, 128, 8, 8>(s, p);
-  else launch_tile<64, 64, 4, 4>(s, p);
+  if (g_precision == PREC_TF32 && tc_gemm(s, p, nullptr)) cls = 2;
+  else if (big) { launch_tile<128, 128, 8, 8>(s, p); cls = 0; }
+  else { launch_tile<64, 64, 4, 4>(s, p); cls = 1; }
+  if (slot >= 0) { g_prof.cls[slot] = cls; cudaEventRecord(g_prof.e1[slot], s); }
 }
 
 void colsum_accum(dx_stream_t s, int M, int N, const float* dy, int64_t lddy, float* db, const int* dy_idx) {
@@ -372,8 +378,11 @@ void gemm(dx_stream_t, const GemmP& p) {
 
 void prof_begin(int) {}
 void prof_end(double* ms, double* flops, long long* n) {
-  for (int c = 0; c < 2; ++c) { if (ms) ms[c] = 0; if (flops) flops[c] = 0; if (n) n[c] = 0; }
+  for (int c = 0; c < 3; ++c) { if (ms) ms[c] = 0; if (flops) flops[c] = 0; if (n) n[c] = 0; }
 }
+static thread_local int g_precision = PREC_FP32;
+void set_precision(int prec) { g_precision = prec; }
+int get_precision() { return g_precision; }
 
 void colsum_accum(dx_stream_t, int M, int N, const float* dy, int64_t lddy, float* db, const int* dy_idx) {
   for (int j = 0; j < N; ++j) {

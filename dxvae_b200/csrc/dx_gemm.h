@@ -30,6 +30,18 @@ struct GemmP {
   int accum = ACC_STORE;
 };
 
+enum { PREC_FP32 = 0, PREC_TF32 = 1 };
+// Arithmetic of the dense products issued by this thread: PREC_FP32 = FFMA kernels (bit-stable,
+// used by decode / inference), PREC_TF32 = tcgen05 tensor cores where the shape is eligible.
+void set_precision(int prec);
+int get_precision();
+struct PrecisionScope {
+  int prev;
+  explicit PrecisionScope(int p) : prev(get_precision()) { set_precision(p); }
+  ~PrecisionScope() { set_precision(prev); }
+};
+bool tc_gemm(dx_stream_t s, const GemmP& p, int* tile_n);   // dx_tc_gemm.cu; false = not eligible
+
 void gemm(dx_stream_t s, const GemmP& p);
 void prof_begin(int max_launches);
 void prof_end(double* ms, double* flops, long long* n);

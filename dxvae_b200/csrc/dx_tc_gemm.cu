@@ -1,0 +1,322 @@
+// tcgen05 / TMA GEMM for sm_100a: the large dense contractions of the TRAINING path
+// (GRU gate products, gate/mapper and edge-head projections, MLP layers and their
+// dgrad / wgrad) on the 5th-generation tensor cores with TF32 inputs and FP32
+// accumulation in TMEM.
+//
+//   C[M,N] (op)= act( sum_r Aop(i,r) Bop(r,j) + bias[j] + add[i,j] )      (same contract as dx_gemm.h)
+//
+// One CTA per 128 x BN output tile (BN = 256 or 128), 192 threads:
+//   warp 0   : TMA producer  (cp.async.bulk.tensor, 128B swizzle, mbarrier complete_tx)
+//   warp 1   : TMEM allocation + single-thread tcgen05.mma issue, tcgen05.commit -> mbarriers
+//   warps 2-5: epilogue (tcgen05.ld 32x32b -> registers -> bias/act -> global, one row per thread)
+// Operands stay fp32 in HBM; the tensor map's TFLOAT32 type rounds on load.  Both operand
+// majors are native (no physical transposes): K-major tiles are one 2-D box of
+// [rows x 32 floats]; MN-major tiles (dgrad's W, wgrad's dy and x) are 32x32 boxes laid out as
+// SWIZZLE_128B_BASE32B MN-major atoms (TMA swizzle 128B_ATOM_32B; SBO = 512 B between 4-row k
+// groups, LBO = 4096 B between 32-element MN groups) — the only MN-major layout tf32 accepts.  Reduction splits (wgrad) use blockIdx.z + atomic epilogue.
+//
+// Roofline: tensor pipe (kind::tf32 = 1/2 of the bf16 rate), fed from L2: a 128x256x32 stage is
+// 48 KB per 512 MMA cycles.
+#include "dx_gemm.h"
+
+#ifndef DX_EMU
+#include <cuda.h>
+
+namespace dx {
+namespace {
+
+constexpr int TBM = 128, TBK = 32;           // 32 fp32 = one 128-byte swizzle row
+constexpr int A_BYTES = TBM * TBK * 4;       // 16 KB
+
+template <int BN> struct TcCfg {
+  static constexpr int B_BYTES = BN * TBK * 4;
+  static constexpr int STAGE = A_BYTES + B_BYTES;
+  static constexpr int STAGES = (BN == 256) ? 4 : 6;
+  static constexpr int SMEM = STAGES * STAGE + 1024 /*align*/ + 256 /*barriers*/;
+};
+
+struct TcParams {
+  int M, N, K;
+  float* C; int64_t ldc; const int* c_idx;
+  const float* bias; const float* add; int64_t ldadd;
+  int act, accum, k_chunk;
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P1;\n\t"
+      "WAIT_LOOP:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
+      "@P1 bra.uni WAIT_DONE;\n\t"
+      "bra.uni WAIT_LOOP;\n\t"
+      "WAIT_DONE:\n\t"
+      "}" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint32_t dst, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1) : "memory");
+}
+// SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor layout)
+// layout_type: 2 = SWIZZLE_128B (K-major tiles), 1 = SWIZZLE_128B_BASE32B (the only layout the
+// hardware accepts for MN-major tf32 operands: 4-row x 128-byte atoms, 32-byte swizzle granules).
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout_type) {
+  return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16) |
+         ((uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32) | (1ull << 46) /*version*/ | ((uint64_t)layout_type << 61);
+}
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
+  uint32_t* r = reinterpret_cast<uint32_t*>(v);
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr) : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ float tc_act(float v, int act) {
+  if (act == ACT_RELU) return v > 0.f ? v : 0.f;
+  if (act == ACT_TANH) return tanhf(v);
+  if (act == ACT_SOFTPLUS) return softplusf_(v);
+  return v;
+}
+
+template <int BN, bool A_MN, bool B_MN>
+__global__ void __launch_bounds__(192, 1) k_tc_gemm(const __grid_constant__ CUtensorMap tmA,
+                                                    const __grid_constant__ CUtensorMap tmB, const TcParams p) {
+  using Cfg = TcCfg<BN>;
+  constexpr int S = Cfg::STAGES;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;       // SWIZZLE_128B atoms need 1024-byte alignment
+  const uint32_t bars = base + S * Cfg::STAGE;                        // full[S], empty[S], tmem_full, tmem slot
+  auto full_bar = [&](int s) { return bars + 8u * s; };
+  auto empty_bar = [&](int s) { return bars + 8u * (S + s); };
+  const uint32_t tmem_full = bars + 8u * (2 * S);
+  const uint32_t tmem_slot = bars + 8u * (2 * S + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m0 = blockIdx.y * TBM, n0 = blockIdx.x * BN;
+  const int kbeg = blockIdx.z * p.k_chunk;
+  const int kend = min(p.K, kbeg + p.k_chunk);
+  const int nkb = (kend - kbeg + TBK - 1) / TBK;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < S; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    mbar_init(tmem_full, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(BN) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  uint32_t tmem_base;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+  if (warp == 0) {
+    if (lane == 0) {                                               // ---- TMA producer
+      for (int kb = 0; kb < nkb; ++kb) {
+        const int s = kb % S;
+        mbar_wait(empty_bar(s), ((kb / S) & 1) ^ 1);
+        mbar_expect_tx(full_bar(s), Cfg::STAGE);
+        const int k0 = kbeg + kb * TBK;
+        const uint32_t sa = base + s * Cfg::STAGE, sb = sa + A_BYTES;
+        if (!A_MN) tma_load_2d(&tmA, sa, full_bar(s), k0, m0);
+        else
+#pragma unroll
+          for (int g = 0; g < TBM / 32; ++g) tma_load_2d(&tmA, sa + g * 4096, full_bar(s), m0 + g * 32, k0);
+        if (!B_MN) tma_load_2d(&tmB, sb, full_bar(s), k0, n0);
+        else
+#pragma unroll
+          for (int g = 0; g < BN / 32; ++g) tma_load_2d(&tmB, sb + g * 4096, full_bar(s), n0 + g * 32, k0);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {                                               // ---- MMA issuer
+      // instruction descriptor: D=F32, A=B=TF32, majors, N>>3, M>>4   (cute::UMMA::InstrDescriptor)
+      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((A_MN ? 1u : 0u) << 15) | ((B_MN ? 1u : 0u) << 16) |
+                             ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TBM >> 4) << 24);
+      for (int kb = 0; kb < nkb; ++kb) {
+        const int s = kb % S;
+        mbar_wait(full_bar(s), (kb / S) & 1);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t sa = base + s * Cfg::STAGE, sb = sa + A_BYTES;
+#pragma unroll
+        for (int k = 0; k < TBK / 8; ++k) {                        // UMMA_K = 8 for tf32
+          // K-major: 8-row x 128 B atoms, SBO 1024; one UMMA_K = 32 B along the swizzled row.
+          // MN-major: 4-row atoms (SBO 512 B), 32-element MN groups 4096 B apart (LBO); UMMA_K = 8 rows.
+          const uint64_t ad = A_MN ? umma_desc(sa + k * 1024, 4096, 512, 1) : umma_desc(sa + k * 32, 16, 1024, 2);
+          const uint64_t bd = B_MN ? umma_desc(sb + k * 1024, 4096, 512, 1) : umma_desc(sb + k * 32, 16, 1024, 2);
+          umma_tf32(tmem_base, ad, bd, idesc, (kb | k) != 0 ? 1u : 0u);
+        }
+        umma_commit(empty_bar(s));                                 // frees the smem stage when these MMAs retire
+      }
+      umma_commit(tmem_full);                                      // accumulator complete
+    }
+  } else {                                                         // ---- epilogue: warps 2..5
+    mbar_wait(tmem_full, 0);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const int q = warp & 3;                                        // TMEM lane quadrant this warp may read
+    const int gi = m0 + q * 32 + lane;
+    const bool row_ok = gi < p.M;
+    const int64_t crow = row_ok ? (p.c_idx ? p.c_idx[gi] : gi) : 0;
+    float* crow_p = p.C + crow * p.ldc;
+    const float* arow_p = (p.add && row_ok) ? p.add + (int64_t)gi * p.ldadd : nullptr;
+    const bool vec = ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0) && (p.ldc % 4 == 0);
+#pragma unroll 1
+    for (int c = 0; c < BN; c += 32) {
+      float v[32];
+      tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c, v);
+      const int gj = n0 + c;
+      if (!row_ok || gj >= p.N) continue;
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        if (gj + j < p.N) {
+          float t = v[j];
+          if (p.bias) t += __ldg(p.bias + gj + j);
+          if (arow_p) t += __ldg(arow_p + gj + j);
+          v[j] = tc_act(t, p.act);
+        }
+      }
+      if (p.accum == ACC_ATOMIC) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (gj + j < p.N) atomicAdd(crow_p + gj + j, v[j]);
+      } else if (vec && gj + 31 < p.N) {
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+          float4* dst = reinterpret_cast<float4*>(crow_p + gj + j);
+          float4 o = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+          if (p.accum == ACC_ADD) { const float4 old = *dst; o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w; }
+          *dst = o;
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (gj + j < p.N) { if (p.accum == ACC_ADD) crow_p[gj + j] += v[j]; else crow_p[gj + j] = v[j]; }
+      }
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(BN) : "memory");
+  }
+}
+
+// ---- host side: tensor maps through the driver entry point (no link-time libcuda dependency)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+// 2-D fp32 tensor [rows][cols] with row pitch ld (floats); box = box_cols x box_rows
+bool make_map(CUtensorMap* m, const float* ptr, int64_t rows, int64_t cols, int64_t ld, int box_cols, int box_rows,
+              bool mn_major) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) return false;
+  cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t gstr[1] = {(cuuint64_t)ld * 4};
+  cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  return enc(m, CU_TENSOR_MAP_DATA_TYPE_TFLOAT32, 2, const_cast<float*>(ptr), gdim, gstr, box, estr,
+             CU_TENSOR_MAP_INTERLEAVE_NONE, mn_major ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+             CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+template <int BN>
+bool launch_tc(dx_stream_t s, const GemmP& g) {
+  using Cfg = TcCfg<BN>;
+  CUtensorMap ta, tb;
+  // K-major: memory [MN rows][reduction cols]; MN-major: memory [reduction rows][MN cols]
+  if (g.a_kc) { if (!make_map(&ta, g.A, g.M, g.K, g.lda, TBK, TBM, false)) return false; }
+  else        { if (!make_map(&ta, g.A, g.K, g.M, g.lda, 32, TBK, true)) return false; }
+  if (g.b_kc) { if (!make_map(&tb, g.B, g.N, g.K, g.ldb, TBK, BN, false)) return false; }
+  else        { if (!make_map(&tb, g.B, g.K, g.N, g.ldb, 32, TBK, true)) return false; }
+  const int gm = (g.M + TBM - 1) / TBM, gn = (g.N + BN - 1) / BN;
+  int splits = 1;
+  if (g.accum == ACC_ATOMIC) {
+    const int tiles = gm * gn;
+    const int want = (148 * 2 + tiles - 1) / tiles;
+    const int maxs = (g.K + TBK * 16 - 1) / (TBK * 16);       // >= 512 reduction rows per split
+    splits = want < 1 ? 1 : (want > maxs ? maxs : want);
+  }
+  int k_chunk = (g.K + splits - 1) / splits;
+  k_chunk = (k_chunk + TBK - 1) / TBK * TBK;
+  splits = (g.K + k_chunk - 1) / k_chunk;
+  TcParams p{g.M, g.N, g.K, g.C, g.ldc, g.c_idx, g.bias, g.add, g.ldadd, g.act, g.accum, k_chunk};
+  dim3 grid(gn, gm, splits);
+  static bool attr_set = false;   // per BN instantiation; all four operand-major variants share the footprint
+  if (!attr_set) {
+    cudaFuncSetAttribute(k_tc_gemm<BN, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM);
+    cudaFuncSetAttribute(k_tc_gemm<BN, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM);
+    cudaFuncSetAttribute(k_tc_gemm<BN, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM);
+    cudaFuncSetAttribute(k_tc_gemm<BN, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM);
+    attr_set = true;
+  }
+  auto run = [&](auto kern) { kern<<<grid, 192, Cfg::SMEM, s>>>(ta, tb, p); };
+  if (g.a_kc && g.b_kc) run(k_tc_gemm<BN, false, false>);
+  else if (g.a_kc && !g.b_kc) run(k_tc_gemm<BN, false, true>);
+  else if (!g.a_kc && !g.b_kc) run(k_tc_gemm<BN, true, true>);
+  else run(k_tc_gemm<BN, true, false>);
+  ++g_launches;
+  return true;
+}
+
+inline bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+}  // namespace
+
+// Returns false when the problem is not eligible (caller falls back to the FP32 SIMT kernel).
+bool tc_gemm(dx_stream_t s, const GemmP& g, int* tile_n) {
+  if (g.a_idx || g.b_idx) return false;                       // TMA tiles cannot gather rows
+  if (g.M < 128 || g.N < 64 || g.K < 32) return false;
+  if (!al16(g.A) || !al16(g.B) || (g.lda % 4) || (g.ldb % 4)) return false;
+  const bool big = g.N >= 192;
+  if (tile_n) *tile_n = big ? 256 : 128;
+  return big ? launch_tc<256>(s, g) : launch_tc<128>(s, g);
+}
+
+}  // namespace dx
+#else
+namespace dx {
+bool tc_gemm(dx_stream_t, const GemmP&, int*) { return false; }
+}  // namespace dx
+#endif

@@ -69,6 +69,10 @@ class DXVAE(nn.Module):
         self.max_chunk = 32768      # graphs per kernel pass for encode / decode
         self.verbose = True
         self.last_margins = None
+        # arithmetic of the training products: "fp32" (FFMA, reference-tolerance parity) or "tf32"
+        # (tcgen05 tensor cores, looser stated tolerance).  Encode for inference and greedy decode
+        # always run in fp32 so their outputs match the reference's decisions.
+        self.precision = "fp32"
         if checkpoint is not None:
             self.load_state_dict(torch.load(checkpoint, map_location=self.device))
 
@@ -95,6 +99,11 @@ class DXVAE(nn.Module):
             self._flat = flat
             self.device = "cuda"
         return L
+
+    def _prec(self):
+        if self.precision not in ("fp32", "tf32"):
+            raise ValueError("precision must be 'fp32' or 'tf32'")
+        return _abi.PREC_TF32 if self.precision == "tf32" else _abi.PREC_FP32
 
     def _workspace(self, op, B, fresh=False):
         L = _lib.lib()
@@ -201,7 +210,7 @@ class DXVAE(nn.Module):
             ws = self._workspace(_abi.OP_ENCODE, d.B)
             _lib.check(L.dxvae_encode_fwd(self._flat.data_ptr(), d.B, d.Xn.data_ptr(), d.adj.data_ptr(), d.n_levels,
                                           d.level_ptr.ctypes.data, d.level_rows.data_ptr(), mu[lo:hi].data_ptr(),
-                                          sd[lo:hi].data_ptr(), ws.data_ptr(), ws.numel(), 0, _stream()),
+                                          sd[lo:hi].data_ptr(), ws.data_ptr(), ws.numel(), 0, _abi.PREC_FP32, _stream()),
                        "dxvae_encode_fwd")
         return Normal(mu, sd, validate_args=False)
 
@@ -294,7 +303,8 @@ class DXVAE(nn.Module):
             d.level_ptr.ctypes.data, d.level_rows.data_ptr(), eps.data_ptr(), w[0], w[1], w[2],
             (1.0 / d.B) if inv_batch is None else inv_batch, loss5.data_ptr(),
             None if mu_out is None else mu_out.data_ptr(), None if std_out is None else std_out.data_ptr(),
-            None if grads is None else grads.data_ptr(), ws.data_ptr(), ws.numel(), _stream()), "dxvae_elbo_step")
+            None if grads is None else grads.data_ptr(), ws.data_ptr(), ws.numel(), self._prec(), _stream()),
+            "dxvae_elbo_step")
         return loss5
 
     # ------------------------------------------------------------------ train
@@ -359,7 +369,7 @@ class _EncodeFn(torch.autograd.Function):
         mu = torch.empty(d.B, 128, device="cuda"); sd = torch.empty(d.B, 128, device="cuda")
         _lib.check(L.dxvae_encode_fwd(model._flat.data_ptr(), d.B, d.Xn.data_ptr(), d.adj.data_ptr(), d.n_levels,
                                       d.level_ptr.ctypes.data, d.level_rows.data_ptr(), mu.data_ptr(), sd.data_ptr(),
-                                      ws.data_ptr(), ws.numel(), 1, _stream()), "dxvae_encode_fwd")
+                                      ws.data_ptr(), ws.numel(), 1, model._prec(), _stream()), "dxvae_encode_fwd")
         ctx.model, ctx.d, ctx.ws, ctx.sd = model, d, ws, sd
         return mu, sd
 
@@ -373,7 +383,7 @@ class _EncodeFn(torch.autograd.Function):
         _lib.check(L.dxvae_encode_bwd(model._flat.data_ptr(), d.B, d.Xn.data_ptr(), d.adj.data_ptr(), d.n_levels,
                                       d.level_ptr.ctypes.data, d.level_rows.data_ptr(), ctx.sd.data_ptr(),
                                       dmu.data_ptr(), dsd.data_ptr(), g.data_ptr(), ctx.ws.data_ptr(), ctx.ws.numel(),
-                                      _stream()), "dxvae_encode_bwd")
+                                      model._prec(), _stream()), "dxvae_encode_bwd")
         return (None, None) + model._grad_views(g)
 
 
@@ -392,7 +402,8 @@ class _LossFn(torch.autograd.Function):
             model._flat.data_ptr(), d.B, d.Xn.data_ptr(), d.cls.data_ptr(), d.adj.data_ptr(), mu.data_ptr(),
             sd.data_ptr(), eps.data_ptr(), w[0], w[1], w[2], 1.0 / d.B, loss5.data_ptr(),
             None if g is None else g.data_ptr(), None if dmu is None else dmu.data_ptr(),
-            None if dsd is None else dsd.data_ptr(), ws.data_ptr(), ws.numel(), _stream()), "dxvae_loss_step")
+            None if dsd is None else dsd.data_ptr(), ws.data_ptr(), ws.numel(), model._prec(), _stream()),
+            "dxvae_loss_step")
         ctx.model, ctx.g, ctx.dmu, ctx.dsd = model, g, dmu, dsd
         total, rest = loss5[0].clone(), loss5[1:].clone()
         ctx.mark_non_differentiable(rest)

@@ -53,9 +53,10 @@ const char* dxvae_last_error(void);
 /* number of kernels this library has launched in this process (bench.py's gpu_launches) */
 long long dxvae_launch_count(void);
 /* per-launch CUDA-event timing of the GEMM kernel family (bench.py roofline): totals per tile
- * class (0: 128x128 tiles, 1: 64x64) of device ms, executed flops (2MNK) and launches. */
+ * class (0: FP32 128x128 tiles, 1: FP32 64x64, 2: tcgen05 TF32) of device ms, executed flops
+ * (2MNK) and launches; each output array has 3 entries. */
 void dxvae_prof_begin(int max_launches);
-void dxvae_prof_end(double* ms2, double* flops2, long long* n2);
+void dxvae_prof_end(double* ms3, double* flops3, long long* n3);
 
 /* ---- parameter blob (state_dict of model.py:24-72) ------------- */
 typedef struct {
@@ -103,6 +104,14 @@ int dxvae_voices_to_graphs(int64_t B, const uint8_t* voices, float* Xn, int32_t*
  * (header/name/trailer bytes are added by the host wrapper). */
 int dxvae_pack_syx(int64_t B, const float* Pg, uint8_t* voices, void* stream);
 
+/* ---- arithmetic of the dense products ---------------------------------------------- *
+ * DXVAE_PREC_FP32: FP32 FFMA kernels everywhere (reference-tolerance parity; the only mode of
+ *                  greedy decode, whose discrete outputs must match the reference exactly).
+ * DXVAE_PREC_TF32: eligible products (rows >= 128, N >= 64, K >= 32, no row gather) run on the
+ *                  tcgen05 tensor cores with TF32 inputs / FP32 accumulation; looser, stated
+ *                  tolerance. */
+enum { DXVAE_PREC_FP32 = 0, DXVAE_PREC_TF32 = 1 };
+
 /* ---- workspace sizes ------------------------------------------------------------ */
 enum { DXVAE_OP_ENCODE = 0, DXVAE_OP_DECODE = 1, DXVAE_OP_TRAIN = 2, DXVAE_OP_SCHEDULE = 3,
        DXVAE_OP_ENCODE_TRAIN = 4, DXVAE_OP_LOSS = 5 };
@@ -114,7 +123,7 @@ size_t dxvae_workspace_bytes(int op, int64_t B);
  * (workspace must then be the DXVAE_OP_TRAIN one). */
 int dxvae_encode_fwd(const float* weights, int64_t B, const float* Xn, const uint64_t* adj, int32_t n_levels,
                      const int32_t* level_ptr_host, const int32_t* level_rows, float* mu, float* std_,
-                     void* workspace, size_t workspace_bytes, int keep, void* stream);
+                     void* workspace, size_t workspace_bytes, int keep, int precision, void* stream);
 
 /* ---- reparameterise (model.py:284, Normal.rsample): z = mu + std*eps -------------- */
 int dxvae_reparameterize(int64_t n, const float* mu, const float* std_, const float* eps, float* z, void* stream);
@@ -138,7 +147,8 @@ int dxvae_decode_greedy(const float* weights, int64_t B, const float* z, float* 
 int dxvae_elbo_step(const float* weights, int64_t B, const float* Xn, const int32_t* cls, const uint64_t* adj,
                     int32_t n_levels, const int32_t* level_ptr_host, const int32_t* level_rows, const float* eps,
                     float w_env, float w_frq, float w_kld, float inv_batch, float* loss5, float* mu_out,
-                    float* std_out, float* grads, void* workspace, size_t workspace_bytes, void* stream);
+                    float* std_out, float* grads, void* workspace, size_t workspace_bytes, int precision,
+                    void* stream);
 
 /* Split form of dxvae_elbo_step, for DXVAE.encode(G) followed by DXVAE.loss(q, G)
  * (model.py:370-371).  encode_fwd(keep=1, workspace of DXVAE_OP_ENCODE_TRAIN) leaves the
@@ -148,10 +158,11 @@ int dxvae_elbo_step(const float* weights, int64_t B, const float* Xn, const int3
 int dxvae_loss_step(const float* weights, int64_t B, const float* Xn, const int32_t* cls, const uint64_t* adj,
                     const float* mu, const float* std_, const float* eps, float w_env, float w_frq, float w_kld,
                     float inv_batch, float* loss5, float* grads, float* dmu, float* dstd, void* workspace,
-                    size_t workspace_bytes, void* stream);
+                    size_t workspace_bytes, int precision, void* stream);
 int dxvae_encode_bwd(const float* weights, int64_t B, const float* Xn, const uint64_t* adj, int32_t n_levels,
                      const int32_t* level_ptr_host, const int32_t* level_rows, const float* std_, const float* dmu,
-                     const float* dstd, float* grads, void* workspace, size_t workspace_bytes, void* stream);
+                     const float* dstd, float* grads, void* workspace, size_t workspace_bytes, int precision,
+                     void* stream);
 
 /* ---- optimiser (model.py:375,386: torch.optim.AdamW defaults) -------------------- */
 int dxvae_adamw_step(int64_t n, float* weights, const float* grads, float* exp_avg, float* exp_avg_sq, float lr,
@@ -159,7 +170,8 @@ int dxvae_adamw_step(int64_t n, float* weights, const float* grads, float* exp_a
                      void* stream);
 
 /* ---- low-level pieces exported for unit tests ------------------------------------ *
- * C[M,N] = act(A[M,K] * W[N,K]^T + bias)  (act: 0 none, 1 relu, 2 tanh, 4 softplus) */
+ * variant 0: C[M,N] = act(A[M,K] W[N,K]^T + bias) (act: 0 none, 1 relu, 2 tanh, 4 softplus);
+ * 1: dgrad C[M,K] (+)= A[M,N] W[N,K]; 2: wgrad C[N,K] += A[M,N]^T B[M,K]; +16: TF32 tensor-core path */
 int dxvae_test_gemm(int variant, int64_t M, int64_t N, int64_t K, const float* A, int64_t lda, const float* Bm,
                     int64_t ldb, float* C, int64_t ldc, const float* bias, int act, int accumulate, void* stream);
 

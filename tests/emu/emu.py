@@ -19,7 +19,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
 SRC = os.path.join(ROOT, "dxvae_b200", "csrc")
 OUT = os.path.join(HERE, "_build", "libdxvae_emu.so")
-FILES = ["dx_gemm.cu", "dx_encoder.cu", "dx_decoder.cu", "dx_data.cu", "dx_api.cu"]
+FILES = ["dx_gemm.cu", "dx_tc_gemm.cu", "dx_encoder.cu", "dx_decoder.cu", "dx_data.cu", "dx_api.cu"]
 
 
 def build():
@@ -87,7 +87,7 @@ class Emu:
         mu = np.zeros((B, 128), np.float32); sd = np.zeros((B, 128), np.float32)
         _abi.check(L, L.dxvae_encode_fwd(ptr(self.blob), B, ptr(bt["Xn"]), ptr(bt["adj"]), bt["n_levels"],
                                          ptr(bt["level_ptr"]), ptr(bt["level_rows"]), ptr(mu), ptr(sd), ptr(ws),
-                                         ws.nbytes, 0, None), "encode")
+                                         ws.nbytes, 0, 0, None), "encode")
         return mu, sd
 
     def elbo(self, bt, eps, w=(2, 5, 0.01), inv_batch=None, grads=True):
@@ -101,7 +101,7 @@ class Emu:
         _abi.check(L, L.dxvae_elbo_step(ptr(self.blob), B, ptr(bt["Xn"]), ptr(bt["cls"]), ptr(bt["adj"]),
                                         bt["n_levels"], ptr(bt["level_ptr"]), ptr(bt["level_rows"]), ptr(eps),
                                         w[0], w[1], w[2], inv_batch or 1.0 / B, ptr(loss5), ptr(mu), ptr(sd), ptr(g),
-                                        ptr(ws), ws.nbytes, None), "elbo")
+                                        ptr(ws), ws.nbytes, 0, None), "elbo")
         return loss5, mu, sd, g
 
     def decode(self, z):

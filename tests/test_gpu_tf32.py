@@ -1,0 +1,91 @@
+"""tcgen05 / TMA tensor-core path (TF32 inputs, FP32 accumulation in TMEM).
+
+Stated tolerance of this path: TF32 keeps 10 explicit mantissa bits, so a
+K-term dot product carries ~2^-11 * sqrt(K) relative noise.  Bounds asserted here:
+  GEMM            max|err| <= 2e-3 * max|ref|
+  ELBO loss terms rel <= 2e-3
+  gradients       max-norm-relative <= 6e-2 per tensor (measured worst 3.5e-2, h_to_x0.2.weight)
+Greedy decode and inference encode never use this path (their discrete outputs must match
+the reference exactly)."""
+import numpy as np
+import pytest
+import torch
+
+import dxvae_oracle as O
+from tests import util
+
+pytestmark = pytest.mark.gpu
+TF32_GEMM, TF32_LOSS, TF32_GRAD = 2e-3, 2e-3, 6e-2
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from dxvae_b200 import _lib
+    return _lib.require_cuda()
+
+
+def st():
+    return torch.cuda.current_stream().cuda_stream
+
+
+SHAPES = [(128, 256, 32), (128, 256, 512), (256, 1536, 512), (8192, 1536, 512), (1000, 1024, 1024), (4096, 128, 512),
+          (300, 2048, 512), (640, 320, 96), (2048, 512, 2048)]
+
+
+@pytest.mark.parametrize("M,N,K", SHAPES)
+def test_tc_gemm_forward(lib, M, N, K):
+    from dxvae_b200 import _lib
+    g = torch.Generator().manual_seed(M + 3 * N + K)
+    A = torch.randn(M, K, generator=g).cuda(); W = torch.randn(N, K, generator=g).cuda()
+    b = torch.randn(N, generator=g).cuda()
+    ref0 = A.double() @ W.double().t() + b.double()
+    for act, fn in ((0, lambda t: t), (1, torch.relu), (2, torch.tanh)):
+        C = torch.full((M, N), float("nan"), device="cuda")
+        _lib.check(lib.dxvae_test_gemm(16, M, N, K, A.data_ptr(), K, W.data_ptr(), K, C.data_ptr(), N, b.data_ptr(),
+                                       act, 0, st()), "tc gemm")
+        ref = fn(ref0)
+        err = (C.double() - ref).abs().max().item()
+        assert err <= TF32_GEMM * max(1.0, ref0.abs().max().item()), (act, err, ref0.abs().max().item())
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 256, 64), (8192, 1536, 512), (1000, 1024, 1024), (300, 2048, 512), (4096, 512, 128)])
+def test_tc_gemm_dgrad_wgrad(lib, M, N, K):
+    from dxvae_b200 import _lib
+    g = torch.Generator().manual_seed(M + N + K)
+    dY = torch.randn(M, N, generator=g).cuda(); W = torch.randn(N, K, generator=g).cuda()
+    X = torch.randn(M, K, generator=g).cuda()
+    dX = torch.full((M, K), float("nan"), device="cuda")
+    _lib.check(lib.dxvae_test_gemm(17, M, N, K, dY.data_ptr(), N, W.data_ptr(), K, dX.data_ptr(), K, None, 0, 0, st()), "dgrad")
+    ref = dY.double() @ W.double()
+    assert (dX.double() - ref).abs().max().item() <= TF32_GEMM * ref.abs().max().item()
+    _lib.check(lib.dxvae_test_gemm(17, M, N, K, dY.data_ptr(), N, W.data_ptr(), K, dX.data_ptr(), K, None, 0, 1, st()), "dgrad+")
+    assert (dX.double() - 2 * ref).abs().max().item() <= 2 * TF32_GEMM * ref.abs().max().item()
+    dW = torch.zeros(N, K, device="cuda")
+    _lib.check(lib.dxvae_test_gemm(18, M, N, K, dY.data_ptr(), N, X.data_ptr(), K, dW.data_ptr(), K, None, 0, 0, st()), "wgrad")
+    refw = dY.double().t() @ X.double()
+    assert (dW.double() - refw).abs().max().item() <= TF32_GEMM * refw.abs().max().item()
+
+
+def test_tf32_training_step_within_stated_tolerance(lib):
+    from dxvae_b200 import DXVAE
+    from dxvae_b200.dxdata import DXGraph
+    idx = list(range(0, 1024, 4))           # 256 graphs: rows >= 128 so the tensor-core path is taken
+    X, P, E, A = util.dataset_graphs(idx)
+    o = O.make_weights(0, 3.0)
+    m = DXVAE(); m.load_state_dict(o.state_dict()); m.verbose = False
+    m.precision = "tf32"
+    G = [DXGraph(X[i], P[i], *E[i]) for i in range(len(idx))]
+    torch.manual_seed(9)
+    eps = torch.randn(len(idx), 128)
+    out = m.forward(G, eps=eps)
+    mu_o, sd_o = o.encode(X, A)
+    lo = o.loss(mu_o, sd_o, X, P, A, eps)
+    rel = [abs(a.item() - b.item()) / abs(b.item()) for a, b in zip(out, lo)]
+    out[0].backward(); lo[0].backward()
+    named = dict(m.named_parameters())
+    worst = {}
+    for n, p in o.named_parameters():
+        worst[n] = (p.grad - named[n].grad.cpu()).abs().max().item() / (p.grad.abs().max().item() + 1e-30)
+    print("tf32 loss rel", rel, "worst grad rel", max(worst.values()), max(worst, key=worst.get))
+    assert max(rel) <= TF32_LOSS, rel
+    assert max(worst.values()) <= TF32_GRAD, sorted(worst.items(), key=lambda kv: -kv[1])[:5]
