@@ -21,6 +21,7 @@
 
 #ifndef DX_EMU
 #include <cuda.h>
+#include <stdlib.h>
 
 namespace dx {
 namespace {
@@ -32,7 +33,7 @@ template <int BN> struct TcCfg {
   static constexpr int B_BYTES = BN * TBK * 4;
   static constexpr int STAGE = A_BYTES + B_BYTES;
   static constexpr int STAGES = (BN == 256) ? 4 : 6;
-  static constexpr int SMEM = STAGES * STAGE + 1024 /*align*/ + 256 /*barriers*/;
+  static constexpr int SMEM = STAGES * STAGE + 1024 /*align*/ + 256 /*barriers*/ + 4 * 32 * 36 * 4 /*epilogue staging*/;
 };
 
 struct TcParams {
@@ -40,6 +41,9 @@ struct TcParams {
   float* C; int64_t ldc; const int* c_idx;
   const float* bias; const float* add; int64_t ldadd;
   int act, accum, k_chunk;
+  int tma_store;    // 1: epilogue stores through TMA (bulk tensor store / reduce-add)
+  int exp;          // bring-up experiments (DX_TC_EXP): 1 skip global stores, 2 skip tmem ld
+  long long* dbg;   // optional per-phase clock64() trace of CTA (0,0,0): DX_TC_DEBUG=1
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -96,6 +100,14 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
       : "r"(taddr) : "memory");
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+               ::"l"(reinterpret_cast<uint64_t>(map)), "r"(src), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tma_reduce_add_2d(const CUtensorMap* map, uint32_t src, int c0, int c1) {
+  asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3}], [%1];"
+               ::"l"(reinterpret_cast<uint64_t>(map)), "r"(src), "r"(c0), "r"(c1) : "memory");
+}
 __device__ __forceinline__ float tc_act(float v, int act) {
   if (act == ACT_RELU) return v > 0.f ? v : 0.f;
   if (act == ACT_TANH) return tanhf(v);
@@ -105,7 +117,8 @@ __device__ __forceinline__ float tc_act(float v, int act) {
 
 template <int BN, bool A_MN, bool B_MN>
 __global__ void __launch_bounds__(192, 1) k_tc_gemm(const __grid_constant__ CUtensorMap tmA,
-                                                    const __grid_constant__ CUtensorMap tmB, const TcParams p) {
+                                                    const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmC,
+                                                    const TcParams p) {
   using Cfg = TcCfg<BN>;
   constexpr int S = Cfg::STAGES;
   extern __shared__ uint8_t smem_raw[];
@@ -121,6 +134,8 @@ __global__ void __launch_bounds__(192, 1) k_tc_gemm(const __grid_constant__ CUte
   const int kbeg = blockIdx.z * p.k_chunk;
   const int kend = min(p.K, kbeg + p.k_chunk);
   const int nkb = (kend - kbeg + TBK - 1) / TBK;
+  const bool trace = p.dbg && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0;
+  if (trace && threadIdx.x == 0) p.dbg[200] = clock64();
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < S; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
@@ -136,12 +151,14 @@ __global__ void __launch_bounds__(192, 1) k_tc_gemm(const __grid_constant__ CUte
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   uint32_t tmem_base;
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+  if (trace && threadIdx.x == 0) p.dbg[201] = clock64();
 
   if (warp == 0) {
     if (lane == 0) {                                               // ---- TMA producer
       for (int kb = 0; kb < nkb; ++kb) {
         const int s = kb % S;
         mbar_wait(empty_bar(s), ((kb / S) & 1) ^ 1);
+        if (trace && kb < 32) p.dbg[kb] = clock64();
         mbar_expect_tx(full_bar(s), Cfg::STAGE);
         const int k0 = kbeg + kb * TBK;
         const uint32_t sa = base + s * Cfg::STAGE, sb = sa + A_BYTES;
@@ -163,6 +180,7 @@ __global__ void __launch_bounds__(192, 1) k_tc_gemm(const __grid_constant__ CUte
       for (int kb = 0; kb < nkb; ++kb) {
         const int s = kb % S;
         mbar_wait(full_bar(s), (kb / S) & 1);
+        if (trace && kb < 32) p.dbg[64 + kb] = clock64();
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint32_t sa = base + s * Cfg::STAGE, sb = sa + A_BYTES;
 #pragma unroll
@@ -179,50 +197,117 @@ __global__ void __launch_bounds__(192, 1) k_tc_gemm(const __grid_constant__ CUte
     }
   } else {                                                         // ---- epilogue: warps 2..5
     mbar_wait(tmem_full, 0);
+    if (trace && threadIdx.x == 64) p.dbg[202] = clock64();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const int q = warp & 3;                                        // TMEM lane quadrant this warp may read
-    const int gi = m0 + q * 32 + lane;
-    const bool row_ok = gi < p.M;
-    const int64_t crow = row_ok ? (p.c_idx ? p.c_idx[gi] : gi) : 0;
-    float* crow_p = p.C + crow * p.ldc;
-    const float* arow_p = (p.add && row_ok) ? p.add + (int64_t)gi * p.ldadd : nullptr;
+    // Each thread owns one accumulator row in TMEM; rows are re-distributed through a private
+    // per-warp staging tile (32 rows x 32 cols, pitch 36 floats: 128-bit accesses conflict-free both
+    // ways) so that global stores are coalesced: one warp instruction = 4 rows x 128 contiguous bytes.
+    float* stg = reinterpret_cast<float*>(smem_raw + (base - smem_u32(smem_raw)) + S * Cfg::STAGE + 256) +
+                 (warp - 2) * (32 * 36);
     const bool vec = ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0) && (p.ldc % 4 == 0);
+    const int rsub = lane >> 3, cc = (lane & 7) * 4;
+    if (p.tma_store) {
+      // All MMAs have retired (tmem_full), so the pipeline stages are free: reuse them as the
+      // store staging area.  Slab (c/32) of warp-quadrant q: 32 rows x 128 B, 128B-swizzled exactly
+      // as the C tensor map expects; each thread deposits its own row (conflict-free 128-bit
+      // writes), then one lane hands the 4 KB block to the TMA unit (plain store, or f32
+      // reduce-add for accumulate / split-K modes).  Bulk stores are not limited by the few
+      // epilogue warps' outstanding-store budget, unlike STG.
+      const int row = q * 32 + lane;
+      const int gi = m0 + row;
+      const bool row_ok = gi < p.M;
+#pragma unroll 1
+      for (int c = 0; c < BN; c += 32) {
+        float v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c, v);
+        const int gj = n0 + c;
+        if (gj >= p.N) continue;                                   // warp-uniform
+        if (p.bias || p.add || p.act) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            float4 a4 = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (p.add && row_ok && gj + j + 3 < p.N) a4 = __ldg(reinterpret_cast<const float4*>(p.add + (int64_t)gi * p.ldadd + gj + j));
+            const float ad[4] = {a4.x, a4.y, a4.z, a4.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              if (gj + j + e < p.N) {
+                float t = v[j + e] + ad[e];
+                if (p.bias) t += __ldg(p.bias + gj + j + e);
+                v[j + e] = tc_act(t, p.act);
+              }
+            }
+          }
+        }
+        const uint32_t slab = base + (uint32_t)(((c >> 5) * 4 + q) * 4096);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const uint32_t dst = slab + (uint32_t)(lane * 128) + (uint32_t)(((j ^ (lane & 7)) << 4));
+          asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "f"(v[4 * j]), "f"(v[4 * j + 1]),
+                       "f"(v[4 * j + 2]), "f"(v[4 * j + 3]) : "memory");
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) {
+          if (p.accum == ACC_STORE) tma_store_2d(&tmC, slab, gj, m0 + q * 32);
+          else tma_reduce_add_2d(&tmC, slab, gj, m0 + q * 32);
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
+      }
+      if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+      __syncwarp();
+    } else
 #pragma unroll 1
     for (int c = 0; c < BN; c += 32) {
       float v[32];
-      tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c, v);
-      const int gj = n0 + c;
-      if (!row_ok || gj >= p.N) continue;
+      if (p.exp & 2) { for (int j = 0; j < 32; ++j) v[j] = (float)(c + j); }
+      else tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c, v);
+      if (n0 + c >= p.N) continue;                                 // warp-uniform
 #pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        if (gj + j < p.N) {
-          float t = v[j];
-          if (p.bias) t += __ldg(p.bias + gj + j);
-          if (arow_p) t += __ldg(arow_p + gj + j);
-          v[j] = tc_act(t, p.act);
+      for (int j = 0; j < 32; j += 4)
+        *reinterpret_cast<float4*>(stg + lane * 36 + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+      __syncwarp();
+      const int gj = n0 + c + cc;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int rr = i * 4 + rsub;
+        const int gi = m0 + q * 32 + rr;
+        if (gi < p.M && gj < p.N && !((p.exp & 1) && gi >= 0)) {
+          const float4 x = *reinterpret_cast<const float4*>(stg + rr * 36 + cc);
+          float o[4] = {x.x, x.y, x.z, x.w};
+          const int64_t crow = p.c_idx ? p.c_idx[gi] : gi;
+          float* dst = p.C + crow * p.ldc + gj;
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            if (gj + e < p.N) {
+              float t = o[e];
+              if (p.bias) t += __ldg(p.bias + gj + e);
+              if (p.add) t += __ldg(p.add + (int64_t)gi * p.ldadd + gj + e);
+              o[e] = tc_act(t, p.act);
+            }
+          }
+          if (p.accum == ACC_ATOMIC) {
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
+              if (gj + e < p.N) atomicAdd(dst + e, o[e]);
+          } else if (vec && gj + 3 < p.N) {
+            float4 w = make_float4(o[0], o[1], o[2], o[3]);
+            if (p.accum == ACC_ADD) { const float4 old = *reinterpret_cast<float4*>(dst); w.x += old.x; w.y += old.y; w.z += old.z; w.w += old.w; }
+            *reinterpret_cast<float4*>(dst) = w;
+          } else {
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
+              if (gj + e < p.N) { if (p.accum == ACC_ADD) dst[e] += o[e]; else dst[e] = o[e]; }
+          }
         }
       }
-      if (p.accum == ACC_ATOMIC) {
-#pragma unroll
-        for (int j = 0; j < 32; ++j)
-          if (gj + j < p.N) atomicAdd(crow_p + gj + j, v[j]);
-      } else if (vec && gj + 31 < p.N) {
-#pragma unroll
-        for (int j = 0; j < 32; j += 4) {
-          float4* dst = reinterpret_cast<float4*>(crow_p + gj + j);
-          float4 o = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-          if (p.accum == ACC_ADD) { const float4 old = *dst; o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w; }
-          *dst = o;
-        }
-      } else {
-#pragma unroll
-        for (int j = 0; j < 32; ++j)
-          if (gj + j < p.N) { if (p.accum == ACC_ADD) crow_p[gj + j] += v[j]; else crow_p[gj + j] = v[j]; }
-      }
+      __syncwarp();
     }
   }
+  if (trace && threadIdx.x == 64) p.dbg[203] = clock64();
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
+  if (trace && threadIdx.x == 0) p.dbg[204] = clock64();
   if (warp == 1) {
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(BN) : "memory");
@@ -248,14 +333,14 @@ EncodeTiledFn get_encode() {
 }
 // 2-D fp32 tensor [rows][cols] with row pitch ld (floats); box = box_cols x box_rows
 bool make_map(CUtensorMap* m, const float* ptr, int64_t rows, int64_t cols, int64_t ld, int box_cols, int box_rows,
-              bool mn_major) {
+              bool mn_major, bool plain_f32 = false) {
   EncodeTiledFn enc = get_encode();
   if (!enc) return false;
   cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
   cuuint64_t gstr[1] = {(cuuint64_t)ld * 4};
   cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1, 1};
-  return enc(m, CU_TENSOR_MAP_DATA_TYPE_TFLOAT32, 2, const_cast<float*>(ptr), gdim, gstr, box, estr,
+  return enc(m, plain_f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_TFLOAT32, 2, const_cast<float*>(ptr), gdim, gstr, box, estr,
              CU_TENSOR_MAP_INTERLEAVE_NONE, mn_major ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
              CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
@@ -270,6 +355,12 @@ bool launch_tc(dx_stream_t s, const GemmP& g) {
   else        { if (!make_map(&ta, g.A, g.K, g.M, g.lda, 32, TBK, true)) return false; }
   if (g.b_kc) { if (!make_map(&tb, g.B, g.N, g.K, g.ldb, TBK, BN, false)) return false; }
   else        { if (!make_map(&tb, g.B, g.K, g.N, g.ldb, 32, TBK, true)) return false; }
+  // C through TMA when it is a plain strided matrix (no row scatter) with 16-byte aligned rows
+  const bool tma_store = !g.c_idx && ((reinterpret_cast<uintptr_t>(g.C) & 15) == 0) && (g.ldc % 4 == 0) &&
+                         !getenv("DX_TC_NO_TMA_STORE");
+  CUtensorMap tc;
+  if (tma_store) { if (!make_map(&tc, g.C, g.M, g.N, g.ldc, 32, 32, false, true)) return false; }
+  else tc = ta;
   const int gm = (g.M + TBM - 1) / TBM, gn = (g.N + BN - 1) / BN;
   int splits = 1;
   if (g.accum == ACC_ATOMIC) {
@@ -281,7 +372,11 @@ bool launch_tc(dx_stream_t s, const GemmP& g) {
   int k_chunk = (g.K + splits - 1) / splits;
   k_chunk = (k_chunk + TBK - 1) / TBK * TBK;
   splits = (g.K + k_chunk - 1) / k_chunk;
-  TcParams p{g.M, g.N, g.K, g.C, g.ldc, g.c_idx, g.bias, g.add, g.ldadd, g.act, g.accum, k_chunk};
+  static long long* dbg = nullptr;
+  static const bool want_dbg = getenv("DX_TC_DEBUG") != nullptr;
+  if (want_dbg && !dbg) cudaMalloc(&dbg, 256 * sizeof(long long));
+  if (want_dbg) cudaMemsetAsync(dbg, 0, 256 * sizeof(long long), s);
+  TcParams p{g.M, g.N, g.K, g.C, g.ldc, g.c_idx, g.bias, g.add, g.ldadd, g.act, g.accum, k_chunk, tma_store ? 1 : 0, getenv("DX_TC_EXP") ? atoi(getenv("DX_TC_EXP")) : 0, want_dbg ? dbg : nullptr};
   dim3 grid(gn, gm, splits);
   static bool attr_set = false;   // per BN instantiation; all four operand-major variants share the footprint
   if (!attr_set) {
@@ -291,12 +386,25 @@ bool launch_tc(dx_stream_t s, const GemmP& g) {
     cudaFuncSetAttribute(k_tc_gemm<BN, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM);
     attr_set = true;
   }
-  auto run = [&](auto kern) { kern<<<grid, 192, Cfg::SMEM, s>>>(ta, tb, p); };
+  auto run = [&](auto kern) { kern<<<grid, 192, Cfg::SMEM, s>>>(ta, tb, tc, p); };
   if (g.a_kc && g.b_kc) run(k_tc_gemm<BN, false, false>);
   else if (g.a_kc && !g.b_kc) run(k_tc_gemm<BN, false, true>);
   else if (!g.a_kc && !g.b_kc) run(k_tc_gemm<BN, true, true>);
   else run(k_tc_gemm<BN, true, false>);
   ++g_launches;
+  if (want_dbg) {
+    long long h[256];
+    cudaStreamSynchronize(s);
+    cudaMemcpy(h, dbg, sizeof(h), cudaMemcpyDeviceToHost);
+    const long long t0 = h[200];
+    fprintf(stderr, "[tc trace] M=%d N=%d K=%d BN=%d splits=%d | setup %lld | epi start %lld end %lld | cta end %lld\n", g.M, g.N, g.K, BN, splits,
+            h[201] - t0, h[202] - t0, h[203] - t0, h[204] - t0);
+    fprintf(stderr, "  producer(empty ok):");
+    for (int i = 0; i < 20 && h[i]; ++i) fprintf(stderr, " %lld", h[i] - t0);
+    fprintf(stderr, "\n  mma(full ok):      ");
+    for (int i = 0; i < 20 && h[64 + i]; ++i) fprintf(stderr, " %lld", h[64 + i] - t0);
+    fprintf(stderr, "\n");
+  }
   return true;
 }
 
