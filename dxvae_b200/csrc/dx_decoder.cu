@@ -32,14 +32,14 @@ DecWs carve_dec(Arena& ar, int64_t B, bool train) {
   };
   per_node(w.A1, 2 * H, train); per_node(w.A2, 2 * H, train); per_node(w.L, LD_L, train);
   per_node(w.gxc, G3, train); per_node(w.gxl, G3, train); per_node(w.Hc0, H, train);
-  per_node(w.Hi_p1, H, train); per_node(w.Hi_p2, H, train); per_node(w.ES1, 2 * H, train); per_node(w.ls, 1, train);
-  per_step(w.E1, 4 * H, train); per_step(w.l2, 2, train); per_step(w.Hin, H, train); per_step(w.Hc, H, train);
+  per_node(w.Hi_p1, H, train); per_node(w.Hi_p2, H, train); per_node(w.ES1, 2 * H, train); per_node(w.ls, LD_E, train);
+  per_step(w.E1, 4 * H, train); per_step(w.l2, LD_E, train); per_step(w.Hin, H, train); per_step(w.Hc, H, train);
   per_step(w.Hi, H, train);
   if (train) {
     w.g_root = ar.take<float>(b * 4 * H);
     per_node(w.dL, LD_L, true); per_node(w.g_c0, 4 * H, true); per_node(w.g_p1, 4 * H, true);
-    per_node(w.g_p2, 4 * H, true); per_node(w.dls, 1, true);
-    per_step(w.dl2, 2, true); per_step(w.g_c, 4 * H, true); per_step(w.g_l, 4 * H, true);
+    per_node(w.g_p2, 4 * H, true); per_node(w.dls, LD_E, true);
+    per_step(w.dl2, LD_E, true); per_step(w.g_c, 4 * H, true); per_step(w.g_l, 4 * H, true);
     w.rowloss = ar.take<float>(4 * b);
     w.dHd = ar.take<float>(7 * b * H); w.dPg = ar.take<float>(6 * b * 2 * H); w.dPm = ar.take<float>(6 * b * 2 * H);
     w.dQ = ar.take<float>(6 * b * 4 * H); w.dgb = ar.take<float>(6 * b * H);
@@ -124,9 +124,9 @@ static void loss_edge(dx_stream_t st, int B, int vi, int vj, const float* lg, in
     float acc = 0.f;
     for (int c = 0; c < n; ++c) {
       const float t = (n == 1) ? (float)abit(A, vi, vi) : (c == 0 ? (float)abit(A, vj, vi) : (float)abit(A, vi, vj));
-      const float x = lg[b * n + c];
+      const float x = lg[b * LD_E + c];
       acc += bce_logits(x, t);
-      dlg[b * n + c] = (sigmoidf_(x) - t) * lw.inv_batch;
+      dlg[b * LD_E + c] = (sigmoidf_(x) - t) * lw.inv_batch;
     }
     rowloss[(int64_t)2 * B + b] += acc * lw.inv_batch;  // slot 2: loss_E
   });
@@ -269,7 +269,7 @@ static void decide_edges(dx_stream_t st, int B, int vi, int vj, const float* lg,
     uint64_t A = adj[b];
     float mg = margins ? margins[b] : 0.f;
     for (int c = 0; c < n; ++c) {
-      const float x = lg[b * n + c];
+      const float x = lg[b * LD_E + c];
       const bool on = sigmoidf_(x) > 0.5f;
       int s, d;
       if (n == 1) { s = vi; d = vi; } else if (c == 0) { s = vj; d = vi; } else { s = vi; d = vj; }
@@ -340,7 +340,7 @@ void decode_fwd_impl(dx_stream_t st, const Weights& W, int B, const float* z, co
     cell_fwd(st, p1);
     // self-loop head (model.py:236/331)
     linear_fwd(st, B, 2 * H, H, w.Hi_p1[vi], H, W[P_ES_W0], H, W[P_ES_B0], w.ES1[vi], 2 * H, ACT_RELU);
-    linear_fwd(st, B, 1, 2 * H, w.ES1[vi], 2 * H, W[P_ES_W2], 2 * H, W[P_ES_B2], w.ls[vi], 1);
+    linear_fwd(st, B, 1, 2 * H, w.ES1[vi], 2 * H, W[P_ES_W2], 2 * H, W[P_ES_B2], w.ls[vi], LD_E);
     if (train) loss_edge(st, B, vi, vi, w.ls[vi], 1, adj, io.lw, w.rowloss, w.dls[vi]);
     else decide_edges(st, B, vi, vi, w.ls[vi], 1, io.adj_out, io.margins);
     // P2 (model.py:240/337): same H_in = 0, x_loop = s*x
@@ -353,7 +353,7 @@ void decode_fwd_impl(dx_stream_t st, const Weights& W, int B, const float* z, co
       // edge head on cat[Hi, Hj] (model.py:245/350): first layer split into Hi half + cached Hj half
       linear_fwd(st, B, 4 * H, H, Hi_prev, H, W[P_E_W0], 2 * H, nullptr, w.E1[t], 4 * H, ACT_RELU, nullptr, nullptr,
                  w.Q + (size_t)vj * B * 4 * H, 4 * H);
-      linear_fwd(st, B, 2, 4 * H, w.E1[t], 4 * H, W[P_E_W2], 4 * H, W[P_E_B2], w.l2[t], 2);
+      linear_fwd(st, B, 2, 4 * H, w.E1[t], 4 * H, W[P_E_W2], 4 * H, W[P_E_B2], w.l2[t], LD_E);
       if (train) loss_edge(st, B, vi, vj, w.l2[t], 2, adj, io.lw, w.rowloss, w.dl2[t]);
       else decide_edges(st, B, vi, vj, w.l2[t], 2, io.adj_out, io.margins);
       // add the message of vj to the running aggregate, then re-propagate (model.py:251/358)
@@ -447,18 +447,18 @@ void decode_bwd_impl(dx_stream_t st, const Weights& W, const Weights& G, int B, 
       msg_bwd(st, mb);
       // edge head of this step read the PREVIOUS Hi (step t-1, or P2 when vj = vi-1)
       const float* Hi_prev = (vj == vi - 1) ? w.Hi_p2[vi] : w.Hi[t - 1];
-      linear_wgrad(st, B, 2, 4 * H, w.dl2[t], 2, w.E1[t], 4 * H, G[P_E_W2], 4 * H);
-      colsum_accum(st, B, 2, w.dl2[t], 2, G[P_E_B2]);
-      relu_head_bwd(st, B, 4 * H, 2, w.E1[t], w.dl2[t], 2, W[P_E_W2], w.dE1, w.dQ + (size_t)vj * B * 4 * H);
+      linear_wgrad(st, B, 2, 4 * H, w.dl2[t], LD_E, w.E1[t], 4 * H, G[P_E_W2], 4 * H);
+      colsum_accum(st, B, 2, w.dl2[t], LD_E, G[P_E_B2]);
+      relu_head_bwd(st, B, 4 * H, 2, w.E1[t], w.dl2[t], LD_E, W[P_E_W2], w.dE1, w.dQ + (size_t)vj * B * 4 * H);
       linear_wgrad(st, B, 4 * H, H, w.dE1, 4 * H, Hi_prev, H, G[P_E_W0], 2 * H);
       linear_dgrad(st, B, 4 * H, H, w.dE1, 4 * H, W[P_E_W0], 2 * H, w.dHi, H, ACC_STORE);
     }
     // dHi now holds the gradient of Hi_p2.  P2 and P1 share Hc0.
     looper_bwd(st, W, G, B, vi, rm, w.dHi, w.g_p2[vi], w.Hc0[vi], S_SELF, adj, Xi, w, w.dHc0, false);
     // self-loop head consumed Hi_p1
-    linear_wgrad(st, B, 1, 2 * H, w.dls[vi], 1, w.ES1[vi], 2 * H, G[P_ES_W2], 2 * H);
-    colsum_accum(st, B, 1, w.dls[vi], 1, G[P_ES_B2]);
-    relu_head_bwd(st, B, 2 * H, 1, w.ES1[vi], w.dls[vi], 1, W[P_ES_W2], w.dES1, nullptr);
+    linear_wgrad(st, B, 1, 2 * H, w.dls[vi], LD_E, w.ES1[vi], 2 * H, G[P_ES_W2], 2 * H);
+    colsum_accum(st, B, 1, w.dls[vi], LD_E, G[P_ES_B2]);
+    relu_head_bwd(st, B, 2 * H, 1, w.ES1[vi], w.dls[vi], LD_E, W[P_ES_W2], w.dES1, nullptr);
     linear_wgrad(st, B, 2 * H, H, w.dES1, 2 * H, w.Hi_p1[vi], H, G[P_ES_W0], H);
     colsum_accum(st, B, 2 * H, w.dES1, 2 * H, G[P_ES_B0]);
     linear_dgrad(st, B, 2 * H, H, w.dES1, 2 * H, W[P_ES_W0], H, w.dHi, H, ACC_STORE);

@@ -7,6 +7,8 @@
 //   projections) -> combiner GRU -> looper GRU (input masked by the self-loop flag)
 //   -> gate/mapper projections of the new state, reused by every lower neighbour.
 // The root step (node 0 of all graphs) runs last, then the two latent heads.
+// Activations live in schedule order (level-major), so every product is a dense row range:
+// no gathers in the GEMMs, which lets them run on the TMA/tcgen05 path.
 #include "dx_engine.h"
 
 namespace dx {
@@ -17,6 +19,7 @@ EncWs carve_enc(Arena& ar, int64_t B, bool train) {
   w.Hin = ar.take<float>(R7 * H); w.Hc = ar.take<float>(R7 * H); w.Hv = ar.take<float>(R7 * H);
   w.Pg = ar.take<float>(R7 * 2 * H); w.Pm = ar.take<float>(R7 * 2 * H);
   w.gxc = ar.take<float>(R6 * G3); w.gxl = ar.take<float>(R6 * G3); w.gh = ar.take<float>(R6 * G3);
+  w.XnS = ar.take<float>(R6 * XP); w.pos = ar.take<int>(R7);
   if (train) {
     w.gc = ar.take<float>(R7 * 4 * H); w.gl = ar.take<float>(R7 * 4 * H);
     w.dH = ar.take<float>(R7 * H); w.dHin = ar.take<float>(R7 * H);
@@ -30,96 +33,121 @@ EncWs carve_enc(Arena& ar, int64_t B, bool train) {
 void encode_fwd_impl(dx_stream_t st, const Weights& W, const Batch& bt, const EncWs& w, float* mu, float* sd,
                      bool train) {
   const int B = (int)bt.B;
+  const int64_t R6 = (int64_t)6 * B;
+  // schedule-order bookkeeping: inverse map and the permuted feature rows
+  {
+    int* pos = w.pos; const int32_t* rows = bt.level_rows; const float* Xn = bt.Xn; float* XnS = w.XnS;
+    foreach (st, (int64_t)7 * B, [=] DX_HD(int64_t i) {
+      if (i < R6) pos[rows[i]] = (int)i; else pos[i - R6] = (int)i;     // node 0 of graph b sits at 6B+b
+    });
+    foreach (st, R6 * (XP / 4), [=] DX_HD(int64_t i) {
+      const int64_t p = i / (XP / 4); const int c = (int)(i % (XP / 4)) * 4;
+      st4f(XnS + p * XP + c, ld4f(Xn + (int64_t)rows[p] * XP + c));
+    });
+  }
   for (int L = 0; L < bt.n_levels; ++L) {
-    const int M = bt.level_ptr[L + 1] - bt.level_ptr[L];
+    const int base = bt.level_ptr[L];
+    const int M = bt.level_ptr[L + 1] - base;
     if (M <= 0) continue;
-    const int* rows = bt.level_rows + bt.level_ptr[L];
-    RowMap rm{M, B, rows, 0};
+    RowMap rm{M, B, bt.level_rows + base, 0};
+    float* Hin = w.Hin + (size_t)base * H; float* Hc = w.Hc + (size_t)base * H; float* Hv = w.Hv + (size_t)base * H;
     if (L > 0) {
-      MsgFwd mf{rm, w.Pg, w.Pm, W[P_G_B], bt.adj, w.Hin, 1, -1, 0, 0};
+      MsgFwd mf{rm, w.Pg, w.Pm, W[P_G_B], bt.adj, Hin, 0, -1, 0, 0};
+      mf.pos = w.pos;
       msg_fwd(st, mf);
     }
-    linear_fwd(st, M, G3, SX, bt.Xn, XP, W[P_CE_WIH], SX, nullptr, w.gxc, G3, ACT_NONE, rows);
-    linear_fwd(st, M, G3, SX, bt.Xn, XP, W[P_LE_WIH], SX, nullptr, w.gxl, G3, ACT_NONE, rows);
-    if (L > 0) linear_fwd(st, M, G3, H, w.Hin, H, W[P_CE_WHH], H, nullptr, w.gh, G3, ACT_NONE, rows);
-    CellFwd c1{rm, w.gxc, L > 0 ? w.gh : nullptr, W[P_CE_BIH], W[P_CE_BHH], L > 0 ? w.Hin : nullptr, 1, w.Hc, 1,
-               train ? w.gc : nullptr, 1, S_ONE, bt.adj};
+    linear_fwd(st, M, G3, SX, w.XnS + (size_t)base * XP, XP, W[P_CE_WIH], SX, nullptr, w.gxc, G3);
+    linear_fwd(st, M, G3, SX, w.XnS + (size_t)base * XP, XP, W[P_LE_WIH], SX, nullptr, w.gxl, G3);
+    if (L > 0) linear_fwd(st, M, G3, H, Hin, H, W[P_CE_WHH], H, nullptr, w.gh, G3);
+    CellFwd c1{rm, w.gxc, L > 0 ? w.gh : nullptr, W[P_CE_BIH], W[P_CE_BHH], L > 0 ? Hin : nullptr, 0, Hc, 0,
+               train ? w.gc + (size_t)base * 4 * H : nullptr, 0, S_ONE, bt.adj};
     cell_fwd(st, c1);
-    linear_fwd(st, M, G3, H, w.Hc, H, W[P_LE_WHH], H, nullptr, w.gh, G3, ACT_NONE, rows);
-    CellFwd c2{rm, w.gxl, w.gh, W[P_LE_BIH], W[P_LE_BHH], w.Hc, 1, w.Hv, 1, train ? w.gl : nullptr, 1, S_SELF, bt.adj};
+    linear_fwd(st, M, G3, H, Hc, H, W[P_LE_WHH], H, nullptr, w.gh, G3);
+    CellFwd c2{rm, w.gxl, w.gh, W[P_LE_BIH], W[P_LE_BHH], Hc, 0, Hv, 0, train ? w.gl + (size_t)base * 4 * H : nullptr, 0,
+               S_SELF, bt.adj};
     cell_fwd(st, c2);
     // projections of the finished state: gate.0.weight (512,1024) viewed as (1024,512) rows (2n,2n+1)=(in,out)
-    linear_fwd(st, M, 2 * H, H, w.Hv, H, W[P_G_W], H, nullptr, w.Pg, 2 * H, ACT_NONE, rows, rows);
-    linear_fwd(st, M, 2 * H, H, w.Hv, H, W[P_M_W], H, nullptr, w.Pm, 2 * H, ACT_NONE, rows, rows);
+    linear_fwd(st, M, 2 * H, H, Hv, H, W[P_G_W], H, nullptr, w.Pg + (size_t)base * 2 * H, 2 * H);
+    linear_fwd(st, M, 2 * H, H, Hv, H, W[P_M_W], H, nullptr, w.Pm + (size_t)base * 2 * H, 2 * H);
   }
-  // root step: node 0 of every graph (global rows 0..B-1)
+  // root step: node 0 of every graph (positions 6B..7B-1)
   RowMap r0{B, B, nullptr, 0};
-  MsgFwd mf{r0, w.Pg, w.Pm, W[P_G_B], bt.adj, w.Hin, 1, -1, 0, 0};
+  float* Hin0 = w.Hin + (size_t)R6 * H; float* Hv0 = w.Hv + (size_t)R6 * H;
+  MsgFwd mf{r0, w.Pg, w.Pm, W[P_G_B], bt.adj, Hin0, 0, -1, 0, 0};
+  mf.pos = w.pos;
   msg_fwd(st, mf);
   linear_fwd(st, B, G3, SX0, bt.Xn, XP, W[P_RE_WIH], SX0, nullptr, w.gxc, G3);
-  linear_fwd(st, B, G3, H, w.Hin, H, W[P_RE_WHH], H, nullptr, w.gh, G3);
-  CellFwd cr{r0, w.gxc, w.gh, W[P_RE_BIH], W[P_RE_BHH], w.Hin, 1, w.Hv, 1, train ? w.gc : nullptr, 1, S_ONE, bt.adj};
+  linear_fwd(st, B, G3, H, Hin0, H, W[P_RE_WHH], H, nullptr, w.gh, G3);
+  CellFwd cr{r0, w.gxc, w.gh, W[P_RE_BIH], W[P_RE_BHH], Hin0, 0, Hv0, 0, train ? w.gc + (size_t)R6 * 4 * H : nullptr, 0,
+             S_ONE, bt.adj};
   cell_fwd(st, cr);
-  linear_fwd(st, B, Z, H, w.Hv, H, W[P_MU_W], H, W[P_MU_B], mu, Z);
-  linear_fwd(st, B, Z, H, w.Hv, H, W[P_STD_W], H, W[P_STD_B], sd, Z, ACT_SOFTPLUS);
+  linear_fwd(st, B, Z, H, Hv0, H, W[P_MU_W], H, W[P_MU_B], mu, Z);
+  linear_fwd(st, B, Z, H, Hv0, H, W[P_STD_W], H, W[P_STD_B], sd, Z, ACT_SOFTPLUS);
 }
 
 // Backward of the above.  dmu, dstd: (B,128).  Accumulates into the gradient blob G.
 void encode_bwd_impl(dx_stream_t st, const Weights& W, const Weights& G, const Batch& bt, const EncWs& w,
                      const float* dmu, const float* dstd, const float* sd) {
   const int B = (int)bt.B;
+  const int64_t R6 = (int64_t)6 * B;
+  float* Hin0 = w.Hin + (size_t)R6 * H; float* Hv0 = w.Hv + (size_t)R6 * H;
+  float* dH0 = w.dH + (size_t)R6 * H; float* dHin0 = w.dHin + (size_t)R6 * H;
   // softplus': sigmoid(raw) = 1 - exp(-std)
   {
     float* dsraw = w.dsraw;
     foreach (st, (int64_t)B * Z, [=] DX_HD(int64_t i) { dsraw[i] = dstd[i] * (1.f - expf(-sd[i])); });
   }
-  linear_dgrad(st, B, Z, H, dmu, Z, W[P_MU_W], H, w.dH, H, ACC_STORE);
-  linear_dgrad(st, B, Z, H, w.dsraw, Z, W[P_STD_W], H, w.dH, H, ACC_ADD);
-  linear_wgrad(st, B, Z, H, dmu, Z, w.Hv, H, G[P_MU_W], H);
-  linear_wgrad(st, B, Z, H, w.dsraw, Z, w.Hv, H, G[P_STD_W], H);
+  linear_dgrad(st, B, Z, H, dmu, Z, W[P_MU_W], H, dH0, H, ACC_STORE);
+  linear_dgrad(st, B, Z, H, w.dsraw, Z, W[P_STD_W], H, dH0, H, ACC_ADD);
+  linear_wgrad(st, B, Z, H, dmu, Z, Hv0, H, G[P_MU_W], H);
+  linear_wgrad(st, B, Z, H, w.dsraw, Z, Hv0, H, G[P_STD_W], H);
   colsum_accum(st, B, Z, dmu, Z, G[P_MU_B]);
   colsum_accum(st, B, Z, w.dsraw, Z, G[P_STD_B]);
   // root cell
   RowMap r0{B, B, nullptr, 0};
-  CellBwd cr{r0, w.dH, 1, w.gc, 1, w.Hin, 1, w.dgx, nullptr, w.dgh, w.dHin, S_ONE, bt.adj};
-  cell_bwd(st, cr);  // dHin rows 0..B-1 <- dh*z (compact == global for the root rows)
-  linear_dgrad(st, B, G3, H, w.dgh, G3, W[P_RE_WHH], H, w.dHin, H, ACC_ADD);
-  linear_wgrad(st, B, G3, H, w.dgh, G3, w.Hin, H, G[P_RE_WHH], H);
+  CellBwd cr{r0, dH0, 0, w.gc + (size_t)R6 * 4 * H, 0, Hin0, 0, w.dgx, nullptr, w.dgh, dHin0, S_ONE, bt.adj};
+  cell_bwd(st, cr);
+  linear_dgrad(st, B, G3, H, w.dgh, G3, W[P_RE_WHH], H, dHin0, H, ACC_ADD);
+  linear_wgrad(st, B, G3, H, w.dgh, G3, Hin0, H, G[P_RE_WHH], H);
   linear_wgrad(st, B, G3, SX0, w.dgx, G3, bt.Xn, XP, G[P_RE_WIH], SX0);
   colsum_accum(st, B, G3, w.dgh, G3, G[P_RE_BHH]);
   colsum_accum(st, B, G3, w.dgx, G3, G[P_RE_BIH]);
 
   for (int L = bt.n_levels - 1; L >= 0; --L) {
-    const int M = bt.level_ptr[L + 1] - bt.level_ptr[L];
+    const int base = bt.level_ptr[L];
+    const int M = bt.level_ptr[L + 1] - base;
     if (M <= 0) continue;
-    const int* rows = bt.level_rows + bt.level_ptr[L];
-    RowMap rm{M, B, rows, 0};
+    RowMap rm{M, B, bt.level_rows + base, 0};
+    float* Hin = w.Hin + (size_t)base * H; float* Hc = w.Hc + (size_t)base * H; float* Hv = w.Hv + (size_t)base * H;
+    float* dH = w.dH + (size_t)base * H; float* dHin = w.dHin + (size_t)base * H;
+    const float* Xs = w.XnS + (size_t)base * XP;
     // gradients reaching the projections of these source rows from every lower neighbour
-    MsgBwd mb{rm, w.Pg, w.Pm, W[P_G_B], bt.adj, w.dHin, B, w.dPg, w.dPm, w.dgb, 0, -1, 0, 0};
+    MsgBwd mb{rm, w.Pg + (size_t)base * 2 * H, w.Pm + (size_t)base * 2 * H, W[P_G_B], bt.adj, w.dHin, 0, w.dPg, w.dPm,
+              w.dgb, 0, -1, 0, 0};
+    mb.pos = w.pos; mb.p_compact = 1;
     msg_bwd(st, mb);
-    linear_dgrad(st, M, 2 * H, H, w.dPg, 2 * H, W[P_G_W], H, w.dH, H, ACC_STORE, nullptr, rows);
-    linear_dgrad(st, M, 2 * H, H, w.dPm, 2 * H, W[P_M_W], H, w.dH, H, ACC_ADD, nullptr, rows);
-    linear_wgrad(st, M, 2 * H, H, w.dPg, 2 * H, w.Hv, H, G[P_G_W], H, nullptr, rows);
-    linear_wgrad(st, M, 2 * H, H, w.dPm, 2 * H, w.Hv, H, G[P_M_W], H, nullptr, rows);
+    linear_dgrad(st, M, 2 * H, H, w.dPg, 2 * H, W[P_G_W], H, dH, H, ACC_STORE);
+    linear_dgrad(st, M, 2 * H, H, w.dPm, 2 * H, W[P_M_W], H, dH, H, ACC_ADD);
+    linear_wgrad(st, M, 2 * H, H, w.dPg, 2 * H, Hv, H, G[P_G_W], H);
+    linear_wgrad(st, M, 2 * H, H, w.dPm, 2 * H, Hv, H, G[P_M_W], H);
     colsum_accum(st, M, H, w.dgb, H, G[P_G_B]);
     // looper
-    CellBwd cl{rm, w.dH, 1, w.gl, 1, w.Hc, 1, w.dgx, w.dgxs, w.dgh, w.dHc, S_SELF, bt.adj};
+    CellBwd cl{rm, dH, 0, w.gl + (size_t)base * 4 * H, 0, Hc, 0, w.dgx, w.dgxs, w.dgh, w.dHc, S_SELF, bt.adj};
     cell_bwd(st, cl);
     linear_dgrad(st, M, G3, H, w.dgh, G3, W[P_LE_WHH], H, w.dHc, H, ACC_ADD);
-    linear_wgrad(st, M, G3, H, w.dgh, G3, w.Hc, H, G[P_LE_WHH], H, nullptr, rows);
-    linear_wgrad(st, M, G3, SX, w.dgxs, G3, bt.Xn, XP, G[P_LE_WIH], SX, nullptr, rows);
+    linear_wgrad(st, M, G3, H, w.dgh, G3, Hc, H, G[P_LE_WHH], H);
+    linear_wgrad(st, M, G3, SX, w.dgxs, G3, Xs, XP, G[P_LE_WIH], SX);
     colsum_accum(st, M, G3, w.dgh, G3, G[P_LE_BHH]);
     colsum_accum(st, M, G3, w.dgx, G3, G[P_LE_BIH]);
     // combiner
-    CellBwd cc{rm, w.dHc, 0, w.gc, 1, L > 0 ? w.Hin : nullptr, 1, w.dgx, nullptr, w.dgh, L > 0 ? w.dHin : nullptr,
-               S_ONE, bt.adj};
-    cc.dhp_global = 1;
+    CellBwd cc{rm, w.dHc, 0, w.gc + (size_t)base * 4 * H, 0, L > 0 ? Hin : nullptr, 0, w.dgx, nullptr, w.dgh,
+               L > 0 ? dHin : nullptr, S_ONE, bt.adj};
     cell_bwd(st, cc);
     if (L > 0) {
-      linear_dgrad(st, M, G3, H, w.dgh, G3, W[P_CE_WHH], H, w.dHin, H, ACC_ADD, nullptr, rows);
-      linear_wgrad(st, M, G3, H, w.dgh, G3, w.Hin, H, G[P_CE_WHH], H, nullptr, rows);
+      linear_dgrad(st, M, G3, H, w.dgh, G3, W[P_CE_WHH], H, dHin, H, ACC_ADD);
+      linear_wgrad(st, M, G3, H, w.dgh, G3, Hin, H, G[P_CE_WHH], H);
     }
-    linear_wgrad(st, M, G3, SX, w.dgx, G3, bt.Xn, XP, G[P_CE_WIH], SX, nullptr, rows);
+    linear_wgrad(st, M, G3, SX, w.dgx, G3, Xs, XP, G[P_CE_WIH], SX);
     colsum_accum(st, M, G3, w.dgh, G3, G[P_CE_BHH]);
     colsum_accum(st, M, G3, w.dgx, G3, G[P_CE_BIH]);
   }

@@ -29,11 +29,16 @@ struct LossW { float w_env, w_frq, w_kld, inv_batch; };
 
 // ---- workspaces (carved from the caller's buffer; see DESIGN.md "HBM layout") ------------
 struct EncWs {
-  float *Hin, *Hc, *Hv, *gc, *gl, *Pg, *Pm, *gxc, *gxl, *gh;
+  // All per-node buffers are in SCHEDULE ORDER: position p in [0,6B) = index into level_rows (so the
+  // rows of one level are contiguous and every GEMM runs on a dense row range), positions
+  // [6B,7B) = node 0 of graph b.  pos[v*B+b] maps a node back to its position.
+  float *Hin, *Hc, *Hv, *gc, *gl, *Pg, *Pm, *gxc, *gxl, *gh, *XnS;
+  int* pos;
   float *dH, *dHin, *dPg, *dPm, *dgb, *dgx, *dgxs, *dgh, *dHc, *dsraw;
 };
 constexpr int LD_L = 64;  // leading dimension of logit buffers (55 / 27 columns used)
 constexpr int NSTEP = 21;
+constexpr int LD_E = 4;    // leading dimension of the edge-head logit buffers (1 or 2 columns used; 16-byte rows for TMA)
 
 struct DecWs {
   float *z, *Hinit, *Hd, *Pg, *Pm, *Q, *g_root;

@@ -135,6 +135,7 @@ inline void cell_bwd(dx_stream_t st, const CellBwd& a) {
 struct MsgFwd {
   RowMap rm; const float* Pg; const float* Pm; const float* bg; const uint64_t* adj; float* hin; int hin_global;
   int x_lo, x_hi; int accum;
+  const int* pos = nullptr;   // optional: row of neighbour (x,b) in Pg/Pm is pos[x*B+b] instead of x*B+b
 };
 
 inline void msg_fwd(dx_stream_t st, const MsgFwd& a) {
@@ -150,7 +151,7 @@ inline void msg_fwd(dx_stream_t st, const MsgFwd& a) {
     for (int x = lo; x <= hi; ++x) {
       const float fi = (float)abit(A, x, v), fo = (float)abit(A, v, x);
       if (fi == 0.f && fo == 0.f) continue;
-      const int64_t xr = (int64_t)x * a.rm.B + b;
+      const int64_t xr = a.pos ? (int64_t)a.pos[x * a.rm.B + b] : (int64_t)x * a.rm.B + b;
       const float4 g = ld4f(a.Pg + xr * (2 * H) + 2 * n);
       const float4 p = ld4f(a.Pm + xr * (2 * H) + 2 * n);
       acc0 += sigmoidf_((fi * g.x + fo * g.y) + bg0) * (fi * p.x + fo * p.y);
@@ -167,6 +168,8 @@ inline void msg_fwd(dx_stream_t st, const MsgFwd& a) {
 struct MsgBwd {
   RowMap rm; const float* Pg; const float* Pm; const float* bg; const uint64_t* adj; const float* dhin;
   int64_t dh_vstride; float* dPg; float* dPm; float* dgb; int out_global; int v_lo, v_hi; int accum;
+  const int* pos = nullptr;   // optional: dhin row of target (v,b) is pos[v*B+b]
+  int p_compact = 0;          // 1: this row's own Pg/Pm are indexed by m (pointer pre-offset), else by r
 };
 
 inline void msg_bwd(dx_stream_t st, const MsgBwd& a) {
@@ -180,13 +183,15 @@ inline void msg_bwd(dx_stream_t st, const MsgBwd& a) {
     if (a.accum) { dg = ld4f(a.dPg + o * (2 * H) + 2 * n); dp = ld4f(a.dPm + o * (2 * H) + 2 * n);
                    db0 = a.dgb[o * H + n]; db1 = a.dgb[o * H + n + 1]; }
     const int lo = a.v_lo < 0 ? 0 : a.v_lo, hi = a.v_lo < 0 ? x - 1 : a.v_hi;
-    const float4 g = ld4f(a.Pg + (int64_t)r * (2 * H) + 2 * n);
-    const float4 p = ld4f(a.Pm + (int64_t)r * (2 * H) + 2 * n);
+    const int64_t own = a.p_compact ? m : r;
+    const float4 g = ld4f(a.Pg + own * (2 * H) + 2 * n);
+    const float4 p = ld4f(a.Pm + own * (2 * H) + 2 * n);
     const float bg0 = a.bg[n], bg1 = a.bg[n + 1];
     for (int v = lo; v <= hi; ++v) {
       const float fi = (float)abit(A, x, v), fo = (float)abit(A, v, x);
       if (fi == 0.f && fo == 0.f) continue;
-      const float* dh = a.dhin + ((int64_t)v * a.dh_vstride + b) * H + n;
+      const int64_t trow = a.pos ? (int64_t)a.pos[v * a.rm.B + b] : (int64_t)v * a.dh_vstride + b;
+      const float* dh = a.dhin + trow * H + n;
       const float s0 = sigmoidf_((fi * g.x + fo * g.y) + bg0), c0 = fi * p.x + fo * p.y;
       const float s1 = sigmoidf_((fi * g.z + fo * g.w) + bg1), c1 = fi * p.z + fo * p.w;
       const float da0 = dh[0] * c0 * s0 * (1.f - s0), dc0 = dh[0] * s0;

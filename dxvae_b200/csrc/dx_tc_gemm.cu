@@ -32,7 +32,7 @@ constexpr int A_BYTES = TBM * TBK * 4;       // 16 KB
 template <int BN> struct TcCfg {
   static constexpr int B_BYTES = BN * TBK * 4;
   static constexpr int STAGE = A_BYTES + B_BYTES;
-  static constexpr int STAGES = (BN == 256) ? 4 : 6;
+  static constexpr int STAGES = (BN == 256) ? 4 : (BN == 128 ? 6 : 8);
   static constexpr int SMEM = STAGES * STAGE + 1024 /*align*/ + 256 /*barriers*/ + 4 * 32 * 36 * 4 /*epilogue staging*/;
 };
 
@@ -415,11 +415,13 @@ inline bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) =
 // Returns false when the problem is not eligible (caller falls back to the FP32 SIMT kernel).
 bool tc_gemm(dx_stream_t s, const GemmP& g, int* tile_n) {
   if (g.a_idx || g.b_idx) return false;                       // TMA tiles cannot gather rows
-  if (g.M < 128 || g.N < 64 || g.K < 32) return false;
+  // TMA needs 16-byte aligned bases and row pitches; everything else (ragged M/N/K) is handled by
+  // the tensor maps' out-of-bounds zero fill / clipping.
   if (!al16(g.A) || !al16(g.B) || (g.lda % 4) || (g.ldb % 4)) return false;
-  const bool big = g.N >= 192;
-  if (tile_n) *tile_n = big ? 256 : 128;
-  return big ? launch_tc<256>(s, g) : launch_tc<128>(s, g);
+  if ((double)g.M * g.N * g.K < 1.0e6) return false;          // launch-bound anyway
+  const int bn = g.N >= 192 ? 256 : (g.N >= 96 ? 128 : 64);
+  if (tile_n) *tile_n = bn;
+  return bn == 256 ? launch_tc<256>(s, g) : (bn == 128 ? launch_tc<128>(s, g) : launch_tc<64>(s, g));
 }
 
 }  // namespace dx

@@ -29,7 +29,8 @@ def st():
 
 
 SHAPES = [(128, 256, 32), (128, 256, 512), (256, 1536, 512), (8192, 1536, 512), (1000, 1024, 1024), (4096, 128, 512),
-          (300, 2048, 512), (640, 320, 96), (2048, 512, 2048)]
+          (300, 2048, 512), (640, 320, 96), (2048, 512, 2048), (8192, 55, 1024), (8192, 27, 1024), (4096, 2, 2048),
+          (1000, 1, 1024), (8192, 64, 512), (128, 100, 36)]
 
 
 @pytest.mark.parametrize("M,N,K", SHAPES)
@@ -48,7 +49,8 @@ def test_tc_gemm_forward(lib, M, N, K):
         assert err <= TF32_GEMM * max(1.0, ref0.abs().max().item()), (act, err, ref0.abs().max().item())
 
 
-@pytest.mark.parametrize("M,N,K", [(128, 256, 64), (8192, 1536, 512), (1000, 1024, 1024), (300, 2048, 512), (4096, 512, 128)])
+@pytest.mark.parametrize("M,N,K", [(128, 256, 64), (8192, 1536, 512), (1000, 1024, 1024), (300, 2048, 512), (4096, 512, 128),
+                                   (8192, 4, 2048), (4096, 56, 1024), (2048, 28, 1024)])
 def test_tc_gemm_dgrad_wgrad(lib, M, N, K):
     from dxvae_b200 import _lib
     g = torch.Generator().manual_seed(M + N + K)
