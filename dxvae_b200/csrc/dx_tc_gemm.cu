@@ -5,7 +5,8 @@
 //
 //   C[M,N] (op)= act( sum_r Aop(i,r) Bop(r,j) + bias[j] + add[i,j] )      (same contract as dx_gemm.h)
 //
-// One CTA per 128 x BN output tile (BN = 256 or 128), 192 threads:
+// Persistent CTAs (one per SM) walk the 128 x BN output tiles (BN = 256 / 128 / 64); two TMEM
+// accumulators let the epilogue of one tile overlap the main loop of the next.  192 threads:
 //   warp 0   : TMA producer  (cp.async.bulk.tensor, 128B swizzle, mbarrier complete_tx)
 //   warp 1   : TMEM allocation + single-thread tcgen05.mma issue, tcgen05.commit -> mbarriers
 //   warps 2-5: epilogue (tcgen05.ld 32x32b -> registers -> bias/act -> global, one row per thread)
@@ -33,7 +34,7 @@ template <int BN> struct TcCfg {
   static constexpr int B_BYTES = BN * TBK * 4;
   static constexpr int STAGE = A_BYTES + B_BYTES;
   static constexpr int STAGES = (BN == 256) ? 4 : (BN == 128 ? 6 : 8);
-  static constexpr int SMEM = STAGES * STAGE + 1024 /*align*/ + 256 /*barriers*/ + 4 * 32 * 36 * 4 /*epilogue staging*/;
+  static constexpr int SMEM = STAGES * STAGE + 1024 /*align*/ + 4 * 2 * 4096 /*store staging*/ + 256 /*barriers*/;
 };
 
 struct TcParams {
@@ -42,7 +43,6 @@ struct TcParams {
   const float* bias; const float* add; int64_t ldadd;
   int act, accum, k_chunk;
   int tma_store;    // 1: epilogue stores through TMA (bulk tensor store / reduce-add)
-  int exp;          // bring-up experiments (DX_TC_EXP): 1 skip global stores, 2 skip tmem ld
   long long* dbg;   // optional per-phase clock64() trace of CTA (0,0,0): DX_TC_DEBUG=1
 };
 
@@ -117,33 +117,36 @@ __device__ __forceinline__ float tc_act(float v, int act) {
 
 template <int BN, bool A_MN, bool B_MN>
 __global__ void __launch_bounds__(192, 1) k_tc_gemm(const __grid_constant__ CUtensorMap tmA,
-                                                    const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmC,
-                                                    const TcParams p) {
+                                                    const __grid_constant__ CUtensorMap tmB,
+                                                    const __grid_constant__ CUtensorMap tmC, const TcParams p) {
+  // Persistent: CTA b processes tiles b, b+grid, ... ; two accumulators in TMEM so the epilogue of
+  // tile i overlaps the main loop of tile i+1.
   using Cfg = TcCfg<BN>;
   constexpr int S = Cfg::STAGES;
   extern __shared__ uint8_t smem_raw[];
-  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;       // SWIZZLE_128B atoms need 1024-byte alignment
-  const uint32_t bars = base + S * Cfg::STAGE;                        // full[S], empty[S], tmem_full, tmem slot
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;       // swizzle atoms need 1024-byte alignment
+  const uint32_t stg_base = base + S * Cfg::STAGE;                    // 4 warps x 2 x 4 KB store staging
+  const uint32_t bars = stg_base + 4 * 2 * 4096;                      // full[S], empty[S], tfull[2], tempty[2], slot
   auto full_bar = [&](int s) { return bars + 8u * s; };
   auto empty_bar = [&](int s) { return bars + 8u * (S + s); };
-  const uint32_t tmem_full = bars + 8u * (2 * S);
-  const uint32_t tmem_slot = bars + 8u * (2 * S + 1);
+  auto tfull_bar = [&](int a) { return bars + 8u * (2 * S + a); };
+  auto tempty_bar = [&](int a) { return bars + 8u * (2 * S + 2 + a); };
+  const uint32_t tmem_slot = bars + 8u * (2 * S + 4);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int m0 = blockIdx.y * TBM, n0 = blockIdx.x * BN;
-  const int kbeg = blockIdx.z * p.k_chunk;
-  const int kend = min(p.K, kbeg + p.k_chunk);
-  const int nkb = (kend - kbeg + TBK - 1) / TBK;
-  const bool trace = p.dbg && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0;
+  const int gm = (p.M + TBM - 1) / TBM, gn = (p.N + BN - 1) / BN;
+  const int splits = (p.K + p.k_chunk - 1) / p.k_chunk;
+  const int total = gm * gn * splits;
+  const bool trace = p.dbg && blockIdx.x == 0;
   if (trace && threadIdx.x == 0) p.dbg[200] = clock64();
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < S; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-    mbar_init(tmem_full, 1);
+    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 4); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(BN) : "memory");
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(2 * BN) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -153,23 +156,34 @@ __global__ void __launch_bounds__(192, 1) k_tc_gemm(const __grid_constant__ CUte
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
   if (trace && threadIdx.x == 0) p.dbg[201] = clock64();
 
+  auto tile_coords = [&](int t, int& m0, int& n0, int& kbeg, int& nkb) {
+    const int mt = t % gm, nt = (t / gm) % gn, z = t / (gm * gn);     // m fastest: neighbours share the B tile in L2
+    m0 = mt * TBM; n0 = nt * BN; kbeg = z * p.k_chunk;
+    const int kend = min(p.K, kbeg + p.k_chunk);
+    nkb = (kend - kbeg + TBK - 1) / TBK;
+  };
+
   if (warp == 0) {
     if (lane == 0) {                                               // ---- TMA producer
-      for (int kb = 0; kb < nkb; ++kb) {
-        const int s = kb % S;
-        mbar_wait(empty_bar(s), ((kb / S) & 1) ^ 1);
-        if (trace && kb < 32) p.dbg[kb] = clock64();
-        mbar_expect_tx(full_bar(s), Cfg::STAGE);
-        const int k0 = kbeg + kb * TBK;
-        const uint32_t sa = base + s * Cfg::STAGE, sb = sa + A_BYTES;
-        if (!A_MN) tma_load_2d(&tmA, sa, full_bar(s), k0, m0);
-        else
+      uint32_t it = 0;
+      for (int t = blockIdx.x; t < total; t += gridDim.x) {
+        int m0, n0, kbeg, nkb; tile_coords(t, m0, n0, kbeg, nkb);
+        for (int kb = 0; kb < nkb; ++kb, ++it) {
+          const int s = it % S;
+          mbar_wait(empty_bar(s), ((it / S) & 1) ^ 1);
+          if (trace && it < 32) p.dbg[it] = clock64();
+          mbar_expect_tx(full_bar(s), Cfg::STAGE);
+          const int k0 = kbeg + kb * TBK;
+          const uint32_t sa = base + s * Cfg::STAGE, sb = sa + A_BYTES;
+          if (!A_MN) tma_load_2d(&tmA, sa, full_bar(s), k0, m0);
+          else
 #pragma unroll
-          for (int g = 0; g < TBM / 32; ++g) tma_load_2d(&tmA, sa + g * 4096, full_bar(s), m0 + g * 32, k0);
-        if (!B_MN) tma_load_2d(&tmB, sb, full_bar(s), k0, n0);
-        else
+            for (int g = 0; g < TBM / 32; ++g) tma_load_2d(&tmA, sa + g * 4096, full_bar(s), m0 + g * 32, k0);
+          if (!B_MN) tma_load_2d(&tmB, sb, full_bar(s), k0, n0);
+          else
 #pragma unroll
-          for (int g = 0; g < BN / 32; ++g) tma_load_2d(&tmB, sb + g * 4096, full_bar(s), n0 + g * 32, k0);
+            for (int g = 0; g < BN / 32; ++g) tma_load_2d(&tmB, sb + g * 4096, full_bar(s), n0 + g * 32, k0);
+        }
       }
     }
   } else if (warp == 1) {
@@ -177,140 +191,158 @@ __global__ void __launch_bounds__(192, 1) k_tc_gemm(const __grid_constant__ CUte
       // instruction descriptor: D=F32, A=B=TF32, majors, N>>3, M>>4   (cute::UMMA::InstrDescriptor)
       const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((A_MN ? 1u : 0u) << 15) | ((B_MN ? 1u : 0u) << 16) |
                              ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TBM >> 4) << 24);
-      for (int kb = 0; kb < nkb; ++kb) {
-        const int s = kb % S;
-        mbar_wait(full_bar(s), (kb / S) & 1);
-        if (trace && kb < 32) p.dbg[64 + kb] = clock64();
+      uint32_t it = 0, lt = 0;
+      for (int t = blockIdx.x; t < total; t += gridDim.x, ++lt) {
+        int m0, n0, kbeg, nkb; tile_coords(t, m0, n0, kbeg, nkb);
+        const uint32_t as = lt & 1;
+        mbar_wait(tempty_bar(as), ((lt >> 1) & 1) ^ 1);            // epilogue has drained this accumulator
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint32_t sa = base + s * Cfg::STAGE, sb = sa + A_BYTES;
+        const uint32_t tacc = tmem_base + as * BN;
+        for (int kb = 0; kb < nkb; ++kb, ++it) {
+          const int s = it % S;
+          mbar_wait(full_bar(s), (it / S) & 1);
+          if (trace && it < 32) p.dbg[64 + it] = clock64();
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const uint32_t sa = base + s * Cfg::STAGE, sb = sa + A_BYTES;
 #pragma unroll
-        for (int k = 0; k < TBK / 8; ++k) {                        // UMMA_K = 8 for tf32
-          // K-major: 8-row x 128 B atoms, SBO 1024; one UMMA_K = 32 B along the swizzled row.
-          // MN-major: 4-row atoms (SBO 512 B), 32-element MN groups 4096 B apart (LBO); UMMA_K = 8 rows.
-          const uint64_t ad = A_MN ? umma_desc(sa + k * 1024, 4096, 512, 1) : umma_desc(sa + k * 32, 16, 1024, 2);
-          const uint64_t bd = B_MN ? umma_desc(sb + k * 1024, 4096, 512, 1) : umma_desc(sb + k * 32, 16, 1024, 2);
-          umma_tf32(tmem_base, ad, bd, idesc, (kb | k) != 0 ? 1u : 0u);
+          for (int k = 0; k < TBK / 8; ++k) {                      // UMMA_K = 8 for tf32
+            // K-major: 8-row x 128 B atoms, SBO 1024; one UMMA_K = 32 B along the swizzled row.
+            // MN-major: 4-row atoms (SBO 512 B), 32-element MN groups 4096 B apart (LBO); UMMA_K = 8 rows.
+            const uint64_t ad = A_MN ? umma_desc(sa + k * 1024, 4096, 512, 1) : umma_desc(sa + k * 32, 16, 1024, 2);
+            const uint64_t bd = B_MN ? umma_desc(sb + k * 1024, 4096, 512, 1) : umma_desc(sb + k * 32, 16, 1024, 2);
+            umma_tf32(tacc, ad, bd, idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(empty_bar(s));                               // frees the smem stage when these MMAs retire
         }
-        umma_commit(empty_bar(s));                                 // frees the smem stage when these MMAs retire
+        umma_commit(tfull_bar(as));                                // accumulator complete
       }
-      umma_commit(tmem_full);                                      // accumulator complete
     }
   } else {                                                         // ---- epilogue: warps 2..5
-    mbar_wait(tmem_full, 0);
-    if (trace && threadIdx.x == 64) p.dbg[202] = clock64();
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const int q = warp & 3;                                        // TMEM lane quadrant this warp may read
-    // Each thread owns one accumulator row in TMEM; rows are re-distributed through a private
-    // per-warp staging tile (32 rows x 32 cols, pitch 36 floats: 128-bit accesses conflict-free both
-    // ways) so that global stores are coalesced: one warp instruction = 4 rows x 128 contiguous bytes.
-    float* stg = reinterpret_cast<float*>(smem_raw + (base - smem_u32(smem_raw)) + S * Cfg::STAGE + 256) +
-                 (warp - 2) * (32 * 36);
+    const uint32_t my_stg = stg_base + (uint32_t)(warp - 2) * 8192u;
+    float* stg = reinterpret_cast<float*>(smem_raw + (my_stg - smem_u32(smem_raw)));
     const bool vec = ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0) && (p.ldc % 4 == 0);
     const int rsub = lane >> 3, cc = (lane & 7) * 4;
-    if (p.tma_store) {
-      // All MMAs have retired (tmem_full), so the pipeline stages are free: reuse them as the
-      // store staging area.  Slab (c/32) of warp-quadrant q: 32 rows x 128 B, 128B-swizzled exactly
-      // as the C tensor map expects; each thread deposits its own row (conflict-free 128-bit
-      // writes), then one lane hands the 4 KB block to the TMA unit (plain store, or f32
-      // reduce-add for accumulate / split-K modes).  Bulk stores are not limited by the few
-      // epilogue warps' outstanding-store budget, unlike STG.
-      const int row = q * 32 + lane;
-      const int gi = m0 + row;
-      const bool row_ok = gi < p.M;
+    uint32_t lt = 0, nstore = 0;
+    for (int t = blockIdx.x; t < total; t += gridDim.x, ++lt) {
+      int m0, n0, kbeg, nkb; tile_coords(t, m0, n0, kbeg, nkb);
+      const uint32_t as = lt & 1;
+      mbar_wait(tfull_bar(as), (lt >> 1) & 1);
+      if (trace && threadIdx.x == 64 && lt < 8) p.dbg[208 + 2 * lt] = clock64();
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const uint32_t tacc = tmem_base + as * BN + ((uint32_t)(q * 32) << 16);
+      if (p.tma_store) {
+        // Each thread owns one accumulator row.  Rows go through a 128B-swizzled 32x32 staging slab
+        // (conflict-free 128-bit writes) and leave as one 4 KB TMA bulk store (plain, or f32
+        // reduce-add for accumulate / split-K modes): bulk stores are not limited by the few
+        // epilogue warps' outstanding-store budget, unlike STG (measured 12x faster here).
+        const int gi = m0 + q * 32 + lane;
+        const bool row_ok = gi < p.M;
 #pragma unroll 1
-      for (int c = 0; c < BN; c += 32) {
-        float v[32];
-        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c, v);
-        const int gj = n0 + c;
-        if (gj >= p.N) continue;                                   // warp-uniform
-        if (p.bias || p.add || p.act) {
+        for (int c = 0; c < BN; c += 32) {
+          float v[32];
+          tmem_ld32(tacc + (uint32_t)c, v);
+          const int gj = n0 + c;
+          if (gj >= p.N) continue;                                 // warp-uniform
+          if (p.bias || p.add || p.act) {
 #pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            float4 a4 = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (p.add && row_ok && gj + j + 3 < p.N) a4 = __ldg(reinterpret_cast<const float4*>(p.add + (int64_t)gi * p.ldadd + gj + j));
-            const float ad[4] = {a4.x, a4.y, a4.z, a4.w};
+            for (int j = 0; j < 32; j += 4) {
+              float4 a4 = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (p.add && row_ok && gj + j + 3 < p.N) a4 = __ldg(reinterpret_cast<const float4*>(p.add + (int64_t)gi * p.ldadd + gj + j));
+              const float ad[4] = {a4.x, a4.y, a4.z, a4.w};
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              if (gj + j + e < p.N) {
-                float t = v[j + e] + ad[e];
-                if (p.bias) t += __ldg(p.bias + gj + j + e);
-                v[j + e] = tc_act(t, p.act);
+              for (int e = 0; e < 4; ++e) {
+                if (gj + j + e < p.N) {
+                  float tt = v[j + e] + ad[e];
+                  if (p.bias) tt += __ldg(p.bias + gj + j + e);
+                  v[j + e] = tc_act(tt, p.act);
+                }
               }
             }
           }
-        }
-        const uint32_t slab = base + (uint32_t)(((c >> 5) * 4 + q) * 4096);
+          const uint32_t slab = my_stg + (nstore & 1) * 4096u;
+          if (nstore >= 2) {                                       // the store that last used this slab has read it
+            if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+            __syncwarp();
+          }
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const uint32_t dst = slab + (uint32_t)(lane * 128) + (uint32_t)(((j ^ (lane & 7)) << 4));
-          asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "f"(v[4 * j]), "f"(v[4 * j + 1]),
-                       "f"(v[4 * j + 2]), "f"(v[4 * j + 3]) : "memory");
+          for (int j = 0; j < 8; ++j) {
+            const uint32_t dst = slab + (uint32_t)(lane * 128) + (uint32_t)(((j ^ (lane & 7)) << 4));
+            asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "f"(v[4 * j]), "f"(v[4 * j + 1]),
+                         "f"(v[4 * j + 2]), "f"(v[4 * j + 3]) : "memory");
+          }
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+          __syncwarp();
+          if (lane == 0) {
+            if (p.accum == ACC_STORE) tma_store_2d(&tmC, slab, gj, m0 + q * 32);
+            else tma_reduce_add_2d(&tmC, slab, gj, m0 + q * 32);
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+          }
+          ++nstore;
         }
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        __syncwarp();
-        if (lane == 0) {
-          if (p.accum == ACC_STORE) tma_store_2d(&tmC, slab, gj, m0 + q * 32);
-          else tma_reduce_add_2d(&tmC, slab, gj, m0 + q * 32);
-          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-        }
-      }
-      if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-      __syncwarp();
-    } else
+      } else {
+        // Fallback (row scatter through c_idx, or rows that are not 16-byte aligned): per-warp
+        // 32x32 staging tile with pitch 36, then coalesced STG / RED.
 #pragma unroll 1
-    for (int c = 0; c < BN; c += 32) {
-      float v[32];
-      if (p.exp & 2) { for (int j = 0; j < 32; ++j) v[j] = (float)(c + j); }
-      else tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c, v);
-      if (n0 + c >= p.N) continue;                                 // warp-uniform
+        for (int c = 0; c < BN; c += 32) {
+          float v[32];
+          tmem_ld32(tacc + (uint32_t)c, v);
+          if (n0 + c >= p.N) continue;                             // warp-uniform
 #pragma unroll
-      for (int j = 0; j < 32; j += 4)
-        *reinterpret_cast<float4*>(stg + lane * 36 + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-      __syncwarp();
-      const int gj = n0 + c + cc;
+          for (int j = 0; j < 32; j += 4)
+            *reinterpret_cast<float4*>(stg + lane * 36 + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+          __syncwarp();
+          const int gj = n0 + c + cc;
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int rr = i * 4 + rsub;
-        const int gi = m0 + q * 32 + rr;
-        if (gi < p.M && gj < p.N && !((p.exp & 1) && gi >= 0)) {
-          const float4 x = *reinterpret_cast<const float4*>(stg + rr * 36 + cc);
-          float o[4] = {x.x, x.y, x.z, x.w};
-          const int64_t crow = p.c_idx ? p.c_idx[gi] : gi;
-          float* dst = p.C + crow * p.ldc + gj;
+          for (int i = 0; i < 8; ++i) {
+            const int rr = i * 4 + rsub;
+            const int gi = m0 + q * 32 + rr;
+            if (gi < p.M && gj < p.N) {
+              const float4 x = *reinterpret_cast<const float4*>(stg + rr * 36 + cc);
+              float o[4] = {x.x, x.y, x.z, x.w};
+              const int64_t crow = p.c_idx ? p.c_idx[gi] : gi;
+              float* dst = p.C + crow * p.ldc + gj;
 #pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            if (gj + e < p.N) {
-              float t = o[e];
-              if (p.bias) t += __ldg(p.bias + gj + e);
-              if (p.add) t += __ldg(p.add + (int64_t)gi * p.ldadd + gj + e);
-              o[e] = tc_act(t, p.act);
+              for (int e = 0; e < 4; ++e) {
+                if (gj + e < p.N) {
+                  float tt = o[e];
+                  if (p.bias) tt += __ldg(p.bias + gj + e);
+                  if (p.add) tt += __ldg(p.add + (int64_t)gi * p.ldadd + gj + e);
+                  o[e] = tc_act(tt, p.act);
+                }
+              }
+              if (p.accum == ACC_ATOMIC) {
+#pragma unroll
+                for (int e = 0; e < 4; ++e)
+                  if (gj + e < p.N) atomicAdd(dst + e, o[e]);
+              } else if (vec && gj + 3 < p.N) {
+                float4 w4 = make_float4(o[0], o[1], o[2], o[3]);
+                if (p.accum == ACC_ADD) { const float4 old = *reinterpret_cast<float4*>(dst); w4.x += old.x; w4.y += old.y; w4.z += old.z; w4.w += old.w; }
+                *reinterpret_cast<float4*>(dst) = w4;
+              } else {
+#pragma unroll
+                for (int e = 0; e < 4; ++e)
+                  if (gj + e < p.N) { if (p.accum == ACC_ADD) dst[e] += o[e]; else dst[e] = o[e]; }
+              }
             }
           }
-          if (p.accum == ACC_ATOMIC) {
-#pragma unroll
-            for (int e = 0; e < 4; ++e)
-              if (gj + e < p.N) atomicAdd(dst + e, o[e]);
-          } else if (vec && gj + 3 < p.N) {
-            float4 w = make_float4(o[0], o[1], o[2], o[3]);
-            if (p.accum == ACC_ADD) { const float4 old = *reinterpret_cast<float4*>(dst); w.x += old.x; w.y += old.y; w.z += old.z; w.w += old.w; }
-            *reinterpret_cast<float4*>(dst) = w;
-          } else {
-#pragma unroll
-            for (int e = 0; e < 4; ++e)
-              if (gj + e < p.N) { if (p.accum == ACC_ADD) dst[e] += o[e]; else dst[e] = o[e]; }
-          }
+          __syncwarp();
         }
       }
+      // this warp's TMEM reads of the accumulator are complete: hand it back to the MMA warp
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       __syncwarp();
+      if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tempty_bar(as)) : "memory");
+      if (trace && threadIdx.x == 64 && lt < 8) p.dbg[209 + 2 * lt] = clock64();
     }
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // staging must outlive the stores
+    __syncwarp();
   }
-  if (trace && threadIdx.x == 64) p.dbg[203] = clock64();
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
-  if (trace && threadIdx.x == 0) p.dbg[204] = clock64();
   if (warp == 1) {
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(BN) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(2 * BN) : "memory");
   }
 }
 
@@ -376,8 +408,11 @@ bool launch_tc(dx_stream_t s, const GemmP& g) {
   static const bool want_dbg = getenv("DX_TC_DEBUG") != nullptr;
   if (want_dbg && !dbg) cudaMalloc(&dbg, 256 * sizeof(long long));
   if (want_dbg) cudaMemsetAsync(dbg, 0, 256 * sizeof(long long), s);
-  TcParams p{g.M, g.N, g.K, g.C, g.ldc, g.c_idx, g.bias, g.add, g.ldadd, g.act, g.accum, k_chunk, tma_store ? 1 : 0, getenv("DX_TC_EXP") ? atoi(getenv("DX_TC_EXP")) : 0, want_dbg ? dbg : nullptr};
-  dim3 grid(gn, gm, splits);
+  TcParams p{g.M, g.N, g.K, g.C, g.ldc, g.c_idx, g.bias, g.add, g.ldadd, g.act, g.accum, k_chunk, tma_store ? 1 : 0, want_dbg ? dbg : nullptr};
+  static int num_sms = 0;
+  if (!num_sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev); }
+  const int total_tiles = gm * gn * splits;
+  dim3 grid(total_tiles < num_sms ? total_tiles : num_sms);
   static bool attr_set = false;   // per BN instantiation; all four operand-major variants share the footprint
   if (!attr_set) {
     cudaFuncSetAttribute(k_tc_gemm<BN, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM);
@@ -397,8 +432,10 @@ bool launch_tc(dx_stream_t s, const GemmP& g) {
     cudaStreamSynchronize(s);
     cudaMemcpy(h, dbg, sizeof(h), cudaMemcpyDeviceToHost);
     const long long t0 = h[200];
-    fprintf(stderr, "[tc trace] M=%d N=%d K=%d BN=%d splits=%d | setup %lld | epi start %lld end %lld | cta end %lld\n", g.M, g.N, g.K, BN, splits,
-            h[201] - t0, h[202] - t0, h[203] - t0, h[204] - t0);
+    fprintf(stderr, "[tc trace] M=%d N=%d K=%d BN=%d splits=%d tiles=%d grid=%d | setup %lld | epilogues:", g.M, g.N, g.K, BN,
+            splits, total_tiles, (int)grid.x, h[201] - t0);
+    for (int i = 0; i < 8 && h[208 + 2 * i]; ++i) fprintf(stderr, " [%lld..%lld]", h[208 + 2 * i] - t0, h[209 + 2 * i] - t0);
+    fprintf(stderr, "\n");
     fprintf(stderr, "  producer(empty ok):");
     for (int i = 0; i < 20 && h[i]; ++i) fprintf(stderr, " %lld", h[i] - t0);
     fprintf(stderr, "\n  mma(full ok):      ");
