@@ -8,6 +8,7 @@
 // Roofline: FP32 FFMA pipe (148 SMs x 128 lanes x 2 flop x f_SM); operands come from
 // L2 (weights <= 8 MB per product, activations streamed once).
 #include "dx_gemm.h"
+#include <stdlib.h>
 
 namespace dx {
 
@@ -236,7 +237,7 @@ struct ProfState {
   bool on = false;
   int cap = 0, used = 0;
   cudaEvent_t* e0 = nullptr; cudaEvent_t* e1 = nullptr;
-  double* flops = nullptr; int* cls = nullptr;
+  double* flops = nullptr; int* cls = nullptr; int* shape = nullptr;   // shape: M,N,K,form per slot
 } g_prof;
 
 template <int BM, int BN, int TM, int TN>
@@ -292,6 +293,7 @@ void prof_begin(int max_launches) {
   g_prof.cap = max_launches; g_prof.used = 0;
   g_prof.e0 = new cudaEvent_t[max_launches]; g_prof.e1 = new cudaEvent_t[max_launches];
   g_prof.flops = new double[max_launches]; g_prof.cls = new int[max_launches];
+  g_prof.shape = new int[4 * (size_t)max_launches];
   for (int i = 0; i < max_launches; ++i) { cudaEventCreate(&g_prof.e0[i]); cudaEventCreate(&g_prof.e1[i]); }
   g_prof.on = true;
 }
@@ -302,14 +304,17 @@ void prof_end(double* ms, double* flops, long long* n) {
   g_prof.on = false;
   cudaDeviceSynchronize();
   double tms[3] = {0, 0, 0}, tfl[3] = {0, 0, 0}; long long tn[3] = {0, 0, 0};
+  const bool dump = getenv("DX_PROF_DUMP") != nullptr;
   for (int i = 0; i < g_prof.used; ++i) {
     float t = 0.f;
     if (cudaEventElapsedTime(&t, g_prof.e0[i], g_prof.e1[i]) == cudaSuccess) {
       tms[g_prof.cls[i]] += t; tfl[g_prof.cls[i]] += g_prof.flops[i]; tn[g_prof.cls[i]]++;
+      if (dump) fprintf(stderr, "[gemm] cls=%d M=%d N=%d K=%d form=%d us=%.1f tflops=%.1f\n", g_prof.cls[i], g_prof.shape[4 * i],
+                        g_prof.shape[4 * i + 1], g_prof.shape[4 * i + 2], g_prof.shape[4 * i + 3], t * 1e3, g_prof.flops[i] / (t * 1e-3) / 1e12);
     }
   }
   for (int i = 0; i < g_prof.cap; ++i) { cudaEventDestroy(g_prof.e0[i]); cudaEventDestroy(g_prof.e1[i]); }
-  delete[] g_prof.e0; delete[] g_prof.e1; delete[] g_prof.flops; delete[] g_prof.cls;
+  delete[] g_prof.e0; delete[] g_prof.e1; delete[] g_prof.flops; delete[] g_prof.cls; delete[] g_prof.shape;
   g_prof = ProfState();
   for (int c = 0; c < 3; ++c) { if (ms) ms[c] = tms[c]; if (flops) flops[c] = tfl[c]; if (n) n[c] = tn[c]; }
 }
@@ -324,6 +329,8 @@ void gemm(dx_stream_t s, const GemmP& p) {
   if (g_prof.on && g_prof.used < g_prof.cap) {
     slot = g_prof.used++;
     g_prof.flops[slot] = 2.0 * p.M * (double)p.N * p.K;
+    g_prof.shape[4 * slot] = p.M; g_prof.shape[4 * slot + 1] = p.N; g_prof.shape[4 * slot + 2] = p.K;
+    g_prof.shape[4 * slot + 3] = (p.a_kc ? 0 : 2) + (p.b_kc ? 0 : 1) + 4 * p.accum;   // 0 fwd, 1 dgrad, 3 wgrad; +4*accum
     cudaEventRecord(g_prof.e0[slot], s);
   }
   int cls;

@@ -43,6 +43,7 @@ struct TcParams {
   const float* bias; const float* add; int64_t ldadd;
   int act, accum, k_chunk;
   int tma_store;    // 1: epilogue stores through TMA (bulk tensor store / reduce-add)
+  int add_tma;      // 1: the `add` matrix tile is prefetched into the staging slab by TMA
   long long* dbg;   // optional per-phase clock64() trace of CTA (0,0,0): DX_TC_DEBUG=1
 };
 
@@ -118,7 +119,8 @@ __device__ __forceinline__ float tc_act(float v, int act) {
 template <int BN, bool A_MN, bool B_MN>
 __global__ void __launch_bounds__(192, 1) k_tc_gemm(const __grid_constant__ CUtensorMap tmA,
                                                     const __grid_constant__ CUtensorMap tmB,
-                                                    const __grid_constant__ CUtensorMap tmC, const TcParams p) {
+                                                    const __grid_constant__ CUtensorMap tmC,
+                                                    const __grid_constant__ CUtensorMap tmAdd, const TcParams p) {
   // Persistent: CTA b processes tiles b, b+grid, ... ; two accumulators in TMEM so the epilogue of
   // tile i overlaps the main loop of tile i+1.
   using Cfg = TcCfg<BN>;
@@ -132,6 +134,7 @@ __global__ void __launch_bounds__(192, 1) k_tc_gemm(const __grid_constant__ CUte
   auto tfull_bar = [&](int a) { return bars + 8u * (2 * S + a); };
   auto tempty_bar = [&](int a) { return bars + 8u * (2 * S + 2 + a); };
   const uint32_t tmem_slot = bars + 8u * (2 * S + 4);
+  auto add_bar = [&](int w, int sl) { return bars + 8u * (2 * S + 5 + 2 * w + sl); };   // per epilogue warp, per slab
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int gm = (p.M + TBM - 1) / TBM, gn = (p.N + BN - 1) / BN;
@@ -143,6 +146,7 @@ __global__ void __launch_bounds__(192, 1) k_tc_gemm(const __grid_constant__ CUte
   if (threadIdx.x == 0) {
     for (int s = 0; s < S; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
     for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 4); }
+    for (int w = 0; w < 4; ++w) { mbar_init(add_bar(w, 0), 1); mbar_init(add_bar(w, 1), 1); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -227,6 +231,19 @@ __global__ void __launch_bounds__(192, 1) k_tc_gemm(const __grid_constant__ CUte
     for (int t = blockIdx.x; t < total; t += gridDim.x, ++lt) {
       int m0, n0, kbeg, nkb; tile_coords(t, m0, n0, kbeg, nkb);
       const uint32_t as = lt & 1;
+      const int nch = (min(BN, p.N - n0) + 31) / 32;               // 32-column chunks of this tile that exist
+      // `add` tile prefetch: chunk i of this warp's 32 rows lands in the slab it will later be stored
+      // from.  Chunk 0 is requested before waiting for the accumulator, chunk i+1 while chunk i is
+      // being processed, so the L2 latency stays off the critical path.
+      auto issue_add = [&](int ci, uint32_t n) {
+        const uint32_t sl = n & 1;
+        mbar_expect_tx(add_bar(warp - 2, sl), 4096);
+        tma_load_2d(&tmAdd, my_stg + sl * 4096u, add_bar(warp - 2, sl), n0 + ci * 32, m0 + q * 32);
+      };
+      if (p.add_tma && lane == 0) {
+        asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");   // the store that last used this slab is done with it
+        issue_add(0, nstore);
+      }
       mbar_wait(tfull_bar(as), (lt >> 1) & 1);
       if (trace && threadIdx.x == 64 && lt < 8) p.dbg[208 + 2 * lt] = clock64();
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -244,24 +261,58 @@ __global__ void __launch_bounds__(192, 1) k_tc_gemm(const __grid_constant__ CUte
           tmem_ld32(tacc + (uint32_t)c, v);
           const int gj = n0 + c;
           if (gj >= p.N) continue;                                 // warp-uniform
-          if (p.bias || p.add || p.act) {
+          const bool full = gj + 32 <= p.N;                        // warp-uniform: whole chunk in bounds
+          if (p.add_tma) {
+            const int ci = c >> 5;
+            if (lane == 0 && ci + 1 < nch) {
+              asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // slab of chunk ci+1 = slab of store ci-1
+              issue_add(ci + 1, nstore + 1);
+            }
+            mbar_wait(add_bar(warp - 2, nstore & 1), (nstore >> 1) & 1);
+            const uint32_t sl = my_stg + (nstore & 1) * 4096u + (uint32_t)(lane * 128);
 #pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              float4 a4 = make_float4(0.f, 0.f, 0.f, 0.f);
-              if (p.add && row_ok && gj + j + 3 < p.N) a4 = __ldg(reinterpret_cast<const float4*>(p.add + (int64_t)gi * p.ldadd + gj + j));
-              const float ad[4] = {a4.x, a4.y, a4.z, a4.w};
+            for (int j = 0; j < 8; ++j) {
+              float a0, a1, a2, a3;
+              asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(a0), "=f"(a1), "=f"(a2), "=f"(a3)
+                           : "r"(sl + (uint32_t)(((j ^ (lane & 7)) << 4))) : "memory");
+              v[4 * j] += a0; v[4 * j + 1] += a1; v[4 * j + 2] += a2; v[4 * j + 3] += a3;
+            }
+          } else if (p.add) {
+            if (row_ok) {
+              const float* ar = p.add + (int64_t)gi * p.ldadd + gj;
+              if (full) {
 #pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                if (gj + j + e < p.N) {
-                  float tt = v[j + e] + ad[e];
-                  if (p.bias) tt += __ldg(p.bias + gj + j + e);
-                  v[j + e] = tc_act(tt, p.act);
+                for (int j = 0; j < 32; j += 4) {
+                  const float4 a4 = __ldg(reinterpret_cast<const float4*>(ar + j));
+                  v[j] += a4.x; v[j + 1] += a4.y; v[j + 2] += a4.z; v[j + 3] += a4.w;
                 }
+              } else {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) if (gj + j < p.N) v[j] += __ldg(ar + j);
               }
             }
           }
+          if (p.bias) {
+            if (full) {
+#pragma unroll
+              for (int j = 0; j < 32; j += 4) {
+                const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + gj + j));   // same address in every lane
+                v[j] += b4.x; v[j + 1] += b4.y; v[j + 2] += b4.z; v[j + 3] += b4.w;
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) if (gj + j < p.N) v[j] += __ldg(p.bias + gj + j);
+            }
+          }
+          if (p.act == ACT_RELU) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+          } else if (p.act != ACT_NONE) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = tc_act(v[j], p.act);
+          }
           const uint32_t slab = my_stg + (nstore & 1) * 4096u;
-          if (nstore >= 2) {                                       // the store that last used this slab has read it
+          if (nstore >= 2 && !p.add_tma) {                         // the store that last used this slab has read it
             if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
             __syncwarp();
           }
@@ -393,6 +444,10 @@ bool launch_tc(dx_stream_t s, const GemmP& g) {
   CUtensorMap tc;
   if (tma_store) { if (!make_map(&tc, g.C, g.M, g.N, g.ldc, 32, 32, false, true)) return false; }
   else tc = ta;
+  const bool add_tma = tma_store && g.add && ((reinterpret_cast<uintptr_t>(g.add) & 15) == 0) && (g.ldadd % 4 == 0);
+  CUtensorMap tadd;
+  if (add_tma) { if (!make_map(&tadd, g.add, g.M, g.N, g.ldadd, 32, 32, false, true)) return false; }
+  else tadd = ta;
   const int gm = (g.M + TBM - 1) / TBM, gn = (g.N + BN - 1) / BN;
   int splits = 1;
   if (g.accum == ACC_ATOMIC) {
@@ -408,7 +463,7 @@ bool launch_tc(dx_stream_t s, const GemmP& g) {
   static const bool want_dbg = getenv("DX_TC_DEBUG") != nullptr;
   if (want_dbg && !dbg) cudaMalloc(&dbg, 256 * sizeof(long long));
   if (want_dbg) cudaMemsetAsync(dbg, 0, 256 * sizeof(long long), s);
-  TcParams p{g.M, g.N, g.K, g.C, g.ldc, g.c_idx, g.bias, g.add, g.ldadd, g.act, g.accum, k_chunk, tma_store ? 1 : 0, want_dbg ? dbg : nullptr};
+  TcParams p{g.M, g.N, g.K, g.C, g.ldc, g.c_idx, g.bias, g.add, g.ldadd, g.act, g.accum, k_chunk, tma_store ? 1 : 0, add_tma ? 1 : 0, want_dbg ? dbg : nullptr};
   static int num_sms = 0;
   if (!num_sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev); }
   const int total_tiles = gm * gn * splits;
@@ -421,7 +476,7 @@ bool launch_tc(dx_stream_t s, const GemmP& g) {
     cudaFuncSetAttribute(k_tc_gemm<BN, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM);
     attr_set = true;
   }
-  auto run = [&](auto kern) { kern<<<grid, 192, Cfg::SMEM, s>>>(ta, tb, tc, p); };
+  auto run = [&](auto kern) { kern<<<grid, 192, Cfg::SMEM, s>>>(ta, tb, tc, tadd, p); };
   if (g.a_kc && g.b_kc) run(k_tc_gemm<BN, false, false>);
   else if (g.a_kc && !g.b_kc) run(k_tc_gemm<BN, false, true>);
   else if (!g.a_kc && !g.b_kc) run(k_tc_gemm<BN, true, true>);
