@@ -24,6 +24,8 @@ SIGNATURES = {
     "dxvae_param_entry": (C.c_int, [C.c_int, C.POINTER(ParamEntry)]),
     "dxvae_batch_build_host": (C.c_int, [I64, P, P, P, P, P, P, P, P, P, P, C.POINTER(I32)]),
     "dxvae_batch_schedule": (C.c_int, [I64, P, P, P, P, P, P, SZ, P]),
+    "dxvae_batch_steps": (C.c_int, [I64, P, P, P, P, P, SZ, P]),
+    "dxvae_batch_steps_host": (C.c_int, [I64, P, P, P]),
     "dxvae_pack_graphs": (C.c_int, [I64, P, P, P, P, P]),
     "dxvae_unpack_graphs": (C.c_int, [I64, P, P, P, P, P]),
     "dxvae_voices_to_graphs": (C.c_int, [I64, P, P, P, P, P, P, P]),
@@ -32,8 +34,8 @@ SIGNATURES = {
     "dxvae_encode_fwd": (C.c_int, [P, I64, P, P, I32, P, P, P, P, P, SZ, C.c_int, C.c_int, P]),
     "dxvae_reparameterize": (C.c_int, [I64, P, P, P, P, P]),
     "dxvae_decode_greedy": (C.c_int, [P, I64, P, P, P, P, P, P, SZ, P]),
-    "dxvae_elbo_step": (C.c_int, [P, I64, P, P, P, I32, P, P, P, F, F, F, F, P, P, P, P, P, SZ, C.c_int, P]),
-    "dxvae_loss_step": (C.c_int, [P, I64, P, P, P, P, P, P, F, F, F, F, P, P, P, P, P, SZ, C.c_int, P]),
+    "dxvae_elbo_step": (C.c_int, [P, I64, P, P, P, I32, P, P, P, F, F, F, F, P, P, P, P, P, SZ, C.c_int, P, P, P]),
+    "dxvae_loss_step": (C.c_int, [P, I64, P, P, P, P, P, P, F, F, F, F, P, P, P, P, P, SZ, C.c_int, P, P, P]),
     "dxvae_encode_bwd": (C.c_int, [P, I64, P, P, I32, P, P, P, P, P, P, P, SZ, C.c_int, P]),
     "dxvae_adamw_step": (C.c_int, [I64, P, P, P, P, F, F, F, F, F, I64, F, P]),
     "dxvae_test_gemm": (C.c_int, [C.c_int, I64, I64, I64, P, I64, P, I64, P, I64, P, C.c_int, C.c_int, P]),

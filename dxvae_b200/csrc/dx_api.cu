@@ -157,6 +157,14 @@ int dxvae_batch_schedule(int64_t B, const uint64_t* adj, uint8_t* level, int32_t
   return batch_schedule(DX_ST(stream), B, adj, level, level_ptr, level_rows, level_ptr_host, workspace,
                         workspace_bytes);
 }
+int dxvae_batch_steps(int64_t B, const uint64_t* adj, int32_t* step_ptr, int32_t* step_rows, int32_t* step_ptr_host,
+                      void* workspace, size_t workspace_bytes, void* stream) {
+  return batch_steps(DX_ST(stream), B, adj, step_ptr, step_rows, step_ptr_host, workspace, workspace_bytes);
+}
+int dxvae_batch_steps_host(int64_t B, const uint64_t* adj_host, int32_t* step_ptr_host, int32_t* step_rows_host) {
+  DX_CHECK(B > 0, "batch_steps_host: empty batch");
+  return batch_steps_host(B, adj_host, step_ptr_host, step_rows_host);
+}
 int dxvae_pack_graphs(int64_t B, const float* Xg, const float* Pg, float* Xn, int32_t* cls, void* stream) {
   DX_CHECK(B > 0, "pack_graphs: empty batch");
   return pack_graphs(DX_ST(stream), B, Xg, Pg, Xn, cls);
@@ -198,11 +206,13 @@ int dxvae_elbo_step(const float* weights, int64_t B, const float* Xn, const int3
                     int32_t n_levels, const int32_t* level_ptr_host, const int32_t* level_rows, const float* eps,
                     float w_env, float w_frq, float w_kld, float inv_batch, float* loss5, float* mu_out,
                     float* std_out, float* grads, void* workspace, size_t workspace_bytes, int precision,
-                    void* stream) {
+                    const int32_t* step_ptr_host, const int32_t* step_rows, void* stream) {
   DX_BATCH_OK(B);
   DX_CHECK(n_levels >= 1 && n_levels <= 6, "elbo_step: n_levels=%d", n_levels);
+  DX_CHECK((step_ptr_host == nullptr) == (step_rows == nullptr), "elbo_step: step_ptr_host and step_rows go together");
   DX_CHECK(precision == PREC_FP32 || precision == PREC_TF32, "elbo_step: unknown precision %d", precision);
   Batch bt{B, Xn, cls, adj, n_levels, level_ptr_host, level_rows};
+  bt.step_ptr = step_ptr_host; bt.step_rows = step_rows;
   LossW lw{w_env, w_frq, w_kld, inv_batch};
   return elbo_step(DX_ST(stream), weights, bt, eps, lw, loss5, mu_out, std_out, grads, workspace, workspace_bytes,
                    precision);
@@ -210,9 +220,12 @@ int dxvae_elbo_step(const float* weights, int64_t B, const float* Xn, const int3
 int dxvae_loss_step(const float* weights, int64_t B, const float* Xn, const int32_t* cls, const uint64_t* adj,
                     const float* mu, const float* std_, const float* eps, float w_env, float w_frq, float w_kld,
                     float inv_batch, float* loss5, float* grads, float* dmu, float* dstd, void* workspace,
-                    size_t workspace_bytes, int precision, void* stream) {
+                    size_t workspace_bytes, int precision, const int32_t* step_ptr_host, const int32_t* step_rows,
+                    void* stream) {
   DX_BATCH_OK(B);
+  DX_CHECK((step_ptr_host == nullptr) == (step_rows == nullptr), "loss_step: step_ptr_host and step_rows go together");
   Batch bt{B, Xn, cls, adj, 0, nullptr, nullptr};
+  bt.step_ptr = step_ptr_host; bt.step_rows = step_rows;
   LossW lw{w_env, w_frq, w_kld, inv_batch};
   return loss_step(DX_ST(stream), weights, bt, mu, std_, eps, lw, loss5, grads, dmu, dstd, workspace, workspace_bytes,
                    precision);

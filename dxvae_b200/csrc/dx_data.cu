@@ -175,6 +175,111 @@ int batch_schedule(dx_stream_t, int64_t B, const uint64_t* adj, uint8_t* level, 
 }
 #endif
 
+// ---- decoder step schedule ---------------------------------------------------------------------
+// Teacher forcing replays 21 (vi,vj) re-propagates per graph, but a re-propagate only changes the
+// node state when the step adds an edge (vj->vi or vi->vj); otherwise it is the identity
+// (model.py:353-358 with nothing added).  step t = vi*(vi-1)/2 + (vi-1-vj) (the order of
+// model.py:311,347).  step_rows[step_ptr[t] .. step_ptr[t+1]) = ascending graph ids that are
+// active at step t.
+DX_HD DX_INLINE int step_vi(int t) { int vi = 1; while ((vi + 1) * vi / 2 <= t) ++vi; return vi; }
+DX_HD DX_INLINE bool step_active(uint64_t A, int t) {
+  const int vi = step_vi(t), vj = vi - 1 - (t - vi * (vi - 1) / 2);
+  return (abit(A, vj, vi) | abit(A, vi, vj)) != 0;
+}
+
+static void steps_host(int64_t B, const uint64_t* adj, int32_t* step_ptr, int32_t* step_rows) {
+  int64_t pos = 0;
+  for (int t = 0; t < 21; ++t) {
+    step_ptr[t] = (int32_t)pos;
+    for (int64_t b = 0; b < B; ++b)
+      if (step_active(adj[b], t)) step_rows[pos++] = (int32_t)b;
+  }
+  step_ptr[21] = (int32_t)pos;
+}
+
+#ifndef DX_EMU
+namespace {
+constexpr int NSTEPB = 21;
+__global__ void __launch_bounds__(SCH_T) k_steps_count(int64_t B, const uint64_t* __restrict__ adj,
+                                                       int32_t* __restrict__ counts, int nblk) {
+  __shared__ int cnt[NSTEPB];
+  if (threadIdx.x < NSTEPB) cnt[threadIdx.x] = 0;
+  __syncthreads();
+  const int64_t b = (int64_t)blockIdx.x * SCH_T + threadIdx.x;
+  if (b < B) {
+    const uint64_t A = adj[b];
+    for (int t = 0; t < NSTEPB; ++t) if (step_active(A, t)) atomicAdd(&cnt[t], 1);
+  }
+  __syncthreads();
+  if (threadIdx.x < NSTEPB) counts[threadIdx.x * nblk + blockIdx.x] = cnt[threadIdx.x];
+}
+__global__ void k_steps_scan(int32_t* __restrict__ counts, int nblk, int32_t* __restrict__ step_ptr) {
+  __shared__ int tot[NSTEPB];
+  const int bin = threadIdx.x;
+  if (bin < NSTEPB) {
+    int s = 0;
+    for (int k = 0; k < nblk; ++k) { const int c = counts[bin * nblk + k]; counts[bin * nblk + k] = s; s += c; }
+    tot[bin] = s;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int s = 0;
+    for (int q = 0; q < NSTEPB; ++q) { const int c = tot[q]; tot[q] = s; step_ptr[q] = s; s += c; }
+    step_ptr[NSTEPB] = s;
+  }
+  __syncthreads();
+  if (bin < NSTEPB)
+    for (int k = 0; k < nblk; ++k) counts[bin * nblk + k] += tot[bin];
+}
+__global__ void __launch_bounds__(SCH_T) k_steps_scatter(int64_t B, const uint64_t* __restrict__ adj,
+                                                         const int32_t* __restrict__ offsets, int nblk,
+                                                         int32_t* __restrict__ step_rows) {
+  __shared__ int wsum[32];
+  const int64_t b = (int64_t)blockIdx.x * SCH_T + threadIdx.x;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const uint64_t A = (b < B) ? adj[b] : 0ull;
+  for (int t = 0; t < NSTEPB; ++t) {
+    const bool f = (b < B) && step_active(A, t);
+    const unsigned bal = __ballot_sync(0xffffffffu, f);
+    const int inwarp = __popc(bal & ((1u << lane) - 1));
+    if (lane == 0) wsum[wid] = __popc(bal);
+    __syncthreads();
+    int base = 0;
+    for (int k = 0; k < wid; ++k) base += wsum[k];
+    if (f) step_rows[offsets[t * nblk + blockIdx.x] + base + inwarp] = (int32_t)b;
+    __syncthreads();
+  }
+}
+}  // namespace
+
+int batch_steps(dx_stream_t st, int64_t B, const uint64_t* adj, int32_t* step_ptr, int32_t* step_rows,
+                int32_t* step_ptr_host, void* ws, size_t ws_bytes) {
+  DX_CHECK(B > 0 && (int64_t)21 * B < (1ll << 31), "batch_steps: bad batch size");
+  const int nblk = (int)((B + SCH_T - 1) / SCH_T);
+  Arena ar(ws, ws_bytes);
+  int32_t* counts = ar.take<int32_t>((size_t)NSTEPB * nblk);
+  DX_CHECK(!ar.overflow, "batch_steps: workspace too small (%zu < %zu)", ws_bytes, ar.off);
+  k_steps_count<<<nblk, SCH_T, 0, st>>>(B, adj, counts, nblk);
+  k_steps_scan<<<1, 32, 0, st>>>(counts, nblk, step_ptr);
+  k_steps_scatter<<<nblk, SCH_T, 0, st>>>(B, adj, counts, nblk, step_rows);
+  g_launches += 3;
+  cudaMemcpyAsync(step_ptr_host, step_ptr, 22 * sizeof(int32_t), cudaMemcpyDeviceToHost, st);
+  cudaStreamSynchronize(st);
+  return check_launch("batch_steps");
+}
+#else
+int batch_steps(dx_stream_t, int64_t B, const uint64_t* adj, int32_t* step_ptr, int32_t* step_rows,
+                int32_t* step_ptr_host, void*, size_t) {
+  steps_host(B, adj, step_ptr, step_rows);
+  memcpy(step_ptr_host, step_ptr, 22 * sizeof(int32_t));
+  return 0;
+}
+#endif
+int batch_steps_host(int64_t B, const uint64_t* adj, int32_t* step_ptr, int32_t* step_rows) {
+  steps_host(B, adj, step_ptr, step_rows);
+  return 0;
+}
+
 // ---- layout conversion ---------------------------------------------------------------------
 int pack_graphs(dx_stream_t st, int64_t B, const float* Xg, const float* Pg, float* Xn, int32_t* cls) {
   foreach (st, B * NN * XP, [=] DX_HD(int64_t i) {

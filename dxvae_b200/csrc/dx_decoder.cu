@@ -22,6 +22,7 @@ DecWs carve_dec(Arena& ar, int64_t B, bool train) {
   w.z = ar.take<float>(b * Z); w.Hinit = ar.take<float>(b * H); w.Hd = ar.take<float>(7 * b * H);
   w.Pg = ar.take<float>(6 * b * 2 * H); w.Pm = ar.take<float>(6 * b * 2 * H); w.Q = ar.take<float>(6 * b * 4 * H);
   w.gh = ar.take<float>(b * G3); w.ghl0 = ar.take<float>(b * G3); w.Hrun = ar.take<float>(b * H);
+  if (train) { w.U = ar.take<float>(b * 4 * H); w.UC = ar.take<float>(b * 4 * H); w.dHiC = ar.take<float>(b * H); }
   auto per_node = [&](float** arr, size_t cols, bool need) {
     float* shared = need ? nullptr : ar.take<float>(b * cols);
     for (int v = 0; v < 7; ++v) arr[v] = need ? ar.take<float>(b * cols) : shared;
@@ -348,6 +349,40 @@ void decode_fwd_impl(dx_stream_t st, const Weights& W, int B, const float* z, co
                0, S_SELF, adj};
     cell_fwd(st, p2);
     zero_async(st, w.Hrun, sizeof(float) * (size_t)B * H);
+    const bool compact = train && io.bt->step_ptr != nullptr;
+    if (compact) {
+      // Compacted teacher forcing (DESIGN.md "identity steps"): a re-propagate changes node vi only for
+      // graphs where the step adds an edge.  Hd[vi] holds the CURRENT state of node vi for every
+      // graph and U = Hd[vi] W_e0[:, :512]^T is kept consistent with it, so the edge head of a step is
+      // element-wise for all graphs and the GRU / projection products run on the active rows only.
+      float* Hcur = w.Hd + (size_t)vi * B * H;
+      copy_async(st, Hcur, w.Hi_p2[vi], sizeof(float) * (size_t)B * H);
+      linear_fwd(st, B, 4 * H, H, w.Hi_p2[vi], H, W[P_E_W0], 2 * H, nullptr, w.U, 4 * H);
+      for (int vj = vi - 1; vj >= 0; --vj, ++t) {
+        add_relu(st, (int64_t)B * 4 * H / 4, w.U, w.Q + (size_t)vj * B * 4 * H, w.E1[t]);
+        linear_fwd(st, B, 2, 4 * H, w.E1[t], 4 * H, W[P_E_W2], 4 * H, W[P_E_B2], w.l2[t], LD_E);
+        loss_edge(st, B, vi, vj, w.l2[t], 2, adj, io.lw, w.rowloss, w.dl2[t]);
+        const int n = io.bt->step_ptr[t + 1] - io.bt->step_ptr[t];
+        if (n <= 0) continue;
+        const int* rows = io.bt->step_rows + io.bt->step_ptr[t];
+        RowMap rc{n, B, rows, vi * B};
+        MsgFwd mf{rc, w.Pg, w.Pm, W[P_G_B], adj, w.Hrun, 0, vj, vj, 1};
+        mf.hin_by_graph = 1; mf.hin_copy = w.Hin[t];
+        msg_fwd(st, mf);
+        linear_fwd(st, n, G3, H, w.Hin[t], H, W[P_CD_WHH], H, nullptr, w.gh, G3);
+        CellFwd cc{rc, w.gxc[vi], w.gh, W[P_CD_BIH], W[P_CD_BHH], w.Hin[t], 0, w.Hc[t], 0, w.g_c[t], 0, S_ONE, adj};
+        cc.gx_by_graph = 1;
+        cell_fwd(st, cc);
+        linear_fwd(st, n, G3, H, w.Hc[t], H, W[P_LD_WHH], H, nullptr, w.gh, G3);
+        CellFwd cl{rc, w.gxl[vi], w.gh, W[P_LD_BIH], W[P_LD_BHH], w.Hc[t], 0, w.Hi[t], 0, w.g_l[t], 0, S_SELF, adj};
+        cl.gx_by_graph = 1; cl.hout2 = Hcur;
+        cell_fwd(st, cl);
+        linear_fwd(st, n, 4 * H, H, w.Hi[t], H, W[P_E_W0], 2 * H, nullptr, w.UC, 4 * H);
+        scatter_rows(st, n, 4 * H, rows, w.UC, w.U, 0);
+      }
+      if (vi < NN - 1) node_projections(st, W, B, vi, w);
+      continue;
+    }
     const float* Hi_prev = w.Hi_p2[vi];
     for (int vj = vi - 1; vj >= 0; --vj, ++t) {
       // edge head on cat[Hi, Hj] (model.py:245/350): first layer split into Hi half + cached Hj half
@@ -395,21 +430,22 @@ static void mlp3_bwd(dx_stream_t st, const Weights& W, const Weights& G, int B, 
 }
 
 // looper cell backward for one propagate: dHi -> (dHc += ..., weight grads)
-static void looper_bwd(dx_stream_t st, const Weights& W, const Weights& G, int B, int vi, const RowMap& rm,
+static void looper_bwd(dx_stream_t st, const Weights& W, const Weights& G, int B, int vi, const RowMap& rm,   // rm.M rows
                        const float* dHi, const float* gates, const float* Hc, int smode, const uint64_t* adj,
                        const float* Xi, const DecWs& w, float* dHc, bool dHc_accum) {
-  // dHc (+)= dHi*z + dgh W_hh
+  // dHc (+)= dHi*z + dgh W_hh            (rm.M rows: all B graphs, or the active rows of a compacted step)
+  const int M = rm.M;
   float* direct = dHc_accum ? w.dHin : dHc;  // dHin is free scratch at this point
   CellBwd cb{rm, dHi, 0, gates, 0, Hc, 0, w.dgx, smode == S_SELF ? w.dgxs : nullptr, w.dgh, direct, smode, adj};
   cell_bwd(st, cb);
-  if (dHc_accum) add_inplace(st, (int64_t)B * H / 4, dHc, direct);
-  linear_dgrad(st, B, G3, H, w.dgh, G3, W[P_LD_WHH], H, dHc, H, ACC_ADD);
-  linear_wgrad(st, B, G3, H, w.dgh, G3, Hc, H, G[P_LD_WHH], H);
-  colsum_accum(st, B, G3, w.dgh, G3, G[P_LD_BHH]);
-  colsum_accum(st, B, G3, w.dgx, G3, G[P_LD_BIH]);
-  if (smode == S_SELF) linear_wgrad(st, B, G3, SX, w.dgxs, G3, Xi, XP, G[P_LD_WIH], SX);
-  else if (smode == S_ONE) linear_wgrad(st, B, G3, SX, w.dgx, G3, Xi, XP, G[P_LD_WIH], SX);
-  (void)vi;
+  if (dHc_accum) add_inplace(st, (int64_t)M * H / 4, dHc, direct);
+  linear_dgrad(st, M, G3, H, w.dgh, G3, W[P_LD_WHH], H, dHc, H, ACC_ADD);
+  linear_wgrad(st, M, G3, H, w.dgh, G3, Hc, H, G[P_LD_WHH], H);
+  colsum_accum(st, M, G3, w.dgh, G3, G[P_LD_BHH]);
+  colsum_accum(st, M, G3, w.dgx, G3, G[P_LD_BIH]);
+  if (smode == S_SELF) linear_wgrad(st, M, G3, SX, w.dgxs, G3, Xi, XP, G[P_LD_WIH], SX, nullptr, rm.rows);
+  else if (smode == S_ONE) linear_wgrad(st, M, G3, SX, w.dgx, G3, Xi, XP, G[P_LD_WIH], SX, nullptr, rm.rows);
+  (void)vi; (void)B;
 }
 
 void decode_bwd_impl(dx_stream_t st, const Weights& W, const Weights& G, int B, const float* z, const DecWs& w,
@@ -429,6 +465,43 @@ void decode_bwd_impl(dx_stream_t st, const Weights& W, const Weights& G, int B, 
     const int t0 = t_end - vi;       // step index of vj = vi-1 ; vj = 0 is t_end-1
     copy_async(st, w.dHi, w.dHd + (size_t)vi * bH, sizeof(float) * bH);
     zero_async(st, w.dHrun, sizeof(float) * bH);
+    const bool compact = bt.step_ptr != nullptr;
+    if (compact) {
+      // dHi is the running gradient of the node's current state, dU (= dE1 buffer) that of U; a step
+      // consumes and clears both on its active rows (their pre-step values only feed earlier heads).
+      float* dU = w.dE1;
+      zero_async(st, dU, sizeof(float) * (size_t)B * 4 * H);
+      for (int vj = 0; vj < vi; ++vj) {
+        const int t = t0 + (vi - 1 - vj);
+        const int n = bt.step_ptr[t + 1] - bt.step_ptr[t];
+        if (n > 0) {
+          const int* rows = bt.step_rows + bt.step_ptr[t];
+          RowMap rc{n, B, rows, vi * B};
+          gather_rows(st, n, 4 * H, rows, dU, w.UC, 1);
+          gather_rows(st, n, H, rows, w.dHi, w.dHiC, 1);
+          linear_dgrad(st, n, 4 * H, H, w.UC, 4 * H, W[P_E_W0], 2 * H, w.dHiC, H, ACC_ADD);
+          linear_wgrad(st, n, 4 * H, H, w.UC, 4 * H, w.Hi[t], H, G[P_E_W0], 2 * H);
+          looper_bwd(st, W, G, B, vi, rc, w.dHiC, w.g_l[t], w.Hc[t], S_SELF, adj, Xi, w, w.dHc, false);
+          CellBwd cc{rc, w.dHc, 0, w.g_c[t], 0, w.Hin[t], 0, w.dgx, nullptr, w.dgh, w.dHin, S_ONE, adj};
+          cell_bwd(st, cc);
+          linear_dgrad(st, n, G3, H, w.dgh, G3, W[P_CD_WHH], H, w.dHin, H, ACC_ADD);
+          linear_wgrad(st, n, G3, H, w.dgh, G3, w.Hin[t], H, G[P_CD_WHH], H);
+          linear_wgrad(st, n, G3, SX, w.dgx, G3, Xi, XP, G[P_CD_WIH], SX, nullptr, rows);
+          colsum_accum(st, n, G3, w.dgh, G3, G[P_CD_BHH]);
+          colsum_accum(st, n, G3, w.dgx, G3, G[P_CD_BIH]);
+          scatter_rows(st, n, H, rows, w.dHin, w.dHrun, 1);
+          RowMap rs{n, B, rows, vj * B};
+          MsgBwd mb{rs, w.Pg, w.Pm, W[P_G_B], adj, w.dHrun, 0, w.dPg, w.dPm, w.dgb, 1, vi, vi, 1};
+          msg_bwd(st, mb);
+        }
+        linear_wgrad(st, B, 2, 4 * H, w.dl2[t], LD_E, w.E1[t], 4 * H, G[P_E_W2], 4 * H);
+        colsum_accum(st, B, 2, w.dl2[t], LD_E, G[P_E_B2]);
+        relu_head_bwd(st, B, 4 * H, 2, w.E1[t], w.dl2[t], LD_E, W[P_E_W2], nullptr, w.dQ + (size_t)vj * B * 4 * H, dU);
+      }
+      // what is left in dU belongs to U = Hi_p2 W^T (the state every graph had before its first edge)
+      linear_wgrad(st, B, 4 * H, H, dU, 4 * H, w.Hi_p2[vi], H, G[P_E_W0], 2 * H);
+      linear_dgrad(st, B, 4 * H, H, dU, 4 * H, W[P_E_W0], 2 * H, w.dHi, H, ACC_ADD);
+    } else
     for (int vj = 0; vj < vi; ++vj) {
       const int t = t0 + (vi - 1 - vj);
       // looper then combiner of this propagate

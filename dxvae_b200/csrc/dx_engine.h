@@ -22,6 +22,9 @@ struct Batch {       // what the batcher produces (device pointers except level_
   int n_levels;
   const int32_t* level_ptr;   // HOST, n_levels+1
   const int32_t* level_rows;  // device, 6B
+  // optional decoder step schedule (teacher forcing): rows active at each of the 21 (vi,vj) steps
+  const int32_t* step_ptr = nullptr;    // HOST, 22
+  const int32_t* step_rows = nullptr;   // device, step_ptr[21] graph ids
 };
 
 struct LossW { float w_env, w_frq, w_kld, inv_batch; };
@@ -46,6 +49,7 @@ struct DecWs {
   float *gxc[7], *gxl[7], *Hc0[7], *g_c0[7], *g_p1[7], *Hi_p1[7], *g_p2[7], *Hi_p2[7], *ES1[7], *ls[7], *dls[7];
   float *E1[NSTEP], *l2[NSTEP], *dl2[NSTEP], *Hin[NSTEP], *g_c[NSTEP], *Hc[NSTEP], *g_l[NSTEP], *Hi[NSTEP];
   float *gh, *ghl0, *Hrun, *rowloss;
+  float *U, *UC, *dHiC;    // compacted teacher forcing: running edge-head product, compact temp, compact dHi
   // greedy only
   float *Xd, *Pn;
   // backward temporaries
@@ -89,6 +93,9 @@ int batch_build_host(int64_t B, const int32_t* edge_ptr, const int8_t* src, cons
                      int32_t* level_rows, int32_t* n_levels);
 int batch_schedule(dx_stream_t st, int64_t B, const uint64_t* adj, uint8_t* level, int32_t* level_ptr,
                    int32_t* level_rows, int32_t* level_ptr_host, void* ws, size_t ws_bytes);
+int batch_steps(dx_stream_t st, int64_t B, const uint64_t* adj, int32_t* step_ptr, int32_t* step_rows,
+                int32_t* step_ptr_host, void* ws, size_t ws_bytes);
+int batch_steps_host(int64_t B, const uint64_t* adj, int32_t* step_ptr, int32_t* step_rows);
 int pack_graphs(dx_stream_t st, int64_t B, const float* Xg, const float* Pg, float* Xn, int32_t* cls);
 int unpack_graphs(dx_stream_t st, int64_t B, const float* Xn, const float* Pn, float* Xg, float* Pg);
 int voices_to_graphs(dx_stream_t st, int64_t B, const uint8_t* voices, float* Xn, int32_t* cls, uint64_t* adj,

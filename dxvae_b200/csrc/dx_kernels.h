@@ -6,7 +6,7 @@
 //
 // Row addressing.  Node-major buffers hold one row per (node v, graph b):
 // global row r = v*B + b.  A launch covers M rows; compact index m in [0,M):
-//     r = rows ? rows[m] : row_base + m ;  b = r % B ;  v = r / B
+//     r = (rows ? rows[m] : m) + row_base ;  b = r % B ;  v = r / B
 // Buffers flagged "global" are indexed by r, the others by m.
 #pragma once
 #include "dx_rt.h"
@@ -20,7 +20,7 @@ DX_HD DX_INLINE float4 f4zero() { return make_float4(0.f, 0.f, 0.f, 0.f); }
 
 struct RowMap {
   int M; int B; const int* rows; int row_base;
-  DX_HD DX_INLINE int r(int m) const { return rows ? rows[m] : row_base + m; }
+  DX_HD DX_INLINE int r(int m) const { return (rows ? rows[m] : m) + row_base; }
 };
 
 enum { S_ONE = 0, S_ZERO = 1, S_SELF = 2 };  // x multiplier of the GRU input: 1, 0, or the node's self-loop flag
@@ -36,6 +36,8 @@ struct CellFwd {
   RowMap rm; const float* gx; const float* gh; const float* bih; const float* bhh;
   const float* hprev; int hprev_global; float* hout; int hout_global; float* gates; int gates_global;
   int smode; const uint64_t* adj;
+  int gx_by_graph = 0;        // 1: gx is [B,1536] indexed by the row's graph b (= r % B), not by m
+  float* hout2 = nullptr;     // optional second copy of h', [B,512] indexed by b (current state of the node)
 };
 
 inline void cell_fwd(dx_stream_t st, const CellFwd& a) {
@@ -45,7 +47,7 @@ inline void cell_fwd(dx_stream_t st, const CellFwd& a) {
     float s = 1.f;
     if (a.smode == S_ZERO) s = 0.f;
     else if (a.smode == S_SELF) { const int b = r % a.rm.B, v = r / a.rm.B; s = (float)abit(a.adj[b], v, v); }
-    const float* gx = a.gx + (int64_t)m * G3 + n;
+    const float* gx = a.gx + (int64_t)(a.gx_by_graph ? r % a.rm.B : m) * G3 + n;
     const float4 xr = ld4f(gx), xz = ld4f(gx + H), xn = ld4f(gx + 2 * H);
     float4 hr = f4zero(), hz = f4zero(), hn = f4zero(), hp = f4zero();
     if (a.gh) { const float* gh = a.gh + (int64_t)m * G3 + n; hr = ld4f(gh); hz = ld4f(gh + H); hn = ld4f(gh + 2 * H); }
@@ -65,6 +67,7 @@ inline void cell_fwd(dx_stream_t st, const CellFwd& a) {
     DX_CELL(x) DX_CELL(y) DX_CELL(z) DX_CELL(w)
 #undef DX_CELL
     st4f(a.hout + (int64_t)(a.hout_global ? r : m) * H + n, O);
+    if (a.hout2) st4f(a.hout2 + (int64_t)(r % a.rm.B) * H + n, O);
     if (a.gates) {
       float* g = a.gates + (int64_t)(a.gates_global ? r : m) * (4 * H) + n;
       st4f(g, R); st4f(g + H, Zg); st4f(g + 2 * H, Ng); st4f(g + 3 * H, NH);
@@ -136,6 +139,8 @@ struct MsgFwd {
   RowMap rm; const float* Pg; const float* Pm; const float* bg; const uint64_t* adj; float* hin; int hin_global;
   int x_lo, x_hi; int accum;
   const int* pos = nullptr;   // optional: row of neighbour (x,b) in Pg/Pm is pos[x*B+b] instead of x*B+b
+  int hin_by_graph = 0;       // 1: hin is [B,512] indexed by the row's graph b
+  float* hin_copy = nullptr;  // optional compact copy [M,512] of the updated aggregate
 };
 
 inline void msg_fwd(dx_stream_t st, const MsgFwd& a) {
@@ -144,7 +149,7 @@ inline void msg_fwd(dx_stream_t st, const MsgFwd& a) {
     const int r = a.rm.r(m);
     const int b = r % a.rm.B, v = r / a.rm.B;
     const uint64_t A = a.adj[b];
-    float* out = a.hin + (int64_t)(a.hin_global ? r : m) * H + n;
+    float* out = a.hin + (int64_t)(a.hin_by_graph ? b : (a.hin_global ? r : m)) * H + n;
     float acc0 = a.accum ? out[0] : 0.f, acc1 = a.accum ? out[1] : 0.f;
     const int lo = a.x_lo < 0 ? v + 1 : a.x_lo, hi = a.x_lo < 0 ? NN - 1 : a.x_hi;
     const float bg0 = a.bg[n], bg1 = a.bg[n + 1];
@@ -158,6 +163,7 @@ inline void msg_fwd(dx_stream_t st, const MsgFwd& a) {
       acc1 += sigmoidf_((fi * g.z + fo * g.w) + bg1) * (fi * p.z + fo * p.w);
     }
     out[0] = acc0; out[1] = acc1;
+    if (a.hin_copy) { a.hin_copy[(int64_t)m * H + n] = acc0; a.hin_copy[(int64_t)m * H + n + 1] = acc1; }
   });
 }
 
@@ -208,6 +214,33 @@ inline void msg_bwd(dx_stream_t st, const MsgBwd& a) {
 // ------------------------------------------------------------------------------------
 // small generic element-wise helpers
 // ------------------------------------------------------------------------------------
+// Row gather / scatter helpers for the compacted teacher-forced steps (rows[m] = graph index).
+//   gather_rows     : dst[m,:] = src[rows[m],:]            ; zero_src also clears the source rows
+//   scatter_rows    : dst[rows[m],:] = src[m,:]            ; add=1 accumulates
+inline void gather_rows(dx_stream_t st, int M, int C, const int* rows, float* src, float* dst, int zero_src) {
+  foreach (st, (int64_t)M * (C / 4), [=] DX_HD(int64_t idx) {
+    const int m = (int)(idx / (C / 4)), c = (int)(idx % (C / 4)) * 4;
+    float* sp = src + (int64_t)rows[m] * C + c;
+    st4f(dst + (int64_t)m * C + c, ld4f(sp));
+    if (zero_src) st4f(sp, f4zero());
+  });
+}
+inline void scatter_rows(dx_stream_t st, int M, int C, const int* rows, const float* src, float* dst, int add) {
+  foreach (st, (int64_t)M * (C / 4), [=] DX_HD(int64_t idx) {
+    const int m = (int)(idx / (C / 4)), c = (int)(idx % (C / 4)) * 4;
+    float* dp = dst + (int64_t)rows[m] * C + c;
+    float4 v = ld4f(src + (int64_t)m * C + c);
+    if (add) { const float4 o = ld4f(dp); v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w; }
+    st4f(dp, v);
+  });
+}
+// e[m,j] = relu(u[m,j] + q[m,j])
+inline void add_relu(dx_stream_t st, int64_t n4, const float* u, const float* q, float* e) {
+  foreach (st, n4, [=] DX_HD(int64_t i) {
+    const float4 a = ld4f(u + 4 * i), b = ld4f(q + 4 * i);
+    st4f(e + 4 * i, make_float4(fmaxf(a.x + b.x, 0.f), fmaxf(a.y + b.y, 0.f), fmaxf(a.z + b.z, 0.f), fmaxf(a.w + b.w, 0.f)));
+  });
+}
 // y[i] (+)= x[i]
 inline void add_inplace(dx_stream_t st, int64_t n4, float* y, const float* x) {
   foreach (st, n4, [=] DX_HD(int64_t i) {
@@ -218,7 +251,7 @@ inline void add_inplace(dx_stream_t st, int64_t n4, float* y, const float* x) {
 // dpre[m,j] = (act[m,j] > 0) * sum_c dl[m,c] * W2[c,j]   (backward of  l = relu-act . W2^T, C = 1 or 2 outputs)
 // optionally also acc[m,j] += dpre[m,j]
 inline void relu_head_bwd(dx_stream_t st, int M, int N, int C, const float* act, const float* dl, int lddl,
-                          const float* W2, float* dpre, float* acc) {
+                          const float* W2, float* dpre, float* acc, float* acc2 = nullptr) {
   foreach (st, (int64_t)M * (N / 4), [=] DX_HD(int64_t idx) {
     const int m = (int)(idx / (N / 4)), j = (int)(idx % (N / 4)) * 4;
     const float4 a = ld4f(act + (int64_t)m * N + j);
@@ -229,7 +262,9 @@ inline void relu_head_bwd(dx_stream_t st, int M, int N, int C, const float* act,
       g.x += d * w.x; g.y += d * w.y; g.z += d * w.z; g.w += d * w.w;
     }
     g.x = a.x > 0.f ? g.x : 0.f; g.y = a.y > 0.f ? g.y : 0.f; g.z = a.z > 0.f ? g.z : 0.f; g.w = a.w > 0.f ? g.w : 0.f;
-    st4f(dpre + (int64_t)m * N + j, g);
+    if (dpre) st4f(dpre + (int64_t)m * N + j, g);
+    if (acc2) { float4 q = ld4f(acc2 + (int64_t)m * N + j); q.x += g.x; q.y += g.y; q.z += g.z; q.w += g.w;
+                st4f(acc2 + (int64_t)m * N + j, q); }
     if (acc) { float4 q = ld4f(acc + (int64_t)m * N + j); q.x += g.x; q.y += g.y; q.z += g.z; q.w += g.w;
                st4f(acc + (int64_t)m * N + j, q); }
   });

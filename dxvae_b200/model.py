@@ -24,7 +24,7 @@ _FIXED = dict(n_nodes=7, n_params=21, size_X=27, size_X0=23, size_H=512, size_Z=
 
 class _DevBatch:
     """Device-resident batch in kernel layout (see include/dxvae_b200.h)."""
-    __slots__ = ("B", "Xn", "cls", "adj", "n_levels", "level_ptr", "level_rows", "level", "csr")
+    __slots__ = ("B", "Xn", "cls", "adj", "n_levels", "level_ptr", "level_rows", "level", "csr", "step_ptr", "step_rows")
 
 
 def _stream():
@@ -73,6 +73,8 @@ class DXVAE(nn.Module):
         # (tcgen05 tensor cores, looser stated tolerance).  Encode for inference and greedy decode
         # always run in fp32 so their outputs match the reference's decisions.
         self.precision = "fp32"
+        # skip teacher-forced re-propagates that add no edge (exact; see dxvae_batch_steps)
+        self.compact_steps = True
         if checkpoint is not None:
             self.load_state_dict(torch.load(checkpoint, map_location=self.device))
 
@@ -160,9 +162,23 @@ class DXVAE(nn.Module):
             d.level_rows = torch.from_numpy(rows).to("cuda")
             d.level = level
             d.csr = (indptr, indices[:int(eptr[-1])], eflags[:int(eptr[-1])])
+            d.step_ptr = d.step_rows = None
+            if need_cls and self.compact_steps:
+                d.step_ptr = np.zeros(22, np.int32)
+                srows = np.zeros(21 * B, np.int32)
+                _lib.check(L.dxvae_batch_steps_host(B, pv(adj), pv(d.step_ptr), pv(srows)), "dxvae_batch_steps_host")
+                d.step_rows = torch.from_numpy(srows[:max(1, int(d.step_ptr[21]))]).to("cuda")
         else:
             d.adj = gb.adj.to("cuda", torch.int64).contiguous()
             self._schedule(d)
+            d.step_ptr = d.step_rows = None
+            if need_cls and self.compact_steps:
+                d.step_ptr = np.zeros(22, np.int32)
+                d.step_rows = torch.empty(21 * B, dtype=torch.int32, device="cuda")
+                sp_dev = torch.empty(22, dtype=torch.int32, device="cuda")
+                ws = self._workspace(_abi.OP_SCHEDULE, B)
+                _lib.check(L.dxvae_batch_steps(B, d.adj.data_ptr(), sp_dev.data_ptr(), d.step_rows.data_ptr(),
+                                               d.step_ptr.ctypes.data, ws.data_ptr(), ws.numel(), st), "dxvae_batch_steps")
         return d
 
     def _schedule(self, d):
@@ -303,8 +319,9 @@ class DXVAE(nn.Module):
             d.level_ptr.ctypes.data, d.level_rows.data_ptr(), eps.data_ptr(), w[0], w[1], w[2],
             (1.0 / d.B) if inv_batch is None else inv_batch, loss5.data_ptr(),
             None if mu_out is None else mu_out.data_ptr(), None if std_out is None else std_out.data_ptr(),
-            None if grads is None else grads.data_ptr(), ws.data_ptr(), ws.numel(), self._prec(), _stream()),
-            "dxvae_elbo_step")
+            None if grads is None else grads.data_ptr(), ws.data_ptr(), ws.numel(), self._prec(),
+            None if d.step_ptr is None else d.step_ptr.ctypes.data,
+            None if d.step_ptr is None else d.step_rows.data_ptr(), _stream()), "dxvae_elbo_step")
         return loss5
 
     # ------------------------------------------------------------------ train
@@ -402,8 +419,9 @@ class _LossFn(torch.autograd.Function):
             model._flat.data_ptr(), d.B, d.Xn.data_ptr(), d.cls.data_ptr(), d.adj.data_ptr(), mu.data_ptr(),
             sd.data_ptr(), eps.data_ptr(), w[0], w[1], w[2], 1.0 / d.B, loss5.data_ptr(),
             None if g is None else g.data_ptr(), None if dmu is None else dmu.data_ptr(),
-            None if dsd is None else dsd.data_ptr(), ws.data_ptr(), ws.numel(), model._prec(), _stream()),
-            "dxvae_loss_step")
+            None if dsd is None else dsd.data_ptr(), ws.data_ptr(), ws.numel(), model._prec(),
+            None if d.step_ptr is None else d.step_ptr.ctypes.data,
+            None if d.step_ptr is None else d.step_rows.data_ptr(), _stream()), "dxvae_loss_step")
         ctx.model, ctx.g, ctx.dmu, ctx.dsd = model, g, dmu, dsd
         total, rest = loss5[0].clone(), loss5[1:].clone()
         ctx.mark_non_differentiable(rest)

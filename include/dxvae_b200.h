@@ -90,6 +90,18 @@ int dxvae_batch_build_host(int64_t B, const int32_t* edge_ptr_host, const int8_t
 int dxvae_batch_schedule(int64_t B, const uint64_t* adj, uint8_t* level, int32_t* level_ptr, int32_t* level_rows,
                          int32_t* level_ptr_host, void* workspace, size_t workspace_bytes, void* stream);
 
+/* Decoder step schedule for teacher forcing (model.py:311-358): the loss replays 21 (vi,vj)
+ * re-propagates per graph, but a re-propagate only changes node vi when that step adds an edge
+ * (vj->vi or vi->vj); otherwise it recomputes the same state.  step t = vi*(vi-1)/2 + (vi-1-vj).
+ * step_rows[step_ptr[t]..step_ptr[t+1]) = ascending ids of the graphs active at step t; passing
+ * the schedule to dxvae_elbo_step / dxvae_loss_step makes the identity steps free (results are
+ * the same function of the inputs; NULL runs every step on every graph as the reference does).
+ * step_ptr: 22 ints; step_rows: up to 21*B ints.  The device form synchronises the stream to
+ * return step_ptr_host. */
+int dxvae_batch_steps(int64_t B, const uint64_t* adj, int32_t* step_ptr, int32_t* step_rows, int32_t* step_ptr_host,
+                      void* workspace, size_t workspace_bytes, void* stream);
+int dxvae_batch_steps_host(int64_t B, const uint64_t* adj_host, int32_t* step_ptr_host, int32_t* step_rows_host);
+
 /* Graph-major reference tensors -> what the kernels read. */
 int dxvae_pack_graphs(int64_t B, const float* Xg, const float* Pg, float* Xn, int32_t* cls, void* stream);
 /* Node-major decode outputs -> graph-major (B,7,27) / (B,7,21). */
@@ -148,7 +160,7 @@ int dxvae_elbo_step(const float* weights, int64_t B, const float* Xn, const int3
                     int32_t n_levels, const int32_t* level_ptr_host, const int32_t* level_rows, const float* eps,
                     float w_env, float w_frq, float w_kld, float inv_batch, float* loss5, float* mu_out,
                     float* std_out, float* grads, void* workspace, size_t workspace_bytes, int precision,
-                    void* stream);
+                    const int32_t* step_ptr_host, const int32_t* step_rows, void* stream);
 
 /* Split form of dxvae_elbo_step, for DXVAE.encode(G) followed by DXVAE.loss(q, G)
  * (model.py:370-371).  encode_fwd(keep=1, workspace of DXVAE_OP_ENCODE_TRAIN) leaves the
@@ -158,7 +170,8 @@ int dxvae_elbo_step(const float* weights, int64_t B, const float* Xn, const int3
 int dxvae_loss_step(const float* weights, int64_t B, const float* Xn, const int32_t* cls, const uint64_t* adj,
                     const float* mu, const float* std_, const float* eps, float w_env, float w_frq, float w_kld,
                     float inv_batch, float* loss5, float* grads, float* dmu, float* dstd, void* workspace,
-                    size_t workspace_bytes, int precision, void* stream);
+                    size_t workspace_bytes, int precision, const int32_t* step_ptr_host, const int32_t* step_rows,
+                    void* stream);
 int dxvae_encode_bwd(const float* weights, int64_t B, const float* Xn, const uint64_t* adj, int32_t n_levels,
                      const int32_t* level_ptr_host, const int32_t* level_rows, const float* std_, const float* dmu,
                      const float* dstd, float* grads, void* workspace, size_t workspace_bytes, int precision,

@@ -90,9 +90,13 @@ class Emu:
                                          ws.nbytes, 0, 0, None), "encode")
         return mu, sd
 
-    def elbo(self, bt, eps, w=(2, 5, 0.01), inv_batch=None, grads=True):
+    def elbo(self, bt, eps, w=(2, 5, 0.01), inv_batch=None, grads=True, compact=False):
         L = self.lib
         B = bt["B"]
+        sp = sr = None
+        if compact:
+            sp = np.zeros(22, np.int32); sr = np.zeros(21 * B, np.int32)
+            _abi.check(L, L.dxvae_batch_steps_host(B, ptr(bt["adj"]), ptr(sp), ptr(sr)), "steps")
         ws = np.zeros(L.dxvae_workspace_bytes(_abi.OP_TRAIN, B), np.uint8)
         loss5 = np.zeros(5, np.float32)
         mu = np.zeros((B, 128), np.float32); sd = np.zeros((B, 128), np.float32)
@@ -101,7 +105,7 @@ class Emu:
         _abi.check(L, L.dxvae_elbo_step(ptr(self.blob), B, ptr(bt["Xn"]), ptr(bt["cls"]), ptr(bt["adj"]),
                                         bt["n_levels"], ptr(bt["level_ptr"]), ptr(bt["level_rows"]), ptr(eps),
                                         w[0], w[1], w[2], inv_batch or 1.0 / B, ptr(loss5), ptr(mu), ptr(sd), ptr(g),
-                                        ptr(ws), ws.nbytes, 0, None), "elbo")
+                                        ptr(ws), ws.nbytes, 0, ptr(sp), ptr(sr), None), "elbo")
         return loss5, mu, sd, g
 
     def decode(self, z):

@@ -35,6 +35,25 @@ def test_batcher_matches_set_logic(setup):
         assert np.array_equal(bt["level_ptr"][:n], ob["level_ptr"])
 
 
+def test_step_schedule_matches_set_logic(setup):
+    """dxvae_batch_steps_host: rows active at step t=(vi,vj) are the graphs with an edge vj->vi or vi->vj."""
+    import ctypes as C
+    from tests.emu import emu as E_
+    L = E_.lib()
+    for edges in (util.random_edge_lists(50, 0.3, 4), util.random_edge_lists(9, 0.0, 5), util.random_edge_lists(9, 1.0, 6)):
+        ob = O.batch_oracle(edges)
+        B = len(edges)
+        sp = np.zeros(22, np.int32); sr = np.zeros(21 * B, np.int32)
+        assert L.dxvae_batch_steps_host(B, E_.ptr(ob["adj"]), E_.ptr(sp), E_.ptr(sr)) == 0
+        t = 0
+        for vi in range(1, 7):
+            for vj in range(vi - 1, -1, -1):
+                want = [b for b, (s, d) in enumerate(edges) if (vj, vi) in set(zip(s, d)) or (vi, vj) in set(zip(s, d))]
+                assert list(sr[sp[t]:sp[t + 1]]) == want, (vi, vj)
+                t += 1
+        assert sp[21] == sum(sp[i + 1] - sp[i] for i in range(21))
+
+
 def test_encode_matches_oracle(setup):
     _, X, P, E, A, o, emu = setup
     mu, sd = emu.encode(emu.batch(X.numpy(), P.numpy(), E))
@@ -52,12 +71,12 @@ def test_encode_arbitrary_topology(setup):
     assert np.abs(sd - sd_o.detach().numpy()).max() < 1e-5
 
 
-@pytest.mark.parametrize("w", [(2, 5, 0.01), (3, 6, 0.002)])
-def test_elbo_and_gradients_match_oracle(setup, w):
+@pytest.mark.parametrize("w,compact", [((2, 5, 0.01), False), ((3, 6, 0.002), False), ((3, 6, 0.002), True)])
+def test_elbo_and_gradients_match_oracle(setup, w, compact):
     _, X, P, E, A, o, emu = setup
     torch.manual_seed(1234)
     eps = torch.randn(len(X), 128)
-    loss5, mu, sd, g = emu.elbo(emu.batch(X.numpy(), P.numpy(), E), eps.numpy(), w)
+    loss5, mu, sd, g = emu.elbo(emu.batch(X.numpy(), P.numpy(), E), eps.numpy(), w, compact=compact)
     mu_o, sd_o = o.encode(X, A)
     lo = o.loss(mu_o, sd_o, X, P, A, eps, *w)
     for a, b in zip(loss5, lo):
@@ -71,13 +90,14 @@ def test_elbo_and_gradients_match_oracle(setup, w):
         assert rel < 1e-4, (n, rel)
 
 
-def test_elbo_arbitrary_topology_gradients(setup):
+@pytest.mark.parametrize("compact", [False, True])
+def test_elbo_arbitrary_topology_gradients(setup, compact):
     _, X, P, _, _, o, emu = setup
     E = util.random_edge_lists(len(X), 0.35, 11)
     A = util.adj_dense(E)
     torch.manual_seed(5)
     eps = torch.randn(len(X), 128)
-    loss5, mu, sd, g = emu.elbo(emu.batch(X.numpy(), P.numpy(), E), eps.numpy())
+    loss5, mu, sd, g = emu.elbo(emu.batch(X.numpy(), P.numpy(), E), eps.numpy(), compact=compact)
     mu_o, sd_o = o.encode(X, A)
     lo = o.loss(mu_o, sd_o, X, P, A, eps)
     assert abs(loss5[0] - lo[0].item()) <= 1e-5 * abs(lo[0].item())

@@ -345,3 +345,51 @@ def test_decode_large_batch_properties(lib):
     # fc in fixed mode is stored mod 4 by _make_graph but the quantiser already emits 0..3: exact round trip
     assert torch.equal(back.params.cpu(), a.params.cpu().abs())
     assert np.abs(back.X.cpu().numpy() - a.X.cpu().numpy()).max() <= 1e-6
+
+
+# --------------------------------------------------------------------------- compacted teacher forcing
+def test_device_step_schedule_matches_set_logic(lib):
+    from dxvae_b200 import DXVAE, _abi, _lib
+    from dxvae_b200.dxdata import mask_from_edges
+    m = DXVAE()
+    for n, p, seed in ((3000, 0.2, 1), (1, 1.0, 2), (1025, 0.0, 3), (2500, 1.0, 4)):
+        E = util.random_edge_lists(n, p, seed)
+        adj = torch.tensor([mask_from_edges(*e) for e in E], dtype=torch.int64, device="cuda")
+        sp = np.zeros(22, np.int32)
+        sr = torch.full((21 * n,), -1, dtype=torch.int32, device="cuda")
+        spd = torch.empty(22, dtype=torch.int32, device="cuda")
+        ws = m._workspace(_abi.OP_SCHEDULE, n)
+        _lib.check(lib.dxvae_batch_steps(n, adj.data_ptr(), spd.data_ptr(), sr.data_ptr(), sp.ctypes.data, ws.data_ptr(),
+                                         ws.numel(), st()), "steps")
+        sr = sr.cpu().numpy()
+        sets = [set(zip(s, d)) for s, d in E]
+        t = 0
+        for vi in range(1, 7):
+            for vj in range(vi - 1, -1, -1):
+                want = [b for b in range(n) if (vj, vi) in sets[b] or (vi, vj) in sets[b]]
+                assert list(sr[sp[t]:sp[t + 1]]) == want, (vi, vj)
+                t += 1
+
+
+def test_compacted_steps_equal_dense_replay(lib):
+    """Skipping identity re-propagates must not change the function: same losses and gradients as
+    replaying all 21 steps on every graph (fp32 path), on dataset and on arbitrary topologies."""
+    idx = list(range(0, 1024, 8))
+    X, P, E, A = util.dataset_graphs(idx)
+    m, o = make_model(3, 3.0)
+    torch.manual_seed(21)
+    eps = torch.randn(len(idx), 128)
+    for edges in (E, util.random_edge_lists(len(idx), 0.3, 17)):
+        G = _graphs(X, P, edges)
+        res = {}
+        for mode in (True, False):
+            m.compact_steps = mode
+            m.zero_grad()
+            out = m.forward(G, eps=eps)
+            out[0].backward()
+            res[mode] = ([t.item() for t in out], {n: p.grad.clone() for n, p in m.named_parameters()})
+        for a, b in zip(res[True][0], res[False][0]):
+            assert abs(a - b) <= 2e-6 * abs(b) + 1e-7
+        for n, g in res[False][1].items():
+            assert (res[True][1][n] - g).abs().max().item() <= 2e-5 * (g.abs().max().item() + 1e-30), n
+    m.compact_steps = True
