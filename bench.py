@@ -316,7 +316,7 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--micro-batch", type=int, default=8192)
+    ap.add_argument("--micro-batch", type=int, default=32768)
     ap.add_argument("--cpu-patches", type=int, default=256)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-extra", action="store_true")

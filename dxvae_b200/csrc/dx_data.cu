@@ -438,6 +438,30 @@ int adamw_step(dx_stream_t st, int64_t n, float* w, const float* g, float* m, fl
   return check_launch("adamw_step");
 }
 
+void pad_wih(dx_stream_t st, const float* W, int K, float* Wp) {
+  foreach (st, (int64_t)G3 * XP, [=] DX_HD(int64_t i) {
+    const int c = (int)(i % XP); const int64_t n = i / XP;
+    Wp[i] = c < K ? W[n * K + c] : 0.f;
+  });
+}
+void unpad_add_wih(dx_stream_t st, const float* dWp, int K, float* dW) {
+  foreach (st, (int64_t)G3 * K, [=] DX_HD(int64_t i) {
+    const int c = (int)(i % K); const int64_t n = i / K;
+    dW[i] += dWp[n * XP + c];
+  });
+}
+void mask_features(dx_stream_t st, int64_t rows, int B, const int* row_ids, int row_base, const uint64_t* adj,
+                   const float* X, float* XL) {
+  foreach (st, rows * (XP / 4), [=] DX_HD(int64_t i) {
+    const int64_t m = i / (XP / 4); const int c = (int)(i % (XP / 4)) * 4;
+    const int64_t r = (row_ids ? row_ids[m] : m) + row_base;
+    const int b = (int)(r % B), v = (int)(r / B);
+    const float s = (float)abit(adj[b], v, v);
+    const float4 x = ld4f(X + m * XP + c);
+    st4f(XL + m * XP + c, make_float4(s * x.x, s * x.y, s * x.z, s * x.w));
+  });
+}
+
 int reparameterize(dx_stream_t st, int64_t n, const float* mu, const float* sd, const float* eps, float* z) {
   foreach (st, n, [=] DX_HD(int64_t i) { z[i] = mu[i] + sd[i] * eps[i]; });
   return check_launch("reparameterize");

@@ -22,7 +22,11 @@ DecWs carve_dec(Arena& ar, int64_t B, bool train) {
   w.z = ar.take<float>(b * Z); w.Hinit = ar.take<float>(b * H); w.Hd = ar.take<float>(7 * b * H);
   w.Pg = ar.take<float>(6 * b * 2 * H); w.Pm = ar.take<float>(6 * b * 2 * H); w.Q = ar.take<float>(6 * b * 4 * H);
   w.gh = ar.take<float>(b * G3); w.ghl0 = ar.take<float>(b * G3); w.Hrun = ar.take<float>(b * H);
-  if (train) { w.U = ar.take<float>(b * 4 * H); w.UC = ar.take<float>(b * 4 * H); w.dHiC = ar.take<float>(b * H); }
+  if (train) {
+    w.U = ar.take<float>(b * 4 * H); w.UC = ar.take<float>(b * 4 * H); w.dHiC = ar.take<float>(b * H);
+    for (int k = 0; k < 3; ++k) { w.WihP[k] = ar.take<float>((size_t)G3 * XP); w.dWihP[k] = ar.take<float>((size_t)G3 * XP); }
+    w.XL = ar.take<float>(7 * b * XP); w.xc = ar.take<float>(b * XP);
+  }
   auto per_node = [&](float** arr, size_t cols, bool need) {
     float* shared = need ? nullptr : ar.take<float>(b * cols);
     for (int v = 0; v < 7; ++v) arr[v] = need ? ar.take<float>(b * cols) : shared;
@@ -306,13 +310,19 @@ void decode_fwd_impl(dx_stream_t st, const Weights& W, int B, const float* z, co
   const uint64_t* adj = train ? io.bt->adj : io.adj_out;
   const float* Xsrc = train ? io.bt->Xn : w.Xd;   // node-major (7,B,32)
   upload_tables();
+  const float* Wc = W[P_CD_WIH]; const float* Wl = W[P_LD_WIH]; const float* Wr = W[P_RD_WIH];
+  int Kx = SX, Kr = SX0, ldx = SX, ldr = SX0;
+  if (train) {   // 32-column padded input weights: TMA-addressable (exact: the padded columns are zero)
+    pad_wih(st, W[P_CD_WIH], SX, w.WihP[0]); pad_wih(st, W[P_LD_WIH], SX, w.WihP[1]); pad_wih(st, W[P_RD_WIH], SX0, w.WihP[2]);
+    Wc = w.WihP[0]; Wl = w.WihP[1]; Wr = w.WihP[2]; Kx = Kr = ldx = ldr = XP;
+  }
 
   linear_fwd(st, B, H, Z, z, Z, W[P_ZH_W], Z, W[P_ZH_B], w.Hinit, H, ACT_TANH);
   mlp3_fwd(st, W, B, P_X0_W0, w.Hinit, SX0 + 32, w.A1[0], w.A2[0], w.L[0]);
   if (train) loss_x0(st, B, w.L[0], Xsrc, io.bt->cls, io.lw, w.rowloss, w.dL[0]);
   else reg_x0(st, B, w.L[0], w.Xd, w.Pn);
   // root: h_0 = GRU_root(x0[:23], H_init)
-  linear_fwd(st, B, G3, SX0, Xsrc, XP, W[P_RD_WIH], SX0, nullptr, w.gxc[0], G3);
+  linear_fwd(st, B, G3, Kr, Xsrc, XP, Wr, ldr, nullptr, w.gxc[0], G3);
   linear_fwd(st, B, G3, H, w.Hinit, H, W[P_RD_WHH], H, nullptr, w.gh, G3);
   {
     RowMap rm{B, B, nullptr, 0};
@@ -329,8 +339,8 @@ void decode_fwd_impl(dx_stream_t st, const Weights& W, int B, const float* z, co
     mlp3_fwd(st, W, B, P_X_W0, hprev_node, SX, w.A1[vi], w.A2[vi], w.L[vi]);
     if (train) loss_xi(st, B, vi, w.L[vi], Xi, io.bt->cls, io.lw, w.rowloss, w.dL[vi]);
     else reg_xi(st, B, w.L[vi], w.Xd + (size_t)vi * B * XP, w.Pn + (size_t)vi * B * XP);
-    linear_fwd(st, B, G3, SX, Xi, XP, W[P_CD_WIH], SX, nullptr, w.gxc[vi], G3);
-    linear_fwd(st, B, G3, SX, Xi, XP, W[P_LD_WIH], SX, nullptr, w.gxl[vi], G3);
+    linear_fwd(st, B, G3, Kx, Xi, XP, Wc, ldx, nullptr, w.gxc[vi], G3);
+    linear_fwd(st, B, G3, Kx, Xi, XP, Wl, ldx, nullptr, w.gxl[vi], G3);
     // P1 (model.py:234/320): no edges yet -> H_in = 0, x_loop = 0
     CellFwd c0{rm, w.gxc[vi], nullptr, W[P_CD_BIH], W[P_CD_BHH], nullptr, 0, w.Hc0[vi], 0, train ? w.g_c0[vi] : nullptr, 0,
                S_ONE, adj};
@@ -436,16 +446,20 @@ static void looper_bwd(dx_stream_t st, const Weights& W, const Weights& G, int B
   // dHc (+)= dHi*z + dgh W_hh            (rm.M rows: all B graphs, or the active rows of a compacted step)
   const int M = rm.M;
   float* direct = dHc_accum ? w.dHin : dHc;  // dHin is free scratch at this point
-  CellBwd cb{rm, dHi, 0, gates, 0, Hc, 0, w.dgx, smode == S_SELF ? w.dgxs : nullptr, w.dgh, direct, smode, adj};
+  CellBwd cb{rm, dHi, 0, gates, 0, Hc, 0, w.dgx, nullptr, w.dgh, direct, smode, adj};
   cell_bwd(st, cb);
   if (dHc_accum) add_inplace(st, (int64_t)M * H / 4, dHc, direct);
   linear_dgrad(st, M, G3, H, w.dgh, G3, W[P_LD_WHH], H, dHc, H, ACC_ADD);
   linear_wgrad(st, M, G3, H, w.dgh, G3, Hc, H, G[P_LD_WHH], H);
   colsum_accum(st, M, G3, w.dgh, G3, G[P_LD_BHH]);
   colsum_accum(st, M, G3, w.dgx, G3, G[P_LD_BIH]);
-  if (smode == S_SELF) linear_wgrad(st, M, G3, SX, w.dgxs, G3, Xi, XP, G[P_LD_WIH], SX, nullptr, rm.rows);
-  else if (smode == S_ONE) linear_wgrad(st, M, G3, SX, w.dgx, G3, Xi, XP, G[P_LD_WIH], SX, nullptr, rm.rows);
-  (void)vi; (void)B;
+  // weight_ih gradient: x masked by the self-loop flag (XL), gathered to the active rows when compacted
+  if (smode != S_ZERO) {
+    const float* xl = w.XL + (size_t)vi * B * XP;
+    if (rm.rows) { gather_rows(st, M, XP, rm.rows, const_cast<float*>(xl), w.xc, 0); xl = w.xc; }
+    linear_wgrad(st, M, G3, XP, w.dgx, G3, xl, XP, w.dWihP[1], XP);
+  }
+  (void)Xi; (void)G;
 }
 
 void decode_bwd_impl(dx_stream_t st, const Weights& W, const Weights& G, int B, const float* z, const DecWs& w,
@@ -457,6 +471,8 @@ void decode_bwd_impl(dx_stream_t st, const Weights& W, const Weights& G, int B, 
   zero_async(st, w.dPm, sizeof(float) * 6 * (size_t)B * 2 * H);
   zero_async(st, w.dQ, sizeof(float) * 6 * (size_t)B * 4 * H);
   zero_async(st, w.dgb, sizeof(float) * 6 * bH);
+  for (int k = 0; k < 3; ++k) zero_async(st, w.dWihP[k], sizeof(float) * G3 * XP);
+  mask_features(st, (int64_t)7 * B, B, nullptr, 0, adj, bt.Xn, w.XL);
 
   int t_end = NSTEP;  // steps of node vi occupy [t_end - vi, t_end)
   for (int vi = NN - 1; vi >= 1; --vi) {
@@ -486,7 +502,8 @@ void decode_bwd_impl(dx_stream_t st, const Weights& W, const Weights& G, int B, 
           cell_bwd(st, cc);
           linear_dgrad(st, n, G3, H, w.dgh, G3, W[P_CD_WHH], H, w.dHin, H, ACC_ADD);
           linear_wgrad(st, n, G3, H, w.dgh, G3, w.Hin[t], H, G[P_CD_WHH], H);
-          linear_wgrad(st, n, G3, SX, w.dgx, G3, Xi, XP, G[P_CD_WIH], SX, nullptr, rows);
+          gather_rows(st, n, XP, rows, const_cast<float*>(Xi), w.xc, 0);
+          linear_wgrad(st, n, G3, XP, w.dgx, G3, w.xc, XP, w.dWihP[0], XP);
           colsum_accum(st, n, G3, w.dgh, G3, G[P_CD_BHH]);
           colsum_accum(st, n, G3, w.dgx, G3, G[P_CD_BIH]);
           scatter_rows(st, n, H, rows, w.dHin, w.dHrun, 1);
@@ -510,7 +527,7 @@ void decode_bwd_impl(dx_stream_t st, const Weights& W, const Weights& G, int B, 
       cell_bwd(st, cc);
       linear_dgrad(st, B, G3, H, w.dgh, G3, W[P_CD_WHH], H, w.dHin, H, ACC_ADD);
       linear_wgrad(st, B, G3, H, w.dgh, G3, w.Hin[t], H, G[P_CD_WHH], H);
-      linear_wgrad(st, B, G3, SX, w.dgx, G3, Xi, XP, G[P_CD_WIH], SX);
+      linear_wgrad(st, B, G3, XP, w.dgx, G3, Xi, XP, w.dWihP[0], XP);
       colsum_accum(st, B, G3, w.dgh, G3, G[P_CD_BHH]);
       colsum_accum(st, B, G3, w.dgx, G3, G[P_CD_BIH]);
       add_inplace(st, (int64_t)bH / 4, w.dHrun, w.dHin);
@@ -539,7 +556,7 @@ void decode_bwd_impl(dx_stream_t st, const Weights& W, const Weights& G, int B, 
     // combiner with H_in = 0: only input weights / biases receive gradient
     CellBwd c0{rm, w.dHc0, 0, w.g_c0[vi], 0, nullptr, 0, w.dgx, nullptr, w.dgh, nullptr, S_ONE, adj};
     cell_bwd(st, c0);
-    linear_wgrad(st, B, G3, SX, w.dgx, G3, Xi, XP, G[P_CD_WIH], SX);
+    linear_wgrad(st, B, G3, XP, w.dgx, G3, Xi, XP, w.dWihP[0], XP);
     colsum_accum(st, B, G3, w.dgh, G3, G[P_CD_BHH]);
     colsum_accum(st, B, G3, w.dgx, G3, G[P_CD_BIH]);
     // parameter head of node vi read h_{vi-1}
@@ -567,7 +584,7 @@ void decode_bwd_impl(dx_stream_t st, const Weights& W, const Weights& G, int B, 
     cell_bwd(st, cr);
     linear_dgrad(st, B, G3, H, w.dgh, G3, W[P_RD_WHH], H, w.dHinit, H, ACC_ADD);
     linear_wgrad(st, B, G3, H, w.dgh, G3, w.Hinit, H, G[P_RD_WHH], H);
-    linear_wgrad(st, B, G3, SX0, w.dgx, G3, bt.Xn, XP, G[P_RD_WIH], SX0);
+    linear_wgrad(st, B, G3, XP, w.dgx, G3, bt.Xn, XP, w.dWihP[2], XP);
     colsum_accum(st, B, G3, w.dgh, G3, G[P_RD_BHH]);
     colsum_accum(st, B, G3, w.dgx, G3, G[P_RD_BIH]);
   }
@@ -576,6 +593,9 @@ void decode_bwd_impl(dx_stream_t st, const Weights& W, const Weights& G, int B, 
   linear_wgrad(st, B, H, Z, w.dHinit, H, z, Z, G[P_ZH_W], Z);
   colsum_accum(st, B, H, w.dHinit, H, G[P_ZH_B]);
   linear_dgrad(st, B, H, Z, w.dHinit, H, W[P_ZH_W], Z, w.dz, Z, ACC_STORE);
+  unpad_add_wih(st, w.dWihP[0], SX, G[P_CD_WIH]);
+  unpad_add_wih(st, w.dWihP[1], SX, G[P_LD_WIH]);
+  unpad_add_wih(st, w.dWihP[2], SX0, G[P_RD_WIH]);
   (void)lw;
 }
 

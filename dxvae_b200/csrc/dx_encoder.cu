@@ -21,6 +21,8 @@ EncWs carve_enc(Arena& ar, int64_t B, bool train) {
   w.gxc = ar.take<float>(R6 * G3); w.gxl = ar.take<float>(R6 * G3); w.gh = ar.take<float>(R6 * G3);
   w.XnS = ar.take<float>(R6 * XP); w.pos = ar.take<int>(R7);
   if (train) {
+    for (int k = 0; k < 3; ++k) { w.WihP[k] = ar.take<float>((size_t)G3 * XP); w.dWihP[k] = ar.take<float>((size_t)G3 * XP); }
+    w.XnSL = ar.take<float>(R6 * XP);
     w.gc = ar.take<float>(R7 * 4 * H); w.gl = ar.take<float>(R7 * 4 * H);
     w.dH = ar.take<float>(R7 * H); w.dHin = ar.take<float>(R7 * H);
     w.dPg = ar.take<float>(R6 * 2 * H); w.dPm = ar.take<float>(R6 * 2 * H); w.dgb = ar.take<float>(R6 * H);
@@ -45,6 +47,13 @@ void encode_fwd_impl(dx_stream_t st, const Weights& W, const Batch& bt, const En
       st4f(XnS + p * XP + c, ld4f(Xn + (int64_t)rows[p] * XP + c));
     });
   }
+  // input weights: training uses 32-column padded copies (TMA-addressable); inference reads the blob
+  const float* Wc = W[P_CE_WIH]; const float* Wl = W[P_LE_WIH]; const float* Wr = W[P_RE_WIH];
+  int Kx = SX, Kr = SX0, ldx = SX, ldr = SX0;
+  if (train) {
+    pad_wih(st, W[P_CE_WIH], SX, w.WihP[0]); pad_wih(st, W[P_LE_WIH], SX, w.WihP[1]); pad_wih(st, W[P_RE_WIH], SX0, w.WihP[2]);
+    Wc = w.WihP[0]; Wl = w.WihP[1]; Wr = w.WihP[2]; Kx = Kr = ldx = ldr = XP;
+  }
   for (int L = 0; L < bt.n_levels; ++L) {
     const int base = bt.level_ptr[L];
     const int M = bt.level_ptr[L + 1] - base;
@@ -56,8 +65,8 @@ void encode_fwd_impl(dx_stream_t st, const Weights& W, const Batch& bt, const En
       mf.pos = w.pos;
       msg_fwd(st, mf);
     }
-    linear_fwd(st, M, G3, SX, w.XnS + (size_t)base * XP, XP, W[P_CE_WIH], SX, nullptr, w.gxc, G3);
-    linear_fwd(st, M, G3, SX, w.XnS + (size_t)base * XP, XP, W[P_LE_WIH], SX, nullptr, w.gxl, G3);
+    linear_fwd(st, M, G3, Kx, w.XnS + (size_t)base * XP, XP, Wc, ldx, nullptr, w.gxc, G3);
+    linear_fwd(st, M, G3, Kx, w.XnS + (size_t)base * XP, XP, Wl, ldx, nullptr, w.gxl, G3);
     if (L > 0) linear_fwd(st, M, G3, H, Hin, H, W[P_CE_WHH], H, nullptr, w.gh, G3);
     CellFwd c1{rm, w.gxc, L > 0 ? w.gh : nullptr, W[P_CE_BIH], W[P_CE_BHH], L > 0 ? Hin : nullptr, 0, Hc, 0,
                train ? w.gc + (size_t)base * 4 * H : nullptr, 0, S_ONE, bt.adj};
@@ -76,7 +85,7 @@ void encode_fwd_impl(dx_stream_t st, const Weights& W, const Batch& bt, const En
   MsgFwd mf{r0, w.Pg, w.Pm, W[P_G_B], bt.adj, Hin0, 0, -1, 0, 0};
   mf.pos = w.pos;
   msg_fwd(st, mf);
-  linear_fwd(st, B, G3, SX0, bt.Xn, XP, W[P_RE_WIH], SX0, nullptr, w.gxc, G3);
+  linear_fwd(st, B, G3, Kr, bt.Xn, XP, Wr, ldr, nullptr, w.gxc, G3);
   linear_fwd(st, B, G3, H, Hin0, H, W[P_RE_WHH], H, nullptr, w.gh, G3);
   CellFwd cr{r0, w.gxc, w.gh, W[P_RE_BIH], W[P_RE_BHH], Hin0, 0, Hv0, 0, train ? w.gc + (size_t)R6 * 4 * H : nullptr, 0,
              S_ONE, bt.adj};
@@ -92,6 +101,8 @@ void encode_bwd_impl(dx_stream_t st, const Weights& W, const Weights& G, const B
   const int64_t R6 = (int64_t)6 * B;
   float* Hin0 = w.Hin + (size_t)R6 * H; float* Hv0 = w.Hv + (size_t)R6 * H;
   float* dH0 = w.dH + (size_t)R6 * H; float* dHin0 = w.dHin + (size_t)R6 * H;
+  for (int k = 0; k < 3; ++k) zero_async(st, w.dWihP[k], sizeof(float) * G3 * XP);
+  mask_features(st, R6, B, bt.level_rows, 0, bt.adj, w.XnS, w.XnSL);
   // softplus': sigmoid(raw) = 1 - exp(-std)
   {
     float* dsraw = w.dsraw;
@@ -109,7 +120,7 @@ void encode_bwd_impl(dx_stream_t st, const Weights& W, const Weights& G, const B
   cell_bwd(st, cr);
   linear_dgrad(st, B, G3, H, w.dgh, G3, W[P_RE_WHH], H, dHin0, H, ACC_ADD);
   linear_wgrad(st, B, G3, H, w.dgh, G3, Hin0, H, G[P_RE_WHH], H);
-  linear_wgrad(st, B, G3, SX0, w.dgx, G3, bt.Xn, XP, G[P_RE_WIH], SX0);
+  linear_wgrad(st, B, G3, XP, w.dgx, G3, bt.Xn, XP, w.dWihP[2], XP);
   colsum_accum(st, B, G3, w.dgh, G3, G[P_RE_BHH]);
   colsum_accum(st, B, G3, w.dgx, G3, G[P_RE_BIH]);
 
@@ -132,11 +143,11 @@ void encode_bwd_impl(dx_stream_t st, const Weights& W, const Weights& G, const B
     linear_wgrad(st, M, 2 * H, H, w.dPm, 2 * H, Hv, H, G[P_M_W], H);
     colsum_accum(st, M, H, w.dgb, H, G[P_G_B]);
     // looper
-    CellBwd cl{rm, dH, 0, w.gl + (size_t)base * 4 * H, 0, Hc, 0, w.dgx, w.dgxs, w.dgh, w.dHc, S_SELF, bt.adj};
+    CellBwd cl{rm, dH, 0, w.gl + (size_t)base * 4 * H, 0, Hc, 0, w.dgx, nullptr, w.dgh, w.dHc, S_SELF, bt.adj};
     cell_bwd(st, cl);
     linear_dgrad(st, M, G3, H, w.dgh, G3, W[P_LE_WHH], H, w.dHc, H, ACC_ADD);
     linear_wgrad(st, M, G3, H, w.dgh, G3, Hc, H, G[P_LE_WHH], H);
-    linear_wgrad(st, M, G3, SX, w.dgxs, G3, Xs, XP, G[P_LE_WIH], SX);
+    linear_wgrad(st, M, G3, XP, w.dgx, G3, w.XnSL + (size_t)base * XP, XP, w.dWihP[1], XP);   // x masked by the self-loop flag
     colsum_accum(st, M, G3, w.dgh, G3, G[P_LE_BHH]);
     colsum_accum(st, M, G3, w.dgx, G3, G[P_LE_BIH]);
     // combiner
@@ -147,10 +158,13 @@ void encode_bwd_impl(dx_stream_t st, const Weights& W, const Weights& G, const B
       linear_dgrad(st, M, G3, H, w.dgh, G3, W[P_CE_WHH], H, dHin, H, ACC_ADD);
       linear_wgrad(st, M, G3, H, w.dgh, G3, Hin, H, G[P_CE_WHH], H);
     }
-    linear_wgrad(st, M, G3, SX, w.dgx, G3, Xs, XP, G[P_CE_WIH], SX);
+    linear_wgrad(st, M, G3, XP, w.dgx, G3, Xs, XP, w.dWihP[0], XP);
     colsum_accum(st, M, G3, w.dgh, G3, G[P_CE_BHH]);
     colsum_accum(st, M, G3, w.dgx, G3, G[P_CE_BIH]);
   }
+  unpad_add_wih(st, w.dWihP[0], SX, G[P_CE_WIH]);
+  unpad_add_wih(st, w.dWihP[1], SX, G[P_LE_WIH]);
+  unpad_add_wih(st, w.dWihP[2], SX0, G[P_RE_WIH]);
 }
 
 int encode_fwd(dx_stream_t st, const float* weights, const Batch& bt, float* mu, float* std_, void* ws,

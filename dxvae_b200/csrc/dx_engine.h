@@ -37,6 +37,9 @@ struct EncWs {
   // [6B,7B) = node 0 of graph b.  pos[v*B+b] maps a node back to its position.
   float *Hin, *Hc, *Hv, *gc, *gl, *Pg, *Pm, *gxc, *gxl, *gh, *XnS;
   int* pos;
+  // training only: input weights padded 27/23 -> 32 columns (16-byte rows, so these products and their
+  // gradients are TMA-addressable), self-loop-masked features for the looper's weight gradient
+  float *WihP[3], *dWihP[3], *XnSL;
   float *dH, *dHin, *dPg, *dPm, *dgb, *dgx, *dgxs, *dgh, *dHc, *dsraw;
 };
 constexpr int LD_L = 64;  // leading dimension of logit buffers (55 / 27 columns used)
@@ -50,6 +53,7 @@ struct DecWs {
   float *E1[NSTEP], *l2[NSTEP], *dl2[NSTEP], *Hin[NSTEP], *g_c[NSTEP], *Hc[NSTEP], *g_l[NSTEP], *Hi[NSTEP];
   float *gh, *ghl0, *Hrun, *rowloss;
   float *U, *UC, *dHiC;    // compacted teacher forcing: running edge-head product, compact temp, compact dHi
+  float *WihP[3], *dWihP[3], *XL, *xc;   // padded input weights / grads (comb, loop, root), masked features (7B,32), compact x rows
   // greedy only
   float *Xd, *Pn;
   // backward temporaries
@@ -77,6 +81,12 @@ void kld_rows(dx_stream_t st, int B, const float* mu, const float* sd, LossW lw,
 void latent_bwd(dx_stream_t st, int B, const float* mu, const float* sd, const float* eps, const float* dz, LossW lw,
                 float* dmu, float* dsd);
 void loss_reduce(dx_stream_t st, int B, const float* rowloss, float* out);
+
+// input-weight padding helpers (dx_data.cu)
+void pad_wih(dx_stream_t st, const float* W, int K, float* Wp);             // (1536,K) -> (1536,32), zero filled
+void unpad_add_wih(dx_stream_t st, const float* dWp, int K, float* dW);      // dW[:, :K] += dWp[:, :K]
+void mask_features(dx_stream_t st, int64_t rows, int B, const int* row_ids, int row_base, const uint64_t* adj,
+                   const float* X, float* XL);                                // XL[m] = selfloop(row) * X[m]
 
 size_t workspace_bytes(int op, int64_t B);
 
