@@ -264,6 +264,11 @@ def run_ours(args):
             model.encode(gb); torch.cuda.synchronize()
             t0 = time.perf_counter(); model.encode(gb); torch.cuda.synchronize()
             extra["encode_patches_per_s"] = ne / (time.perf_counter() - t0)
+            model.encode_precision = "tf32"
+            model.encode(gb); torch.cuda.synchronize()
+            t0 = time.perf_counter(); model.encode(gb); torch.cuda.synchronize()
+            extra["encode_tf32_patches_per_s"] = ne / (time.perf_counter() - t0)
+            model.encode_precision = "fp32"
             z = torch.randn(16384, 128, device="cuda")
             model.decode(z); torch.cuda.synchronize()
             t0 = time.perf_counter(); model.decode(z); torch.cuda.synchronize()

@@ -447,12 +447,10 @@ static void looper_bwd(dx_stream_t st, const Weights& W, const Weights& G, int B
   const int M = rm.M;
   float* direct = dHc_accum ? w.dHin : dHc;  // dHin is free scratch at this point
   CellBwd cb{rm, dHi, 0, gates, 0, Hc, 0, w.dgx, nullptr, w.dgh, direct, smode, adj};
-  cell_bwd(st, cb);
+  cell_bwd(st, cb, G[P_LD_BIH], G[P_LD_BHH]);
   if (dHc_accum) add_inplace(st, (int64_t)M * H / 4, dHc, direct);
   linear_dgrad(st, M, G3, H, w.dgh, G3, W[P_LD_WHH], H, dHc, H, ACC_ADD);
   linear_wgrad(st, M, G3, H, w.dgh, G3, Hc, H, G[P_LD_WHH], H);
-  colsum_accum(st, M, G3, w.dgh, G3, G[P_LD_BHH]);
-  colsum_accum(st, M, G3, w.dgx, G3, G[P_LD_BIH]);
   // weight_ih gradient: x masked by the self-loop flag (XL), gathered to the active rows when compacted
   if (smode != S_ZERO) {
     const float* xl = w.XL + (size_t)vi * B * XP;
@@ -499,13 +497,11 @@ void decode_bwd_impl(dx_stream_t st, const Weights& W, const Weights& G, int B, 
           linear_wgrad(st, n, 4 * H, H, w.UC, 4 * H, w.Hi[t], H, G[P_E_W0], 2 * H);
           looper_bwd(st, W, G, B, vi, rc, w.dHiC, w.g_l[t], w.Hc[t], S_SELF, adj, Xi, w, w.dHc, false);
           CellBwd cc{rc, w.dHc, 0, w.g_c[t], 0, w.Hin[t], 0, w.dgx, nullptr, w.dgh, w.dHin, S_ONE, adj};
-          cell_bwd(st, cc);
+          cell_bwd(st, cc, G[P_CD_BIH], G[P_CD_BHH]);
           linear_dgrad(st, n, G3, H, w.dgh, G3, W[P_CD_WHH], H, w.dHin, H, ACC_ADD);
           linear_wgrad(st, n, G3, H, w.dgh, G3, w.Hin[t], H, G[P_CD_WHH], H);
           gather_rows(st, n, XP, rows, const_cast<float*>(Xi), w.xc, 0);
           linear_wgrad(st, n, G3, XP, w.dgx, G3, w.xc, XP, w.dWihP[0], XP);
-          colsum_accum(st, n, G3, w.dgh, G3, G[P_CD_BHH]);
-          colsum_accum(st, n, G3, w.dgx, G3, G[P_CD_BIH]);
           scatter_rows(st, n, H, rows, w.dHin, w.dHrun, 1);
           RowMap rs{n, B, rows, vj * B};
           MsgBwd mb{rs, w.Pg, w.Pm, W[P_G_B], adj, w.dHrun, 0, w.dPg, w.dPm, w.dgb, 1, vi, vi, 1};
@@ -524,12 +520,10 @@ void decode_bwd_impl(dx_stream_t st, const Weights& W, const Weights& G, int B, 
       // looper then combiner of this propagate
       looper_bwd(st, W, G, B, vi, rm, w.dHi, w.g_l[t], w.Hc[t], S_SELF, adj, Xi, w, w.dHc, false);
       CellBwd cc{rm, w.dHc, 0, w.g_c[t], 0, w.Hin[t], 0, w.dgx, nullptr, w.dgh, w.dHin, S_ONE, adj};
-      cell_bwd(st, cc);
+      cell_bwd(st, cc, G[P_CD_BIH], G[P_CD_BHH]);
       linear_dgrad(st, B, G3, H, w.dgh, G3, W[P_CD_WHH], H, w.dHin, H, ACC_ADD);
       linear_wgrad(st, B, G3, H, w.dgh, G3, w.Hin[t], H, G[P_CD_WHH], H);
       linear_wgrad(st, B, G3, XP, w.dgx, G3, Xi, XP, w.dWihP[0], XP);
-      colsum_accum(st, B, G3, w.dgh, G3, G[P_CD_BHH]);
-      colsum_accum(st, B, G3, w.dgx, G3, G[P_CD_BIH]);
       add_inplace(st, (int64_t)bH / 4, w.dHrun, w.dHin);
       // message of vj was part of this and every later aggregate of node vi
       RowMap rs{B, B, nullptr, vj * B};
@@ -555,10 +549,8 @@ void decode_bwd_impl(dx_stream_t st, const Weights& W, const Weights& G, int B, 
     looper_bwd(st, W, G, B, vi, rm, w.dHi, w.g_p1[vi], w.Hc0[vi], S_ZERO, adj, Xi, w, w.dHc0, true);
     // combiner with H_in = 0: only input weights / biases receive gradient
     CellBwd c0{rm, w.dHc0, 0, w.g_c0[vi], 0, nullptr, 0, w.dgx, nullptr, w.dgh, nullptr, S_ONE, adj};
-    cell_bwd(st, c0);
+    cell_bwd(st, c0, G[P_CD_BIH], G[P_CD_BHH]);
     linear_wgrad(st, B, G3, XP, w.dgx, G3, Xi, XP, w.dWihP[0], XP);
-    colsum_accum(st, B, G3, w.dgh, G3, G[P_CD_BHH]);
-    colsum_accum(st, B, G3, w.dgx, G3, G[P_CD_BIH]);
     // parameter head of node vi read h_{vi-1}
     float* dprev = w.dHd + (size_t)(vi - 1) * bH;
     const float* hprev = w.Hd + (size_t)(vi - 1) * bH;
@@ -581,12 +573,10 @@ void decode_bwd_impl(dx_stream_t st, const Weights& W, const Weights& G, int B, 
   {
     RowMap rm{B, B, nullptr, 0};
     CellBwd cr{rm, w.dHd, 0, w.g_root, 0, w.Hinit, 0, w.dgx, nullptr, w.dgh, w.dHinit, S_ONE, adj};
-    cell_bwd(st, cr);
+    cell_bwd(st, cr, G[P_RD_BIH], G[P_RD_BHH]);
     linear_dgrad(st, B, G3, H, w.dgh, G3, W[P_RD_WHH], H, w.dHinit, H, ACC_ADD);
     linear_wgrad(st, B, G3, H, w.dgh, G3, w.Hinit, H, G[P_RD_WHH], H);
     linear_wgrad(st, B, G3, XP, w.dgx, G3, bt.Xn, XP, w.dWihP[2], XP);
-    colsum_accum(st, B, G3, w.dgh, G3, G[P_RD_BHH]);
-    colsum_accum(st, B, G3, w.dgx, G3, G[P_RD_BIH]);
   }
   mlp3_bwd(st, W, G, B, P_X0_W0, w.Hinit, SX0 + 32, w.A1[0], w.A2[0], w.dL[0], w, w.dHinit);
   tanh_bwd(st, (int64_t)bH, w.dHinit, w.Hinit);

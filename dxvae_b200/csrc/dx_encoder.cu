@@ -117,12 +117,10 @@ void encode_bwd_impl(dx_stream_t st, const Weights& W, const Weights& G, const B
   // root cell
   RowMap r0{B, B, nullptr, 0};
   CellBwd cr{r0, dH0, 0, w.gc + (size_t)R6 * 4 * H, 0, Hin0, 0, w.dgx, nullptr, w.dgh, dHin0, S_ONE, bt.adj};
-  cell_bwd(st, cr);
+  cell_bwd(st, cr, G[P_RE_BIH], G[P_RE_BHH]);
   linear_dgrad(st, B, G3, H, w.dgh, G3, W[P_RE_WHH], H, dHin0, H, ACC_ADD);
   linear_wgrad(st, B, G3, H, w.dgh, G3, Hin0, H, G[P_RE_WHH], H);
   linear_wgrad(st, B, G3, XP, w.dgx, G3, bt.Xn, XP, w.dWihP[2], XP);
-  colsum_accum(st, B, G3, w.dgh, G3, G[P_RE_BHH]);
-  colsum_accum(st, B, G3, w.dgx, G3, G[P_RE_BIH]);
 
   for (int L = bt.n_levels - 1; L >= 0; --L) {
     const int base = bt.level_ptr[L];
@@ -144,23 +142,19 @@ void encode_bwd_impl(dx_stream_t st, const Weights& W, const Weights& G, const B
     colsum_accum(st, M, H, w.dgb, H, G[P_G_B]);
     // looper
     CellBwd cl{rm, dH, 0, w.gl + (size_t)base * 4 * H, 0, Hc, 0, w.dgx, nullptr, w.dgh, w.dHc, S_SELF, bt.adj};
-    cell_bwd(st, cl);
+    cell_bwd(st, cl, G[P_LE_BIH], G[P_LE_BHH]);
     linear_dgrad(st, M, G3, H, w.dgh, G3, W[P_LE_WHH], H, w.dHc, H, ACC_ADD);
     linear_wgrad(st, M, G3, H, w.dgh, G3, Hc, H, G[P_LE_WHH], H);
     linear_wgrad(st, M, G3, XP, w.dgx, G3, w.XnSL + (size_t)base * XP, XP, w.dWihP[1], XP);   // x masked by the self-loop flag
-    colsum_accum(st, M, G3, w.dgh, G3, G[P_LE_BHH]);
-    colsum_accum(st, M, G3, w.dgx, G3, G[P_LE_BIH]);
     // combiner
     CellBwd cc{rm, w.dHc, 0, w.gc + (size_t)base * 4 * H, 0, L > 0 ? Hin : nullptr, 0, w.dgx, nullptr, w.dgh,
                L > 0 ? dHin : nullptr, S_ONE, bt.adj};
-    cell_bwd(st, cc);
+    cell_bwd(st, cc, G[P_CE_BIH], G[P_CE_BHH]);
     if (L > 0) {
       linear_dgrad(st, M, G3, H, w.dgh, G3, W[P_CE_WHH], H, dHin, H, ACC_ADD);
       linear_wgrad(st, M, G3, H, w.dgh, G3, Hin, H, G[P_CE_WHH], H);
     }
     linear_wgrad(st, M, G3, XP, w.dgx, G3, Xs, XP, w.dWihP[0], XP);
-    colsum_accum(st, M, G3, w.dgh, G3, G[P_CE_BHH]);
-    colsum_accum(st, M, G3, w.dgx, G3, G[P_CE_BIH]);
   }
   unpad_add_wih(st, w.dWihP[0], SX, G[P_CE_WIH]);
   unpad_add_wih(st, w.dWihP[1], SX, G[P_LE_WIH]);

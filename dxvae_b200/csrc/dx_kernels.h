@@ -86,43 +86,106 @@ struct CellBwd {
   int dhp_global = 0;
 };
 
-inline void cell_bwd(dx_stream_t st, const CellBwd& a) {
-  foreach (st, (int64_t)a.rm.M * (H / 4), [=] DX_HD(int64_t idx) {
-    const int m = (int)(idx / (H / 4)), n = (int)(idx % (H / 4)) * 4;
-    const int r = a.rm.r(m);
-    float s = 1.f;
-    if (a.smode == S_ZERO) s = 0.f;
-    else if (a.smode == S_SELF) { const int b = r % a.rm.B, v = r / a.rm.B; s = (float)abit(a.adj[b], v, v); }
-    const float4 d = ld4f(a.dh + (int64_t)(a.dh_global ? r : m) * H + n);
-    const float* g = a.gates + (int64_t)(a.gates_global ? r : m) * (4 * H) + n;
-    const float4 R = ld4f(g), Zg = ld4f(g + H), Ng = ld4f(g + 2 * H), NH = ld4f(g + 3 * H);
-    float4 hp = f4zero();
-    if (a.hprev) hp = ld4f(a.hprev + (int64_t)(a.hprev_global ? r : m) * H + n);
-    float4 ar, az, an, anr, dp;
+// One (row m, 4 hidden units at n) element of the backward pass; returns the bias-gradient
+// contributions (ar, az, an, an*r) of that element.
+DX_HD DX_INLINE void cell_bwd_elem(const CellBwd& a, int m, int n, float4& ar, float4& az, float4& an, float4& anr) {
+  const int r = a.rm.r(m);
+  float s = 1.f;
+  if (a.smode == S_ZERO) s = 0.f;
+  else if (a.smode == S_SELF) { const int b = r % a.rm.B, v = r / a.rm.B; s = (float)abit(a.adj[b], v, v); }
+  const float4 d = ld4f(a.dh + (int64_t)(a.dh_global ? r : m) * H + n);
+  const float* g = a.gates + (int64_t)(a.gates_global ? r : m) * (4 * H) + n;
+  const float4 R = ld4f(g), Zg = ld4f(g + H), Ng = ld4f(g + 2 * H), NH = ld4f(g + 3 * H);
+  float4 hp = f4zero();
+  if (a.hprev) hp = ld4f(a.hprev + (int64_t)(a.hprev_global ? r : m) * H + n);
+  float4 dp;
 #define DX_CELLB(c)                                            \
-    {                                                          \
-      const float dn = d.c * (1.f - Zg.c);                     \
-      const float dz = d.c * (hp.c - Ng.c);                    \
-      const float dan = dn * (1.f - Ng.c * Ng.c);              \
-      const float dr = dan * NH.c;                             \
-      ar.c = dr * R.c * (1.f - R.c);                           \
-      az.c = dz * Zg.c * (1.f - Zg.c);                         \
-      an.c = dan; anr.c = dan * R.c; dp.c = d.c * Zg.c;        \
-    }
-    DX_CELLB(x) DX_CELLB(y) DX_CELLB(z) DX_CELLB(w)
+  {                                                            \
+    const float dn = d.c * (1.f - Zg.c);                       \
+    const float dz = d.c * (hp.c - Ng.c);                      \
+    const float dan = dn * (1.f - Ng.c * Ng.c);                \
+    const float dr = dan * NH.c;                               \
+    ar.c = dr * R.c * (1.f - R.c);                             \
+    az.c = dz * Zg.c * (1.f - Zg.c);                           \
+    an.c = dan; anr.c = dan * R.c; dp.c = d.c * Zg.c;          \
+  }
+  DX_CELLB(x) DX_CELLB(y) DX_CELLB(z) DX_CELLB(w)
 #undef DX_CELLB
-    float* o = a.dgx + (int64_t)m * G3 + n;
-    st4f(o, ar); st4f(o + H, az); st4f(o + 2 * H, an);
-    if (a.dgxs) {
-      float* os = a.dgxs + (int64_t)m * G3 + n;
-      st4f(os, make_float4(s * ar.x, s * ar.y, s * ar.z, s * ar.w));
-      st4f(os + H, make_float4(s * az.x, s * az.y, s * az.z, s * az.w));
-      st4f(os + 2 * H, make_float4(s * an.x, s * an.y, s * an.z, s * an.w));
+  float* o = a.dgx + (int64_t)m * G3 + n;
+  st4f(o, ar); st4f(o + H, az); st4f(o + 2 * H, an);
+  if (a.dgxs) {
+    float* os = a.dgxs + (int64_t)m * G3 + n;
+    st4f(os, make_float4(s * ar.x, s * ar.y, s * ar.z, s * ar.w));
+    st4f(os + H, make_float4(s * az.x, s * az.y, s * az.z, s * az.w));
+    st4f(os + 2 * H, make_float4(s * an.x, s * an.y, s * an.z, s * an.w));
+  }
+  float* oh = a.dgh + (int64_t)m * G3 + n;
+  st4f(oh, ar); st4f(oh + H, az); st4f(oh + 2 * H, anr);
+  if (a.dhp) st4f(a.dhp + (int64_t)(a.dhp_global ? r : m) * H + n, dp);
+}
+
+#ifndef DX_EMU
+// Block = 4 row groups x 128 threads (the 512 hidden units, 4 per thread); blocks stride over rows.
+// Every thread keeps the column sums of its 4 units in registers (bias gradients = column sums of
+// dgx / dgh), the 4 row groups are folded through shared memory, and 128 threads issue the atomics:
+// no second pass over 12 KB/row, and only 2 blocks/SM worth of atomics per address.
+static __global__ void __launch_bounds__(512) k_cell_bwd(const CellBwd a, float* __restrict__ dbih, float* __restrict__ dbhh) {
+  __shared__ float red[3][16][128];
+  const int q = threadIdx.x & 127, rg = threadIdx.x >> 7;
+  const int n = q * 4;
+  float4 sr = f4zero(), sz = f4zero(), sn = f4zero(), snr = f4zero();
+  for (int m = blockIdx.x * 4 + rg; m < a.rm.M; m += gridDim.x * 4) {
+    float4 ar, az, an, anr;
+    cell_bwd_elem(a, m, n, ar, az, an, anr);
+    sr.x += ar.x; sr.y += ar.y; sr.z += ar.z; sr.w += ar.w;
+    sz.x += az.x; sz.y += az.y; sz.z += az.z; sz.w += az.w;
+    sn.x += an.x; sn.y += an.y; sn.z += an.z; sn.w += an.w;
+    snr.x += anr.x; snr.y += anr.y; snr.z += anr.z; snr.w += anr.w;
+  }
+  if (!dbih) return;
+  const float v[16] = {sr.x, sr.y, sr.z, sr.w, sz.x, sz.y, sz.z, sz.w, sn.x, sn.y, sn.z, sn.w, snr.x, snr.y, snr.z, snr.w};
+  if (rg > 0) {
+#pragma unroll
+    for (int e = 0; e < 16; ++e) red[rg - 1][e][q] = v[e];
+  }
+  __syncthreads();
+  if (rg == 0) {
+    float t[16];
+#pragma unroll
+    for (int e = 0; e < 16; ++e) t[e] = v[e] + red[0][e][q] + red[1][e][q] + red[2][e][q];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      atomicAdd(dbih + n + e, t[e]);          atomicAdd(dbhh + n + e, t[e]);            // r gate
+      atomicAdd(dbih + H + n + e, t[4 + e]);  atomicAdd(dbhh + H + n + e, t[4 + e]);    // z gate
+      atomicAdd(dbih + 2 * H + n + e, t[8 + e]);                                         // n gate, input side
+      atomicAdd(dbhh + 2 * H + n + e, t[12 + e]);                                        // n gate, hidden side (x r)
     }
-    float* oh = a.dgh + (int64_t)m * G3 + n;
-    st4f(oh, ar); st4f(oh + H, az); st4f(oh + 2 * H, anr);
-    if (a.dhp) st4f(a.dhp + (int64_t)(a.dhp_global ? r : m) * H + n, dp);
-  });
+  }
+}
+#endif
+
+// dbih / dbhh (optional): bias_ih / bias_hh gradients, accumulated (+=) with the column sums of dgx / dgh.
+inline void cell_bwd(dx_stream_t st, const CellBwd& a, float* dbih = nullptr, float* dbhh = nullptr) {
+  if (a.rm.M <= 0) return;
+#ifndef DX_EMU
+  int blocks = (a.rm.M + 3) / 4;
+  if (blocks > 148 * 2) blocks = 148 * 2;
+  k_cell_bwd<<<blocks, 512, 0, st>>>(a, dbih, dbhh);
+  ++g_launches;
+#else
+  for (int m = 0; m < a.rm.M; ++m)
+    for (int n = 0; n < H; n += 4) {
+      float4 ar, az, an, anr;
+      cell_bwd_elem(a, m, n, ar, az, an, anr);
+      if (dbih) {
+        const float vi[12] = {ar.x, ar.y, ar.z, ar.w, az.x, az.y, az.z, az.w, an.x, an.y, an.z, an.w};
+        const float vh[12] = {ar.x, ar.y, ar.z, ar.w, az.x, az.y, az.z, az.w, anr.x, anr.y, anr.z, anr.w};
+        for (int g = 0; g < 3; ++g)
+          for (int e = 0; e < 4; ++e) { dbih[g * H + n + e] += vi[g * 4 + e]; dbhh[g * H + n + e] += vh[g * 4 + e]; }
+      }
+    }
+  ++g_launches;
+#endif
 }
 
 // ------------------------------------------------------------------------------------

@@ -451,8 +451,9 @@ bool launch_tc(dx_stream_t s, const GemmP& g) {
   const int gm = (g.M + TBM - 1) / TBM, gn = (g.N + BN - 1) / BN;
   int splits = 1;
   if (g.accum == ACC_ATOMIC) {
+    // split the batch reduction so that tiles x splits just fits two rounds of the persistent grid
     const int tiles = gm * gn;
-    const int want = (148 * 2 + tiles - 1) / tiles;
+    const int want = (148 * 2) / tiles;                        // floor: never spill into a third round
     const int maxs = (g.K + TBK * 16 - 1) / (TBK * 16);       // >= 512 reduction rows per split
     splits = want < 1 ? 1 : (want > maxs ? maxs : want);
   }

@@ -73,6 +73,9 @@ class DXVAE(nn.Module):
         # (tcgen05 tensor cores, looser stated tolerance).  Encode for inference and greedy decode
         # always run in fp32 so their outputs match the reference's decisions.
         self.precision = "fp32"
+        # inference encode: "fp32" (default, reference-tolerance latents) or "tf32" (tensor cores,
+        # latents within the looser TF32 bound of tests/test_gpu_tf32.py); greedy decode is always fp32
+        self.encode_precision = "fp32"
         # skip teacher-forced re-propagates that add no edge (exact; see dxvae_batch_steps)
         self.compact_steps = True
         if checkpoint is not None:
@@ -226,7 +229,8 @@ class DXVAE(nn.Module):
             ws = self._workspace(_abi.OP_ENCODE, d.B)
             _lib.check(L.dxvae_encode_fwd(self._flat.data_ptr(), d.B, d.Xn.data_ptr(), d.adj.data_ptr(), d.n_levels,
                                           d.level_ptr.ctypes.data, d.level_rows.data_ptr(), mu[lo:hi].data_ptr(),
-                                          sd[lo:hi].data_ptr(), ws.data_ptr(), ws.numel(), 0, _abi.PREC_FP32, _stream()),
+                                          sd[lo:hi].data_ptr(), ws.data_ptr(), ws.numel(), 0,
+                                          _abi.PREC_TF32 if self.encode_precision == "tf32" else _abi.PREC_FP32, _stream()),
                        "dxvae_encode_fwd")
         return Normal(mu, sd, validate_args=False)
 

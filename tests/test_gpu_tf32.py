@@ -91,3 +91,20 @@ def test_tf32_training_step_within_stated_tolerance(lib):
     print("tf32 loss rel", rel, "worst grad rel", max(worst.values()), max(worst, key=worst.get))
     assert max(rel) <= TF32_LOSS, rel
     assert max(worst.values()) <= TF32_GRAD, sorted(worst.items(), key=lambda kv: -kv[1])[:5]
+
+
+def test_tf32_inference_encode_within_stated_tolerance(lib):
+    """encode_precision="tf32": latents within 2e-3 abs of the oracle (|mu| ~ 0.03..1, std ~ 0.7)."""
+    from dxvae_b200 import DXVAE
+    from dxvae_b200.dxdata import DXGraph
+    idx = list(range(0, 1024, 4))
+    X, P, E, A = util.dataset_graphs(idx)
+    o = O.make_weights(0, 3.0)
+    m = DXVAE(); m.load_state_dict(o.state_dict()); m.verbose = False
+    m.encode_precision = "tf32"
+    with torch.no_grad():
+        q = m.encode([DXGraph(X[i], P[i], *E[i]) for i in range(len(idx))])
+        mu_o, sd_o = o.encode(X, A)
+    err = max((q.loc.cpu() - mu_o).abs().max().item(), (q.scale.cpu() - sd_o).abs().max().item())
+    print("tf32 encode latent err", err)
+    assert err <= 2e-3
