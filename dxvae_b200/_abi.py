@@ -33,7 +33,7 @@ SIGNATURES = {
     "dxvae_workspace_bytes": (SZ, [C.c_int, I64]),
     "dxvae_encode_fwd": (C.c_int, [P, I64, P, P, I32, P, P, P, P, P, SZ, C.c_int, C.c_int, P]),
     "dxvae_reparameterize": (C.c_int, [I64, P, P, P, P, P]),
-    "dxvae_decode_greedy": (C.c_int, [P, I64, P, P, P, P, P, P, SZ, P]),
+    "dxvae_decode_greedy": (C.c_int, [P, I64, P, P, P, P, P, P, SZ, C.c_int, P]),
     "dxvae_elbo_step": (C.c_int, [P, I64, P, P, P, I32, P, P, P, F, F, F, F, P, P, P, P, P, SZ, C.c_int, P, P, P]),
     "dxvae_loss_step": (C.c_int, [P, I64, P, P, P, P, P, P, F, F, F, F, P, P, P, P, P, SZ, C.c_int, P, P, P]),
     "dxvae_encode_bwd": (C.c_int, [P, I64, P, P, I32, P, P, P, P, P, P, P, SZ, C.c_int, P]),
@@ -41,7 +41,7 @@ SIGNATURES = {
     "dxvae_test_gemm": (C.c_int, [C.c_int, I64, I64, I64, P, I64, P, I64, P, I64, P, C.c_int, C.c_int, P]),
 }
 
-PREC_FP32, PREC_TF32 = 0, 1
+PREC_FP32, PREC_TF32, PREC_3XTF32 = 0, 1, 2
 OP_ENCODE, OP_DECODE, OP_TRAIN, OP_SCHEDULE, OP_ENCODE_TRAIN, OP_LOSS = 0, 1, 2, 3, 4, 5
 
 

@@ -105,16 +105,25 @@ int encode_bwd(dx_stream_t st, const float* weights, const Batch& bt, const floa
 }
 
 int decode_greedy(dx_stream_t st, const float* weights, int64_t B64, const float* z, float* Xg, float* Pg,
-                  uint64_t* adj, float* margins, void* ws, size_t ws_bytes) {
+                  uint64_t* adj, float* margins, void* ws, size_t ws_bytes, int precision) {
   const int B = (int)B64;
+  PrecisionScope prec(precision);
   Arena ar(ws, ws_bytes);
   DecWs w = carve_dec(ar, B64, false);
   DX_CHECK(!ar.overflow, "decode_greedy: workspace too small (%zu < %zu bytes)", ws_bytes, ar.off);
   Weights W(weights);
   zero_async(st, adj, sizeof(uint64_t) * (size_t)B);
   if (margins) foreach (st, B, [=] DX_HD(int64_t i) { margins[i] = 3.0e38f; });
+  SplitCtx sc;
+  if (precision == PREC_3XTF32) {
+    split_tf32(st, 1, param_blob_floats(), weights, param_blob_floats(), w.Whi, w.Wlo);
+    sc.w_base = weights; sc.w_floats = param_blob_floats(); sc.w_hi = w.Whi; sc.w_lo = w.Wlo;
+    sc.a_hi = w.xs_hi; sc.a_lo = w.xs_lo; sc.a_floats = (int64_t)B * 2 * H;
+    set_split_ctx(&sc);
+  }
   DecIO io{false, nullptr, LossW{0, 0, 0, 0}, adj, margins};
   decode_fwd_impl(st, W, B, z, w, io);
+  set_split_ctx(nullptr);
   unpack_graphs(st, B, w.Xd, w.Pn, Xg, Pg);
   return check_launch("decode_greedy");
 }
@@ -189,7 +198,7 @@ int dxvae_encode_fwd(const float* weights, int64_t B, const float* Xn, const uin
                      size_t workspace_bytes, int keep, int precision, void* stream) {
   DX_BATCH_OK(B);
   DX_CHECK(n_levels >= 1 && n_levels <= 6, "encode_fwd: n_levels=%d", n_levels);
-  DX_CHECK(precision == PREC_FP32 || precision == PREC_TF32, "encode_fwd: unknown precision %d", precision);
+  DX_CHECK(precision >= PREC_FP32 && precision <= PREC_3XTF32, "encode_fwd: unknown precision %d", precision);
   Batch bt{B, Xn, nullptr, adj, n_levels, level_ptr_host, level_rows};
   PrecisionScope prec(precision);
   return encode_fwd(DX_ST(stream), weights, bt, mu, std_, workspace, workspace_bytes, keep);
@@ -198,9 +207,10 @@ int dxvae_reparameterize(int64_t n, const float* mu, const float* std_, const fl
   return reparameterize(DX_ST(stream), n, mu, std_, eps, z);
 }
 int dxvae_decode_greedy(const float* weights, int64_t B, const float* z, float* Xg, float* Pg, uint64_t* adj,
-                        float* margins, void* workspace, size_t workspace_bytes, void* stream) {
+                        float* margins, void* workspace, size_t workspace_bytes, int precision, void* stream) {
   DX_BATCH_OK(B);
-  return decode_greedy(DX_ST(stream), weights, B, z, Xg, Pg, adj, margins, workspace, workspace_bytes);
+  DX_CHECK(precision == PREC_FP32 || precision == PREC_3XTF32, "decode_greedy: precision must be FP32 or 3XTF32 (discrete outputs)");
+  return decode_greedy(DX_ST(stream), weights, B, z, Xg, Pg, adj, margins, workspace, workspace_bytes, precision);
 }
 int dxvae_elbo_step(const float* weights, int64_t B, const float* Xn, const int32_t* cls, const uint64_t* adj,
                     int32_t n_levels, const int32_t* level_ptr_host, const int32_t* level_rows, const float* eps,
@@ -248,13 +258,29 @@ int dxvae_adamw_step(int64_t n, float* weights, const float* grads, float* exp_a
 }
 int dxvae_test_gemm(int variant, int64_t M, int64_t N, int64_t K, const float* A, int64_t lda, const float* Bm,
                     int64_t ldb, float* C, int64_t ldc, const float* bias, int act, int accumulate, void* stream) {
-  // variant 0: y = act(x W^T + b) ; 1: dx (+)= dy W ; 2: dW += dy^T x ; +16: tcgen05 TF32 path
-  PrecisionScope prec((variant & 16) ? PREC_TF32 : PREC_FP32);
+  // variant 0: y = act(x W^T + b) ; 1: dx (+)= dy W ; 2: dW += dy^T x ; +16: tcgen05 TF32 path ; +32: 3xTF32
+  PrecisionScope prec((variant & 32) ? PREC_3XTF32 : ((variant & 16) ? PREC_TF32 : PREC_FP32));
+  SplitCtx sc;
+#ifndef DX_EMU
+  float* tmp = nullptr;
+  if (variant & 32) {     // test-only scratch: the weight operand plays the role of the parameter blob
+    const int64_t wf = (int64_t)N * ldb, af = (int64_t)M * K;
+    cudaMalloc(&tmp, sizeof(float) * (2 * wf + 2 * af));
+    split_tf32(DX_ST(stream), 1, wf, Bm, wf, tmp, tmp + wf);
+    sc.w_base = Bm; sc.w_floats = wf; sc.w_hi = tmp; sc.w_lo = tmp + wf;
+    sc.a_hi = tmp + 2 * wf; sc.a_lo = tmp + 2 * wf + af; sc.a_floats = af;
+    set_split_ctx(&sc);
+  }
+#endif
   variant &= 15;
   if (variant == 0) linear_fwd(DX_ST(stream), (int)M, (int)N, (int)K, A, lda, Bm, ldb, bias, C, ldc, act);
   else if (variant == 1) linear_dgrad(DX_ST(stream), (int)M, (int)N, (int)K, A, lda, Bm, ldb, C, ldc, accumulate);
   else if (variant == 2) linear_wgrad(DX_ST(stream), (int)M, (int)N, (int)K, A, lda, Bm, ldb, C, ldc);
   else { set_error("test_gemm: unknown variant %d", variant); return 1; }
+  set_split_ctx(nullptr);
+#ifndef DX_EMU
+  if (tmp) { cudaStreamSynchronize(DX_ST(stream)); cudaFree(tmp); }
+#endif
   return check_launch("test_gemm");
 }
 

@@ -55,6 +55,8 @@ DecWs carve_dec(Arena& ar, int64_t B, bool train) {
     w.dES1 = ar.take<float>(b * 2 * H); w.dHinit = ar.take<float>(b * H); w.dz = ar.take<float>(b * Z);
   } else {
     w.Xd = ar.take<float>(7 * b * XP); w.Pn = ar.take<float>(7 * b * XP);
+    w.Whi = ar.take<float>((size_t)param_blob_floats()); w.Wlo = ar.take<float>((size_t)param_blob_floats());
+    w.xs_hi = ar.take<float>(b * 2 * H); w.xs_lo = ar.take<float>(b * 2 * H);
   }
   return w;
 }

@@ -37,6 +37,7 @@ struct EncWs {
   // [6B,7B) = node 0 of graph b.  pos[v*B+b] maps a node back to its position.
   float *Hin, *Hc, *Hv, *gc, *gl, *Pg, *Pm, *gxc, *gxl, *gh, *XnS;
   int* pos;
+  float *Whi, *Wlo, *xs_hi, *xs_lo;   // inference only: 3xTF32 operand splits (weights blob, scratch 6B x 512)
   // training only: input weights padded 27/23 -> 32 columns (16-byte rows, so these products and their
   // gradients are TMA-addressable), self-loop-masked features for the looper's weight gradient
   float *WihP[3], *dWihP[3], *XnSL;
@@ -56,6 +57,7 @@ struct DecWs {
   float *WihP[3], *dWihP[3], *XL, *xc;   // padded input weights / grads (comb, loop, root), masked features (7B,32), compact x rows
   // greedy only
   float *Xd, *Pn;
+  float *Whi, *Wlo, *xs_hi, *xs_lo;   // 3xTF32 operand splits (weights blob, activation scratch B x 1024)
   // backward temporaries
   float *dHd, *dPg, *dPm, *dQ, *dgb, *dHi, *dHc, *dHin, *dHrun, *dHc0, *dgx, *dgxs, *dgh, *dE1, *dA1, *dA2, *dES1,
       *dHinit, *dz;
@@ -95,7 +97,7 @@ int encode_fwd(dx_stream_t st, const float* weights, const Batch& bt, float* mu,
 int elbo_step(dx_stream_t st, const float* weights, const Batch& bt, const float* eps, LossW lw, float* loss5,
               float* mu_out, float* std_out, float* grads, void* ws, size_t ws_bytes, int precision);
 int decode_greedy(dx_stream_t st, const float* weights, int64_t B, const float* z, float* Xg, float* Pg, uint64_t* adj,
-                  float* margins, void* ws, size_t ws_bytes);
+                  float* margins, void* ws, size_t ws_bytes, int precision);
 
 // batcher / data-format kernels (dx_data.cu)
 int batch_build_host(int64_t B, const int32_t* edge_ptr, const int8_t* src, const int8_t* dst, uint64_t* adj,

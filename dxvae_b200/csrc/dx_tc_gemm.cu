@@ -30,10 +30,13 @@ namespace {
 constexpr int TBM = 128, TBK = 32;           // 32 fp32 = one 128-byte swizzle row
 constexpr int A_BYTES = TBM * TBK * 4;       // 16 KB
 
-template <int BN> struct TcCfg {
+// X3: error-compensated "3xTF32" mode for FP32-accurate results on the tensor cores: every operand
+// comes as an exact pair (hi = top 11 mantissa bits, lo = remainder) and each k-step issues
+// hi*hi + hi*lo + lo*hi into the same FP32 accumulator (the dropped lo*lo term is ~2^-22 relative).
+template <int BN, bool X3 = false> struct TcCfg {
   static constexpr int B_BYTES = BN * TBK * 4;
-  static constexpr int STAGE = A_BYTES + B_BYTES;
-  static constexpr int STAGES = (BN == 256) ? 4 : (BN == 128 ? 6 : 8);
+  static constexpr int STAGE = (A_BYTES + B_BYTES) * (X3 ? 2 : 1);
+  static constexpr int STAGES = X3 ? (BN == 128 ? 3 : 4) : ((BN == 256) ? 4 : (BN == 128 ? 6 : 8));
   static constexpr int SMEM = STAGES * STAGE + 1024 /*align*/ + 4 * 2 * 4096 /*store staging*/ + 256 /*barriers*/;
 };
 
@@ -116,15 +119,19 @@ __device__ __forceinline__ float tc_act(float v, int act) {
   return v;
 }
 
-template <int BN, bool A_MN, bool B_MN>
+template <int BN, bool A_MN, bool B_MN, bool X3 = false>
 __global__ void __launch_bounds__(192, 1) k_tc_gemm(const __grid_constant__ CUtensorMap tmA,
                                                     const __grid_constant__ CUtensorMap tmB,
                                                     const __grid_constant__ CUtensorMap tmC,
-                                                    const __grid_constant__ CUtensorMap tmAdd, const TcParams p) {
+                                                    const __grid_constant__ CUtensorMap tmAdd,
+                                                    const __grid_constant__ CUtensorMap tmAlo,
+                                                    const __grid_constant__ CUtensorMap tmBlo, const TcParams p) {
+  static_assert(!X3 || (!A_MN && !B_MN), "3xTF32 is only built for the forward (K-major) form");
   // Persistent: CTA b processes tiles b, b+grid, ... ; two accumulators in TMEM so the epilogue of
   // tile i overlaps the main loop of tile i+1.
-  using Cfg = TcCfg<BN>;
+  using Cfg = TcCfg<BN, X3>;
   constexpr int S = Cfg::STAGES;
+  constexpr int HALF = A_BYTES + Cfg::B_BYTES;                     // X3: [A_hi|B_hi] then [A_lo|B_lo]
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;       // swizzle atoms need 1024-byte alignment
   const uint32_t stg_base = base + S * Cfg::STAGE;                    // 4 warps x 2 x 4 KB store staging
@@ -187,6 +194,10 @@ __global__ void __launch_bounds__(192, 1) k_tc_gemm(const __grid_constant__ CUte
           else
 #pragma unroll
             for (int g = 0; g < BN / 32; ++g) tma_load_2d(&tmB, sb + g * 4096, full_bar(s), n0 + g * 32, k0);
+          if (X3) {
+            tma_load_2d(&tmAlo, sa + HALF, full_bar(s), k0, m0);
+            tma_load_2d(&tmBlo, sb + HALF, full_bar(s), k0, n0);
+          }
         }
       }
     }
@@ -215,6 +226,11 @@ __global__ void __launch_bounds__(192, 1) k_tc_gemm(const __grid_constant__ CUte
             const uint64_t ad = A_MN ? umma_desc(sa + k * 1024, 4096, 512, 1) : umma_desc(sa + k * 32, 16, 1024, 2);
             const uint64_t bd = B_MN ? umma_desc(sb + k * 1024, 4096, 512, 1) : umma_desc(sb + k * 32, 16, 1024, 2);
             umma_tf32(tacc, ad, bd, idesc, (kb | k) != 0 ? 1u : 0u);
+            if (X3) {
+              const uint64_t adl = umma_desc(sa + HALF + k * 32, 16, 1024, 2), bdl = umma_desc(sb + HALF + k * 32, 16, 1024, 2);
+              umma_tf32(tacc, ad, bdl, idesc, 1u);                 // hi * lo
+              umma_tf32(tacc, adl, bd, idesc, 1u);                 // lo * hi
+            }
           }
           umma_commit(empty_bar(s));                               // frees the smem stage when these MMAs retire
         }
@@ -429,15 +445,22 @@ bool make_map(CUtensorMap* m, const float* ptr, int64_t rows, int64_t cols, int6
              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-template <int BN>
-bool launch_tc(dx_stream_t s, const GemmP& g) {
-  using Cfg = TcCfg<BN>;
-  CUtensorMap ta, tb;
+template <int BN, bool X3 = false>
+bool launch_tc(dx_stream_t s, const GemmP& g, const float* A_lo = nullptr, const float* B_lo = nullptr) {
+  using Cfg = TcCfg<BN, X3>;
+  CUtensorMap ta, tb, talo, tblo;
   // K-major: memory [MN rows][reduction cols]; MN-major: memory [reduction rows][MN cols]
+  if (X3) {   // exact hi/lo pairs: plain FP32 maps (no rounding on load)
+    if (!make_map(&ta, g.A, g.M, g.K, g.lda, TBK, TBM, false, true) || !make_map(&talo, A_lo, g.M, g.K, g.lda, TBK, TBM, false, true) ||
+        !make_map(&tb, g.B, g.N, g.K, g.ldb, TBK, BN, false, true) || !make_map(&tblo, B_lo, g.N, g.K, g.ldb, TBK, BN, false, true))
+      return false;
+  } else {
   if (g.a_kc) { if (!make_map(&ta, g.A, g.M, g.K, g.lda, TBK, TBM, false)) return false; }
   else        { if (!make_map(&ta, g.A, g.K, g.M, g.lda, 32, TBK, true)) return false; }
   if (g.b_kc) { if (!make_map(&tb, g.B, g.N, g.K, g.ldb, TBK, BN, false)) return false; }
   else        { if (!make_map(&tb, g.B, g.K, g.N, g.ldb, 32, TBK, true)) return false; }
+  talo = ta; tblo = tb;
+  }
   // C through TMA when it is a plain strided matrix (no row scatter) with 16-byte aligned rows
   const bool tma_store = !g.c_idx && ((reinterpret_cast<uintptr_t>(g.C) & 15) == 0) && (g.ldc % 4 == 0) &&
                          !getenv("DX_TC_NO_TMA_STORE");
@@ -469,16 +492,19 @@ bool launch_tc(dx_stream_t s, const GemmP& g) {
   if (!num_sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev); }
   const int total_tiles = gm * gn * splits;
   dim3 grid(total_tiles < num_sms ? total_tiles : num_sms);
-  static bool attr_set = false;   // per BN instantiation; all four operand-major variants share the footprint
+  static bool attr_set = false;   // per (BN, X3) instantiation; the operand-major variants share the footprint
   if (!attr_set) {
-    cudaFuncSetAttribute(k_tc_gemm<BN, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM);
-    cudaFuncSetAttribute(k_tc_gemm<BN, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM);
-    cudaFuncSetAttribute(k_tc_gemm<BN, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM);
-    cudaFuncSetAttribute(k_tc_gemm<BN, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM);
+    cudaFuncSetAttribute(k_tc_gemm<BN, false, false, X3>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM);
+    if (!X3) {
+      cudaFuncSetAttribute(k_tc_gemm<BN, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM);
+      cudaFuncSetAttribute(k_tc_gemm<BN, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM);
+      cudaFuncSetAttribute(k_tc_gemm<BN, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM);
+    }
     attr_set = true;
   }
-  auto run = [&](auto kern) { kern<<<grid, 192, Cfg::SMEM, s>>>(ta, tb, tc, tadd, p); };
-  if (g.a_kc && g.b_kc) run(k_tc_gemm<BN, false, false>);
+  auto run = [&](auto kern) { kern<<<grid, 192, Cfg::SMEM, s>>>(ta, tb, tc, tadd, talo, tblo, p); };
+  if (X3) run(k_tc_gemm<BN, false, false, X3>);
+  else if (g.a_kc && g.b_kc) run(k_tc_gemm<BN, false, false>);
   else if (g.a_kc && !g.b_kc) run(k_tc_gemm<BN, false, true>);
   else if (!g.a_kc && !g.b_kc) run(k_tc_gemm<BN, true, true>);
   else run(k_tc_gemm<BN, true, false>);
@@ -517,9 +543,18 @@ bool tc_gemm(dx_stream_t s, const GemmP& g, int* tile_n) {
   return bn == 256 ? launch_tc<256>(s, g) : (bn == 128 ? launch_tc<128>(s, g) : launch_tc<64>(s, g));
 }
 
+// FP32-accurate forward product on the tensor cores (3xTF32).  A_hi/A_lo and B_hi/B_lo are exact splits
+// of the operands (same shapes / pitches as g.A / g.B, which must point at the hi parts).
+bool tc_gemm_x3(dx_stream_t s, const GemmP& g, const float* A_lo, const float* B_lo) {
+  if (g.a_idx || g.b_idx || !g.a_kc || !g.b_kc || g.accum == ACC_ATOMIC) return false;
+  if (!al16(g.A) || !al16(g.B) || !al16(A_lo) || !al16(B_lo) || (g.lda % 4) || (g.ldb % 4)) return false;
+  return g.N >= 96 ? launch_tc<128, true>(s, g, A_lo, B_lo) : launch_tc<64, true>(s, g, A_lo, B_lo);
+}
+
 }  // namespace dx
 #else
 namespace dx {
 bool tc_gemm(dx_stream_t, const GemmP&, int*) { return false; }
+bool tc_gemm_x3(dx_stream_t, const GemmP&, const float*, const float*) { return false; }
 }  // namespace dx
 #endif

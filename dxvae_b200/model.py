@@ -76,6 +76,8 @@ class DXVAE(nn.Module):
         # inference encode: "fp32" (default, reference-tolerance latents) or "tf32" (tensor cores,
         # latents within the looser TF32 bound of tests/test_gpu_tf32.py); greedy decode is always fp32
         self.encode_precision = "fp32"
+        # greedy decode: "fp32" (FFMA) or "3xtf32" (error-compensated tensor-core products, FP32-accurate)
+        self.decode_precision = "fp32"
         # skip teacher-forced re-propagates that add no edge (exact; see dxvae_batch_steps)
         self.compact_steps = True
         if checkpoint is not None:
@@ -230,7 +232,8 @@ class DXVAE(nn.Module):
             _lib.check(L.dxvae_encode_fwd(self._flat.data_ptr(), d.B, d.Xn.data_ptr(), d.adj.data_ptr(), d.n_levels,
                                           d.level_ptr.ctypes.data, d.level_rows.data_ptr(), mu[lo:hi].data_ptr(),
                                           sd[lo:hi].data_ptr(), ws.data_ptr(), ws.numel(), 0,
-                                          _abi.PREC_TF32 if self.encode_precision == "tf32" else _abi.PREC_FP32, _stream()),
+                                          {"fp32": _abi.PREC_FP32, "tf32": _abi.PREC_TF32, "3xtf32": _abi.PREC_3XTF32}[self.encode_precision],
+                                          _stream()),
                        "dxvae_encode_fwd")
         return Normal(mu, sd, validate_args=False)
 
@@ -264,7 +267,9 @@ class DXVAE(nn.Module):
             ws = self._workspace(_abi.OP_DECODE, hi - lo)
             _lib.check(L.dxvae_decode_greedy(self._flat.data_ptr(), hi - lo, z[lo:hi].data_ptr(), Xg[lo:hi].data_ptr(),
                                              Pg[lo:hi].data_ptr(), adj[lo:hi].data_ptr(), mg[lo:hi].data_ptr(),
-                                             ws.data_ptr(), ws.numel(), _stream()), "dxvae_decode_greedy")
+                                             ws.data_ptr(), ws.numel(),
+                                             {"fp32": _abi.PREC_FP32, "3xtf32": _abi.PREC_3XTF32}[self.decode_precision],
+                                             _stream()), "dxvae_decode_greedy")
         self.last_margins = mg
         return DXGraphBatch(Xg, Pg, adj)
 

@@ -121,8 +121,12 @@ int dxvae_pack_syx(int64_t B, const float* Pg, uint8_t* voices, void* stream);
  *                  greedy decode, whose discrete outputs must match the reference exactly).
  * DXVAE_PREC_TF32: eligible products (rows >= 128, N >= 64, K >= 32, no row gather) run on the
  *                  tcgen05 tensor cores with TF32 inputs / FP32 accumulation; looser, stated
- *                  tolerance. */
-enum { DXVAE_PREC_FP32 = 0, DXVAE_PREC_TF32 = 1 };
+ *                  tolerance.
+ * DXVAE_PREC_3XTF32: inference only (encode_fwd keep=0, decode_greedy).  FP32-accurate products on the
+ *                  tensor cores: operands are split exactly into tf32 hi + lo parts and every k-step
+ *                  issues hi*hi + hi*lo + lo*hi into the FP32 accumulator (error ~2^-21 per product,
+ *                  the size of FP32 summation-order noise), so discrete decode outputs keep matching. */
+enum { DXVAE_PREC_FP32 = 0, DXVAE_PREC_TF32 = 1, DXVAE_PREC_3XTF32 = 2 };
 
 /* ---- workspace sizes ------------------------------------------------------------ */
 enum { DXVAE_OP_ENCODE = 0, DXVAE_OP_DECODE = 1, DXVAE_OP_TRAIN = 2, DXVAE_OP_SCHEDULE = 3,
@@ -146,7 +150,7 @@ int dxvae_reparameterize(int64_t n, const float* mu, const float* std_, const fl
  * margins (B) = min |logit| over the 48 edge decisions of each graph, for tie-aware
  * parity checks. */
 int dxvae_decode_greedy(const float* weights, int64_t B, const float* z, float* Xg, float* Pg, uint64_t* adj,
-                        float* margins, void* workspace, size_t workspace_bytes, void* stream);
+                        float* margins, void* workspace, size_t workspace_bytes, int precision, void* stream);
 
 /* ---- teacher-forced ELBO (model.py:270-367) + backward (model.py:385) ------------ *
  * One call = encode_fwd + loss_fwd (+ backward of both when grads != NULL).

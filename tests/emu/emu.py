@@ -116,5 +116,5 @@ class Emu:
         Xg = np.zeros((B, 7, 27), np.float32); Pg = np.zeros((B, 7, 21), np.float32)
         adj = np.zeros(B, np.uint64); mg = np.zeros(B, np.float32)
         _abi.check(L, L.dxvae_decode_greedy(ptr(self.blob), B, ptr(z), ptr(Xg), ptr(Pg), ptr(adj), ptr(mg), ptr(ws),
-                                            ws.nbytes, None), "decode")
+                                            ws.nbytes, 0, None), "decode")
         return Xg, Pg, adj, mg

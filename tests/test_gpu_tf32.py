@@ -108,3 +108,58 @@ def test_tf32_inference_encode_within_stated_tolerance(lib):
     err = max((q.loc.cpu() - mu_o).abs().max().item(), (q.scale.cpu() - sd_o).abs().max().item())
     print("tf32 encode latent err", err)
     assert err <= 2e-3
+
+
+# --------------------------------------------------------------------------- 3xTF32 (FP32-accurate tensor-core inference)
+def test_3xtf32_encode_within_fp32_tolerance(lib):
+    """Error-compensated products: latents must meet the FP32 tolerance (1e-5), not the TF32 one."""
+    from dxvae_b200 import DXVAE
+    from dxvae_b200.dxdata import DXGraph
+    idx = list(range(0, 1024, 4))
+    X, P, E, A = util.dataset_graphs(idx)
+    o = O.make_weights(0, 3.0)
+    m = DXVAE(); m.load_state_dict(o.state_dict()); m.verbose = False
+    m.encode_precision = "3xtf32"
+    with torch.no_grad():
+        q = m.encode([DXGraph(X[i], P[i], *E[i]) for i in range(len(idx))])
+        mu_o, sd_o = o.encode(X, A)
+    err = max((q.loc.cpu() - mu_o).abs().max().item(), (q.scale.cpu() - sd_o).abs().max().item())
+    print("3xtf32 encode latent err", err)
+    assert err <= 1e-5
+
+
+def test_3xtf32_decode_matches_reference_golden(lib):
+    import os
+    from dxvae_b200 import DXVAE
+    golden = np.load(os.path.join(util.GOLDEN, "model_golden.npz"))
+    o = O.make_weights(0, 3.0)
+    m = DXVAE(); m.load_state_dict(o.state_dict()); m.verbose = False
+    m.decode_precision = "3xtf32"
+    for zt in ("mu", "prior"):
+        z = torch.from_numpy(golden["stress_dec_%s_z" % zt])
+        z = torch.cat([z, z, z], 0)                      # 192 rows: the tensor-core path needs >= 1e6 MACs per product
+        gb = m.decode(z)
+        ok = np.tile(golden["stress_dec_%s_minmargin" % zt] > 2e-5, 3)
+        A = util.adj_from_masks(gb.adj.cpu().numpy().view(np.uint64))
+        assert np.array_equal(A[ok], np.tile(golden["stress_dec_%s_adj" % zt], (3, 1, 1))[ok])
+        assert np.array_equal(gb.params.cpu().numpy().astype(np.int32)[ok],
+                              np.tile(golden["stress_dec_%s_params" % zt].astype(np.int32), (3, 1, 1))[ok])
+        assert np.abs(gb.X.cpu().numpy() - np.tile(golden["stress_dec_%s_X" % zt], (3, 1, 1)))[ok].max() <= 1e-6
+
+
+def test_3xtf32_decode_equals_fp32_decode_on_large_batch(lib):
+    """Both paths are FP32-accurate evaluations: they may only disagree on graphs with a decision on the
+    threshold (margin below 1e-4)."""
+    from dxvae_b200 import DXVAE
+    o = O.make_weights(0, 3.0)
+    m = DXVAE(); m.load_state_dict(o.state_dict()); m.verbose = False
+    g = torch.Generator().manual_seed(5)
+    z = torch.randn(20000, 128, generator=g)
+    a = m.decode(z); mg = m.last_margins.cpu().numpy()
+    m.decode_precision = "3xtf32"
+    b = m.decode(z)
+    diff = ((a.adj != b.adj) | (a.params != b.params).flatten(1).any(1)).cpu().numpy()
+    print("3xtf32 vs fp32 decode: %d / %d graphs differ; max margin among them %.2e" %
+          (diff.sum(), len(diff), mg[diff].max() if diff.any() else 0.0))
+    assert diff.sum() <= 0.02 * len(diff)
+    assert not diff.any() or mg[diff].max() < 1e-4
