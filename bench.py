@@ -268,11 +268,20 @@ def run_ours(args):
             model.encode(gb); torch.cuda.synchronize()
             t0 = time.perf_counter(); model.encode(gb); torch.cuda.synchronize()
             extra["encode_tf32_patches_per_s"] = ne / (time.perf_counter() - t0)
+            model.encode_precision = "3xtf32"
+            model.encode(gb); torch.cuda.synchronize()
+            t0 = time.perf_counter(); model.encode(gb); torch.cuda.synchronize()
+            extra["encode_3xtf32_patches_per_s"] = ne / (time.perf_counter() - t0)
             model.encode_precision = "fp32"
             z = torch.randn(16384, 128, device="cuda")
             model.decode(z); torch.cuda.synchronize()
             t0 = time.perf_counter(); model.decode(z); torch.cuda.synchronize()
             extra["decode_patches_per_s"] = 16384 / (time.perf_counter() - t0)
+            model.decode_precision = "3xtf32"
+            model.decode(z); torch.cuda.synchronize()
+            t0 = time.perf_counter(); model.decode(z); torch.cuda.synchronize()
+            extra["decode_3xtf32_patches_per_s"] = 16384 / (time.perf_counter() - t0)
+            model.decode_precision = "fp32"
         idx = list(range(128))
         for _ in range(3):
             tr.step(pool, idx)
