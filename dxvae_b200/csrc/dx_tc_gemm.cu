@@ -6,10 +6,11 @@
 //   C[M,N] (op)= act( sum_r Aop(i,r) Bop(r,j) + bias[j] + add[i,j] )      (same contract as dx_gemm.h)
 //
 // Persistent CTAs (one per SM) walk the 128 x BN output tiles (BN = 256 / 128 / 64); two TMEM
-// accumulators let the epilogue of one tile overlap the main loop of the next.  192 threads:
+// accumulators let the epilogue of one tile overlap the main loop of the next.  320 threads:
 //   warp 0   : TMA producer  (cp.async.bulk.tensor, 128B swizzle, mbarrier complete_tx)
 //   warp 1   : TMEM allocation + single-thread tcgen05.mma issue, tcgen05.commit -> mbarriers
-//   warps 2-5: epilogue (tcgen05.ld 32x32b -> registers -> bias/act -> global, one row per thread)
+//   warps 2-9: epilogue (tcgen05.ld 32x32b -> registers -> bias/add/act -> swizzled smem slab -> TMA bulk
+//              store / reduce-add), two warps per TMEM lane quadrant, half of the columns each
 // Operands stay fp32 in HBM; the tensor map's TFLOAT32 type rounds on load.  Both operand
 // majors are native (no physical transposes): K-major tiles are one 2-D box of
 // [rows x 32 floats]; MN-major tiles (dgrad's W, wgrad's dy and x) are 32x32 boxes laid out as
@@ -37,7 +38,7 @@ template <int BN, bool X3 = false> struct TcCfg {
   static constexpr int B_BYTES = BN * TBK * 4;
   static constexpr int STAGE = (A_BYTES + B_BYTES) * (X3 ? 2 : 1);
   static constexpr int STAGES = X3 ? (BN == 128 ? 3 : 4) : ((BN == 256) ? 4 : (BN == 128 ? 6 : 8));
-  static constexpr int SMEM = STAGES * STAGE + 1024 /*align*/ + 4 * 2 * 4096 /*store staging*/ + 256 /*barriers*/;
+  static constexpr int SMEM = STAGES * STAGE + 1024 /*align*/ + 8 * 4096 /*store staging*/ + 256 /*barriers*/;
 };
 
 struct TcParams {
@@ -120,7 +121,7 @@ __device__ __forceinline__ float tc_act(float v, int act) {
 }
 
 template <int BN, bool A_MN, bool B_MN, bool X3 = false>
-__global__ void __launch_bounds__(192, 1) k_tc_gemm(const __grid_constant__ CUtensorMap tmA,
+__global__ void __launch_bounds__(320, 1) k_tc_gemm(const __grid_constant__ CUtensorMap tmA,
                                                     const __grid_constant__ CUtensorMap tmB,
                                                     const __grid_constant__ CUtensorMap tmC,
                                                     const __grid_constant__ CUtensorMap tmAdd,
@@ -135,13 +136,12 @@ __global__ void __launch_bounds__(192, 1) k_tc_gemm(const __grid_constant__ CUte
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;       // swizzle atoms need 1024-byte alignment
   const uint32_t stg_base = base + S * Cfg::STAGE;                    // 4 warps x 2 x 4 KB store staging
-  const uint32_t bars = stg_base + 4 * 2 * 4096;                      // full[S], empty[S], tfull[2], tempty[2], slot
+  const uint32_t bars = stg_base + 8 * 4096;                      // full[S], empty[S], tfull[2], tempty[2], slot
   auto full_bar = [&](int s) { return bars + 8u * s; };
   auto empty_bar = [&](int s) { return bars + 8u * (S + s); };
   auto tfull_bar = [&](int a) { return bars + 8u * (2 * S + a); };
   auto tempty_bar = [&](int a) { return bars + 8u * (2 * S + 2 + a); };
   const uint32_t tmem_slot = bars + 8u * (2 * S + 4);
-  auto add_bar = [&](int w, int sl) { return bars + 8u * (2 * S + 5 + 2 * w + sl); };   // per epilogue warp, per slab
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int gm = (p.M + TBM - 1) / TBM, gn = (p.N + BN - 1) / BN;
@@ -152,8 +152,8 @@ __global__ void __launch_bounds__(192, 1) k_tc_gemm(const __grid_constant__ CUte
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < S; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 4); }
-    for (int w = 0; w < 4; ++w) { mbar_init(add_bar(w, 0), 1); mbar_init(add_bar(w, 1), 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 8); }
+    for (int w = 0; w < 8; ++w) mbar_init(bars + 8u * (2 * S + 5 + w), 1);   // per-warp `add` tile barriers
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -237,107 +237,94 @@ __global__ void __launch_bounds__(192, 1) k_tc_gemm(const __grid_constant__ CUte
         umma_commit(tfull_bar(as));                                // accumulator complete
       }
     }
-  } else {                                                         // ---- epilogue: warps 2..5
-    const int q = warp & 3;                                        // TMEM lane quadrant this warp may read
-    const uint32_t my_stg = stg_base + (uint32_t)(warp - 2) * 8192u;
-    float* stg = reinterpret_cast<float*>(smem_raw + (my_stg - smem_u32(smem_raw)));
+  } else {                                                         // ---- epilogue: warps 2..9
+    // Two warps per TMEM lane quadrant (a warp may only read lanes 32*(warp%4)..+31), each taking
+    // half of the tile's columns, so draining an accumulator costs about half a main loop.
+    const int ew = warp - 2;                                       // 0..7
+    const int q = warp & 3;                                        // TMEM lane quadrant
+    const int half = ew >> 2;                                      // which half of the BN columns
+    constexpr int HC = BN / 2;
+    const uint32_t slab = stg_base + (uint32_t)ew * 4096u;         // one 32x32 fp32 staging slab per warp
+    const uint32_t abar = bars + 8u * (2 * S + 5 + ew);            // `add` tile arrival barrier of this warp
     const bool vec = ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0) && (p.ldc % 4 == 0);
-    const int rsub = lane >> 3, cc = (lane & 7) * 4;
+    const int rsub = lane >> 3, cc4 = lane & 7;
     uint32_t lt = 0, nstore = 0;
     for (int t = blockIdx.x; t < total; t += gridDim.x, ++lt) {
       int m0, n0, kbeg, nkb; tile_coords(t, m0, n0, kbeg, nkb);
       const uint32_t as = lt & 1;
-      const int nch = (min(BN, p.N - n0) + 31) / 32;               // 32-column chunks of this tile that exist
-      // `add` tile prefetch: chunk i of this warp's 32 rows lands in the slab it will later be stored
-      // from.  Chunk 0 is requested before waiting for the accumulator, chunk i+1 while chunk i is
-      // being processed, so the L2 latency stays off the critical path.
-      auto issue_add = [&](int ci, uint32_t n) {
-        const uint32_t sl = n & 1;
-        mbar_expect_tx(add_bar(warp - 2, sl), 4096);
-        tma_load_2d(&tmAdd, my_stg + sl * 4096u, add_bar(warp - 2, sl), n0 + ci * 32, m0 + q * 32);
-      };
-      if (p.add_tma && lane == 0) {
-        asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");   // the store that last used this slab is done with it
-        issue_add(0, nstore);
-      }
       mbar_wait(tfull_bar(as), (lt >> 1) & 1);
       if (trace && threadIdx.x == 64 && lt < 8) p.dbg[208 + 2 * lt] = clock64();
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const uint32_t tacc = tmem_base + as * BN + ((uint32_t)(q * 32) << 16);
-      if (p.tma_store) {
-        // Each thread owns one accumulator row.  Rows go through a 128B-swizzled 32x32 staging slab
-        // (conflict-free 128-bit writes) and leave as one 4 KB TMA bulk store (plain, or f32
-        // reduce-add for accumulate / split-K modes): bulk stores are not limited by the few
-        // epilogue warps' outstanding-store budget, unlike STG (measured 12x faster here).
-        const int gi = m0 + q * 32 + lane;
-        const bool row_ok = gi < p.M;
+      const int gi = m0 + q * 32 + lane;                           // the accumulator row this thread owns
+      const bool row_ok = gi < p.M;
 #pragma unroll 1
-        for (int c = 0; c < BN; c += 32) {
-          float v[32];
-          tmem_ld32(tacc + (uint32_t)c, v);
-          const int gj = n0 + c;
-          if (gj >= p.N) continue;                                 // warp-uniform
-          const bool full = gj + 32 <= p.N;                        // warp-uniform: whole chunk in bounds
-          if (p.add_tma) {
-            const int ci = c >> 5;
-            if (lane == 0 && ci + 1 < nch) {
-              asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // slab of chunk ci+1 = slab of store ci-1
-              issue_add(ci + 1, nstore + 1);
-            }
-            mbar_wait(add_bar(warp - 2, nstore & 1), (nstore >> 1) & 1);
-            const uint32_t sl = my_stg + (nstore & 1) * 4096u + (uint32_t)(lane * 128);
+      for (int c = half * HC; c < (half + 1) * HC; c += 32) {
+        float v[32];
+        tmem_ld32(tacc + (uint32_t)c, v);
+        const int gj = n0 + c;
+        if (gj >= p.N) continue;                                   // warp-uniform
+        const bool full = gj + 32 <= p.N;                          // warp-uniform: whole chunk in bounds
+        // the previous bulk store of this warp must have finished reading the slab
+        if (nstore > 0) { if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); __syncwarp(); }
+        if (p.add_tma) {
+          // `add` tile (32 rows x 32 cols of this warp) fetched by TMA into the slab it is later stored from
+          if (lane == 0) { mbar_expect_tx(abar, 4096); tma_load_2d(&tmAdd, slab, abar, gj, m0 + q * 32); }
+          mbar_wait(abar, nstore & 1);
+          const uint32_t sl = slab + (uint32_t)(lane * 128);
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              float a0, a1, a2, a3;
-              asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(a0), "=f"(a1), "=f"(a2), "=f"(a3)
-                           : "r"(sl + (uint32_t)(((j ^ (lane & 7)) << 4))) : "memory");
-              v[4 * j] += a0; v[4 * j + 1] += a1; v[4 * j + 2] += a2; v[4 * j + 3] += a3;
-            }
-          } else if (p.add) {
-            if (row_ok) {
-              const float* ar = p.add + (int64_t)gi * p.ldadd + gj;
-              if (full) {
-#pragma unroll
-                for (int j = 0; j < 32; j += 4) {
-                  const float4 a4 = __ldg(reinterpret_cast<const float4*>(ar + j));
-                  v[j] += a4.x; v[j + 1] += a4.y; v[j + 2] += a4.z; v[j + 3] += a4.w;
-                }
-              } else {
-#pragma unroll
-                for (int j = 0; j < 32; ++j) if (gj + j < p.N) v[j] += __ldg(ar + j);
-              }
-            }
+          for (int j = 0; j < 8; ++j) {
+            float a0, a1, a2, a3;
+            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(a0), "=f"(a1), "=f"(a2), "=f"(a3)
+                         : "r"(sl + (uint32_t)(((j ^ (lane & 7)) << 4))) : "memory");
+            v[4 * j] += a0; v[4 * j + 1] += a1; v[4 * j + 2] += a2; v[4 * j + 3] += a3;
           }
-          if (p.bias) {
+        } else if (p.add) {
+          if (row_ok) {
+            const float* ar = p.add + (int64_t)gi * p.ldadd + gj;
             if (full) {
 #pragma unroll
               for (int j = 0; j < 32; j += 4) {
-                const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + gj + j));   // same address in every lane
-                v[j] += b4.x; v[j + 1] += b4.y; v[j + 2] += b4.z; v[j + 3] += b4.w;
+                const float4 a4 = __ldg(reinterpret_cast<const float4*>(ar + j));
+                v[j] += a4.x; v[j + 1] += a4.y; v[j + 2] += a4.z; v[j + 3] += a4.w;
               }
             } else {
 #pragma unroll
-              for (int j = 0; j < 32; ++j) if (gj + j < p.N) v[j] += __ldg(p.bias + gj + j);
+              for (int j = 0; j < 32; ++j) if (gj + j < p.N) v[j] += __ldg(ar + j);
             }
           }
-          if (p.act == ACT_RELU) {
+        }
+        if (p.bias) {
+          if (full) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
-          } else if (p.act != ACT_NONE) {
+            for (int j = 0; j < 32; j += 4) {
+              const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + gj + j));   // same address in every lane
+              v[j] += b4.x; v[j + 1] += b4.y; v[j + 2] += b4.z; v[j + 3] += b4.w;
+            }
+          } else {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = tc_act(v[j], p.act);
+            for (int j = 0; j < 32; ++j) if (gj + j < p.N) v[j] += __ldg(p.bias + gj + j);
           }
-          const uint32_t slab = my_stg + (nstore & 1) * 4096u;
-          if (nstore >= 2 && !p.add_tma) {                         // the store that last used this slab has read it
-            if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
-            __syncwarp();
-          }
+        }
+        if (p.act == ACT_RELU) {
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const uint32_t dst = slab + (uint32_t)(lane * 128) + (uint32_t)(((j ^ (lane & 7)) << 4));
-            asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "f"(v[4 * j]), "f"(v[4 * j + 1]),
-                         "f"(v[4 * j + 2]), "f"(v[4 * j + 3]) : "memory");
-          }
+          for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+        } else if (p.act != ACT_NONE) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = tc_act(v[j], p.act);
+        }
+        // Each thread owns one accumulator row; rows go through the 128B-swizzled slab (conflict-free
+        // 128-bit accesses both ways).
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const uint32_t dst = slab + (uint32_t)(lane * 128) + (uint32_t)(((j ^ (lane & 7)) << 4));
+          asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "f"(v[4 * j]), "f"(v[4 * j + 1]),
+                       "f"(v[4 * j + 2]), "f"(v[4 * j + 3]) : "memory");
+        }
+        if (p.tma_store) {
+          // ... and leave as one 4 KB TMA bulk store (plain, or f32 reduce-add for accumulate / split-K
+          // modes): bulk stores are not limited by the epilogue warps' outstanding-store budget, unlike
+          // STG (measured 12x faster here).
           asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
           __syncwarp();
           if (lane == 0) {
@@ -346,50 +333,32 @@ __global__ void __launch_bounds__(192, 1) k_tc_gemm(const __grid_constant__ CUte
             asm volatile("cp.async.bulk.commit_group;" ::: "memory");
           }
           ++nstore;
-        }
-      } else {
-        // Fallback (row scatter through c_idx, or rows that are not 16-byte aligned): per-warp
-        // 32x32 staging tile with pitch 36, then coalesced STG / RED.
-#pragma unroll 1
-        for (int c = 0; c < BN; c += 32) {
-          float v[32];
-          tmem_ld32(tacc + (uint32_t)c, v);
-          if (n0 + c >= p.N) continue;                             // warp-uniform
-#pragma unroll
-          for (int j = 0; j < 32; j += 4)
-            *reinterpret_cast<float4*>(stg + lane * 36 + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+        } else {
+          // Fallback (row scatter through c_idx, or rows that are not 16-byte aligned): read the slab back
+          // row-wise and issue coalesced STG / RED (one warp instruction = 4 rows x 128 contiguous bytes).
           __syncwarp();
-          const int gj = n0 + c + cc;
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
             const int rr = i * 4 + rsub;
-            const int gi = m0 + q * 32 + rr;
-            if (gi < p.M && gj < p.N) {
-              const float4 x = *reinterpret_cast<const float4*>(stg + rr * 36 + cc);
-              float o[4] = {x.x, x.y, x.z, x.w};
-              const int64_t crow = p.c_idx ? p.c_idx[gi] : gi;
-              float* dst = p.C + crow * p.ldc + gj;
-#pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                if (gj + e < p.N) {
-                  float tt = o[e];
-                  if (p.bias) tt += __ldg(p.bias + gj + e);
-                  if (p.add) tt += __ldg(p.add + (int64_t)gi * p.ldadd + gj + e);
-                  o[e] = tc_act(tt, p.act);
-                }
-              }
+            const int gr = m0 + q * 32 + rr, gc = gj + cc4 * 4;
+            float o[4];
+            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(o[0]), "=f"(o[1]), "=f"(o[2]), "=f"(o[3])
+                         : "r"(slab + (uint32_t)(rr * 128) + (uint32_t)(((cc4 ^ (rr & 7)) << 4))) : "memory");
+            if (gr < p.M && gc < p.N) {
+              const int64_t crow = p.c_idx ? p.c_idx[gr] : gr;
+              float* dst = p.C + crow * p.ldc + gc;
               if (p.accum == ACC_ATOMIC) {
 #pragma unroll
                 for (int e = 0; e < 4; ++e)
-                  if (gj + e < p.N) atomicAdd(dst + e, o[e]);
-              } else if (vec && gj + 3 < p.N) {
+                  if (gc + e < p.N) atomicAdd(dst + e, o[e]);
+              } else if (vec && gc + 3 < p.N) {
                 float4 w4 = make_float4(o[0], o[1], o[2], o[3]);
                 if (p.accum == ACC_ADD) { const float4 old = *reinterpret_cast<float4*>(dst); w4.x += old.x; w4.y += old.y; w4.z += old.z; w4.w += old.w; }
                 *reinterpret_cast<float4*>(dst) = w4;
               } else {
 #pragma unroll
                 for (int e = 0; e < 4; ++e)
-                  if (gj + e < p.N) { if (p.accum == ACC_ADD) dst[e] += o[e]; else dst[e] = o[e]; }
+                  if (gc + e < p.N) { if (p.accum == ACC_ADD) dst[e] += o[e]; else dst[e] = o[e]; }
               }
             }
           }
@@ -502,7 +471,7 @@ bool launch_tc(dx_stream_t s, const GemmP& g, const float* A_lo = nullptr, const
     }
     attr_set = true;
   }
-  auto run = [&](auto kern) { kern<<<grid, 192, Cfg::SMEM, s>>>(ta, tb, tc, tadd, talo, tblo, p); };
+  auto run = [&](auto kern) { kern<<<grid, 320, Cfg::SMEM, s>>>(ta, tb, tc, tadd, talo, tblo, p); };
   if (X3) run(k_tc_gemm<BN, false, false, X3>);
   else if (g.a_kc && g.b_kc) run(k_tc_gemm<BN, false, false>);
   else if (g.a_kc && !g.b_kc) run(k_tc_gemm<BN, false, true>);
