@@ -120,6 +120,150 @@ __device__ __forceinline__ float tc_act(float v, int act) {
   return v;
 }
 
+// Epilogue of the persistent GEMM kernels (warps 2..9 of a CTA): drains the CTA's 128 accumulator lanes.
+template <int BN, class TileFn, class ArriveFn>
+__device__ __forceinline__ void tc_epilogue(const TcParams& p, const CUtensorMap* tmC, const CUtensorMap* tmAdd,
+                                            uint32_t tmem_base, uint32_t stg_base, uint32_t abar0, uint32_t tfull0,
+                                            int t_first, int t_stride, int total, TileFn tile_coords,
+                                            ArriveFn arrive_empty, bool trace) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // Two warps per TMEM lane quadrant (a warp may only read lanes 32*(warp%4)..+31), each taking
+  // half of the tile's columns, so draining an accumulator costs about half a main loop.
+  const int ew = warp - 2;                                       // 0..7
+  const int q = warp & 3;                                        // TMEM lane quadrant
+  const int half = ew >> 2;                                      // which half of the BN columns
+  constexpr int HC = BN / 2;
+  const uint32_t slab = stg_base + (uint32_t)ew * 4096u;         // one 32x32 fp32 staging slab per warp
+  const uint32_t abar = abar0 + 8u * ew;                         // `add` tile arrival barrier of this warp
+  const bool vec = ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0) && (p.ldc % 4 == 0);
+  const int rsub = lane >> 3, cc4 = lane & 7;
+  uint32_t lt = 0, nstore = 0;
+  for (int t = t_first; t < total; t += t_stride, ++lt) {
+    int m0, n0, kbeg, nkb; tile_coords(t, m0, n0, kbeg, nkb);
+    const uint32_t as = lt & 1;
+    mbar_wait(tfull0 + 8u * as, (lt >> 1) & 1);
+    if (trace && threadIdx.x == 64 && lt < 8) p.dbg[208 + 2 * lt] = clock64();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tacc = tmem_base + as * BN + ((uint32_t)(q * 32) << 16);
+    const int gi = m0 + q * 32 + lane;                           // the accumulator row this thread owns
+    const bool row_ok = gi < p.M;
+#pragma unroll 1
+    for (int c = half * HC; c < (half + 1) * HC; c += 32) {
+      float v[32];
+      tmem_ld32(tacc + (uint32_t)c, v);
+      const int gj = n0 + c;
+      if (gj >= p.N) continue;                                   // warp-uniform
+      const bool full = gj + 32 <= p.N;                          // warp-uniform: whole chunk in bounds
+      // the previous bulk store of this warp must have finished reading the slab
+      if (nstore > 0) { if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); __syncwarp(); }
+      if (p.add_tma) {
+        // `add` tile (32 rows x 32 cols of this warp) fetched by TMA into the slab it is later stored from
+        if (lane == 0) { mbar_expect_tx(abar, 4096); tma_load_2d(tmAdd, slab, abar, gj, m0 + q * 32); }
+        mbar_wait(abar, nstore & 1);
+        const uint32_t sl = slab + (uint32_t)(lane * 128);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          float a0, a1, a2, a3;
+          asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(a0), "=f"(a1), "=f"(a2), "=f"(a3)
+                       : "r"(sl + (uint32_t)(((j ^ (lane & 7)) << 4))) : "memory");
+          v[4 * j] += a0; v[4 * j + 1] += a1; v[4 * j + 2] += a2; v[4 * j + 3] += a3;
+        }
+      } else if (p.add) {
+        if (row_ok) {
+          const float* ar = p.add + (int64_t)gi * p.ldadd + gj;
+          if (full) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              const float4 a4 = __ldg(reinterpret_cast<const float4*>(ar + j));
+              v[j] += a4.x; v[j + 1] += a4.y; v[j + 2] += a4.z; v[j + 3] += a4.w;
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) if (gj + j < p.N) v[j] += __ldg(ar + j);
+          }
+        }
+      }
+      if (p.bias) {
+        if (full) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + gj + j));   // same address in every lane
+            v[j] += b4.x; v[j + 1] += b4.y; v[j + 2] += b4.z; v[j + 3] += b4.w;
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) if (gj + j < p.N) v[j] += __ldg(p.bias + gj + j);
+        }
+      }
+      if (p.act == ACT_RELU) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+      } else if (p.act != ACT_NONE) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = tc_act(v[j], p.act);
+      }
+      // Each thread owns one accumulator row; rows go through the 128B-swizzled slab (conflict-free
+      // 128-bit accesses both ways).
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const uint32_t dst = slab + (uint32_t)(lane * 128) + (uint32_t)(((j ^ (lane & 7)) << 4));
+        asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "f"(v[4 * j]), "f"(v[4 * j + 1]),
+                     "f"(v[4 * j + 2]), "f"(v[4 * j + 3]) : "memory");
+      }
+      if (p.tma_store) {
+        // ... and leave as one 4 KB TMA bulk store (plain, or f32 reduce-add for accumulate / split-K
+        // modes): bulk stores are not limited by the epilogue warps' outstanding-store budget, unlike
+        // STG (measured 12x faster here).
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) {
+          if (p.accum == ACC_STORE) tma_store_2d(tmC, slab, gj, m0 + q * 32);
+          else tma_reduce_add_2d(tmC, slab, gj, m0 + q * 32);
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
+        ++nstore;
+      } else {
+        // Fallback (row scatter through c_idx, or rows that are not 16-byte aligned): read the slab back
+        // row-wise and issue coalesced STG / RED (one warp instruction = 4 rows x 128 contiguous bytes).
+        __syncwarp();
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int rr = i * 4 + rsub;
+          const int gr = m0 + q * 32 + rr, gc = gj + cc4 * 4;
+          float o[4];
+          asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(o[0]), "=f"(o[1]), "=f"(o[2]), "=f"(o[3])
+                       : "r"(slab + (uint32_t)(rr * 128) + (uint32_t)(((cc4 ^ (rr & 7)) << 4))) : "memory");
+          if (gr < p.M && gc < p.N) {
+            const int64_t crow = p.c_idx ? p.c_idx[gr] : gr;
+            float* dst = p.C + crow * p.ldc + gc;
+            if (p.accum == ACC_ATOMIC) {
+#pragma unroll
+              for (int e = 0; e < 4; ++e)
+                if (gc + e < p.N) atomicAdd(dst + e, o[e]);
+            } else if (vec && gc + 3 < p.N) {
+              float4 w4 = make_float4(o[0], o[1], o[2], o[3]);
+              if (p.accum == ACC_ADD) { const float4 old = *reinterpret_cast<float4*>(dst); w4.x += old.x; w4.y += old.y; w4.z += old.z; w4.w += old.w; }
+              *reinterpret_cast<float4*>(dst) = w4;
+            } else {
+#pragma unroll
+              for (int e = 0; e < 4; ++e)
+                if (gc + e < p.N) { if (p.accum == ACC_ADD) dst[e] += o[e]; else dst[e] = o[e]; }
+            }
+          }
+        }
+        __syncwarp();
+      }
+    }
+    // this warp's TMEM reads of the accumulator are complete: hand it back to the MMA warp
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncwarp();
+    if (lane == 0) arrive_empty(as);
+    if (trace && threadIdx.x == 64 && lt < 8) p.dbg[209 + 2 * lt] = clock64();
+  }
+  if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // staging must outlive the stores
+  __syncwarp();
+}
+
 template <int BN, bool A_MN, bool B_MN, bool X3 = false>
 __global__ void __launch_bounds__(320, 1) k_tc_gemm(const __grid_constant__ CUtensorMap tmA,
                                                     const __grid_constant__ CUtensorMap tmB,
@@ -238,147 +382,184 @@ __global__ void __launch_bounds__(320, 1) k_tc_gemm(const __grid_constant__ CUte
       }
     }
   } else {                                                         // ---- epilogue: warps 2..9
-    // Two warps per TMEM lane quadrant (a warp may only read lanes 32*(warp%4)..+31), each taking
-    // half of the tile's columns, so draining an accumulator costs about half a main loop.
-    const int ew = warp - 2;                                       // 0..7
-    const int q = warp & 3;                                        // TMEM lane quadrant
-    const int half = ew >> 2;                                      // which half of the BN columns
-    constexpr int HC = BN / 2;
-    const uint32_t slab = stg_base + (uint32_t)ew * 4096u;         // one 32x32 fp32 staging slab per warp
-    const uint32_t abar = bars + 8u * (2 * S + 5 + ew);            // `add` tile arrival barrier of this warp
-    const bool vec = ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0) && (p.ldc % 4 == 0);
-    const int rsub = lane >> 3, cc4 = lane & 7;
-    uint32_t lt = 0, nstore = 0;
-    for (int t = blockIdx.x; t < total; t += gridDim.x, ++lt) {
-      int m0, n0, kbeg, nkb; tile_coords(t, m0, n0, kbeg, nkb);
-      const uint32_t as = lt & 1;
-      mbar_wait(tfull_bar(as), (lt >> 1) & 1);
-      if (trace && threadIdx.x == 64 && lt < 8) p.dbg[208 + 2 * lt] = clock64();
-      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      const uint32_t tacc = tmem_base + as * BN + ((uint32_t)(q * 32) << 16);
-      const int gi = m0 + q * 32 + lane;                           // the accumulator row this thread owns
-      const bool row_ok = gi < p.M;
-#pragma unroll 1
-      for (int c = half * HC; c < (half + 1) * HC; c += 32) {
-        float v[32];
-        tmem_ld32(tacc + (uint32_t)c, v);
-        const int gj = n0 + c;
-        if (gj >= p.N) continue;                                   // warp-uniform
-        const bool full = gj + 32 <= p.N;                          // warp-uniform: whole chunk in bounds
-        // the previous bulk store of this warp must have finished reading the slab
-        if (nstore > 0) { if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); __syncwarp(); }
-        if (p.add_tma) {
-          // `add` tile (32 rows x 32 cols of this warp) fetched by TMA into the slab it is later stored from
-          if (lane == 0) { mbar_expect_tx(abar, 4096); tma_load_2d(&tmAdd, slab, abar, gj, m0 + q * 32); }
-          mbar_wait(abar, nstore & 1);
-          const uint32_t sl = slab + (uint32_t)(lane * 128);
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            float a0, a1, a2, a3;
-            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(a0), "=f"(a1), "=f"(a2), "=f"(a3)
-                         : "r"(sl + (uint32_t)(((j ^ (lane & 7)) << 4))) : "memory");
-            v[4 * j] += a0; v[4 * j + 1] += a1; v[4 * j + 2] += a2; v[4 * j + 3] += a3;
-          }
-        } else if (p.add) {
-          if (row_ok) {
-            const float* ar = p.add + (int64_t)gi * p.ldadd + gj;
-            if (full) {
-#pragma unroll
-              for (int j = 0; j < 32; j += 4) {
-                const float4 a4 = __ldg(reinterpret_cast<const float4*>(ar + j));
-                v[j] += a4.x; v[j + 1] += a4.y; v[j + 2] += a4.z; v[j + 3] += a4.w;
-              }
-            } else {
-#pragma unroll
-              for (int j = 0; j < 32; ++j) if (gj + j < p.N) v[j] += __ldg(ar + j);
-            }
-          }
-        }
-        if (p.bias) {
-          if (full) {
-#pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + gj + j));   // same address in every lane
-              v[j] += b4.x; v[j + 1] += b4.y; v[j + 2] += b4.z; v[j + 3] += b4.w;
-            }
-          } else {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) if (gj + j < p.N) v[j] += __ldg(p.bias + gj + j);
-          }
-        }
-        if (p.act == ACT_RELU) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
-        } else if (p.act != ACT_NONE) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = tc_act(v[j], p.act);
-        }
-        // Each thread owns one accumulator row; rows go through the 128B-swizzled slab (conflict-free
-        // 128-bit accesses both ways).
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const uint32_t dst = slab + (uint32_t)(lane * 128) + (uint32_t)(((j ^ (lane & 7)) << 4));
-          asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "f"(v[4 * j]), "f"(v[4 * j + 1]),
-                       "f"(v[4 * j + 2]), "f"(v[4 * j + 3]) : "memory");
-        }
-        if (p.tma_store) {
-          // ... and leave as one 4 KB TMA bulk store (plain, or f32 reduce-add for accumulate / split-K
-          // modes): bulk stores are not limited by the epilogue warps' outstanding-store budget, unlike
-          // STG (measured 12x faster here).
-          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-          __syncwarp();
-          if (lane == 0) {
-            if (p.accum == ACC_STORE) tma_store_2d(&tmC, slab, gj, m0 + q * 32);
-            else tma_reduce_add_2d(&tmC, slab, gj, m0 + q * 32);
-            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-          }
-          ++nstore;
-        } else {
-          // Fallback (row scatter through c_idx, or rows that are not 16-byte aligned): read the slab back
-          // row-wise and issue coalesced STG / RED (one warp instruction = 4 rows x 128 contiguous bytes).
-          __syncwarp();
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const int rr = i * 4 + rsub;
-            const int gr = m0 + q * 32 + rr, gc = gj + cc4 * 4;
-            float o[4];
-            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(o[0]), "=f"(o[1]), "=f"(o[2]), "=f"(o[3])
-                         : "r"(slab + (uint32_t)(rr * 128) + (uint32_t)(((cc4 ^ (rr & 7)) << 4))) : "memory");
-            if (gr < p.M && gc < p.N) {
-              const int64_t crow = p.c_idx ? p.c_idx[gr] : gr;
-              float* dst = p.C + crow * p.ldc + gc;
-              if (p.accum == ACC_ATOMIC) {
-#pragma unroll
-                for (int e = 0; e < 4; ++e)
-                  if (gc + e < p.N) atomicAdd(dst + e, o[e]);
-              } else if (vec && gc + 3 < p.N) {
-                float4 w4 = make_float4(o[0], o[1], o[2], o[3]);
-                if (p.accum == ACC_ADD) { const float4 old = *reinterpret_cast<float4*>(dst); w4.x += old.x; w4.y += old.y; w4.z += old.z; w4.w += old.w; }
-                *reinterpret_cast<float4*>(dst) = w4;
-              } else {
-#pragma unroll
-                for (int e = 0; e < 4; ++e)
-                  if (gc + e < p.N) { if (p.accum == ACC_ADD) dst[e] += o[e]; else dst[e] = o[e]; }
-              }
-            }
-          }
-          __syncwarp();
-        }
-      }
-      // this warp's TMEM reads of the accumulator are complete: hand it back to the MMA warp
-      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-      __syncwarp();
-      if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tempty_bar(as)) : "memory");
-      if (trace && threadIdx.x == 64 && lt < 8) p.dbg[209 + 2 * lt] = clock64();
-    }
-    if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // staging must outlive the stores
-    __syncwarp();
+    tc_epilogue<BN>(p, &tmC, &tmAdd, tmem_base, stg_base, bars + 8u * (2 * S + 5), tfull_bar(0), (int)blockIdx.x,
+                    (int)gridDim.x, total, tile_coords,
+                    [&](uint32_t as) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tempty_bar(as)) : "memory"); },
+                    trace);
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   if (warp == 1) {
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(2 * BN) : "memory");
+  }
+}
+
+// =============================================================================================
+// 2-CTA variant (cta_group::2) for the large products: a cluster of two CTAs on one TPC computes a
+// 256 x 256 output tile.  Each CTA stages its own 128 rows of A and HALF of the B tile (128 of the
+// 256 N rows); tcgen05.mma.cta_group::2, issued by the leader CTA only, reads both halves, so the
+// L2 -> SM traffic per flop drops by a third against the 128 x 256 single-CTA tile (the single-CTA
+// main loop is L2-feed bound: ncu shows the tensor pipe 50 % active).  Both CTAs' TMA loads signal
+// the leader's "full" barrier; tcgen05.commit multicasts to both CTAs' "empty" / "accumulator full"
+// barriers; each CTA drains its own 128 TMEM lanes and both report to the leader's "accumulator
+// empty" barrier.
+// =============================================================================================
+constexpr int S2 = 6;
+constexpr int STAGE2 = A_BYTES + 128 * TBK * 4;   // 32 KB per CTA
+constexpr int SMEM2 = S2 * STAGE2 + 1024 + 8 * 4096 + 256;
+
+__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P1;\n\t"
+      "WAIT_LOOP:\n\t"
+      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 P1, [%0], %1;\n\t"
+      "@P1 bra.uni WAIT_DONE;\n\t"
+      "bra.uni WAIT_LOOP;\n\t"
+      "WAIT_DONE:\n\t"
+      "}" ::"r"(bar), "r"(parity) : "memory");
+}
+// TMA load whose completion bytes go to the LEADER CTA's mbarrier (peer bit cleared: cute Sm100MmaPeerBitMask)
+__device__ __forceinline__ void tma_load_2d_2sm(const CUtensorMap* map, uint32_t dst, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar & 0xFEFFFFFFu), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void umma_tf32_2sm(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
+}
+__device__ __forceinline__ void umma_commit_2sm(uint32_t bar) {   // arrives on `bar` in both CTAs of the pair
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(bar), "h"((uint16_t)3) : "memory");
+}
+
+template <bool A_MN, bool B_MN>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(320, 1)
+k_tc_gemm2(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+           const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmAdd, const TcParams p) {
+  constexpr int BN = 256, S = S2;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t stg_base = base + S * STAGE2;
+  const uint32_t bars = stg_base + 8 * 4096;
+  auto full_bar = [&](int s) { return bars + 8u * s; };
+  auto empty_bar = [&](int s) { return bars + 8u * (S + s); };
+  auto tfull_bar = [&](int a) { return bars + 8u * (2 * S + a); };
+  auto tempty_bar = [&](int a) { return bars + 8u * (2 * S + 2 + a); };
+  const uint32_t tmem_slot = bars + 8u * (2 * S + 4);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+  const int gm2 = (p.M + 255) / 256, gn = (p.N + BN - 1) / BN;
+  const int splits = (p.K + p.k_chunk - 1) / p.k_chunk;
+  const int total = gm2 * gn * splits;
+  const int cid = blockIdx.x >> 1, ncl = gridDim.x >> 1;
+  const bool trace = p.dbg && blockIdx.x == 0;
+  if (trace && threadIdx.x == 0) p.dbg[200] = clock64();
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < S; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 16); }   // 8 warps x 2 CTAs
+    for (int w = 0; w < 8; ++w) mbar_init(bars + 8u * (2 * S + 5 + w), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(2 * BN) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  cluster_sync_all();                                              // peer barriers are initialised, TMEM is allocated
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  uint32_t tmem_base;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+  if (trace && threadIdx.x == 0) p.dbg[201] = clock64();
+
+  auto tile_coords = [&](int t, int& m0, int& n0, int& kbeg, int& nkb) {
+    const int mt = t % gm2, nt = (t / gm2) % gn, z = t / (gm2 * gn);
+    m0 = mt * 256 + (int)rank * TBM; n0 = nt * BN; kbeg = z * p.k_chunk;   // this CTA's 128 rows of the pair's tile
+    const int kend = min(p.K, kbeg + p.k_chunk);
+    nkb = (kend - kbeg + TBK - 1) / TBK;
+  };
+
+  if (warp == 0) {
+    if (lane == 0) {                                               // ---- TMA producer (both CTAs)
+      uint32_t it = 0;
+      for (int t = cid; t < total; t += ncl) {
+        int m0, n0, kbeg, nkb; tile_coords(t, m0, n0, kbeg, nkb);
+        const int nb0 = n0 + (int)rank * 128;                      // this CTA's half of the B tile
+        for (int kb = 0; kb < nkb; ++kb, ++it) {
+          const int s = it % S;
+          mbar_wait_cluster(empty_bar(s), ((it / S) & 1) ^ 1);
+          if (trace && it < 32) p.dbg[it] = clock64();
+          if (leader) mbar_expect_tx(full_bar(s), 2 * STAGE2);     // bytes of both CTAs land on the leader's barrier
+          const int k0 = kbeg + kb * TBK;
+          const uint32_t sa = base + s * STAGE2, sb = sa + A_BYTES;
+          if (!A_MN) tma_load_2d_2sm(&tmA, sa, full_bar(s), k0, m0);
+          else
+#pragma unroll
+            for (int g = 0; g < 4; ++g) tma_load_2d_2sm(&tmA, sa + g * 4096, full_bar(s), m0 + g * 32, k0);
+          if (!B_MN) tma_load_2d_2sm(&tmB, sb, full_bar(s), k0, nb0);
+          else
+#pragma unroll
+            for (int g = 0; g < 4; ++g) tma_load_2d_2sm(&tmB, sb + g * 4096, full_bar(s), nb0 + g * 32, k0);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0 && leader) {                                     // ---- MMA issuer (leader CTA only)
+      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((A_MN ? 1u : 0u) << 15) | ((B_MN ? 1u : 0u) << 16) |
+                             ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+      uint32_t it = 0, lt = 0;
+      for (int t = cid; t < total; t += ncl, ++lt) {
+        int m0, n0, kbeg, nkb; tile_coords(t, m0, n0, kbeg, nkb);
+        const uint32_t as = lt & 1;
+        mbar_wait_cluster(tempty_bar(as), ((lt >> 1) & 1) ^ 1);    // both CTAs have drained this accumulator
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t tacc = tmem_base + as * BN;
+        for (int kb = 0; kb < nkb; ++kb, ++it) {
+          const int s = it % S;
+          mbar_wait_cluster(full_bar(s), (it / S) & 1);
+          if (trace && it < 32) p.dbg[64 + it] = clock64();
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const uint32_t sa = base + s * STAGE2, sb = sa + A_BYTES;
+#pragma unroll
+          for (int k = 0; k < TBK / 8; ++k) {
+            const uint64_t ad = A_MN ? umma_desc(sa + k * 1024, 4096, 512, 1) : umma_desc(sa + k * 32, 16, 1024, 2);
+            const uint64_t bd = B_MN ? umma_desc(sb + k * 1024, 4096, 512, 1) : umma_desc(sb + k * 32, 16, 1024, 2);
+            umma_tf32_2sm(tacc, ad, bd, idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          umma_commit_2sm(empty_bar(s));                           // frees the stage in both CTAs
+        }
+        umma_commit_2sm(tfull_bar(as));                            // accumulator complete, both CTAs' epilogues
+      }
+    }
+  } else {
+    tc_epilogue<BN>(p, &tmC, &tmAdd, tmem_base, stg_base, bars + 8u * (2 * S + 5), tfull_bar(0), cid, ncl, total, tile_coords,
+                    [&](uint32_t as) {
+                      // report to the LEADER's "accumulator empty" barrier (remote arrive from the peer CTA)
+                      uint32_t ra;
+                      asm volatile("mapa.shared::cluster.u32 %0, %1, 0;" : "=r"(ra) : "r"(tempty_bar(as)));
+                      asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(ra) : "memory");
+                    },
+                    trace);
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  cluster_sync_all();                                              // nobody may still address the peer's smem / TMEM
+  if (warp == 1) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(2 * BN) : "memory");
   }
 }
 
@@ -496,6 +677,72 @@ bool launch_tc(dx_stream_t s, const GemmP& g, const float* A_lo = nullptr, const
   return true;
 }
 
+// 2-CTA launch (BN = 256).  Returns false if not applicable.
+bool launch_tc2(dx_stream_t s, const GemmP& g) {
+  static const bool disabled = getenv("DX_TC_NO_CG2") != nullptr;
+  if (disabled) return false;
+  const int gm2 = (g.M + 255) / 256, gn = (g.N + 255) / 256;
+  int splits = 1;
+  if (g.accum == ACC_ATOMIC) {
+    const int tiles = gm2 * gn;
+    const int want = 148 / tiles;                               // two rounds of the 74 clusters
+    const int maxs = (g.K + TBK * 16 - 1) / (TBK * 16);
+    splits = want < 1 ? 1 : (want > maxs ? maxs : want);
+  }
+  int k_chunk = (g.K + splits - 1) / splits;
+  k_chunk = (k_chunk + TBK - 1) / TBK * TBK;
+  splits = (g.K + k_chunk - 1) / k_chunk;
+  const int total = gm2 * gn * splits;
+  if (total < 37) return false;                                 // too little work for the pair-tile: 1-CTA kernel
+  const bool tma_store = !g.c_idx && ((reinterpret_cast<uintptr_t>(g.C) & 15) == 0) && (g.ldc % 4 == 0);
+  if (!tma_store) return false;
+  CUtensorMap ta, tb, tc, tadd;
+  if (g.a_kc) { if (!make_map(&ta, g.A, g.M, g.K, g.lda, TBK, TBM, false)) return false; }
+  else        { if (!make_map(&ta, g.A, g.K, g.M, g.lda, 32, TBK, true)) return false; }
+  if (g.b_kc) { if (!make_map(&tb, g.B, g.N, g.K, g.ldb, TBK, 128, false)) return false; }   // half of the B tile per CTA
+  else        { if (!make_map(&tb, g.B, g.K, g.N, g.ldb, 32, TBK, true)) return false; }
+  if (!make_map(&tc, g.C, g.M, g.N, g.ldc, 32, 32, false, true)) return false;
+  const bool add_tma = g.add && ((reinterpret_cast<uintptr_t>(g.add) & 15) == 0) && (g.ldadd % 4 == 0);
+  if (g.add && !add_tma) return false;
+  if (add_tma) { if (!make_map(&tadd, g.add, g.M, g.N, g.ldadd, 32, 32, false, true)) return false; }
+  else tadd = ta;
+  static long long* dbg = nullptr;
+  static const bool want_dbg = getenv("DX_TC_DEBUG") != nullptr;
+  if (want_dbg && !dbg) cudaMalloc(&dbg, 256 * sizeof(long long));
+  if (want_dbg) cudaMemsetAsync(dbg, 0, 256 * sizeof(long long), s);
+  TcParams p{g.M, g.N, g.K, g.C, g.ldc, g.c_idx, g.bias, g.add, g.ldadd, g.act, g.accum, k_chunk, 1, add_tma ? 1 : 0,
+             want_dbg ? dbg : nullptr};
+  static int num_sms = 0;
+  if (!num_sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev); }
+  const int ncl = total < num_sms / 2 ? total : num_sms / 2;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaFuncSetAttribute(k_tc_gemm2<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM2);
+    cudaFuncSetAttribute(k_tc_gemm2<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM2);
+    cudaFuncSetAttribute(k_tc_gemm2<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM2);
+    attr_set = true;
+  }
+  dim3 grid(2 * ncl);
+  if (g.a_kc && g.b_kc) k_tc_gemm2<false, false><<<grid, 320, SMEM2, s>>>(ta, tb, tc, tadd, p);
+  else if (g.a_kc && !g.b_kc) k_tc_gemm2<false, true><<<grid, 320, SMEM2, s>>>(ta, tb, tc, tadd, p);
+  else if (!g.a_kc && !g.b_kc) k_tc_gemm2<true, true><<<grid, 320, SMEM2, s>>>(ta, tb, tc, tadd, p);
+  else return false;
+  ++g_launches;
+  if (want_dbg) {
+    long long h[256];
+    cudaStreamSynchronize(s);
+    cudaMemcpy(h, dbg, sizeof(h), cudaMemcpyDeviceToHost);
+    const long long t0 = h[200];
+    fprintf(stderr, "[tc2 trace] M=%d N=%d K=%d splits=%d pair-tiles=%d clusters=%d | setup %lld | epilogues:", g.M, g.N, g.K,
+            splits, total, ncl, h[201] - t0);
+    for (int i = 0; i < 8 && h[208 + 2 * i]; ++i) fprintf(stderr, " [%lld..%lld]", h[208 + 2 * i] - t0, h[209 + 2 * i] - t0);
+    fprintf(stderr, "\n  mma(full ok):");
+    for (int i = 0; i < 20 && h[64 + i]; ++i) fprintf(stderr, " %lld", h[64 + i] - t0);
+    fprintf(stderr, "\n");
+  }
+  return true;
+}
+
 inline bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
 }  // namespace
@@ -509,6 +756,7 @@ bool tc_gemm(dx_stream_t s, const GemmP& g, int* tile_n) {
   if ((double)g.M * g.N * g.K < 1.0e6) return false;          // launch-bound anyway
   const int bn = g.N >= 192 ? 256 : (g.N >= 96 ? 128 : 64);
   if (tile_n) *tile_n = bn;
+  if (bn == 256 && launch_tc2(s, g)) return true;
   return bn == 256 ? launch_tc<256>(s, g) : (bn == 128 ? launch_tc<128>(s, g) : launch_tc<64>(s, g));
 }
 
