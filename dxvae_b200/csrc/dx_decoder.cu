@@ -289,6 +289,146 @@ static void decide_edges(dx_stream_t st, int B, int vi, int vj, const float* lg,
 }
 
 // =============================================================================================
+// Fused edge head of a compacted teacher-forced step (model.py:348-351 + its loss :363 + the
+// gradients that are local to the head):  e = relu(U + Q_vj) ;  l = e W2^T + b2 ;  BCE against the
+// true (vj->vi, vi->vj) flags ;  dl = (sigmoid(l) - t) / B ;  dW2 += dl^T e ;  db2 += sum dl.
+// One pass over U and Q (16 KB/row); only the relu bit-mask (256 B/row) and dl are kept for the
+// backward pass instead of the 8 KB/row activation.
+// =============================================================================================
+struct EdgeHeadP {
+  int B, vi, vj; const float* U; const float* Q; const float* W2; const float* b2; const uint64_t* adj; float inv_batch;
+  float* l2; float* dl2; float* rowloss; uint8_t* mask; float* dW2; float* db2;
+};
+
+DX_HD DX_INLINE void edge_head_row_finish(const EdgeHeadP& a, int b, float l0, float l1, float* dl) {
+  const uint64_t A = a.adj[b];
+  const float t0 = (float)abit(A, a.vj, a.vi), t1 = (float)abit(A, a.vi, a.vj);
+  l0 += a.b2[0]; l1 += a.b2[1];
+  a.l2[(int64_t)b * LD_E] = l0; a.l2[(int64_t)b * LD_E + 1] = l1;
+  dl[0] = (sigmoidf_(l0) - t0) * a.inv_batch; dl[1] = (sigmoidf_(l1) - t1) * a.inv_batch;
+  a.dl2[(int64_t)b * LD_E] = dl[0]; a.dl2[(int64_t)b * LD_E + 1] = dl[1];
+  a.rowloss[(int64_t)2 * a.B + b] += (bce_logits(l0, t0) + bce_logits(l1, t1)) * a.inv_batch;
+}
+
+#ifndef DX_EMU
+constexpr int EH_R = 4;   // rows per block iteration
+static __global__ void __launch_bounds__(256) k_edge_head_fwd(const EdgeHeadP a) {
+  __shared__ float red[8][2 * EH_R];
+  __shared__ float dls[2 * EH_R];
+  const int t = threadIdx.x, lane = t & 31, wid = t >> 5;
+  const int c0 = t * 8;
+  float w0[8], w1[8], acc0[8], acc1[8];
+  {
+    const float4 x0 = ld4f(a.W2 + c0), x1 = ld4f(a.W2 + c0 + 4), y0 = ld4f(a.W2 + 4 * H + c0), y1 = ld4f(a.W2 + 4 * H + c0 + 4);
+    w0[0] = x0.x; w0[1] = x0.y; w0[2] = x0.z; w0[3] = x0.w; w0[4] = x1.x; w0[5] = x1.y; w0[6] = x1.z; w0[7] = x1.w;
+    w1[0] = y0.x; w1[1] = y0.y; w1[2] = y0.z; w1[3] = y0.w; w1[4] = y1.x; w1[5] = y1.y; w1[6] = y1.z; w1[7] = y1.w;
+  }
+#pragma unroll
+  for (int k = 0; k < 8; ++k) { acc0[k] = 0.f; acc1[k] = 0.f; }
+  float db0 = 0.f, db1 = 0.f;
+  for (int r0 = blockIdx.x * EH_R; r0 < a.B; r0 += gridDim.x * EH_R) {
+    float e[EH_R][8], part[2 * EH_R];
+#pragma unroll
+    for (int r = 0; r < EH_R; ++r) {
+      const int b = r0 + r;
+      float4 u0 = f4zero(), u1 = f4zero(), q0 = f4zero(), q1 = f4zero();
+      if (b < a.B) {
+        const float* up = a.U + (int64_t)b * 4 * H + c0; const float* qp = a.Q + (int64_t)b * 4 * H + c0;
+        u0 = ld4f(up); u1 = ld4f(up + 4); q0 = ld4f(qp); q1 = ld4f(qp + 4);
+      }
+      e[r][0] = fmaxf(u0.x + q0.x, 0.f); e[r][1] = fmaxf(u0.y + q0.y, 0.f); e[r][2] = fmaxf(u0.z + q0.z, 0.f);
+      e[r][3] = fmaxf(u0.w + q0.w, 0.f); e[r][4] = fmaxf(u1.x + q1.x, 0.f); e[r][5] = fmaxf(u1.y + q1.y, 0.f);
+      e[r][6] = fmaxf(u1.z + q1.z, 0.f); e[r][7] = fmaxf(u1.w + q1.w, 0.f);
+      float p0 = 0.f, p1 = 0.f; unsigned m = 0;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) { p0 = fmaf(e[r][k], w0[k], p0); p1 = fmaf(e[r][k], w1[k], p1); m |= (e[r][k] > 0.f ? 1u : 0u) << k; }
+      if (b < a.B) a.mask[(int64_t)b * 256 + t] = (uint8_t)m;
+      part[2 * r] = p0; part[2 * r + 1] = p1;
+    }
+#pragma unroll
+    for (int i = 0; i < 2 * EH_R; ++i) {
+      float v = part[i];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+      if (lane == 0) red[wid][i] = v;
+    }
+    __syncthreads();
+    if (t < EH_R) {
+      const int b = r0 + t;
+      float dl[2] = {0.f, 0.f};
+      if (b < a.B) {
+        float l0 = 0.f, l1 = 0.f;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) { l0 += red[w][2 * t]; l1 += red[w][2 * t + 1]; }
+        edge_head_row_finish(a, b, l0, l1, dl);
+      }
+      dls[2 * t] = dl[0]; dls[2 * t + 1] = dl[1];
+    }
+    __syncthreads();
+    if (a.dW2) {
+#pragma unroll
+      for (int r = 0; r < EH_R; ++r) {
+        const float d0 = dls[2 * r], d1 = dls[2 * r + 1];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { acc0[k] = fmaf(d0, e[r][k], acc0[k]); acc1[k] = fmaf(d1, e[r][k], acc1[k]); }
+        if (t == 0) { db0 += d0; db1 += d1; }
+      }
+    }
+    __syncthreads();
+  }
+  if (a.dW2) {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { atomicAdd(a.dW2 + c0 + k, acc0[k]); atomicAdd(a.dW2 + 4 * H + c0 + k, acc1[k]); }
+    if (t == 0) { atomicAdd(a.db2, db0); atomicAdd(a.db2 + 1, db1); }
+  }
+}
+static void edge_head_fwd(dx_stream_t st, const EdgeHeadP& a) {
+  int blocks = (a.B + EH_R - 1) / EH_R;
+  if (blocks > 148 * 2) blocks = 148 * 2;
+  k_edge_head_fwd<<<blocks, 256, 0, st>>>(a);
+  ++g_launches;
+}
+#else
+static void edge_head_fwd(dx_stream_t, const EdgeHeadP& a) {
+  for (int b = 0; b < a.B; ++b) {
+    float l0 = 0.f, l1 = 0.f;
+    for (int j = 0; j < 4 * H; ++j) {
+      const float e = fmaxf(a.U[(int64_t)b * 4 * H + j] + a.Q[(int64_t)b * 4 * H + j], 0.f);
+      l0 += e * a.W2[j]; l1 += e * a.W2[4 * H + j];
+      if ((j & 7) == 0) a.mask[(int64_t)b * 256 + j / 8] = 0;
+      if (e > 0.f) a.mask[(int64_t)b * 256 + j / 8] |= (uint8_t)(1u << (j & 7));
+    }
+    float dl[2];
+    edge_head_row_finish(a, b, l0, l1, dl);
+    if (a.dW2) {
+      for (int j = 0; j < 4 * H; ++j) {
+        const float e = fmaxf(a.U[(int64_t)b * 4 * H + j] + a.Q[(int64_t)b * 4 * H + j], 0.f);
+        a.dW2[j] += dl[0] * e; a.dW2[4 * H + j] += dl[1] * e;
+      }
+      a.db2[0] += dl[0]; a.db2[1] += dl[1];
+    }
+  }
+  ++g_launches;
+}
+#endif
+// backward of the head w.r.t. its pre-activation: g = mask * (dl0 W2[0] + dl1 W2[1]) ;  dQ += g ; dU += g
+static void edge_head_bwd(dx_stream_t st, int B, const uint8_t* mask, const float* dl2, const float* W2, float* dQ,
+                          float* dU) {
+  foreach (st, (int64_t)B * 256, [=] DX_HD(int64_t idx) {
+    const int64_t b = idx >> 8; const int c0 = (int)(idx & 255) * 8;
+    const unsigned m = mask[idx];
+    const float d0 = dl2[b * LD_E], d1 = dl2[b * LD_E + 1];
+    float g[8];
+    for (int k = 0; k < 8; ++k) g[k] = ((m >> k) & 1u) ? d0 * W2[c0 + k] + d1 * W2[4 * H + c0 + k] : 0.f;
+    float* q = dQ + b * 4 * H + c0; float* u = dU + b * 4 * H + c0;
+    float4 q0 = ld4f(q), q1 = ld4f(q + 4), u0 = ld4f(u), u1 = ld4f(u + 4);
+    q0.x += g[0]; q0.y += g[1]; q0.z += g[2]; q0.w += g[3]; q1.x += g[4]; q1.y += g[5]; q1.z += g[6]; q1.w += g[7];
+    u0.x += g[0]; u0.y += g[1]; u0.z += g[2]; u0.w += g[3]; u1.x += g[4]; u1.y += g[5]; u1.z += g[6]; u1.w += g[7];
+    st4f(q, q0); st4f(q + 4, q1); st4f(u, u0); st4f(u + 4, u1);
+  });
+}
+
+// =============================================================================================
 // forward
 // =============================================================================================
 
@@ -371,9 +511,10 @@ void decode_fwd_impl(dx_stream_t st, const Weights& W, int B, const float* z, co
       copy_async(st, Hcur, w.Hi_p2[vi], sizeof(float) * (size_t)B * H);
       linear_fwd(st, B, 4 * H, H, w.Hi_p2[vi], H, W[P_E_W0], 2 * H, nullptr, w.U, 4 * H);
       for (int vj = vi - 1; vj >= 0; --vj, ++t) {
-        add_relu(st, (int64_t)B * 4 * H / 4, w.U, w.Q + (size_t)vj * B * 4 * H, w.E1[t]);
-        linear_fwd(st, B, 2, 4 * H, w.E1[t], 4 * H, W[P_E_W2], 4 * H, W[P_E_B2], w.l2[t], LD_E);
-        loss_edge(st, B, vi, vj, w.l2[t], 2, adj, io.lw, w.rowloss, w.dl2[t]);
+        // fused edge head: the E1 buffer of the step only stores the relu bit-mask (256 B/row)
+        EdgeHeadP eh{B, vi, vj, w.U, w.Q + (size_t)vj * B * 4 * H, W[P_E_W2], W[P_E_B2], adj, io.lw.inv_batch, w.l2[t], w.dl2[t],
+                     w.rowloss, reinterpret_cast<uint8_t*>(w.E1[t]), io.dW2, io.db2};
+        edge_head_fwd(st, eh);
         const int n = io.bt->step_ptr[t + 1] - io.bt->step_ptr[t];
         if (n <= 0) continue;
         const int* rows = io.bt->step_rows + io.bt->step_ptr[t];
@@ -509,9 +650,8 @@ void decode_bwd_impl(dx_stream_t st, const Weights& W, const Weights& G, int B, 
           MsgBwd mb{rs, w.Pg, w.Pm, W[P_G_B], adj, w.dHrun, 0, w.dPg, w.dPm, w.dgb, 1, vi, vi, 1};
           msg_bwd(st, mb);
         }
-        linear_wgrad(st, B, 2, 4 * H, w.dl2[t], LD_E, w.E1[t], 4 * H, G[P_E_W2], 4 * H);
-        colsum_accum(st, B, 2, w.dl2[t], LD_E, G[P_E_B2]);
-        relu_head_bwd(st, B, 4 * H, 2, w.E1[t], w.dl2[t], LD_E, W[P_E_W2], nullptr, w.dQ + (size_t)vj * B * 4 * H, dU);
+        // (dW2 / db2 of this head were accumulated by the fused forward kernel)
+        edge_head_bwd(st, B, reinterpret_cast<const uint8_t*>(w.E1[t]), w.dl2[t], W[P_E_W2], w.dQ + (size_t)vj * B * 4 * H, dU);
       }
       // what is left in dU belongs to U = Hi_p2 W^T (the state every graph had before its first edge)
       linear_wgrad(st, B, 4 * H, H, dU, 4 * H, w.Hi_p2[vi], H, G[P_E_W0], 2 * H);

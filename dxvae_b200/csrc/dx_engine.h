@@ -69,6 +69,8 @@ struct DecIO {
   LossW lw;
   uint64_t* adj_out;      // greedy: adjacency being built
   float* margins;         // greedy, optional
+  float* dW2 = nullptr;   // train + compacted steps: gradient slots of h_to_edge.2.{weight,bias}; the fused edge
+  float* db2 = nullptr;   //   head accumulates them during the forward pass (NULL: loss only, no gradients)
 };
 
 EncWs carve_enc(Arena& ar, int64_t B, bool train);
