@@ -393,3 +393,40 @@ def test_compacted_steps_equal_dense_replay(lib):
         for n, g in res[False][1].items():
             assert (res[True][1][n] - g).abs().max().item() <= 2e-5 * (g.abs().max().item() + 1e-30), n
     m.compact_steps = True
+
+
+# --------------------------------------------------------------------------- DXVAE.train (model.py:374-391)
+def test_train_method_semantics(lib, tmp_path):
+    """epochs+1 passes, drop-last batching, in-place shuffle of the caller's list driven by Python's
+    `random`, checkpoint per epoch that the reference layout can load, loss going down."""
+    import random
+    from dxvae_b200 import DXVAE
+    idx = list(range(0, 1024, 4))[:200]
+    X, P, E, A = util.dataset_graphs(idx)
+    G = _graphs(X, P, E)
+    ids = {id(g): i for i, g in enumerate(G)}
+    torch.manual_seed(0)
+    m = DXVAE(); m.verbose = False
+    chk = str(tmp_path / "t.chk")
+    random.seed(3)
+    expect = list(range(len(G)))
+    rnd = random.Random(3)
+    for _ in range(3):                                   # epochs + 1 shuffles of the same list
+        rnd.shuffle(expect)
+    with torch.no_grad():
+        before = m.forward(G, eps=torch.zeros(len(G), 128))[0].item()
+    m.train(G, epochs=2, size_batch=64, lr=1e-3, checkpoint=chk)
+    assert [ids[id(g)] for g in G] == expect             # same permutation random.shuffle(G) x3 would produce
+    with torch.no_grad():
+        after = m.forward(G, eps=torch.zeros(len(G), 128))[0].item()
+    assert after < before                                 # 9 AdamW steps (3 per pass, remainder dropped)
+    sd = torch.load(chk, map_location="cpu")
+    o = O.OracleDXVAE()
+    o.load_state_dict(sd)                                 # same 53 keys / shapes as the reference module
+    for n, p in m.state_dict().items():
+        assert torch.equal(sd[n], p.cpu()), n
+    m2 = DXVAE(checkpoint=chk)                            # model.py:80-81
+    m2.verbose = False
+    with torch.no_grad():
+        again = m2.forward(G, eps=torch.zeros(len(G), 128))[0].item()
+    assert abs(again - after) <= 1e-5 * abs(after)
