@@ -160,7 +160,10 @@ def run_ours(args):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     if world > 1:
-        os.environ["NCCL_DEBUG"] = os.environ.get("DX_NCCL_DEBUG", "WARN")   # keep stdout to the one JSON line
+        if "DX_NCCL_DEBUG" in os.environ:                 # default: NCCL silent, stdout is the one JSON line
+            os.environ["NCCL_DEBUG"] = os.environ["DX_NCCL_DEBUG"]
+        else:
+            os.environ.pop("NCCL_DEBUG", None)
         import datetime
         dist.init_process_group("nccl", device_id=torch.device("cuda", local),
                                 timeout=datetime.timedelta(seconds=120))

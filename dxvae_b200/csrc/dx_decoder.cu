@@ -312,9 +312,12 @@ DX_HD DX_INLINE void edge_head_row_finish(const EdgeHeadP& a, int b, float l0, f
 
 #ifndef DX_EMU
 constexpr int EH_R = 4;   // rows per block iteration
+// 256 threads x 8 columns; every iteration takes EH_R rows.  The per-row logits go warp-shuffle ->
+// shared (double-buffered by iteration parity: ONE __syncthreads per iteration) and every warp then
+// finishes the EH_R rows redundantly in its first 2*EH_R lanes (lane = 2*row + output), so no thread
+// waits on a serial tail; warp 0 alone writes the row outputs.
 static __global__ void __launch_bounds__(256) k_edge_head_fwd(const EdgeHeadP a) {
-  __shared__ float red[8][2 * EH_R];
-  __shared__ float dls[2 * EH_R];
+  __shared__ float red[2][8][2 * EH_R];
   const int t = threadIdx.x, lane = t & 31, wid = t >> 5;
   const int c0 = t * 8;
   float w0[8], w1[8], acc0[8], acc1[8];
@@ -325,8 +328,17 @@ static __global__ void __launch_bounds__(256) k_edge_head_fwd(const EdgeHeadP a)
   }
 #pragma unroll
   for (int k = 0; k < 8; ++k) { acc0[k] = 0.f; acc1[k] = 0.f; }
-  float db0 = 0.f, db1 = 0.f;
-  for (int r0 = blockIdx.x * EH_R; r0 < a.B; r0 += gridDim.x * EH_R) {
+  float dbsum = 0.f;                                   // lanes 0..2*EH_R-1 of warp 0: sum of their dl
+  const float bias = a.b2[lane & 1];
+  int par = 0;
+  for (int r0 = blockIdx.x * EH_R; r0 < a.B; r0 += gridDim.x * EH_R, par ^= 1) {
+    // target flag of (row lane>>1, output lane&1): issued before the big loads, used after the reduction
+    const int rb = r0 + (lane >> 1);
+    float tgt = 0.f;
+    if (lane < 2 * EH_R && rb < a.B) {
+      const uint64_t A = a.adj[rb];
+      tgt = (lane & 1) ? (float)abit(A, a.vi, a.vj) : (float)abit(A, a.vj, a.vi);
+    }
     float e[EH_R][8], part[2 * EH_R];
 #pragma unroll
     for (int r = 0; r < EH_R; ++r) {
@@ -350,36 +362,44 @@ static __global__ void __launch_bounds__(256) k_edge_head_fwd(const EdgeHeadP a)
       float v = part[i];
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-      if (lane == 0) red[wid][i] = v;
+      if (lane == 0) red[par][wid][i] = v;
     }
     __syncthreads();
-    if (t < EH_R) {
-      const int b = r0 + t;
-      float dl[2] = {0.f, 0.f};
-      if (b < a.B) {
-        float l0 = 0.f, l1 = 0.f;
+    float dl = 0.f;
+    if (lane < 2 * EH_R) {
+      float l = 0.f;
 #pragma unroll
-        for (int w = 0; w < 8; ++w) { l0 += red[w][2 * t]; l1 += red[w][2 * t + 1]; }
-        edge_head_row_finish(a, b, l0, l1, dl);
+      for (int w = 0; w < 8; ++w) l += red[par][w][lane];
+      l += bias;
+      const bool ok = rb < a.B;
+      dl = ok ? (sigmoidf_(l) - tgt) * a.inv_batch : 0.f;
+      if (wid == 0) {
+        float bce = ok ? bce_logits(l, tgt) : 0.f;
+        bce += __shfl_down_sync((1u << (2 * EH_R)) - 1u, bce, 1);
+        if (ok) {
+          a.l2[(int64_t)rb * LD_E + (lane & 1)] = l; a.dl2[(int64_t)rb * LD_E + (lane & 1)] = dl;
+          if (!(lane & 1)) a.rowloss[(int64_t)2 * a.B + rb] += bce * a.inv_batch;
+        }
+        dbsum += dl;
       }
-      dls[2 * t] = dl[0]; dls[2 * t + 1] = dl[1];
     }
-    __syncthreads();
     if (a.dW2) {
 #pragma unroll
       for (int r = 0; r < EH_R; ++r) {
-        const float d0 = dls[2 * r], d1 = dls[2 * r + 1];
+        const float d0 = __shfl_sync(0xffffffffu, dl, 2 * r), d1 = __shfl_sync(0xffffffffu, dl, 2 * r + 1);
 #pragma unroll
         for (int k = 0; k < 8; ++k) { acc0[k] = fmaf(d0, e[r][k], acc0[k]); acc1[k] = fmaf(d1, e[r][k], acc1[k]); }
-        if (t == 0) { db0 += d0; db1 += d1; }
       }
     }
-    __syncthreads();
   }
   if (a.dW2) {
 #pragma unroll
     for (int k = 0; k < 8; ++k) { atomicAdd(a.dW2 + c0 + k, acc0[k]); atomicAdd(a.dW2 + 4 * H + c0 + k, acc1[k]); }
-    if (t == 0) { atomicAdd(a.db2, db0); atomicAdd(a.db2 + 1, db1); }
+    if (wid == 0) {                                    // db2[c] = sum over rows: fold lanes of equal parity
+      float v = dbsum;
+      v += __shfl_down_sync(0xffffffffu, v, 4); v += __shfl_down_sync(0xffffffffu, v, 2);
+      if (lane < 2) atomicAdd(a.db2 + lane, v);
+    }
   }
 }
 static void edge_head_fwd(dx_stream_t st, const EdgeHeadP& a) {
@@ -411,20 +431,36 @@ static void edge_head_fwd(dx_stream_t, const EdgeHeadP& a) {
   ++g_launches;
 }
 #endif
-// backward of the head w.r.t. its pre-activation: g = mask * (dl0 W2[0] + dl1 W2[1]) ;  dQ += g ; dU += g
-static void edge_head_bwd(dx_stream_t st, int B, const uint8_t* mask, const float* dl2, const float* W2, float* dQ,
-                          float* dU) {
-  foreach (st, (int64_t)B * 256, [=] DX_HD(int64_t idx) {
-    const int64_t b = idx >> 8; const int c0 = (int)(idx & 255) * 8;
-    const unsigned m = mask[idx];
-    const float d0 = dl2[b * LD_E], d1 = dl2[b * LD_E + 1];
-    float g[8];
-    for (int k = 0; k < 8; ++k) g[k] = ((m >> k) & 1u) ? d0 * W2[c0 + k] + d1 * W2[4 * H + c0 + k] : 0.f;
-    float* q = dQ + b * 4 * H + c0; float* u = dU + b * 4 * H + c0;
-    float4 q0 = ld4f(q), q1 = ld4f(q + 4), u0 = ld4f(u), u1 = ld4f(u + 4);
-    q0.x += g[0]; q0.y += g[1]; q0.z += g[2]; q0.w += g[3]; q1.x += g[4]; q1.y += g[5]; q1.z += g[6]; q1.w += g[7];
-    u0.x += g[0]; u0.y += g[1]; u0.z += g[2]; u0.w += g[3]; u1.x += g[4]; u1.y += g[5]; u1.z += g[6]; u1.w += g[7];
-    st4f(q, q0); st4f(q + 4, q1); st4f(u, u0); st4f(u + 4, u1);
+// Backward of the heads w.r.t. their pre-activations.  A head gradient is rank-2 under its relu mask,
+//   g_t[b,:] = mask_t[b,:] * (dl0_t[b] W2[0,:] + dl1_t[b] W2[1,:]),
+// so sums of them (dQ of a finished node over its later readers; dU of a node state over the heads that
+// read that state) are re-formed from the 256 B/row masks where they are consumed instead of being
+// accumulated through HBM (8 KB/row read-modify-write per step and buffer).
+//   out[m,:] = sum_k g_{step k}[b,:]   over the listed steps, b = rows ? rows[m] : m ;
+//   until_active: stop after the first listed step at which graph b adds an edge to node vi
+//   (that step replaces the state, so earlier-listed heads are the only readers of this version).
+struct HeadSumP {
+  int M; const int* rows; const uint64_t* adj; int vi; int n; int until_active;
+  const uint8_t* mask[6]; const float* dl[6]; int vj[6];
+  const float* W2; float* out;
+};
+static void head_sum(dx_stream_t st, const HeadSumP& a) {
+  foreach (st, (int64_t)a.M * 256, [=] DX_HD(int64_t idx) {
+    const int m = (int)(idx >> 8); const int tc = (int)(idx & 255), c0 = tc * 8;
+    const int64_t b = a.rows ? a.rows[m] : m;
+    const uint64_t A = a.adj[b];
+    const float4 wa0 = ld4f(a.W2 + c0), wa1 = ld4f(a.W2 + c0 + 4), wb0 = ld4f(a.W2 + 4 * H + c0), wb1 = ld4f(a.W2 + 4 * H + c0 + 4);
+    const float w0[8] = {wa0.x, wa0.y, wa0.z, wa0.w, wa1.x, wa1.y, wa1.z, wa1.w};
+    const float w1[8] = {wb0.x, wb0.y, wb0.z, wb0.w, wb1.x, wb1.y, wb1.z, wb1.w};
+    float g[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    for (int k = 0; k < a.n; ++k) {
+      const unsigned mk = a.mask[k][b * 256 + tc];
+      const float d0 = a.dl[k][b * LD_E], d1 = a.dl[k][b * LD_E + 1];
+      for (int e = 0; e < 8; ++e) g[e] += ((mk >> e) & 1u) ? d0 * w0[e] + d1 * w1[e] : 0.f;
+      if (a.until_active && (abit(A, a.vj[k], a.vi) | abit(A, a.vi, a.vj[k]))) break;
+    }
+    float* o = a.out + (int64_t)m * 4 * H + c0;
+    st4f(o, make_float4(g[0], g[1], g[2], g[3])); st4f(o + 4, make_float4(g[4], g[5], g[6], g[7]));
   });
 }
 
@@ -610,7 +646,7 @@ void decode_bwd_impl(dx_stream_t st, const Weights& W, const Weights& G, int B, 
   zero_async(st, w.dHd, sizeof(float) * 7 * bH);
   zero_async(st, w.dPg, sizeof(float) * 6 * (size_t)B * 2 * H);
   zero_async(st, w.dPm, sizeof(float) * 6 * (size_t)B * 2 * H);
-  zero_async(st, w.dQ, sizeof(float) * 6 * (size_t)B * 4 * H);
+  if (!bt.step_ptr) zero_async(st, w.dQ, sizeof(float) * 6 * (size_t)B * 4 * H);   // (compacted steps store dQ whole)
   zero_async(st, w.dgb, sizeof(float) * 6 * bH);
   for (int k = 0; k < 3; ++k) zero_async(st, w.dWihP[k], sizeof(float) * G3 * XP);
   mask_features(st, (int64_t)7 * B, B, nullptr, 0, adj, bt.Xn, w.XL);
@@ -624,38 +660,60 @@ void decode_bwd_impl(dx_stream_t st, const Weights& W, const Weights& G, int B, 
     zero_async(st, w.dHrun, sizeof(float) * bH);
     const bool compact = bt.step_ptr != nullptr;
     if (compact) {
-      // dHi is the running gradient of the node's current state, dU (= dE1 buffer) that of U; a step
-      // consumes and clears both on its active rows (their pre-step values only feed earlier heads).
-      float* dU = w.dE1;
-      zero_async(st, dU, sizeof(float) * (size_t)B * 4 * H);
+      // dHi is the running gradient of the node's current state; a step consumes and clears it on its
+      // active rows.  The gradient of U (the state's edge-head product) is never materialised for all
+      // graphs: the version of U written by step (vi,vj) is read by the heads (vi,vj-1), (vi,vj-2), ... up to
+      // and including the graph's next active step, and head_sum re-forms exactly that sum for the active rows.
+      auto head_list = [&](HeadSumP& hs, int vj_first) {     // heads (vi, vj_first), (vi, vj_first-1), ..., (vi, 0)
+        hs.n = 0;
+        for (int x = vj_first; x >= 0; --x, ++hs.n) {
+          const int tx = t0 + (vi - 1 - x);
+          hs.mask[hs.n] = reinterpret_cast<const uint8_t*>(w.E1[tx]); hs.dl[hs.n] = w.dl2[tx]; hs.vj[hs.n] = x;
+        }
+      };
       for (int vj = 0; vj < vi; ++vj) {
         const int t = t0 + (vi - 1 - vj);
         const int n = bt.step_ptr[t + 1] - bt.step_ptr[t];
-        if (n > 0) {
-          const int* rows = bt.step_rows + bt.step_ptr[t];
-          RowMap rc{n, B, rows, vi * B};
-          gather_rows(st, n, 4 * H, rows, dU, w.UC, 1);
-          gather_rows(st, n, H, rows, w.dHi, w.dHiC, 1);
+        if (n <= 0) continue;
+        const int* rows = bt.step_rows + bt.step_ptr[t];
+        RowMap rc{n, B, rows, vi * B};
+        gather_rows(st, n, H, rows, w.dHi, w.dHiC, 1);
+        if (vj > 0) {                                        // (the last step's state feeds no later head)
+          HeadSumP hs{n, rows, adj, vi, 0, 1, {}, {}, {}, W[P_E_W2], w.UC};
+          head_list(hs, vj - 1);
+          head_sum(st, hs);
           linear_dgrad(st, n, 4 * H, H, w.UC, 4 * H, W[P_E_W0], 2 * H, w.dHiC, H, ACC_ADD);
           linear_wgrad(st, n, 4 * H, H, w.UC, 4 * H, w.Hi[t], H, G[P_E_W0], 2 * H);
-          looper_bwd(st, W, G, B, vi, rc, w.dHiC, w.g_l[t], w.Hc[t], S_SELF, adj, Xi, w, w.dHc, false);
-          CellBwd cc{rc, w.dHc, 0, w.g_c[t], 0, w.Hin[t], 0, w.dgx, nullptr, w.dgh, w.dHin, S_ONE, adj};
-          cell_bwd(st, cc, G[P_CD_BIH], G[P_CD_BHH]);
-          linear_dgrad(st, n, G3, H, w.dgh, G3, W[P_CD_WHH], H, w.dHin, H, ACC_ADD);
-          linear_wgrad(st, n, G3, H, w.dgh, G3, w.Hin[t], H, G[P_CD_WHH], H);
-          gather_rows(st, n, XP, rows, const_cast<float*>(Xi), w.xc, 0);
-          linear_wgrad(st, n, G3, XP, w.dgx, G3, w.xc, XP, w.dWihP[0], XP);
-          scatter_rows(st, n, H, rows, w.dHin, w.dHrun, 1);
-          RowMap rs{n, B, rows, vj * B};
-          MsgBwd mb{rs, w.Pg, w.Pm, W[P_G_B], adj, w.dHrun, 0, w.dPg, w.dPm, w.dgb, 1, vi, vi, 1};
-          msg_bwd(st, mb);
         }
-        // (dW2 / db2 of this head were accumulated by the fused forward kernel)
-        edge_head_bwd(st, B, reinterpret_cast<const uint8_t*>(w.E1[t]), w.dl2[t], W[P_E_W2], w.dQ + (size_t)vj * B * 4 * H, dU);
+        looper_bwd(st, W, G, B, vi, rc, w.dHiC, w.g_l[t], w.Hc[t], S_SELF, adj, Xi, w, w.dHc, false);
+        CellBwd cc{rc, w.dHc, 0, w.g_c[t], 0, w.Hin[t], 0, w.dgx, nullptr, w.dgh, w.dHin, S_ONE, adj};
+        cell_bwd(st, cc, G[P_CD_BIH], G[P_CD_BHH]);
+        linear_dgrad(st, n, G3, H, w.dgh, G3, W[P_CD_WHH], H, w.dHin, H, ACC_ADD);
+        linear_wgrad(st, n, G3, H, w.dgh, G3, w.Hin[t], H, G[P_CD_WHH], H);
+        gather_rows(st, n, XP, rows, const_cast<float*>(Xi), w.xc, 0);
+        linear_wgrad(st, n, G3, XP, w.dgx, G3, w.xc, XP, w.dWihP[0], XP);
+        scatter_rows(st, n, H, rows, w.dHin, w.dHrun, 1);
+        RowMap rs{n, B, rows, vj * B};
+        MsgBwd mb{rs, w.Pg, w.Pm, W[P_G_B], adj, w.dHrun, 0, w.dPg, w.dPm, w.dgb, 1, vi, vi, 1};
+        msg_bwd(st, mb);
       }
-      // what is left in dU belongs to U = Hi_p2 W^T (the state every graph had before its first edge)
+      // U = Hi_p2 W^T (the state every graph had before its first edge): read by the heads up to the first active step
+      float* dU = w.dE1;
+      HeadSumP hs{B, nullptr, adj, vi, 0, 1, {}, {}, {}, W[P_E_W2], dU};
+      head_list(hs, vi - 1);
+      head_sum(st, hs);
       linear_wgrad(st, B, 4 * H, H, dU, 4 * H, w.Hi_p2[vi], H, G[P_E_W0], 2 * H);
       linear_dgrad(st, B, 4 * H, H, dU, 4 * H, W[P_E_W0], 2 * H, w.dHi, H, ACC_ADD);
+      // dQ of node j = vi-1 (consumed below): heads (vi', j) of every later node vi' (all of them are done)
+      {
+        const int j = vi - 1;
+        HeadSumP hq{B, nullptr, adj, vi, 0, 0, {}, {}, {}, W[P_E_W2], w.dQ + (size_t)j * B * 4 * H};
+        for (int v2 = NN - 1; v2 > j; --v2, ++hq.n) {
+          const int tx = v2 * (v2 - 1) / 2 + (v2 - 1 - j);
+          hq.mask[hq.n] = reinterpret_cast<const uint8_t*>(w.E1[tx]); hq.dl[hq.n] = w.dl2[tx]; hq.vj[hq.n] = j;
+        }
+        head_sum(st, hq);
+      }
     } else
     for (int vj = 0; vj < vi; ++vj) {
       const int t = t0 + (vi - 1 - vj);

@@ -1,0 +1,20 @@
+#!/bin/bash
+# Full evidence pass for the current tree (1 GPU): smoke, GPU parity tests, default bench, the ncu launch
+# list of the benchmark's step at the benchmark micro-batch and one --set full capture of the top GEMM.
+# Every ncu pass runs only after the same command exited 0 without ncu.  Outputs in gpurun_out/.
+mkdir -p gpurun_out
+TAG=${TAG:-cur}
+echo "== smoke"; timeout 600 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke_$TAG.log 2>&1; echo "smoke rc=$?"; tail -3 gpurun_out/smoke_$TAG.log
+echo "== tests"; timeout 1500 python -m pytest tests -m gpu -q --tb=short -p no:cacheprovider > gpurun_out/tests_$TAG.log 2>&1; echo "tests rc=$?"; tail -15 gpurun_out/tests_$TAG.log
+echo "== bench"; timeout 900 python bench.py > gpurun_out/bench_$TAG.json 2> gpurun_out/bench_$TAG.err; echo "bench rc=$?"; cat gpurun_out/bench_$TAG.json; tail -5 gpurun_out/bench_$TAG.err
+if [ -n "$PROFILE" ]; then
+CMD="python bench.py --steps 1 --warmup 1 --no-cpu --no-extra --micro-batch ${MB:-32768}"
+$CMD > gpurun_out/prof_plain_$TAG.log 2>&1 &&
+timeout 1200 ncu --metrics gpu__time_duration.sum --clock-control none -s ${SKIP:-1100} -c ${COUNT:-1000} --csv \
+    --log-file gpurun_out/launches_$TAG.csv $CMD > gpurun_out/ncu_launches_$TAG.log 2>&1
+echo "launch list rc=$?"
+$CMD > gpurun_out/prof_plain2_$TAG.log 2>&1 &&
+timeout 1200 ncu --set full --clock-control none --import-source on -k regex:k_tc_gemm -s ${GSKIP:-600} -c ${GCOUNT:-12} \
+    -o gpurun_out/prof_tc_$TAG -f $CMD > gpurun_out/ncu_full_$TAG.log 2>&1
+echo "full rc=$?"
+fi
