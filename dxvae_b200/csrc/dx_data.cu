@@ -183,23 +183,24 @@ int batch_schedule(dx_stream_t, int64_t B, const uint64_t* adj, uint8_t* level, 
 // active at step t.
 DX_HD DX_INLINE int step_vi(int t) { int vi = 1; while ((vi + 1) * vi / 2 <= t) ++vi; return vi; }
 DX_HD DX_INLINE bool step_active(uint64_t A, int t) {
+  if (t >= 21) return abit(A, t - 20, t - 20) != 0;     // lists 21..26: self-loop on node 1..6
   const int vi = step_vi(t), vj = vi - 1 - (t - vi * (vi - 1) / 2);
   return (abit(A, vj, vi) | abit(A, vi, vj)) != 0;
 }
 
 static void steps_host(int64_t B, const uint64_t* adj, int32_t* step_ptr, int32_t* step_rows) {
   int64_t pos = 0;
-  for (int t = 0; t < 21; ++t) {
+  for (int t = 0; t < 27; ++t) {
     step_ptr[t] = (int32_t)pos;
     for (int64_t b = 0; b < B; ++b)
       if (step_active(adj[b], t)) step_rows[pos++] = (int32_t)b;
   }
-  step_ptr[21] = (int32_t)pos;
+  step_ptr[27] = (int32_t)pos;
 }
 
 #ifndef DX_EMU
 namespace {
-constexpr int NSTEPB = 21;
+constexpr int NSTEPB = 27;
 __global__ void __launch_bounds__(SCH_T) k_steps_count(int64_t B, const uint64_t* __restrict__ adj,
                                                        int32_t* __restrict__ counts, int nblk) {
   __shared__ int cnt[NSTEPB];
@@ -254,7 +255,7 @@ __global__ void __launch_bounds__(SCH_T) k_steps_scatter(int64_t B, const uint64
 
 int batch_steps(dx_stream_t st, int64_t B, const uint64_t* adj, int32_t* step_ptr, int32_t* step_rows,
                 int32_t* step_ptr_host, void* ws, size_t ws_bytes) {
-  DX_CHECK(B > 0 && (int64_t)21 * B < (1ll << 31), "batch_steps: bad batch size");
+  DX_CHECK(B > 0 && (int64_t)27 * B < (1ll << 31), "batch_steps: bad batch size");
   const int nblk = (int)((B + SCH_T - 1) / SCH_T);
   Arena ar(ws, ws_bytes);
   int32_t* counts = ar.take<int32_t>((size_t)NSTEPB * nblk);
@@ -263,7 +264,7 @@ int batch_steps(dx_stream_t st, int64_t B, const uint64_t* adj, int32_t* step_pt
   k_steps_scan<<<1, 32, 0, st>>>(counts, nblk, step_ptr);
   k_steps_scatter<<<nblk, SCH_T, 0, st>>>(B, adj, counts, nblk, step_rows);
   g_launches += 3;
-  cudaMemcpyAsync(step_ptr_host, step_ptr, 22 * sizeof(int32_t), cudaMemcpyDeviceToHost, st);
+  cudaMemcpyAsync(step_ptr_host, step_ptr, 28 * sizeof(int32_t), cudaMemcpyDeviceToHost, st);
   cudaStreamSynchronize(st);
   return check_launch("batch_steps");
 }
@@ -271,7 +272,7 @@ int batch_steps(dx_stream_t st, int64_t B, const uint64_t* adj, int32_t* step_pt
 int batch_steps(dx_stream_t, int64_t B, const uint64_t* adj, int32_t* step_ptr, int32_t* step_rows,
                 int32_t* step_ptr_host, void*, size_t) {
   steps_host(B, adj, step_ptr, step_rows);
-  memcpy(step_ptr_host, step_ptr, 22 * sizeof(int32_t));
+  memcpy(step_ptr_host, step_ptr, 28 * sizeof(int32_t));
   return 0;
 }
 #endif

@@ -533,11 +533,24 @@ void decode_fwd_impl(dx_stream_t st, const Weights& W, int B, const float* z, co
     if (train) loss_edge(st, B, vi, vi, w.ls[vi], 1, adj, io.lw, w.rowloss, w.dls[vi]);
     else decide_edges(st, B, vi, vi, w.ls[vi], 1, io.adj_out, io.margins);
     // P2 (model.py:240/337): same H_in = 0, x_loop = s*x
-    CellFwd p2{rm, w.gxl[vi], w.ghl0, W[P_LD_BIH], W[P_LD_BHH], w.Hc0[vi], 0, w.Hi_p2[vi], 0, train ? w.g_p2[vi] : nullptr,
-               0, S_SELF, adj};
-    cell_fwd(st, p2);
-    zero_async(st, w.Hrun, sizeof(float) * (size_t)B * H);
     const bool compact = train && io.bt->step_ptr != nullptr;
+    if (compact) {
+      // x_loop = s*x: P2 repeats P1 exactly on graphs without a self-loop on vi, so it is computed on the
+      // self-loop rows only (schedule list NSTEP+vi-1); their gates are stored compactly.
+      copy_async(st, w.Hi_p2[vi], w.Hi_p1[vi], sizeof(float) * (size_t)B * H);
+      const int ts = NSTEP + vi - 1, ns = io.bt->step_ptr[ts + 1] - io.bt->step_ptr[ts];
+      if (ns > 0) {
+        RowMap rs{ns, B, io.bt->step_rows + io.bt->step_ptr[ts], vi * B};
+        CellFwd p2{rs, w.gxl[vi], w.ghl0, W[P_LD_BIH], W[P_LD_BHH], w.Hc0[vi], 0, w.UC, 0, w.g_p2[vi], 0, S_SELF, adj};
+        p2.gx_by_graph = 1; p2.gh_by_graph = 1; p2.hprev_by_graph = 1; p2.hout2 = w.Hi_p2[vi];
+        cell_fwd(st, p2);
+      }
+    } else {
+      CellFwd p2{rm, w.gxl[vi], w.ghl0, W[P_LD_BIH], W[P_LD_BHH], w.Hc0[vi], 0, w.Hi_p2[vi], 0, train ? w.g_p2[vi] : nullptr,
+                 0, S_SELF, adj};
+      cell_fwd(st, p2);
+    }
+    zero_async(st, w.Hrun, sizeof(float) * (size_t)B * H);
     if (compact) {
       // Compacted teacher forcing (DESIGN.md "identity steps"): a re-propagate changes node vi only for
       // graphs where the step adds an edge.  Hd[vi] holds the CURRENT state of node vi for every
@@ -607,12 +620,10 @@ static void mlp3_bwd(dx_stream_t st, const Weights& W, const Weights& G, int B, 
                      const float* A1, const float* A2, const float* dL, const DecWs& w, float* dhin) {
   linear_wgrad(st, B, nout, 2 * H, dL, LD_L, A2, 2 * H, G[w0 + 4], 2 * H);
   colsum_accum(st, B, nout, dL, LD_L, G[w0 + 5]);
-  linear_dgrad(st, B, nout, 2 * H, dL, LD_L, W[w0 + 4], 2 * H, w.dA2, 2 * H, ACC_STORE);
-  relu_mask(st, (int64_t)B * 2 * H / 4, w.dA2, A2);
+  linear_dgrad(st, B, nout, 2 * H, dL, LD_L, W[w0 + 4], 2 * H, w.dA2, 2 * H, ACC_STORE, nullptr, nullptr, A2, 2 * H);   // relu backward fused
   linear_wgrad(st, B, 2 * H, 2 * H, w.dA2, 2 * H, A1, 2 * H, G[w0 + 2], 2 * H);
   colsum_accum(st, B, 2 * H, w.dA2, 2 * H, G[w0 + 3]);
-  linear_dgrad(st, B, 2 * H, 2 * H, w.dA2, 2 * H, W[w0 + 2], 2 * H, w.dA1, 2 * H, ACC_STORE);
-  relu_mask(st, (int64_t)B * 2 * H / 4, w.dA1, A1);
+  linear_dgrad(st, B, 2 * H, 2 * H, w.dA2, 2 * H, W[w0 + 2], 2 * H, w.dA1, 2 * H, ACC_STORE, nullptr, nullptr, A1, 2 * H);
   linear_wgrad(st, B, 2 * H, H, w.dA1, 2 * H, hin, H, G[w0], H);
   colsum_accum(st, B, 2 * H, w.dA1, 2 * H, G[w0 + 1]);
   linear_dgrad(st, B, 2 * H, H, w.dA1, 2 * H, W[w0], H, dhin, H, ACC_ADD);
@@ -738,15 +749,30 @@ void decode_bwd_impl(dx_stream_t st, const Weights& W, const Weights& G, int B, 
       linear_dgrad(st, B, 4 * H, H, w.dE1, 4 * H, W[P_E_W0], 2 * H, w.dHi, H, ACC_STORE);
     }
     // dHi now holds the gradient of Hi_p2.  P2 and P1 share Hc0.
-    looper_bwd(st, W, G, B, vi, rm, w.dHi, w.g_p2[vi], w.Hc0[vi], S_SELF, adj, Xi, w, w.dHc0, false);
+    int ns = 0; const int* rows_s = nullptr;
+    if (compact) {
+      // P2 ran on the self-loop rows only: their gradient goes through P2's looper (compact), every other
+      // row's gradient passes straight to Hi_p1 (Hi_p2 == Hi_p1 there) and joins the self-loop head's.
+      const int ts = NSTEP + vi - 1;
+      ns = bt.step_ptr[ts + 1] - bt.step_ptr[ts]; rows_s = bt.step_rows + bt.step_ptr[ts];
+      if (ns > 0) {
+        RowMap rs{ns, B, rows_s, vi * B};
+        gather_rows(st, ns, H, rows_s, w.dHi, w.dHiC, 1);
+        gather_rows(st, ns, H, rows_s, w.Hc0[vi], w.Hrun, 0);          // (Hrun is free scratch in the backward pass)
+        looper_bwd(st, W, G, B, vi, rs, w.dHiC, w.g_p2[vi], w.Hrun, S_SELF, adj, Xi, w, w.dHc, false);
+      }
+    } else {
+      looper_bwd(st, W, G, B, vi, rm, w.dHi, w.g_p2[vi], w.Hc0[vi], S_SELF, adj, Xi, w, w.dHc0, false);
+    }
     // self-loop head consumed Hi_p1
     linear_wgrad(st, B, 1, 2 * H, w.dls[vi], LD_E, w.ES1[vi], 2 * H, G[P_ES_W2], 2 * H);
     colsum_accum(st, B, 1, w.dls[vi], LD_E, G[P_ES_B2]);
     relu_head_bwd(st, B, 2 * H, 1, w.ES1[vi], w.dls[vi], LD_E, W[P_ES_W2], w.dES1, nullptr);
     linear_wgrad(st, B, 2 * H, H, w.dES1, 2 * H, w.Hi_p1[vi], H, G[P_ES_W0], H);
     colsum_accum(st, B, 2 * H, w.dES1, 2 * H, G[P_ES_B0]);
-    linear_dgrad(st, B, 2 * H, H, w.dES1, 2 * H, W[P_ES_W0], H, w.dHi, H, ACC_STORE);
-    looper_bwd(st, W, G, B, vi, rm, w.dHi, w.g_p1[vi], w.Hc0[vi], S_ZERO, adj, Xi, w, w.dHc0, true);
+    linear_dgrad(st, B, 2 * H, H, w.dES1, 2 * H, W[P_ES_W0], H, w.dHi, H, compact ? ACC_ADD : ACC_STORE);
+    looper_bwd(st, W, G, B, vi, rm, w.dHi, w.g_p1[vi], w.Hc0[vi], S_ZERO, adj, Xi, w, w.dHc0, !compact);
+    if (ns > 0) scatter_rows(st, ns, H, rows_s, w.dHc, w.dHc0, 1);
     // combiner with H_in = 0: only input weights / biases receive gradient
     CellBwd c0{rm, w.dHc0, 0, w.g_c0[vi], 0, nullptr, 0, w.dgx, nullptr, w.dgh, nullptr, S_ONE, adj};
     cell_bwd(st, c0, G[P_CD_BIH], G[P_CD_BHH]);

@@ -22,9 +22,10 @@ struct Batch {       // what the batcher produces (device pointers except level_
   int n_levels;
   const int32_t* level_ptr;   // HOST, n_levels+1
   const int32_t* level_rows;  // device, 6B
-  // optional decoder step schedule (teacher forcing): rows active at each of the 21 (vi,vj) steps
-  const int32_t* step_ptr = nullptr;    // HOST, 22
-  const int32_t* step_rows = nullptr;   // device, step_ptr[21] graph ids
+  // optional decoder step schedule (teacher forcing): rows active at each of the 21 (vi,vj) steps, then
+  // (lists 21..26) the graphs with a self-loop on node vi = 1..6 (the only rows where P2 differs from P1)
+  const int32_t* step_ptr = nullptr;    // HOST, NLIST+1
+  const int32_t* step_rows = nullptr;   // device, step_ptr[NLIST] graph ids
 };
 
 struct LossW { float w_env, w_frq, w_kld, inv_batch; };
@@ -45,6 +46,7 @@ struct EncWs {
 };
 constexpr int LD_L = 64;  // leading dimension of logit buffers (55 / 27 columns used)
 constexpr int NSTEP = 21;
+constexpr int NLIST = NSTEP + 6;   // step-schedule lists: 21 edge steps + 6 self-loop row lists
 constexpr int LD_E = 4;    // leading dimension of the edge-head logit buffers (1 or 2 columns used; 16-byte rows for TMA)
 
 struct DecWs {

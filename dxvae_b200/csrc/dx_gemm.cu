@@ -203,8 +203,11 @@ __global__ void __launch_bounds__(256, (BM >= 128 ? 2 : 3)) k_gemm(const GemmP p
         float t = acc[i][g * 4 + c];
         if (gj + c < p.N) {
           if (p.bias) t += __ldg(p.bias + gj + c);
-          if (arow_p) t += __ldg(arow_p + gj + c);
-          t = apply_act(t, p.act);
+          if (p.act == ACT_GATE) t = __ldg(arow_p + gj + c) > 0.f ? t : 0.f;
+          else {
+            if (arow_p) t += __ldg(arow_p + gj + c);
+            t = apply_act(t, p.act);
+          }
         }
         v[c] = t;
       }
@@ -398,7 +401,8 @@ void gemm(dx_stream_t, const GemmP& p) {
         acc = fmaf(a, b, acc);
       }
       if (p.bias) acc += p.bias[j];
-      if (p.add) acc += p.add[(int64_t)i * p.ldadd + j];
+      if (p.act == ACT_GATE) acc = p.add[(int64_t)i * p.ldadd + j] > 0.f ? acc : 0.f;
+      else if (p.add) acc += p.add[(int64_t)i * p.ldadd + j];
       if (p.act == ACT_RELU) acc = acc > 0.f ? acc : 0.f;
       else if (p.act == ACT_TANH) acc = tanhf(acc);
       else if (p.act == ACT_SOFTPLUS) acc = softplusf_(acc);

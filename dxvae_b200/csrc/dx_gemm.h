@@ -16,7 +16,8 @@
 
 namespace dx {
 
-enum { ACT_NONE = 0, ACT_RELU = 1, ACT_TANH = 2, ACT_SOFTPLUS = 4 };
+enum { ACT_NONE = 0, ACT_RELU = 1, ACT_TANH = 2, ACT_SOFTPLUS = 4,
+       ACT_GATE = 8 };   // `add` is not added but gates the result: C = add[i,j] > 0 ? acc : 0  (relu backward fused into dgrad)
 enum { ACC_STORE = 0, ACC_ADD = 1, ACC_ATOMIC = 2 };
 
 struct GemmP {
@@ -67,9 +68,11 @@ inline void linear_fwd(dx_stream_t s, int M, int N, int K, const float* x, int64
 // dx[M,K] (+)= dy[M,N] W[N,K]
 inline void linear_dgrad(dx_stream_t s, int M, int N, int K, const float* dy, int64_t lddy, const float* W,
                          int64_t ldw, float* dx_, int64_t lddx, int accum, const int* dy_idx = nullptr,
-                         const int* dx_idx = nullptr) {
+                         const int* dx_idx = nullptr, const float* relu_out = nullptr, int64_t ldrelu = 0) {
   GemmP p; p.M = M; p.N = K; p.K = N; p.A = dy; p.lda = lddy; p.a_kc = true; p.a_idx = dy_idx;
-  p.B = W; p.ldb = ldw; p.b_kc = false; p.C = dx_; p.ldc = lddx; p.c_idx = dx_idx; p.accum = accum; gemm(s, p);
+  p.B = W; p.ldb = ldw; p.b_kc = false; p.C = dx_; p.ldc = lddx; p.c_idx = dx_idx; p.accum = accum;
+  if (relu_out) { p.add = relu_out; p.ldadd = ldrelu; p.act = ACT_GATE; }   // dx = (relu_out > 0) * (dy W)
+  gemm(s, p);
 }
 // dW[N,K] += dy[M,N]^T x[M,K]   (atomic accumulation; caller zero-initialises dW)
 inline void linear_wgrad(dx_stream_t s, int M, int N, int K, const float* dy, int64_t lddy, const float* x,

@@ -38,6 +38,8 @@ struct CellFwd {
   int smode; const uint64_t* adj;
   int gx_by_graph = 0;        // 1: gx is [B,1536] indexed by the row's graph b (= r % B), not by m
   float* hout2 = nullptr;     // optional second copy of h', [B,512] indexed by b (current state of the node)
+  int gh_by_graph = 0;        // 1: gh is [B,1536] indexed by the row's graph b
+  int hprev_by_graph = 0;     // 1: hprev is [B,512] indexed by the row's graph b
 };
 
 inline void cell_fwd(dx_stream_t st, const CellFwd& a) {
@@ -50,8 +52,8 @@ inline void cell_fwd(dx_stream_t st, const CellFwd& a) {
     const float* gx = a.gx + (int64_t)(a.gx_by_graph ? r % a.rm.B : m) * G3 + n;
     const float4 xr = ld4f(gx), xz = ld4f(gx + H), xn = ld4f(gx + 2 * H);
     float4 hr = f4zero(), hz = f4zero(), hn = f4zero(), hp = f4zero();
-    if (a.gh) { const float* gh = a.gh + (int64_t)m * G3 + n; hr = ld4f(gh); hz = ld4f(gh + H); hn = ld4f(gh + 2 * H); }
-    if (a.hprev) hp = ld4f(a.hprev + (int64_t)(a.hprev_global ? r : m) * H + n);
+    if (a.gh) { const float* gh = a.gh + (int64_t)(a.gh_by_graph ? r % a.rm.B : m) * G3 + n; hr = ld4f(gh); hz = ld4f(gh + H); hn = ld4f(gh + 2 * H); }
+    if (a.hprev) hp = ld4f(a.hprev + (int64_t)(a.hprev_by_graph ? r % a.rm.B : (a.hprev_global ? r : m)) * H + n);
     const float4 bir = ld4f(a.bih + n), biz = ld4f(a.bih + H + n), bin = ld4f(a.bih + 2 * H + n);
     const float4 bhr = ld4f(a.bhh + n), bhz = ld4f(a.bhh + H + n), bhn = ld4f(a.bhh + 2 * H + n);
     float4 R, Zg, Ng, NH, O;

@@ -166,7 +166,10 @@ __device__ __forceinline__ void tc_epilogue(const TcParams& p, const CUtensorMap
           float a0, a1, a2, a3;
           asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(a0), "=f"(a1), "=f"(a2), "=f"(a3)
                        : "r"(sl + (uint32_t)(((j ^ (lane & 7)) << 4))) : "memory");
-          v[4 * j] += a0; v[4 * j + 1] += a1; v[4 * j + 2] += a2; v[4 * j + 3] += a3;
+          if (p.act == ACT_GATE) {
+            v[4 * j] = a0 > 0.f ? v[4 * j] : 0.f; v[4 * j + 1] = a1 > 0.f ? v[4 * j + 1] : 0.f;
+            v[4 * j + 2] = a2 > 0.f ? v[4 * j + 2] : 0.f; v[4 * j + 3] = a3 > 0.f ? v[4 * j + 3] : 0.f;
+          } else { v[4 * j] += a0; v[4 * j + 1] += a1; v[4 * j + 2] += a2; v[4 * j + 3] += a3; }
         }
       } else if (p.add) {
         if (row_ok) {
@@ -175,11 +178,15 @@ __device__ __forceinline__ void tc_epilogue(const TcParams& p, const CUtensorMap
 #pragma unroll
             for (int j = 0; j < 32; j += 4) {
               const float4 a4 = __ldg(reinterpret_cast<const float4*>(ar + j));
-              v[j] += a4.x; v[j + 1] += a4.y; v[j + 2] += a4.z; v[j + 3] += a4.w;
+              if (p.act == ACT_GATE) {
+                v[j] = a4.x > 0.f ? v[j] : 0.f; v[j + 1] = a4.y > 0.f ? v[j + 1] : 0.f;
+                v[j + 2] = a4.z > 0.f ? v[j + 2] : 0.f; v[j + 3] = a4.w > 0.f ? v[j + 3] : 0.f;
+              } else { v[j] += a4.x; v[j + 1] += a4.y; v[j + 2] += a4.z; v[j + 3] += a4.w; }
             }
           } else {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) if (gj + j < p.N) v[j] += __ldg(ar + j);
+            for (int j = 0; j < 32; ++j)
+              if (gj + j < p.N) { const float a1 = __ldg(ar + j); if (p.act == ACT_GATE) v[j] = a1 > 0.f ? v[j] : 0.f; else v[j] += a1; }
           }
         }
       }
@@ -198,7 +205,7 @@ __device__ __forceinline__ void tc_epilogue(const TcParams& p, const CUtensorMap
       if (p.act == ACT_RELU) {
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
-      } else if (p.act != ACT_NONE) {
+      } else if (p.act != ACT_NONE && p.act != ACT_GATE) {
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = tc_act(v[j], p.act);
       }

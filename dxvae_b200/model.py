@@ -169,18 +169,18 @@ class DXVAE(nn.Module):
             d.csr = (indptr, indices[:int(eptr[-1])], eflags[:int(eptr[-1])])
             d.step_ptr = d.step_rows = None
             if need_cls and self.compact_steps:
-                d.step_ptr = np.zeros(22, np.int32)
-                srows = np.zeros(21 * B, np.int32)
+                d.step_ptr = np.zeros(28, np.int32)
+                srows = np.zeros(27 * B, np.int32)
                 _lib.check(L.dxvae_batch_steps_host(B, pv(adj), pv(d.step_ptr), pv(srows)), "dxvae_batch_steps_host")
-                d.step_rows = torch.from_numpy(srows[:max(1, int(d.step_ptr[21]))]).to("cuda")
+                d.step_rows = torch.from_numpy(srows[:max(1, int(d.step_ptr[27]))]).to("cuda")
         else:
             d.adj = gb.adj.to("cuda", torch.int64).contiguous()
             self._schedule(d)
             d.step_ptr = d.step_rows = None
             if need_cls and self.compact_steps:
-                d.step_ptr = np.zeros(22, np.int32)
-                d.step_rows = torch.empty(21 * B, dtype=torch.int32, device="cuda")
-                sp_dev = torch.empty(22, dtype=torch.int32, device="cuda")
+                d.step_ptr = np.zeros(28, np.int32)
+                d.step_rows = torch.empty(27 * B, dtype=torch.int32, device="cuda")
+                sp_dev = torch.empty(28, dtype=torch.int32, device="cuda")
                 ws = self._workspace(_abi.OP_SCHEDULE, B)
                 _lib.check(L.dxvae_batch_steps(B, d.adj.data_ptr(), sp_dev.data_ptr(), d.step_rows.data_ptr(),
                                                d.step_ptr.ctypes.data, ws.data_ptr(), ws.numel(), st), "dxvae_batch_steps")

@@ -38,7 +38,7 @@
 extern "C" {
 #endif
 
-#define DXVAE_ABI_VERSION 1
+#define DXVAE_ABI_VERSION 2
 #define DXVAE_N_NODES 7
 #define DXVAE_N_PARAMS 21
 #define DXVAE_SIZE_X 27
@@ -96,7 +96,9 @@ int dxvae_batch_schedule(int64_t B, const uint64_t* adj, uint8_t* level, int32_t
  * step_rows[step_ptr[t]..step_ptr[t+1]) = ascending ids of the graphs active at step t; passing
  * the schedule to dxvae_elbo_step / dxvae_loss_step makes the identity steps free (results are
  * the same function of the inputs; NULL runs every step on every graph as the reference does).
- * step_ptr: 22 ints; step_rows: up to 21*B ints.  The device form synchronises the stream to
+ * Lists 21..26 hold the graphs with a self-loop on node vi = 1..6: the second propagate of a new node
+ * (model.py:337, x_loop = selfloop * x) differs from the first only on those graphs.
+ * step_ptr: 28 ints; step_rows: up to 27*B ints.  The device form synchronises the stream to
  * return step_ptr_host. */
 int dxvae_batch_steps(int64_t B, const uint64_t* adj, int32_t* step_ptr, int32_t* step_rows, int32_t* step_ptr_host,
                       void* workspace, size_t workspace_bytes, void* stream);

@@ -95,7 +95,7 @@ class Emu:
         B = bt["B"]
         sp = sr = None
         if compact:
-            sp = np.zeros(22, np.int32); sr = np.zeros(21 * B, np.int32)
+            sp = np.zeros(28, np.int32); sr = np.zeros(27 * B, np.int32)
             _abi.check(L, L.dxvae_batch_steps_host(B, ptr(bt["adj"]), ptr(sp), ptr(sr)), "steps")
         ws = np.zeros(L.dxvae_workspace_bytes(_abi.OP_TRAIN, B), np.uint8)
         loss5 = np.zeros(5, np.float32)

@@ -43,7 +43,7 @@ def test_step_schedule_matches_set_logic(setup):
     for edges in (util.random_edge_lists(50, 0.3, 4), util.random_edge_lists(9, 0.0, 5), util.random_edge_lists(9, 1.0, 6)):
         ob = O.batch_oracle(edges)
         B = len(edges)
-        sp = np.zeros(22, np.int32); sr = np.zeros(21 * B, np.int32)
+        sp = np.zeros(28, np.int32); sr = np.zeros(27 * B, np.int32)
         assert L.dxvae_batch_steps_host(B, E_.ptr(ob["adj"]), E_.ptr(sp), E_.ptr(sr)) == 0
         t = 0
         for vi in range(1, 7):
@@ -51,7 +51,11 @@ def test_step_schedule_matches_set_logic(setup):
                 want = [b for b, (s, d) in enumerate(edges) if (vj, vi) in set(zip(s, d)) or (vi, vj) in set(zip(s, d))]
                 assert list(sr[sp[t]:sp[t + 1]]) == want, (vi, vj)
                 t += 1
-        assert sp[21] == sum(sp[i + 1] - sp[i] for i in range(21))
+        for vi in range(1, 7):                       # lists 21..26: graphs with a self-loop on node vi
+            want = [b for b, (s, d) in enumerate(edges) if (vi, vi) in set(zip(s, d))]
+            assert list(sr[sp[t]:sp[t + 1]]) == want, ("self", vi)
+            t += 1
+        assert sp[27] == sum(sp[i + 1] - sp[i] for i in range(27))
 
 
 def test_encode_matches_oracle(setup):

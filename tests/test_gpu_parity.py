@@ -355,9 +355,9 @@ def test_device_step_schedule_matches_set_logic(lib):
     for n, p, seed in ((3000, 0.2, 1), (1, 1.0, 2), (1025, 0.0, 3), (2500, 1.0, 4)):
         E = util.random_edge_lists(n, p, seed)
         adj = torch.tensor([mask_from_edges(*e) for e in E], dtype=torch.int64, device="cuda")
-        sp = np.zeros(22, np.int32)
-        sr = torch.full((21 * n,), -1, dtype=torch.int32, device="cuda")
-        spd = torch.empty(22, dtype=torch.int32, device="cuda")
+        sp = np.zeros(28, np.int32)
+        sr = torch.full((27 * n,), -1, dtype=torch.int32, device="cuda")
+        spd = torch.empty(28, dtype=torch.int32, device="cuda")
         ws = m._workspace(_abi.OP_SCHEDULE, n)
         _lib.check(lib.dxvae_batch_steps(n, adj.data_ptr(), spd.data_ptr(), sr.data_ptr(), sp.ctypes.data, ws.data_ptr(),
                                          ws.numel(), st()), "steps")
@@ -369,6 +369,10 @@ def test_device_step_schedule_matches_set_logic(lib):
                 want = [b for b in range(n) if (vj, vi) in sets[b] or (vi, vj) in sets[b]]
                 assert list(sr[sp[t]:sp[t + 1]]) == want, (vi, vj)
                 t += 1
+        for vi in range(1, 7):
+            want = [b for b in range(n) if (vi, vi) in sets[b]]
+            assert list(sr[sp[t]:sp[t + 1]]) == want, ("self", vi)
+            t += 1
 
 
 def test_compacted_steps_equal_dense_replay(lib):
