@@ -316,7 +316,7 @@ constexpr int EH_R = 4;   // rows per block iteration
 // shared (double-buffered by iteration parity: ONE __syncthreads per iteration) and every warp then
 // finishes the EH_R rows redundantly in its first 2*EH_R lanes (lane = 2*row + output), so no thread
 // waits on a serial tail; warp 0 alone writes the row outputs.
-static __global__ void __launch_bounds__(256) k_edge_head_fwd(const EdgeHeadP a) {
+static __global__ void __launch_bounds__(256, 2) k_edge_head_fwd(const EdgeHeadP a) {
   __shared__ float red[2][8][2 * EH_R];
   const int t = threadIdx.x, lane = t & 31, wid = t >> 5;
   const int c0 = t * 8;
@@ -339,24 +339,32 @@ static __global__ void __launch_bounds__(256) k_edge_head_fwd(const EdgeHeadP a)
       const uint64_t A = a.adj[rb];
       tgt = (lane & 1) ? (float)abit(A, a.vi, a.vj) : (float)abit(A, a.vj, a.vi);
     }
-    float e[EH_R][8], part[2 * EH_R];
+    // all 4*EH_R 128-bit loads of the iteration are issued before anything consumes them (rows past the end
+    // re-read the last row: their dl is forced to 0 and their mask is not stored)
+    float4 lu[EH_R][2], lq[EH_R][2];
 #pragma unroll
     for (int r = 0; r < EH_R; ++r) {
-      const int b = r0 + r;
-      float4 u0 = f4zero(), u1 = f4zero(), q0 = f4zero(), q1 = f4zero();
-      if (b < a.B) {
-        const float* up = a.U + (int64_t)b * 4 * H + c0; const float* qp = a.Q + (int64_t)b * 4 * H + c0;
-        u0 = ld4f(up); u1 = ld4f(up + 4); q0 = ld4f(qp); q1 = ld4f(qp + 4);
-      }
+      const int bb = min(r0 + r, a.B - 1);
+      const float* up = a.U + (int64_t)bb * 4 * H + c0; const float* qp = a.Q + (int64_t)bb * 4 * H + c0;
+      lu[r][0] = ld4f(up); lu[r][1] = ld4f(up + 4); lq[r][0] = ld4f(qp); lq[r][1] = ld4f(qp + 4);
+    }
+    float e[EH_R][8], part[2 * EH_R];
+    unsigned mk[EH_R];
+#pragma unroll
+    for (int r = 0; r < EH_R; ++r) {
+      const float4 u0 = lu[r][0], u1 = lu[r][1], q0 = lq[r][0], q1 = lq[r][1];
       e[r][0] = fmaxf(u0.x + q0.x, 0.f); e[r][1] = fmaxf(u0.y + q0.y, 0.f); e[r][2] = fmaxf(u0.z + q0.z, 0.f);
       e[r][3] = fmaxf(u0.w + q0.w, 0.f); e[r][4] = fmaxf(u1.x + q1.x, 0.f); e[r][5] = fmaxf(u1.y + q1.y, 0.f);
       e[r][6] = fmaxf(u1.z + q1.z, 0.f); e[r][7] = fmaxf(u1.w + q1.w, 0.f);
       float p0 = 0.f, p1 = 0.f; unsigned m = 0;
 #pragma unroll
       for (int k = 0; k < 8; ++k) { p0 = fmaf(e[r][k], w0[k], p0); p1 = fmaf(e[r][k], w1[k], p1); m |= (e[r][k] > 0.f ? 1u : 0u) << k; }
-      if (b < a.B) a.mask[(int64_t)b * 256 + t] = (uint8_t)m;
+      mk[r] = m;
       part[2 * r] = p0; part[2 * r + 1] = p1;
     }
+#pragma unroll
+    for (int r = 0; r < EH_R; ++r)
+      if (r0 + r < a.B) a.mask[(int64_t)(r0 + r) * 256 + t] = (uint8_t)mk[r];
 #pragma unroll
     for (int i = 0; i < 2 * EH_R; ++i) {
       float v = part[i];
@@ -453,11 +461,20 @@ static void head_sum(dx_stream_t st, const HeadSumP& a) {
     const float w0[8] = {wa0.x, wa0.y, wa0.z, wa0.w, wa1.x, wa1.y, wa1.z, wa1.w};
     const float w1[8] = {wb0.x, wb0.y, wb0.z, wb0.w, wb1.x, wb1.y, wb1.z, wb1.w};
     float g[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-    for (int k = 0; k < a.n; ++k) {
-      const unsigned mk = a.mask[k][b * 256 + tc];
-      const float d0 = a.dl[k][b * LD_E], d1 = a.dl[k][b * LD_E + 1];
-      for (int e = 0; e < 8; ++e) g[e] += ((mk >> e) & 1u) ? d0 * w0[e] + d1 * w1[e] : 0.f;
-      if (a.until_active && (abit(A, a.vj[k], a.vi) | abit(A, a.vi, a.vj[k]))) break;
+    // the (at most 6) mask bytes and dl pairs are loaded up front: independent loads, no serial chain
+    unsigned mk[6]; float d0[6], d1[6];
+#pragma unroll
+    for (int k = 0; k < 6; ++k) {
+      const int kk = k < a.n ? k : 0;
+      mk[k] = a.mask[kk][b * 256 + tc]; d0[k] = a.dl[kk][b * LD_E]; d1[k] = a.dl[kk][b * LD_E + 1];
+    }
+    bool live = true;
+#pragma unroll
+    for (int k = 0; k < 6; ++k) {
+      if (k < a.n && live) {
+        for (int e = 0; e < 8; ++e) g[e] += ((mk[k] >> e) & 1u) ? d0[k] * w0[e] + d1[k] * w1[e] : 0.f;
+        if (a.until_active && (abit(A, a.vj[k], a.vi) | abit(A, a.vi, a.vj[k]))) live = false;
+      }
     }
     float* o = a.out + (int64_t)m * 4 * H + c0;
     st4f(o, make_float4(g[0], g[1], g[2], g[3])); st4f(o + 4, make_float4(g[4], g[5], g[6], g[7]));

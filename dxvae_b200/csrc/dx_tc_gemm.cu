@@ -48,6 +48,8 @@ struct TcParams {
   int act, accum, k_chunk;
   int tma_store;    // 1: epilogue stores through TMA (bulk tensor store / reduce-add)
   int add_tma;      // 1: the `add` matrix tile is prefetched into the staging slab by TMA
+  int n_fast;       // tile order: 1 = the N tiles of one M panel are adjacent (concurrent CTAs share the big A panel in L2;
+                    //             the weight-side operand is small and L2-resident anyway), 0 = M fastest
   long long* dbg;   // optional per-phase clock64() trace of CTA (0,0,0): DX_TC_DEBUG=1
 };
 
@@ -319,7 +321,7 @@ __global__ void __launch_bounds__(320, 1) k_tc_gemm(const __grid_constant__ CUte
   if (trace && threadIdx.x == 0) p.dbg[201] = clock64();
 
   auto tile_coords = [&](int t, int& m0, int& n0, int& kbeg, int& nkb) {
-    const int mt = t % gm, nt = (t / gm) % gn, z = t / (gm * gn);     // m fastest: neighbours share the B tile in L2
+    const int mt = p.n_fast ? (t / gn) % gm : t % gm, nt = p.n_fast ? t % gn : (t / gm) % gn, z = t / (gm * gn);
     m0 = mt * TBM; n0 = nt * BN; kbeg = z * p.k_chunk;
     const int kend = min(p.K, kbeg + p.k_chunk);
     nkb = (kend - kbeg + TBK - 1) / TBK;
@@ -494,7 +496,7 @@ k_tc_gemm2(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
   if (trace && threadIdx.x == 0) p.dbg[201] = clock64();
 
   auto tile_coords = [&](int t, int& m0, int& n0, int& kbeg, int& nkb) {
-    const int mt = t % gm2, nt = (t / gm2) % gn, z = t / (gm2 * gn);
+    const int mt = p.n_fast ? (t / gn) % gm2 : t % gm2, nt = p.n_fast ? t % gn : (t / gm2) % gn, z = t / (gm2 * gn);
     m0 = mt * 256 + (int)rank * TBM; n0 = nt * BN; kbeg = z * p.k_chunk;   // this CTA's 128 rows of the pair's tile
     const int kend = min(p.K, kbeg + p.k_chunk);
     nkb = (kend - kbeg + TBK - 1) / TBK;
@@ -644,7 +646,9 @@ bool launch_tc(dx_stream_t s, const GemmP& g, const float* A_lo = nullptr, const
   static const bool want_dbg = getenv("DX_TC_DEBUG") != nullptr;
   if (want_dbg && !dbg) cudaMalloc(&dbg, 256 * sizeof(long long));
   if (want_dbg) cudaMemsetAsync(dbg, 0, 256 * sizeof(long long), s);
-  TcParams p{g.M, g.N, g.K, g.C, g.ldc, g.c_idx, g.bias, g.add, g.ldadd, g.act, g.accum, k_chunk, tma_store ? 1 : 0, add_tma ? 1 : 0, want_dbg ? dbg : nullptr};
+  static const bool m_fast = getenv("DX_TC_M_FAST") != nullptr;
+  TcParams p{g.M, g.N, g.K, g.C, g.ldc, g.c_idx, g.bias, g.add, g.ldadd, g.act, g.accum, k_chunk, tma_store ? 1 : 0, add_tma ? 1 : 0,
+             m_fast ? 0 : 1, want_dbg ? dbg : nullptr};
   static int num_sms = 0;
   if (!num_sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev); }
   const int total_tiles = gm * gn * splits;
@@ -717,8 +721,9 @@ bool launch_tc2(dx_stream_t s, const GemmP& g) {
   static const bool want_dbg = getenv("DX_TC_DEBUG") != nullptr;
   if (want_dbg && !dbg) cudaMalloc(&dbg, 256 * sizeof(long long));
   if (want_dbg) cudaMemsetAsync(dbg, 0, 256 * sizeof(long long), s);
+  static const bool m_fast = getenv("DX_TC_M_FAST") != nullptr;
   TcParams p{g.M, g.N, g.K, g.C, g.ldc, g.c_idx, g.bias, g.add, g.ldadd, g.act, g.accum, k_chunk, 1, add_tma ? 1 : 0,
-             want_dbg ? dbg : nullptr};
+             m_fast ? 0 : 1, want_dbg ? dbg : nullptr};
   static int num_sms = 0;
   if (!num_sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev); }
   const int ncl = total < num_sms / 2 ? total : num_sms / 2;
@@ -761,7 +766,14 @@ bool tc_gemm(dx_stream_t s, const GemmP& g, int* tile_n) {
   // the tensor maps' out-of-bounds zero fill / clipping.
   if (!al16(g.A) || !al16(g.B) || (g.lda % 4) || (g.ldb % 4)) return false;
   if ((double)g.M * g.N * g.K < 1.0e6) return false;          // launch-bound anyway
-  const int bn = g.N >= 192 ? 256 : (g.N >= 96 ? 128 : 64);
+  int bn = g.N >= 192 ? 256 : (g.N >= 96 ? 128 : 64);
+  // Small batches (M of a few hundred rows): a 128 x 256 tiling leaves most SMs idle and each CTA streams a large
+  // slice of the weight matrix alone; narrower tiles spread that stream over more SMs (latency, not throughput).
+  auto ntiles = [&](int b) { return ((g.M + TBM - 1) / TBM) * ((g.N + b - 1) / b); };
+  if (g.accum != ACC_ATOMIC) {
+    if (bn == 256 && ntiles(256) < 48) bn = 128;
+    if (bn == 128 && ntiles(128) < 48) bn = 64;
+  }
   if (tile_n) *tile_n = bn;
   if (bn == 256 && launch_tc2(s, g)) return true;
   return bn == 256 ? launch_tc<256>(s, g) : (bn == 128 ? launch_tc<128>(s, g) : launch_tc<64>(s, g));

@@ -347,6 +347,33 @@ def test_decode_large_batch_properties(lib):
     assert np.abs(back.X.cpu().numpy() - a.X.cpu().numpy()).max() <= 1e-6
 
 
+def test_graph_replayed_step_equals_eager_step(lib):
+    """Small batches replay a captured CUDA graph over a batch-independent schedule (node-order levels,
+    every teacher-forcing step on every graph): same losses and same weights as the eager, compacted step."""
+    from dxvae_b200.train import Trainer
+    idx = list(range(0, 1024, 4))
+    X, P, E, A = util.dataset_graphs(idx)
+    res = {}
+    for mode, gmax in (("graph", 1024), ("eager", 0)):
+        m, _ = make_model(0, 1.0)
+        t = Trainer(m, lr=1e-3, w=(2, 5, 0.01))
+        t.graph_max_batch = gmax
+        data = t.upload(_graphs(X, P, E))
+        g = torch.Generator().manual_seed(5)
+        losses = []
+        for step in range(3):
+            pick = torch.randperm(len(idx), generator=g)[:96].tolist()       # a different batch every step
+            eps = torch.randn(96, 128, generator=g)
+            losses.append(t.step(data, pick, eps=eps).cpu())
+        assert (len(t._graphs) == 1) == (mode == "graph")
+        res[mode] = (torch.stack(losses), m._flat.clone())
+    assert (res["graph"][0] - res["eager"][0]).abs().max().item() <= 1e-5 * res["eager"][0].abs().max().item()
+    # AdamW normalises each gradient element, so elements whose gradient is pure round-off may move by +-lr
+    # either way; everything else must land on the same weight
+    diff = (res["graph"][1] - res["eager"][1]).abs()
+    assert (diff > 2e-6).float().mean().item() <= 1e-4 and diff.max().item() <= 3.1e-3
+
+
 # --------------------------------------------------------------------------- compacted teacher forcing
 def test_device_step_schedule_matches_set_logic(lib):
     from dxvae_b200 import DXVAE, _abi, _lib
