@@ -49,8 +49,13 @@ inline void cell_fwd(dx_stream_t st, const CellFwd& a) {
     float s = 1.f;
     if (a.smode == S_ZERO) s = 0.f;
     else if (a.smode == S_SELF) { const int b = r % a.rm.B, v = r / a.rm.B; s = (float)abit(a.adj[b], v, v); }
-    const float* gx = a.gx + (int64_t)(a.gx_by_graph ? r % a.rm.B : m) * G3 + n;
-    const float4 xr = ld4f(gx), xz = ld4f(gx + H), xn = ld4f(gx + 2 * H);
+    // s == 0 (first propagate of a new node; looper input of a node without a self-loop): s*gx is +-0 whatever
+    // gx holds, so the 6 KB/row input product is not read at all
+    float4 xr = f4zero(), xz = f4zero(), xn = f4zero();
+    if (s != 0.f) {
+      const float* gx = a.gx + (int64_t)(a.gx_by_graph ? r % a.rm.B : m) * G3 + n;
+      xr = ld4f(gx); xz = ld4f(gx + H); xn = ld4f(gx + 2 * H);
+    }
     float4 hr = f4zero(), hz = f4zero(), hn = f4zero(), hp = f4zero();
     if (a.gh) { const float* gh = a.gh + (int64_t)(a.gh_by_graph ? r % a.rm.B : m) * G3 + n; hr = ld4f(gh); hz = ld4f(gh + H); hn = ld4f(gh + 2 * H); }
     if (a.hprev) hp = ld4f(a.hprev + (int64_t)(a.hprev_by_graph ? r % a.rm.B : (a.hprev_global ? r : m)) * H + n);

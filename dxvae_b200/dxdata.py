@@ -114,6 +114,8 @@ class DXGraphBatch:
         if isinstance(graphs, DXGraphBatch):
             return graphs
         graphs = list(graphs)
+        if not graphs:
+            raise ValueError("empty batch")
         X = torch.stack([g.ndata["X"].detach().to("cpu", torch.float32) for g in graphs])
         P = torch.stack([g.ndata["params"].detach().to("cpu", torch.float32) for g in graphs])
         edges = [_graph_edges(g) for g in graphs]

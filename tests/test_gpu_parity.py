@@ -326,6 +326,54 @@ def test_decode_matches_oracle_and_reference_golden(lib, golden, tag, gain):
                            golden["%s_dec_%s_minmargin" % (tag, zt)][ok], rtol=1e-2, atol=1e-5)
 
 
+def test_api_compositions_and_rng_seams(lib):
+    """model.py:255-268 (`encode_decode`, `generate`) and the `rsample` seam (model.py:284): with the same
+    torch seed the class draws the same noise the reference's calls would, and the compositions equal
+    their parts."""
+    from torch.distributions import Normal
+    idx = util.pick_by_alg([0, 3, 5, 7, 16, 18, 20, 31])
+    X, P, E, A = util.dataset_graphs(idx)
+    m, o = make_model(0, 3.0)
+    G = _graphs(X, P, E)
+    with torch.no_grad():
+        q = m.encode(G)
+    # reparameterize: explicit eps, and eps=None == Normal.rsample() on the same device generator
+    eps = torch.randn(len(G), 128, generator=torch.Generator().manual_seed(2))
+    z = m.reparameterize(q, eps)
+    assert torch.equal(z, q.loc + q.scale * eps.cuda()) or (z - (q.loc + q.scale * eps.cuda())).abs().max() <= 1e-6
+    torch.manual_seed(9); z1 = m.reparameterize(q)
+    torch.manual_seed(9); z2 = Normal(q.loc, q.scale).rsample()
+    assert (z1 - z2).abs().max().item() <= 1e-6
+    # loss(eps=None) consumes the generator exactly like rsample: same value as injecting that draw
+    torch.manual_seed(4)
+    with torch.no_grad():
+        l_none = m.loss(q, G)
+    torch.manual_seed(4)
+    e4 = torch.empty(len(G), 128, device="cuda").normal_()
+    with torch.no_grad():
+        l_inj = m.loss(q, G, eps=e4)
+    assert all(abs(a.item() - b.item()) <= 1e-6 * abs(b.item()) + 1e-9 for a, b in zip(l_none, l_inj))
+    # encode_decode(G) == decode(mu)  (deterministic branch), stochastic branch == decode(q.sample()) under the seed
+    a = m.encode_decode(G)
+    b = m.decode(q.loc)
+    assert torch.equal(a.params, b.params) and torch.equal(a.adj, b.adj)
+    torch.manual_seed(6); c = m.encode_decode(G, stochastic=True)
+    torch.manual_seed(6); d = m.decode(Normal(q.loc, q.scale).sample())
+    assert torch.equal(c.params, d.params) and torch.equal(c.adj, d.adj)
+    # generate(n): prior draw on the CPU generator as the reference does (p_dist = Normal(0., 1.)), then decode
+    torch.manual_seed(8); g1 = m.generate(64)
+    torch.manual_seed(8); zp = Normal(0., 1.).sample((64, 128))
+    Xo, Po, Ao, mg = o.decode(zp, return_margins=True)
+    margins = torch.cat([l.flatten(1) for l in mg["edge"] + mg["self"]], 1).abs().min(1).values.numpy()
+    ok = margins > 1e-4
+    assert ok.sum() >= 32 and len(g1) == 64 and m.hidden == 64
+    assert np.array_equal(util.adj_from_masks(g1.adj.cpu().numpy().view(np.uint64))[ok], Ao.numpy()[ok])
+    assert np.array_equal(g1.params.cpu().numpy().astype(np.int32)[ok], Po.numpy().astype(np.int32)[ok])
+    # empty input is an error, not a silent no-op
+    with pytest.raises(ValueError):
+        m.encode([])
+
+
 def test_decode_large_batch_properties(lib):
     """Full-size style checks that need no oracle: chunking invariance, legal parameter ranges,
     decode -> .syx -> _make_graph round trip."""
