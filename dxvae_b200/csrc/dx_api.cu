@@ -33,7 +33,7 @@ size_t workspace_bytes(int op, int64_t B) {
     case DXVAE_OP_ENCODE: carve_enc(ar, B, false); break;
     case DXVAE_OP_DECODE: carve_dec(ar, B, false); break;
     case DXVAE_OP_TRAIN: carve_train(ar, B); break;
-    case DXVAE_OP_SCHEDULE: ar.take<int32_t>((size_t)36 * ((B + 1023) / 1024)); break;
+    case DXVAE_OP_SCHEDULE: ar.take<int32_t>((size_t)72 * ((B + 1023) / 1024)); break;
     case DXVAE_OP_ENCODE_TRAIN: carve_enc(ar, B, true); break;
     case DXVAE_OP_LOSS: carve_dec(ar, B, true); break;
     default: return 0;
@@ -196,12 +196,13 @@ int dxvae_pack_syx(int64_t B, const float* Pg, uint8_t* voices, void* stream) {
 size_t dxvae_workspace_bytes(int op, int64_t B) { return workspace_bytes(op, B); }
 
 int dxvae_encode_fwd(const float* weights, int64_t B, const float* Xn, const uint64_t* adj, int32_t n_levels,
-                     const int32_t* level_ptr_host, const int32_t* level_rows, float* mu, float* std_, void* workspace,
-                     size_t workspace_bytes, int keep, int precision, void* stream) {
+                     const int32_t* level_ptr_host, const int32_t* level_rows, const int32_t* level_rare_host, float* mu,
+                     float* std_, void* workspace, size_t workspace_bytes, int keep, int precision, void* stream) {
   DX_BATCH_OK(B);
   DX_CHECK(n_levels >= 1 && n_levels <= 6, "encode_fwd: n_levels=%d", n_levels);
   DX_CHECK(precision >= PREC_FP32 && precision <= PREC_3XTF32, "encode_fwd: unknown precision %d", precision);
   Batch bt{B, Xn, nullptr, adj, n_levels, level_ptr_host, level_rows};
+  bt.level_rare = level_rare_host;
   PrecisionScope prec(precision);
   return encode_fwd(DX_ST(stream), weights, bt, mu, std_, workspace, workspace_bytes, keep);
 }
@@ -215,7 +216,8 @@ int dxvae_decode_greedy(const float* weights, int64_t B, const float* z, float* 
   return decode_greedy(DX_ST(stream), weights, B, z, Xg, Pg, adj, margins, workspace, workspace_bytes, precision);
 }
 int dxvae_elbo_step(const float* weights, int64_t B, const float* Xn, const int32_t* cls, const uint64_t* adj,
-                    int32_t n_levels, const int32_t* level_ptr_host, const int32_t* level_rows, const float* eps,
+                    int32_t n_levels, const int32_t* level_ptr_host, const int32_t* level_rows,
+                    const int32_t* level_rare_host, const float* eps,
                     float w_env, float w_frq, float w_kld, float inv_batch, float* loss5, float* mu_out,
                     float* std_out, float* grads, void* workspace, size_t workspace_bytes, int precision,
                     const int32_t* step_ptr_host, const int32_t* step_rows, void* stream) {
@@ -224,6 +226,7 @@ int dxvae_elbo_step(const float* weights, int64_t B, const float* Xn, const int3
   DX_CHECK((step_ptr_host == nullptr) == (step_rows == nullptr), "elbo_step: step_ptr_host and step_rows go together");
   DX_CHECK(precision == PREC_FP32 || precision == PREC_TF32, "elbo_step: unknown precision %d", precision);
   Batch bt{B, Xn, cls, adj, n_levels, level_ptr_host, level_rows};
+  bt.level_rare = level_rare_host;
   bt.step_ptr = step_ptr_host; bt.step_rows = step_rows;
   LossW lw{w_env, w_frq, w_kld, inv_batch};
   return elbo_step(DX_ST(stream), weights, bt, eps, lw, loss5, mu_out, std_out, grads, workspace, workspace_bytes,
@@ -243,12 +246,14 @@ int dxvae_loss_step(const float* weights, int64_t B, const float* Xn, const int3
                    precision);
 }
 int dxvae_encode_bwd(const float* weights, int64_t B, const float* Xn, const uint64_t* adj, int32_t n_levels,
-                     const int32_t* level_ptr_host, const int32_t* level_rows, const float* std_, const float* dmu,
+                     const int32_t* level_ptr_host, const int32_t* level_rows, const int32_t* level_rare_host,
+                     const float* std_, const float* dmu,
                      const float* dstd, float* grads, void* workspace, size_t workspace_bytes, int precision,
                      void* stream) {
   DX_BATCH_OK(B);
   DX_CHECK(n_levels >= 1 && n_levels <= 6, "encode_bwd: n_levels=%d", n_levels);
   Batch bt{B, Xn, nullptr, adj, n_levels, level_ptr_host, level_rows};
+  bt.level_rare = level_rare_host;
   return encode_bwd(DX_ST(stream), weights, bt, std_, dmu, dstd, grads, workspace, workspace_bytes, precision);
 }
 int dxvae_adamw_step(int64_t n, float* weights, const float* grads, float* exp_avg, float* exp_avg_sq, float lr,

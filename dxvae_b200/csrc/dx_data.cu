@@ -36,6 +36,15 @@ DX_HD DX_INLINE void graph_levels(uint64_t A, uint8_t* lv) {
   }
 }
 
+// A node that receives an edge from a LOWER node (a feedback back-edge arrives at it): the only rows whose "out"
+// projection half the encoder reads.  Inside a level those rows come first, so the half is a dense row prefix.
+DX_HD DX_INLINE bool has_back_in(uint64_t A, int v) {
+  for (int u = 0; u < v; ++u)
+    if (abit(A, u, v)) return true;
+  return false;
+}
+
+// level_ptr: 16 ints.  [0..7] level offsets (as before); [8 + L] = number of leading rows of level L with has_back_in.
 static void schedule_host(int64_t B, const uint64_t* adj, uint8_t* level, int32_t* level_ptr, int32_t* level_rows,
                           int32_t* n_levels) {
   int maxl = 0;
@@ -48,12 +57,16 @@ static void schedule_host(int64_t B, const uint64_t* adj, uint8_t* level, int32_
   int64_t pos = 0;
   for (int L = 0; L < 7; ++L) {
     level_ptr[L] = (int32_t)pos;
+    level_ptr[8 + L] = 0;
     if (L < nl)
-      for (int v = 1; v < NN; ++v)
-        for (int64_t b = 0; b < B; ++b)
-          if (level[b * NN + v] == L) level_rows[pos++] = (int32_t)(v * B + b);
+      for (int pass = 0; pass < 2; ++pass) {               // pass 0: rows a back-edge arrives at, pass 1: the rest
+        for (int v = 1; v < NN; ++v)
+          for (int64_t b = 0; b < B; ++b)
+            if (level[b * NN + v] == L && has_back_in(adj[b], v) == (pass == 0)) level_rows[pos++] = (int32_t)(v * B + b);
+        if (pass == 0) level_ptr[8 + L] = (int32_t)pos - level_ptr[L];
+      }
   }
-  level_ptr[7] = (int32_t)pos;
+  level_ptr[7] = (int32_t)pos; level_ptr[15] = 0;
   *n_levels = nl;
 }
 
@@ -90,7 +103,7 @@ int batch_build_host(int64_t B, const int32_t* edge_ptr, const int8_t* src, cons
 #ifndef DX_EMU
 namespace {
 constexpr int SCH_T = 1024;  // graphs per block
-constexpr int NBIN = 36;     // (level 0..5) x (operator 1..6), ordered level-major
+constexpr int NBIN = 72;     // (level 0..5) x (back-edge target first, others second) x (operator 1..6), in that order
 
 __global__ void __launch_bounds__(SCH_T) k_levels_count(int64_t B, const uint64_t* __restrict__ adj,
                                                         uint8_t* __restrict__ level, int32_t* __restrict__ counts,
@@ -103,7 +116,7 @@ __global__ void __launch_bounds__(SCH_T) k_levels_count(int64_t B, const uint64_
     uint8_t lv[NN];
     graph_levels(adj[b], lv);
     for (int v = 0; v < NN; ++v) level[b * NN + v] = lv[v];
-    for (int v = 1; v < NN; ++v) atomicAdd(&cnt[lv[v] * 6 + (v - 1)], 1);
+    for (int v = 1; v < NN; ++v) atomicAdd(&cnt[lv[v] * 12 + (has_back_in(adj[b], v) ? 0 : 6) + (v - 1)], 1);
   }
   __syncthreads();
   if (threadIdx.x < NBIN) counts[threadIdx.x * nblk + blockIdx.x] = cnt[threadIdx.x];
@@ -120,14 +133,20 @@ __global__ void k_scan_bins(int32_t* __restrict__ counts, int nblk, int32_t* __r
   __syncthreads();
   if (threadIdx.x == 0) {
     int s = 0;
-    for (int q = 0; q < NBIN; ++q) { const int c = tot[q]; tot[q] = s; if (q % 6 == 0) level_ptr[q / 6] = s; s += c; }
-    level_ptr[6] = s; level_ptr[7] = s;
+    for (int q = 0; q < NBIN; ++q) {
+      const int c = tot[q]; tot[q] = s;
+      if (q % 12 == 0) level_ptr[q / 12] = s;
+      if (q % 12 == 6) level_ptr[8 + q / 12] = s - level_ptr[q / 12];     // rows of this level a back-edge arrives at
+      s += c;
+    }
+    level_ptr[6] = s; level_ptr[7] = s; level_ptr[14] = 0; level_ptr[15] = 0;
   }
   __syncthreads();
   if (bin < NBIN)
     for (int k = 0; k < nblk; ++k) counts[bin * nblk + k] += tot[bin];
 }
 __global__ void __launch_bounds__(SCH_T) k_scatter_rows(int64_t B, const uint8_t* __restrict__ level,
+                                                        const uint64_t* __restrict__ adj,
                                                         const int32_t* __restrict__ offsets, int nblk,
                                                         int32_t* __restrict__ level_rows) {
   __shared__ int wsum[32];
@@ -135,9 +154,12 @@ __global__ void __launch_bounds__(SCH_T) k_scatter_rows(int64_t B, const uint8_t
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   uint8_t lv[NN];
   for (int v = 0; v < NN; ++v) lv[v] = (b < B) ? level[b * NN + v] : 255;
+  const uint64_t A = (b < B) ? adj[b] : 0ull;
+  unsigned back = 0;
+  for (int v = 1; v < NN; ++v) back |= (has_back_in(A, v) ? 1u : 0u) << v;
   for (int bin = 0; bin < NBIN; ++bin) {
-    const int L = bin / 6, v = bin % 6 + 1;
-    const bool f = lv[v] == L;
+    const int L = bin / 12, v = bin % 6 + 1;
+    const bool f = lv[v] == L && (((back >> v) & 1u) != 0) == (bin % 12 < 6);
     const unsigned bal = __ballot_sync(0xffffffffu, f);
     const int inwarp = __popc(bal & ((1u << lane) - 1));
     if (lane == 0) wsum[wid] = __popc(bal);
@@ -158,10 +180,10 @@ int batch_schedule(dx_stream_t st, int64_t B, const uint64_t* adj, uint8_t* leve
   int32_t* counts = ar.take<int32_t>((size_t)NBIN * nblk);
   DX_CHECK(!ar.overflow, "batch_schedule: workspace too small (%zu < %zu)", ws_bytes, ar.off);
   k_levels_count<<<nblk, SCH_T, 0, st>>>(B, adj, level, counts, nblk);
-  k_scan_bins<<<1, 64, 0, st>>>(counts, nblk, level_ptr);
-  k_scatter_rows<<<nblk, SCH_T, 0, st>>>(B, level, counts, nblk, level_rows);
+  k_scan_bins<<<1, 96, 0, st>>>(counts, nblk, level_ptr);
+  k_scatter_rows<<<nblk, SCH_T, 0, st>>>(B, level, adj, counts, nblk, level_rows);
   g_launches += 3;
-  cudaMemcpyAsync(level_ptr_host, level_ptr, 8 * sizeof(int32_t), cudaMemcpyDeviceToHost, st);
+  cudaMemcpyAsync(level_ptr_host, level_ptr, 16 * sizeof(int32_t), cudaMemcpyDeviceToHost, st);
   cudaStreamSynchronize(st);
   return check_launch("batch_schedule");
 }
@@ -170,7 +192,7 @@ int batch_schedule(dx_stream_t, int64_t B, const uint64_t* adj, uint8_t* level, 
                    int32_t* level_ptr_host, void*, size_t) {
   int32_t nl = 0;
   schedule_host(B, adj, level, level_ptr, level_rows, &nl);
-  memcpy(level_ptr_host, level_ptr, 8 * sizeof(int32_t));
+  memcpy(level_ptr_host, level_ptr, 16 * sizeof(int32_t));
   return 0;
 }
 #endif
@@ -183,6 +205,12 @@ int batch_schedule(dx_stream_t, int64_t B, const uint64_t* adj, uint8_t* level, 
 // active at step t.
 DX_HD DX_INLINE int step_vi(int t) { int vi = 1; while ((vi + 1) * vi / 2 <= t) ++vi; return vi; }
 DX_HD DX_INLINE bool step_active(uint64_t A, int t) {
+  if (t >= 27) {                                        // lists 27..32: node x = 0..5 has an edge to a HIGHER node
+    const int x = t - 27;                                //   (a feedback back-edge leaves x: the decoder then needs the
+    for (int v = x + 1; v < NN; ++v)                     //    "in" half of x's projections)
+      if (abit(A, x, v)) return true;
+    return false;
+  }
   if (t >= 21) return abit(A, t - 20, t - 20) != 0;     // lists 21..26: self-loop on node 1..6
   const int vi = step_vi(t), vj = vi - 1 - (t - vi * (vi - 1) / 2);
   return (abit(A, vj, vi) | abit(A, vi, vj)) != 0;
@@ -190,17 +218,17 @@ DX_HD DX_INLINE bool step_active(uint64_t A, int t) {
 
 static void steps_host(int64_t B, const uint64_t* adj, int32_t* step_ptr, int32_t* step_rows) {
   int64_t pos = 0;
-  for (int t = 0; t < 27; ++t) {
+  for (int t = 0; t < NLIST; ++t) {
     step_ptr[t] = (int32_t)pos;
     for (int64_t b = 0; b < B; ++b)
       if (step_active(adj[b], t)) step_rows[pos++] = (int32_t)b;
   }
-  step_ptr[27] = (int32_t)pos;
+  step_ptr[NLIST] = (int32_t)pos;
 }
 
 #ifndef DX_EMU
 namespace {
-constexpr int NSTEPB = 27;
+constexpr int NSTEPB = NLIST;
 __global__ void __launch_bounds__(SCH_T) k_steps_count(int64_t B, const uint64_t* __restrict__ adj,
                                                        int32_t* __restrict__ counts, int nblk) {
   __shared__ int cnt[NSTEPB];
@@ -255,16 +283,16 @@ __global__ void __launch_bounds__(SCH_T) k_steps_scatter(int64_t B, const uint64
 
 int batch_steps(dx_stream_t st, int64_t B, const uint64_t* adj, int32_t* step_ptr, int32_t* step_rows,
                 int32_t* step_ptr_host, void* ws, size_t ws_bytes) {
-  DX_CHECK(B > 0 && (int64_t)27 * B < (1ll << 31), "batch_steps: bad batch size");
+  DX_CHECK(B > 0 && (int64_t)NLIST * B < (1ll << 31), "batch_steps: bad batch size");
   const int nblk = (int)((B + SCH_T - 1) / SCH_T);
   Arena ar(ws, ws_bytes);
   int32_t* counts = ar.take<int32_t>((size_t)NSTEPB * nblk);
   DX_CHECK(!ar.overflow, "batch_steps: workspace too small (%zu < %zu)", ws_bytes, ar.off);
   k_steps_count<<<nblk, SCH_T, 0, st>>>(B, adj, counts, nblk);
-  k_steps_scan<<<1, 32, 0, st>>>(counts, nblk, step_ptr);
+  k_steps_scan<<<1, 64, 0, st>>>(counts, nblk, step_ptr);
   k_steps_scatter<<<nblk, SCH_T, 0, st>>>(B, adj, counts, nblk, step_rows);
   g_launches += 3;
-  cudaMemcpyAsync(step_ptr_host, step_ptr, 28 * sizeof(int32_t), cudaMemcpyDeviceToHost, st);
+  cudaMemcpyAsync(step_ptr_host, step_ptr, (NLIST + 1) * sizeof(int32_t), cudaMemcpyDeviceToHost, st);
   cudaStreamSynchronize(st);
   return check_launch("batch_steps");
 }
@@ -272,7 +300,7 @@ int batch_steps(dx_stream_t st, int64_t B, const uint64_t* adj, int32_t* step_pt
 int batch_steps(dx_stream_t, int64_t B, const uint64_t* adj, int32_t* step_ptr, int32_t* step_rows,
                 int32_t* step_ptr_host, void*, size_t) {
   steps_host(B, adj, step_ptr, step_rows);
-  memcpy(step_ptr_host, step_ptr, 28 * sizeof(int32_t));
+  memcpy(step_ptr_host, step_ptr, (NLIST + 1) * sizeof(int32_t));
   return 0;
 }
 #endif

@@ -492,10 +492,30 @@ static void mlp3_fwd(dx_stream_t st, const Weights& W, int B, int w0, const floa
   linear_fwd(st, B, nout, 2 * H, A2, 2 * H, W[w0 + 4], 2 * H, W[w0 + 5], L, LD_L);
 }
 
-static void node_projections(dx_stream_t st, const Weights& W, int B, int v, const DecWs& w) {
-  const float* h = w.Hd + (size_t)v * B * H;
-  linear_fwd(st, B, 2 * H, H, h, H, W[P_G_W], H, nullptr, w.Pg + (size_t)v * B * 2 * H, 2 * H);
-  linear_fwd(st, B, 2 * H, H, h, H, W[P_M_W], H, nullptr, w.Pm + (size_t)v * B * 2 * H, 2 * H);
+// bt != NULL (teacher forcing with the step schedule): a later node vi reads the "out" half of node v's projections
+// through its forward edge vi -> v and the "in" half only through a feedback back-edge v -> vi, so the "in" half is
+// computed on the rows of schedule list NSTEP+6+v alone (gather -> product -> scatter).  Greedy decoding does not know
+// its edges yet and computes both halves for every graph.
+static void node_projections(dx_stream_t st, const Weights& W, int B, int v, const DecWs& w, const Batch* bt = nullptr) {
+  float* h = w.Hd + (size_t)v * B * H;
+  float* Pg = w.Pg + (size_t)v * B * 2 * H; float* Pm = w.Pm + (size_t)v * B * 2 * H;
+  proj_fwd(st, B, h, W[P_G_W], Pg, HALF_OUT);
+  proj_fwd(st, B, h, W[P_M_W], Pm, HALF_OUT);
+  if (bt && bt->step_ptr) {
+    const int tl = NSTEP + 6 + v, n = bt->step_ptr[tl + 1] - bt->step_ptr[tl];
+    if (n > 0) {
+      const int* rows = bt->step_rows + bt->step_ptr[tl];
+      float* th = w.UC; float* tg = w.UC + (size_t)B * H; float* tm = w.UC + (size_t)2 * B * H;   // (UC is idle between steps)
+      gather_rows(st, n, H, rows, h, th, 0);
+      linear_fwd(st, n, H, H, th, H, W[P_G_W], 2 * H, nullptr, tg, H);
+      linear_fwd(st, n, H, H, th, H, W[P_M_W], 2 * H, nullptr, tm, H);
+      scatter_rows(st, n, H, rows, tg, Pg, 0, 2 * H);
+      scatter_rows(st, n, H, rows, tm, Pm, 0, 2 * H);
+    }
+  } else {
+    proj_fwd(st, B, h, W[P_G_W], Pg, HALF_IN);
+    proj_fwd(st, B, h, W[P_M_W], Pm, HALF_IN);
+  }
   // Hj half of h_to_edge.0 (columns 512..1023 of the (2048,1024) weight) + its bias
   linear_fwd(st, B, 4 * H, H, h, H, W[P_E_W0] + H, 2 * H, W[P_E_B0], w.Q + (size_t)v * B * 4 * H, 4 * H);
 }
@@ -524,7 +544,7 @@ void decode_fwd_impl(dx_stream_t st, const Weights& W, int B, const float* z, co
     CellFwd c{rm, w.gxc[0], w.gh, W[P_RD_BIH], W[P_RD_BHH], w.Hinit, 0, w.Hd, 0, train ? w.g_root : nullptr, 0, S_ONE, adj};
     cell_fwd(st, c);
   }
-  node_projections(st, W, B, 0, w);
+  node_projections(st, W, B, 0, w, train ? io.bt : nullptr);
 
   int t = 0;
   for (int vi = 1; vi < NN; ++vi) {
@@ -599,7 +619,7 @@ void decode_fwd_impl(dx_stream_t st, const Weights& W, int B, const float* z, co
         linear_fwd(st, n, 4 * H, H, w.Hi[t], H, W[P_E_W0], 2 * H, nullptr, w.UC, 4 * H);
         scatter_rows(st, n, 4 * H, rows, w.UC, w.U, 0);
       }
-      if (vi < NN - 1) node_projections(st, W, B, vi, w);
+      if (vi < NN - 1) node_projections(st, W, B, vi, w, io.bt);
       continue;
     }
     const float* Hi_prev = w.Hi_p2[vi];
@@ -802,11 +822,29 @@ void decode_bwd_impl(dx_stream_t st, const Weights& W, const Weights& G, int B, 
     const int j = vi - 1;
     const float* dPg = w.dPg + (size_t)j * B * 2 * H; const float* dPm = w.dPm + (size_t)j * B * 2 * H;
     const float* dQ = w.dQ + (size_t)j * B * 4 * H;
-    linear_dgrad(st, B, 2 * H, H, dPg, 2 * H, W[P_G_W], H, dprev, H, ACC_ADD);
-    linear_dgrad(st, B, 2 * H, H, dPm, 2 * H, W[P_M_W], H, dprev, H, ACC_ADD);
+    for (int half = 0; half < 2; ++half) {
+      if (half == HALF_IN && compact) {
+        // the "in" half was only produced (and only received gradient) on the back-edge-source rows of node j
+        const int tl = NSTEP + 6 + j, n = bt.step_ptr[tl + 1] - bt.step_ptr[tl];
+        if (n <= 0) continue;
+        const int* rows = bt.step_rows + bt.step_ptr[tl];
+        float* tg = w.UC; float* tm = w.UC + bH; float* th = w.UC + 2 * bH; float* tdx = w.UC + 3 * bH;
+        gather_rows(st, n, H, rows, const_cast<float*>(dPg), tg, 0, 2 * H);
+        gather_rows(st, n, H, rows, const_cast<float*>(dPm), tm, 0, 2 * H);
+        gather_rows(st, n, H, rows, const_cast<float*>(hprev), th, 0);
+        linear_dgrad(st, n, H, H, tg, H, W[P_G_W], 2 * H, tdx, H, ACC_STORE);
+        linear_dgrad(st, n, H, H, tm, H, W[P_M_W], 2 * H, tdx, H, ACC_ADD);
+        scatter_rows(st, n, H, rows, tdx, dprev, 1);
+        linear_wgrad(st, n, H, H, tg, H, th, H, G[P_G_W], 2 * H);
+        linear_wgrad(st, n, H, H, tm, H, th, H, G[P_M_W], 2 * H);
+        continue;
+      }
+      proj_dgrad(st, B, dPg, W[P_G_W], dprev, half, ACC_ADD);
+      proj_dgrad(st, B, dPm, W[P_M_W], dprev, half, ACC_ADD);
+      proj_wgrad(st, B, dPg, hprev, G[P_G_W], half);
+      proj_wgrad(st, B, dPm, hprev, G[P_M_W], half);
+    }
     linear_dgrad(st, B, 4 * H, H, dQ, 4 * H, W[P_E_W0] + H, 2 * H, dprev, H, ACC_ADD);
-    linear_wgrad(st, B, 2 * H, H, dPg, 2 * H, hprev, H, G[P_G_W], H);
-    linear_wgrad(st, B, 2 * H, H, dPm, 2 * H, hprev, H, G[P_M_W], H);
     linear_wgrad(st, B, 4 * H, H, dQ, 4 * H, hprev, H, G[P_E_W0] + H, 2 * H);
     colsum_accum(st, B, 4 * H, dQ, 4 * H, G[P_E_B0]);
     colsum_accum(st, B, H, w.dgb + (size_t)j * bH, H, G[P_G_B]);

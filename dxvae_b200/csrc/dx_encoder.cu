@@ -79,9 +79,16 @@ void encode_fwd_impl(dx_stream_t st, const Weights& W, const Batch& bt, const En
     CellFwd c2{rm, w.gxl, w.gh, W[P_LE_BIH], W[P_LE_BHH], Hc, 0, Hv, 0, train ? w.gl + (size_t)base * 4 * H : nullptr, 0,
                S_SELF, bt.adj};
     cell_fwd(st, c2);
-    // projections of the finished state: gate.0.weight (512,1024) viewed as (1024,512) rows (2n,2n+1)=(in,out)
-    linear_fwd(st, M, 2 * H, H, Hv, H, W[P_G_W], H, nullptr, w.Pg + (size_t)base * 2 * H, 2 * H);
-    linear_fwd(st, M, 2 * H, H, Hv, H, W[P_M_W], H, nullptr, w.Pm + (size_t)base * 2 * H, 2 * H);
+    // projections of the finished state, by half (see proj_fwd): a lower node v reads the "in" half of x through
+    // its forward edge x -> v and the "out" half only through a feedback back-edge v -> x, so the "out" half is
+    // computed on the level's leading rows alone (the batcher puts the back-edge targets first)
+    const int Mr = bt.level_rare ? bt.level_rare[L] : M;
+    proj_fwd(st, M, Hv, W[P_G_W], w.Pg + (size_t)base * 2 * H, HALF_IN);
+    proj_fwd(st, M, Hv, W[P_M_W], w.Pm + (size_t)base * 2 * H, HALF_IN);
+    if (Mr > 0) {
+      proj_fwd(st, Mr, Hv, W[P_G_W], w.Pg + (size_t)base * 2 * H, HALF_OUT);
+      proj_fwd(st, Mr, Hv, W[P_M_W], w.Pm + (size_t)base * 2 * H, HALF_OUT);
+    }
   }
   // root step: node 0 of every graph (positions 6B..7B-1)
   RowMap r0{B, B, nullptr, 0};
@@ -139,10 +146,15 @@ void encode_bwd_impl(dx_stream_t st, const Weights& W, const Weights& G, const B
               w.dgb, 0, -1, 0, 0};
     mb.pos = w.pos; mb.p_compact = 1;
     msg_bwd(st, mb);
-    linear_dgrad(st, M, 2 * H, H, w.dPg, 2 * H, W[P_G_W], H, dH, H, ACC_STORE);
-    linear_dgrad(st, M, 2 * H, H, w.dPm, 2 * H, W[P_M_W], H, dH, H, ACC_ADD);
-    linear_wgrad(st, M, 2 * H, H, w.dPg, 2 * H, Hv, H, G[P_G_W], H);
-    linear_wgrad(st, M, 2 * H, H, w.dPm, 2 * H, Hv, H, G[P_M_W], H);
+    const int Mr = bt.level_rare ? bt.level_rare[L] : M;      // rows whose "out" half exists (leading rows of the level)
+    for (int half = 0; half < 2; ++half) {
+      const int Mh = half == HALF_IN ? M : Mr;
+      if (Mh <= 0) continue;
+      proj_dgrad(st, Mh, w.dPg, W[P_G_W], dH, half, half == HALF_IN ? ACC_STORE : ACC_ADD);
+      proj_dgrad(st, Mh, w.dPm, W[P_M_W], dH, half, ACC_ADD);
+      proj_wgrad(st, Mh, w.dPg, Hv, G[P_G_W], half);
+      proj_wgrad(st, Mh, w.dPm, Hv, G[P_M_W], half);
+    }
     colsum_accum(st, M, H, w.dgb, H, G[P_G_B]);
     // looper
     CellBwd cl{rm, dH, 0, w.gl + (size_t)base * 4 * H, 0, Hc, 0, w.dgx, nullptr, w.dgh, w.dHc, S_SELF, bt.adj};

@@ -22,8 +22,10 @@ struct Batch {       // what the batcher produces (device pointers except level_
   int n_levels;
   const int32_t* level_ptr;   // HOST, n_levels+1
   const int32_t* level_rows;  // device, 6B
+  const int32_t* level_rare = nullptr;  // HOST, n_levels (optional): leading rows of each level that need the "out" projection half
   // optional decoder step schedule (teacher forcing): rows active at each of the 21 (vi,vj) steps, then
-  // (lists 21..26) the graphs with a self-loop on node vi = 1..6 (the only rows where P2 differs from P1)
+  // (lists 21..26) the graphs with a self-loop on node vi = 1..6 (the only rows where P2 differs from P1), then
+  // (lists 27..32) the graphs in which node x = 0..5 has an edge to a higher node (rows needing x's "in" projections)
   const int32_t* step_ptr = nullptr;    // HOST, NLIST+1
   const int32_t* step_rows = nullptr;   // device, step_ptr[NLIST] graph ids
 };
@@ -46,7 +48,7 @@ struct EncWs {
 };
 constexpr int LD_L = 64;  // leading dimension of logit buffers (55 / 27 columns used)
 constexpr int NSTEP = 21;
-constexpr int NLIST = NSTEP + 6;   // step-schedule lists: 21 edge steps + 6 self-loop row lists
+constexpr int NLIST = NSTEP + 6 + 6;   // step-schedule lists: 21 edge steps + 6 self-loop row lists + 6 back-edge-source lists
 constexpr int LD_E = 4;    // leading dimension of the edge-head logit buffers (1 or 2 columns used; 16-byte rows for TMA)
 
 struct DecWs {
@@ -74,6 +76,20 @@ struct DecIO {
   float* dW2 = nullptr;   // train + compacted steps: gradient slots of h_to_edge.2.{weight,bias}; the fused edge
   float* db2 = nullptr;   //   head accumulates them during the forward pass (NULL: loss only, no gradients)
 };
+
+// Gate / mapper projections of a node state (gate.0.weight, mapper.0.weight: (H, 2H)), by half:
+//   P[:, :H] = h W[:, :H]^T  ("in" half: the neighbour is a predecessor),  P[:, H:] = h W[:, H:]^T  ("out" half).
+// Away from feedback back-edges the encoder only ever reads the "in" half and the decoder the "out" half.
+enum { HALF_IN = 0, HALF_OUT = 1 };
+inline void proj_fwd(dx_stream_t st, int M, const float* h, const float* Wp, float* P, int half) {
+  linear_fwd(st, M, H, H, h, H, Wp + half * H, 2 * H, nullptr, P + half * H, 2 * H);
+}
+inline void proj_dgrad(dx_stream_t st, int M, const float* dP, const float* Wp, float* dh, int half, int accum) {
+  linear_dgrad(st, M, H, H, dP + half * H, 2 * H, Wp + half * H, 2 * H, dh, H, accum);
+}
+inline void proj_wgrad(dx_stream_t st, int M, const float* dP, const float* h, float* dWp, int half) {
+  linear_wgrad(st, M, H, H, dP + half * H, 2 * H, h, H, dWp + half * H, 2 * H);
+}
 
 EncWs carve_enc(Arena& ar, int64_t B, bool train);
 DecWs carve_dec(Arena& ar, int64_t B, bool train);

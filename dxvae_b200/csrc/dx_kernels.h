@@ -197,8 +197,9 @@ inline void cell_bwd(dx_stream_t st, const CellBwd& a, float* dbih = nullptr, fl
 
 // ------------------------------------------------------------------------------------
 // Gated-sum neighbour aggregation (model.py:163-181) on pre-projected neighbour states.
-//   Pg[x-row, 2n..2n+1] = (W_g[n,:512] h_x, W_g[n,512:] h_x)   ("in" half, "out" half)
-//   Pm likewise for the bias-free mapper.
+//   Pg[x-row, n] = W_g[n,:512] h_x ("in" half), Pg[x-row, 512+n] = W_g[n,512:] h_x ("out" half)
+//   Pm likewise for the bias-free mapper.  A half is only read where its edge flag is set, so the
+//   producer may skip the half a row never needs (DESIGN.md "projection halves").
 //   message x->v:  i=[x->v], o=[v->x] ;  m = sig(i*Pg_in + o*Pg_out + b_g) * (i*Pm_in + o*Pm_out)
 //   (i=o=0 gives exactly 0 in the reference because the mapper has no bias: skipped.)
 // Forward: target rows (RowMap), neighbours x = x_lo..x_hi in steps of +1 (encode: v+1..6,
@@ -214,26 +215,30 @@ struct MsgFwd {
 };
 
 inline void msg_fwd(dx_stream_t st, const MsgFwd& a) {
-  foreach (st, (int64_t)a.rm.M * (H / 2), [=] DX_HD(int64_t idx) {
-    const int m = (int)(idx / (H / 2)), n = (int)(idx % (H / 2)) * 2;
+  foreach (st, (int64_t)a.rm.M * (H / 4), [=] DX_HD(int64_t idx) {
+    const int m = (int)(idx / (H / 4)), n = (int)(idx % (H / 4)) * 4;
     const int r = a.rm.r(m);
     const int b = r % a.rm.B, v = r / a.rm.B;
     const uint64_t A = a.adj[b];
     float* out = a.hin + (int64_t)(a.hin_by_graph ? b : (a.hin_global ? r : m)) * H + n;
-    float acc0 = a.accum ? out[0] : 0.f, acc1 = a.accum ? out[1] : 0.f;
+    float4 acc = a.accum ? ld4f(out) : f4zero();
     const int lo = a.x_lo < 0 ? v + 1 : a.x_lo, hi = a.x_lo < 0 ? NN - 1 : a.x_hi;
-    const float bg0 = a.bg[n], bg1 = a.bg[n + 1];
+    const float4 bg = ld4f(a.bg + n);
     for (int x = lo; x <= hi; ++x) {
       const float fi = (float)abit(A, x, v), fo = (float)abit(A, v, x);
       if (fi == 0.f && fo == 0.f) continue;
       const int64_t xr = a.pos ? (int64_t)a.pos[x * a.rm.B + b] : (int64_t)x * a.rm.B + b;
-      const float4 g = ld4f(a.Pg + xr * (2 * H) + 2 * n);
-      const float4 p = ld4f(a.Pm + xr * (2 * H) + 2 * n);
-      acc0 += sigmoidf_((fi * g.x + fo * g.y) + bg0) * (fi * p.x + fo * p.y);
-      acc1 += sigmoidf_((fi * g.z + fo * g.w) + bg1) * (fi * p.z + fo * p.w);
+      // a half is only read where its flag is set: the other one may not have been computed for this row
+      float4 gi = f4zero(), go = f4zero(), pi = f4zero(), po = f4zero();
+      if (fi != 0.f) { gi = ld4f(a.Pg + xr * (2 * H) + n); pi = ld4f(a.Pm + xr * (2 * H) + n); }
+      if (fo != 0.f) { go = ld4f(a.Pg + xr * (2 * H) + H + n); po = ld4f(a.Pm + xr * (2 * H) + H + n); }
+      acc.x += sigmoidf_((fi * gi.x + fo * go.x) + bg.x) * (fi * pi.x + fo * po.x);
+      acc.y += sigmoidf_((fi * gi.y + fo * go.y) + bg.y) * (fi * pi.y + fo * po.y);
+      acc.z += sigmoidf_((fi * gi.z + fo * go.z) + bg.z) * (fi * pi.z + fo * po.z);
+      acc.w += sigmoidf_((fi * gi.w + fo * go.w) + bg.w) * (fi * pi.w + fo * po.w);
     }
-    out[0] = acc0; out[1] = acc1;
-    if (a.hin_copy) { a.hin_copy[(int64_t)m * H + n] = acc0; a.hin_copy[(int64_t)m * H + n + 1] = acc1; }
+    st4f(out, acc);
+    if (a.hin_copy) st4f(a.hin_copy + (int64_t)m * H + n, acc);
   });
 }
 
@@ -249,35 +254,37 @@ struct MsgBwd {
 };
 
 inline void msg_bwd(dx_stream_t st, const MsgBwd& a) {
-  foreach (st, (int64_t)a.rm.M * (H / 2), [=] DX_HD(int64_t idx) {
-    const int m = (int)(idx / (H / 2)), n = (int)(idx % (H / 2)) * 2;
+  foreach (st, (int64_t)a.rm.M * (H / 4), [=] DX_HD(int64_t idx) {
+    const int m = (int)(idx / (H / 4)), n = (int)(idx % (H / 4)) * 4;
     const int r = a.rm.r(m);
     const int b = r % a.rm.B, x = r / a.rm.B;
     const uint64_t A = a.adj[b];
     const int64_t o = a.out_global ? r : m;
-    float4 dg = f4zero(), dp = f4zero(); float db0 = 0.f, db1 = 0.f;
-    if (a.accum) { dg = ld4f(a.dPg + o * (2 * H) + 2 * n); dp = ld4f(a.dPm + o * (2 * H) + 2 * n);
-                   db0 = a.dgb[o * H + n]; db1 = a.dgb[o * H + n + 1]; }
+    float* dgp = a.dPg + o * (2 * H) + n; float* dpp = a.dPm + o * (2 * H) + n; float* dbp = a.dgb + o * H + n;
+    float4 dgi = f4zero(), dgo = f4zero(), dpi = f4zero(), dpo = f4zero(), db = f4zero();
+    if (a.accum) { dgi = ld4f(dgp); dgo = ld4f(dgp + H); dpi = ld4f(dpp); dpo = ld4f(dpp + H); db = ld4f(dbp); }
     const int lo = a.v_lo < 0 ? 0 : a.v_lo, hi = a.v_lo < 0 ? x - 1 : a.v_hi;
     const int64_t own = a.p_compact ? m : r;
-    const float4 g = ld4f(a.Pg + own * (2 * H) + 2 * n);
-    const float4 p = ld4f(a.Pm + own * (2 * H) + 2 * n);
-    const float bg0 = a.bg[n], bg1 = a.bg[n + 1];
+    const float* gp = a.Pg + own * (2 * H) + n; const float* pp = a.Pm + own * (2 * H) + n;
+    const float4 bg = ld4f(a.bg + n);
     for (int v = lo; v <= hi; ++v) {
       const float fi = (float)abit(A, x, v), fo = (float)abit(A, v, x);
       if (fi == 0.f && fo == 0.f) continue;
       const int64_t trow = a.pos ? (int64_t)a.pos[v * a.rm.B + b] : (int64_t)v * a.dh_vstride + b;
-      const float* dh = a.dhin + trow * H + n;
-      const float s0 = sigmoidf_((fi * g.x + fo * g.y) + bg0), c0 = fi * p.x + fo * p.y;
-      const float s1 = sigmoidf_((fi * g.z + fo * g.w) + bg1), c1 = fi * p.z + fo * p.w;
-      const float da0 = dh[0] * c0 * s0 * (1.f - s0), dc0 = dh[0] * s0;
-      const float da1 = dh[1] * c1 * s1 * (1.f - s1), dc1 = dh[1] * s1;
-      dg.x += fi * da0; dg.y += fo * da0; dg.z += fi * da1; dg.w += fo * da1;
-      dp.x += fi * dc0; dp.y += fo * dc0; dp.z += fi * dc1; dp.w += fo * dc1;
-      db0 += da0; db1 += da1;
+      const float4 dh = ld4f(a.dhin + trow * H + n);
+      float4 gi = f4zero(), go = f4zero(), pi = f4zero(), po = f4zero();
+      if (fi != 0.f) { gi = ld4f(gp); pi = ld4f(pp); }
+      if (fo != 0.f) { go = ld4f(gp + H); po = ld4f(pp + H); }
+#define DX_MSGB(c)                                                                \
+      {                                                                           \
+        const float s_ = sigmoidf_((fi * gi.c + fo * go.c) + bg.c), c_ = fi * pi.c + fo * po.c; \
+        const float da = dh.c * c_ * s_ * (1.f - s_), dc = dh.c * s_;             \
+        dgi.c += fi * da; dgo.c += fo * da; dpi.c += fi * dc; dpo.c += fo * dc; db.c += da; \
+      }
+      DX_MSGB(x) DX_MSGB(y) DX_MSGB(z) DX_MSGB(w)
+#undef DX_MSGB
     }
-    st4f(a.dPg + o * (2 * H) + 2 * n, dg); st4f(a.dPm + o * (2 * H) + 2 * n, dp);
-    a.dgb[o * H + n] = db0; a.dgb[o * H + n + 1] = db1;
+    st4f(dgp, dgi); st4f(dgp + H, dgo); st4f(dpp, dpi); st4f(dpp + H, dpo); st4f(dbp, db);
   });
 }
 
@@ -287,18 +294,20 @@ inline void msg_bwd(dx_stream_t st, const MsgBwd& a) {
 // Row gather / scatter helpers for the compacted teacher-forced steps (rows[m] = graph index).
 //   gather_rows     : dst[m,:] = src[rows[m],:]            ; zero_src also clears the source rows
 //   scatter_rows    : dst[rows[m],:] = src[m,:]            ; add=1 accumulates
-inline void gather_rows(dx_stream_t st, int M, int C, const int* rows, float* src, float* dst, int zero_src) {
+inline void gather_rows(dx_stream_t st, int M, int C, const int* rows, float* src, float* dst, int zero_src, int ld_src = 0) {
+  if (ld_src == 0) ld_src = C;                       // row pitch of src (a column block of a wider matrix when > C)
   foreach (st, (int64_t)M * (C / 4), [=] DX_HD(int64_t idx) {
     const int m = (int)(idx / (C / 4)), c = (int)(idx % (C / 4)) * 4;
-    float* sp = src + (int64_t)rows[m] * C + c;
+    float* sp = src + (int64_t)rows[m] * ld_src + c;
     st4f(dst + (int64_t)m * C + c, ld4f(sp));
     if (zero_src) st4f(sp, f4zero());
   });
 }
-inline void scatter_rows(dx_stream_t st, int M, int C, const int* rows, const float* src, float* dst, int add) {
+inline void scatter_rows(dx_stream_t st, int M, int C, const int* rows, const float* src, float* dst, int add, int ld_dst = 0) {
+  if (ld_dst == 0) ld_dst = C;
   foreach (st, (int64_t)M * (C / 4), [=] DX_HD(int64_t idx) {
     const int m = (int)(idx / (C / 4)), c = (int)(idx % (C / 4)) * 4;
-    float* dp = dst + (int64_t)rows[m] * C + c;
+    float* dp = dst + (int64_t)rows[m] * ld_dst + c;
     float4 v = ld4f(src + (int64_t)m * C + c);
     if (add) { const float4 o = ld4f(dp); v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w; }
     st4f(dp, v);

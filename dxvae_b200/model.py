@@ -145,7 +145,7 @@ class DXVAE(nn.Module):
         _lib.check(L.dxvae_pack_graphs(B, Xg.data_ptr(), Pg.data_ptr(), d.Xn.data_ptr(), d.cls.data_ptr(), st),
                    "dxvae_pack_graphs")
         use_host = (not gb.adj.is_cuda) if host_batcher is None else host_batcher
-        d.level_ptr = np.zeros(8, np.int32)
+        d.level_ptr = np.zeros(16, np.int32)       # 8 level offsets, then per-level counts of back-edge-target rows
         d.csr = None
         if use_host:
             edges = gb.edge_lists()
@@ -169,18 +169,18 @@ class DXVAE(nn.Module):
             d.csr = (indptr, indices[:int(eptr[-1])], eflags[:int(eptr[-1])])
             d.step_ptr = d.step_rows = None
             if need_cls and self.compact_steps:
-                d.step_ptr = np.zeros(28, np.int32)
-                srows = np.zeros(27 * B, np.int32)
+                d.step_ptr = np.zeros(34, np.int32)
+                srows = np.zeros(33 * B, np.int32)
                 _lib.check(L.dxvae_batch_steps_host(B, pv(adj), pv(d.step_ptr), pv(srows)), "dxvae_batch_steps_host")
-                d.step_rows = torch.from_numpy(srows[:max(1, int(d.step_ptr[27]))]).to("cuda")
+                d.step_rows = torch.from_numpy(srows[:max(1, int(d.step_ptr[33]))]).to("cuda")
         else:
             d.adj = gb.adj.to("cuda", torch.int64).contiguous()
             self._schedule(d)
             d.step_ptr = d.step_rows = None
             if need_cls and self.compact_steps:
-                d.step_ptr = np.zeros(28, np.int32)
-                d.step_rows = torch.empty(27 * B, dtype=torch.int32, device="cuda")
-                sp_dev = torch.empty(28, dtype=torch.int32, device="cuda")
+                d.step_ptr = np.zeros(34, np.int32)
+                d.step_rows = torch.empty(33 * B, dtype=torch.int32, device="cuda")
+                sp_dev = torch.empty(34, dtype=torch.int32, device="cuda")
                 ws = self._workspace(_abi.OP_SCHEDULE, B)
                 _lib.check(L.dxvae_batch_steps(B, d.adj.data_ptr(), sp_dev.data_ptr(), d.step_rows.data_ptr(),
                                                d.step_ptr.ctypes.data, ws.data_ptr(), ws.numel(), st), "dxvae_batch_steps")
@@ -230,7 +230,7 @@ class DXVAE(nn.Module):
             d = self._prepare(gb[lo:hi], need_cls=False)
             ws = self._workspace(_abi.OP_ENCODE, d.B)
             _lib.check(L.dxvae_encode_fwd(self._flat.data_ptr(), d.B, d.Xn.data_ptr(), d.adj.data_ptr(), d.n_levels,
-                                          d.level_ptr.ctypes.data, d.level_rows.data_ptr(), mu[lo:hi].data_ptr(),
+                                          d.level_ptr.ctypes.data, d.level_rows.data_ptr(), d.level_ptr[8:].ctypes.data, mu[lo:hi].data_ptr(),
                                           sd[lo:hi].data_ptr(), ws.data_ptr(), ws.numel(), 0,
                                           {"fp32": _abi.PREC_FP32, "tf32": _abi.PREC_TF32, "3xtf32": _abi.PREC_3XTF32}[self.encode_precision],
                                           _stream()),
@@ -325,7 +325,7 @@ class DXVAE(nn.Module):
         ws = self._workspace(_abi.OP_TRAIN, d.B)
         _lib.check(L.dxvae_elbo_step(
             self._flat.data_ptr(), d.B, d.Xn.data_ptr(), d.cls.data_ptr(), d.adj.data_ptr(), d.n_levels,
-            d.level_ptr.ctypes.data, d.level_rows.data_ptr(), eps.data_ptr(), w[0], w[1], w[2],
+            d.level_ptr.ctypes.data, d.level_rows.data_ptr(), d.level_ptr[8:].ctypes.data, eps.data_ptr(), w[0], w[1], w[2],
             (1.0 / d.B) if inv_batch is None else inv_batch, loss5.data_ptr(),
             None if mu_out is None else mu_out.data_ptr(), None if std_out is None else std_out.data_ptr(),
             None if grads is None else grads.data_ptr(), ws.data_ptr(), ws.numel(), self._prec(),
@@ -394,7 +394,7 @@ class _EncodeFn(torch.autograd.Function):
         ws = model._workspace(_abi.OP_ENCODE_TRAIN, d.B, fresh=True)
         mu = torch.empty(d.B, 128, device="cuda"); sd = torch.empty(d.B, 128, device="cuda")
         _lib.check(L.dxvae_encode_fwd(model._flat.data_ptr(), d.B, d.Xn.data_ptr(), d.adj.data_ptr(), d.n_levels,
-                                      d.level_ptr.ctypes.data, d.level_rows.data_ptr(), mu.data_ptr(), sd.data_ptr(),
+                                      d.level_ptr.ctypes.data, d.level_rows.data_ptr(), d.level_ptr[8:].ctypes.data, mu.data_ptr(), sd.data_ptr(),
                                       ws.data_ptr(), ws.numel(), 1, model._prec(), _stream()), "dxvae_encode_fwd")
         ctx.model, ctx.d, ctx.ws, ctx.sd = model, d, ws, sd
         return mu, sd
@@ -407,7 +407,7 @@ class _EncodeFn(torch.autograd.Function):
         dmu = torch.zeros(d.B, 128, device="cuda") if dmu is None else dmu.contiguous()
         dsd = torch.zeros(d.B, 128, device="cuda") if dsd is None else dsd.contiguous()
         _lib.check(L.dxvae_encode_bwd(model._flat.data_ptr(), d.B, d.Xn.data_ptr(), d.adj.data_ptr(), d.n_levels,
-                                      d.level_ptr.ctypes.data, d.level_rows.data_ptr(), ctx.sd.data_ptr(),
+                                      d.level_ptr.ctypes.data, d.level_rows.data_ptr(), d.level_ptr[8:].ctypes.data, ctx.sd.data_ptr(),
                                       dmu.data_ptr(), dsd.data_ptr(), g.data_ptr(), ctx.ws.data_ptr(), ctx.ws.numel(),
                                       model._prec(), _stream()), "dxvae_encode_bwd")
         return (None, None) + model._grad_views(g)

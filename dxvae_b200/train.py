@@ -85,7 +85,7 @@ class Trainer:
         # node-order level schedule: level k = node 6-k over all graphs (rows v*B + b)
         rows = np.concatenate([np.arange(v * B, (v + 1) * B, dtype=np.int32) for v in range(6, 0, -1)])
         st["level_rows"] = torch.from_numpy(rows).to(dev)
-        st["level_ptr"] = np.array([0, B, 2 * B, 3 * B, 4 * B, 5 * B, 6 * B, 6 * B], np.int32)
+        st["level_ptr"] = np.array([0, B, 2 * B, 3 * B, 4 * B, 5 * B, 6 * B, 6 * B], np.int32)   # (no rare-first order: both halves)
         st["ws"] = m._workspace(_abi.OP_TRAIN, B, fresh=True)
 
         def body(inv_batch):
@@ -95,7 +95,7 @@ class Trainer:
             self.g.zero_()
             _lib.check(L.dxvae_elbo_step(
                 m._flat.data_ptr(), B, st["Xn"].data_ptr(), st["cls"].data_ptr(), st["adj"].data_ptr(), 6,
-                st["level_ptr"].ctypes.data, st["level_rows"].data_ptr(), st["eps"].data_ptr(), self.w[0], self.w[1],
+                st["level_ptr"].ctypes.data, st["level_rows"].data_ptr(), None, st["eps"].data_ptr(), self.w[0], self.w[1],
                 self.w[2], inv_batch, st["loss5"].data_ptr(), None, None, self.g.data_ptr(), st["ws"].data_ptr(),
                 st["ws"].numel(), m._prec(), None, None, s), "dxvae_elbo_step")
 

@@ -38,7 +38,7 @@
 extern "C" {
 #endif
 
-#define DXVAE_ABI_VERSION 2
+#define DXVAE_ABI_VERSION 3
 #define DXVAE_N_NODES 7
 #define DXVAE_N_PARAMS 21
 #define DXVAE_SIZE_X 27
@@ -77,7 +77,8 @@ int dxvae_param_entry(int k, dxvae_param_entry_t* out); /* k in [0,53) */
  * ids b*7+v (sources ascending), per-edge feedback marks (0 forward src>dst, 1 back
  * edge src<dst, 2 self-loop), encode level per node and the level schedule (operator
  * rows v*B+b grouped by level, ascending).  All pointers are HOST pointers.
- * edge_ptr has B+1 entries; indices/eflags need edge_ptr[B] entries; level_ptr needs 8;
+ * edge_ptr has B+1 entries; indices/eflags need edge_ptr[B] entries; level_ptr needs 16 (8 offsets, then at
+ * [8 + L] the number of leading rows of level L that a feedback back-edge arrives at);
  * level_rows needs 6*B.  *n_levels receives the number of operator levels. */
 int dxvae_batch_build_host(int64_t B, const int32_t* edge_ptr_host, const int8_t* src_host, const int8_t* dst_host,
                            uint64_t* adj_host, int32_t* indptr_host, int32_t* indices_host, uint8_t* eflags_host,
@@ -85,7 +86,7 @@ int dxvae_batch_build_host(int64_t B, const int32_t* edge_ptr_host, const int8_t
                            int32_t* n_levels);
 
 /* Device level schedule from adjacency masks (same outputs as the host batcher's
- * level / level_ptr / level_rows).  level_ptr (8 ints) is written on the device AND
+ * level / level_ptr / level_rows).  level_ptr (16 ints, same layout) is written on the device AND
  * copied to level_ptr_host (pinned or pageable) — this call synchronises the stream. */
 int dxvae_batch_schedule(int64_t B, const uint64_t* adj, uint8_t* level, int32_t* level_ptr, int32_t* level_rows,
                          int32_t* level_ptr_host, void* workspace, size_t workspace_bytes, void* stream);
@@ -98,7 +99,9 @@ int dxvae_batch_schedule(int64_t B, const uint64_t* adj, uint8_t* level, int32_t
  * the same function of the inputs; NULL runs every step on every graph as the reference does).
  * Lists 21..26 hold the graphs with a self-loop on node vi = 1..6: the second propagate of a new node
  * (model.py:337, x_loop = selfloop * x) differs from the first only on those graphs.
- * step_ptr: 28 ints; step_rows: up to 27*B ints.  The device form synchronises the stream to
+ * Lists 27..32 hold the graphs in which node x = 0..5 has an edge to a higher node (a feedback back-edge leaves x):
+ * only those rows need the "in" half of x's gate / mapper projections in the decoder.
+ * step_ptr: 34 ints; step_rows: up to 33*B ints.  The device form synchronises the stream to
  * return step_ptr_host. */
 int dxvae_batch_steps(int64_t B, const uint64_t* adj, int32_t* step_ptr, int32_t* step_rows, int32_t* step_ptr_host,
                       void* workspace, size_t workspace_bytes, void* stream);
@@ -137,11 +140,15 @@ size_t dxvae_workspace_bytes(int op, int64_t B);
 
 /* ---- encode (model.py:200-212; _propagate :151-198 with encode=True) ------------- *
  * level_ptr_host (n_levels+1 ints, HOST) and level_rows (DEVICE) come from the batcher.
+ * level_rare_host (HOST, n_levels ints, or NULL): the batcher orders every level with the rows a feedback
+ * back-edge ARRIVES at first and reports how many there are (level_ptr[8 + L]); only those rows need the "out"
+ * half of their gate / mapper projections, so the encoder computes that half on the prefix alone.  NULL (or a
+ * schedule that is not ordered that way) computes both halves for every row; results are identical.
  * Outputs mu, std (B,128).  With keep=1 the workspace retains what encode_bwd needs
  * (workspace must then be the DXVAE_OP_TRAIN one). */
 int dxvae_encode_fwd(const float* weights, int64_t B, const float* Xn, const uint64_t* adj, int32_t n_levels,
-                     const int32_t* level_ptr_host, const int32_t* level_rows, float* mu, float* std_,
-                     void* workspace, size_t workspace_bytes, int keep, int precision, void* stream);
+                     const int32_t* level_ptr_host, const int32_t* level_rows, const int32_t* level_rare_host, float* mu,
+                     float* std_, void* workspace, size_t workspace_bytes, int keep, int precision, void* stream);
 
 /* ---- reparameterise (model.py:284, Normal.rsample): z = mu + std*eps -------------- */
 int dxvae_reparameterize(int64_t n, const float* mu, const float* std_, const float* eps, float* z, void* stream);
@@ -163,7 +170,8 @@ int dxvae_decode_greedy(const float* weights, int64_t B, const float* z, float* 
  * loss5 / grads across ranks.  grads: flat blob, same layout as weights, ACCUMULATED
  * into (caller zeroes it). */
 int dxvae_elbo_step(const float* weights, int64_t B, const float* Xn, const int32_t* cls, const uint64_t* adj,
-                    int32_t n_levels, const int32_t* level_ptr_host, const int32_t* level_rows, const float* eps,
+                    int32_t n_levels, const int32_t* level_ptr_host, const int32_t* level_rows,
+                    const int32_t* level_rare_host, const float* eps,
                     float w_env, float w_frq, float w_kld, float inv_batch, float* loss5, float* mu_out,
                     float* std_out, float* grads, void* workspace, size_t workspace_bytes, int precision,
                     const int32_t* step_ptr_host, const int32_t* step_rows, void* stream);
@@ -179,7 +187,8 @@ int dxvae_loss_step(const float* weights, int64_t B, const float* Xn, const int3
                     size_t workspace_bytes, int precision, const int32_t* step_ptr_host, const int32_t* step_rows,
                     void* stream);
 int dxvae_encode_bwd(const float* weights, int64_t B, const float* Xn, const uint64_t* adj, int32_t n_levels,
-                     const int32_t* level_ptr_host, const int32_t* level_rows, const float* std_, const float* dmu,
+                     const int32_t* level_ptr_host, const int32_t* level_rows, const int32_t* level_rare_host,
+                     const float* std_, const float* dmu,
                      const float* dstd, float* grads, void* workspace, size_t workspace_bytes, int precision,
                      void* stream);
 

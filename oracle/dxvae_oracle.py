@@ -360,8 +360,11 @@ def batch_oracle(edge_lists):
       level    u8[B,7]    encode level: 0 if no adjacent x>v, else 1+max level(x)  
       level_ptr i32[nl+1], level_rows i32[6B]
                           operator nodes (v>=1) grouped by level; row id = v*B+b
-                          (node-major), ascending inside a level.  Node 0 rows are not
-                          listed: the root step always runs last over all B graphs.
+                          (node-major).  Inside a level the rows a feedback back-edge ARRIVES
+                          at (an edge u->v with u < v) come first, then the rest; ascending in
+                          each group.  Node 0 rows are not listed: the root step always runs
+                          last over all B graphs.
+      level_rare i32[nl]  size of the first group of every level
     """
     B = len(edge_lists)
     adj = np.zeros(B, np.uint64)
@@ -385,13 +388,18 @@ def batch_oracle(edge_lists):
         eflags += [fl for _, fl in lst]
         indptr[n + 1] = len(indices)
     nl = int(level[:, 1:].max()) + 1 if B else 0
-    rows, ptr = [], [0]
+    rows, ptr, rare = [], [0], []
+    sets = [set(zip([int(s) for s in src], [int(d) for d in dst])) for src, dst in edge_lists]
+    back_in = lambda b, v: any((u, v) in sets[b] for u in range(v))
     for L in range(nl):
-        r = sorted(v * B + b for b in range(B) for v in range(1, 7) if level[b, v] == L)
-        rows += r
+        r1 = sorted(v * B + b for b in range(B) for v in range(1, 7) if level[b, v] == L and back_in(b, v))
+        r2 = sorted(v * B + b for b in range(B) for v in range(1, 7) if level[b, v] == L and not back_in(b, v))
+        rows += r1 + r2
+        rare.append(len(r1))
         ptr.append(len(rows))
     return dict(adj=adj, indptr=indptr, indices=np.array(indices, np.int32), eflags=np.array(eflags, np.uint8),
-                level=level, level_ptr=np.array(ptr, np.int32), level_rows=np.array(rows, np.int32))
+                level=level, level_ptr=np.array(ptr, np.int32), level_rows=np.array(rows, np.int32),
+                level_rare=np.array(rare, np.int32))
 
 
 # =============================================================================

@@ -65,7 +65,7 @@ class Emu:
         eptr[1:] = np.cumsum([len(e[0]) for e in edge_lists])
         out = dict(adj=np.zeros(B, np.uint64), indptr=np.zeros(7 * B + 1, np.int32),
                    indices=np.zeros(max(1, len(src)), np.int32), eflags=np.zeros(max(1, len(src)), np.uint8),
-                   level=np.zeros((B, 7), np.uint8), level_ptr=np.zeros(8, np.int32),
+                   level=np.zeros((B, 7), np.uint8), level_ptr=np.zeros(16, np.int32),
                    level_rows=np.zeros(6 * B, np.int32))
         nl = C.c_int32(0)
         _abi.check(L, L.dxvae_batch_build_host(B, ptr(eptr), ptr(src), ptr(dst), ptr(out["adj"]), ptr(out["indptr"]),
@@ -86,7 +86,7 @@ class Emu:
         ws = np.zeros(L.dxvae_workspace_bytes(_abi.OP_ENCODE, B), np.uint8)
         mu = np.zeros((B, 128), np.float32); sd = np.zeros((B, 128), np.float32)
         _abi.check(L, L.dxvae_encode_fwd(ptr(self.blob), B, ptr(bt["Xn"]), ptr(bt["adj"]), bt["n_levels"],
-                                         ptr(bt["level_ptr"]), ptr(bt["level_rows"]), ptr(mu), ptr(sd), ptr(ws),
+                                         ptr(bt["level_ptr"]), ptr(bt["level_rows"]), ptr(bt["level_ptr"][8:]), ptr(mu), ptr(sd), ptr(ws),
                                          ws.nbytes, 0, 0, None), "encode")
         return mu, sd
 
@@ -95,7 +95,7 @@ class Emu:
         B = bt["B"]
         sp = sr = None
         if compact:
-            sp = np.zeros(28, np.int32); sr = np.zeros(27 * B, np.int32)
+            sp = np.zeros(34, np.int32); sr = np.zeros(33 * B, np.int32)
             _abi.check(L, L.dxvae_batch_steps_host(B, ptr(bt["adj"]), ptr(sp), ptr(sr)), "steps")
         ws = np.zeros(L.dxvae_workspace_bytes(_abi.OP_TRAIN, B), np.uint8)
         loss5 = np.zeros(5, np.float32)
@@ -103,7 +103,7 @@ class Emu:
         g = np.zeros(self.total, np.float32) if grads else None
         eps = np.ascontiguousarray(eps, np.float32)
         _abi.check(L, L.dxvae_elbo_step(ptr(self.blob), B, ptr(bt["Xn"]), ptr(bt["cls"]), ptr(bt["adj"]),
-                                        bt["n_levels"], ptr(bt["level_ptr"]), ptr(bt["level_rows"]), ptr(eps),
+                                        bt["n_levels"], ptr(bt["level_ptr"]), ptr(bt["level_rows"]), ptr(bt["level_ptr"][8:]), ptr(eps),
                                         w[0], w[1], w[2], inv_batch or 1.0 / B, ptr(loss5), ptr(mu), ptr(sd), ptr(g),
                                         ptr(ws), ws.nbytes, 0, ptr(sp), ptr(sr), None), "elbo")
         return loss5, mu, sd, g

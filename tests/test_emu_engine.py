@@ -33,6 +33,7 @@ def test_batcher_matches_set_logic(setup):
         n = len(ob["level_ptr"])
         assert bt["n_levels"] == n - 1
         assert np.array_equal(bt["level_ptr"][:n], ob["level_ptr"])
+        assert np.array_equal(bt["level_ptr"][8:8 + n - 1], ob["level_rare"])
 
 
 def test_step_schedule_matches_set_logic(setup):
@@ -43,7 +44,7 @@ def test_step_schedule_matches_set_logic(setup):
     for edges in (util.random_edge_lists(50, 0.3, 4), util.random_edge_lists(9, 0.0, 5), util.random_edge_lists(9, 1.0, 6)):
         ob = O.batch_oracle(edges)
         B = len(edges)
-        sp = np.zeros(28, np.int32); sr = np.zeros(27 * B, np.int32)
+        sp = np.zeros(34, np.int32); sr = np.zeros(33 * B, np.int32)
         assert L.dxvae_batch_steps_host(B, E_.ptr(ob["adj"]), E_.ptr(sp), E_.ptr(sr)) == 0
         t = 0
         for vi in range(1, 7):
@@ -55,7 +56,11 @@ def test_step_schedule_matches_set_logic(setup):
             want = [b for b, (s, d) in enumerate(edges) if (vi, vi) in set(zip(s, d))]
             assert list(sr[sp[t]:sp[t + 1]]) == want, ("self", vi)
             t += 1
-        assert sp[27] == sum(sp[i + 1] - sp[i] for i in range(27))
+        for x in range(6):                           # lists 27..32: graphs where node x has an edge to a higher node
+            want = [b for b, (s, d) in enumerate(edges) if any(si == x and di > x for si, di in zip(s, d))]
+            assert list(sr[sp[t]:sp[t + 1]]) == want, ("back-edge source", x)
+            t += 1
+        assert t == 33 and sp[33] == sum(sp[i + 1] - sp[i] for i in range(33))
 
 
 def test_encode_matches_oracle(setup):

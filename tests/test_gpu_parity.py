@@ -92,12 +92,13 @@ def test_device_schedule_matches_set_logic(lib):
         ob = O.batch_oracle(E)
         adj = torch.tensor([mask_from_edges(*e) for e in E], dtype=torch.int64, device="cuda")
         d = type("D", (), {})()
-        d.B, d.adj, d.level_ptr = n, adj, np.zeros(8, np.int32)
+        d.B, d.adj, d.level_ptr = n, adj, np.zeros(16, np.int32)
         m._schedule(d)
         assert np.array_equal(d.level.cpu().numpy(), ob["level"])
         assert d.n_levels == len(ob["level_ptr"]) - 1
         assert np.array_equal(d.level_ptr[:d.n_levels + 1], ob["level_ptr"])
         assert np.array_equal(d.level_rows.cpu().numpy(), ob["level_rows"])
+        assert np.array_equal(d.level_ptr[8:8 + d.n_levels], ob["level_rare"])
 
 
 def test_host_batcher_matches_set_logic(lib):
@@ -430,9 +431,9 @@ def test_device_step_schedule_matches_set_logic(lib):
     for n, p, seed in ((3000, 0.2, 1), (1, 1.0, 2), (1025, 0.0, 3), (2500, 1.0, 4)):
         E = util.random_edge_lists(n, p, seed)
         adj = torch.tensor([mask_from_edges(*e) for e in E], dtype=torch.int64, device="cuda")
-        sp = np.zeros(28, np.int32)
-        sr = torch.full((27 * n,), -1, dtype=torch.int32, device="cuda")
-        spd = torch.empty(28, dtype=torch.int32, device="cuda")
+        sp = np.zeros(34, np.int32)
+        sr = torch.full((33 * n,), -1, dtype=torch.int32, device="cuda")
+        spd = torch.empty(34, dtype=torch.int32, device="cuda")
         ws = m._workspace(_abi.OP_SCHEDULE, n)
         _lib.check(lib.dxvae_batch_steps(n, adj.data_ptr(), spd.data_ptr(), sr.data_ptr(), sp.ctypes.data, ws.data_ptr(),
                                          ws.numel(), st()), "steps")
@@ -447,6 +448,10 @@ def test_device_step_schedule_matches_set_logic(lib):
         for vi in range(1, 7):
             want = [b for b in range(n) if (vi, vi) in sets[b]]
             assert list(sr[sp[t]:sp[t + 1]]) == want, ("self", vi)
+            t += 1
+        for x in range(6):
+            want = [b for b in range(n) if any(s == x and d > x for s, d in sets[b])]
+            assert list(sr[sp[t]:sp[t + 1]]) == want, ("back-edge source", x)
             t += 1
 
 
