@@ -473,10 +473,12 @@ void pad_wih(dx_stream_t st, const float* W, int K, float* Wp) {
     Wp[i] = c < K ? W[n * K + c] : 0.f;
   });
 }
+// dWp rows are in (n, r, z) gate order (the D4 view the cell backward hands to the weight_ih products), the blob
+// is (r, z, n): blob row n takes padded row (n + H) mod 3H.
 void unpad_add_wih(dx_stream_t st, const float* dWp, int K, float* dW) {
   foreach (st, (int64_t)G3 * K, [=] DX_HD(int64_t i) {
     const int c = (int)(i % K); const int64_t n = i / K;
-    dW[i] += dWp[n * XP + c];
+    dW[i] += dWp[((n + H) % G3) * XP + c];
   });
 }
 void mask_features(dx_stream_t st, int64_t rows, int B, const int* row_ids, int row_base, const uint64_t* adj,

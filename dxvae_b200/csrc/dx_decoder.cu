@@ -50,7 +50,7 @@ DecWs carve_dec(Arena& ar, int64_t B, bool train) {
     w.dQ = ar.take<float>(6 * b * 4 * H); w.dgb = ar.take<float>(6 * b * H);
     w.dHi = ar.take<float>(b * H); w.dHc = ar.take<float>(b * H); w.dHin = ar.take<float>(b * H);
     w.dHrun = ar.take<float>(b * H); w.dHc0 = ar.take<float>(b * H);
-    w.dgx = ar.take<float>(b * G3); w.dgxs = ar.take<float>(b * G3); w.dgh = ar.take<float>(b * G3);
+    w.dgx = ar.take<float>(b * 4 * H); w.dgh = w.dgx + H; w.dgxs = nullptr;   // one D4 buffer, two views (CellBwd)
     w.dE1 = ar.take<float>(b * 4 * H); w.dA1 = ar.take<float>(b * 2 * H); w.dA2 = ar.take<float>(b * 2 * H);
     w.dES1 = ar.take<float>(b * 2 * H); w.dHinit = ar.take<float>(b * H); w.dz = ar.take<float>(b * Z);
   } else {
@@ -676,13 +676,13 @@ static void looper_bwd(dx_stream_t st, const Weights& W, const Weights& G, int B
   CellBwd cb{rm, dHi, 0, gates, 0, Hc, 0, w.dgx, nullptr, w.dgh, direct, smode, adj};
   cell_bwd(st, cb, G[P_LD_BIH], G[P_LD_BHH]);
   if (dHc_accum) add_inplace(st, (int64_t)M * H / 4, dHc, direct);
-  linear_dgrad(st, M, G3, H, w.dgh, G3, W[P_LD_WHH], H, dHc, H, ACC_ADD);
-  linear_wgrad(st, M, G3, H, w.dgh, G3, Hc, H, G[P_LD_WHH], H);
+  linear_dgrad(st, M, G3, H, w.dgh, 4 * H, W[P_LD_WHH], H, dHc, H, ACC_ADD);
+  linear_wgrad(st, M, G3, H, w.dgh, 4 * H, Hc, H, G[P_LD_WHH], H);
   // weight_ih gradient: x masked by the self-loop flag (XL), gathered to the active rows when compacted
   if (smode != S_ZERO) {
     const float* xl = w.XL + (size_t)vi * B * XP;
     if (rm.rows) { gather_rows(st, M, XP, rm.rows, const_cast<float*>(xl), w.xc, 0); xl = w.xc; }
-    linear_wgrad(st, M, G3, XP, w.dgx, G3, xl, XP, w.dWihP[1], XP);
+    linear_wgrad(st, M, G3, XP, w.dgx, 4 * H, xl, XP, w.dWihP[1], XP);
   }
   (void)Xi; (void)G;
 }
@@ -736,10 +736,10 @@ void decode_bwd_impl(dx_stream_t st, const Weights& W, const Weights& G, int B, 
         looper_bwd(st, W, G, B, vi, rc, w.dHiC, w.g_l[t], w.Hc[t], S_SELF, adj, Xi, w, w.dHc, false);
         CellBwd cc{rc, w.dHc, 0, w.g_c[t], 0, w.Hin[t], 0, w.dgx, nullptr, w.dgh, w.dHin, S_ONE, adj};
         cell_bwd(st, cc, G[P_CD_BIH], G[P_CD_BHH]);
-        linear_dgrad(st, n, G3, H, w.dgh, G3, W[P_CD_WHH], H, w.dHin, H, ACC_ADD);
-        linear_wgrad(st, n, G3, H, w.dgh, G3, w.Hin[t], H, G[P_CD_WHH], H);
+        linear_dgrad(st, n, G3, H, w.dgh, 4 * H, W[P_CD_WHH], H, w.dHin, H, ACC_ADD);
+        linear_wgrad(st, n, G3, H, w.dgh, 4 * H, w.Hin[t], H, G[P_CD_WHH], H);
         gather_rows(st, n, XP, rows, const_cast<float*>(Xi), w.xc, 0);
-        linear_wgrad(st, n, G3, XP, w.dgx, G3, w.xc, XP, w.dWihP[0], XP);
+        linear_wgrad(st, n, G3, XP, w.dgx, 4 * H, w.xc, XP, w.dWihP[0], XP);
         scatter_rows(st, n, H, rows, w.dHin, w.dHrun, 1);
         RowMap rs{n, B, rows, vj * B};
         MsgBwd mb{rs, w.Pg, w.Pm, W[P_G_B], adj, w.dHrun, 0, w.dPg, w.dPm, w.dgb, 1, vi, vi, 1};
@@ -769,9 +769,9 @@ void decode_bwd_impl(dx_stream_t st, const Weights& W, const Weights& G, int B, 
       looper_bwd(st, W, G, B, vi, rm, w.dHi, w.g_l[t], w.Hc[t], S_SELF, adj, Xi, w, w.dHc, false);
       CellBwd cc{rm, w.dHc, 0, w.g_c[t], 0, w.Hin[t], 0, w.dgx, nullptr, w.dgh, w.dHin, S_ONE, adj};
       cell_bwd(st, cc, G[P_CD_BIH], G[P_CD_BHH]);
-      linear_dgrad(st, B, G3, H, w.dgh, G3, W[P_CD_WHH], H, w.dHin, H, ACC_ADD);
-      linear_wgrad(st, B, G3, H, w.dgh, G3, w.Hin[t], H, G[P_CD_WHH], H);
-      linear_wgrad(st, B, G3, XP, w.dgx, G3, Xi, XP, w.dWihP[0], XP);
+      linear_dgrad(st, B, G3, H, w.dgh, 4 * H, W[P_CD_WHH], H, w.dHin, H, ACC_ADD);
+      linear_wgrad(st, B, G3, H, w.dgh, 4 * H, w.Hin[t], H, G[P_CD_WHH], H);
+      linear_wgrad(st, B, G3, XP, w.dgx, 4 * H, Xi, XP, w.dWihP[0], XP);
       add_inplace(st, (int64_t)bH / 4, w.dHrun, w.dHin);
       // message of vj was part of this and every later aggregate of node vi
       RowMap rs{B, B, nullptr, vj * B};
@@ -813,7 +813,7 @@ void decode_bwd_impl(dx_stream_t st, const Weights& W, const Weights& G, int B, 
     // combiner with H_in = 0: only input weights / biases receive gradient
     CellBwd c0{rm, w.dHc0, 0, w.g_c0[vi], 0, nullptr, 0, w.dgx, nullptr, w.dgh, nullptr, S_ONE, adj};
     cell_bwd(st, c0, G[P_CD_BIH], G[P_CD_BHH]);
-    linear_wgrad(st, B, G3, XP, w.dgx, G3, Xi, XP, w.dWihP[0], XP);
+    linear_wgrad(st, B, G3, XP, w.dgx, 4 * H, Xi, XP, w.dWihP[0], XP);
     // parameter head of node vi read h_{vi-1}
     float* dprev = w.dHd + (size_t)(vi - 1) * bH;
     const float* hprev = w.Hd + (size_t)(vi - 1) * bH;
@@ -855,9 +855,9 @@ void decode_bwd_impl(dx_stream_t st, const Weights& W, const Weights& G, int B, 
     RowMap rm{B, B, nullptr, 0};
     CellBwd cr{rm, w.dHd, 0, w.g_root, 0, w.Hinit, 0, w.dgx, nullptr, w.dgh, w.dHinit, S_ONE, adj};
     cell_bwd(st, cr, G[P_RD_BIH], G[P_RD_BHH]);
-    linear_dgrad(st, B, G3, H, w.dgh, G3, W[P_RD_WHH], H, w.dHinit, H, ACC_ADD);
-    linear_wgrad(st, B, G3, H, w.dgh, G3, w.Hinit, H, G[P_RD_WHH], H);
-    linear_wgrad(st, B, G3, XP, w.dgx, G3, bt.Xn, XP, w.dWihP[2], XP);
+    linear_dgrad(st, B, G3, H, w.dgh, 4 * H, W[P_RD_WHH], H, w.dHinit, H, ACC_ADD);
+    linear_wgrad(st, B, G3, H, w.dgh, 4 * H, w.Hinit, H, G[P_RD_WHH], H);
+    linear_wgrad(st, B, G3, XP, w.dgx, 4 * H, bt.Xn, XP, w.dWihP[2], XP);
   }
   mlp3_bwd(st, W, G, B, P_X0_W0, w.Hinit, SX0 + 32, w.A1[0], w.A2[0], w.dL[0], w, w.dHinit);
   tanh_bwd(st, (int64_t)bH, w.dHinit, w.Hinit);

@@ -30,7 +30,7 @@ EncWs carve_enc(Arena& ar, int64_t B, bool train) {
     w.gc = ar.take<float>(R7 * 4 * H); w.gl = ar.take<float>(R7 * 4 * H);
     w.dH = ar.take<float>(R7 * H); w.dHin = ar.take<float>(R7 * H);
     w.dPg = ar.take<float>(R6 * 2 * H); w.dPm = ar.take<float>(R6 * 2 * H); w.dgb = ar.take<float>(R6 * H);
-    w.dgx = ar.take<float>(R6 * G3); w.dgxs = ar.take<float>(R6 * G3); w.dgh = ar.take<float>(R6 * G3);
+    w.dgx = ar.take<float>(R6 * 4 * H); w.dgh = w.dgx + H; w.dgxs = nullptr;   // one D4 buffer, two views (CellBwd)
     w.dHc = ar.take<float>(R6 * H); w.dsraw = ar.take<float>((size_t)B * Z);
   }
   return w;
@@ -129,9 +129,9 @@ void encode_bwd_impl(dx_stream_t st, const Weights& W, const Weights& G, const B
   RowMap r0{B, B, nullptr, 0};
   CellBwd cr{r0, dH0, 0, w.gc + (size_t)R6 * 4 * H, 0, Hin0, 0, w.dgx, nullptr, w.dgh, dHin0, S_ONE, bt.adj};
   cell_bwd(st, cr, G[P_RE_BIH], G[P_RE_BHH]);
-  linear_dgrad(st, B, G3, H, w.dgh, G3, W[P_RE_WHH], H, dHin0, H, ACC_ADD);
-  linear_wgrad(st, B, G3, H, w.dgh, G3, Hin0, H, G[P_RE_WHH], H);
-  linear_wgrad(st, B, G3, XP, w.dgx, G3, bt.Xn, XP, w.dWihP[2], XP);
+  linear_dgrad(st, B, G3, H, w.dgh, 4 * H, W[P_RE_WHH], H, dHin0, H, ACC_ADD);
+  linear_wgrad(st, B, G3, H, w.dgh, 4 * H, Hin0, H, G[P_RE_WHH], H);
+  linear_wgrad(st, B, G3, XP, w.dgx, 4 * H, bt.Xn, XP, w.dWihP[2], XP);
 
   for (int L = bt.n_levels - 1; L >= 0; --L) {
     const int base = bt.level_ptr[L];
@@ -159,18 +159,18 @@ void encode_bwd_impl(dx_stream_t st, const Weights& W, const Weights& G, const B
     // looper
     CellBwd cl{rm, dH, 0, w.gl + (size_t)base * 4 * H, 0, Hc, 0, w.dgx, nullptr, w.dgh, w.dHc, S_SELF, bt.adj};
     cell_bwd(st, cl, G[P_LE_BIH], G[P_LE_BHH]);
-    linear_dgrad(st, M, G3, H, w.dgh, G3, W[P_LE_WHH], H, w.dHc, H, ACC_ADD);
-    linear_wgrad(st, M, G3, H, w.dgh, G3, Hc, H, G[P_LE_WHH], H);
-    linear_wgrad(st, M, G3, XP, w.dgx, G3, w.XnSL + (size_t)base * XP, XP, w.dWihP[1], XP);   // x masked by the self-loop flag
+    linear_dgrad(st, M, G3, H, w.dgh, 4 * H, W[P_LE_WHH], H, w.dHc, H, ACC_ADD);
+    linear_wgrad(st, M, G3, H, w.dgh, 4 * H, Hc, H, G[P_LE_WHH], H);
+    linear_wgrad(st, M, G3, XP, w.dgx, 4 * H, w.XnSL + (size_t)base * XP, XP, w.dWihP[1], XP);   // x masked by the self-loop flag
     // combiner
     CellBwd cc{rm, w.dHc, 0, w.gc + (size_t)base * 4 * H, 0, L > 0 ? Hin : nullptr, 0, w.dgx, nullptr, w.dgh,
                L > 0 ? dHin : nullptr, S_ONE, bt.adj};
     cell_bwd(st, cc, G[P_CE_BIH], G[P_CE_BHH]);
     if (L > 0) {
-      linear_dgrad(st, M, G3, H, w.dgh, G3, W[P_CE_WHH], H, dHin, H, ACC_ADD);
-      linear_wgrad(st, M, G3, H, w.dgh, G3, Hin, H, G[P_CE_WHH], H);
+      linear_dgrad(st, M, G3, H, w.dgh, 4 * H, W[P_CE_WHH], H, dHin, H, ACC_ADD);
+      linear_wgrad(st, M, G3, H, w.dgh, 4 * H, Hin, H, G[P_CE_WHH], H);
     }
-    linear_wgrad(st, M, G3, XP, w.dgx, G3, Xs, XP, w.dWihP[0], XP);
+    linear_wgrad(st, M, G3, XP, w.dgx, 4 * H, Xs, XP, w.dWihP[0], XP);
   }
   unpad_add_wih(st, w.dWihP[0], SX, G[P_CE_WIH]);
   unpad_add_wih(st, w.dWihP[1], SX, G[P_LE_WIH]);

@@ -83,9 +83,12 @@ inline void cell_fwd(dx_stream_t st, const CellFwd& a) {
 }
 
 // GRU cell backward.  dh: gradient of h' ; outputs (compact [M,.]):
-//   dgx  = [da_r, da_z, da_n]          (bias_ih gradient = column sums)
-//   dgxs = s * dgx  (optional)         (weight_ih gradient uses the masked form)
-//   dgh  = [da_r, da_z, da_n * r]      (bias_hh / weight_hh gradient, and dh_prev += dgh W_hh)
+//   ONE buffer D4[M, 4H] = [da_n | da_r | da_z | da_n * r] serves both gate-gradient matrices as strided views
+//   (8 KB/row written instead of 12):
+//     dgx = D4[:, 0:3H]   = [da_n, da_r, da_z]      weight_ih gradient; its rows come out in (n, r, z) gate order and
+//                                                    unpad_add_wih() folds them back into the (r, z, n) blob order
+//     dgh = D4[:, H:4H]   = [da_r, da_z, da_n * r]  bias_hh / weight_hh gradient, and dh_prev += dgh W_hh
+//   a.dgx points at D4 (a.dgh == a.dgx + H, row pitch 4H for both; a.dgxs is unused)
 //   dhp  = dh * z                      (direct path to h_prev)
 struct CellBwd {
   RowMap rm; const float* dh; int dh_global; const float* gates; int gates_global; const float* hprev;
@@ -118,16 +121,9 @@ DX_HD DX_INLINE void cell_bwd_elem(const CellBwd& a, int m, int n, float4& ar, f
   }
   DX_CELLB(x) DX_CELLB(y) DX_CELLB(z) DX_CELLB(w)
 #undef DX_CELLB
-  float* o = a.dgx + (int64_t)m * G3 + n;
-  st4f(o, ar); st4f(o + H, az); st4f(o + 2 * H, an);
-  if (a.dgxs) {
-    float* os = a.dgxs + (int64_t)m * G3 + n;
-    st4f(os, make_float4(s * ar.x, s * ar.y, s * ar.z, s * ar.w));
-    st4f(os + H, make_float4(s * az.x, s * az.y, s * az.z, s * az.w));
-    st4f(os + 2 * H, make_float4(s * an.x, s * an.y, s * an.z, s * an.w));
-  }
-  float* oh = a.dgh + (int64_t)m * G3 + n;
-  st4f(oh, ar); st4f(oh + H, az); st4f(oh + 2 * H, anr);
+  float* o = a.dgx + (int64_t)m * (4 * H) + n;
+  st4f(o, an); st4f(o + H, ar); st4f(o + 2 * H, az); st4f(o + 3 * H, anr);
+  (void)s;
   if (a.dhp) st4f(a.dhp + (int64_t)(a.dhp_global ? r : m) * H + n, dp);
 }
 
