@@ -292,6 +292,31 @@ def run_ours(args):
             t0 = time.perf_counter(); model.decode(z); torch.cuda.synchronize()
             extra["decode_3xtf32_patches_per_s"] = 16384 / (time.perf_counter() - t0)
             model.decode_precision = "fp32"
+        # cfg3 / cfg4 at their full size (1 M patches), end to end from HOST buffers: packed voices (128 B/patch) ->
+        # on-device _make_graph -> encode -> latents on the host;  z on the host -> greedy decode -> .syx bytes on the host
+        from dxvae_b200.dxdata import graph_to_syx_bytes
+        nfull = args.full_patches
+        if nfull > 0:
+            hv = torch.from_numpy(random_voices(nfull, seed=7)).pin_memory()
+            hz = torch.randn(nfull, 128, generator=torch.Generator().manual_seed(0)).pin_memory()
+            mu_h = torch.empty(nfull, 128).pin_memory(); sd_h = torch.empty(nfull, 128).pin_memory()
+            with torch.no_grad():
+                for prec in ("fp32", "3xtf32"):
+                    model.encode_precision = prec
+                    torch.cuda.synchronize(); t0 = time.perf_counter()
+                    q = model.encode(voices_to_batch(hv))
+                    mu_h.copy_(q.loc, non_blocking=True); sd_h.copy_(q.scale, non_blocking=True)
+                    torch.cuda.synchronize()
+                    extra["cfg3_encode_%d_e2e_%s_patches_per_s" % (nfull, prec)] = nfull / (time.perf_counter() - t0)
+                model.encode_precision = "fp32"
+                for prec in ("fp32", "3xtf32"):
+                    model.decode_precision = prec
+                    torch.cuda.synchronize(); t0 = time.perf_counter()
+                    syx = graph_to_syx_bytes(model.decode(hz))
+                    extra["cfg4_decode_%d_to_syx_e2e_%s_patches_per_s" % (nfull, prec)] = nfull / (time.perf_counter() - t0)
+                    assert len(syx) == 8 + 128 * nfull
+                model.decode_precision = "fp32"
+            del hv, hz, q, mu_h, sd_h, syx
         idx = list(range(128))
         for _ in range(3):
             tr.step(pool, idx)
@@ -346,6 +371,7 @@ def main():
     ap.add_argument("--cpu-patches", type=int, default=2048)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-extra", action="store_true")
+    ap.add_argument("--full-patches", type=int, default=1 << 20, help="size of the cfg3/cfg4 end-to-end extras (0 skips them)")
     ap.add_argument("--precision", default="tf32", choices=["fp32", "tf32"])
     args = ap.parse_args()
     if args.impl == "reference":

@@ -199,7 +199,10 @@ def voices_to_batch(voices, device="cuda"):
     """dxdata.py:174-312 for many voices at once on the GPU: (n,128) uint8 -> DXGraphBatch
     (tensors on `device`)."""
     L = _lib.require_cuda()
-    v = torch.as_tensor(np.ascontiguousarray(voices, np.uint8)).to(device)
+    if torch.is_tensor(voices):                      # (a pinned host tensor uploads without a staging copy)
+        v = voices.to(device, torch.uint8, non_blocking=True).contiguous()
+    else:
+        v = torch.as_tensor(np.array(voices, np.uint8, copy=True)).to(device)
     n = v.shape[0]
     Xg = torch.empty(n, N_NODES, SIZE_X, device=device)
     Pg = torch.empty(n, N_NODES, N_PARAMS, device=device)
