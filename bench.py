@@ -284,9 +284,13 @@ def run_ours(args):
             extra["encode_3xtf32_patches_per_s"] = ne / (time.perf_counter() - t0)
             model.encode_precision = "fp32"
             z = torch.randn(16384, 128, device="cuda")
-            model.decode(z); torch.cuda.synchronize()
+            gdec = model.decode(z); torch.cuda.synchronize()
             t0 = time.perf_counter(); model.decode(z); torch.cuda.synchronize()
             extra["decode_patches_per_s"] = 16384 / (time.perf_counter() - t0)
+            # greedy decode re-propagates only the graphs that gain an edge at a step: its speed depends on how many
+            # edges the (here randomly initialised) model decides, so report that next to the number
+            am = gdec.adj.cpu().numpy().view(np.uint64)
+            extra["decode_mean_edges_per_graph"] = float(np.mean([bin(int(a)).count("1") for a in am[:4096]]))
             model.decode_precision = "3xtf32"
             model.decode(z); torch.cuda.synchronize()
             t0 = time.perf_counter(); model.decode(z); torch.cuda.synchronize()

@@ -54,6 +54,8 @@ DecWs carve_dec(Arena& ar, int64_t B, bool train) {
     w.dE1 = ar.take<float>(b * 4 * H); w.dA1 = ar.take<float>(b * 2 * H); w.dA2 = ar.take<float>(b * 2 * H);
     w.dES1 = ar.take<float>(b * 2 * H); w.dHinit = ar.take<float>(b * H); w.dz = ar.take<float>(b * Z);
   } else {
+    w.U = ar.take<float>(b * 4 * H); w.UC = ar.take<float>(b * 4 * H);
+    w.act_rows = ar.take<int>(b); w.act_cnt = ar.take<int>(64); w.act_flag = ar.take<uint8_t>(b);
     w.Xd = ar.take<float>(7 * b * XP); w.Pn = ar.take<float>(7 * b * XP);
     w.Whi = ar.take<float>((size_t)param_blob_floats()); w.Wlo = ar.take<float>((size_t)param_blob_floats());
     w.xs_hi = ar.take<float>(b * 2 * H); w.xs_lo = ar.take<float>(b * 2 * H);
@@ -298,7 +300,21 @@ static void decide_edges(dx_stream_t st, int B, int vi, int vj, const float* lg,
 struct EdgeHeadP {
   int B, vi, vj; const float* U; const float* Q; const float* W2; const float* b2; const uint64_t* adj; float inv_batch;
   float* l2; float* dl2; float* rowloss; uint8_t* mask; float* dW2; float* db2;
+  // greedy generation (model.py:245-250) instead of the teacher-forced loss: decide both edges from the logits
+  // (sigmoid > 0.5), set them in adj_out, track the decision margin and flag the graphs that gained an edge
+  uint64_t* adj_out = nullptr; float* margins = nullptr; uint8_t* active = nullptr;
 };
+// greedy finish of one graph: returns nothing; l0 = logit of vj -> vi, l1 = logit of vi -> vj
+DX_HD DX_INLINE void edge_head_row_decide(const EdgeHeadP& a, int b, float l0, float l1) {
+  a.l2[(int64_t)b * LD_E] = l0; a.l2[(int64_t)b * LD_E + 1] = l1;
+  const bool on0 = sigmoidf_(l0) > 0.5f, on1 = sigmoidf_(l1) > 0.5f;
+  uint64_t A = a.adj_out[b];
+  if (on0) A |= 1ull << (a.vj * 7 + a.vi);
+  if (on1) A |= 1ull << (a.vi * 7 + a.vj);
+  a.adj_out[b] = A;
+  if (a.margins) a.margins[b] = fminf(a.margins[b], fminf(fabsf(l0), fabsf(l1)));
+  a.active[b] = (uint8_t)((on0 || on1) ? 1 : 0);
+}
 
 DX_HD DX_INLINE void edge_head_row_finish(const EdgeHeadP& a, int b, float l0, float l1, float* dl) {
   const uint64_t A = a.adj[b];
@@ -335,7 +351,8 @@ static __global__ void __launch_bounds__(256, 2) k_edge_head_fwd(const EdgeHeadP
     // target flag of (row lane>>1, output lane&1): issued before the big loads, used after the reduction
     const int rb = r0 + (lane >> 1);
     float tgt = 0.f;
-    if (lane < 2 * EH_R && rb < a.B) {
+    const bool greedy = a.adj_out != nullptr;
+    if (!greedy && lane < 2 * EH_R && rb < a.B) {
       const uint64_t A = a.adj[rb];
       tgt = (lane & 1) ? (float)abit(A, a.vi, a.vj) : (float)abit(A, a.vj, a.vi);
     }
@@ -364,7 +381,7 @@ static __global__ void __launch_bounds__(256, 2) k_edge_head_fwd(const EdgeHeadP
     }
 #pragma unroll
     for (int r = 0; r < EH_R; ++r)
-      if (r0 + r < a.B) a.mask[(int64_t)(r0 + r) * 256 + t] = (uint8_t)mk[r];
+      if (a.mask && r0 + r < a.B) a.mask[(int64_t)(r0 + r) * 256 + t] = (uint8_t)mk[r];
 #pragma unroll
     for (int i = 0; i < 2 * EH_R; ++i) {
       float v = part[i];
@@ -380,6 +397,12 @@ static __global__ void __launch_bounds__(256, 2) k_edge_head_fwd(const EdgeHeadP
       for (int w = 0; w < 8; ++w) l += red[par][w][lane];
       l += bias;
       const bool ok = rb < a.B;
+      if (greedy) {
+        if (wid == 0) {
+          const float l_other = __shfl_down_sync((1u << (2 * EH_R)) - 1u, l, 1);     // the row's second logit (odd lane)
+          if (ok && !(lane & 1)) edge_head_row_decide(a, rb, l, l_other);
+        }
+      } else {
       dl = ok ? (sigmoidf_(l) - tgt) * a.inv_batch : 0.f;
       if (wid == 0) {
         float bce = ok ? bce_logits(l, tgt) : 0.f;
@@ -389,6 +412,7 @@ static __global__ void __launch_bounds__(256, 2) k_edge_head_fwd(const EdgeHeadP
           if (!(lane & 1)) a.rowloss[(int64_t)2 * a.B + rb] += bce * a.inv_batch;
         }
         dbsum += dl;
+      }
       }
     }
     if (a.dW2) {
@@ -423,9 +447,12 @@ static void edge_head_fwd(dx_stream_t, const EdgeHeadP& a) {
     for (int j = 0; j < 4 * H; ++j) {
       const float e = fmaxf(a.U[(int64_t)b * 4 * H + j] + a.Q[(int64_t)b * 4 * H + j], 0.f);
       l0 += e * a.W2[j]; l1 += e * a.W2[4 * H + j];
-      if ((j & 7) == 0) a.mask[(int64_t)b * 256 + j / 8] = 0;
-      if (e > 0.f) a.mask[(int64_t)b * 256 + j / 8] |= (uint8_t)(1u << (j & 7));
+      if (a.mask) {
+        if ((j & 7) == 0) a.mask[(int64_t)b * 256 + j / 8] = 0;
+        if (e > 0.f) a.mask[(int64_t)b * 256 + j / 8] |= (uint8_t)(1u << (j & 7));
+      }
     }
+    if (a.adj_out) { edge_head_row_decide(a, b, l0 + a.b2[0], l1 + a.b2[1]); continue; }
     float dl[2];
     edge_head_row_finish(a, b, l0, l1, dl);
     if (a.dW2) {
@@ -616,10 +643,48 @@ void decode_fwd_impl(dx_stream_t st, const Weights& W, int B, const float* z, co
         CellFwd cl{rc, w.gxl[vi], w.gh, W[P_LD_BIH], W[P_LD_BHH], w.Hc[t], 0, w.Hi[t], 0, w.g_l[t], 0, S_SELF, adj};
         cl.gx_by_graph = 1; cl.hout2 = Hcur;
         cell_fwd(st, cl);
-        linear_fwd(st, n, 4 * H, H, w.Hi[t], H, W[P_E_W0], 2 * H, nullptr, w.UC, 4 * H);
-        scatter_rows(st, n, 4 * H, rows, w.UC, w.U, 0);
+        if (vj > 0) {                                          // (no head reads U after the node's last step)
+          linear_fwd(st, n, 4 * H, H, w.Hi[t], H, W[P_E_W0], 2 * H, nullptr, w.UC, 4 * H);
+          scatter_rows(st, n, 4 * H, rows, w.UC, w.U, 0);
+        }
       }
       if (vi < NN - 1) node_projections(st, W, B, vi, w, io.bt);
+      continue;
+    }
+    if (!train) {
+      // Greedy generation with the same identity-step compaction: after each pair of edge decisions only the
+      // graphs that gained an edge re-propagate (the others would recompute the state they already have).  The
+      // active rows are compacted on the device and their count read back (one small sync per step) to size the
+      // products; U = Hd[vi] W_e0[:, :512]^T is kept current, so the edge head is element-wise for all graphs.
+      float* Hcur = w.Hd + (size_t)vi * B * H;
+      copy_async(st, Hcur, w.Hi_p2[vi], sizeof(float) * (size_t)B * H);
+      linear_fwd(st, B, 4 * H, H, w.Hi_p2[vi], H, W[P_E_W0], 2 * H, nullptr, w.U, 4 * H);
+      for (int vj = vi - 1; vj >= 0; --vj, ++t) {
+        EdgeHeadP eh{B, vi, vj, w.U, w.Q + (size_t)vj * B * 4 * H, W[P_E_W2], W[P_E_B2], nullptr, 0.f, w.l2[t], nullptr,
+                     nullptr, nullptr, nullptr, nullptr};
+        eh.adj_out = io.adj_out; eh.margins = io.margins; eh.active = w.act_flag;
+        edge_head_fwd(st, eh);
+        const int n = compact_flags(st, B, w.act_flag, w.act_rows, w.act_cnt);
+        if (n <= 0) continue;
+        RowMap rc{n, B, w.act_rows, vi * B};
+        float* HinC = w.Hin[t]; float* HcC = w.Hc[t]; float* HiC = w.Hi[t];       // (one shared scratch each when not training)
+        MsgFwd mf{rc, w.Pg, w.Pm, W[P_G_B], adj, w.Hrun, 0, vj, vj, 1};
+        mf.hin_by_graph = 1; mf.hin_copy = HinC;
+        msg_fwd(st, mf);
+        linear_fwd(st, n, G3, H, HinC, H, W[P_CD_WHH], H, nullptr, w.gh, G3);
+        CellFwd cc{rc, w.gxc[vi], w.gh, W[P_CD_BIH], W[P_CD_BHH], HinC, 0, HcC, 0, nullptr, 0, S_ONE, adj};
+        cc.gx_by_graph = 1;
+        cell_fwd(st, cc);
+        linear_fwd(st, n, G3, H, HcC, H, W[P_LD_WHH], H, nullptr, w.gh, G3);
+        CellFwd cl{rc, w.gxl[vi], w.gh, W[P_LD_BIH], W[P_LD_BHH], HcC, 0, HiC, 0, nullptr, 0, S_SELF, adj};
+        cl.gx_by_graph = 1; cl.hout2 = Hcur;
+        cell_fwd(st, cl);
+        if (vj > 0) {                                          // (no head reads U after the node's last step)
+          linear_fwd(st, n, 4 * H, H, HiC, H, W[P_E_W0], 2 * H, nullptr, w.UC, 4 * H);
+          scatter_rows(st, n, 4 * H, w.act_rows, w.UC, w.U, 0);
+        }
+      }
+      if (vi < NN - 1) node_projections(st, W, B, vi, w);
       continue;
     }
     const float* Hi_prev = w.Hi_p2[vi];

@@ -61,6 +61,7 @@ struct DecWs {
   float *WihP[3], *dWihP[3], *XL, *xc;   // padded input weights / grads (comb, loop, root), masked features (7B,32), compact x rows
   // greedy only
   float *Xd, *Pn;
+  int *act_rows, *act_cnt; uint8_t* act_flag;   // graphs that gained an edge at the current step (device-compacted)
   float *Whi, *Wlo, *xs_hi, *xs_lo;   // 3xTF32 operand splits (weights blob, activation scratch B x 1024)
   // backward temporaries
   float *dHd, *dPg, *dPm, *dQ, *dgb, *dHi, *dHc, *dHin, *dHrun, *dHc0, *dgx, *dgxs, *dgh, *dE1, *dA1, *dA2, *dES1,

@@ -99,10 +99,7 @@ struct CellBwd {
 // One (row m, 4 hidden units at n) element of the backward pass; returns the bias-gradient
 // contributions (ar, az, an, an*r) of that element.
 DX_HD DX_INLINE void cell_bwd_elem(const CellBwd& a, int m, int n, float4& ar, float4& az, float4& an, float4& anr) {
-  const int r = a.rm.r(m);
-  float s = 1.f;
-  if (a.smode == S_ZERO) s = 0.f;
-  else if (a.smode == S_SELF) { const int b = r % a.rm.B, v = r / a.rm.B; s = (float)abit(a.adj[b], v, v); }
+  const int r = a.rm.r(m);   // (the gate gradients do not depend on the input multiplier s: it only scales x in the weight_ih product)
   const float4 d = ld4f(a.dh + (int64_t)(a.dh_global ? r : m) * H + n);
   const float* g = a.gates + (int64_t)(a.gates_global ? r : m) * (4 * H) + n;
   const float4 R = ld4f(g), Zg = ld4f(g + H), Ng = ld4f(g + 2 * H), NH = ld4f(g + 3 * H);
@@ -123,7 +120,6 @@ DX_HD DX_INLINE void cell_bwd_elem(const CellBwd& a, int m, int n, float4& ar, f
 #undef DX_CELLB
   float* o = a.dgx + (int64_t)m * (4 * H) + n;
   st4f(o, an); st4f(o + H, ar); st4f(o + 2 * H, az); st4f(o + 3 * H, anr);
-  (void)s;
   if (a.dhp) st4f(a.dhp + (int64_t)(a.dhp_global ? r : m) * H + n, dp);
 }
 

@@ -29,6 +29,39 @@ inline void zero_async(dx_stream_t s, void* p, size_t bytes) {
 inline void copy_async(dx_stream_t s, void* dst, const void* src, size_t bytes) {
   if (bytes) cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, s);
 }
+// Row compaction: rows[0..n) = ascending indices i < B with flag[i] != 0; *count = n.  One block scans the flags
+// in 1024-wide chunks (ballot + popc inside warps, warp totals through shared memory).
+static __global__ void __launch_bounds__(1024) k_compact_flags(int B, const uint8_t* __restrict__ flag, int* __restrict__ rows,
+                                                               int* __restrict__ count) {
+  __shared__ int wsum[32];
+  __shared__ int base;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  if (threadIdx.x == 0) base = 0;
+  __syncthreads();
+  for (int i0 = 0; i0 < B; i0 += 1024) {
+    const int i = i0 + threadIdx.x;
+    const bool f = i < B && flag[i] != 0;
+    const unsigned bal = __ballot_sync(0xffffffffu, f);
+    if (lane == 0) wsum[wid] = __popc(bal);
+    __syncthreads();
+    int off = base, tot = 0;
+    for (int k = 0; k < 32; ++k) { if (k < wid) off += wsum[k]; tot += wsum[k]; }
+    if (f) rows[off + __popc(bal & ((1u << lane) - 1))] = i;
+    __syncthreads();
+    if (threadIdx.x == 0) base += tot;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *count = base;
+}
+// Compacts and returns the count on the host (synchronises the stream: the caller sizes its next launches with it).
+inline int compact_flags(dx_stream_t s, int B, const uint8_t* flag, int* rows, int* count_dev) {
+  k_compact_flags<<<1, 1024, 0, s>>>(B, flag, rows, count_dev);
+  ++g_launches;
+  int n = 0;
+  cudaMemcpyAsync(&n, count_dev, sizeof(int), cudaMemcpyDeviceToHost, s);
+  cudaStreamSynchronize(s);
+  return n;
+}
 inline int check_launch(const char* what) {
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) { set_error("%s: CUDA error %s", what, cudaGetErrorString(e)); return 1; }
@@ -42,6 +75,13 @@ inline void foreach (dx_stream_t, int64_t n, F f) {
 }
 inline void zero_async(dx_stream_t, void* p, size_t bytes) { if (bytes) memset(p, 0, bytes); }
 inline void copy_async(dx_stream_t, void* dst, const void* src, size_t bytes) { if (bytes) memcpy(dst, src, bytes); }
+inline int compact_flags(dx_stream_t, int B, const uint8_t* flag, int* rows, int* count_dev) {
+  int n = 0;
+  for (int i = 0; i < B; ++i) if (flag[i]) rows[n++] = i;
+  *count_dev = n;
+  ++g_launches;
+  return n;
+}
 inline int check_launch(const char*) { return 0; }
 #endif
 
