@@ -375,6 +375,29 @@ def test_api_compositions_and_rng_seams(lib):
         m.encode([])
 
 
+def test_decode_ragged_batch_sizes_are_position_independent(lib):
+    """Batches of 1, 3, 129 and 1000 graphs decode to exactly the rows of the 1000-graph batch (the greedy path compacts
+    the graphs that gain an edge at every step: row lists of any length, including empty ones, must work)."""
+    m, _ = make_model(0, 3.0)
+    z = torch.randn(1000, 128, generator=torch.Generator().manual_seed(9))
+    full = m.decode(z)
+    for n in (1, 3, 129):
+        part = m.decode(z[:n])
+        assert torch.equal(part.params, full.params[:n]) and torch.equal(part.adj, full.adj[:n]) and torch.equal(part.X, full.X[:n])
+    last = m.decode(z[-1:])
+    assert torch.equal(last.params, full.params[-1:]) and torch.equal(last.adj, full.adj[-1:])
+    # a model that decides no edge at all (every step's active list is empty) and one that decides all of them
+    named = dict(m.named_parameters())
+    for shift in (-50.0, 50.0):
+        eb, sb = named["h_to_edge.2.bias"], named["h_to_edge_self.2.bias"]
+        eb0, sb0 = eb.data.clone(), sb.data.clone()
+        eb.data.add_(shift); sb.data.add_(shift)
+        g = m.decode(z[:65])
+        nbits = [bin(int(a) & ((1 << 49) - 1)).count("1") for a in g.adj.cpu().numpy().view(np.uint64)]
+        assert set(nbits) == ({0} if shift < 0 else {48})          # 6 self-loops + 21 pairs x 2 directions
+        eb.data.copy_(eb0); sb.data.copy_(sb0)
+
+
 def test_decode_large_batch_properties(lib):
     """Full-size style checks that need no oracle: chunking invariance, legal parameter ranges,
     decode -> .syx -> _make_graph round trip."""
