@@ -157,7 +157,9 @@ int dxvae_reparameterize(int64_t n, const float* mu, const float* std_, const fl
  * z (B,128) -> Xg (B,7,27), Pg (B,7,21), adj (B).  logits_out (optional, may be NULL):
  * (B,34) fp32 decision logits [6 self-loop | 21 x (in,out) ... ] is NOT provided; use
  * margins (B) = min |logit| over the 48 edge decisions of each graph, for tie-aware
- * parity checks. */
+ * parity checks.  After each pair of edge decisions only the graphs that gained an edge
+ * re-propagate; their count is read back to size the next launches, so this call
+ * synchronises the stream (21 small copies per call) and must not be stream-captured. */
 int dxvae_decode_greedy(const float* weights, int64_t B, const float* z, float* Xg, float* Pg, uint64_t* adj,
                         float* margins, void* workspace, size_t workspace_bytes, int precision, void* stream);
 
