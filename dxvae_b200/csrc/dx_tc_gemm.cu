@@ -589,6 +589,12 @@ EncodeTiledFn get_encode() {
   }
   return fn;
 }
+inline CUtensorMapL2promotion l2_promo() {
+  static const char* e = getenv("DX_TC_L2PROMO");
+  if (e && e[0] == '2') return CU_TENSOR_MAP_L2_PROMOTION_L2_256B;
+  if (e && e[0] == '0') return CU_TENSOR_MAP_L2_PROMOTION_NONE;
+  return CU_TENSOR_MAP_L2_PROMOTION_L2_128B;
+}
 // 2-D fp32 tensor [rows][cols] with row pitch ld (floats); box = box_cols x box_rows
 bool make_map(CUtensorMap* m, const float* ptr, int64_t rows, int64_t cols, int64_t ld, int box_cols, int box_rows,
               bool mn_major, bool plain_f32 = false) {
@@ -600,7 +606,7 @@ bool make_map(CUtensorMap* m, const float* ptr, int64_t rows, int64_t cols, int6
   cuuint32_t estr[2] = {1, 1};
   return enc(m, plain_f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_TFLOAT32, 2, const_cast<float*>(ptr), gdim, gstr, box, estr,
              CU_TENSOR_MAP_INTERLEAVE_NONE, mn_major ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
-             CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+             l2_promo(),
              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
