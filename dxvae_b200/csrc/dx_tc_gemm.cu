@@ -645,6 +645,20 @@ bool launch_tc(dx_stream_t s, const GemmP& g, const float* A_lo = nullptr, const
     const int maxs = (g.K + TBK * 16 - 1) / (TBK * 16);       // >= 512 reduction rows per split
     splits = want < 1 ? 1 : (want > maxs ? maxs : want);
   }
+  // Few-row products with a long reduction (the dgrads of a small batch: M = 128, K = 1536..2048, a handful of tiles):
+  // split the reduction as well, so that more than a handful of SMs stream the weight matrix.  The partial results go
+  // out through TMA reduce-add; a plain store becomes zero-fill + reduce-add.  (No bias / added matrix: they would be
+  // applied once per split; the relu gate is a 0/1 factor and distributes over the partial sums.)
+  int accum = g.accum;
+  if (g.accum != ACC_ATOMIC && tma_store && gm * gn < 48 && g.K >= 512 && !g.bias && (!g.add || g.act == ACT_GATE) &&
+      (g.act == ACT_NONE || g.act == ACT_GATE) && !getenv("DX_TC_NO_SMALL_SPLIT")) {
+    const int want = 96 / (gm * gn), maxs = g.K / 256;
+    splits = want < 1 ? 1 : (want > maxs ? maxs : want);
+    if (splits > 1) {
+      if (g.accum == ACC_STORE) cudaMemset2DAsync(g.C, (size_t)g.ldc * 4, 0, (size_t)g.N * 4, (size_t)g.M, s);
+      accum = ACC_ADD;
+    }
+  }
   int k_chunk = (g.K + splits - 1) / splits;
   k_chunk = (k_chunk + TBK - 1) / TBK * TBK;
   splits = (g.K + k_chunk - 1) / k_chunk;
@@ -653,7 +667,7 @@ bool launch_tc(dx_stream_t s, const GemmP& g, const float* A_lo = nullptr, const
   if (want_dbg && !dbg) cudaMalloc(&dbg, 256 * sizeof(long long));
   if (want_dbg) cudaMemsetAsync(dbg, 0, 256 * sizeof(long long), s);
   static const bool m_fast = getenv("DX_TC_M_FAST") != nullptr;
-  TcParams p{g.M, g.N, g.K, g.C, g.ldc, g.c_idx, g.bias, g.add, g.ldadd, g.act, g.accum, k_chunk, tma_store ? 1 : 0, add_tma ? 1 : 0,
+  TcParams p{g.M, g.N, g.K, g.C, g.ldc, g.c_idx, g.bias, g.add, g.ldadd, g.act, accum, k_chunk, tma_store ? 1 : 0, add_tma ? 1 : 0,
              m_fast ? 0 : 1, want_dbg ? dbg : nullptr};
   static int num_sms = 0;
   if (!num_sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev); }
