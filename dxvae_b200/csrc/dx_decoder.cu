@@ -508,6 +508,44 @@ static void head_sum(dx_stream_t st, const HeadSumP& a) {
   });
 }
 
+// y[m] = a[m, :] . w + b for a one-output head (h_to_edge_self.2: N = 1, K = 1024).  A GEMM tile wastes 63/64 of its
+// columns and, at small batches, runs on two CTAs; here one warp takes a row (128-bit loads, shuffle reduction).
+#ifndef DX_EMU
+static __global__ void __launch_bounds__(256) k_rowdot(int M, int K, const float* __restrict__ A, int64_t lda,
+                                                       const float* __restrict__ w, const float* __restrict__ b,
+                                                       float* __restrict__ out, int64_t ldo) {
+  const int lane = threadIdx.x & 31;
+  const int warp = (int)((blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5), nw = (int)((gridDim.x * (int64_t)blockDim.x) >> 5);
+  for (int m = warp; m < M; m += nw) {
+    const float* a = A + (int64_t)m * lda;
+    float s = 0.f;
+#pragma unroll 8
+    for (int k = lane * 4; k < K; k += 128) {
+      const float4 x = ld4f(a + k), y = ld4f(w + k);
+      s = fmaf(x.x, y.x, s); s = fmaf(x.y, y.y, s); s = fmaf(x.z, y.z, s); s = fmaf(x.w, y.w, s);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) out[(int64_t)m * ldo] = s + (b ? b[0] : 0.f);
+  }
+}
+static void rowdot(dx_stream_t st, int M, int K, const float* A, int64_t lda, const float* w, const float* b, float* out, int64_t ldo) {
+  int blocks = (M + 7) / 8;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  k_rowdot<<<blocks, 256, 0, st>>>(M, K, A, lda, w, b, out, ldo);
+  ++g_launches;
+}
+#else
+static void rowdot(dx_stream_t, int M, int K, const float* A, int64_t lda, const float* w, const float* b, float* out, int64_t ldo) {
+  for (int m = 0; m < M; ++m) {
+    float s = 0.f;
+    for (int k = 0; k < K; ++k) s = fmaf(A[(int64_t)m * lda + k], w[k], s);
+    out[(int64_t)m * ldo] = s + (b ? b[0] : 0.f);
+  }
+  ++g_launches;
+}
+#endif
+
 // =============================================================================================
 // forward
 // =============================================================================================
@@ -593,7 +631,7 @@ void decode_fwd_impl(dx_stream_t st, const Weights& W, int B, const float* z, co
     cell_fwd(st, p1);
     // self-loop head (model.py:236/331)
     linear_fwd(st, B, 2 * H, H, w.Hi_p1[vi], H, W[P_ES_W0], H, W[P_ES_B0], w.ES1[vi], 2 * H, ACT_RELU);
-    linear_fwd(st, B, 1, 2 * H, w.ES1[vi], 2 * H, W[P_ES_W2], 2 * H, W[P_ES_B2], w.ls[vi], LD_E);
+    rowdot(st, B, 2 * H, w.ES1[vi], 2 * H, W[P_ES_W2], W[P_ES_B2], w.ls[vi], LD_E);
     if (train) loss_edge(st, B, vi, vi, w.ls[vi], 1, adj, io.lw, w.rowloss, w.dls[vi]);
     else decide_edges(st, B, vi, vi, w.ls[vi], 1, io.adj_out, io.margins);
     // P2 (model.py:240/337): same H_in = 0, x_loop = s*x
