@@ -846,6 +846,7 @@ void decode_bwd_impl(dx_stream_t st, const Weights& W, const Weights& G, int B, 
         scatter_rows(st, n, H, rows, w.dHin, w.dHrun, 1);
         RowMap rs{n, B, rows, vj * B};
         MsgBwd mb{rs, w.Pg, w.Pm, W[P_G_B], adj, w.dHrun, 0, w.dPg, w.dPm, w.dgb, 1, vi, vi, 1};
+        mb.lazy_in = 1;                                          // the "in" half only exists on back-edge rows
         msg_bwd(st, mb);
       }
       // U = Hi_p2 W^T (the state every graph had before its first edge): read by the heads up to the first active step

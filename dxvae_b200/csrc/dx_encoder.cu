@@ -145,6 +145,7 @@ void encode_bwd_impl(dx_stream_t st, const Weights& W, const Weights& G, const B
     MsgBwd mb{rm, w.Pg + (size_t)base * 2 * H, w.Pm + (size_t)base * 2 * H, W[P_G_B], bt.adj, w.dHin, 0, w.dPg, w.dPm,
               w.dgb, 0, -1, 0, 0};
     mb.pos = w.pos; mb.p_compact = 1;
+    mb.out_rows = bt.level_rare ? bt.level_rare[L] : -1;      // rows past the back-edge-target prefix never read their "out" half
     msg_bwd(st, mb);
     const int Mr = bt.level_rare ? bt.level_rare[L] : M;      // rows whose "out" half exists (leading rows of the level)
     for (int half = 0; half < 2; ++half) {

@@ -243,6 +243,9 @@ struct MsgBwd {
   int64_t dh_vstride; float* dPg; float* dPm; float* dgb; int out_global; int v_lo, v_hi; int accum;
   const int* pos = nullptr;   // optional: dhin row of target (v,b) is pos[v*B+b]
   int p_compact = 0;          // 1: this row's own Pg/Pm are indexed by m (pointer pre-offset), else by r
+  // halves nobody reads are not written (DESIGN.md "projection halves"):
+  int out_rows = -1;          // >= 0 (encoder, accum = 0): only rows m < out_rows can have an "out" flag; the others skip that half
+  int lazy_in = 0;            // 1 (decoder, accum = 1): the "in" half is read-modify-written only when an "in" flag is set
 };
 
 inline void msg_bwd(dx_stream_t st, const MsgBwd& a) {
@@ -254,7 +257,16 @@ inline void msg_bwd(dx_stream_t st, const MsgBwd& a) {
     const int64_t o = a.out_global ? r : m;
     float* dgp = a.dPg + o * (2 * H) + n; float* dpp = a.dPm + o * (2 * H) + n; float* dbp = a.dgb + o * H + n;
     float4 dgi = f4zero(), dgo = f4zero(), dpi = f4zero(), dpo = f4zero(), db = f4zero();
-    if (a.accum) { dgi = ld4f(dgp); dgo = ld4f(dgp + H); dpi = ld4f(dpp); dpo = ld4f(dpp + H); db = ld4f(dbp); }
+    bool any_in = false;
+    if (a.lazy_in) {
+      const int l0 = a.v_lo < 0 ? 0 : a.v_lo, h0 = a.v_lo < 0 ? x - 1 : a.v_hi;
+      for (int v = l0; v <= h0; ++v) any_in = any_in || abit(A, x, v);
+    }
+    const bool touch_in = !a.lazy_in || any_in;
+    if (a.accum) {
+      if (touch_in) { dgi = ld4f(dgp); dpi = ld4f(dpp); }
+      dgo = ld4f(dgp + H); dpo = ld4f(dpp + H); db = ld4f(dbp);
+    }
     const int lo = a.v_lo < 0 ? 0 : a.v_lo, hi = a.v_lo < 0 ? x - 1 : a.v_hi;
     const int64_t own = a.p_compact ? m : r;
     const float* gp = a.Pg + own * (2 * H) + n; const float* pp = a.Pm + own * (2 * H) + n;
@@ -276,7 +288,9 @@ inline void msg_bwd(dx_stream_t st, const MsgBwd& a) {
       DX_MSGB(x) DX_MSGB(y) DX_MSGB(z) DX_MSGB(w)
 #undef DX_MSGB
     }
-    st4f(dgp, dgi); st4f(dgp + H, dgo); st4f(dpp, dpi); st4f(dpp + H, dpo); st4f(dbp, db);
+    if (touch_in) { st4f(dgp, dgi); st4f(dpp, dpi); }
+    if (a.out_rows < 0 || m < a.out_rows) { st4f(dgp + H, dgo); st4f(dpp + H, dpo); }
+    st4f(dbp, db);
   });
 }
 
