@@ -54,7 +54,7 @@ int elbo_step(dx_stream_t st, const float* weights, const Batch& bt, const float
   reparameterize(st, (int64_t)B * Z, t.mu, t.sd, eps, t.d.z);
   zero_async(st, t.d.rowloss, sizeof(float) * 4 * (size_t)B);
   DecIO io{true, &bt, lw, nullptr, nullptr};
-  if (grads) { Weights Gf(grads); io.dW2 = Gf[P_E_W2]; io.db2 = Gf[P_E_B2]; }
+  if (grads) { Weights Gf(grads); io.dW2 = Gf[P_E_W2]; io.db2 = Gf[P_E_B2]; io.db0 = Gf[P_E_B0]; }
   decode_fwd_impl(st, W, B, t.d.z, t.d, io);
   kld_rows(st, B, t.mu, t.sd, lw, t.d.rowloss);
   loss_reduce(st, B, t.d.rowloss, loss5);
@@ -82,7 +82,7 @@ int loss_step(dx_stream_t st, const float* weights, const Batch& bt, const float
   reparameterize(st, (int64_t)B * Z, mu, sd, eps, d.z);
   zero_async(st, d.rowloss, sizeof(float) * 4 * (size_t)B);
   DecIO io{true, &bt, lw, nullptr, nullptr};
-  if (grads) { Weights Gf(grads); io.dW2 = Gf[P_E_W2]; io.db2 = Gf[P_E_B2]; }
+  if (grads) { Weights Gf(grads); io.dW2 = Gf[P_E_W2]; io.db2 = Gf[P_E_B2]; io.db0 = Gf[P_E_B0]; }
   decode_fwd_impl(st, W, B, d.z, d, io);
   kld_rows(st, B, mu, sd, lw, d.rowloss);
   loss_reduce(st, B, d.rowloss, loss5);

@@ -300,6 +300,7 @@ static void decide_edges(dx_stream_t st, int B, int vi, int vj, const float* lg,
 struct EdgeHeadP {
   int B, vi, vj; const float* U; const float* Q; const float* W2; const float* b2; const uint64_t* adj; float inv_batch;
   float* l2; float* dl2; float* rowloss; uint8_t* mask; float* dW2; float* db2;
+  float* db0 = nullptr;   // optional (with dW2): gradient slot of h_to_edge.0.bias; receives sum_b mask * (dl0 W2[0] + dl1 W2[1])
   // greedy generation (model.py:245-250) instead of the teacher-forced loss: decide both edges from the logits
   // (sigmoid > 0.5), set them in adj_out, track the decision margin and flag the graphs that gained an edge
   uint64_t* adj_out = nullptr; float* margins = nullptr; uint8_t* active = nullptr;
@@ -344,6 +345,9 @@ static __global__ void __launch_bounds__(256, 2) k_edge_head_fwd(const EdgeHeadP
   }
 #pragma unroll
   for (int k = 0; k < 8; ++k) { acc0[k] = 0.f; acc1[k] = 0.f; }
+  float accb[8];                                       // the head's pre-activation gradient summed over rows (h_to_edge.0.bias)
+#pragma unroll
+  for (int k = 0; k < 8; ++k) accb[k] = 0.f;
   float dbsum = 0.f;                                   // lanes 0..2*EH_R-1 of warp 0: sum of their dl
   const float bias = a.b2[lane & 1];
   int par = 0;
@@ -421,12 +425,20 @@ static __global__ void __launch_bounds__(256, 2) k_edge_head_fwd(const EdgeHeadP
         const float d0 = __shfl_sync(0xffffffffu, dl, 2 * r), d1 = __shfl_sync(0xffffffffu, dl, 2 * r + 1);
 #pragma unroll
         for (int k = 0; k < 8; ++k) { acc0[k] = fmaf(d0, e[r][k], acc0[k]); acc1[k] = fmaf(d1, e[r][k], acc1[k]); }
+        if (a.db0) {
+#pragma unroll
+          for (int k = 0; k < 8; ++k) accb[k] += e[r][k] > 0.f ? d0 * w0[k] + d1 * w1[k] : 0.f;
+        }
       }
     }
   }
   if (a.dW2) {
 #pragma unroll
     for (int k = 0; k < 8; ++k) { atomicAdd(a.dW2 + c0 + k, acc0[k]); atomicAdd(a.dW2 + 4 * H + c0 + k, acc1[k]); }
+    if (a.db0) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) atomicAdd(a.db0 + c0 + k, accb[k]);
+    }
     if (wid == 0) {                                    // db2[c] = sum over rows: fold lanes of equal parity
       float v = dbsum;
       v += __shfl_down_sync(0xffffffffu, v, 4); v += __shfl_down_sync(0xffffffffu, v, 2);
@@ -459,6 +471,7 @@ static void edge_head_fwd(dx_stream_t, const EdgeHeadP& a) {
       for (int j = 0; j < 4 * H; ++j) {
         const float e = fmaxf(a.U[(int64_t)b * 4 * H + j] + a.Q[(int64_t)b * 4 * H + j], 0.f);
         a.dW2[j] += dl[0] * e; a.dW2[4 * H + j] += dl[1] * e;
+        if (a.db0 && e > 0.f) a.db0[j] += dl[0] * a.W2[j] + dl[1] * a.W2[4 * H + j];
       }
       a.db2[0] += dl[0]; a.db2[1] += dl[1];
     }
@@ -665,6 +678,7 @@ void decode_fwd_impl(dx_stream_t st, const Weights& W, int B, const float* z, co
         // fused edge head: the E1 buffer of the step only stores the relu bit-mask (256 B/row)
         EdgeHeadP eh{B, vi, vj, w.U, w.Q + (size_t)vj * B * 4 * H, W[P_E_W2], W[P_E_B2], adj, io.lw.inv_batch, w.l2[t], w.dl2[t],
                      w.rowloss, reinterpret_cast<uint8_t*>(w.E1[t]), io.dW2, io.db2};
+        eh.db0 = io.db0;
         edge_head_fwd(st, eh);
         const int n = io.bt->step_ptr[t + 1] - io.bt->step_ptr[t];
         if (n <= 0) continue;
@@ -950,7 +964,7 @@ void decode_bwd_impl(dx_stream_t st, const Weights& W, const Weights& G, int B, 
     }
     linear_dgrad(st, B, 4 * H, H, dQ, 4 * H, W[P_E_W0] + H, 2 * H, dprev, H, ACC_ADD);
     linear_wgrad(st, B, 4 * H, H, dQ, 4 * H, hprev, H, G[P_E_W0] + H, 2 * H);
-    colsum_accum(st, B, 4 * H, dQ, 4 * H, G[P_E_B0]);
+    if (!compact) colsum_accum(st, B, 4 * H, dQ, 4 * H, G[P_E_B0]);   // (compacted steps: the fused forward head summed it)
     colsum_accum(st, B, H, w.dgb + (size_t)j * bH, H, G[P_G_B]);
     t_end = t0;
   }

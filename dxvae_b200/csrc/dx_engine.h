@@ -76,6 +76,7 @@ struct DecIO {
   float* margins;         // greedy, optional
   float* dW2 = nullptr;   // train + compacted steps: gradient slots of h_to_edge.2.{weight,bias}; the fused edge
   float* db2 = nullptr;   //   head accumulates them during the forward pass (NULL: loss only, no gradients)
+  float* db0 = nullptr;   // likewise h_to_edge.0.bias (= column sums of every head's pre-activation gradient)
 };
 
 // Gate / mapper projections of a node state (gate.0.weight, mapper.0.weight: (H, 2H)), by half:
