@@ -28,7 +28,10 @@ def build():
     if os.path.exists(OUT) and all(os.path.getmtime(OUT) >= os.path.getmtime(d) for d in deps):
         return OUT
     os.makedirs(os.path.dirname(OUT), exist_ok=True)
-    cmd = ["g++", "-std=c++17", "-O2", "-DDX_EMU", "-fPIC", "-shared", "-x", "c++"] + srcs + ["-o", OUT]
+    # DX_EMU_ASAN=1 (with LD_PRELOAD=$(g++ -print-file-name=libasan.so)): the same orchestration and functors under
+    # AddressSanitizer — the nearest thing to compute-sanitizer for the host-side indexing of the hot path
+    san = ["-fsanitize=address", "-fno-omit-frame-pointer", "-g"] if os.environ.get("DX_EMU_ASAN") else []
+    cmd = ["g++", "-std=c++17", "-O2", "-DDX_EMU", "-fPIC", "-shared"] + san + ["-x", "c++"] + srcs + ["-o", OUT]
     subprocess.check_call(cmd)
     return OUT
 
