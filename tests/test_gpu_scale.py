@@ -140,3 +140,30 @@ def test_train_step_is_a_batch_mean_at_benchmark_size(lib, precision, tol_l, tol
         a, b = g_all[lo:lo + p.numel()], gs[lo:lo + p.numel()]
         rel = (a - b).abs().max().item() / (a.abs().max().item() + 1e-30)
         assert rel <= tol_g, (n, rel)
+
+
+def test_tf32_and_fp32_training_trajectories_agree(lib):
+    """Twelve AdamW steps on 8192 synthetic patches from the same initial weights and the same injected noise: the
+    tensor-core path (TF32 products, compacted schedules) must follow the FP32 FFMA path — total loss within 2e-3
+    relative at every step — and both must descend."""
+    from dxvae_b200 import DXVAE
+    from dxvae_b200.dxdata import voices_to_batch
+    from dxvae_b200.synth import random_voices
+    from dxvae_b200.train import Trainer
+    B = 8192
+    pool = voices_to_batch(random_voices(B, seed=11))
+    idx = list(range(B))
+    traj = {}
+    for prec in ("fp32", "tf32"):
+        torch.manual_seed(0)
+        m = DXVAE(); m.verbose = False; m.precision = prec
+        tr = Trainer(m, lr=1e-3)
+        g = torch.Generator(device="cuda").manual_seed(5)
+        losses = []
+        for step in range(12):
+            eps = torch.randn(B, 128, device="cuda", generator=g)
+            losses.append(tr.step(pool, idx, eps=eps)[0].item())
+        traj[prec] = losses
+        assert all(np.isfinite(losses)) and losses[-1] < 0.9 * losses[0], (prec, losses)
+    for a, b in zip(traj["fp32"], traj["tf32"]):
+        assert abs(a - b) <= 2e-3 * abs(a), (traj["fp32"], traj["tf32"])
