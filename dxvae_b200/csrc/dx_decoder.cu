@@ -492,34 +492,58 @@ struct HeadSumP {
   const uint8_t* mask[6]; const float* dl[6]; int vj[6];
   const float* W2; float* out;
 };
-static void head_sum(dx_stream_t st, const HeadSumP& a) {
-  foreach (st, (int64_t)a.M * 256, [=] DX_HD(int64_t idx) {
-    const int m = (int)(idx >> 8); const int tc = (int)(idx & 255), c0 = tc * 8;
-    const int64_t b = a.rows ? a.rows[m] : m;
-    const uint64_t A = a.adj[b];
-    const float4 wa0 = ld4f(a.W2 + c0), wa1 = ld4f(a.W2 + c0 + 4), wb0 = ld4f(a.W2 + 4 * H + c0), wb1 = ld4f(a.W2 + 4 * H + c0 + 4);
-    const float w0[8] = {wa0.x, wa0.y, wa0.z, wa0.w, wa1.x, wa1.y, wa1.z, wa1.w};
-    const float w1[8] = {wb0.x, wb0.y, wb0.z, wb0.w, wb1.x, wb1.y, wb1.z, wb1.w};
-    float g[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-    // the (at most 6) mask bytes and dl pairs are loaded up front: independent loads, no serial chain
-    unsigned mk[6]; float d0[6], d1[6];
+DX_HD DX_INLINE void head_sum_item(const HeadSumP& a, int m, int tc, const float* w0, const float* w1) {
+  const int64_t b = a.rows ? a.rows[m] : m;
+  const uint64_t A = a.adj[b];
+  float g[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  // the (at most 6) mask bytes and dl pairs are loaded up front: independent loads, no serial chain
+  unsigned mk[6]; float d0[6], d1[6];
+#ifndef DX_EMU
 #pragma unroll
-    for (int k = 0; k < 6; ++k) {
-      const int kk = k < a.n ? k : 0;
-      mk[k] = a.mask[kk][b * 256 + tc]; d0[k] = a.dl[kk][b * LD_E]; d1[k] = a.dl[kk][b * LD_E + 1];
-    }
-    bool live = true;
+#endif
+  for (int k = 0; k < 6; ++k) {
+    const int kk = k < a.n ? k : 0;
+    mk[k] = a.mask[kk][b * 256 + tc];
+    const float2 dd = *reinterpret_cast<const float2*>(a.dl[kk] + b * LD_E);
+    d0[k] = dd.x; d1[k] = dd.y;
+  }
+  bool live = true;
+#ifndef DX_EMU
 #pragma unroll
-    for (int k = 0; k < 6; ++k) {
-      if (k < a.n && live) {
-        for (int e = 0; e < 8; ++e) g[e] += ((mk[k] >> e) & 1u) ? d0[k] * w0[e] + d1[k] * w1[e] : 0.f;
-        if (a.until_active && (abit(A, a.vj[k], a.vi) | abit(A, a.vi, a.vj[k]))) live = false;
-      }
+#endif
+  for (int k = 0; k < 6; ++k) {
+    if (k < a.n && live) {
+      for (int e = 0; e < 8; ++e) g[e] += ((mk[k] >> e) & 1u) ? d0[k] * w0[e] + d1[k] * w1[e] : 0.f;
+      if (a.until_active && (abit(A, a.vj[k], a.vi) | abit(A, a.vi, a.vj[k]))) live = false;
     }
-    float* o = a.out + (int64_t)m * 4 * H + c0;
-    st4f(o, make_float4(g[0], g[1], g[2], g[3])); st4f(o + 4, make_float4(g[4], g[5], g[6], g[7]));
-  });
+  }
+  float* o = a.out + (int64_t)m * 4 * H + tc * 8;
+  st4f(o, make_float4(g[0], g[1], g[2], g[3])); st4f(o + 4, make_float4(g[4], g[5], g[6], g[7]));
 }
+#ifndef DX_EMU
+// thread = one group of 8 columns (its two W2 slices stay in registers), blocks stride over the rows
+static __global__ void __launch_bounds__(256, 4) k_head_sum(const HeadSumP a) {
+  const int tc = threadIdx.x, c0 = tc * 8;
+  float w0[8], w1[8];
+  {
+    const float4 x0 = ld4f(a.W2 + c0), x1 = ld4f(a.W2 + c0 + 4), y0 = ld4f(a.W2 + 4 * H + c0), y1 = ld4f(a.W2 + 4 * H + c0 + 4);
+    w0[0] = x0.x; w0[1] = x0.y; w0[2] = x0.z; w0[3] = x0.w; w0[4] = x1.x; w0[5] = x1.y; w0[6] = x1.z; w0[7] = x1.w;
+    w1[0] = y0.x; w1[1] = y0.y; w1[2] = y0.z; w1[3] = y0.w; w1[4] = y1.x; w1[5] = y1.y; w1[6] = y1.z; w1[7] = y1.w;
+  }
+  for (int m = blockIdx.x; m < a.M; m += gridDim.x) head_sum_item(a, m, tc, w0, w1);
+}
+static void head_sum(dx_stream_t st, const HeadSumP& a) {
+  if (a.M <= 0) return;
+  k_head_sum<<<a.M < 148 * 8 ? a.M : 148 * 8, 256, 0, st>>>(a);
+  ++g_launches;
+}
+#else
+static void head_sum(dx_stream_t, const HeadSumP& a) {
+  for (int m = 0; m < a.M; ++m)
+    for (int tc = 0; tc < 256; ++tc) head_sum_item(a, m, tc, a.W2 + tc * 8, a.W2 + 4 * H + tc * 8);
+  ++g_launches;
+}
+#endif
 
 // y[m] = a[m, :] . w + b for a one-output head (h_to_edge_self.2: N = 1, K = 1024).  A GEMM tile wastes 63/64 of its
 // columns and, at small batches, runs on two CTAs; here one warp takes a row (128-bit loads, shuffle reduction).
