@@ -833,8 +833,25 @@ void decode_bwd_impl(dx_stream_t st, const Weights& W, const Weights& G, int B, 
   const uint64_t* adj = bt.adj;
   const size_t bH = (size_t)B * H;
   zero_async(st, w.dHd, sizeof(float) * 7 * bH);
-  zero_async(st, w.dPg, sizeof(float) * 6 * (size_t)B * 2 * H);
-  zero_async(st, w.dPm, sizeof(float) * 6 * (size_t)B * 2 * H);
+  if (bt.step_ptr) {
+    // compacted steps: msg_bwd accumulates the "out" halves for every graph, the "in" halves only on the rows of the
+    // back-edge-source lists (and only those are read back): zero exactly that
+    zero2d_async(st, w.dPg + H, sizeof(float) * 2 * H, sizeof(float) * H, (size_t)6 * B);
+    zero2d_async(st, w.dPm + H, sizeof(float) * 2 * H, sizeof(float) * H, (size_t)6 * B);
+    for (int x = 0; x < 6; ++x) {
+      const int tl = NSTEP + 6 + x, n = bt.step_ptr[tl + 1] - bt.step_ptr[tl];
+      if (n <= 0) continue;
+      const int* rows = bt.step_rows + bt.step_ptr[tl];
+      float* pg = w.dPg + (size_t)x * B * 2 * H; float* pm = w.dPm + (size_t)x * B * 2 * H;
+      foreach (st, (int64_t)n * (H / 4), [=] DX_HD(int64_t i) {
+        const int64_t r = rows[i / (H / 4)]; const int c = (int)(i % (H / 4)) * 4;
+        st4f(pg + r * 2 * H + c, f4zero()); st4f(pm + r * 2 * H + c, f4zero());
+      });
+    }
+  } else {
+    zero_async(st, w.dPg, sizeof(float) * 6 * (size_t)B * 2 * H);
+    zero_async(st, w.dPm, sizeof(float) * 6 * (size_t)B * 2 * H);
+  }
   if (!bt.step_ptr) zero_async(st, w.dQ, sizeof(float) * 6 * (size_t)B * 4 * H);   // (compacted steps store dQ whole)
   zero_async(st, w.dgb, sizeof(float) * 6 * bH);
   for (int k = 0; k < 3; ++k) zero_async(st, w.dWihP[k], sizeof(float) * G3 * XP);
@@ -845,7 +862,7 @@ void decode_bwd_impl(dx_stream_t st, const Weights& W, const Weights& G, int B, 
     const float* Xi = bt.Xn + (size_t)vi * B * XP;
     RowMap rm{B, B, nullptr, vi * B};
     const int t0 = t_end - vi;       // step index of vj = vi-1 ; vj = 0 is t_end-1
-    copy_async(st, w.dHi, w.dHd + (size_t)vi * bH, sizeof(float) * bH);
+    float* const dHi = w.dHd + (size_t)vi * bH;   // the node's state gradient is consumed in place (no later reader of dHd[vi])
     zero_async(st, w.dHrun, sizeof(float) * bH);
     const bool compact = bt.step_ptr != nullptr;
     if (compact) {
@@ -866,7 +883,7 @@ void decode_bwd_impl(dx_stream_t st, const Weights& W, const Weights& G, int B, 
         if (n <= 0) continue;
         const int* rows = bt.step_rows + bt.step_ptr[t];
         RowMap rc{n, B, rows, vi * B};
-        gather_rows(st, n, H, rows, w.dHi, w.dHiC, 1);
+        gather_rows(st, n, H, rows, dHi, w.dHiC, 1);
         if (vj > 0) {                                        // (the last step's state feeds no later head)
           HeadSumP hs{n, rows, adj, vi, 0, 1, {}, {}, {}, W[P_E_W2], w.UC};
           head_list(hs, vj - 1);
@@ -893,7 +910,7 @@ void decode_bwd_impl(dx_stream_t st, const Weights& W, const Weights& G, int B, 
       head_list(hs, vi - 1);
       head_sum(st, hs);
       linear_wgrad(st, B, 4 * H, H, dU, 4 * H, w.Hi_p2[vi], H, G[P_E_W0], 2 * H);
-      linear_dgrad(st, B, 4 * H, H, dU, 4 * H, W[P_E_W0], 2 * H, w.dHi, H, ACC_ADD);
+      linear_dgrad(st, B, 4 * H, H, dU, 4 * H, W[P_E_W0], 2 * H, dHi, H, ACC_ADD);
       // dQ of node j = vi-1 (consumed below): heads (vi', j) of every later node vi' (all of them are done)
       {
         const int j = vi - 1;
@@ -908,7 +925,7 @@ void decode_bwd_impl(dx_stream_t st, const Weights& W, const Weights& G, int B, 
     for (int vj = 0; vj < vi; ++vj) {
       const int t = t0 + (vi - 1 - vj);
       // looper then combiner of this propagate
-      looper_bwd(st, W, G, B, vi, rm, w.dHi, w.g_l[t], w.Hc[t], S_SELF, adj, Xi, w, w.dHc, false);
+      looper_bwd(st, W, G, B, vi, rm, dHi, w.g_l[t], w.Hc[t], S_SELF, adj, Xi, w, w.dHc, false);
       CellBwd cc{rm, w.dHc, 0, w.g_c[t], 0, w.Hin[t], 0, w.dgx, nullptr, w.dgh, w.dHin, S_ONE, adj};
       cell_bwd(st, cc, G[P_CD_BIH], G[P_CD_BHH]);
       linear_dgrad(st, B, G3, H, w.dgh, 4 * H, W[P_CD_WHH], H, w.dHin, H, ACC_ADD);
@@ -925,7 +942,7 @@ void decode_bwd_impl(dx_stream_t st, const Weights& W, const Weights& G, int B, 
       colsum_accum(st, B, 2, w.dl2[t], LD_E, G[P_E_B2]);
       relu_head_bwd(st, B, 4 * H, 2, w.E1[t], w.dl2[t], LD_E, W[P_E_W2], w.dE1, w.dQ + (size_t)vj * B * 4 * H);
       linear_wgrad(st, B, 4 * H, H, w.dE1, 4 * H, Hi_prev, H, G[P_E_W0], 2 * H);
-      linear_dgrad(st, B, 4 * H, H, w.dE1, 4 * H, W[P_E_W0], 2 * H, w.dHi, H, ACC_STORE);
+      linear_dgrad(st, B, 4 * H, H, w.dE1, 4 * H, W[P_E_W0], 2 * H, dHi, H, ACC_STORE);
     }
     // dHi now holds the gradient of Hi_p2.  P2 and P1 share Hc0.
     int ns = 0; const int* rows_s = nullptr;
@@ -936,12 +953,12 @@ void decode_bwd_impl(dx_stream_t st, const Weights& W, const Weights& G, int B, 
       ns = bt.step_ptr[ts + 1] - bt.step_ptr[ts]; rows_s = bt.step_rows + bt.step_ptr[ts];
       if (ns > 0) {
         RowMap rs{ns, B, rows_s, vi * B};
-        gather_rows(st, ns, H, rows_s, w.dHi, w.dHiC, 1);
+        gather_rows(st, ns, H, rows_s, dHi, w.dHiC, 1);
         gather_rows(st, ns, H, rows_s, w.Hc0[vi], w.Hrun, 0);          // (Hrun is free scratch in the backward pass)
         looper_bwd(st, W, G, B, vi, rs, w.dHiC, w.g_p2[vi], w.Hrun, S_SELF, adj, Xi, w, w.dHc, false);
       }
     } else {
-      looper_bwd(st, W, G, B, vi, rm, w.dHi, w.g_p2[vi], w.Hc0[vi], S_SELF, adj, Xi, w, w.dHc0, false);
+      looper_bwd(st, W, G, B, vi, rm, dHi, w.g_p2[vi], w.Hc0[vi], S_SELF, adj, Xi, w, w.dHc0, false);
     }
     // self-loop head consumed Hi_p1
     linear_wgrad(st, B, 1, 2 * H, w.dls[vi], LD_E, w.ES1[vi], 2 * H, G[P_ES_W2], 2 * H);
@@ -949,8 +966,8 @@ void decode_bwd_impl(dx_stream_t st, const Weights& W, const Weights& G, int B, 
     relu_head_bwd(st, B, 2 * H, 1, w.ES1[vi], w.dls[vi], LD_E, W[P_ES_W2], w.dES1, nullptr);
     linear_wgrad(st, B, 2 * H, H, w.dES1, 2 * H, w.Hi_p1[vi], H, G[P_ES_W0], H);
     colsum_accum(st, B, 2 * H, w.dES1, 2 * H, G[P_ES_B0]);
-    linear_dgrad(st, B, 2 * H, H, w.dES1, 2 * H, W[P_ES_W0], H, w.dHi, H, compact ? ACC_ADD : ACC_STORE);
-    looper_bwd(st, W, G, B, vi, rm, w.dHi, w.g_p1[vi], w.Hc0[vi], S_ZERO, adj, Xi, w, w.dHc0, !compact);
+    linear_dgrad(st, B, 2 * H, H, w.dES1, 2 * H, W[P_ES_W0], H, dHi, H, compact ? ACC_ADD : ACC_STORE);
+    looper_bwd(st, W, G, B, vi, rm, dHi, w.g_p1[vi], w.Hc0[vi], S_ZERO, adj, Xi, w, w.dHc0, !compact);
     if (ns > 0) scatter_rows(st, ns, H, rows_s, w.dHc, w.dHc0, 1);
     // combiner with H_in = 0: only input weights / biases receive gradient
     CellBwd c0{rm, w.dHc0, 0, w.g_c0[vi], 0, nullptr, 0, w.dgx, nullptr, w.dgh, nullptr, S_ONE, adj};

@@ -29,6 +29,10 @@ inline void zero_async(dx_stream_t s, void* p, size_t bytes) {
 inline void copy_async(dx_stream_t s, void* dst, const void* src, size_t bytes) {
   if (bytes) cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, s);
 }
+// zero `rows` rows of `width` bytes, `pitch` bytes apart (a column block of a wider matrix)
+inline void zero2d_async(dx_stream_t s, void* p, size_t pitch, size_t width, size_t rows) {
+  if (width && rows) cudaMemset2DAsync(p, pitch, 0, width, rows, s);
+}
 // Row compaction: rows[0..n) = ascending indices i < B with flag[i] != 0; *count = n.  One block scans the flags
 // in 1024-wide chunks (ballot + popc inside warps, warp totals through shared memory).
 static __global__ void __launch_bounds__(1024) k_compact_flags(int B, const uint8_t* __restrict__ flag, int* __restrict__ rows,
@@ -75,6 +79,9 @@ inline void foreach (dx_stream_t, int64_t n, F f) {
 }
 inline void zero_async(dx_stream_t, void* p, size_t bytes) { if (bytes) memset(p, 0, bytes); }
 inline void copy_async(dx_stream_t, void* dst, const void* src, size_t bytes) { if (bytes) memcpy(dst, src, bytes); }
+inline void zero2d_async(dx_stream_t, void* p, size_t pitch, size_t width, size_t rows) {
+  for (size_t r = 0; r < rows; ++r) memset((char*)p + r * pitch, 0, width);
+}
 inline int compact_flags(dx_stream_t, int B, const uint8_t* flag, int* rows, int* count_dev) {
   int n = 0;
   for (int i = 0; i < B; ++i) if (flag[i]) rows[n++] = i;

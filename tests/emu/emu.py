@@ -86,7 +86,7 @@ class Emu:
     def encode(self, bt):
         L = self.lib
         B = bt["B"]
-        ws = np.zeros(L.dxvae_workspace_bytes(_abi.OP_ENCODE, B), np.uint8)
+        ws = np.full(L.dxvae_workspace_bytes(_abi.OP_ENCODE, B), 0xFF, np.uint8)   # NaN-poisoned: a read of workspace that was never written shows up in the outputs
         mu = np.zeros((B, 128), np.float32); sd = np.zeros((B, 128), np.float32)
         _abi.check(L, L.dxvae_encode_fwd(ptr(self.blob), B, ptr(bt["Xn"]), ptr(bt["adj"]), bt["n_levels"],
                                          ptr(bt["level_ptr"]), ptr(bt["level_rows"]), ptr(bt["level_ptr"][8:]), ptr(mu), ptr(sd), ptr(ws),
@@ -100,7 +100,7 @@ class Emu:
         if compact:
             sp = np.zeros(34, np.int32); sr = np.zeros(33 * B, np.int32)
             _abi.check(L, L.dxvae_batch_steps_host(B, ptr(bt["adj"]), ptr(sp), ptr(sr)), "steps")
-        ws = np.zeros(L.dxvae_workspace_bytes(_abi.OP_TRAIN, B), np.uint8)
+        ws = np.full(L.dxvae_workspace_bytes(_abi.OP_TRAIN, B), 0xFF, np.uint8)   # NaN-poisoned: a read of workspace that was never written shows up in the outputs
         loss5 = np.zeros(5, np.float32)
         mu = np.zeros((B, 128), np.float32); sd = np.zeros((B, 128), np.float32)
         g = np.zeros(self.total, np.float32) if grads else None
@@ -115,7 +115,7 @@ class Emu:
         L = self.lib
         z = np.ascontiguousarray(z, np.float32)
         B = z.shape[0]
-        ws = np.zeros(L.dxvae_workspace_bytes(_abi.OP_DECODE, B), np.uint8)
+        ws = np.full(L.dxvae_workspace_bytes(_abi.OP_DECODE, B), 0xFF, np.uint8)   # NaN-poisoned: a read of workspace that was never written shows up in the outputs
         Xg = np.zeros((B, 7, 27), np.float32); Pg = np.zeros((B, 7, 21), np.float32)
         adj = np.zeros(B, np.uint64); mg = np.zeros(B, np.float32)
         _abi.check(L, L.dxvae_decode_greedy(ptr(self.blob), B, ptr(z), ptr(Xg), ptr(Pg), ptr(adj), ptr(mg), ptr(ws),
