@@ -663,8 +663,13 @@ void decode_fwd_impl(dx_stream_t st, const Weights& W, int B, const float* z, co
                S_ONE, adj};
     cell_fwd(st, c0);
     linear_fwd(st, B, G3, H, w.Hc0[vi], H, W[P_LD_WHH], H, nullptr, w.ghl0, G3);
+    const bool compact = train && io.bt->step_ptr != nullptr;
+    float* const Hcur = w.Hd + (size_t)vi * B * H;   // compacted steps / greedy: the CURRENT state of node vi for every graph
     CellFwd p1{rm, w.gxl[vi], w.ghl0, W[P_LD_BIH], W[P_LD_BHH], w.Hc0[vi], 0, w.Hi_p1[vi], 0, train ? w.g_p1[vi] : nullptr,
                0, S_ZERO, adj};
+    // compacted steps: P2 equals P1 except on the self-loop rows, so P1 also fills the P2 state and the current state
+    // (the self-loop rows are overwritten below) instead of two device copies
+    if (compact) { p1.hout2 = w.Hi_p2[vi]; p1.hout3 = Hcur; }
     cell_fwd(st, p1);
     // self-loop head (model.py:236/331)
     linear_fwd(st, B, 2 * H, H, w.Hi_p1[vi], H, W[P_ES_W0], H, W[P_ES_B0], w.ES1[vi], 2 * H, ACT_RELU);
@@ -672,31 +677,28 @@ void decode_fwd_impl(dx_stream_t st, const Weights& W, int B, const float* z, co
     if (train) loss_edge(st, B, vi, vi, w.ls[vi], 1, adj, io.lw, w.rowloss, w.dls[vi]);
     else decide_edges(st, B, vi, vi, w.ls[vi], 1, io.adj_out, io.margins);
     // P2 (model.py:240/337): same H_in = 0, x_loop = s*x
-    const bool compact = train && io.bt->step_ptr != nullptr;
     if (compact) {
       // x_loop = s*x: P2 repeats P1 exactly on graphs without a self-loop on vi, so it is computed on the
       // self-loop rows only (schedule list NSTEP+vi-1); their gates are stored compactly.
-      copy_async(st, w.Hi_p2[vi], w.Hi_p1[vi], sizeof(float) * (size_t)B * H);
       const int ts = NSTEP + vi - 1, ns = io.bt->step_ptr[ts + 1] - io.bt->step_ptr[ts];
       if (ns > 0) {
         RowMap rs{ns, B, io.bt->step_rows + io.bt->step_ptr[ts], vi * B};
         CellFwd p2{rs, w.gxl[vi], w.ghl0, W[P_LD_BIH], W[P_LD_BHH], w.Hc0[vi], 0, w.UC, 0, w.g_p2[vi], 0, S_SELF, adj};
-        p2.gx_by_graph = 1; p2.gh_by_graph = 1; p2.hprev_by_graph = 1; p2.hout2 = w.Hi_p2[vi];
+        p2.gx_by_graph = 1; p2.gh_by_graph = 1; p2.hprev_by_graph = 1; p2.hout2 = w.Hi_p2[vi]; p2.hout3 = Hcur;
         cell_fwd(st, p2);
       }
     } else {
       CellFwd p2{rm, w.gxl[vi], w.ghl0, W[P_LD_BIH], W[P_LD_BHH], w.Hc0[vi], 0, w.Hi_p2[vi], 0, train ? w.g_p2[vi] : nullptr,
                  0, S_SELF, adj};
+      if (!train) p2.hout2 = Hcur;                         // greedy: the current state starts as the P2 state
       cell_fwd(st, p2);
     }
-    zero_async(st, w.Hrun, sizeof(float) * (size_t)B * H);
+    if (train && !compact) zero_async(st, w.Hrun, sizeof(float) * (size_t)B * H);   // (compacted / greedy steps: first-touch, msg_fwd accum = 2)
     if (compact) {
       // Compacted teacher forcing (DESIGN.md "identity steps"): a re-propagate changes node vi only for
       // graphs where the step adds an edge.  Hd[vi] holds the CURRENT state of node vi for every
       // graph and U = Hd[vi] W_e0[:, :512]^T is kept consistent with it, so the edge head of a step is
       // element-wise for all graphs and the GRU / projection products run on the active rows only.
-      float* Hcur = w.Hd + (size_t)vi * B * H;
-      copy_async(st, Hcur, w.Hi_p2[vi], sizeof(float) * (size_t)B * H);
       linear_fwd(st, B, 4 * H, H, w.Hi_p2[vi], H, W[P_E_W0], 2 * H, nullptr, w.U, 4 * H);
       for (int vj = vi - 1; vj >= 0; --vj, ++t) {
         // fused edge head: the E1 buffer of the step only stores the relu bit-mask (256 B/row)
@@ -708,7 +710,7 @@ void decode_fwd_impl(dx_stream_t st, const Weights& W, int B, const float* z, co
         if (n <= 0) continue;
         const int* rows = io.bt->step_rows + io.bt->step_ptr[t];
         RowMap rc{n, B, rows, vi * B};
-        MsgFwd mf{rc, w.Pg, w.Pm, W[P_G_B], adj, w.Hrun, 0, vj, vj, 1};
+        MsgFwd mf{rc, w.Pg, w.Pm, W[P_G_B], adj, w.Hrun, 0, vj, vj, 2};
         mf.hin_by_graph = 1; mf.hin_copy = w.Hin[t];
         msg_fwd(st, mf);
         linear_fwd(st, n, G3, H, w.Hin[t], H, W[P_CD_WHH], H, nullptr, w.gh, G3);
@@ -732,8 +734,6 @@ void decode_fwd_impl(dx_stream_t st, const Weights& W, int B, const float* z, co
       // graphs that gained an edge re-propagate (the others would recompute the state they already have).  The
       // active rows are compacted on the device and their count read back (one small sync per step) to size the
       // products; U = Hd[vi] W_e0[:, :512]^T is kept current, so the edge head is element-wise for all graphs.
-      float* Hcur = w.Hd + (size_t)vi * B * H;
-      copy_async(st, Hcur, w.Hi_p2[vi], sizeof(float) * (size_t)B * H);
       linear_fwd(st, B, 4 * H, H, w.Hi_p2[vi], H, W[P_E_W0], 2 * H, nullptr, w.U, 4 * H);
       for (int vj = vi - 1; vj >= 0; --vj, ++t) {
         EdgeHeadP eh{B, vi, vj, w.U, w.Q + (size_t)vj * B * 4 * H, W[P_E_W2], W[P_E_B2], nullptr, 0.f, w.l2[t], nullptr,
@@ -744,7 +744,7 @@ void decode_fwd_impl(dx_stream_t st, const Weights& W, int B, const float* z, co
         if (n <= 0) continue;
         RowMap rc{n, B, w.act_rows, vi * B};
         float* HinC = w.Hin[t]; float* HcC = w.Hc[t]; float* HiC = w.Hi[t];       // (one shared scratch each when not training)
-        MsgFwd mf{rc, w.Pg, w.Pm, W[P_G_B], adj, w.Hrun, 0, vj, vj, 1};
+        MsgFwd mf{rc, w.Pg, w.Pm, W[P_G_B], adj, w.Hrun, 0, vj, vj, 2};
         mf.hin_by_graph = 1; mf.hin_copy = HinC;
         msg_fwd(st, mf);
         linear_fwd(st, n, G3, H, HinC, H, W[P_CD_WHH], H, nullptr, w.gh, G3);
@@ -863,7 +863,7 @@ void decode_bwd_impl(dx_stream_t st, const Weights& W, const Weights& G, int B, 
     RowMap rm{B, B, nullptr, vi * B};
     const int t0 = t_end - vi;       // step index of vj = vi-1 ; vj = 0 is t_end-1
     float* const dHi = w.dHd + (size_t)vi * bH;   // the node's state gradient is consumed in place (no later reader of dHd[vi])
-    zero_async(st, w.dHrun, sizeof(float) * bH);
+    if (!bt.step_ptr) zero_async(st, w.dHrun, sizeof(float) * bH);   // (compacted steps accumulate first-touch, below)
     const bool compact = bt.step_ptr != nullptr;
     if (compact) {
       // dHi is the running gradient of the node's current state; a step consumes and clears it on its
@@ -898,7 +898,21 @@ void decode_bwd_impl(dx_stream_t st, const Weights& W, const Weights& G, int B, 
         linear_wgrad(st, n, G3, H, w.dgh, 4 * H, w.Hin[t], H, G[P_CD_WHH], H);
         gather_rows(st, n, XP, rows, const_cast<float*>(Xi), w.xc, 0);
         linear_wgrad(st, n, G3, XP, w.dgx, 4 * H, w.xc, XP, w.dWihP[0], XP);
-        scatter_rows(st, n, H, rows, w.dHin, w.dHrun, 1);
+        {
+          // dHrun[b] += dHin[m]: the running gradient of the aggregate.  Steps are walked with vj ascending, so a row was
+          // written before iff the graph has an edge between vi and some node below vj: first touch stores (no zero fill)
+          const float* src = w.dHin; float* dst = w.dHrun;
+          foreach (st, (int64_t)n * (H / 4), [=] DX_HD(int64_t idx) {
+            const int m = (int)(idx / (H / 4)), c = (int)(idx % (H / 4)) * 4;
+            const int64_t b = rows[m];
+            const uint64_t A = adj[b];
+            bool add = false;
+            for (int x = 0; x < vj; ++x) add = add || (abit(A, x, vi) | abit(A, vi, x));
+            float4 v = ld4f(src + (int64_t)m * H + c);
+            if (add) { const float4 o = ld4f(dst + b * H + c); v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w; }
+            st4f(dst + b * H + c, v);
+          });
+        }
         RowMap rs{n, B, rows, vj * B};
         MsgBwd mb{rs, w.Pg, w.Pm, W[P_G_B], adj, w.dHrun, 0, w.dPg, w.dPm, w.dgb, 1, vi, vi, 1};
         mb.lazy_in = 1;                                          // the "in" half only exists on back-edge rows

@@ -38,6 +38,7 @@ struct CellFwd {
   int smode; const uint64_t* adj;
   int gx_by_graph = 0;        // 1: gx is [B,1536] indexed by the row's graph b (= r % B), not by m
   float* hout2 = nullptr;     // optional second copy of h', [B,512] indexed by b (current state of the node)
+  float* hout3 = nullptr;     // optional third copy, likewise
   int gh_by_graph = 0;        // 1: gh is [B,1536] indexed by the row's graph b
   int hprev_by_graph = 0;     // 1: hprev is [B,512] indexed by the row's graph b
 };
@@ -75,6 +76,7 @@ inline void cell_fwd(dx_stream_t st, const CellFwd& a) {
 #undef DX_CELL
     st4f(a.hout + (int64_t)(a.hout_global ? r : m) * H + n, O);
     if (a.hout2) st4f(a.hout2 + (int64_t)(r % a.rm.B) * H + n, O);
+    if (a.hout3) st4f(a.hout3 + (int64_t)(r % a.rm.B) * H + n, O);
     if (a.gates) {
       float* g = a.gates + (int64_t)(a.gates_global ? r : m) * (4 * H) + n;
       st4f(g, R); st4f(g + H, Zg); st4f(g + 2 * H, Ng); st4f(g + 3 * H, NH);
@@ -200,7 +202,7 @@ inline void cell_bwd(dx_stream_t st, const CellBwd& a, float* dbih = nullptr, fl
 // ------------------------------------------------------------------------------------
 struct MsgFwd {
   RowMap rm; const float* Pg; const float* Pm; const float* bg; const uint64_t* adj; float* hin; int hin_global;
-  int x_lo, x_hi; int accum;
+  int x_lo, x_hi; int accum;   // accum: see msg_fwd
   const int* pos = nullptr;   // optional: row of neighbour (x,b) in Pg/Pm is pos[x*B+b] instead of x*B+b
   int hin_by_graph = 0;       // 1: hin is [B,512] indexed by the row's graph b
   float* hin_copy = nullptr;  // optional compact copy [M,512] of the updated aggregate
@@ -213,8 +215,14 @@ inline void msg_fwd(dx_stream_t st, const MsgFwd& a) {
     const int b = r % a.rm.B, v = r / a.rm.B;
     const uint64_t A = a.adj[b];
     float* out = a.hin + (int64_t)(a.hin_by_graph ? b : (a.hin_global ? r : m)) * H + n;
-    float4 acc = a.accum ? ld4f(out) : f4zero();
     const int lo = a.x_lo < 0 ? v + 1 : a.x_lo, hi = a.x_lo < 0 ? NN - 1 : a.x_hi;
+    // accum: 0 = store, 1 = add to what hin holds, 2 (decoder steps, one neighbour x per call, x descending from v-1) =
+    // add only if an earlier call already wrote this row, i.e. the graph has an edge between v and a neighbour in
+    // (x, v): the first message of a row then needs no zero-initialised aggregate
+    bool add = a.accum == 1;
+    if (a.accum == 2)
+      for (int xe = hi + 1; xe < v; ++xe) add = add || (abit(A, xe, v) | abit(A, v, xe));
+    float4 acc = add ? ld4f(out) : f4zero();
     const float4 bg = ld4f(a.bg + n);
     for (int x = lo; x <= hi; ++x) {
       const float fi = (float)abit(A, x, v), fo = (float)abit(A, v, x);
