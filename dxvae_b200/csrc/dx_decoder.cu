@@ -795,7 +795,7 @@ void decode_fwd_impl(dx_stream_t st, const Weights& W, int B, const float* z, co
 // backward (teacher-forced loss only)
 // =============================================================================================
 static void mlp3_bwd(dx_stream_t st, const Weights& W, const Weights& G, int B, int w0, const float* hin, int nout,
-                     const float* A1, const float* A2, const float* dL, const DecWs& w, float* dhin) {
+                     const float* A1, const float* A2, const float* dL, const DecWs& w, float* dhin, int dhin_accum = ACC_ADD) {
   linear_wgrad(st, B, nout, 2 * H, dL, LD_L, A2, 2 * H, G[w0 + 4], 2 * H);
   colsum_accum(st, B, nout, dL, LD_L, G[w0 + 5]);
   linear_dgrad(st, B, nout, 2 * H, dL, LD_L, W[w0 + 4], 2 * H, w.dA2, 2 * H, ACC_STORE, nullptr, nullptr, A2, 2 * H);   // relu backward fused
@@ -804,7 +804,7 @@ static void mlp3_bwd(dx_stream_t st, const Weights& W, const Weights& G, int B, 
   linear_dgrad(st, B, 2 * H, 2 * H, w.dA2, 2 * H, W[w0 + 2], 2 * H, w.dA1, 2 * H, ACC_STORE, nullptr, nullptr, A1, 2 * H);
   linear_wgrad(st, B, 2 * H, H, w.dA1, 2 * H, hin, H, G[w0], H);
   colsum_accum(st, B, 2 * H, w.dA1, 2 * H, G[w0 + 1]);
-  linear_dgrad(st, B, 2 * H, H, w.dA1, 2 * H, W[w0], H, dhin, H, ACC_ADD);
+  linear_dgrad(st, B, 2 * H, H, w.dA1, 2 * H, W[w0], H, dhin, H, dhin_accum);
 }
 
 // looper cell backward for one propagate: dHi -> (dHc += ..., weight grads)
@@ -832,7 +832,7 @@ void decode_bwd_impl(dx_stream_t st, const Weights& W, const Weights& G, int B, 
                      const Batch& bt, LossW lw) {
   const uint64_t* adj = bt.adj;
   const size_t bH = (size_t)B * H;
-  zero_async(st, w.dHd, sizeof(float) * 7 * bH);
+  zero_async(st, w.dHd + 6 * bH, sizeof(float) * bH);   // nothing reads the last node's state: its gradient is zero
   if (bt.step_ptr) {
     // compacted steps: msg_bwd accumulates the "out" halves for every graph, the "in" halves only on the rows of the
     // back-edge-source lists (and only those are read back): zero exactly that
@@ -990,7 +990,8 @@ void decode_bwd_impl(dx_stream_t st, const Weights& W, const Weights& G, int B, 
     // parameter head of node vi read h_{vi-1}
     float* dprev = w.dHd + (size_t)(vi - 1) * bH;
     const float* hprev = w.Hd + (size_t)(vi - 1) * bH;
-    mlp3_bwd(st, W, G, B, P_X_W0, hprev, SX, w.A1[vi], w.A2[vi], w.dL[vi], w, dprev);
+    // first writer of dh_{vi-1} (its other consumers are folded in just below): stores, so dHd needs no zero fill
+    mlp3_bwd(st, W, G, B, P_X_W0, hprev, SX, w.A1[vi], w.A2[vi], w.dL[vi], w, dprev, ACC_STORE);
     // every consumer of node vi-1 is done: fold its projection gradients into dh_{vi-1}
     const int j = vi - 1;
     const float* dPg = w.dPg + (size_t)j * B * 2 * H; const float* dPm = w.dPm + (size_t)j * B * 2 * H;
