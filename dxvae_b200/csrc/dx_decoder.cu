@@ -47,7 +47,7 @@ DecWs carve_dec(Arena& ar, int64_t B, bool train) {
     per_step(w.dl2, LD_E, true); per_step(w.g_c, 4 * H, true); per_step(w.g_l, 4 * H, true);
     w.rowloss = ar.take<float>(4 * b);
     w.dHd = ar.take<float>(7 * b * H); w.dPg = ar.take<float>(6 * b * 2 * H); w.dPm = ar.take<float>(6 * b * 2 * H);
-    w.dQ = ar.take<float>(6 * b * 4 * H); w.dgb = ar.take<float>(6 * b * H);
+    w.dQ = ar.take<float>(6 * b * 4 * H); w.dgb = nullptr;   // (gate-bias gradient: summed inside msg_bwd)
     w.dHi = ar.take<float>(b * H); w.dHc = ar.take<float>(b * H); w.dHin = ar.take<float>(b * H);
     w.dHrun = ar.take<float>(b * H); w.dHc0 = ar.take<float>(b * H);
     w.dgx = ar.take<float>(b * 4 * H); w.dgh = w.dgx + H; w.dgxs = nullptr;   // one D4 buffer, two views (CellBwd)
@@ -853,7 +853,6 @@ void decode_bwd_impl(dx_stream_t st, const Weights& W, const Weights& G, int B, 
     zero_async(st, w.dPm, sizeof(float) * 6 * (size_t)B * 2 * H);
   }
   if (!bt.step_ptr) zero_async(st, w.dQ, sizeof(float) * 6 * (size_t)B * 4 * H);   // (compacted steps store dQ whole)
-  zero_async(st, w.dgb, sizeof(float) * 6 * bH);
   for (int k = 0; k < 3; ++k) zero_async(st, w.dWihP[k], sizeof(float) * G3 * XP);
   mask_features(st, (int64_t)7 * B, B, nullptr, 0, adj, bt.Xn, w.XL);
 
@@ -914,7 +913,7 @@ void decode_bwd_impl(dx_stream_t st, const Weights& W, const Weights& G, int B, 
           });
         }
         RowMap rs{n, B, rows, vj * B};
-        MsgBwd mb{rs, w.Pg, w.Pm, W[P_G_B], adj, w.dHrun, 0, w.dPg, w.dPm, w.dgb, 1, vi, vi, 1};
+        MsgBwd mb{rs, w.Pg, w.Pm, W[P_G_B], adj, w.dHrun, 0, w.dPg, w.dPm, G[P_G_B], 1, vi, vi, 1};
         mb.lazy_in = 1;                                          // the "in" half only exists on back-edge rows
         msg_bwd(st, mb);
       }
@@ -948,7 +947,7 @@ void decode_bwd_impl(dx_stream_t st, const Weights& W, const Weights& G, int B, 
       add_inplace(st, (int64_t)bH / 4, w.dHrun, w.dHin);
       // message of vj was part of this and every later aggregate of node vi
       RowMap rs{B, B, nullptr, vj * B};
-      MsgBwd mb{rs, w.Pg, w.Pm, W[P_G_B], adj, w.dHrun, 0, w.dPg, w.dPm, w.dgb, 1, vi, vi, 1};
+      MsgBwd mb{rs, w.Pg, w.Pm, W[P_G_B], adj, w.dHrun, 0, w.dPg, w.dPm, G[P_G_B], 1, vi, vi, 1};
       msg_bwd(st, mb);
       // edge head of this step read the PREVIOUS Hi (step t-1, or P2 when vj = vi-1)
       const float* Hi_prev = (vj == vi - 1) ? w.Hi_p2[vi] : w.Hi[t - 1];
@@ -1021,7 +1020,6 @@ void decode_bwd_impl(dx_stream_t st, const Weights& W, const Weights& G, int B, 
     linear_dgrad(st, B, 4 * H, H, dQ, 4 * H, W[P_E_W0] + H, 2 * H, dprev, H, ACC_ADD);
     linear_wgrad(st, B, 4 * H, H, dQ, 4 * H, hprev, H, G[P_E_W0] + H, 2 * H);
     if (!compact) colsum_accum(st, B, 4 * H, dQ, 4 * H, G[P_E_B0]);   // (compacted steps: the fused forward head summed it)
-    colsum_accum(st, B, H, w.dgb + (size_t)j * bH, H, G[P_G_B]);
     t_end = t0;
   }
   // root cell: h_0 = GRU_root(x0, H_init)

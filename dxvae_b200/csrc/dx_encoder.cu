@@ -29,7 +29,7 @@ EncWs carve_enc(Arena& ar, int64_t B, bool train) {
     w.XnSL = ar.take<float>(R6 * XP);
     w.gc = ar.take<float>(R7 * 4 * H); w.gl = ar.take<float>(R7 * 4 * H);
     w.dH = ar.take<float>(R7 * H); w.dHin = ar.take<float>(R7 * H);
-    w.dPg = ar.take<float>(R6 * 2 * H); w.dPm = ar.take<float>(R6 * 2 * H); w.dgb = ar.take<float>(R6 * H);
+    w.dPg = ar.take<float>(R6 * 2 * H); w.dPm = ar.take<float>(R6 * 2 * H); w.dgb = nullptr;
     w.dgx = ar.take<float>(R6 * 4 * H); w.dgh = w.dgx + H; w.dgxs = nullptr;   // one D4 buffer, two views (CellBwd)
     w.dHc = ar.take<float>(R6 * H); w.dsraw = ar.take<float>((size_t)B * Z);
   }
@@ -143,7 +143,7 @@ void encode_bwd_impl(dx_stream_t st, const Weights& W, const Weights& G, const B
     const float* Xs = w.XnS + (size_t)base * XP;
     // gradients reaching the projections of these source rows from every lower neighbour
     MsgBwd mb{rm, w.Pg + (size_t)base * 2 * H, w.Pm + (size_t)base * 2 * H, W[P_G_B], bt.adj, w.dHin, 0, w.dPg, w.dPm,
-              w.dgb, 0, -1, 0, 0};
+              G[P_G_B], 0, -1, 0, 0};
     mb.pos = w.pos; mb.p_compact = 1;
     mb.out_rows = bt.level_rare ? bt.level_rare[L] : -1;      // rows past the back-edge-target prefix never read their "out" half
     msg_bwd(st, mb);
@@ -156,7 +156,6 @@ void encode_bwd_impl(dx_stream_t st, const Weights& W, const Weights& G, const B
       proj_wgrad(st, Mh, w.dPg, Hv, G[P_G_W], half);
       proj_wgrad(st, Mh, w.dPm, Hv, G[P_M_W], half);
     }
-    colsum_accum(st, M, H, w.dgb, H, G[P_G_B]);
     // looper
     CellBwd cl{rm, dH, 0, w.gl + (size_t)base * 4 * H, 0, Hc, 0, w.dgx, nullptr, w.dgh, w.dHc, S_SELF, bt.adj};
     cell_bwd(st, cl, G[P_LE_BIH], G[P_LE_BHH]);

@@ -242,13 +242,14 @@ inline void msg_fwd(dx_stream_t st, const MsgFwd& a) {
   });
 }
 
-// Backward, from the SOURCE row's perspective (no atomics, deterministic):
+// Backward, from the SOURCE row's perspective:
 // source rows (RowMap) x; targets v = v_lo..v_hi (encode: 0..x-1 when v_lo<0).
-// dhin row of target v: (v*dh_vstride + b).  Writes/accumulates dPg, dPm ([.,1024]) and the
-// gate-bias row gradient dgb ([.,512]) at the source row (global r or compact m).
+// dhin row of target v: (v*dh_vstride + b).  Writes/accumulates dPg, dPm ([.,1024]) at the source row (global r or
+// compact m).  The gate-bias gradient only matters summed over rows: every thread keeps the column sums of its 4
+// hidden units in registers and the block adds them to dbias atomically (no per-row buffer, no second pass).
 struct MsgBwd {
   RowMap rm; const float* Pg; const float* Pm; const float* bg; const uint64_t* adj; const float* dhin;
-  int64_t dh_vstride; float* dPg; float* dPm; float* dgb; int out_global; int v_lo, v_hi; int accum;
+  int64_t dh_vstride; float* dPg; float* dPm; float* dbias; int out_global; int v_lo, v_hi; int accum;
   const int* pos = nullptr;   // optional: dhin row of target (v,b) is pos[v*B+b]
   int p_compact = 0;          // 1: this row's own Pg/Pm are indexed by m (pointer pre-offset), else by r
   // halves nobody reads are not written (DESIGN.md "projection halves"):
@@ -256,50 +257,87 @@ struct MsgBwd {
   int lazy_in = 0;            // 1 (decoder, accum = 1): the "in" half is read-modify-written only when an "in" flag is set
 };
 
-inline void msg_bwd(dx_stream_t st, const MsgBwd& a) {
-  foreach (st, (int64_t)a.rm.M * (H / 4), [=] DX_HD(int64_t idx) {
-    const int m = (int)(idx / (H / 4)), n = (int)(idx % (H / 4)) * 4;
-    const int r = a.rm.r(m);
-    const int b = r % a.rm.B, x = r / a.rm.B;
-    const uint64_t A = a.adj[b];
-    const int64_t o = a.out_global ? r : m;
-    float* dgp = a.dPg + o * (2 * H) + n; float* dpp = a.dPm + o * (2 * H) + n; float* dbp = a.dgb + o * H + n;
-    float4 dgi = f4zero(), dgo = f4zero(), dpi = f4zero(), dpo = f4zero(), db = f4zero();
-    bool any_in = false;
-    if (a.lazy_in) {
-      const int l0 = a.v_lo < 0 ? 0 : a.v_lo, h0 = a.v_lo < 0 ? x - 1 : a.v_hi;
-      for (int v = l0; v <= h0; ++v) any_in = any_in || abit(A, x, v);
-    }
-    const bool touch_in = !a.lazy_in || any_in;
-    if (a.accum) {
-      if (touch_in) { dgi = ld4f(dgp); dpi = ld4f(dpp); }
-      dgo = ld4f(dgp + H); dpo = ld4f(dpp + H); db = ld4f(dbp);
-    }
-    const int lo = a.v_lo < 0 ? 0 : a.v_lo, hi = a.v_lo < 0 ? x - 1 : a.v_hi;
-    const int64_t own = a.p_compact ? m : r;
-    const float* gp = a.Pg + own * (2 * H) + n; const float* pp = a.Pm + own * (2 * H) + n;
-    const float4 bg = ld4f(a.bg + n);
-    for (int v = lo; v <= hi; ++v) {
-      const float fi = (float)abit(A, x, v), fo = (float)abit(A, v, x);
-      if (fi == 0.f && fo == 0.f) continue;
-      const int64_t trow = a.pos ? (int64_t)a.pos[v * a.rm.B + b] : (int64_t)v * a.dh_vstride + b;
-      const float4 dh = ld4f(a.dhin + trow * H + n);
-      float4 gi = f4zero(), go = f4zero(), pi = f4zero(), po = f4zero();
-      if (fi != 0.f) { gi = ld4f(gp); pi = ld4f(pp); }
-      if (fo != 0.f) { go = ld4f(gp + H); po = ld4f(pp + H); }
+// One (row m, 4 hidden units at n) element; returns this call's gate pre-activation gradient (bias contribution).
+DX_HD DX_INLINE float4 msg_bwd_elem(const MsgBwd& a, int m, int n) {
+  const int r = a.rm.r(m);
+  const int b = r % a.rm.B, x = r / a.rm.B;
+  const uint64_t A = a.adj[b];
+  const int64_t o = a.out_global ? r : m;
+  float* dgp = a.dPg + o * (2 * H) + n; float* dpp = a.dPm + o * (2 * H) + n;
+  float4 dgi = f4zero(), dgo = f4zero(), dpi = f4zero(), dpo = f4zero(), db = f4zero();
+  bool any_in = false;
+  if (a.lazy_in) {
+    const int l0 = a.v_lo < 0 ? 0 : a.v_lo, h0 = a.v_lo < 0 ? x - 1 : a.v_hi;
+    for (int v = l0; v <= h0; ++v) any_in = any_in || abit(A, x, v);
+  }
+  const bool touch_in = !a.lazy_in || any_in;
+  if (a.accum) {
+    if (touch_in) { dgi = ld4f(dgp); dpi = ld4f(dpp); }
+    dgo = ld4f(dgp + H); dpo = ld4f(dpp + H);
+  }
+  const int lo = a.v_lo < 0 ? 0 : a.v_lo, hi = a.v_lo < 0 ? x - 1 : a.v_hi;
+  const int64_t own = a.p_compact ? m : r;
+  const float* gp = a.Pg + own * (2 * H) + n; const float* pp = a.Pm + own * (2 * H) + n;
+  const float4 bg = ld4f(a.bg + n);
+  for (int v = lo; v <= hi; ++v) {
+    const float fi = (float)abit(A, x, v), fo = (float)abit(A, v, x);
+    if (fi == 0.f && fo == 0.f) continue;
+    const int64_t trow = a.pos ? (int64_t)a.pos[v * a.rm.B + b] : (int64_t)v * a.dh_vstride + b;
+    const float4 dh = ld4f(a.dhin + trow * H + n);
+    float4 gi = f4zero(), go = f4zero(), pi = f4zero(), po = f4zero();
+    if (fi != 0.f) { gi = ld4f(gp); pi = ld4f(pp); }
+    if (fo != 0.f) { go = ld4f(gp + H); po = ld4f(pp + H); }
 #define DX_MSGB(c)                                                                \
-      {                                                                           \
-        const float s_ = sigmoidf_((fi * gi.c + fo * go.c) + bg.c), c_ = fi * pi.c + fo * po.c; \
-        const float da = dh.c * c_ * s_ * (1.f - s_), dc = dh.c * s_;             \
-        dgi.c += fi * da; dgo.c += fo * da; dpi.c += fi * dc; dpo.c += fo * dc; db.c += da; \
-      }
-      DX_MSGB(x) DX_MSGB(y) DX_MSGB(z) DX_MSGB(w)
-#undef DX_MSGB
+    {                                                                             \
+      const float s_ = sigmoidf_((fi * gi.c + fo * go.c) + bg.c), c_ = fi * pi.c + fo * po.c; \
+      const float da = dh.c * c_ * s_ * (1.f - s_), dc = dh.c * s_;               \
+      dgi.c += fi * da; dgo.c += fo * da; dpi.c += fi * dc; dpo.c += fo * dc; db.c += da; \
     }
-    if (touch_in) { st4f(dgp, dgi); st4f(dpp, dpi); }
-    if (a.out_rows < 0 || m < a.out_rows) { st4f(dgp + H, dgo); st4f(dpp + H, dpo); }
-    st4f(dbp, db);
-  });
+    DX_MSGB(x) DX_MSGB(y) DX_MSGB(z) DX_MSGB(w)
+#undef DX_MSGB
+  }
+  if (touch_in) { st4f(dgp, dgi); st4f(dpp, dpi); }
+  if (a.out_rows < 0 || m < a.out_rows) { st4f(dgp + H, dgo); st4f(dpp + H, dpo); }
+  return db;
+}
+
+#ifndef DX_EMU
+// Block = 4 row groups x 128 threads (the 512 hidden units, 4 per thread); blocks stride over the rows (as k_cell_bwd).
+static __global__ void __launch_bounds__(512, 2) k_msg_bwd(const MsgBwd a) {
+  __shared__ float red[3][4][128];
+  const int q = threadIdx.x & 127, rg = threadIdx.x >> 7;
+  float4 s = f4zero();
+  for (int m = blockIdx.x * 4 + rg; m < a.rm.M; m += gridDim.x * 4) {
+    const float4 d = msg_bwd_elem(a, m, q * 4);
+    s.x += d.x; s.y += d.y; s.z += d.z; s.w += d.w;
+  }
+  if (!a.dbias) return;
+  if (rg > 0) { red[rg - 1][0][q] = s.x; red[rg - 1][1][q] = s.y; red[rg - 1][2][q] = s.z; red[rg - 1][3][q] = s.w; }
+  __syncthreads();
+  if (rg == 0) {
+    atomicAdd(a.dbias + q * 4 + 0, s.x + red[0][0][q] + red[1][0][q] + red[2][0][q]);
+    atomicAdd(a.dbias + q * 4 + 1, s.y + red[0][1][q] + red[1][1][q] + red[2][1][q]);
+    atomicAdd(a.dbias + q * 4 + 2, s.z + red[0][2][q] + red[1][2][q] + red[2][2][q]);
+    atomicAdd(a.dbias + q * 4 + 3, s.w + red[0][3][q] + red[1][3][q] + red[2][3][q]);
+  }
+}
+#endif
+
+inline void msg_bwd(dx_stream_t st, const MsgBwd& a) {
+  if (a.rm.M <= 0) return;
+#ifndef DX_EMU
+  int blocks = (a.rm.M + 3) / 4;
+  if (blocks > 148 * 2) blocks = 148 * 2;
+  k_msg_bwd<<<blocks, 512, 0, st>>>(a);
+  ++g_launches;
+#else
+  for (int m = 0; m < a.rm.M; ++m)
+    for (int n = 0; n < H; n += 4) {
+      const float4 d = msg_bwd_elem(a, m, n);
+      if (a.dbias) { a.dbias[n] += d.x; a.dbias[n + 1] += d.y; a.dbias[n + 2] += d.z; a.dbias[n + 3] += d.w; }
+    }
+  ++g_launches;
+#endif
 }
 
 // ------------------------------------------------------------------------------------
