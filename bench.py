@@ -13,6 +13,9 @@ Workload (BASELINE.json config 5, the data-parallel one, at N GPUs; per-GPU work
   --precision tf32 (default): dense products on the tcgen05 tensor cores, looser stated tolerance
               fp32: FFMA kernels, reference-tolerance parity (also reported in extra)
   cpu_baseline  the oracle port of the reference (torch CPU, all host cores) on a bounded sample
+  extra      the other BASELINE configs, N=1 only: batched encode (cfg3) and greedy decode (cfg4) at micro-batch size and
+             end to end at 1 M patches from host buffers (voices -> latents; z -> .syx bytes), decode also at Dexed edge
+             density, the B=128 training step (cfg2) and the FP32 FFMA training path
 `--impl reference` times that CPU port alone (the reference itself is Python+DGL and cannot
 travel to the GPU box).
 """
