@@ -266,6 +266,12 @@ int dxvae_adamw_step(int64_t n, float* weights, const float* grads, float* exp_a
 int dxvae_test_gemm(int variant, int64_t M, int64_t N, int64_t K, const float* A, int64_t lda, const float* Bm,
                     int64_t ldb, float* C, int64_t ldc, const float* bias, int act, int accumulate, void* stream) {
   // variant 0: y = act(x W^T + b) ; 1: dx (+)= dy W ; 2: dW += dy^T x ; +16: tcgen05 TF32 path ; +32: 3xTF32
+  // variant 64: y = act(x W^T + b) with A and Bm pointing at BF16 data (pitches in elements), tcgen05 kind::f16
+  if (variant == 64) {
+    GemmP g; g.M = (int)M; g.N = (int)N; g.K = (int)K; g.lda = lda; g.ldb = ldb; g.C = C; g.ldc = ldc; g.bias = bias; g.act = act;
+    DX_CHECK(tc_gemm_bf16(DX_ST(stream), g, A, Bm), "test_gemm: bf16 product not eligible");
+    return check_launch("test_gemm_bf16");
+  }
   PrecisionScope prec((variant & 32) ? PREC_3XTF32 : ((variant & 16) ? PREC_TF32 : PREC_FP32));
   SplitCtx sc;
 #ifndef DX_EMU

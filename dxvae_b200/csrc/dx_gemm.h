@@ -81,6 +81,8 @@ inline void linear_wgrad(dx_stream_t s, int M, int N, int K, const float* dy, in
   GemmP p; p.M = N; p.N = K; p.K = M; p.A = dy; p.lda = lddy; p.a_kc = false; p.a_idx = dy_idx;
   p.B = x; p.ldb = ldx; p.b_kc = false; p.b_idx = x_idx; p.C = dW; p.ldc = lddw; p.accum = ACC_ATOMIC; gemm(s, p);
 }
+// bf16 K-major operands (groundwork, test entry only): C = act(A16 B16^T + bias), fp32 accumulate and output
+bool tc_gemm_bf16(dx_stream_t s, const GemmP& g, const void* A16, const void* B16);
 // db[N] += column sums of dy[M,N] (atomic)
 void colsum_accum(dx_stream_t s, int M, int N, const float* dy, int64_t lddy, float* db, const int* dy_idx = nullptr);
 

@@ -448,16 +448,29 @@ __device__ __forceinline__ void umma_tf32_2sm(uint32_t tmem_d, uint64_t adesc, u
       "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t"
       "}" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
 }
+__device__ __forceinline__ void umma_f16_2sm(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
+}
 __device__ __forceinline__ void umma_commit_2sm(uint32_t bar) {   // arrives on `bar` in both CTAs of the pair
   asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
                ::"r"(bar), "h"((uint16_t)3) : "memory");
 }
 
-template <bool A_MN, bool B_MN>
+// BF16 (K-major operands only, groundwork for DESIGN.md §7 item 1): the operands are bf16 in HBM; a 128-byte tile row then
+// holds 64 k-values and one UMMA (kind::f16) covers K = 16 = the same 32 bytes, so stage bytes, swizzle, descriptors and
+// barriers are unchanged — only the k extent of a stage, the instruction kind and the format codes differ.
+template <bool A_MN, bool B_MN, bool BF16 = false>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(320, 1)
 k_tc_gemm2(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
            const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmAdd, const TcParams p) {
+  static_assert(!BF16 || (!A_MN && !B_MN), "bf16 operands: K-major only");
   constexpr int BN = 256, S = S2;
+  constexpr int TKE = BF16 ? 64 : TBK;                              // k-values per stage
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t stg_base = base + S * STAGE2;
@@ -499,7 +512,7 @@ k_tc_gemm2(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
     const int mt = p.n_fast ? (t / gn) % gm2 : t % gm2, nt = p.n_fast ? t % gn : (t / gm2) % gn, z = t / (gm2 * gn);
     m0 = mt * 256 + (int)rank * TBM; n0 = nt * BN; kbeg = z * p.k_chunk;   // this CTA's 128 rows of the pair's tile
     const int kend = min(p.K, kbeg + p.k_chunk);
-    nkb = (kend - kbeg + TBK - 1) / TBK;
+    nkb = (kend - kbeg + TKE - 1) / TKE;
   };
 
   if (warp == 0) {
@@ -513,7 +526,7 @@ k_tc_gemm2(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
           mbar_wait_cluster(empty_bar(s), ((it / S) & 1) ^ 1);
           if (trace && it < 32) p.dbg[it] = clock64();
           if (leader) mbar_expect_tx(full_bar(s), 2 * STAGE2);     // bytes of both CTAs land on the leader's barrier
-          const int k0 = kbeg + kb * TBK;
+          const int k0 = kbeg + kb * TKE;
           const uint32_t sa = base + s * STAGE2, sb = sa + A_BYTES;
           if (!A_MN) tma_load_2d_2sm(&tmA, sa, full_bar(s), k0, m0);
           else
@@ -528,7 +541,8 @@ k_tc_gemm2(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
     }
   } else if (warp == 1) {
     if (lane == 0 && leader) {                                     // ---- MMA issuer (leader CTA only)
-      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((A_MN ? 1u : 0u) << 15) | ((B_MN ? 1u : 0u) << 16) |
+      const uint32_t fmt = BF16 ? 1u : 2u;                         // F16F32Format: 1 = BF16, 2 = TF32
+      const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((A_MN ? 1u : 0u) << 15) | ((B_MN ? 1u : 0u) << 16) |
                              ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
       uint32_t it = 0, lt = 0;
       for (int t = cid; t < total; t += ncl, ++lt) {
@@ -547,7 +561,8 @@ k_tc_gemm2(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
           for (int k = 0; k < TBK / 8; ++k) {
             const uint64_t ad = A_MN ? umma_desc(sa + k * 1024, 4096, 512, 1) : umma_desc(sa + k * 32, 16, 1024, 2);
             const uint64_t bd = B_MN ? umma_desc(sb + k * 1024, 4096, 512, 1) : umma_desc(sb + k * 32, 16, 1024, 2);
-            umma_tf32_2sm(tacc, ad, bd, idesc, (kb | k) != 0 ? 1u : 0u);
+            if (BF16) umma_f16_2sm(tacc, ad, bd, idesc, (kb | k) != 0 ? 1u : 0u);
+            else umma_tf32_2sm(tacc, ad, bd, idesc, (kb | k) != 0 ? 1u : 0u);
           }
           umma_commit_2sm(empty_bar(s));                           // frees the stage in both CTAs
         }
@@ -608,6 +623,18 @@ bool make_map(CUtensorMap* m, const float* ptr, int64_t rows, int64_t cols, int6
              CU_TENSOR_MAP_INTERLEAVE_NONE, mn_major ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
              l2_promo(),
              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+// 2-D bf16 tensor [rows][cols] with row pitch ld (elements); box = 64 columns (128 bytes) x box_rows, 128-byte swizzle
+bool make_map_bf16(CUtensorMap* m, const void* ptr, int64_t rows, int64_t cols, int64_t ld, int box_rows) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) return false;
+  cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t gstr[1] = {(cuuint64_t)ld * 2};
+  cuuint32_t box[2] = {64u, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  return enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+             CU_TENSOR_MAP_SWIZZLE_128B, l2_promo(), CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
 template <int BN, bool X3 = false>
@@ -777,7 +804,30 @@ bool launch_tc2(dx_stream_t s, const GemmP& g) {
 
 inline bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
+// C[M,N] = act(A B^T + bias) with bf16 K-major operands (A [M,K], B [N,K], pitches in elements), fp32 accumulate / output.
+bool launch_tc2_bf16(dx_stream_t s, const GemmP& g, const void* A16, const void* B16) {
+  if (g.accum != ACC_STORE || g.c_idx || g.add || !al16(A16) || !al16(B16) || (g.lda % 8) || (g.ldb % 8) || !al16(g.C) || (g.ldc % 4))
+    return false;
+  CUtensorMap ta, tb, tc;
+  if (!make_map_bf16(&ta, A16, g.M, g.K, g.lda, TBM) || !make_map_bf16(&tb, B16, g.N, g.K, g.ldb, 128) ||
+      !make_map(&tc, g.C, g.M, g.N, g.ldc, 32, 32, false, true))
+    return false;
+  const int gm2 = (g.M + 255) / 256, gn = (g.N + 255) / 256;
+  const int k_chunk = (g.K + 63) / 64 * 64;
+  TcParams p{g.M, g.N, g.K, g.C, g.ldc, nullptr, g.bias, nullptr, 0, g.act, ACC_STORE, k_chunk, 1, 0, 1, nullptr};
+  static int num_sms = 0;
+  if (!num_sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev); }
+  const int total = gm2 * gn, ncl = total < num_sms / 2 ? total : num_sms / 2;
+  static bool attr_set = false;
+  if (!attr_set) { cudaFuncSetAttribute(k_tc_gemm2<false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM2); attr_set = true; }
+  k_tc_gemm2<false, false, true><<<dim3(2 * ncl), 320, SMEM2, s>>>(ta, tb, tc, ta, p);
+  ++g_launches;
+  return true;
+}
+
 }  // namespace
+
+bool tc_gemm_bf16(dx_stream_t s, const GemmP& g, const void* A16, const void* B16) { return launch_tc2_bf16(s, g, A16, B16); }
 
 // Returns false when the problem is not eligible (caller falls back to the FP32 SIMT kernel).
 bool tc_gemm(dx_stream_t s, const GemmP& g, int* tile_n) {
@@ -812,5 +862,6 @@ bool tc_gemm_x3(dx_stream_t s, const GemmP& g, const float* A_lo, const float* B
 namespace dx {
 bool tc_gemm(dx_stream_t, const GemmP&, int*) { return false; }
 bool tc_gemm_x3(dx_stream_t, const GemmP&, const float*, const float*) { return false; }
+bool tc_gemm_bf16(dx_stream_t, const GemmP&, const void*, const void*) { return false; }
 }  // namespace dx
 #endif

@@ -147,3 +147,21 @@ def test_3xtf32_decode_is_fp32_accurate_but_not_bit_stable(lib):
     identical = same_topo & (dp == 0)
     print("3xtf32 vs fp32 decode: identical %.2f%%, same topology %.2f%%" % (100 * identical.mean(), 100 * same_topo.mean()))
     assert identical.mean() >= 0.98
+
+
+# --------------------------------------------------------------------------- BF16 operands (groundwork)
+@pytest.mark.parametrize("M,N,K", [(256, 256, 64), (8192, 1536, 512), (1000, 1024, 1024), (300, 2048, 512), (4096, 512, 128)])
+def test_tc_gemm_bf16_forward(lib, M, N, K):
+    """tcgen05 kind::f16 with bf16 K-major operands, FP32 accumulate: exact up to FP32 summation order against a float64
+    product of the SAME bf16-rounded operands (ragged M / N exercise the tensor maps' out-of-bounds fill)."""
+    from dxvae_b200 import _lib
+    g = torch.Generator().manual_seed(M + N + K)
+    A = torch.randn(M, K, generator=g).cuda().to(torch.bfloat16); W = torch.randn(N, K, generator=g).cuda().to(torch.bfloat16)
+    b = torch.randn(N, generator=g).cuda()
+    for act, fn in ((0, lambda t: t), (1, torch.relu)):
+        C = torch.full((M, N), float("nan"), device="cuda")
+        _lib.check(lib.dxvae_test_gemm(64, M, N, K, A.data_ptr(), K, W.data_ptr(), K, C.data_ptr(), N, b.data_ptr(), act, 0,
+                                       torch.cuda.current_stream().cuda_stream), "gemm bf16")
+        ref = fn(A.double() @ W.double().t() + b.double())
+        err = (C.double() - ref).abs().max().item()
+        assert err <= 2e-5 * max(1.0, ref.abs().max().item()), (act, err)
