@@ -260,7 +260,10 @@ def run_ours(args):
         except Exception:
             pass
         roof = {"bound": "tensor", "kernel": names[dom], "achieved": ach, "peak": pk["tensor"], "unit": "TFLOP/s",
-                "frac": ach / pk["tensor"], "traffic": traffic, "peak_source": pk["source"] + ", bf16 sustained",
+                "frac": ach / pk["tensor"], "traffic": traffic,
+                "traffic_source": "mean dram__bytes_read+write of the launches in the committed ncu --set full capture "
+                                  "(profiles/r01b_tc_gemm_ncu.txt); `achieved` averages every launch of the timed steps",
+                "peak_source": pk["source"] + ", bf16 sustained",
                 "launches_per_step": nv[dom] / K, "avg_launch_ms": msv[dom] / max(1, nv[dom]),
                 "share_of_step": msv[dom] / K / (ms / K), "fp32_ffma_peak_tflops": ffma_peak,
                 "classes": [{"kernel": names[c], "ms_per_step": msv[c] / K, "tflops": (flv[c] / (msv[c] * 1e-3) / 1e12)
