@@ -116,16 +116,8 @@ int decode_greedy(dx_stream_t st, const float* weights, int64_t B64, const float
   Weights W(weights);
   zero_async(st, adj, sizeof(uint64_t) * (size_t)B);
   if (margins) foreach (st, B, [=] DX_HD(int64_t i) { margins[i] = 3.0e38f; });
-  SplitCtx sc;
-  if (precision == PREC_3XTF32) {
-    split_tf32(st, 1, param_blob_floats(), weights, param_blob_floats(), w.Whi, w.Wlo);
-    sc.w_base = weights; sc.w_floats = param_blob_floats(); sc.w_hi = w.Whi; sc.w_lo = w.Wlo;
-    sc.a_hi = w.xs_hi; sc.a_lo = w.xs_lo; sc.a_floats = (int64_t)B * 2 * H;
-    set_split_ctx(&sc);
-  }
   DecIO io{false, nullptr, LossW{0, 0, 0, 0}, adj, margins};
   decode_fwd_impl(st, W, B, z, w, io);
-  set_split_ctx(nullptr);
   unpack_graphs(st, B, w.Xd, w.Pn, Xg, Pg);
   return check_launch("decode_greedy");
 }
@@ -224,7 +216,7 @@ int dxvae_elbo_step(const float* weights, int64_t B, const float* Xn, const int3
   DX_BATCH_OK(B);
   DX_CHECK(n_levels >= 1 && n_levels <= 6, "elbo_step: n_levels=%d", n_levels);
   DX_CHECK((step_ptr_host == nullptr) == (step_rows == nullptr), "elbo_step: step_ptr_host and step_rows go together");
-  DX_CHECK(precision == PREC_FP32 || precision == PREC_TF32, "elbo_step: unknown precision %d", precision);
+  DX_CHECK(precision >= PREC_FP32 && precision <= PREC_3XTF32, "elbo_step: unknown precision %d", precision);
   Batch bt{B, Xn, cls, adj, n_levels, level_ptr_host, level_rows};
   bt.level_rare = level_rare_host;
   bt.step_ptr = step_ptr_host; bt.step_rows = step_rows;
@@ -239,6 +231,7 @@ int dxvae_loss_step(const float* weights, int64_t B, const float* Xn, const int3
                     void* stream) {
   DX_BATCH_OK(B);
   DX_CHECK((step_ptr_host == nullptr) == (step_rows == nullptr), "loss_step: step_ptr_host and step_rows go together");
+  DX_CHECK(precision >= PREC_FP32 && precision <= PREC_3XTF32, "loss_step: unknown precision %d", precision);
   Batch bt{B, Xn, cls, adj, 0, nullptr, nullptr};
   bt.step_ptr = step_ptr_host; bt.step_rows = step_rows;
   LossW lw{w_env, w_frq, w_kld, inv_batch};
@@ -252,6 +245,7 @@ int dxvae_encode_bwd(const float* weights, int64_t B, const float* Xn, const uin
                      void* stream) {
   DX_BATCH_OK(B);
   DX_CHECK(n_levels >= 1 && n_levels <= 6, "encode_bwd: n_levels=%d", n_levels);
+  DX_CHECK(precision >= PREC_FP32 && precision <= PREC_3XTF32, "encode_bwd: unknown precision %d", precision);
   Batch bt{B, Xn, nullptr, adj, n_levels, level_ptr_host, level_rows};
   bt.level_rare = level_rare_host;
   return encode_bwd(DX_ST(stream), weights, bt, std_, dmu, dstd, grads, workspace, workspace_bytes, precision);
@@ -273,27 +267,11 @@ int dxvae_test_gemm(int variant, int64_t M, int64_t N, int64_t K, const float* A
     return check_launch("test_gemm_bf16");
   }
   PrecisionScope prec((variant & 32) ? PREC_3XTF32 : ((variant & 16) ? PREC_TF32 : PREC_FP32));
-  SplitCtx sc;
-#ifndef DX_EMU
-  float* tmp = nullptr;
-  if (variant & 32) {     // test-only scratch: the weight operand plays the role of the parameter blob
-    const int64_t wf = (int64_t)N * ldb, af = (int64_t)M * K;
-    cudaMalloc(&tmp, sizeof(float) * (2 * wf + 2 * af));
-    split_tf32(DX_ST(stream), 1, wf, Bm, wf, tmp, tmp + wf);
-    sc.w_base = Bm; sc.w_floats = wf; sc.w_hi = tmp; sc.w_lo = tmp + wf;
-    sc.a_hi = tmp + 2 * wf; sc.a_lo = tmp + 2 * wf + af; sc.a_floats = af;
-    set_split_ctx(&sc);
-  }
-#endif
   variant &= 15;
+  DX_CHECK(variant >= 0 && variant <= 2, "test_gemm: unknown variant %d", variant);
   if (variant == 0) linear_fwd(DX_ST(stream), (int)M, (int)N, (int)K, A, lda, Bm, ldb, bias, C, ldc, act);
   else if (variant == 1) linear_dgrad(DX_ST(stream), (int)M, (int)N, (int)K, A, lda, Bm, ldb, C, ldc, accumulate);
-  else if (variant == 2) linear_wgrad(DX_ST(stream), (int)M, (int)N, (int)K, A, lda, Bm, ldb, C, ldc);
-  else { set_error("test_gemm: unknown variant %d", variant); return 1; }
-  set_split_ctx(nullptr);
-#ifndef DX_EMU
-  if (tmp) { cudaStreamSynchronize(DX_ST(stream)); cudaFree(tmp); }
-#endif
+  else linear_wgrad(DX_ST(stream), (int)M, (int)N, (int)K, A, lda, Bm, ldb, C, ldc);
   return check_launch("test_gemm");
 }
 

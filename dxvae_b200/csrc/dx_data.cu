@@ -350,11 +350,13 @@ __constant__ uint32_t d_tab100[100];
 #define DXD_TAB32 d_tab32
 #define DXD_TAB100 d_tab100
 static void upload_data_tables() {
-  static bool done = false;
-  if (done) return;
+  static unsigned long long done = 0;   // __constant__ memory is per device: one bit per device ordinal
+  int dev = 0; cudaGetDevice(&dev);
+  const unsigned long long bit = 1ull << (dev & 63);
+  if (done & bit) return;
   cudaMemcpyToSymbol(d_tab32, kLogTab32, sizeof(kLogTab32));
   cudaMemcpyToSymbol(d_tab100, kLogTab100, sizeof(kLogTab100));
-  done = true;
+  done |= bit;
 }
 #else
 #define DXD_TAB32 kLogTab32

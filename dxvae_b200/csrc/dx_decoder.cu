@@ -22,9 +22,10 @@ DecWs carve_dec(Arena& ar, int64_t B, bool train) {
   w.z = ar.take<float>(b * Z); w.Hinit = ar.take<float>(b * H); w.Hd = ar.take<float>(7 * b * H);
   w.Pg = ar.take<float>(6 * b * 2 * H); w.Pm = ar.take<float>(6 * b * 2 * H); w.Q = ar.take<float>(6 * b * 4 * H);
   w.gh = ar.take<float>(b * G3); w.ghl0 = ar.take<float>(b * G3); w.Hrun = ar.take<float>(b * H);
+  for (int k = 0; k < 3; ++k) w.WihP[k] = ar.take<float>((size_t)G3 * XP);
   if (train) {
     w.U = ar.take<float>(b * 4 * H); w.UC = ar.take<float>(b * 4 * H); w.dHiC = ar.take<float>(b * H);
-    for (int k = 0; k < 3; ++k) { w.WihP[k] = ar.take<float>((size_t)G3 * XP); w.dWihP[k] = ar.take<float>((size_t)G3 * XP); }
+    for (int k = 0; k < 3; ++k) w.dWihP[k] = ar.take<float>((size_t)G3 * XP);
     w.XL = ar.take<float>(7 * b * XP); w.xc = ar.take<float>(b * XP);
   }
   auto per_node = [&](float** arr, size_t cols, bool need) {
@@ -57,8 +58,6 @@ DecWs carve_dec(Arena& ar, int64_t B, bool train) {
     w.U = ar.take<float>(b * 4 * H); w.UC = ar.take<float>(b * 4 * H);
     w.act_rows = ar.take<int>(b); w.act_cnt = ar.take<int>(64); w.act_flag = ar.take<uint8_t>(b);
     w.Xd = ar.take<float>(7 * b * XP); w.Pn = ar.take<float>(7 * b * XP);
-    w.Whi = ar.take<float>((size_t)param_blob_floats()); w.Wlo = ar.take<float>((size_t)param_blob_floats());
-    w.xs_hi = ar.take<float>(b * 2 * H); w.xs_lo = ar.take<float>(b * 2 * H);
   }
   return w;
 }
@@ -208,11 +207,13 @@ __constant__ uint32_t c_tab100[100];
 #define DX_TAB32 c_tab32
 #define DX_TAB100 c_tab100
 static void upload_tables() {
-  static bool done = false;  // per process; the tables are immutable constants
-  if (done) return;
+  static unsigned long long done = 0;   // __constant__ memory is per device: one bit per device ordinal
+  int dev = 0; cudaGetDevice(&dev);
+  const unsigned long long bit = 1ull << (dev & 63);
+  if (done & bit) return;
   cudaMemcpyToSymbol(c_tab32, kLogTab32, sizeof(kLogTab32));
   cudaMemcpyToSymbol(c_tab100, kLogTab100, sizeof(kLogTab100));
-  done = true;
+  done |= bit;
 }
 #else
 #define DX_TAB32 kLogTab32
@@ -629,7 +630,7 @@ void decode_fwd_impl(dx_stream_t st, const Weights& W, int B, const float* z, co
   upload_tables();
   const float* Wc = W[P_CD_WIH]; const float* Wl = W[P_LD_WIH]; const float* Wr = W[P_RD_WIH];
   int Kx = SX, Kr = SX0, ldx = SX, ldr = SX0;
-  if (train) {   // 32-column padded input weights: TMA-addressable (exact: the padded columns are zero)
+  if (train || get_precision() != PREC_FP32) {   // 32-column padded input weights: TMA-addressable (exact: the padded columns are zero)
     pad_wih(st, W[P_CD_WIH], SX, w.WihP[0]); pad_wih(st, W[P_LD_WIH], SX, w.WihP[1]); pad_wih(st, W[P_RD_WIH], SX0, w.WihP[2]);
     Wc = w.WihP[0]; Wl = w.WihP[1]; Wr = w.WihP[2]; Kx = Kr = ldx = ldr = XP;
   }

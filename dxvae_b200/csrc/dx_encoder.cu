@@ -20,12 +20,9 @@ EncWs carve_enc(Arena& ar, int64_t B, bool train) {
   w.Pg = ar.take<float>(R7 * 2 * H); w.Pm = ar.take<float>(R7 * 2 * H);
   w.gxc = ar.take<float>(R6 * G3); w.gxl = ar.take<float>(R6 * G3); w.gh = ar.take<float>(R6 * G3);
   w.XnS = ar.take<float>(R6 * XP); w.pos = ar.take<int>(R7);
-  if (!train) {
-    w.Whi = ar.take<float>((size_t)param_blob_floats()); w.Wlo = ar.take<float>((size_t)param_blob_floats());
-    w.xs_hi = ar.take<float>(R6 * H); w.xs_lo = ar.take<float>(R6 * H);
-  }
+  for (int k = 0; k < 3; ++k) w.WihP[k] = ar.take<float>((size_t)G3 * XP);
   if (train) {
-    for (int k = 0; k < 3; ++k) { w.WihP[k] = ar.take<float>((size_t)G3 * XP); w.dWihP[k] = ar.take<float>((size_t)G3 * XP); }
+    for (int k = 0; k < 3; ++k) w.dWihP[k] = ar.take<float>((size_t)G3 * XP);
     w.XnSL = ar.take<float>(R6 * XP);
     w.gc = ar.take<float>(R7 * 4 * H); w.gl = ar.take<float>(R7 * 4 * H);
     w.dH = ar.take<float>(R7 * H); w.dHin = ar.take<float>(R7 * H);
@@ -51,10 +48,11 @@ void encode_fwd_impl(dx_stream_t st, const Weights& W, const Batch& bt, const En
       st4f(XnS + p * XP + c, ld4f(Xn + (int64_t)rows[p] * XP + c));
     });
   }
-  // input weights: training uses 32-column padded copies (TMA-addressable); inference reads the blob
+  // input weights: training and the tensor-core modes use 32-column padded copies (TMA-addressable, exact: the
+  // padded columns are zero); FP32 FFMA inference reads the blob
   const float* Wc = W[P_CE_WIH]; const float* Wl = W[P_LE_WIH]; const float* Wr = W[P_RE_WIH];
   int Kx = SX, Kr = SX0, ldx = SX, ldr = SX0;
-  if (train) {
+  if (train || get_precision() != PREC_FP32) {
     pad_wih(st, W[P_CE_WIH], SX, w.WihP[0]); pad_wih(st, W[P_LE_WIH], SX, w.WihP[1]); pad_wih(st, W[P_RE_WIH], SX0, w.WihP[2]);
     Wc = w.WihP[0]; Wl = w.WihP[1]; Wr = w.WihP[2]; Kx = Kr = ldx = ldr = XP;
   }
@@ -183,16 +181,7 @@ int encode_fwd(dx_stream_t st, const float* weights, const Batch& bt, float* mu,
   EncWs w = carve_enc(ar, bt.B, keep != 0);
   DX_CHECK(!ar.overflow, "encode_fwd: workspace too small (%zu < %zu bytes)", ws_bytes, ar.off);
   Weights W(weights);
-  SplitCtx sc;
-  if (get_precision() == PREC_3XTF32) {
-    DX_CHECK(!keep, "encode_fwd: 3xTF32 is an inference mode");
-    split_tf32(st, 1, param_blob_floats(), weights, param_blob_floats(), w.Whi, w.Wlo);
-    sc.w_base = weights; sc.w_floats = param_blob_floats(); sc.w_hi = w.Whi; sc.w_lo = w.Wlo;
-    sc.a_hi = w.xs_hi; sc.a_lo = w.xs_lo; sc.a_floats = (int64_t)6 * bt.B * H;
-    set_split_ctx(&sc);
-  }
   encode_fwd_impl(st, W, bt, w, mu, std_, keep != 0);
-  set_split_ctx(nullptr);
   return check_launch("encode_fwd");
 }
 

@@ -40,9 +40,8 @@ struct EncWs {
   // [6B,7B) = node 0 of graph b.  pos[v*B+b] maps a node back to its position.
   float *Hin, *Hc, *Hv, *gc, *gl, *Pg, *Pm, *gxc, *gxl, *gh, *XnS;
   int* pos;
-  float *Whi, *Wlo, *xs_hi, *xs_lo;   // inference only: 3xTF32 operand splits (weights blob, scratch 6B x 512)
-  // training only: input weights padded 27/23 -> 32 columns (16-byte rows, so these products and their
-  // gradients are TMA-addressable), self-loop-masked features for the looper's weight gradient
+  // input weights padded 27/23 -> 32 columns (16-byte rows, so these products and their gradients are
+  // TMA-addressable); training only: their gradients, self-loop-masked features for the looper's weight gradient
   float *WihP[3], *dWihP[3], *XnSL;
   float *dH, *dHin, *dPg, *dPm, *dgb, *dgx, *dgxs, *dgh, *dHc, *dsraw;
 };
@@ -62,7 +61,6 @@ struct DecWs {
   // greedy only
   float *Xd, *Pn;
   int *act_rows, *act_cnt; uint8_t* act_flag;   // graphs that gained an edge at the current step (device-compacted)
-  float *Whi, *Wlo, *xs_hi, *xs_lo;   // 3xTF32 operand splits (weights blob, activation scratch B x 1024)
   // backward temporaries
   float *dHd, *dPg, *dPm, *dQ, *dgb, *dHi, *dHc, *dHin, *dHrun, *dHc0, *dgx, *dgxs, *dgh, *dE1, *dA1, *dA2, *dES1,
       *dHinit, *dz;

@@ -325,19 +325,6 @@ void prof_end(double* ms, double* flops, long long* n) {
 thread_local int g_precision = PREC_FP32;
 void set_precision(int prec) { g_precision = prec; }
 int get_precision() { return g_precision; }
-thread_local const SplitCtx* g_split = nullptr;
-void set_split_ctx(const SplitCtx* ctx) { g_split = ctx; }
-
-// hi = value with the low 13 mantissa bits cleared (exactly a tf32 number), lo = src - hi (exact in fp32)
-void split_tf32(dx_stream_t s, int64_t rows, int64_t cols, const float* src, int64_t ld, float* hi, float* lo) {
-  foreach (s, rows * cols, [=] DX_HD(int64_t i) {
-    const int64_t r = i / cols, c = i % cols;
-    const float v = src[r * ld + c];
-    union { float f; uint32_t u; } cv; cv.f = v; cv.u &= 0xFFFFE000u;
-    const float h = cv.f;
-    hi[i] = h; lo[i] = v - h;
-  });
-}
 
 void gemm(dx_stream_t s, const GemmP& p) {
   if (p.M <= 0 || p.N <= 0 || p.K <= 0) return;
@@ -353,19 +340,7 @@ void gemm(dx_stream_t s, const GemmP& p) {
   // Large tile when both output extents fill it; otherwise 64x64 so small batches
   // (B=128) and narrow heads (N=27/55/2/1) still spread over the SMs.
   const bool big = (p.M >= 512 && p.N >= 96);
-  bool done = false;
-  if (g_precision == PREC_3XTF32 && g_split && p.a_kc && p.b_kc && p.N >= 8 && p.K % 4 == 0 && !p.a_idx && !p.b_idx &&
-      (int64_t)p.M * p.K <= g_split->a_floats && p.B >= g_split->w_base && p.B < g_split->w_base + g_split->w_floats &&
-      (double)p.M * p.N * p.K >= 1.0e6) {
-    // exact operand pairs: activation split into scratch (dense pitch K), weights from the pre-split blobs
-    split_tf32(s, p.M, p.K, p.A, p.lda, g_split->a_hi, g_split->a_lo);
-    GemmP q = p;
-    q.A = g_split->a_hi; q.lda = p.K;
-    const int64_t off = p.B - g_split->w_base;
-    q.B = g_split->w_hi + off;
-    done = tc_gemm_x3(s, q, g_split->a_lo, g_split->w_lo + off);
-  }
-  if (done) cls = 2;
+  if (g_precision == PREC_3XTF32 && tc_gemm(s, p, nullptr, true)) cls = 2;
   else if (g_precision == PREC_TF32 && tc_gemm(s, p, nullptr)) cls = 2;
   else if (big) { launch_tile<128, 128, 8, 8>(s, p); cls = 0; }
   else { launch_tile<64, 64, 4, 4>(s, p); cls = 1; }
@@ -420,8 +395,6 @@ void prof_end(double* ms, double* flops, long long* n) {
 static thread_local int g_precision = PREC_FP32;
 void set_precision(int prec) { g_precision = prec; }
 int get_precision() { return g_precision; }
-void set_split_ctx(const SplitCtx*) {}
-void split_tf32(dx_stream_t, int64_t, int64_t, const float*, int64_t, float*, float*) {}
 
 void colsum_accum(dx_stream_t, int M, int N, const float* dy, int64_t lddy, float* db, const int* dy_idx) {
   for (int j = 0; j < N; ++j) {

@@ -32,8 +32,9 @@ struct GemmP {
 };
 
 enum { PREC_FP32 = 0, PREC_TF32 = 1, PREC_3XTF32 = 2 };
-// Arithmetic of the dense products issued by this thread: PREC_FP32 = FFMA kernels (bit-stable,
-// used by decode / inference), PREC_TF32 = tcgen05 tensor cores where the shape is eligible.
+// Arithmetic of the dense products issued by this thread: PREC_FP32 = FFMA kernels (bit-stable),
+// PREC_TF32 = tcgen05 tensor cores where the shape is eligible, PREC_3XTF32 = tensor cores with error-compensated
+// (hi/lo split) operands: FP32-accurate.
 void set_precision(int prec);
 int get_precision();
 struct PrecisionScope {
@@ -41,17 +42,9 @@ struct PrecisionScope {
   explicit PrecisionScope(int p) : prev(get_precision()) { set_precision(p); }
   ~PrecisionScope() { set_precision(prev); }
 };
-bool tc_gemm(dx_stream_t s, const GemmP& p, int* tile_n);   // dx_tc_gemm.cu; false = not eligible
-bool tc_gemm_x3(dx_stream_t s, const GemmP& p, const float* A_lo, const float* B_lo);
-// PREC_3XTF32 needs exact hi/lo splits of both operands: the weights are split once per call into two
-// blobs with the layout of the parameter blob; activations are split into scratch before each product.
-struct SplitCtx {
-  const float* w_base = nullptr; int64_t w_floats = 0;   // the parameter blob the B operands point into
-  float* w_hi = nullptr; float* w_lo = nullptr;          // its splits
-  float* a_hi = nullptr; float* a_lo = nullptr; int64_t a_floats = 0;   // activation scratch
-};
-void set_split_ctx(const SplitCtx* ctx);   // thread-local; nullptr disables
-void split_tf32(dx_stream_t s, int64_t rows, int64_t cols, const float* src, int64_t ld, float* hi, float* lo);
+bool tc_gemm(dx_stream_t s, const GemmP& p, int* tile_n, bool x3 = false);   // dx_tc_gemm.cu; false = not eligible
+// PREC_3XTF32: the same kernels with the operand hi/lo split done inside the kernel (shared memory), three MMAs per
+// k-step: FP32-accurate products for every operand form (forward, dgrad, wgrad), no operand copies in HBM.
 
 void gemm(dx_stream_t s, const GemmP& p);
 void prof_begin(int max_launches);

@@ -31,13 +31,20 @@ namespace {
 constexpr int TBM = 128, TBK = 32;           // 32 fp32 = one 128-byte swizzle row
 constexpr int A_BYTES = TBM * TBK * 4;       // 16 KB
 
-// X3: error-compensated "3xTF32" mode for FP32-accurate results on the tensor cores: every operand
-// comes as an exact pair (hi = top 11 mantissa bits, lo = remainder) and each k-step issues
-// hi*hi + hi*lo + lo*hi into the same FP32 accumulator (the dropped lo*lo term is ~2^-22 relative).
+// X3: error-compensated "3xTF32" mode for FP32-accurate results on the tensor cores.  kind::tf32 reads the top
+// 19 bits of each 32-bit operand word, so the raw fp32 tile TMA delivers IS the hi part (hi = v with the low 13
+// mantissa bits dropped).  Four extra "converter" warps (10..13) write lo = v - hi (exact in fp32) for every
+// element of a landed stage into a second buffer of the same layout — element-wise, so it is valid for K-major
+// and MN-major tiles alike — and each k-step issues hi*hi + hi*lo + lo*hi into the same FP32 accumulator (the
+// dropped lo*lo term is ~2^-22 relative).  No operand copies in HBM, no extra L2 traffic: the mode costs 3x the
+// MMA issue and one shared-memory read + write of the stage.
+constexpr int X3_WARPS = 4;
 template <int BN, bool X3 = false> struct TcCfg {
   static constexpr int B_BYTES = BN * TBK * 4;
-  static constexpr int STAGE = (A_BYTES + B_BYTES) * (X3 ? 2 : 1);
-  static constexpr int STAGES = X3 ? (BN == 128 ? 3 : 4) : ((BN == 256) ? 4 : (BN == 128 ? 6 : 8));
+  static constexpr int RAW = A_BYTES + B_BYTES;                    // bytes TMA delivers per stage
+  static constexpr int STAGE = RAW * (X3 ? 2 : 1);                 // X3: [A|B] raw, then [A_lo|B_lo]
+  static constexpr int STAGES = X3 ? (BN == 256 ? 2 : (BN == 128 ? 3 : 4)) : ((BN == 256) ? 4 : (BN == 128 ? 6 : 8));
+  static constexpr int THREADS = 320 + (X3 ? 32 * X3_WARPS : 0);
   static constexpr int SMEM = STAGES * STAGE + 1024 /*align*/ + 8 * 4096 /*store staging*/ + 256 /*barriers*/;
 };
 
@@ -50,6 +57,9 @@ struct TcParams {
   int add_tma;      // 1: the `add` matrix tile is prefetched into the staging slab by TMA
   int n_fast;       // tile order: 1 = the N tiles of one M panel are adjacent (concurrent CTAs share the big A panel in L2;
                     //             the weight-side operand is small and L2-resident anyway), 0 = M fastest
+  int x3_inplace;   // 3xTF32 debug switch (DX_X3_INPLACE=1): converters also overwrite the raw tile with hi
+  int x3_chunk;     // k_tc_gemm_x3: k-blocks (of 32) accumulated in TMEM before the FP32 register drain
+  int prefetch;     // producers prefetch their next tile's operand boxes into L2 (DX_TC_NO_PREFETCH=1 turns it off)
   long long* dbg;   // optional per-phase clock64() trace of CTA (0,0,0): DX_TC_DEBUG=1
 };
 
@@ -75,6 +85,11 @@ __device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint32_t dst
   asm volatile(
       "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
       ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1) : "memory");
+}
+// L2 prefetch of a tensor-map box (no shared-memory destination, no barrier)
+__device__ __forceinline__ void tma_prefetch_2d(const CUtensorMap* map, int c0, int c1) {
+  asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];"
+               ::"l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1) : "memory");
 }
 // SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor layout)
 // layout_type: 2 = SWIZZLE_128B (K-major tiles), 1 = SWIZZLE_128B_BASE32B (the only layout the
@@ -122,6 +137,159 @@ __device__ __forceinline__ float tc_act(float v, int act) {
   return v;
 }
 
+// 3xTF32 converter (warps 10..13, `tid` in [0, 32*X3_WARPS)): lo[i] = raw[i] - tf32_hi(raw[i]) over one landed stage.
+// The writes are generic-proxy stores that tcgen05.mma reads through the async proxy: fence before signalling.
+template <int NT>
+__device__ __forceinline__ void x3_split_stage_t(uint32_t raw, uint32_t lo, int bytes, int tid) {
+  // plain (non-volatile) vector accesses, four in flight per thread, so the loads of a batch overlap
+  const float4* src = reinterpret_cast<const float4*>(__cvta_shared_to_generic(raw));
+  float4* dst = reinterpret_cast<float4*>(__cvta_shared_to_generic(lo));
+  const int n = bytes / 16;
+  // lo = v - hi is exact in fp32 but has up to 13 significant bits, and the tensor core would TRUNCATE it to 11: round it
+  // to the nearest tf32 value here instead (half-up on the magnitude), which halves that residual and removes its bias
+  auto lo_of = [](float v) {
+    const float l = v - __uint_as_float(__float_as_uint(v) & 0xFFFFE000u);
+    return __uint_as_float((__float_as_uint(l) + 0x1000u) & 0xFFFFE000u);
+  };
+  int i = tid;
+  for (; i + 3 * NT < n; i += 4 * NT) {
+    const float4 v0 = src[i], v1 = src[i + NT], v2 = src[i + 2 * NT], v3 = src[i + 3 * NT];
+    dst[i] = make_float4(lo_of(v0.x), lo_of(v0.y), lo_of(v0.z), lo_of(v0.w));
+    dst[i + NT] = make_float4(lo_of(v1.x), lo_of(v1.y), lo_of(v1.z), lo_of(v1.w));
+    dst[i + 2 * NT] = make_float4(lo_of(v2.x), lo_of(v2.y), lo_of(v2.z), lo_of(v2.w));
+    dst[i + 3 * NT] = make_float4(lo_of(v3.x), lo_of(v3.y), lo_of(v3.z), lo_of(v3.w));
+  }
+  for (; i < n; i += NT) { const float4 v = src[i]; dst[i] = make_float4(lo_of(v.x), lo_of(v.y), lo_of(v.z), lo_of(v.w)); }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void x3_split_stage(uint32_t raw, uint32_t lo, int bytes, int tid, bool inplace) {
+  (void)inplace;
+  x3_split_stage_t<32 * X3_WARPS>(raw, lo, bytes, tid);
+}
+
+// One 32-row x 32-column piece of the output (v = this thread's accumulator row, columns gj..gj+31 of the tile row
+// block starting at row mq = m0 + 32*q): add / gate / bias / activation, then out through the warp's staging slab.
+struct EpiWarp {
+  uint32_t slab, abar, nstore; int lane, rsub, cc4; bool vec;
+};
+__device__ __forceinline__ void epi_cols32(const TcParams& p, const CUtensorMap* tmC, const CUtensorMap* tmAdd, float (&v)[32],
+                                           int gj, int mq, EpiWarp& w) {
+  const int lane = w.lane, rsub = w.rsub, cc4 = w.cc4;
+  const uint32_t slab = w.slab, abar = w.abar;
+  uint32_t& nstore = w.nstore;
+  const bool vec = w.vec;
+  const int gi = mq + lane;                                      // the accumulator row this thread owns
+  const bool row_ok = gi < p.M;
+  const bool full = gj + 32 <= p.N;                              // warp-uniform: whole chunk in bounds
+  const int m0 = mq, q = 0;                                      // (row block base: m0 + q * 32 == mq)
+    // the previous bulk store of this warp must have finished reading the slab
+    if (nstore > 0) { if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); __syncwarp(); }
+    if (p.add_tma) {
+      // `add` tile (32 rows x 32 cols of this warp) fetched by TMA into the slab it is later stored from
+      if (lane == 0) { mbar_expect_tx(abar, 4096); tma_load_2d(tmAdd, slab, abar, gj, m0 + q * 32); }
+      mbar_wait(abar, nstore & 1);
+      const uint32_t sl = slab + (uint32_t)(lane * 128);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float a0, a1, a2, a3;
+        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(a0), "=f"(a1), "=f"(a2), "=f"(a3)
+                     : "r"(sl + (uint32_t)(((j ^ (lane & 7)) << 4))) : "memory");
+        if (p.act == ACT_GATE) {
+          v[4 * j] = a0 > 0.f ? v[4 * j] : 0.f; v[4 * j + 1] = a1 > 0.f ? v[4 * j + 1] : 0.f;
+          v[4 * j + 2] = a2 > 0.f ? v[4 * j + 2] : 0.f; v[4 * j + 3] = a3 > 0.f ? v[4 * j + 3] : 0.f;
+        } else { v[4 * j] += a0; v[4 * j + 1] += a1; v[4 * j + 2] += a2; v[4 * j + 3] += a3; }
+      }
+    } else if (p.add) {
+      if (row_ok) {
+        const float* ar = p.add + (int64_t)gi * p.ldadd + gj;
+        if (full) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            const float4 a4 = __ldg(reinterpret_cast<const float4*>(ar + j));
+            if (p.act == ACT_GATE) {
+              v[j] = a4.x > 0.f ? v[j] : 0.f; v[j + 1] = a4.y > 0.f ? v[j + 1] : 0.f;
+              v[j + 2] = a4.z > 0.f ? v[j + 2] : 0.f; v[j + 3] = a4.w > 0.f ? v[j + 3] : 0.f;
+            } else { v[j] += a4.x; v[j + 1] += a4.y; v[j + 2] += a4.z; v[j + 3] += a4.w; }
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (gj + j < p.N) { const float a1 = __ldg(ar + j); if (p.act == ACT_GATE) v[j] = a1 > 0.f ? v[j] : 0.f; else v[j] += a1; }
+        }
+      }
+    }
+    if (p.bias) {
+      if (full) {
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+          const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + gj + j));   // same address in every lane
+          v[j] += b4.x; v[j + 1] += b4.y; v[j + 2] += b4.z; v[j + 3] += b4.w;
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) if (gj + j < p.N) v[j] += __ldg(p.bias + gj + j);
+      }
+    }
+    if (p.act == ACT_RELU) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+    } else if (p.act != ACT_NONE && p.act != ACT_GATE) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = tc_act(v[j], p.act);
+    }
+    // Each thread owns one accumulator row; rows go through the 128B-swizzled slab (conflict-free
+    // 128-bit accesses both ways).
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const uint32_t dst = slab + (uint32_t)(lane * 128) + (uint32_t)(((j ^ (lane & 7)) << 4));
+      asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "f"(v[4 * j]), "f"(v[4 * j + 1]),
+                   "f"(v[4 * j + 2]), "f"(v[4 * j + 3]) : "memory");
+    }
+    if (p.tma_store) {
+      // ... and leave as one 4 KB TMA bulk store (plain, or f32 reduce-add for accumulate / split-K
+      // modes): bulk stores are not limited by the epilogue warps' outstanding-store budget, unlike
+      // STG (measured 12x faster here).
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) {
+        if (p.accum == ACC_STORE) tma_store_2d(tmC, slab, gj, m0 + q * 32);
+        else tma_reduce_add_2d(tmC, slab, gj, m0 + q * 32);
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+      }
+      ++nstore;
+    } else {
+      // Fallback (row scatter through c_idx, or rows that are not 16-byte aligned): read the slab back
+      // row-wise and issue coalesced STG / RED (one warp instruction = 4 rows x 128 contiguous bytes).
+      __syncwarp();
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int rr = i * 4 + rsub;
+        const int gr = m0 + q * 32 + rr, gc = gj + cc4 * 4;
+        float o[4];
+        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(o[0]), "=f"(o[1]), "=f"(o[2]), "=f"(o[3])
+                     : "r"(slab + (uint32_t)(rr * 128) + (uint32_t)(((cc4 ^ (rr & 7)) << 4))) : "memory");
+        if (gr < p.M && gc < p.N) {
+          const int64_t crow = p.c_idx ? p.c_idx[gr] : gr;
+          float* dst = p.C + crow * p.ldc + gc;
+          if (p.accum == ACC_ATOMIC) {
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
+              if (gc + e < p.N) atomicAdd(dst + e, o[e]);
+          } else if (vec && gc + 3 < p.N) {
+            float4 w4 = make_float4(o[0], o[1], o[2], o[3]);
+            if (p.accum == ACC_ADD) { const float4 old = *reinterpret_cast<float4*>(dst); w4.x += old.x; w4.y += old.y; w4.z += old.z; w4.w += old.w; }
+            *reinterpret_cast<float4*>(dst) = w4;
+          } else {
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
+              if (gc + e < p.N) { if (p.accum == ACC_ADD) dst[e] += o[e]; else dst[e] = o[e]; }
+          }
+        }
+      }
+      __syncwarp();
+    }
+}
+
 // Epilogue of the persistent GEMM kernels (warps 2..9 of a CTA): drains the CTA's 128 accumulator lanes.
 template <int BN, class TileFn, class ArriveFn>
 __device__ __forceinline__ void tc_epilogue(const TcParams& p, const CUtensorMap* tmC, const CUtensorMap* tmAdd,
@@ -135,11 +303,11 @@ __device__ __forceinline__ void tc_epilogue(const TcParams& p, const CUtensorMap
   const int q = warp & 3;                                        // TMEM lane quadrant
   const int half = ew >> 2;                                      // which half of the BN columns
   constexpr int HC = BN / 2;
-  const uint32_t slab = stg_base + (uint32_t)ew * 4096u;         // one 32x32 fp32 staging slab per warp
-  const uint32_t abar = abar0 + 8u * ew;                         // `add` tile arrival barrier of this warp
-  const bool vec = ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0) && (p.ldc % 4 == 0);
-  const int rsub = lane >> 3, cc4 = lane & 7;
-  uint32_t lt = 0, nstore = 0;
+  EpiWarp w{stg_base + (uint32_t)ew * 4096u,                     // one 32x32 fp32 staging slab per warp
+            abar0 + 8u * ew,                                     // `add` tile arrival barrier of this warp
+            0u, lane, lane >> 3, lane & 7,
+            ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0) && (p.ldc % 4 == 0)};
+  uint32_t lt = 0;
   for (int t = t_first; t < total; t += t_stride, ++lt) {
     int m0, n0, kbeg, nkb; tile_coords(t, m0, n0, kbeg, nkb);
     const uint32_t as = lt & 1;
@@ -147,121 +315,13 @@ __device__ __forceinline__ void tc_epilogue(const TcParams& p, const CUtensorMap
     if (trace && threadIdx.x == 64 && lt < 8) p.dbg[208 + 2 * lt] = clock64();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tacc = tmem_base + as * BN + ((uint32_t)(q * 32) << 16);
-    const int gi = m0 + q * 32 + lane;                           // the accumulator row this thread owns
-    const bool row_ok = gi < p.M;
 #pragma unroll 1
     for (int c = half * HC; c < (half + 1) * HC; c += 32) {
       float v[32];
       tmem_ld32(tacc + (uint32_t)c, v);
       const int gj = n0 + c;
       if (gj >= p.N) continue;                                   // warp-uniform
-      const bool full = gj + 32 <= p.N;                          // warp-uniform: whole chunk in bounds
-      // the previous bulk store of this warp must have finished reading the slab
-      if (nstore > 0) { if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); __syncwarp(); }
-      if (p.add_tma) {
-        // `add` tile (32 rows x 32 cols of this warp) fetched by TMA into the slab it is later stored from
-        if (lane == 0) { mbar_expect_tx(abar, 4096); tma_load_2d(tmAdd, slab, abar, gj, m0 + q * 32); }
-        mbar_wait(abar, nstore & 1);
-        const uint32_t sl = slab + (uint32_t)(lane * 128);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          float a0, a1, a2, a3;
-          asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(a0), "=f"(a1), "=f"(a2), "=f"(a3)
-                       : "r"(sl + (uint32_t)(((j ^ (lane & 7)) << 4))) : "memory");
-          if (p.act == ACT_GATE) {
-            v[4 * j] = a0 > 0.f ? v[4 * j] : 0.f; v[4 * j + 1] = a1 > 0.f ? v[4 * j + 1] : 0.f;
-            v[4 * j + 2] = a2 > 0.f ? v[4 * j + 2] : 0.f; v[4 * j + 3] = a3 > 0.f ? v[4 * j + 3] : 0.f;
-          } else { v[4 * j] += a0; v[4 * j + 1] += a1; v[4 * j + 2] += a2; v[4 * j + 3] += a3; }
-        }
-      } else if (p.add) {
-        if (row_ok) {
-          const float* ar = p.add + (int64_t)gi * p.ldadd + gj;
-          if (full) {
-#pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              const float4 a4 = __ldg(reinterpret_cast<const float4*>(ar + j));
-              if (p.act == ACT_GATE) {
-                v[j] = a4.x > 0.f ? v[j] : 0.f; v[j + 1] = a4.y > 0.f ? v[j + 1] : 0.f;
-                v[j + 2] = a4.z > 0.f ? v[j + 2] : 0.f; v[j + 3] = a4.w > 0.f ? v[j + 3] : 0.f;
-              } else { v[j] += a4.x; v[j + 1] += a4.y; v[j + 2] += a4.z; v[j + 3] += a4.w; }
-            }
-          } else {
-#pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (gj + j < p.N) { const float a1 = __ldg(ar + j); if (p.act == ACT_GATE) v[j] = a1 > 0.f ? v[j] : 0.f; else v[j] += a1; }
-          }
-        }
-      }
-      if (p.bias) {
-        if (full) {
-#pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + gj + j));   // same address in every lane
-            v[j] += b4.x; v[j + 1] += b4.y; v[j + 2] += b4.z; v[j + 3] += b4.w;
-          }
-        } else {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) if (gj + j < p.N) v[j] += __ldg(p.bias + gj + j);
-        }
-      }
-      if (p.act == ACT_RELU) {
-#pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
-      } else if (p.act != ACT_NONE && p.act != ACT_GATE) {
-#pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = tc_act(v[j], p.act);
-      }
-      // Each thread owns one accumulator row; rows go through the 128B-swizzled slab (conflict-free
-      // 128-bit accesses both ways).
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const uint32_t dst = slab + (uint32_t)(lane * 128) + (uint32_t)(((j ^ (lane & 7)) << 4));
-        asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "f"(v[4 * j]), "f"(v[4 * j + 1]),
-                     "f"(v[4 * j + 2]), "f"(v[4 * j + 3]) : "memory");
-      }
-      if (p.tma_store) {
-        // ... and leave as one 4 KB TMA bulk store (plain, or f32 reduce-add for accumulate / split-K
-        // modes): bulk stores are not limited by the epilogue warps' outstanding-store budget, unlike
-        // STG (measured 12x faster here).
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        __syncwarp();
-        if (lane == 0) {
-          if (p.accum == ACC_STORE) tma_store_2d(tmC, slab, gj, m0 + q * 32);
-          else tma_reduce_add_2d(tmC, slab, gj, m0 + q * 32);
-          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-        }
-        ++nstore;
-      } else {
-        // Fallback (row scatter through c_idx, or rows that are not 16-byte aligned): read the slab back
-        // row-wise and issue coalesced STG / RED (one warp instruction = 4 rows x 128 contiguous bytes).
-        __syncwarp();
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int rr = i * 4 + rsub;
-          const int gr = m0 + q * 32 + rr, gc = gj + cc4 * 4;
-          float o[4];
-          asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(o[0]), "=f"(o[1]), "=f"(o[2]), "=f"(o[3])
-                       : "r"(slab + (uint32_t)(rr * 128) + (uint32_t)(((cc4 ^ (rr & 7)) << 4))) : "memory");
-          if (gr < p.M && gc < p.N) {
-            const int64_t crow = p.c_idx ? p.c_idx[gr] : gr;
-            float* dst = p.C + crow * p.ldc + gc;
-            if (p.accum == ACC_ATOMIC) {
-#pragma unroll
-              for (int e = 0; e < 4; ++e)
-                if (gc + e < p.N) atomicAdd(dst + e, o[e]);
-            } else if (vec && gc + 3 < p.N) {
-              float4 w4 = make_float4(o[0], o[1], o[2], o[3]);
-              if (p.accum == ACC_ADD) { const float4 old = *reinterpret_cast<float4*>(dst); w4.x += old.x; w4.y += old.y; w4.z += old.z; w4.w += old.w; }
-              *reinterpret_cast<float4*>(dst) = w4;
-            } else {
-#pragma unroll
-              for (int e = 0; e < 4; ++e)
-                if (gc + e < p.N) { if (p.accum == ACC_ADD) dst[e] += o[e]; else dst[e] = o[e]; }
-            }
-          }
-        }
-        __syncwarp();
-      }
+      epi_cols32(p, tmC, tmAdd, v, gj, m0 + q * 32, w);
     }
     // this warp's TMEM reads of the accumulator are complete: hand it back to the MMA warp
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -274,26 +334,24 @@ __device__ __forceinline__ void tc_epilogue(const TcParams& p, const CUtensorMap
 }
 
 template <int BN, bool A_MN, bool B_MN, bool X3 = false>
-__global__ void __launch_bounds__(320, 1) k_tc_gemm(const __grid_constant__ CUtensorMap tmA,
+__global__ void __launch_bounds__(TcCfg<BN, X3>::THREADS, 1) k_tc_gemm(const __grid_constant__ CUtensorMap tmA,
                                                     const __grid_constant__ CUtensorMap tmB,
                                                     const __grid_constant__ CUtensorMap tmC,
-                                                    const __grid_constant__ CUtensorMap tmAdd,
-                                                    const __grid_constant__ CUtensorMap tmAlo,
-                                                    const __grid_constant__ CUtensorMap tmBlo, const TcParams p) {
-  static_assert(!X3 || (!A_MN && !B_MN), "3xTF32 is only built for the forward (K-major) form");
+                                                    const __grid_constant__ CUtensorMap tmAdd, const TcParams p) {
   // Persistent: CTA b processes tiles b, b+grid, ... ; two accumulators in TMEM so the epilogue of
   // tile i overlaps the main loop of tile i+1.
   using Cfg = TcCfg<BN, X3>;
   constexpr int S = Cfg::STAGES;
-  constexpr int HALF = A_BYTES + Cfg::B_BYTES;                     // X3: [A_hi|B_hi] then [A_lo|B_lo]
+  constexpr int RAW = Cfg::RAW;                                    // X3: [A|B] raw then [A_lo|B_lo]
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;       // swizzle atoms need 1024-byte alignment
   const uint32_t stg_base = base + S * Cfg::STAGE;                    // 4 warps x 2 x 4 KB store staging
-  const uint32_t bars = stg_base + 8 * 4096;                      // full[S], empty[S], tfull[2], tempty[2], slot
+  const uint32_t bars = stg_base + 8 * 4096;                      // full[S], empty[S], tfull[2], tempty[2], slot, add[8], conv[S]
   auto full_bar = [&](int s) { return bars + 8u * s; };
   auto empty_bar = [&](int s) { return bars + 8u * (S + s); };
   auto tfull_bar = [&](int a) { return bars + 8u * (2 * S + a); };
   auto tempty_bar = [&](int a) { return bars + 8u * (2 * S + 2 + a); };
+  auto conv_bar = [&](int s) { return bars + 8u * (2 * S + 13 + s); };
   const uint32_t tmem_slot = bars + 8u * (2 * S + 4);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -304,7 +362,7 @@ __global__ void __launch_bounds__(320, 1) k_tc_gemm(const __grid_constant__ CUte
   if (trace && threadIdx.x == 0) p.dbg[200] = clock64();
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < S; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    for (int s = 0; s < S; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); if (X3) mbar_init(conv_bar(s), X3_WARPS); }
     for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 8); }
     for (int w = 0; w < 8; ++w) mbar_init(bars + 8u * (2 * S + 5 + w), 1);   // per-warp `add` tile barriers
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -336,7 +394,7 @@ __global__ void __launch_bounds__(320, 1) k_tc_gemm(const __grid_constant__ CUte
           const int s = it % S;
           mbar_wait(empty_bar(s), ((it / S) & 1) ^ 1);
           if (trace && it < 32) p.dbg[it] = clock64();
-          mbar_expect_tx(full_bar(s), Cfg::STAGE);
+          mbar_expect_tx(full_bar(s), RAW);
           const int k0 = kbeg + kb * TBK;
           const uint32_t sa = base + s * Cfg::STAGE, sb = sa + A_BYTES;
           if (!A_MN) tma_load_2d(&tmA, sa, full_bar(s), k0, m0);
@@ -347,10 +405,6 @@ __global__ void __launch_bounds__(320, 1) k_tc_gemm(const __grid_constant__ CUte
           else
 #pragma unroll
             for (int g = 0; g < BN / 32; ++g) tma_load_2d(&tmB, sb + g * 4096, full_bar(s), n0 + g * 32, k0);
-          if (X3) {
-            tma_load_2d(&tmAlo, sa + HALF, full_bar(s), k0, m0);
-            tma_load_2d(&tmBlo, sb + HALF, full_bar(s), k0, n0);
-          }
         }
       }
     }
@@ -368,7 +422,7 @@ __global__ void __launch_bounds__(320, 1) k_tc_gemm(const __grid_constant__ CUte
         const uint32_t tacc = tmem_base + as * BN;
         for (int kb = 0; kb < nkb; ++kb, ++it) {
           const int s = it % S;
-          mbar_wait(full_bar(s), (it / S) & 1);
+          mbar_wait(X3 ? conv_bar(s) : full_bar(s), (it / S) & 1); // X3: the converters have written the lo tiles
           if (trace && it < 32) p.dbg[64 + it] = clock64();
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
           const uint32_t sa = base + s * Cfg::STAGE, sb = sa + A_BYTES;
@@ -376,13 +430,17 @@ __global__ void __launch_bounds__(320, 1) k_tc_gemm(const __grid_constant__ CUte
           for (int k = 0; k < TBK / 8; ++k) {                      // UMMA_K = 8 for tf32
             // K-major: 8-row x 128 B atoms, SBO 1024; one UMMA_K = 32 B along the swizzled row.
             // MN-major: 4-row atoms (SBO 512 B), 32-element MN groups 4096 B apart (LBO); UMMA_K = 8 rows.
-            const uint64_t ad = A_MN ? umma_desc(sa + k * 1024, 4096, 512, 1) : umma_desc(sa + k * 32, 16, 1024, 2);
-            const uint64_t bd = B_MN ? umma_desc(sb + k * 1024, 4096, 512, 1) : umma_desc(sb + k * 32, 16, 1024, 2);
-            umma_tf32(tacc, ad, bd, idesc, (kb | k) != 0 ? 1u : 0u);
+            const uint32_t oa = A_MN ? sa + k * 1024 : sa + k * 32, ob = B_MN ? sb + k * 1024 : sb + k * 32;
+            const uint64_t ad = A_MN ? umma_desc(oa, 4096, 512, 1) : umma_desc(oa, 16, 1024, 2);
+            const uint64_t bd = B_MN ? umma_desc(ob, 4096, 512, 1) : umma_desc(ob, 16, 1024, 2);
             if (X3) {
-              const uint64_t adl = umma_desc(sa + HALF + k * 32, 16, 1024, 2), bdl = umma_desc(sb + HALF + k * 32, 16, 1024, 2);
-              umma_tf32(tacc, ad, bdl, idesc, 1u);                 // hi * lo
-              umma_tf32(tacc, adl, bd, idesc, 1u);                 // lo * hi
+              const uint64_t adl = A_MN ? umma_desc(oa + RAW, 4096, 512, 1) : umma_desc(oa + RAW, 16, 1024, 2);
+              const uint64_t bdl = B_MN ? umma_desc(ob + RAW, 4096, 512, 1) : umma_desc(ob + RAW, 16, 1024, 2);
+              umma_tf32(tacc, ad, bdl, idesc, (kb | k) != 0 ? 1u : 0u);   // hi * lo   (small terms first)
+              umma_tf32(tacc, adl, bd, idesc, 1u);                        // lo * hi
+              umma_tf32(tacc, ad, bd, idesc, 1u);                         // hi * hi
+            } else {
+              umma_tf32(tacc, ad, bd, idesc, (kb | k) != 0 ? 1u : 0u);
             }
           }
           umma_commit(empty_bar(s));                               // frees the smem stage when these MMAs retire
@@ -390,11 +448,25 @@ __global__ void __launch_bounds__(320, 1) k_tc_gemm(const __grid_constant__ CUte
         umma_commit(tfull_bar(as));                                // accumulator complete
       }
     }
-  } else {                                                         // ---- epilogue: warps 2..9
+  } else if (warp < 10) {                                          // ---- epilogue: warps 2..9
     tc_epilogue<BN>(p, &tmC, &tmAdd, tmem_base, stg_base, bars + 8u * (2 * S + 5), tfull_bar(0), (int)blockIdx.x,
                     (int)gridDim.x, total, tile_coords,
                     [&](uint32_t as) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tempty_bar(as)) : "memory"); },
                     trace);
+  } else if (X3) {                                                 // ---- 3xTF32 converters: warps 10..13
+    uint32_t it = 0;
+    const int ctid = threadIdx.x - 320;
+    for (int t = blockIdx.x; t < total; t += gridDim.x) {
+      int m0, n0, kbeg, nkb; tile_coords(t, m0, n0, kbeg, nkb);
+      for (int kb = 0; kb < nkb; ++kb, ++it) {
+        const int s = it % S;
+        mbar_wait(full_bar(s), (it / S) & 1);
+        const uint32_t sa = base + s * Cfg::STAGE;
+        x3_split_stage(sa, sa + RAW, RAW, ctid, p.x3_inplace != 0);
+        __syncwarp();
+        if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(conv_bar(s)) : "memory");
+      }
+    }
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
@@ -414,9 +486,13 @@ __global__ void __launch_bounds__(320, 1) k_tc_gemm(const __grid_constant__ CUte
 // barriers; each CTA drains its own 128 TMEM lanes and both report to the leader's "accumulator
 // empty" barrier.
 // =============================================================================================
-constexpr int S2 = 6;
-constexpr int STAGE2 = A_BYTES + 128 * TBK * 4;   // 32 KB per CTA
-constexpr int SMEM2 = S2 * STAGE2 + 1024 + 8 * 4096 + 256;
+constexpr int RAW2 = A_BYTES + 128 * TBK * 4;     // 32 KB per CTA per stage from TMA
+template <bool X3> struct Tc2Cfg {
+  static constexpr int S = X3 ? 3 : 6;
+  static constexpr int STAGE = RAW2 * (X3 ? 2 : 1);                // X3: raw [A|B half] then [A_lo|B_lo]
+  static constexpr int THREADS = 320 + (X3 ? 32 * X3_WARPS : 0);
+  static constexpr int SMEM = S * STAGE + 1024 + 8 * 4096 + 256;
+};
 
 __device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
 __device__ __forceinline__ void cluster_sync_all() {
@@ -433,6 +509,12 @@ __device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity)
       "bra.uni WAIT_LOOP;\n\t"
       "WAIT_DONE:\n\t"
       "}" ::"r"(bar), "r"(parity) : "memory");
+}
+// arrive on the LEADER CTA's copy of a barrier (remote arrive from the peer, local from the leader itself)
+__device__ __forceinline__ void mbar_arrive_leader(uint32_t bar) {
+  uint32_t ra;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, 0;" : "=r"(ra) : "r"(bar));
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(ra) : "memory");
 }
 // TMA load whose completion bytes go to the LEADER CTA's mbarrier (peer bit cleared: cute Sm100MmaPeerBitMask)
 __device__ __forceinline__ void tma_load_2d_2sm(const CUtensorMap* map, uint32_t dst, uint32_t bar, int c0, int c1) {
@@ -464,12 +546,14 @@ __device__ __forceinline__ void umma_commit_2sm(uint32_t bar) {   // arrives on 
 // BF16 (K-major operands only, groundwork for DESIGN.md §7 item 1): the operands are bf16 in HBM; a 128-byte tile row then
 // holds 64 k-values and one UMMA (kind::f16) covers K = 16 = the same 32 bytes, so stage bytes, swizzle, descriptors and
 // barriers are unchanged — only the k extent of a stage, the instruction kind and the format codes differ.
-template <bool A_MN, bool B_MN, bool BF16 = false>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(320, 1)
+// X3 (3xTF32, see TcCfg): each CTA's TMA signals its OWN "full" barrier; its converter warps (10..13) write the lo
+// tiles and report to the leader's "converted" barrier, which is what the MMA issuer waits on.
+template <bool A_MN, bool B_MN, bool BF16 = false, bool X3 = false>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(Tc2Cfg<X3>::THREADS, 1)
 k_tc_gemm2(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
            const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmAdd, const TcParams p) {
-  static_assert(!BF16 || (!A_MN && !B_MN), "bf16 operands: K-major only");
-  constexpr int BN = 256, S = S2;
+  static_assert(!BF16 || (!A_MN && !B_MN && !X3), "bf16 operands: K-major only");
+  constexpr int BN = 256, S = Tc2Cfg<X3>::S, STAGE2 = Tc2Cfg<X3>::STAGE;
   constexpr int TKE = BF16 ? 64 : TBK;                              // k-values per stage
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -479,6 +563,7 @@ k_tc_gemm2(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
   auto empty_bar = [&](int s) { return bars + 8u * (S + s); };
   auto tfull_bar = [&](int a) { return bars + 8u * (2 * S + a); };
   auto tempty_bar = [&](int a) { return bars + 8u * (2 * S + 2 + a); };
+  auto conv_bar = [&](int s) { return bars + 8u * (2 * S + 13 + s); };
   const uint32_t tmem_slot = bars + 8u * (2 * S + 4);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -492,7 +577,7 @@ k_tc_gemm2(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
   if (trace && threadIdx.x == 0) p.dbg[200] = clock64();
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < S; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    for (int s = 0; s < S; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); if (X3) mbar_init(conv_bar(s), 2 * X3_WARPS); }
     for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 16); }   // 8 warps x 2 CTAs
     for (int w = 0; w < 8; ++w) mbar_init(bars + 8u * (2 * S + 5 + w), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -521,13 +606,41 @@ k_tc_gemm2(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
       for (int t = cid; t < total; t += ncl) {
         int m0, n0, kbeg, nkb; tile_coords(t, m0, n0, kbeg, nkb);
         const int nb0 = n0 + (int)rank * 128;                      // this CTA's half of the B tile
+        // L2 prefetch of this cluster's next tile (see k_tc_gemm_x3w): the clusters sharing a panel ask for it at the
+        // same moment, so without it every operand load sees DRAM latency
+        int pm0 = 0, pn0 = 0, pk = 0, pnkb = 0;
+        const bool pf = p.prefetch && t + ncl < total;
+        if (pf) tile_coords(t + ncl, pm0, pn0, pk, pnkb);
         for (int kb = 0; kb < nkb; ++kb, ++it) {
           const int s = it % S;
           mbar_wait_cluster(empty_bar(s), ((it / S) & 1) ^ 1);
           if (trace && it < 32) p.dbg[it] = clock64();
-          if (leader) mbar_expect_tx(full_bar(s), 2 * STAGE2);     // bytes of both CTAs land on the leader's barrier
           const int k0 = kbeg + kb * TKE;
+          if (pf && kb < pnkb) {
+            const int q0 = pk + kb * TKE, qn = pn0 + (int)rank * 128;
+            if (!A_MN) tma_prefetch_2d(&tmA, q0, pm0);
+            else
+#pragma unroll
+              for (int g = 0; g < 4; ++g) tma_prefetch_2d(&tmA, pm0 + g * 32, q0);
+            if (!B_MN) tma_prefetch_2d(&tmB, q0, qn);
+            else
+#pragma unroll
+              for (int g = 0; g < 4; ++g) tma_prefetch_2d(&tmB, qn + g * 32, q0);
+          }
           const uint32_t sa = base + s * STAGE2, sb = sa + A_BYTES;
+          if (X3) {                                                // bytes land on this CTA's own barrier (its converters wait there)
+            mbar_expect_tx(full_bar(s), RAW2);
+            if (!A_MN) tma_load_2d(&tmA, sa, full_bar(s), k0, m0);
+            else
+#pragma unroll
+              for (int g = 0; g < 4; ++g) tma_load_2d(&tmA, sa + g * 4096, full_bar(s), m0 + g * 32, k0);
+            if (!B_MN) tma_load_2d(&tmB, sb, full_bar(s), k0, nb0);
+            else
+#pragma unroll
+              for (int g = 0; g < 4; ++g) tma_load_2d(&tmB, sb + g * 4096, full_bar(s), nb0 + g * 32, k0);
+            continue;
+          }
+          if (leader) mbar_expect_tx(full_bar(s), 2 * RAW2);       // bytes of both CTAs land on the leader's barrier
           if (!A_MN) tma_load_2d_2sm(&tmA, sa, full_bar(s), k0, m0);
           else
 #pragma unroll
@@ -553,37 +666,510 @@ k_tc_gemm2(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
         const uint32_t tacc = tmem_base + as * BN;
         for (int kb = 0; kb < nkb; ++kb, ++it) {
           const int s = it % S;
-          mbar_wait_cluster(full_bar(s), (it / S) & 1);
+          mbar_wait_cluster(X3 ? conv_bar(s) : full_bar(s), (it / S) & 1);
           if (trace && it < 32) p.dbg[64 + it] = clock64();
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
           const uint32_t sa = base + s * STAGE2, sb = sa + A_BYTES;
 #pragma unroll
           for (int k = 0; k < TBK / 8; ++k) {
-            const uint64_t ad = A_MN ? umma_desc(sa + k * 1024, 4096, 512, 1) : umma_desc(sa + k * 32, 16, 1024, 2);
-            const uint64_t bd = B_MN ? umma_desc(sb + k * 1024, 4096, 512, 1) : umma_desc(sb + k * 32, 16, 1024, 2);
+            const uint32_t oa = A_MN ? sa + k * 1024 : sa + k * 32, ob = B_MN ? sb + k * 1024 : sb + k * 32;
+            const uint64_t ad = A_MN ? umma_desc(oa, 4096, 512, 1) : umma_desc(oa, 16, 1024, 2);
+            const uint64_t bd = B_MN ? umma_desc(ob, 4096, 512, 1) : umma_desc(ob, 16, 1024, 2);
             if (BF16) umma_f16_2sm(tacc, ad, bd, idesc, (kb | k) != 0 ? 1u : 0u);
-            else umma_tf32_2sm(tacc, ad, bd, idesc, (kb | k) != 0 ? 1u : 0u);
+            else if (X3) {
+              const uint64_t adl = A_MN ? umma_desc(oa + RAW2, 4096, 512, 1) : umma_desc(oa + RAW2, 16, 1024, 2);
+              const uint64_t bdl = B_MN ? umma_desc(ob + RAW2, 4096, 512, 1) : umma_desc(ob + RAW2, 16, 1024, 2);
+              umma_tf32_2sm(tacc, ad, bdl, idesc, (kb | k) != 0 ? 1u : 0u);   // hi * lo   (small terms first)
+              umma_tf32_2sm(tacc, adl, bd, idesc, 1u);                        // lo * hi
+              umma_tf32_2sm(tacc, ad, bd, idesc, 1u);                         // hi * hi
+            } else umma_tf32_2sm(tacc, ad, bd, idesc, (kb | k) != 0 ? 1u : 0u);
           }
           umma_commit_2sm(empty_bar(s));                           // frees the stage in both CTAs
         }
         umma_commit_2sm(tfull_bar(as));                            // accumulator complete, both CTAs' epilogues
       }
     }
-  } else {
+  } else if (warp < 10) {
     tc_epilogue<BN>(p, &tmC, &tmAdd, tmem_base, stg_base, bars + 8u * (2 * S + 5), tfull_bar(0), cid, ncl, total, tile_coords,
-                    [&](uint32_t as) {
-                      // report to the LEADER's "accumulator empty" barrier (remote arrive from the peer CTA)
-                      uint32_t ra;
-                      asm volatile("mapa.shared::cluster.u32 %0, %1, 0;" : "=r"(ra) : "r"(tempty_bar(as)));
-                      asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(ra) : "memory");
-                    },
+                    [&](uint32_t as) { mbar_arrive_leader(tempty_bar(as)); },   // the LEADER's "accumulator empty" barrier
                     trace);
+  } else if (X3) {                                                 // ---- 3xTF32 converters: warps 10..13 of both CTAs
+    uint32_t it = 0;
+    const int ctid = threadIdx.x - 320;
+    for (int t = cid; t < total; t += ncl) {
+      int m0, n0, kbeg, nkb; tile_coords(t, m0, n0, kbeg, nkb);
+      for (int kb = 0; kb < nkb; ++kb, ++it) {
+        const int s = it % S;
+        mbar_wait(full_bar(s), (it / S) & 1);                      // this CTA's own tiles have landed
+        const uint32_t sa = base + s * STAGE2;
+        x3_split_stage(sa, sa + RAW2, RAW2, ctid, p.x3_inplace != 0);
+        __syncwarp();
+        if (lane == 0) mbar_arrive_leader(conv_bar(s));
+      }
+    }
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   cluster_sync_all();                                              // nobody may still address the peer's smem / TMEM
   if (warp == 1) {
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(2 * BN) : "memory");
+  }
+}
+
+// =============================================================================================
+// 3xTF32 with chunked accumulation ("x3c"): FP32-accurate products on the tensor cores.
+//
+// Measured on B200 (tools/x3_bias_probe.py): tcgen05 adds each MMA's partial product into the FP32 TMEM
+// accumulator with TRUNCATION toward zero, about one ulp per instruction, so a K = 1024 reduction issued as
+// 3 x 128 MMAs into one accumulator comes out 2e-5 short — a bias that is coherent across the 40 dependent
+// products of a training step (gradients off by 5e-4).  The error is proportional to the number of MMAs
+// accumulated in TMEM, so this kernel keeps that number small:
+//   * the hi*hi terms of x3c_chunk k-blocks (default 2 = 8 MMAs) go into a "chunk" accumulator that the epilogue
+//     warps drain into FP32 REGISTERS (round-to-nearest adds) while the next chunk runs in the other buffer;
+//   * the hi*lo / lo*hi cross terms (2^-11 of the result) go into their own accumulator for the whole tile:
+//     their truncation is relative to that small magnitude.
+// Tile: 128 rows x 128 columns per CTA (a pair of CTAs forms 256 x 128 with cta_group::2, each staging its 128
+// rows of A and 64 of the 128 B rows).  TMEM: 2 chunk buffers + 2 cross buffers (tile double buffering) x 128
+// columns = 512.  Warps: 0 TMA, 1 MMA issue, 2-9 epilogue (64 columns of one lane quadrant each: 64 running
+// sums per thread), 10-13 converters (lo = v - tf32(v) over each landed stage, see x3_split_stage).
+// =============================================================================================
+template <bool CTA2> struct X3Cfg {
+  static constexpr int BN = 128;
+  static constexpr int BROWS = CTA2 ? 64 : 128;                    // B rows staged by one CTA
+  static constexpr int RAW = A_BYTES + BROWS * TBK * 4;            // 24 KB / 32 KB
+  static constexpr int STAGE = 2 * RAW;
+  static constexpr int S = CTA2 ? 4 : 3;
+  static constexpr int THREADS = 320 + 32 * X3_WARPS;
+  static constexpr int SMEM = S * STAGE + 1024 + 8 * 4096 + 256;
+};
+
+template <bool A_MN, bool B_MN, bool CTA2>
+__global__ void __launch_bounds__(X3Cfg<CTA2>::THREADS, 1)
+k_tc_gemm_x3(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+             const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmAdd, const TcParams p) {
+  using Cfg = X3Cfg<CTA2>;
+  constexpr int BN = Cfg::BN, S = Cfg::S, RAW = Cfg::RAW, STAGE = Cfg::STAGE, BROWS = Cfg::BROWS;
+  constexpr int TM = CTA2 ? 256 : 128;                             // rows of the (pair) tile
+  constexpr uint32_t NEPI = CTA2 ? 16 : 8;                         // epilogue warps reporting to a leader barrier
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t stg_base = base + S * STAGE;
+  const uint32_t bars = stg_base + 8 * 4096;
+  // full[S] empty[S] conv[S] | cfull[2] cempty[2] xfull[2] xempty[2] | tmem slot | add[8]
+  auto full_bar = [&](int s) { return bars + 8u * s; };
+  auto empty_bar = [&](int s) { return bars + 8u * (S + s); };
+  auto conv_bar = [&](int s) { return bars + 8u * (2 * S + s); };
+  auto cfull_bar = [&](int b) { return bars + 8u * (3 * S + b); };
+  auto cempty_bar = [&](int b) { return bars + 8u * (3 * S + 2 + b); };
+  auto xfull_bar = [&](int b) { return bars + 8u * (3 * S + 4 + b); };
+  auto xempty_bar = [&](int b) { return bars + 8u * (3 * S + 6 + b); };
+  const uint32_t tmem_slot = bars + 8u * (3 * S + 8);
+  const uint32_t add_bar0 = bars + 8u * (3 * S + 9);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = CTA2 ? cluster_ctarank() : 0u;
+  const bool leader = rank == 0;
+  const int gm = (p.M + TM - 1) / TM, gn = (p.N + BN - 1) / BN;
+  const int splits = (p.K + p.k_chunk - 1) / p.k_chunk;
+  const int total = gm * gn * splits;
+  const int cid = CTA2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x, ncl = CTA2 ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+  const int CH = p.x3_chunk;                                       // k-blocks per chunk accumulator
+  const int dbg = p.x3_inplace;                                    // DX_X3_DBG experiment switches (results are wrong when set)
+  const bool trace = p.dbg && blockIdx.x == 0;                     // DX_TC_DEBUG: clock64() stamps of the first 40 k-blocks of CTA 0
+  if (trace && threadIdx.x == 0) p.dbg[250] = clock64();
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < S; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); mbar_init(conv_bar(s), (CTA2 ? 2 : 1) * X3_WARPS); }
+    for (int b = 0; b < 2; ++b) { mbar_init(cfull_bar(b), 1); mbar_init(cempty_bar(b), NEPI); mbar_init(xfull_bar(b), 1); mbar_init(xempty_bar(b), NEPI); }
+    for (int w = 0; w < 8; ++w) mbar_init(add_bar0 + 8u * w, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    if (CTA2) {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(512) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(512) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  if (CTA2) cluster_sync_all(); else __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  uint32_t tmem_base;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+  auto tile_coords = [&](int t, int& m0, int& n0, int& kbeg, int& nkb) {
+    const int mt = p.n_fast ? (t / gn) % gm : t % gm, nt = p.n_fast ? t % gn : (t / gm) % gn, z = t / (gm * gn);
+    m0 = mt * TM + (int)rank * TBM; n0 = nt * BN; kbeg = z * p.k_chunk;   // this CTA's 128 rows
+    const int kend = min(p.K, kbeg + p.k_chunk);
+    nkb = (kend - kbeg + TBK - 1) / TBK;
+  };
+  auto wait_leader = [&](uint32_t bar, uint32_t parity) { if (CTA2) mbar_wait_cluster(bar, parity); else mbar_wait(bar, parity); };
+  auto arrive_leader = [&](uint32_t bar) {
+    if (CTA2) mbar_arrive_leader(bar);
+    else asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+  };
+  auto commit = [&](uint32_t bar) { if (CTA2) umma_commit_2sm(bar); else umma_commit(bar); };
+
+  if (warp == 0) {
+    if (lane == 0) {                                               // ---- TMA producer: bytes land on this CTA's own barrier
+      uint32_t it = 0;
+      for (int t = cid; t < total; t += ncl) {
+        int m0, n0, kbeg, nkb; tile_coords(t, m0, n0, kbeg, nkb);
+        const int nb0 = n0 + (int)rank * BROWS;                    // this CTA's rows of the B tile
+        for (int kb = 0; kb < nkb; ++kb, ++it) {
+          const int s = it % S;
+          wait_leader(empty_bar(s), ((it / S) & 1) ^ 1);
+          if (trace && it < 40) p.dbg[it] = clock64();
+          mbar_expect_tx(full_bar(s), RAW);
+          const int k0 = kbeg + kb * TBK;
+          const uint32_t sa = base + s * STAGE, sb = sa + A_BYTES;
+          if (!A_MN) tma_load_2d(&tmA, sa, full_bar(s), k0, m0);
+          else
+#pragma unroll
+            for (int g = 0; g < TBM / 32; ++g) tma_load_2d(&tmA, sa + g * 4096, full_bar(s), m0 + g * 32, k0);
+          if (!B_MN) tma_load_2d(&tmB, sb, full_bar(s), k0, nb0);
+          else
+#pragma unroll
+            for (int g = 0; g < BROWS / 32; ++g) tma_load_2d(&tmB, sb + g * 4096, full_bar(s), nb0 + g * 32, k0);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0 && leader) {                                     // ---- MMA issuer
+      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((A_MN ? 1u : 0u) << 15) | ((B_MN ? 1u : 0u) << 16) |
+                             ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
+      auto mma = [&](uint32_t d, uint64_t ad, uint64_t bd, uint32_t acc) {
+        if (CTA2) umma_tf32_2sm(d, ad, bd, idesc, acc); else umma_tf32(d, ad, bd, idesc, acc);
+      };
+      uint32_t it = 0, lt = 0, gc = 0;                             // stage, tile and chunk counters
+      for (int t = cid; t < total; t += ncl, ++lt) {
+        int m0, n0, kbeg, nkb; tile_coords(t, m0, n0, kbeg, nkb);
+        const uint32_t xb = lt & 1;
+        wait_leader(xempty_bar(xb), ((lt >> 1) & 1) ^ 1);          // cross accumulator of tile lt-2 has been read
+        const uint32_t tcross = tmem_base + 256 + xb * BN;
+        for (int kb0 = 0; kb0 < nkb; kb0 += CH, ++gc) {
+          const uint32_t cb = gc & 1;
+          wait_leader(cempty_bar(cb), ((gc >> 1) & 1) ^ 1);        // chunk accumulator drained
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const uint32_t tmain = tmem_base + cb * BN;
+          const int kb1 = min(nkb, kb0 + CH);
+          for (int kb = kb0; kb < kb1; ++kb, ++it) {
+            const int s = it % S;
+            wait_leader(conv_bar(s), (it / S) & 1);                // raw tiles landed and lo tiles written, both CTAs
+            if (trace && it < 40) p.dbg[120 + it] = clock64();
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t sa = base + s * STAGE, sb = sa + A_BYTES;
+#pragma unroll
+            for (int k = 0; k < TBK / 8; ++k) {
+              const uint32_t oa = A_MN ? sa + k * 1024 : sa + k * 32, ob = B_MN ? sb + k * 1024 : sb + k * 32;
+              const uint64_t ad = A_MN ? umma_desc(oa, 4096, 512, 1) : umma_desc(oa, 16, 1024, 2);
+              const uint64_t bd = B_MN ? umma_desc(ob, 4096, 512, 1) : umma_desc(ob, 16, 1024, 2);
+              const uint64_t adl = A_MN ? umma_desc(oa + RAW, 4096, 512, 1) : umma_desc(oa + RAW, 16, 1024, 2);
+              const uint64_t bdl = B_MN ? umma_desc(ob + RAW, 4096, 512, 1) : umma_desc(ob + RAW, 16, 1024, 2);
+              if (dbg & 16) continue;
+              if (!(dbg & 2)) {
+                mma((dbg & 4) ? tmain : tcross, ad, bdl, ((dbg & 4) ? (kb != kb0 || k != 0) : (kb | k) != 0) ? 1u : 0u);   // hi * lo
+                mma((dbg & 4) ? tmain : tcross, adl, bd, 1u);      // lo * hi
+                mma(tmain, ad, bd, ((dbg & 4) || kb != kb0 || k != 0) ? 1u : 0u);   // hi * hi, fresh accumulator per chunk
+              } else
+              mma(tmain, ad, bd, (kb != kb0 || k != 0) ? 1u : 0u); // hi * hi, fresh accumulator per chunk
+            }
+            commit(empty_bar(s));
+          }
+          commit(cfull_bar(cb));
+        }
+        commit(xfull_bar(xb));
+      }
+    }
+  } else if (warp < 10) {                                          // ---- epilogue: warps 2..9
+    const int ew = warp - 2, q = warp & 3, half = ew >> 2;
+    EpiWarp w{stg_base + (uint32_t)ew * 4096u, add_bar0 + 8u * ew, 0u, lane, lane >> 3, lane & 7,
+              ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0) && (p.ldc % 4 == 0)};
+    const uint32_t tlane = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(half * 64);
+    uint32_t lt = 0, gc = 0;
+    for (int t = cid; t < total; t += ncl, ++lt) {
+      int m0, n0, kbeg, nkb; tile_coords(t, m0, n0, kbeg, nkb);
+      float a0[32], a1[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) { a0[j] = 0.f; a1[j] = 0.f; }
+      for (int kb0 = 0; kb0 < nkb; kb0 += CH, ++gc) {
+        const uint32_t cb = gc & 1;
+        mbar_wait(cfull_bar(cb), (gc >> 1) & 1);
+        if (trace && threadIdx.x == 64 && gc < 20) p.dbg[160 + gc] = clock64();
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        if (!(dbg & 8)) {
+          float v[32];                                             // (32 columns at a time: 64 sums + 32 loaded values live)
+          tmem_ld32(tlane + cb * BN, v);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) a0[j] += v[j];
+          tmem_ld32(tlane + cb * BN + 32, v);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) a1[j] += v[j];
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) arrive_leader(cempty_bar(cb));
+        if (trace && threadIdx.x == 64 && gc < 20) p.dbg[180 + gc] = clock64();
+      }
+      {
+        const uint32_t xb = lt & 1;
+        mbar_wait(xfull_bar(xb), (lt >> 1) & 1);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        {
+          float v[32];
+          tmem_ld32(tlane + 256 + xb * BN, v);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) a0[j] += v[j];
+          tmem_ld32(tlane + 256 + xb * BN + 32, v);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) a1[j] += v[j];
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) arrive_leader(xempty_bar(xb));
+      }
+      const int gj = n0 + half * 64;
+      if (gj < p.N) epi_cols32(p, &tmC, &tmAdd, a0, gj, m0 + q * 32, w);
+      if (gj + 32 < p.N) epi_cols32(p, &tmC, &tmAdd, a1, gj + 32, m0 + q * 32, w);
+    }
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+    __syncwarp();
+  } else {                                                         // ---- converters: warps 10..13
+    uint32_t it = 0;
+    const int ctid = threadIdx.x - 320;
+    for (int t = cid; t < total; t += ncl) {
+      int m0, n0, kbeg, nkb; tile_coords(t, m0, n0, kbeg, nkb);
+      for (int kb = 0; kb < nkb; ++kb, ++it) {
+        const int s = it % S;
+        mbar_wait(full_bar(s), (it / S) & 1);
+        if (trace && ctid == 0 && it < 40) p.dbg[40 + it] = clock64();
+        const uint32_t sa = base + s * STAGE;
+        if (!(dbg & 1)) x3_split_stage(sa, sa + RAW, RAW, ctid, false);
+        __syncwarp();
+        if (lane == 0) arrive_leader(conv_bar(s));
+        if (trace && ctid == 0 && it < 40) p.dbg[80 + it] = clock64();
+      }
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  if (CTA2) cluster_sync_all(); else __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    if (CTA2) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+    else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+  }
+}
+
+// =============================================================================================
+// "x3w": the chunked 3xTF32 scheme on the WIDE pair tile (256 x 256, cta_group::2) for the large products.
+// k_tc_gemm_x3 above pays for its 128-column tiles: half the flops per staged byte, and the main loop of this path is
+// bound by the latency of the load -> convert -> MMA -> release loop times the bytes that fit in shared memory
+// (measured: 143 TFLOP/s against 224 for the single-accumulator 256 x 256 kernel on the same product).  Here:
+//   * a chunk is ONE k-block (32 k): its 8 cross-term MMAs (hi*lo, lo*hi) are issued FIRST into the fresh chunk
+//     accumulator, while it only holds values 2^-11 of the final size (their truncation is then negligible), followed
+//     by the 4 hi*hi MMAs — four truncating accumulations per chunk, no separate cross accumulator;
+//   * the two chunk accumulators take the whole TMEM (2 x 256 columns); the 8 epilogue warps drain each finished
+//     chunk into 128 FP32 running sums per thread (the kernel runs 384 threads so that each may hold 168 registers).
+// Warps: 0 TMA, 1 MMA issue, 2-3 converters, 4-11 epilogue (lane quadrant = warp % 4, column half = (warp-4) / 4).
+// =============================================================================================
+struct X3wCfg {
+  static constexpr int BN = 256, S = 3;
+  static constexpr int RAW = A_BYTES + 128 * TBK * 4;              // 32 KB per CTA per stage
+  static constexpr int STAGE = 2 * RAW;
+  static constexpr int THREADS = 384;
+  static constexpr int SMEM = S * STAGE + 1024 + 8 * 4096 + 256;
+};
+
+template <bool A_MN, bool B_MN>
+__global__ void __launch_bounds__(X3wCfg::THREADS, 1)
+k_tc_gemm_x3w(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+              const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmAdd, const TcParams p) {
+  using Cfg = X3wCfg;
+  constexpr int BN = Cfg::BN, S = Cfg::S, RAW = Cfg::RAW, STAGE = Cfg::STAGE;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t stg_base = base + S * STAGE;
+  const uint32_t bars = stg_base + 8 * 4096;
+  // full[S] empty[S] conv[S] | cfull[2] cempty[2] | tmem slot | add[8]
+  auto full_bar = [&](int s) { return bars + 8u * s; };
+  auto empty_bar = [&](int s) { return bars + 8u * (S + s); };
+  auto conv_bar = [&](int s) { return bars + 8u * (2 * S + s); };
+  auto cfull_bar = [&](int b) { return bars + 8u * (3 * S + b); };
+  auto cempty_bar = [&](int b) { return bars + 8u * (3 * S + 2 + b); };
+  const uint32_t tmem_slot = bars + 8u * (3 * S + 4);
+  const uint32_t add_bar0 = bars + 8u * (3 * S + 5);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+  const int gm = (p.M + 255) / 256, gn = (p.N + BN - 1) / BN;
+  const int splits = (p.K + p.k_chunk - 1) / p.k_chunk;
+  const int total = gm * gn * splits;
+  const int cid = blockIdx.x >> 1, ncl = gridDim.x >> 1;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < S; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); mbar_init(conv_bar(s), 4); }   // 2 warps x 2 CTAs
+    for (int b = 0; b < 2; ++b) { mbar_init(cfull_bar(b), 1); mbar_init(cempty_bar(b), 16); }                           // 8 warps x 2 CTAs
+    for (int w = 0; w < 8; ++w) mbar_init(add_bar0 + 8u * w, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(512) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  cluster_sync_all();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  uint32_t tmem_base;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+  auto tile_coords = [&](int t, int& m0, int& n0, int& kbeg, int& nkb) {
+    const int mt = p.n_fast ? (t / gn) % gm : t % gm, nt = p.n_fast ? t % gn : (t / gm) % gn, z = t / (gm * gn);
+    m0 = mt * 256 + (int)rank * TBM; n0 = nt * BN; kbeg = z * p.k_chunk;
+    const int kend = min(p.K, kbeg + p.k_chunk);
+    nkb = (kend - kbeg + TBK - 1) / TBK;
+  };
+
+  if (warp < 4) {
+    if (warp == 0) {
+      if (lane == 0) {                                             // ---- TMA producer (bytes land on this CTA's own barrier)
+        uint32_t it = 0;
+        for (int t = cid; t < total; t += ncl) {
+          int m0, n0, kbeg, nkb; tile_coords(t, m0, n0, kbeg, nkb);
+          const int nb0 = n0 + (int)rank * 128;
+          // the operands stream from HBM and the clusters that share a panel request it at the same moment, so a plain
+          // load sees DRAM latency: prefetch this cluster's NEXT tile into L2 while the current one is loaded
+          int pm0 = 0, pn0 = 0, pk = 0, pnkb = 0;
+          const bool pf = p.prefetch && t + ncl < total;
+          if (pf) tile_coords(t + ncl, pm0, pn0, pk, pnkb);
+          for (int kb = 0; kb < nkb; ++kb, ++it) {
+            const int s = it % S;
+            mbar_wait_cluster(empty_bar(s), ((it / S) & 1) ^ 1);
+            mbar_expect_tx(full_bar(s), RAW);
+            const int k0 = kbeg + kb * TBK;
+            if (pf && kb < pnkb) {
+              const int q0 = pk + kb * TBK, qn = pn0 + (int)rank * 128;
+              if (!A_MN) tma_prefetch_2d(&tmA, q0, pm0);
+              else
+#pragma unroll
+                for (int g = 0; g < 4; ++g) tma_prefetch_2d(&tmA, pm0 + g * 32, q0);
+              if (!B_MN) tma_prefetch_2d(&tmB, q0, qn);
+              else
+#pragma unroll
+                for (int g = 0; g < 4; ++g) tma_prefetch_2d(&tmB, qn + g * 32, q0);
+            }
+            const uint32_t sa = base + s * STAGE, sb = sa + A_BYTES;
+            if (!A_MN) tma_load_2d(&tmA, sa, full_bar(s), k0, m0);
+            else
+#pragma unroll
+              for (int g = 0; g < 4; ++g) tma_load_2d(&tmA, sa + g * 4096, full_bar(s), m0 + g * 32, k0);
+            if (!B_MN) tma_load_2d(&tmB, sb, full_bar(s), k0, nb0);
+            else
+#pragma unroll
+              for (int g = 0; g < 4; ++g) tma_load_2d(&tmB, sb + g * 4096, full_bar(s), nb0 + g * 32, k0);
+          }
+        }
+      }
+    } else if (warp == 1) {
+      if (lane == 0 && leader) {                                   // ---- MMA issuer: one chunk accumulator per k-block
+        const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((A_MN ? 1u : 0u) << 15) | ((B_MN ? 1u : 0u) << 16) |
+                               ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+        uint32_t it = 0;
+        for (int t = cid; t < total; t += ncl) {
+          int m0, n0, kbeg, nkb; tile_coords(t, m0, n0, kbeg, nkb);
+          for (int kb = 0; kb < nkb; ++kb, ++it) {
+            const int s = it % S;
+            const uint32_t cb = it & 1;
+            mbar_wait_cluster(cempty_bar(cb), ((it >> 1) & 1) ^ 1); // both CTAs have drained this chunk accumulator
+            mbar_wait_cluster(conv_bar(s), (it / S) & 1);          // raw tiles landed and lo tiles written, both CTAs
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t tacc = tmem_base + cb * BN;
+            const uint32_t sa = base + s * STAGE, sb = sa + A_BYTES;
+            uint64_t ad[4], bd[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const uint32_t oa = A_MN ? sa + k * 1024 : sa + k * 32, ob = B_MN ? sb + k * 1024 : sb + k * 32;
+              ad[k] = A_MN ? umma_desc(oa, 4096, 512, 1) : umma_desc(oa, 16, 1024, 2);
+              bd[k] = B_MN ? umma_desc(ob, 4096, 512, 1) : umma_desc(ob, 16, 1024, 2);
+            }
+            constexpr uint64_t LO = (uint64_t)(RAW >> 4);          // the lo tiles sit RAW bytes after the raw ones (address field, 16-byte units)
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {                          // cross terms first, into the still tiny accumulator
+              umma_tf32_2sm(tacc, ad[k], bd[k] + LO, idesc, k != 0 ? 1u : 0u);   // hi * lo
+              umma_tf32_2sm(tacc, ad[k] + LO, bd[k], idesc, 1u);                 // lo * hi
+            }
+#pragma unroll
+            for (int k = 0; k < 4; ++k) umma_tf32_2sm(tacc, ad[k], bd[k], idesc, 1u);   // hi * hi
+            umma_commit_2sm(empty_bar(s));
+            umma_commit_2sm(cfull_bar(cb));
+          }
+        }
+      }
+    } else {                                                       // ---- converters: warps 2-3 of both CTAs
+      uint32_t it = 0;
+      const int ctid = threadIdx.x - 64;
+      for (int t = cid; t < total; t += ncl) {
+        int m0, n0, kbeg, nkb; tile_coords(t, m0, n0, kbeg, nkb);
+        for (int kb = 0; kb < nkb; ++kb, ++it) {
+          const int s = it % S;
+          mbar_wait(full_bar(s), (it / S) & 1);
+          const uint32_t sa = base + s * STAGE;
+          x3_split_stage_t<64>(sa, sa + RAW, RAW, ctid);
+          __syncwarp();
+          if (lane == 0) mbar_arrive_leader(conv_bar(s));
+        }
+      }
+    }
+  } else {                                                         // ---- epilogue: warps 4..11
+    const int ew = warp - 4, q = warp & 3, half = ew >> 2;
+    EpiWarp w{stg_base + (uint32_t)ew * 4096u, add_bar0 + 8u * ew, 0u, lane, lane >> 3, lane & 7,
+              ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0) && (p.ldc % 4 == 0)};
+    const uint32_t tlane = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(half * 128);
+    uint32_t it = 0;
+    for (int t = cid; t < total; t += ncl) {
+      int m0, n0, kbeg, nkb; tile_coords(t, m0, n0, kbeg, nkb);
+      float a0[32], a1[32], a2[32], a3[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) { a0[j] = 0.f; a1[j] = 0.f; a2[j] = 0.f; a3[j] = 0.f; }
+      for (int kb = 0; kb < nkb; ++kb, ++it) {
+        const uint32_t cb = it & 1;
+        mbar_wait(cfull_bar(cb), (it >> 1) & 1);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        {
+          float v[32];
+          tmem_ld32(tlane + cb * BN, v);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) a0[j] += v[j];
+          tmem_ld32(tlane + cb * BN + 32, v);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) a1[j] += v[j];
+          tmem_ld32(tlane + cb * BN + 64, v);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) a2[j] += v[j];
+          tmem_ld32(tlane + cb * BN + 96, v);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) a3[j] += v[j];
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) mbar_arrive_leader(cempty_bar(cb));
+      }
+      const int gj = n0 + half * 128;
+      if (gj < p.N) epi_cols32(p, &tmC, &tmAdd, a0, gj, m0 + q * 32, w);
+      if (gj + 32 < p.N) epi_cols32(p, &tmC, &tmAdd, a1, gj + 32, m0 + q * 32, w);
+      if (gj + 64 < p.N) epi_cols32(p, &tmC, &tmAdd, a2, gj + 64, m0 + q * 32, w);
+      if (gj + 96 < p.N) epi_cols32(p, &tmC, &tmAdd, a3, gj + 96, m0 + q * 32, w);
+    }
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+    __syncwarp();
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  cluster_sync_all();
+  if (warp == 1) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
   }
 }
 
@@ -637,22 +1223,42 @@ bool make_map_bf16(CUtensorMap* m, const void* ptr, int64_t rows, int64_t cols, 
              CU_TENSOR_MAP_SWIZZLE_128B, l2_promo(), CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-template <int BN, bool X3 = false>
-bool launch_tc(dx_stream_t s, const GemmP& g, const float* A_lo = nullptr, const float* B_lo = nullptr) {
-  using Cfg = TcCfg<BN, X3>;
-  CUtensorMap ta, tb, talo, tblo;
-  // K-major: memory [MN rows][reduction cols]; MN-major: memory [reduction rows][MN cols]
-  if (X3) {   // exact hi/lo pairs: plain FP32 maps (no rounding on load)
-    if (!make_map(&ta, g.A, g.M, g.K, g.lda, TBK, TBM, false, true) || !make_map(&talo, A_lo, g.M, g.K, g.lda, TBK, TBM, false, true) ||
-        !make_map(&tb, g.B, g.N, g.K, g.ldb, TBK, BN, false, true) || !make_map(&tblo, B_lo, g.N, g.K, g.ldb, TBK, BN, false, true))
-      return false;
-  } else {
-  if (g.a_kc) { if (!make_map(&ta, g.A, g.M, g.K, g.lda, TBK, TBM, false)) return false; }
-  else        { if (!make_map(&ta, g.A, g.K, g.M, g.lda, 32, TBK, true)) return false; }
-  if (g.b_kc) { if (!make_map(&tb, g.B, g.N, g.K, g.ldb, TBK, BN, false)) return false; }
-  else        { if (!make_map(&tb, g.B, g.K, g.N, g.ldb, 32, TBK, true)) return false; }
-  talo = ta; tblo = tb;
+inline int sm_count() {
+  int dev = 0, n = 0;
+  cudaGetDevice(&dev);
+  static int cache[64] = {0};
+  if (dev >= 0 && dev < 64 && cache[dev]) return cache[dev];
+  cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+  if (dev >= 0 && dev < 64) cache[dev] = n;
+  return n;
+}
+// cudaFuncSetAttribute is per device: remember which devices a kernel family was configured on
+struct AttrOnce {
+  unsigned long long done = 0;
+  template <class F> void operator()(F set) {
+    int dev = 0; cudaGetDevice(&dev);
+    const unsigned long long bit = 1ull << (dev & 63);
+    if (!(done & bit)) { set(); done |= bit; }
   }
+};
+inline bool x3_inplace() { static const bool v = getenv("DX_X3_INPLACE") != nullptr; return v; }
+inline int tc_prefetch() { static const int v = getenv("DX_TC_NO_PREFETCH") ? 0 : 1; return v; }
+inline int x3_dbg() { static const int v = [] { const char* e = getenv("DX_X3_DBG"); return e ? atoi(e) : 0; }(); return v; }
+inline int x3_chunk() {   // k-blocks per chunk accumulator of k_tc_gemm_x3 (DX_X3_CHUNK overrides; see the kernel's header)
+  static const int v = [] { const char* e = getenv("DX_X3_CHUNK"); const int c = e ? atoi(e) : 2; return c < 1 ? 1 : c; }();
+  return v;
+}
+
+template <int BN, bool X3 = false>
+bool launch_tc(dx_stream_t s, const GemmP& g) {
+  using Cfg = TcCfg<BN, X3>;
+  CUtensorMap ta, tb;
+  // K-major: memory [MN rows][reduction cols]; MN-major: memory [reduction rows][MN cols].
+  // X3 reads the raw fp32 words (the converters need the exact value): plain FLOAT32 maps, no rounding on load.
+  if (g.a_kc) { if (!make_map(&ta, g.A, g.M, g.K, g.lda, TBK, TBM, false, X3)) return false; }
+  else        { if (!make_map(&ta, g.A, g.K, g.M, g.lda, 32, TBK, true, X3)) return false; }
+  if (g.b_kc) { if (!make_map(&tb, g.B, g.N, g.K, g.ldb, TBK, BN, false, X3)) return false; }
+  else        { if (!make_map(&tb, g.B, g.K, g.N, g.ldb, 32, TBK, true, X3)) return false; }
   // C through TMA when it is a plain strided matrix (no row scatter) with 16-byte aligned rows
   const bool tma_store = !g.c_idx && ((reinterpret_cast<uintptr_t>(g.C) & 15) == 0) && (g.ldc % 4 == 0) &&
                          !getenv("DX_TC_NO_TMA_STORE");
@@ -664,11 +1270,12 @@ bool launch_tc(dx_stream_t s, const GemmP& g, const float* A_lo = nullptr, const
   if (add_tma) { if (!make_map(&tadd, g.add, g.M, g.N, g.ldadd, 32, 32, false, true)) return false; }
   else tadd = ta;
   const int gm = (g.M + TBM - 1) / TBM, gn = (g.N + BN - 1) / BN;
+  const int num_sms = sm_count();
   int splits = 1;
   if (g.accum == ACC_ATOMIC) {
     // split the batch reduction so that tiles x splits just fits two rounds of the persistent grid
     const int tiles = gm * gn;
-    const int want = (148 * 2) / tiles;                        // floor: never spill into a third round
+    const int want = (num_sms * 2) / tiles;                    // floor: never spill into a third round
     const int maxs = (g.K + TBK * 16 - 1) / (TBK * 16);       // >= 512 reduction rows per split
     splits = want < 1 ? 1 : (want > maxs ? maxs : want);
   }
@@ -695,35 +1302,29 @@ bool launch_tc(dx_stream_t s, const GemmP& g, const float* A_lo = nullptr, const
   if (want_dbg) cudaMemsetAsync(dbg, 0, 256 * sizeof(long long), s);
   static const bool m_fast = getenv("DX_TC_M_FAST") != nullptr;
   TcParams p{g.M, g.N, g.K, g.C, g.ldc, g.c_idx, g.bias, g.add, g.ldadd, g.act, accum, k_chunk, tma_store ? 1 : 0, add_tma ? 1 : 0,
-             m_fast ? 0 : 1, want_dbg ? dbg : nullptr};
-  static int num_sms = 0;
-  if (!num_sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev); }
+             m_fast ? 0 : 1, x3_inplace() ? 1 : 0, x3_chunk(), tc_prefetch(), want_dbg ? dbg : nullptr};
   const int total_tiles = gm * gn * splits;
   dim3 grid(total_tiles < num_sms ? total_tiles : num_sms);
-  static bool attr_set = false;   // per (BN, X3) instantiation; the operand-major variants share the footprint
-  if (!attr_set) {
+  static AttrOnce attr;   // per (BN, X3) instantiation; the operand-major variants share the footprint
+  attr([] {
     cudaFuncSetAttribute(k_tc_gemm<BN, false, false, X3>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM);
-    if (!X3) {
-      cudaFuncSetAttribute(k_tc_gemm<BN, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM);
-      cudaFuncSetAttribute(k_tc_gemm<BN, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM);
-      cudaFuncSetAttribute(k_tc_gemm<BN, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM);
-    }
-    attr_set = true;
-  }
-  auto run = [&](auto kern) { kern<<<grid, 320, Cfg::SMEM, s>>>(ta, tb, tc, tadd, talo, tblo, p); };
-  if (X3) run(k_tc_gemm<BN, false, false, X3>);
-  else if (g.a_kc && g.b_kc) run(k_tc_gemm<BN, false, false>);
-  else if (g.a_kc && !g.b_kc) run(k_tc_gemm<BN, false, true>);
-  else if (!g.a_kc && !g.b_kc) run(k_tc_gemm<BN, true, true>);
-  else run(k_tc_gemm<BN, true, false>);
+    cudaFuncSetAttribute(k_tc_gemm<BN, false, true, X3>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM);
+    cudaFuncSetAttribute(k_tc_gemm<BN, true, true, X3>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM);
+    cudaFuncSetAttribute(k_tc_gemm<BN, true, false, X3>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM);
+  });
+  auto run = [&](auto kern) { kern<<<grid, Cfg::THREADS, Cfg::SMEM, s>>>(ta, tb, tc, tadd, p); };
+  if (g.a_kc && g.b_kc) run(k_tc_gemm<BN, false, false, X3>);
+  else if (g.a_kc && !g.b_kc) run(k_tc_gemm<BN, false, true, X3>);
+  else if (!g.a_kc && !g.b_kc) run(k_tc_gemm<BN, true, true, X3>);
+  else run(k_tc_gemm<BN, true, false, X3>);
   ++g_launches;
   if (want_dbg) {
     long long h[256];
     cudaStreamSynchronize(s);
     cudaMemcpy(h, dbg, sizeof(h), cudaMemcpyDeviceToHost);
     const long long t0 = h[200];
-    fprintf(stderr, "[tc trace] M=%d N=%d K=%d BN=%d splits=%d tiles=%d grid=%d | setup %lld | epilogues:", g.M, g.N, g.K, BN,
-            splits, total_tiles, (int)grid.x, h[201] - t0);
+    fprintf(stderr, "[tc trace] M=%d N=%d K=%d BN=%d x3=%d splits=%d tiles=%d grid=%d | setup %lld | epilogues:", g.M, g.N, g.K, BN,
+            (int)X3, splits, total_tiles, (int)grid.x, h[201] - t0);
     for (int i = 0; i < 8 && h[208 + 2 * i]; ++i) fprintf(stderr, " [%lld..%lld]", h[208 + 2 * i] - t0, h[209 + 2 * i] - t0);
     fprintf(stderr, "\n");
     fprintf(stderr, "  producer(empty ok):");
@@ -736,14 +1337,17 @@ bool launch_tc(dx_stream_t s, const GemmP& g, const float* A_lo = nullptr, const
 }
 
 // 2-CTA launch (BN = 256).  Returns false if not applicable.
+template <bool X3>
 bool launch_tc2(dx_stream_t s, const GemmP& g) {
+  using Cfg = Tc2Cfg<X3>;
   static const bool disabled = getenv("DX_TC_NO_CG2") != nullptr;
   if (disabled) return false;
+  const int num_sms = sm_count();
   const int gm2 = (g.M + 255) / 256, gn = (g.N + 255) / 256;
   int splits = 1;
   if (g.accum == ACC_ATOMIC) {
     const int tiles = gm2 * gn;
-    const int want = 148 / tiles;                               // two rounds of the 74 clusters
+    const int want = num_sms / tiles;                           // two rounds of the 74 clusters
     const int maxs = (g.K + TBK * 16 - 1) / (TBK * 16);
     splits = want < 1 ? 1 : (want > maxs ? maxs : want);
   }
@@ -754,11 +1358,12 @@ bool launch_tc2(dx_stream_t s, const GemmP& g) {
   if (total < 37) return false;                                 // too little work for the pair-tile: 1-CTA kernel
   const bool tma_store = !g.c_idx && ((reinterpret_cast<uintptr_t>(g.C) & 15) == 0) && (g.ldc % 4 == 0);
   if (!tma_store) return false;
+  if (!g.a_kc && g.b_kc) return false;                          // (no product of the path has this form)
   CUtensorMap ta, tb, tc, tadd;
-  if (g.a_kc) { if (!make_map(&ta, g.A, g.M, g.K, g.lda, TBK, TBM, false)) return false; }
-  else        { if (!make_map(&ta, g.A, g.K, g.M, g.lda, 32, TBK, true)) return false; }
-  if (g.b_kc) { if (!make_map(&tb, g.B, g.N, g.K, g.ldb, TBK, 128, false)) return false; }   // half of the B tile per CTA
-  else        { if (!make_map(&tb, g.B, g.K, g.N, g.ldb, 32, TBK, true)) return false; }
+  if (g.a_kc) { if (!make_map(&ta, g.A, g.M, g.K, g.lda, TBK, TBM, false, X3)) return false; }
+  else        { if (!make_map(&ta, g.A, g.K, g.M, g.lda, 32, TBK, true, X3)) return false; }
+  if (g.b_kc) { if (!make_map(&tb, g.B, g.N, g.K, g.ldb, TBK, 128, false, X3)) return false; }   // half of the B tile per CTA
+  else        { if (!make_map(&tb, g.B, g.K, g.N, g.ldb, 32, TBK, true, X3)) return false; }
   if (!make_map(&tc, g.C, g.M, g.N, g.ldc, 32, 32, false, true)) return false;
   const bool add_tma = g.add && ((reinterpret_cast<uintptr_t>(g.add) & 15) == 0) && (g.ldadd % 4 == 0);
   if (g.add && !add_tma) return false;
@@ -770,35 +1375,178 @@ bool launch_tc2(dx_stream_t s, const GemmP& g) {
   if (want_dbg) cudaMemsetAsync(dbg, 0, 256 * sizeof(long long), s);
   static const bool m_fast = getenv("DX_TC_M_FAST") != nullptr;
   TcParams p{g.M, g.N, g.K, g.C, g.ldc, g.c_idx, g.bias, g.add, g.ldadd, g.act, g.accum, k_chunk, 1, add_tma ? 1 : 0,
-             m_fast ? 0 : 1, want_dbg ? dbg : nullptr};
-  static int num_sms = 0;
-  if (!num_sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev); }
+             m_fast ? 0 : 1, x3_inplace() ? 1 : 0, x3_chunk(), tc_prefetch(), want_dbg ? dbg : nullptr};
   const int ncl = total < num_sms / 2 ? total : num_sms / 2;
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaFuncSetAttribute(k_tc_gemm2<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM2);
-    cudaFuncSetAttribute(k_tc_gemm2<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM2);
-    cudaFuncSetAttribute(k_tc_gemm2<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM2);
-    attr_set = true;
-  }
+  static AttrOnce attr;
+  attr([] {
+    cudaFuncSetAttribute(k_tc_gemm2<false, false, false, X3>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM);
+    cudaFuncSetAttribute(k_tc_gemm2<false, true, false, X3>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM);
+    cudaFuncSetAttribute(k_tc_gemm2<true, true, false, X3>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM);
+  });
   dim3 grid(2 * ncl);
-  if (g.a_kc && g.b_kc) k_tc_gemm2<false, false><<<grid, 320, SMEM2, s>>>(ta, tb, tc, tadd, p);
-  else if (g.a_kc && !g.b_kc) k_tc_gemm2<false, true><<<grid, 320, SMEM2, s>>>(ta, tb, tc, tadd, p);
-  else if (!g.a_kc && !g.b_kc) k_tc_gemm2<true, true><<<grid, 320, SMEM2, s>>>(ta, tb, tc, tadd, p);
-  else return false;
+  if (g.a_kc && g.b_kc) k_tc_gemm2<false, false, false, X3><<<grid, Cfg::THREADS, Cfg::SMEM, s>>>(ta, tb, tc, tadd, p);
+  else if (g.a_kc && !g.b_kc) k_tc_gemm2<false, true, false, X3><<<grid, Cfg::THREADS, Cfg::SMEM, s>>>(ta, tb, tc, tadd, p);
+  else k_tc_gemm2<true, true, false, X3><<<grid, Cfg::THREADS, Cfg::SMEM, s>>>(ta, tb, tc, tadd, p);
   ++g_launches;
   if (want_dbg) {
     long long h[256];
     cudaStreamSynchronize(s);
     cudaMemcpy(h, dbg, sizeof(h), cudaMemcpyDeviceToHost);
     const long long t0 = h[200];
-    fprintf(stderr, "[tc2 trace] M=%d N=%d K=%d splits=%d pair-tiles=%d clusters=%d | setup %lld | epilogues:", g.M, g.N, g.K,
-            splits, total, ncl, h[201] - t0);
+    fprintf(stderr, "[tc2 trace] M=%d N=%d K=%d x3=%d splits=%d pair-tiles=%d clusters=%d | setup %lld | epilogues:", g.M, g.N, g.K,
+            (int)X3, splits, total, ncl, h[201] - t0);
     for (int i = 0; i < 8 && h[208 + 2 * i]; ++i) fprintf(stderr, " [%lld..%lld]", h[208 + 2 * i] - t0, h[209 + 2 * i] - t0);
     fprintf(stderr, "\n  mma(full ok):");
     for (int i = 0; i < 20 && h[64 + i]; ++i) fprintf(stderr, " %lld", h[64 + i] - t0);
     fprintf(stderr, "\n");
   }
+  return true;
+}
+
+// Chunked 3xTF32 launch (k_tc_gemm_x3): CTA2 = pair tiles 256 x 128, else 128 x 128.  Returns false if not applicable.
+template <bool CTA2>
+bool launch_x3(dx_stream_t s, const GemmP& g) {
+  using Cfg = X3Cfg<CTA2>;
+  constexpr int TM = CTA2 ? 256 : 128, BN = Cfg::BN;
+  const int num_sms = sm_count();
+  const int ncta = CTA2 ? num_sms / 2 : num_sms;               // concurrent tiles
+  const int gm = (g.M + TM - 1) / TM, gn = (g.N + BN - 1) / BN;
+  const bool tma_store = !g.c_idx && ((reinterpret_cast<uintptr_t>(g.C) & 15) == 0) && (g.ldc % 4 == 0);
+  if (CTA2 && !tma_store) return false;
+  int splits = 1, accum = g.accum;
+  if (g.accum == ACC_ATOMIC) {
+    const int want = (2 * ncta) / (gm * gn);                    // two rounds of the persistent grid
+    const int maxs = (g.K + TBK * 16 - 1) / (TBK * 16);        // >= 512 reduction rows per split
+    splits = want < 1 ? 1 : (want > maxs ? maxs : want);
+  } else if (!CTA2 && tma_store && gm * gn < 48 && g.K >= 512 && !g.bias && (!g.add || g.act == ACT_GATE) &&
+             (g.act == ACT_NONE || g.act == ACT_GATE)) {
+    // few-row products with a long reduction: split it so that more SMs stream the weight matrix (see launch_tc)
+    const int want = 96 / (gm * gn), maxs = g.K / 256;
+    splits = want < 1 ? 1 : (want > maxs ? maxs : want);
+    if (splits > 1) {
+      if (g.accum == ACC_STORE) cudaMemset2DAsync(g.C, (size_t)g.ldc * 4, 0, (size_t)g.N * 4, (size_t)g.M, s);
+      accum = ACC_ADD;
+    }
+  }
+  int k_chunk = (g.K + splits - 1) / splits;
+  k_chunk = (k_chunk + TBK - 1) / TBK * TBK;
+  splits = (g.K + k_chunk - 1) / k_chunk;
+  const int total = gm * gn * splits;
+  if (CTA2 && total < ncta / 2) return false;                   // too little work for pair tiles
+  CUtensorMap ta, tb, tc, tadd;
+  if (g.a_kc) { if (!make_map(&ta, g.A, g.M, g.K, g.lda, TBK, TBM, false, true)) return false; }
+  else        { if (!make_map(&ta, g.A, g.K, g.M, g.lda, 32, TBK, true, true)) return false; }
+  if (g.b_kc) { if (!make_map(&tb, g.B, g.N, g.K, g.ldb, TBK, Cfg::BROWS, false, true)) return false; }
+  else        { if (!make_map(&tb, g.B, g.K, g.N, g.ldb, 32, TBK, true, true)) return false; }
+  if (tma_store) { if (!make_map(&tc, g.C, g.M, g.N, g.ldc, 32, 32, false, true)) return false; }
+  else tc = ta;
+  const bool add_tma = tma_store && g.add && ((reinterpret_cast<uintptr_t>(g.add) & 15) == 0) && (g.ldadd % 4 == 0);
+  if (CTA2 && g.add && !add_tma) return false;
+  if (add_tma) { if (!make_map(&tadd, g.add, g.M, g.N, g.ldadd, 32, 32, false, true)) return false; }
+  else tadd = ta;
+  static const bool m_fast = getenv("DX_TC_M_FAST") != nullptr;
+  static long long* dbg = nullptr;
+  static const bool want_dbg = getenv("DX_TC_DEBUG") != nullptr;
+  if (want_dbg && !dbg) cudaMalloc(&dbg, 256 * sizeof(long long));
+  if (want_dbg) cudaMemsetAsync(dbg, 0, 256 * sizeof(long long), s);
+  TcParams p{g.M, g.N, g.K, g.C, g.ldc, g.c_idx, g.bias, g.add, g.ldadd, g.act, accum, k_chunk, tma_store ? 1 : 0, add_tma ? 1 : 0,
+             m_fast ? 0 : 1, x3_dbg(), x3_chunk(), tc_prefetch(), want_dbg ? dbg : nullptr};
+  static AttrOnce attr;
+  attr([] {
+    cudaFuncSetAttribute(k_tc_gemm_x3<false, false, CTA2>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM);
+    cudaFuncSetAttribute(k_tc_gemm_x3<false, true, CTA2>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM);
+    cudaFuncSetAttribute(k_tc_gemm_x3<true, true, CTA2>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM);
+    cudaFuncSetAttribute(k_tc_gemm_x3<true, false, CTA2>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM);
+  });
+  const int nt = total < ncta ? total : ncta;
+  dim3 grid(CTA2 ? 2 * nt : nt);
+  auto run = [&](auto kern) {
+    if (CTA2) {
+      cudaLaunchConfig_t cfg = {};
+      cfg.gridDim = grid; cfg.blockDim = dim3(Cfg::THREADS); cfg.dynamicSmemBytes = Cfg::SMEM; cfg.stream = s;
+      cudaLaunchAttribute at[1];
+      at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+      cfg.attrs = at; cfg.numAttrs = 1;
+      cudaLaunchKernelEx(&cfg, kern, ta, tb, tc, tadd, p);
+    } else {
+      kern<<<grid, Cfg::THREADS, Cfg::SMEM, s>>>(ta, tb, tc, tadd, p);
+    }
+  };
+  if (g.a_kc && g.b_kc) run(k_tc_gemm_x3<false, false, CTA2>);
+  else if (g.a_kc && !g.b_kc) run(k_tc_gemm_x3<false, true, CTA2>);
+  else if (!g.a_kc && !g.b_kc) run(k_tc_gemm_x3<true, true, CTA2>);
+  else run(k_tc_gemm_x3<true, false, CTA2>);
+  ++g_launches;
+  if (want_dbg) {
+    long long h[256];
+    cudaStreamSynchronize(s);
+    cudaMemcpy(h, dbg, sizeof(h), cudaMemcpyDeviceToHost);
+    const long long t0 = h[250];
+    fprintf(stderr, "[x3 trace] M=%d N=%d K=%d cta2=%d splits=%d tiles=%d\n", g.M, g.N, g.K, (int)CTA2, splits, total);
+    const char* nm[4] = {"tma issue (empty ok)", "conv start (full ok)", "conv done            ", "mma start (conv ok) "};
+    for (int r = 0; r < 4; ++r) {
+      fprintf(stderr, "  %s:", nm[r]);
+      for (int i = 0; i < 36 && h[40 * r + i]; ++i) fprintf(stderr, " %lld", h[40 * r + i] - t0);
+      fprintf(stderr, "\n");
+    }
+    fprintf(stderr, "  chunk full seen by epilogue:");
+    for (int i = 0; i < 18 && h[160 + i]; ++i) fprintf(stderr, " %lld", h[160 + i] - t0);
+    fprintf(stderr, "\n  chunk drained              :");
+    for (int i = 0; i < 18 && h[180 + i]; ++i) fprintf(stderr, " %lld", h[180 + i] - t0);
+    fprintf(stderr, "\n");
+  }
+  return true;
+}
+
+// Wide chunked 3xTF32 launch (k_tc_gemm_x3w, pair tiles 256 x 256).  Returns false if not applicable.
+bool launch_x3w(dx_stream_t s, const GemmP& g) {
+  using Cfg = X3wCfg;
+  static const bool off = getenv("DX_X3_NO_WIDE") != nullptr;
+  if (off) return false;
+  const int ncl = sm_count() / 2;
+  const int gm = (g.M + 255) / 256, gn = (g.N + 255) / 256;
+  const bool tma_store = !g.c_idx && ((reinterpret_cast<uintptr_t>(g.C) & 15) == 0) && (g.ldc % 4 == 0);
+  if (!tma_store || g.N < 192 || (!g.a_kc && g.b_kc)) return false;
+  int splits = 1;
+  if (g.accum == ACC_ATOMIC) {
+    const int want = (2 * ncl) / (gm * gn);
+    const int maxs = (g.K + TBK * 16 - 1) / (TBK * 16);
+    splits = want < 1 ? 1 : (want > maxs ? maxs : want);
+  }
+  int k_chunk = (g.K + splits - 1) / splits;
+  k_chunk = (k_chunk + TBK - 1) / TBK * TBK;
+  splits = (g.K + k_chunk - 1) / k_chunk;
+  const int total = gm * gn * splits;
+  if (total < 37) return false;
+  CUtensorMap ta, tb, tc, tadd;
+  if (g.a_kc) { if (!make_map(&ta, g.A, g.M, g.K, g.lda, TBK, TBM, false, true)) return false; }
+  else        { if (!make_map(&ta, g.A, g.K, g.M, g.lda, 32, TBK, true, true)) return false; }
+  if (g.b_kc) { if (!make_map(&tb, g.B, g.N, g.K, g.ldb, TBK, 128, false, true)) return false; }
+  else        { if (!make_map(&tb, g.B, g.K, g.N, g.ldb, 32, TBK, true, true)) return false; }
+  if (!make_map(&tc, g.C, g.M, g.N, g.ldc, 32, 32, false, true)) return false;
+  const bool add_tma = g.add && ((reinterpret_cast<uintptr_t>(g.add) & 15) == 0) && (g.ldadd % 4 == 0);
+  if (g.add && !add_tma) return false;
+  if (add_tma) { if (!make_map(&tadd, g.add, g.M, g.N, g.ldadd, 32, 32, false, true)) return false; }
+  else tadd = ta;
+  static const bool m_fast = getenv("DX_TC_M_FAST") != nullptr;
+  TcParams p{g.M, g.N, g.K, g.C, g.ldc, g.c_idx, g.bias, g.add, g.ldadd, g.act, g.accum, k_chunk, 1, add_tma ? 1 : 0,
+             m_fast ? 0 : 1, 0, 1, tc_prefetch(), nullptr};
+  static AttrOnce attr;
+  attr([] {
+    cudaFuncSetAttribute(k_tc_gemm_x3w<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM);
+    cudaFuncSetAttribute(k_tc_gemm_x3w<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM);
+    cudaFuncSetAttribute(k_tc_gemm_x3w<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM);
+  });
+  const int nt = total < ncl ? total : ncl;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(2 * nt); cfg.blockDim = dim3(Cfg::THREADS); cfg.dynamicSmemBytes = Cfg::SMEM; cfg.stream = s;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+  cfg.attrs = at; cfg.numAttrs = 1;
+  if (g.a_kc && g.b_kc) cudaLaunchKernelEx(&cfg, k_tc_gemm_x3w<false, false>, ta, tb, tc, tadd, p);
+  else if (g.a_kc && !g.b_kc) cudaLaunchKernelEx(&cfg, k_tc_gemm_x3w<false, true>, ta, tb, tc, tadd, p);
+  else cudaLaunchKernelEx(&cfg, k_tc_gemm_x3w<true, true>, ta, tb, tc, tadd, p);
+  ++g_launches;
   return true;
 }
 
@@ -814,13 +1562,12 @@ bool launch_tc2_bf16(dx_stream_t s, const GemmP& g, const void* A16, const void*
     return false;
   const int gm2 = (g.M + 255) / 256, gn = (g.N + 255) / 256;
   const int k_chunk = (g.K + 63) / 64 * 64;
-  TcParams p{g.M, g.N, g.K, g.C, g.ldc, nullptr, g.bias, nullptr, 0, g.act, ACC_STORE, k_chunk, 1, 0, 1, nullptr};
-  static int num_sms = 0;
-  if (!num_sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev); }
+  TcParams p{g.M, g.N, g.K, g.C, g.ldc, nullptr, g.bias, nullptr, 0, g.act, ACC_STORE, k_chunk, 1, 0, 1, 0, 0, 0, nullptr};
+  const int num_sms = sm_count();
   const int total = gm2 * gn, ncl = total < num_sms / 2 ? total : num_sms / 2;
-  static bool attr_set = false;
-  if (!attr_set) { cudaFuncSetAttribute(k_tc_gemm2<false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM2); attr_set = true; }
-  k_tc_gemm2<false, false, true><<<dim3(2 * ncl), 320, SMEM2, s>>>(ta, tb, tc, ta, p);
+  static AttrOnce attr;
+  attr([] { cudaFuncSetAttribute(k_tc_gemm2<false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Tc2Cfg<false>::SMEM); });
+  k_tc_gemm2<false, false, true><<<dim3(2 * ncl), 320, Tc2Cfg<false>::SMEM, s>>>(ta, tb, tc, ta, p);
   ++g_launches;
   return true;
 }
@@ -830,7 +1577,8 @@ bool launch_tc2_bf16(dx_stream_t s, const GemmP& g, const void* A16, const void*
 bool tc_gemm_bf16(dx_stream_t s, const GemmP& g, const void* A16, const void* B16) { return launch_tc2_bf16(s, g, A16, B16); }
 
 // Returns false when the problem is not eligible (caller falls back to the FP32 SIMT kernel).
-bool tc_gemm(dx_stream_t s, const GemmP& g, int* tile_n) {
+// x3: error-compensated 3xTF32 (FP32-accurate) instead of plain TF32.
+bool tc_gemm(dx_stream_t s, const GemmP& g, int* tile_n, bool x3) {
   if (g.a_idx || g.b_idx) return false;                       // TMA tiles cannot gather rows
   // TMA needs 16-byte aligned bases and row pitches; everything else (ragged M/N/K) is handled by
   // the tensor maps' out-of-bounds zero fill / clipping.
@@ -845,23 +1593,24 @@ bool tc_gemm(dx_stream_t s, const GemmP& g, int* tile_n) {
     if (bn == 128 && ntiles(128) < 48) bn = 64;
   }
   if (tile_n) *tile_n = bn;
-  if (bn == 256 && launch_tc2(s, g)) return true;
+  if (x3) {
+    static const bool v1 = getenv("DX_X3_V1") != nullptr;      // first version: single accumulator, no chunked drain
+    if (v1) {
+      if (bn == 256 && launch_tc2<true>(s, g)) return true;
+      return bn == 256 ? launch_tc<256, true>(s, g) : (bn == 128 ? launch_tc<128, true>(s, g) : launch_tc<64, true>(s, g));
+    }
+    if (bn == 256 && launch_x3w(s, g)) return true;
+    if (launch_x3<true>(s, g)) return true;
+    return launch_x3<false>(s, g);
+  }
+  if (bn == 256 && launch_tc2<false>(s, g)) return true;
   return bn == 256 ? launch_tc<256>(s, g) : (bn == 128 ? launch_tc<128>(s, g) : launch_tc<64>(s, g));
-}
-
-// FP32-accurate forward product on the tensor cores (3xTF32).  A_hi/A_lo and B_hi/B_lo are exact splits
-// of the operands (same shapes / pitches as g.A / g.B, which must point at the hi parts).
-bool tc_gemm_x3(dx_stream_t s, const GemmP& g, const float* A_lo, const float* B_lo) {
-  if (g.a_idx || g.b_idx || !g.a_kc || !g.b_kc || g.accum == ACC_ATOMIC) return false;
-  if (!al16(g.A) || !al16(g.B) || !al16(A_lo) || !al16(B_lo) || (g.lda % 4) || (g.ldb % 4)) return false;
-  return g.N >= 96 ? launch_tc<128, true>(s, g, A_lo, B_lo) : launch_tc<64, true>(s, g, A_lo, B_lo);
 }
 
 }  // namespace dx
 #else
 namespace dx {
-bool tc_gemm(dx_stream_t, const GemmP&, int*) { return false; }
-bool tc_gemm_x3(dx_stream_t, const GemmP&, const float*, const float*) { return false; }
+bool tc_gemm(dx_stream_t, const GemmP&, int*, bool) { return false; }
 bool tc_gemm_bf16(dx_stream_t, const GemmP&, const void*, const void*) { return false; }
 }  // namespace dx
 #endif

@@ -69,9 +69,9 @@ class DXVAE(nn.Module):
         self.max_chunk = 32768      # graphs per kernel pass for encode / decode
         self.verbose = True
         self.last_margins = None
-        # arithmetic of the training products: "fp32" (FFMA, reference-tolerance parity) or "tf32"
-        # (tcgen05 tensor cores, looser stated tolerance).  Encode for inference and greedy decode
-        # always run in fp32 so their outputs match the reference's decisions.
+        # arithmetic of the training products: "fp32" (FFMA), "3xtf32" (tcgen05 tensor cores with
+        # error-compensated hi/lo operands: FP32-accurate, meets the reference tolerance) or "tf32"
+        # (plain tensor-core TF32, looser stated tolerance)
         self.precision = "fp32"
         # inference encode: "fp32" (default, reference-tolerance latents) or "tf32" (tensor cores,
         # latents within the looser TF32 bound of tests/test_gpu_tf32.py); greedy decode is always fp32
@@ -107,10 +107,12 @@ class DXVAE(nn.Module):
             self.device = "cuda"
         return L
 
+    _PREC = {"fp32": _abi.PREC_FP32, "tf32": _abi.PREC_TF32, "3xtf32": _abi.PREC_3XTF32}
+
     def _prec(self):
-        if self.precision not in ("fp32", "tf32"):
-            raise ValueError("precision must be 'fp32' or 'tf32'")
-        return _abi.PREC_TF32 if self.precision == "tf32" else _abi.PREC_FP32
+        if self.precision not in self._PREC:
+            raise ValueError("precision must be 'fp32', '3xtf32' or 'tf32'")
+        return self._PREC[self.precision]
 
     def _workspace(self, op, B, fresh=False):
         L = _lib.lib()
@@ -191,7 +193,7 @@ class DXVAE(nn.Module):
         B = d.B
         d.level = torch.empty(B, 7, dtype=torch.uint8, device="cuda")
         d.level_rows = torch.empty(6 * B, dtype=torch.int32, device="cuda")
-        lp_dev = torch.empty(8, dtype=torch.int32, device="cuda")
+        lp_dev = torch.empty(16, dtype=torch.int32, device="cuda")     # 8 offsets + 8 per-level prefix sizes (ABI: 16 ints)
         ws = self._workspace(_abi.OP_SCHEDULE, B)
         _lib.check(L.dxvae_batch_schedule(B, d.adj.data_ptr(), d.level.data_ptr(), lp_dev.data_ptr(),
                                           d.level_rows.data_ptr(), d.level_ptr.ctypes.data, ws.data_ptr(), ws.numel(),
@@ -218,11 +220,14 @@ class DXVAE(nn.Module):
         gb = DXGraphBatch.from_graphs(G)
         B = len(gb)
         self.hidden = B                                   # model.py:201 sizes the scratch state here
-        if torch.is_grad_enabled() and B <= self.max_chunk:
+        if torch.is_grad_enabled() and B > self.max_chunk and any(p.requires_grad for p in self.parameters()):
+            raise ValueError("encode() with autograd enabled takes at most max_chunk=%d graphs per call (got %d); "
+                             "use torch.no_grad() for inference or raise max_chunk" % (self.max_chunk, B))
+        if torch.is_grad_enabled():
             d = self._prepare(gb, need_cls=True)
             mu, sd = _EncodeFn.apply(self, d, *self._params_tuple())
             q = Normal(mu, sd, validate_args=False)
-            q._dx_batch = d
+            q._dx_batch = (d, G)                          # reused by loss(q, G) when it is handed the same G
             return q
         mu = torch.empty(B, 128, device="cuda"); sd = torch.empty(B, 128, device="cuda")
         for lo in range(0, B, self.max_chunk):
@@ -291,8 +296,10 @@ class DXVAE(nn.Module):
         """model.py:270-367.  `eps` injects the reparameterisation noise; None draws it the way
         q_dist.rsample() would (the reference always samples: App. C.1)."""
         self._ensure_flat()
-        d = getattr(q_dist, "_dx_batch", None)
-        if d is None or d.B != len(G_true):
+        cached = getattr(q_dist, "_dx_batch", None)
+        if cached is not None and cached[1] is G_true:   # the targets must come from G_true itself (model.py:272-280)
+            d = cached[0]
+        else:
             d = self._prepare(G_true, need_cls=True)
         mu, sd = q_dist.loc, q_dist.scale
         if eps is None:
