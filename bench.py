@@ -7,17 +7,21 @@ Workload (BASELINE.json config 5, the data-parallel one, at N GPUs; per-GPU work
   -> NCCL all-reduce of the flat gradient (N>1) -> AdamW.  metric = patches/sec.
 
   value      device-timed, inputs (graph-format tensors) already resident in HBM
-  e2e        same step driven from pinned HOST buffers through the public API: H2D of the
-             batch inside the timed region, D2H of the 5 loss terms
-  roofline   the dominant GEMM kernel class (tcgen05 TF32 by default), per-launch CUDA events
-  --precision tf32 (default): dense products on the tcgen05 tensor cores, looser stated tolerance
-              fp32: FFMA kernels, reference-tolerance parity (also reported in extra)
-  cpu_baseline  the oracle port of the reference (torch CPU, all host cores) on a bounded sample
+  e2e        the same step through the PUBLIC API a user of the reference calls (model.py:383-386):
+                 opt.zero_grad(); loss, *_ = model(G); loss.backward(); opt.step()
+             with G a Python list of host-resident graph objects: the list -> batch conversion, the H2D copy of the
+             batch from pinned memory and the D2H copy of the 5 loss terms are inside the timed region
+             (`e2e.tensor_input` = the same step fed pre-batched pinned tensors, round 1's figure)
+  roofline   the dominant GEMM kernel class, per-launch CUDA events on the launching stream
+  --precision 3xtf32 (default): dense products on the tcgen05 tensor cores with in-kernel hi/lo operand splits and
+                      chunked FP32 accumulation: FP32-accurate, meets the reference tolerances (tests/test_gpu_tf32.py)
+              tf32:   plain TF32 tensor-core products, looser stated tolerance (reported in `extra`)
+              fp32:   FFMA kernels (reported in `extra`)
+  cpu_baseline  the UNMODIFIED reference (baseline/_ref, staged by baseline/stage_ref.py) under the dgl/mido stand-in,
+             on a bounded sample, timed in a CPU-only subprocess; the vectorised oracle port beside it
   extra      the other BASELINE configs, N=1 only: batched encode (cfg3) and greedy decode (cfg4) at micro-batch size and
-             end to end at 1 M patches from host buffers (voices -> latents; z -> .syx bytes), decode also at Dexed edge
-             density, the B=128 training step (cfg2) and the FP32 FFMA training path
-`--impl reference` times that CPU port alone (the reference itself is Python+DGL and cannot
-travel to the GPU box).
+             end to end at 1 M patches from host buffers, the B=128 training step (cfg2), the TF32 / FFMA training paths
+`--impl reference` times the reference's own CPU train step (model.py:383-386) on the host cores.
 """
 import argparse
 import ctypes
@@ -131,21 +135,94 @@ def cpu_train_sample(n_patches, steps, warmup, seed=0):
     return n_patches / sec, sec, torch.get_num_threads()
 
 
+REF_DIR = os.path.join(ROOT, "baseline", "_ref")
+
+
+def ref_staged():
+    return os.path.isfile(os.path.join(REF_DIR, "model.py")) and os.path.isfile(os.path.join(REF_DIR, "dxdata.py"))
+
+
+def ref_train_sample(n_patches, steps, warmup, seed=0):
+    """The UNMODIFIED reference (baseline/_ref/{model,dxdata}.py, staged byte for byte from the reference tree) under the
+    dgl/mido stand-in of oracle/shim: its own graph builder (`DXDataset._make_graph`, dxdata.py:174-312) on synthetic
+    voices, its own `DXVAE.forward` + autograd backward + torch.optim.AdamW step (model.py:383-386), on the host cores.
+    Must run in a process that has not initialised CUDA (model.py:13 would move the model to the GPU, where the
+    reference's CPU-allocating quantisers and this benchmark's intent part ways).
+    Returns (patches_per_s, seconds_per_step, threads)."""
+    import torch
+    os.environ["DXVAE_REFERENCE_ROOT"] = REF_DIR
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import ref_loader
+    from dxvae_b200.synth import random_voices
+    assert not torch.cuda.is_available(), "the reference arm runs CPU-only (CUDA_VISIBLE_DEVICES must be empty)"
+    torch.set_num_threads(os.cpu_count())
+    model_mod, dxdata = ref_loader.load_reference()
+    ds = dxdata.DXDataset(raw_dir=os.path.join(REF_DIR, "DX_data"))          # loads the cached DXDataset.bin (dxdata.py:334)
+    v = random_voices(n_patches, seed)
+    G = [ds._make_graph(torch.tensor(v[i].astype("int64"))) for i in range(n_patches)]
+    torch.manual_seed(0)
+    m = model_mod.DXVAE()
+    opt = torch.optim.AdamW(m.parameters(), lr=1e-3)                           # model.py:375
+    times = []
+    for it in range(warmup + steps):
+        t0 = time.perf_counter()
+        opt.zero_grad()                                                        # model.py:383
+        loss = m.forward(G)[0]                                                 # model.py:384
+        loss.backward()                                                        # model.py:385
+        opt.step()                                                             # model.py:386
+        if it >= warmup:
+            times.append(time.perf_counter() - t0)
+    sec = sum(times) / len(times)
+    return n_patches / sec, sec, torch.get_num_threads()
+
+
+def reference_line(args):
+    """The JSON line of the CPU arm (the process must be CPU-only, see main)."""
+    port_pps, port_sec, thr = cpu_train_sample(args.cpu_patches, max(1, min(args.steps, 3)), 1)
+    port = {"value": port_pps, "unit": UNIT, "cores": thr, "kind": "port",
+            "sample": "%d synthetic patches per step, oracle port (oracle/dxvae_oracle.py: the reference's per-graph Python / "
+                      "DGL loops vectorised over the batch) on torch CPU" % args.cpu_patches}
+    if ref_staged():
+        n = args.ref_patches
+        pps, sec, thr = ref_train_sample(n, args.steps, args.warmup)
+        kind = "reference"
+        sample = ("%d synthetic patches per step through the UNMODIFIED reference (baseline/_ref/model.py + dxdata.py under the "
+                  "dgl/mido stand-in of oracle/shim; batch %d is the reference's own regime, BASELINE config 2; its cost is "
+                  "linear in the batch): zero_grad + forward + backward + AdamW.step, model.py:383-386" % (n, n))
+    else:
+        n, pps, sec, kind, sample = args.cpu_patches, port_pps, port_sec, "port", port["sample"] + " (baseline/_ref is not staged)"
+    return {"impl": "reference", "metric": METRIC, "value": pps, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "cfg5: ELBO train step on synthetic patch graphs (bounded CPU sample of the GPU arm's workload)",
+                       "micro_batch": n},
+            "cpu_baseline": {"value": pps, "unit": UNIT, "cores": thr, "kind": kind, "sample": sample},
+            "extra": {"oracle_port": port},
+            "e2e": {"value": pps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    n = args.cpu_patches
-    pps, sec, thr = cpu_train_sample(n, args.steps, args.warmup)
-    sample = "%d synthetic patches per step (oracle port of model.py:374-386 on torch CPU; the reference's Python/DGL " \
-             "loops are vectorised in the port, so this is an upper bound on the reference's own speed)" % n
-    line = {"impl": "reference", "metric": METRIC, "value": pps, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "cfg5: ELBO train step on synthetic patch graphs (CPU sample)", "micro_batch": n},
-            "cpu_baseline": {"value": pps, "unit": UNIT, "cores": thr, "kind": "port", "sample": sample},
-            "e2e": {"value": pps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), flush=True)
+    print(json.dumps(reference_line(args)), flush=True)
+
+
+def cpu_baseline_subprocess(args):
+    """cpu_baseline of the GPU arm: the CPU arm in a CPU-only child process (this one has initialised CUDA)."""
+    env = dict(os.environ, CUDA_VISIBLE_DEVICES="")
+    for k in ("RANK", "LOCAL_RANK", "WORLD_SIZE"):
+        env.pop(k, None)
+    cmd = [sys.executable, os.path.abspath(__file__), "--impl", "reference", "--steps", "2", "--warmup", "1",
+           "--cpu-patches", str(args.cpu_patches), "--ref-patches", str(args.ref_patches)]
+    out = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=900)
+    for ln in reversed(out.stdout.splitlines()):
+        if ln.startswith("{"):
+            j = json.loads(ln)
+            cb = j["cpu_baseline"]
+            cb["oracle_port"] = j["extra"]["oracle_port"]
+            return cb
+    raise RuntimeError("CPU arm failed: " + out.stderr[-400:])
 
 
 # ------------------------------------------------------------------------------------------ GPU arm
@@ -156,17 +233,17 @@ def run_ours(args):
     from dxvae_b200 import DXVAE, _lib
     from dxvae_b200.dxdata import DXGraphBatch, voices_to_batch
     from dxvae_b200.synth import random_voices
-    from dxvae_b200.train import Trainer
+    from dxvae_b200.train import FusedAdamW, Trainer
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     if world > 1:
-        if "DX_NCCL_DEBUG" in os.environ:                 # default: NCCL silent, stdout is the one JSON line
-            os.environ["NCCL_DEBUG"] = os.environ["DX_NCCL_DEBUG"]
-        else:
-            os.environ.pop("NCCL_DEBUG", None)
+        # NCCL's own log (NCCL_DEBUG=INFO shows the ring / NVLS set-up and the rank count) goes to stderr so that stdout stays
+        # the one JSON line
+        if os.environ.get("NCCL_DEBUG") and not os.environ.get("NCCL_DEBUG_FILE"):
+            os.environ["NCCL_DEBUG_FILE"] = "/dev/stderr"
         import datetime
         dist.init_process_group("nccl", device_id=torch.device("cuda", local),
                                 timeout=datetime.timedelta(seconds=120))
@@ -183,27 +260,41 @@ def run_ours(args):
     tr = Trainer(model, lr=1e-3, w=(2.0, 5.0, 0.01))
     voices = random_voices(NPOOL * M, seed=1000 + rank)
     pool = voices_to_batch(voices)                      # graph-format tensors resident in HBM
-    host = pool.cpu()
-    hX = host.X.pin_memory(); hP = host.params.pin_memory(); hA = host.adj.pin_memory()
+    host = pool.cpu().pin_memory()                      # the same graphs as host-resident data (pinned)
+    hX, hP, hA = host.X, host.params, host.adj
 
     def device_step(i):
         lo = (i % NPOOL) * M
         sub = DXGraphBatch(pool.X[lo:lo + M], pool.params[lo:lo + M], pool.adj[lo:lo + M])
         d = model._prepare(sub)                          # batcher: pack + device level schedule
-        eps = torch.empty(M, 128, device="cuda").normal_()
+        eps = tr.draw_eps(rank * M, (rank + 1) * M, M * world)
         loss5 = tr.grad_step(d, eps, M * world)          # fused fwd+bwd (+ NCCL all-reduce)
         tr.apply()                                       # AdamW
         return loss5
 
-    def host_step(i):
+    def tensor_step(i):                                  # pre-batched pinned host tensors (round 1's e2e)
         lo = (i % NPOOL) * M
         sub = DXGraphBatch(hX[lo:lo + M].to("cuda", non_blocking=True), hP[lo:lo + M].to("cuda", non_blocking=True),
                            hA[lo:lo + M].to("cuda", non_blocking=True))
         d = model._prepare(sub)
-        eps = torch.empty(M, 128, device="cuda").normal_()
+        eps = tr.draw_eps(rank * M, (rank + 1) * M, M * world)
         loss5 = tr.grad_step(d, eps, M * world)
         tr.apply()
         return loss5.cpu()                               # D2H of the step's result
+
+    # ---- the public API: lists of host graph objects through DXVAE.forward / backward / optimiser step
+    glists = [list(host[k * M:(k + 1) * M]) for k in range(NPOOL)]       # the user's data: Python lists of graph objects
+    opt = FusedAdamW(model, lr=1e-3)
+    loss_host = torch.empty(max(K, W, 1), 5).pin_memory()
+
+    def api_step(i):
+        G = glists[i % NPOOL]
+        opt.zero_grad()
+        loss = model(G)[0]                               # list -> batch (host), H2D from pinned memory, batcher, fused fwd+bwd
+        loss.backward()                                  # hands the native gradients to .grad (views of one blob)
+        opt.step()                                       # all-reduce (N>1) + fused AdamW
+        loss_host[i % loss_host.shape[0]].copy_(model.last_loss5, non_blocking=True)   # D2H of the 5 loss terms
+        return model.last_loss5
 
     def timed(fn, steps):
         if world > 1:
@@ -229,11 +320,16 @@ def run_ours(args):
         ms, launches, last = timed(device_step, K)
     clocks = cs.summary()
     value = M * world * K / (ms * 1e-3)
+    last = last.clone()
 
     for i in range(max(1, W // 2)):
-        host_step(i)
-    ms_e2e, _, _ = timed(host_step, K)
+        api_step(i)
+    ms_e2e, _, _ = timed(api_step, K)
     e2e = M * world * K / (ms_e2e * 1e-3)
+    for i in range(max(1, W // 2)):
+        tensor_step(i)
+    ms_t, _, _ = timed(tensor_step, K)
+    e2e_tensor = M * world * K / (ms_t * 1e-3)
     h2d = M * (7 * 27 * 4 + 7 * 21 * 4 + 8)
 
     # ---- roofline of the dominant kernel family: per-launch events on the launching stream
@@ -246,23 +342,32 @@ def run_ours(args):
         device_step(i)
     msv = (ctypes.c_double * 3)(); flv = (ctypes.c_double * 3)(); nv = (ctypes.c_longlong * 3)()
     L.dxvae_prof_end(msv, flv, nv)
-    names = ["dx::k_gemm<128,128,8,8> (fp32 FFMA GEMM family)", "dx::k_gemm<64,64,4,4> (fp32 FFMA, small tiles)",
-             "dx::k_tc_gemm (tcgen05 kind::tf32, TMA-fed, TMEM accumulators)"]
+    tc_name = {"3xtf32": "dx::k_tc_gemm_x3w / k_tc_gemm_x3 (tcgen05 kind::tf32 x3: in-kernel hi/lo operand split, chunked FP32 "
+                         "accumulation; TMA-fed, TMEM accumulators)",
+               "tf32": "dx::k_tc_gemm2 / k_tc_gemm (tcgen05 kind::tf32, TMA-fed, TMEM accumulators)"}.get(args.precision, "tcgen05 GEMM")
+    names = ["dx::k_gemm<128,128,8,8> (fp32 FFMA GEMM family)", "dx::k_gemm<64,64,4,4> (fp32 FFMA, small tiles)", tc_name]
     dom = max(range(3), key=lambda c: msv[c])
     if msv[dom] > 0:
         ach = flv[dom] / (msv[dom] * 1e-3) / 1e12
         ffma_peak = 148 * 128 * 2 * (clocks["sm_mhz"] or 1965.0) * 1e6 / 1e12
-        traffic = None
-        try:    # DRAM bytes per launch of this kernel family from the committed ncu --set full capture
-            tj = json.load(open(os.path.join(ROOT, "profiles", "tc_gemm_traffic.json")))
-            if dom == 2:
-                traffic = tj["dram_bytes_per_launch"]
+        traffic, tnote = None, None
+        try:    # DRAM bytes of a designated large launch of this kernel family against its algorithmic bytes, from the
+                # committed ncu --set full capture of this round (tools/traffic_from_ncu.py writes the json)
+            tj = json.load(open(os.path.join(ROOT, "profiles", "r02_tc_gemm_traffic.json")))
+            if dom == 2 and args.precision in tj:
+                traffic = tj[args.precision]["dram_bytes_per_launch"]
+                tnote = tj[args.precision]
         except Exception:
             pass
+        # executed MMA flops per algorithmic flop: 3 for the error-compensated mode
+        mma_x = 3.0 if (dom == 2 and args.precision == "3xtf32") else 1.0
         roof = {"bound": "tensor", "kernel": names[dom], "achieved": ach, "peak": pk["tensor"], "unit": "TFLOP/s",
-                "frac": ach / pk["tensor"], "traffic": traffic,
-                "traffic_source": "mean dram__bytes_read+write of the launches in the committed ncu --set full capture "
-                                  "(profiles/r01b_tc_gemm_ncu.txt); `achieved` averages every launch of the timed steps",
+                "frac": ach / pk["tensor"], "traffic": traffic, "traffic_detail": tnote,
+                "note": "achieved = algorithmic 2MNK of every launch of the class in the timed steps / their CUDA-event time; "
+                        "peak = measured bf16 dense sustained.  kind::tf32 runs at 1/2 of the bf16 rate and the 3xTF32 mode issues "
+                        "3 MMAs per algorithmic product, so the ceiling of `frac` is 0.5 for tf32 and 0.167 for 3xtf32; "
+                        "`tensor_pipe_frac` = executed MMA flops / the tf32 pipe rate",
+                "tensor_pipe_frac": ach * mma_x / (pk["tensor"] * 0.5),
                 "peak_source": pk["source"] + ", bf16 sustained",
                 "launches_per_step": nv[dom] / K, "avg_launch_ms": msv[dom] / max(1, nv[dom]),
                 "share_of_step": msv[dom] / K / (ms / K), "fp32_ffma_peak_tflops": ffma_peak,
@@ -272,36 +377,46 @@ def run_ours(args):
     if world > 1:
         dist.barrier()
 
+    def wall(fn, n_units, reps=1):
+        fn(); torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            fn()
+        torch.cuda.synchronize()
+        return n_units * reps / (time.perf_counter() - t0)
+
+    def infer_roof(pps, flop, prec):
+        # encode / decode products run on the pipe their precision names; algorithmic flops per patch from SURVEY 8(d)
+        ach = pps * flop / 1e12
+        if prec == "fp32":
+            peak, unit_note = 148 * 128 * 2 * (clocks["sm_mhz"] or 1965.0) * 1e6 / 1e12, "FP32 FFMA pipe at the sampled SM clock"
+        else:
+            peak, unit_note = pk["tensor"], pk["source"] + ", bf16 sustained (3xtf32 ceiling 0.167, tf32 0.5)"
+        return {"bound": "tensor" if prec != "fp32" else "fp32-ffma", "achieved": ach, "peak": peak, "unit": "TFLOP/s",
+                "frac": ach / peak, "precision": prec, "peak_source": unit_note, "patches_per_s": pps,
+                "algorithmic_mflop_per_patch": flop / 1e6}
+
+    roof_enc = roof_dec = None
     # ---- the other configs, briefly (N=1 only): cfg3 encode, cfg4 decode, cfg2 B=128 train
     if rank == 0 and world == 1 and not args.no_extra:
         with torch.no_grad():
             ne = min(NPOOL * M, 32768)
             gb = DXGraphBatch(pool.X[:ne], pool.params[:ne], pool.adj[:ne])
-            model.encode(gb); torch.cuda.synchronize()
-            t0 = time.perf_counter(); model.encode(gb); torch.cuda.synchronize()
-            extra["encode_patches_per_s"] = ne / (time.perf_counter() - t0)
-            model.encode_precision = "tf32"
-            model.encode(gb); torch.cuda.synchronize()
-            t0 = time.perf_counter(); model.encode(gb); torch.cuda.synchronize()
-            extra["encode_tf32_patches_per_s"] = ne / (time.perf_counter() - t0)
-            model.encode_precision = "3xtf32"
-            model.encode(gb); torch.cuda.synchronize()
-            t0 = time.perf_counter(); model.encode(gb); torch.cuda.synchronize()
-            extra["encode_3xtf32_patches_per_s"] = ne / (time.perf_counter() - t0)
-            model.encode_precision = "fp32"
+            for prec in ("fp32", "tf32", "3xtf32"):
+                model.encode_precision = prec
+                extra["encode_%s_patches_per_s" % prec] = wall(lambda: model.encode(gb), ne, 2)
+            model.encode_precision = DXVAE().encode_precision
+            roof_enc = infer_roof(extra["encode_%s_patches_per_s" % model.encode_precision], F_ENC, model.encode_precision)
             z = torch.randn(16384, 128, device="cuda")
-            gdec = model.decode(z); torch.cuda.synchronize()
-            t0 = time.perf_counter(); model.decode(z); torch.cuda.synchronize()
-            extra["decode_patches_per_s"] = 16384 / (time.perf_counter() - t0)
+            model.decode_precision = "fp32"
+            gdec = model.decode(z)
+            extra["decode_fp32_patches_per_s"] = wall(lambda: model.decode(z), 16384)
             # greedy decode re-propagates only the graphs that gain an edge at a step: its speed depends on how many
             # edges the (here randomly initialised) model decides, so report that next to the number
             am = gdec.adj.cpu().numpy().view(np.uint64)
             extra["decode_mean_edges_per_graph"] = float(np.mean([bin(int(a)).count("1") for a in am[:4096]]))
             model.decode_precision = "3xtf32"
-            model.decode(z); torch.cuda.synchronize()
-            t0 = time.perf_counter(); model.decode(z); torch.cuda.synchronize()
-            extra["decode_3xtf32_patches_per_s"] = 16384 / (time.perf_counter() - t0)
-            model.decode_precision = "fp32"
+            extra["decode_3xtf32_patches_per_s"] = wall(lambda: model.decode(z), 16384)
             # the same decode with the edge-head biases shifted until the model decides as many edges as a Dexed patch
             # has (DX_ALGO: 7.3 on average); there is no trained checkpoint in the reference tree to take them from
             named = dict(model.named_parameters())
@@ -314,16 +429,14 @@ def run_ours(args):
                 am = model.decode(z[:2048]).adj.cpu().numpy().view(np.uint64)
                 me = float(np.mean([bin(int(a)).count("1") for a in am]))
                 lo_b, hi_b = (lo_b, mid) if me > 7.3 else (mid, hi_b)
-            model.decode(z); torch.cuda.synchronize()
-            t0 = time.perf_counter(); gd2 = model.decode(z); torch.cuda.synchronize()
-            extra["decode_dexed_density_patches_per_s"] = 16384 / (time.perf_counter() - t0)
-            am = gd2.adj.cpu().numpy().view(np.uint64)
+            for prec in ("fp32", "3xtf32"):
+                model.decode_precision = prec
+                extra["decode_dexed_density_%s_patches_per_s" % prec] = wall(lambda: model.decode(z), 16384)
+            am = model.decode(z).adj.cpu().numpy().view(np.uint64)
             extra["decode_dexed_density_mean_edges_per_graph"] = float(np.mean([bin(int(a)).count("1") for a in am[:4096]]))
-            model.decode_precision = "3xtf32"
-            model.decode(z); torch.cuda.synchronize()
-            t0 = time.perf_counter(); model.decode(z); torch.cuda.synchronize()
-            extra["decode_dexed_density_3xtf32_patches_per_s"] = 16384 / (time.perf_counter() - t0)
-            model.decode_precision = "fp32"
+            model.decode_precision = DXVAE().decode_precision
+            roof_dec = infer_roof(extra["decode_dexed_density_%s_patches_per_s" % model.decode_precision], F_DEC, model.decode_precision)
+            roof_dec["note"] = "greedy decode at Dexed edge density (7.3 decided edges per graph); F_dec counts the reference's 34 propagates"
             eb.data.copy_(eb0); sb.data.copy_(sb0)
         # cfg3 / cfg4 at their full size (1 M patches), end to end from HOST buffers: packed voices (128 B/patch) ->
         # on-device _make_graph -> encode -> latents on the host;  z on the host -> greedy decode -> .syx bytes on the host
@@ -341,14 +454,14 @@ def run_ours(args):
                     mu_h.copy_(q.loc, non_blocking=True); sd_h.copy_(q.scale, non_blocking=True)
                     torch.cuda.synchronize()
                     extra["cfg3_encode_%d_e2e_%s_patches_per_s" % (nfull, prec)] = nfull / (time.perf_counter() - t0)
-                model.encode_precision = "fp32"
+                model.encode_precision = DXVAE().encode_precision
                 for prec in ("fp32", "3xtf32"):
                     model.decode_precision = prec
                     torch.cuda.synchronize(); t0 = time.perf_counter()
                     syx = graph_to_syx_bytes(model.decode(hz))
                     extra["cfg4_decode_%d_to_syx_e2e_%s_patches_per_s" % (nfull, prec)] = nfull / (time.perf_counter() - t0)
                     assert len(syx) == 8 + 128 * nfull
-                model.decode_precision = "fp32"
+                model.decode_precision = DXVAE().decode_precision
             del hv, hz, q, mu_h, sd_h, syx
         idx = list(range(128))
         for _ in range(3):
@@ -358,25 +471,27 @@ def run_ours(args):
             tr.step(pool, idx)
         torch.cuda.synchronize()
         extra["train_b128_patches_per_s"] = 1280 / (time.perf_counter() - t0)
-        if args.precision != "fp32":        # the FP32 FFMA path (reference-tolerance parity) on the same workload
-            model.precision = "fp32"
+        for prec in ("tf32", "fp32"):        # the other arithmetics on the same workload (same micro-batch)
+            if prec == args.precision:
+                continue
+            model.precision = prec
             device_step(0); torch.cuda.synchronize(); t0 = time.perf_counter()
             for i in range(2):
                 device_step(i)
             torch.cuda.synchronize()
-            extra["fp32_path_patches_per_s"] = 2 * M / (time.perf_counter() - t0)
-            model.precision = args.precision
+            extra["%s_path_patches_per_s" % prec] = 2 * M / (time.perf_counter() - t0)
+        model.precision = args.precision
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
-        pps, sec, thr = cpu_train_sample(args.cpu_patches, 3, 1)
-        cpu = {"value": pps, "unit": UNIT, "cores": thr, "kind": "port",
-               "sample": "%d synthetic patches x 3 train steps (+1 warm-up), oracle port on torch CPU" % args.cpu_patches}
+        cpu = cpu_baseline_subprocess(args)
 
     if rank == 0:
+        dtype = {"fp32": "f32", "3xtf32": "f32 (3xTF32: fp32 operands split hi/lo inside the tensor-core kernels, fp32 accumulate)",
+                 "tf32": "tf32 (fp32 accumulate)"}[args.precision]
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
                 "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-                "dtype": "f32" if args.precision == "fp32" else "tf32 (fp32 accumulate)", "data": "synthetic",
+                "dtype": dtype, "data": "synthetic",
                 "config": {"workload": "cfg5 (the config the metric's 1/2/4/8-GPU patches/sec is quoted on), one GPU's share: "
                                        "data-parallel ELBO train step on synthetic 6-operator patch graphs; cfg2/3/4 "
                                        "figures are in `extra`",
@@ -387,8 +502,13 @@ def run_ours(args):
                            (NPOOL * M, L.dxvae_workspace_bytes(2, M) / 1e9)},
                 "clocks": clocks, "gpu_launches": int(launches),
                 "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 20,
-                        "ms_per_step": ms_e2e / K},
-                "roofline": roof, "cpu_baseline": cpu, "loss": float(last[0]), "extra": extra}
+                        "ms_per_step": ms_e2e / K,
+                        "api": "opt.zero_grad(); loss = model(list_of_graphs)[0]; loss.backward(); opt.step()  "
+                               "(DXVAE.forward on a Python list of host graph objects, FusedAdamW)",
+                        "tensor_input": {"value": e2e_tensor, "ms_per_step": ms_t / K,
+                                         "note": "same step fed pre-batched pinned tensors (Trainer.grad_step)"}},
+                "roofline": roof, "roofline_encode": roof_enc, "roofline_decode": roof_dec,
+                "cpu_baseline": cpu, "loss": float(last[0]), "extra": extra}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -401,13 +521,15 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--micro-batch", type=int, default=32768)
-    ap.add_argument("--cpu-patches", type=int, default=2048)
+    ap.add_argument("--cpu-patches", type=int, default=2048, help="patches per step of the oracle-port CPU sample")
+    ap.add_argument("--ref-patches", type=int, default=128, help="patches per step of the unmodified-reference CPU sample")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-extra", action="store_true")
     ap.add_argument("--full-patches", type=int, default=1 << 20, help="size of the cfg3/cfg4 end-to-end extras (0 skips them)")
-    ap.add_argument("--precision", default="tf32", choices=["fp32", "tf32"])
+    ap.add_argument("--precision", default="3xtf32", choices=["fp32", "3xtf32", "tf32"])
     args = ap.parse_args()
     if args.impl == "reference":
+        os.environ["CUDA_VISIBLE_DEVICES"] = ""       # the reference arm is the reference's CPU path (BASELINE config 1)
         run_reference(args)
     else:
         run_ours(args)

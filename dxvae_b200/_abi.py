@@ -34,7 +34,7 @@ SIGNATURES = {
     "dxvae_encode_fwd": (C.c_int, [P, I64, P, P, I32, P, P, P, P, P, P, SZ, C.c_int, C.c_int, P]),
     "dxvae_reparameterize": (C.c_int, [I64, P, P, P, P, P]),
     "dxvae_decode_greedy": (C.c_int, [P, I64, P, P, P, P, P, P, SZ, C.c_int, P]),
-    "dxvae_elbo_step": (C.c_int, [P, I64, P, P, P, I32, P, P, P, P, F, F, F, F, P, P, P, P, P, SZ, C.c_int, P, P, P]),
+    "dxvae_elbo_step": (C.c_int, [P, I64, P, P, P, I32, P, P, P, P, F, F, F, F, P, P, P, P, P, SZ, C.c_int, P, P, P, P]),
     "dxvae_loss_step": (C.c_int, [P, I64, P, P, P, P, P, P, F, F, F, F, P, P, P, P, P, SZ, C.c_int, P, P, P]),
     "dxvae_encode_bwd": (C.c_int, [P, I64, P, P, I32, P, P, P, P, P, P, P, P, SZ, C.c_int, P]),
     "dxvae_adamw_step": (C.c_int, [I64, P, P, P, P, F, F, F, F, F, I64, F, P]),

@@ -23,7 +23,7 @@ def lib():
                 "dxvae_b200: CUDA extension %s is not built (run `python -m dxvae_b200.build`); "
                 "there is no CPU fallback" % _PATH)
         _lib = _abi.bind(ctypes.CDLL(_PATH))
-        if _lib.dxvae_abi_version() != 3:
+        if _lib.dxvae_abi_version() != 4:
             raise RuntimeError("dxvae_b200: ABI version mismatch")
     return _lib
 

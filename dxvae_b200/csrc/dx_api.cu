@@ -43,7 +43,7 @@ size_t workspace_bytes(int op, int64_t B) {
 
 // model.py:369-372 forward (= encode + loss) and model.py:385 backward, one call.
 int elbo_step(dx_stream_t st, const float* weights, const Batch& bt, const float* eps, LossW lw, float* loss5,
-              float* mu_out, float* std_out, float* grads, void* ws, size_t ws_bytes, int precision) {
+              float* mu_out, float* std_out, float* grads, void* ws, size_t ws_bytes, int precision, void* dec_done_event) {
   const int B = (int)bt.B;
   PrecisionScope prec(precision);
   Arena ar(ws, ws_bytes);
@@ -63,6 +63,11 @@ int elbo_step(dx_stream_t st, const float* weights, const Batch& bt, const float
   if (grads) {
     Weights G(grads);
     decode_bwd_impl(st, W, G, B, t.d.z, t.d, bt, lw);
+#ifndef DX_EMU
+    // the decoder-only tensors (combin_decode .. h_to_edge) receive no further gradient: a data-parallel caller may
+    // start reducing that range while the encoder backward runs
+    if (dec_done_event) cudaEventRecord((cudaEvent_t)dec_done_event, st);
+#endif
     latent_bwd(st, B, t.mu, t.sd, eps, t.d.dz, lw, t.dmu, t.dsd);
     encode_bwd_impl(st, W, G, bt, t.e, t.dmu, t.dsd, t.sd);
   }
@@ -115,7 +120,7 @@ int decode_greedy(dx_stream_t st, const float* weights, int64_t B64, const float
   DX_CHECK(!ar.overflow, "decode_greedy: workspace too small (%zu < %zu bytes)", ws_bytes, ar.off);
   Weights W(weights);
   zero_async(st, adj, sizeof(uint64_t) * (size_t)B);
-  if (margins) foreach (st, B, [=] DX_HD(int64_t i) { margins[i] = 3.0e38f; });
+  if (margins) foreach (st, (int64_t)2 * B, [=] DX_HD(int64_t i) { margins[i] = 3.0e38f; });
   DecIO io{false, nullptr, LossW{0, 0, 0, 0}, adj, margins};
   decode_fwd_impl(st, W, B, z, w, io);
   unpack_graphs(st, B, w.Xd, w.Pn, Xg, Pg);
@@ -212,7 +217,7 @@ int dxvae_elbo_step(const float* weights, int64_t B, const float* Xn, const int3
                     const int32_t* level_rare_host, const float* eps,
                     float w_env, float w_frq, float w_kld, float inv_batch, float* loss5, float* mu_out,
                     float* std_out, float* grads, void* workspace, size_t workspace_bytes, int precision,
-                    const int32_t* step_ptr_host, const int32_t* step_rows, void* stream) {
+                    const int32_t* step_ptr_host, const int32_t* step_rows, void* decoder_done_event, void* stream) {
   DX_BATCH_OK(B);
   DX_CHECK(n_levels >= 1 && n_levels <= 6, "elbo_step: n_levels=%d", n_levels);
   DX_CHECK((step_ptr_host == nullptr) == (step_rows == nullptr), "elbo_step: step_ptr_host and step_rows go together");
@@ -222,7 +227,7 @@ int dxvae_elbo_step(const float* weights, int64_t B, const float* Xn, const int3
   bt.step_ptr = step_ptr_host; bt.step_rows = step_rows;
   LossW lw{w_env, w_frq, w_kld, inv_batch};
   return elbo_step(DX_ST(stream), weights, bt, eps, lw, loss5, mu_out, std_out, grads, workspace, workspace_bytes,
-                   precision);
+                   precision, decoder_done_event);
 }
 int dxvae_loss_step(const float* weights, int64_t B, const float* Xn, const int32_t* cls, const uint64_t* adj,
                     const float* mu, const float* std_, const float* eps, float w_env, float w_frq, float w_kld,

@@ -221,63 +221,83 @@ static void upload_tables() {
 static void upload_tables() {}
 #endif
 
-DX_HD DX_INLINE void q_lin(float x, float scale, float* xo, float* po) {   // model.py:87-91
-  float p = rintf(x * scale);
+// Every quantiser also reports its decision MARGIN in units of the logit x: how far x is from the nearest point where
+// the discrete result would change (a rounding tie, a sigmoid at 0.5, an arg-max tie).  The per-graph minimum goes out
+// with the decode so that parity checks can tell a rounding tie from a bug (*mg = min(*mg, margin)).
+DX_HD DX_INLINE void q_lin(float x, float scale, float* xo, float* po, float* mg) {   // model.py:87-91
+  const float t = x * scale;
+  float p = rintf(t);
+  *mg = fminf(*mg, (0.5f - fabsf(t - p)) / scale);
   p = fminf(fmaxf(p, 0.f), scale);
   *po = p; *xo = p / scale;
 }
-DX_HD DX_INLINE float q_round_log(float x, float scale) {                  // model.py:93-96
-  float p = rintf(expf(x * logf(scale + 1.f)) - 1.f);
+DX_HD DX_INLINE float q_round_log(float x, float scale, float* mg) {       // model.py:93-96
+  const float ls = logf(scale + 1.f);
+  const float t = expf(x * ls) - 1.f;
+  float p = rintf(t);
+  *mg = fminf(*mg, (0.5f - fabsf(t - p)) / (ls * (t + 1.f)));             // dt/dx = ls * (t + 1)
   return fminf(fmaxf(p, 0.f), scale);
 }
-DX_HD DX_INLINE int argmax_n(const float* l, int n) {
-  int best = 0; float bv = l[0];
-  for (int c = 1; c < n; ++c) if (l[c] > bv) { bv = l[c]; best = c; }
+DX_HD DX_INLINE float q_bool(float x, float* mg) {                          // model.py:100-102: round(sigmoid(x))
+  *mg = fminf(*mg, fabsf(x));
+  return rintf(sigmoidf_(x));
+}
+DX_HD DX_INLINE int argmax_n(const float* l, int n, float* mg = nullptr) {
+  int best = 0; float bv = l[0], second = -3.0e38f;
+  for (int c = 1; c < n; ++c) {
+    if (l[c] > bv) { second = bv; bv = l[c]; best = c; }
+    else if (l[c] > second) second = l[c];
+  }
+  if (mg) *mg = fminf(*mg, bv - second);
   return best;
 }
 // _reg_x0, model.py:109-125.  Writes node-major X row (32 wide, zero padded) and params row (32 wide).
-static void reg_x0(dx_stream_t st, int B, const float* L0, float* Xd, float* Pn) {
+static void reg_x0(dx_stream_t st, int B, const float* L0, float* Xd, float* Pn, float* margins) {
   foreach (st, B, [=] DX_HD(int64_t b) {
     const float* l = L0 + b * LD_L; float* x = Xd + b * XP; float* p = Pn + b * XP;
+    float mg = 3.0e38f;
     for (int c = 0; c < XP; ++c) { x[c] = 0.f; p[c] = 0.f; }
     for (int c = 0; c < 15; ++c) {
       const float sc = c == 8 ? 48.f : (c >= 13 ? 7.f : 99.f);
-      q_lin(l[c], sc, &x[c], &p[c]);
+      q_lin(l[c], sc, &x[c], &p[c], &mg);
     }
-    for (int c = 15; c < 17; ++c) { const float v = rintf(sigmoidf_(l[c])); x[c] = v; p[c] = v; }
-    const int lfw = argmax_n(l + 17, 6);
+    for (int c = 15; c < 17; ++c) { const float v = q_bool(l[c], &mg); x[c] = v; p[c] = v; }
+    const int lfw = argmax_n(l + 17, 6, &mg);
     x[17 + lfw] = 1.f; p[17] = (float)lfw;
-    p[18] = (float)argmax_n(l + 23, 32);
+    p[18] = (float)argmax_n(l + 23, 32, &mg);
+    if (margins) margins[2 * b + 1] = fminf(margins[2 * b + 1], mg);
   });
 }
 // _reg_xi, model.py:127-149 (incl. the 23:26 argmax quirk and the per-mode fc/ff quantiser)
-static void reg_xi(dx_stream_t st, int B, const float* Li, float* Xd, float* Pn) {
+static void reg_xi(dx_stream_t st, int B, const float* Li, float* Xd, float* Pn, float* margins) {
   foreach (st, B, [=] DX_HD(int64_t b) {
     const float* l = Li + b * LD_L; float* x = Xd + b * XP; float* p = Pn + b * XP;
+    float mg = 3.0e38f;
     for (int c = 0; c < XP; ++c) { x[c] = 0.f; p[c] = 0.f; }
-    for (int c = 0; c < 9; ++c) q_lin(l[c], 99.f, &x[c], &p[c]);
-    q_lin(l[11], 14.f, &x[11], &p[11]);
-    for (int c = 12; c < 15; ++c) q_lin(l[c], 99.f, &x[c], &p[c]);
-    q_lin(l[15], 3.f, &x[15], &p[15]);
-    q_lin(l[16], 7.f, &x[16], &p[16]); q_lin(l[17], 7.f, &x[17], &p[17]);
-    const float mode = rintf(sigmoidf_(l[18]));
+    for (int c = 0; c < 9; ++c) q_lin(l[c], 99.f, &x[c], &p[c], &mg);
+    q_lin(l[11], 14.f, &x[11], &p[11], &mg);
+    for (int c = 12; c < 15; ++c) q_lin(l[c], 99.f, &x[c], &p[c], &mg);
+    q_lin(l[15], 3.f, &x[15], &p[15], &mg);
+    q_lin(l[16], 7.f, &x[16], &p[16], &mg); q_lin(l[17], 7.f, &x[17], &p[17], &mg);
+    const float mode = q_bool(l[18], &mg);
     x[18] = mode; p[18] = mode;
-    const int lc = argmax_n(l + 19, 4); x[19 + lc] = 1.f; p[19] = (float)lc;
-    const int rc = argmax_n(l + 23, 3); x[23 + rc] = 1.f; p[20] = (float)rc;
+    const int lc = argmax_n(l + 19, 4, &mg); x[19 + lc] = 1.f; p[19] = (float)lc;
+    const int rc = argmax_n(l + 23, 3, &mg); x[23 + rc] = 1.f; p[20] = (float)rc;
     if (mode == 0.f) {
-      const float pc = q_round_log(l[9], 31.f), pf = q_round_log(l[10], 99.f);
+      const float pc = q_round_log(l[9], 31.f, &mg), pf = q_round_log(l[10], 99.f, &mg);
       p[9] = pc; x[9] = tab_f(DX_TAB32, (int)pc);
       p[10] = pf; x[10] = tab_f(DX_TAB100, (int)pf);
     } else {
-      q_lin(l[9], 3.f, &x[9], &p[9]); q_lin(l[10], 99.f, &x[10], &p[10]);
+      q_lin(l[9], 3.f, &x[9], &p[9], &mg); q_lin(l[10], 99.f, &x[10], &p[10], &mg);
     }
+    if (margins) margins[2 * b + 1] = fminf(margins[2 * b + 1], mg);
   });
 }
 // edge decisions (model.py:236-239, 245-250): sigmoid(logit) > 0.5 ; sets adjacency bits, tracks margins
 static void decide_edges(dx_stream_t st, int B, int vi, int vj, const float* lg, int n, uint64_t* adj, float* margins) {
   foreach (st, B, [=] DX_HD(int64_t b) {
     uint64_t A = adj[b];
-    float mg = margins ? margins[b] : 0.f;
+    float mg = margins ? margins[2 * b] : 0.f;
     for (int c = 0; c < n; ++c) {
       const float x = lg[b * LD_E + c];
       const bool on = sigmoidf_(x) > 0.5f;
@@ -287,7 +307,7 @@ static void decide_edges(dx_stream_t st, int B, int vi, int vj, const float* lg,
       mg = fminf(mg, fabsf(x));
     }
     adj[b] = A;
-    if (margins) margins[b] = mg;
+    if (margins) margins[2 * b] = mg;
   });
 }
 
@@ -314,7 +334,7 @@ DX_HD DX_INLINE void edge_head_row_decide(const EdgeHeadP& a, int b, float l0, f
   if (on0) A |= 1ull << (a.vj * 7 + a.vi);
   if (on1) A |= 1ull << (a.vi * 7 + a.vj);
   a.adj_out[b] = A;
-  if (a.margins) a.margins[b] = fminf(a.margins[b], fminf(fabsf(l0), fabsf(l1)));
+  if (a.margins) a.margins[2 * b] = fminf(a.margins[2 * b], fminf(fabsf(l0), fabsf(l1)));
   a.active[b] = (uint8_t)((on0 || on1) ? 1 : 0);
 }
 
@@ -638,7 +658,7 @@ void decode_fwd_impl(dx_stream_t st, const Weights& W, int B, const float* z, co
   linear_fwd(st, B, H, Z, z, Z, W[P_ZH_W], Z, W[P_ZH_B], w.Hinit, H, ACT_TANH);
   mlp3_fwd(st, W, B, P_X0_W0, w.Hinit, SX0 + 32, w.A1[0], w.A2[0], w.L[0]);
   if (train) loss_x0(st, B, w.L[0], Xsrc, io.bt->cls, io.lw, w.rowloss, w.dL[0]);
-  else reg_x0(st, B, w.L[0], w.Xd, w.Pn);
+  else reg_x0(st, B, w.L[0], w.Xd, w.Pn, io.margins);
   // root: h_0 = GRU_root(x0[:23], H_init)
   linear_fwd(st, B, G3, Kr, Xsrc, XP, Wr, ldr, nullptr, w.gxc[0], G3);
   linear_fwd(st, B, G3, H, w.Hinit, H, W[P_RD_WHH], H, nullptr, w.gh, G3);
@@ -656,7 +676,7 @@ void decode_fwd_impl(dx_stream_t st, const Weights& W, int B, const float* z, co
     RowMap rm{B, B, nullptr, vi * B};
     mlp3_fwd(st, W, B, P_X_W0, hprev_node, SX, w.A1[vi], w.A2[vi], w.L[vi]);
     if (train) loss_xi(st, B, vi, w.L[vi], Xi, io.bt->cls, io.lw, w.rowloss, w.dL[vi]);
-    else reg_xi(st, B, w.L[vi], w.Xd + (size_t)vi * B * XP, w.Pn + (size_t)vi * B * XP);
+    else reg_xi(st, B, w.L[vi], w.Xd + (size_t)vi * B * XP, w.Pn + (size_t)vi * B * XP, io.margins);
     linear_fwd(st, B, G3, Kx, Xi, XP, Wc, ldx, nullptr, w.gxc[vi], G3);
     linear_fwd(st, B, G3, Kx, Xi, XP, Wl, ldx, nullptr, w.gxl[vi], G3);
     // P1 (model.py:234/320): no edges yet -> H_in = 0, x_loop = 0

@@ -71,7 +71,7 @@ struct DecIO {
   const Batch* bt;        // train: teacher-forcing inputs
   LossW lw;
   uint64_t* adj_out;      // greedy: adjacency being built
-  float* margins;         // greedy, optional
+  float* margins;         // greedy, optional: (B,2) = min |edge logit|, min quantiser margin (logit units)
   float* dW2 = nullptr;   // train + compacted steps: gradient slots of h_to_edge.2.{weight,bias}; the fused edge
   float* db2 = nullptr;   //   head accumulates them during the forward pass (NULL: loss only, no gradients)
   float* db0 = nullptr;   // likewise h_to_edge.0.bias (= column sums of every head's pre-activation gradient)
@@ -115,7 +115,8 @@ size_t workspace_bytes(int op, int64_t B);
 int encode_fwd(dx_stream_t st, const float* weights, const Batch& bt, float* mu, float* std_, void* ws, size_t ws_bytes,
                int keep);
 int elbo_step(dx_stream_t st, const float* weights, const Batch& bt, const float* eps, LossW lw, float* loss5,
-              float* mu_out, float* std_out, float* grads, void* ws, size_t ws_bytes, int precision);
+              float* mu_out, float* std_out, float* grads, void* ws, size_t ws_bytes, int precision,
+              void* dec_done_event = nullptr);
 int decode_greedy(dx_stream_t st, const float* weights, int64_t B, const float* z, float* Xg, float* Pg, uint64_t* adj,
                   float* margins, void* ws, size_t ws_bytes, int precision);
 

@@ -70,6 +70,7 @@ class DXGraph:
     def __init__(self, X, params, src, dst):
         self.ndata = {"X": X, "params": params}
         self._edges = ([int(s) for s in src], [int(d) for d in dst])
+        self._owner = None      # (DXGraphBatch, index, X view, params view, edge tuple) when this graph is a row view of a batch
 
     def edges(self):
         return (torch.tensor(self._edges[0], dtype=torch.int64), torch.tensor(self._edges[1], dtype=torch.int64))
@@ -116,11 +117,40 @@ class DXGraphBatch:
         graphs = list(graphs)
         if not graphs:
             raise ValueError("empty batch")
+        fast = cls._from_views(graphs)
+        if fast is not None:
+            return fast
         X = torch.stack([g.ndata["X"].detach().to("cpu", torch.float32) for g in graphs])
         P = torch.stack([g.ndata["params"].detach().to("cpu", torch.float32) for g in graphs])
         edges = [_graph_edges(g) for g in graphs]
         adj = torch.tensor([_to_i64(mask_from_edges(*e)) for e in edges], dtype=torch.int64)
         return cls(X, P, adj, edges)
+
+    @classmethod
+    def _from_views(cls, graphs):
+        """Batcher fast path: graphs that are untouched row views of ONE DXGraphBatch (what iterating / indexing a batch or
+        a DXDataset hands out) are re-batched by index — one gather (a plain slice when the rows are consecutive) instead
+        of stacking thousands of (7,27) tensors.  Returns None when any graph is foreign or was modified."""
+        own = getattr(graphs[0], "_owner", None)
+        if own is None:
+            return None
+        base = own[0]
+        idx = []
+        for g in graphs:
+            o = getattr(g, "_owner", None)
+            if o is None or o[0] is not base or g.ndata.get("X") is not o[2] or g.ndata.get("params") is not o[3] \
+                    or g._edges is not o[4]:
+                return None
+            idx.append(o[1])
+        n = len(idx)
+        el = base._edge_lists
+        if idx[-1] - idx[0] == n - 1 and all(idx[k + 1] - idx[k] == 1 for k in range(n - 1)):
+            sl = slice(idx[0], idx[0] + n)
+            return cls(base.X[sl], base.params[sl], base.adj[sl], el[sl] if el is not None else None)
+        ii = torch.as_tensor(idx, dtype=torch.int64, device=base.X.device)
+        pin = (not base.X.is_cuda) and base.X.is_pinned()
+        take = lambda t: (t.index_select(0, ii).pin_memory() if pin else t.index_select(0, ii))
+        return cls(take(base.X), take(base.params), take(base.adj), [el[i] for i in idx] if el is not None else None)
 
     def __len__(self):
         return self.X.shape[0]
@@ -133,12 +163,26 @@ class DXGraphBatch:
             i += len(self)
         if not 0 <= i < len(self):
             raise IndexError(i)
-        e = self._edge_lists[i] if self._edge_lists is not None else edges_from_mask(int(self.adj[i]) & (2 ** 49 - 1))
-        return DXGraph(self.X[i].cpu(), self.params[i].cpu(), e[0], e[1])
+        return self._view(i, int(self.adj[i]) if self._edge_lists is None else 0)
+
+    def _view(self, i, mask):
+        e = self._edge_lists[i] if self._edge_lists is not None else edges_from_mask(mask & (2 ** 49 - 1))
+        X, P = self.X[i], self.params[i]
+        if X.is_cuda:
+            return DXGraph(X.cpu(), P.cpu(), e[0], e[1])
+        g = DXGraph.__new__(DXGraph)
+        g.ndata = {"X": X, "params": P}
+        g._edges = (list(e[0]), list(e[1]))
+        g._owner = (self, i, X, P, g._edges)
+        return g
 
     def __iter__(self):
+        masks = self.adj.cpu().tolist() if self._edge_lists is None else None
         for i in range(len(self)):
-            yield self[i]
+            yield self._view(i, masks[i] if masks is not None else 0)
+
+    def pin_memory(self):
+        return DXGraphBatch(self.X.pin_memory(), self.params.pin_memory(), self.adj.pin_memory(), self._edge_lists)
 
     def edge_lists(self):
         if self._edge_lists is not None:

@@ -67,8 +67,12 @@ class DXVAE(nn.Module):
         self._table = None
         self._ws = {}
         self.max_chunk = 32768      # graphs per kernel pass for encode / decode
+        self.host_batcher_max = 2048   # larger host batches are scheduled on the device
         self.verbose = True
         self.last_margins = None
+        self.last_quant_margins = None
+        self.last_loss5 = None      # device tensor (total, x0, xi, e, kld*w) of the latest forward()
+        self._last_gflat = None     # flat gradient blob the latest backward() handed out views of
         # arithmetic of the training products: "fp32" (FFMA), "3xtf32" (tcgen05 tensor cores with
         # error-compensated hi/lo operands: FP32-accurate, meets the reference tolerance) or "tf32"
         # (plain tensor-core TF32, looser stated tolerance)
@@ -146,7 +150,9 @@ class DXVAE(nn.Module):
         d.cls = torch.empty(14, B, dtype=torch.int32, device="cuda")
         _lib.check(L.dxvae_pack_graphs(B, Xg.data_ptr(), Pg.data_ptr(), d.Xn.data_ptr(), d.cls.data_ptr(), st),
                    "dxvae_pack_graphs")
-        use_host = (not gb.adj.is_cuda) if host_batcher is None else host_batcher
+        # host-resident batches of a few thousand graphs go through the C++ host batcher (explicit CSR, no device round
+        # trip); larger ones are uploaded and scheduled on the device (same result, bit for bit)
+        use_host = (not gb.adj.is_cuda and B <= self.host_batcher_max) if host_batcher is None else host_batcher
         d.level_ptr = np.zeros(16, np.int32)       # 8 level offsets, then per-level counts of back-edge-target rows
         d.csr = None
         if use_host:
@@ -266,7 +272,7 @@ class DXVAE(nn.Module):
         z = torch.as_tensor(z).to("cuda", torch.float32).contiguous()
         B = z.shape[0]
         Xg = torch.empty(B, 7, 27, device="cuda"); Pg = torch.empty(B, 7, 21, device="cuda")
-        adj = torch.empty(B, dtype=torch.int64, device="cuda"); mg = torch.empty(B, device="cuda")
+        adj = torch.empty(B, dtype=torch.int64, device="cuda"); mg = torch.empty(B, 2, device="cuda")
         for lo in range(0, B, self.max_chunk):
             hi = min(B, lo + self.max_chunk)
             ws = self._workspace(_abi.OP_DECODE, hi - lo)
@@ -275,7 +281,8 @@ class DXVAE(nn.Module):
                                              ws.data_ptr(), ws.numel(),
                                              {"fp32": _abi.PREC_FP32, "3xtf32": _abi.PREC_3XTF32}[self.decode_precision],
                                              _stream()), "dxvae_decode_greedy")
-        self.last_margins = mg
+        self.last_margins = mg[:, 0]          # min |edge logit| per graph
+        self.last_quant_margins = mg[:, 1]    # min distance of a parameter logit to a rounding / arg-max tie
         return DXGraphBatch(Xg, Pg, adj)
 
     def encode_decode(self, G_true, stochastic=False):
@@ -324,11 +331,13 @@ class DXVAE(nn.Module):
         total, rest = out[0], out[1]
         return total, rest[0], rest[1], rest[2], rest[3]
 
-    def elbo_step(self, d, eps, w, grads=None, inv_batch=None, mu_out=None, std_out=None):
-        """Raw fused step on a prepared batch: returns loss5 (device tensor of 5); accumulates
-        into `grads` (flat blob) when given."""
+    def elbo_step(self, d, eps, w, grads=None, inv_batch=None, mu_out=None, std_out=None, loss5=None, decoder_done=None):
+        """Raw fused step on a prepared batch: returns loss5 (device tensor of 5, or the caller's); accumulates
+        into `grads` (flat blob) when given.  decoder_done (torch.cuda.Event): recorded on the stream once the decoder's
+        backward has been issued, i.e. when the decoder-only gradient range is final (data-parallel overlap)."""
         L = _lib.lib()
-        loss5 = torch.empty(5, device="cuda")
+        if loss5 is None:
+            loss5 = torch.empty(5, device="cuda")
         ws = self._workspace(_abi.OP_TRAIN, d.B)
         _lib.check(L.dxvae_elbo_step(
             self._flat.data_ptr(), d.B, d.Xn.data_ptr(), d.cls.data_ptr(), d.adj.data_ptr(), d.n_levels,
@@ -337,7 +346,8 @@ class DXVAE(nn.Module):
             None if mu_out is None else mu_out.data_ptr(), None if std_out is None else std_out.data_ptr(),
             None if grads is None else grads.data_ptr(), ws.data_ptr(), ws.numel(), self._prec(),
             None if d.step_ptr is None else d.step_ptr.ctypes.data,
-            None if d.step_ptr is None else d.step_rows.data_ptr(), _stream()), "dxvae_elbo_step")
+            None if d.step_ptr is None else d.step_rows.data_ptr(),
+            None if decoder_done is None else decoder_done.cuda_event, _stream()), "dxvae_elbo_step")
         return loss5
 
     # ------------------------------------------------------------------ train
@@ -347,7 +357,8 @@ class DXVAE(nn.Module):
         does.)  Under torch.distributed every global batch is sharded in equal contiguous
         slices across ranks and the flat gradient is all-reduced (sum) over NCCL."""
         from .train import Trainer
-        t = Trainer(self, lr=lr, w=(float(w_env), float(w_frq), float(w_kld)))
+        import torch.distributed as dist
+        t = Trainer(self, lr=lr, w=(float(w_env), float(w_frq), float(w_kld)))   # (data parallel: broadcasts rank 0's weights)
         n_samples = len(G_true)
         n_iters = int(n_samples / size_batch)
         data = t.upload(G_true)
@@ -357,6 +368,10 @@ class DXVAE(nn.Module):
                 print(f'Epoch: {epoch}')
             perm = list(range(n_samples))
             random.shuffle(perm)                      # same RNG consumption as random.shuffle(G_true)
+            if t.world > 1:                           # one permutation for all ranks (rank 0's), whatever their seeds
+                box = [perm]
+                dist.broadcast_object_list(box, src=0)
+                perm = box[0]
             order = [order[i] for i in perm]
             if isinstance(G_true, list):
                 G_true[:] = [G_true[i] for i in perm]  # the reference shuffles the caller's list in place
@@ -367,7 +382,10 @@ class DXVAE(nn.Module):
                     l = loss5.tolist()
                     print(f'batch: {i}\tloss: {l[0]:.4f}\tx0: {l[1]:.4f}\txi: {l[2]:.4f}\te: {l[3]:.4f}\tkld: {l[4]:.4f}')
             if checkpoint is not None:
-                torch.save(self.state_dict(), checkpoint)
+                if t.rank == 0:                       # replicas hold identical weights: one writer
+                    torch.save(self.state_dict(), checkpoint)
+                if t.world > 1:
+                    dist.barrier()
                 if self.verbose:
                     print(f'\nCheckpoint [{checkpoint}] saved\n')
         if self.verbose:
@@ -384,14 +402,21 @@ class _ElboFn(torch.autograd.Function):
         g = torch.zeros(model._total, device="cuda") if need else None
         loss5 = model.elbo_step(d, eps, w, grads=g)
         ctx.model, ctx.g = model, g
+        model.last_loss5 = loss5
         total, rest = loss5[0].clone(), loss5[1:].clone()
         ctx.mark_non_differentiable(rest)
         return total, rest
 
     @staticmethod
     def backward(ctx, gtotal, _grest):
-        grads = ctx.model._grad_views(ctx.g, gtotal)
-        return (None, None, None, None) + grads
+        # one in-place scale of the flat blob (the chain rule's upstream factor), then views of it: the parameters'
+        # .grad tensors alias ONE buffer, which FusedAdamW / the data-parallel all-reduce consume without a gather
+        if getattr(ctx, "consumed", False):
+            raise RuntimeError("DXVAE.forward(): backward() through the fused step can run once (its gradient blob is scaled in place)")
+        ctx.consumed = True
+        ctx.g.mul_(gtotal)
+        ctx.model._last_gflat = ctx.g
+        return (None, None, None, None) + ctx.model._grad_views(ctx.g)
 
 
 class _EncodeFn(torch.autograd.Function):
@@ -445,4 +470,8 @@ class _LossFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, gtotal, _grest):
-        return (None, None, None, None, ctx.dmu * gtotal, ctx.dsd * gtotal) + ctx.model._grad_views(ctx.g, gtotal)
+        if getattr(ctx, "consumed", False):
+            raise RuntimeError("DXVAE.loss(): backward() through the fused step can run once (its gradient blob is scaled in place)")
+        ctx.consumed = True
+        ctx.g.mul_(gtotal)
+        return (None, None, None, None, ctx.dmu * gtotal, ctx.dsd * gtotal) + ctx.model._grad_views(ctx.g)

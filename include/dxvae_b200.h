@@ -13,7 +13,9 @@
  *   - `stream` is a cudaStream_t passed as void*; all work is enqueued on it and
  *     nothing synchronises unless stated;
  *   - return 0 = ok, non-zero = error; dxvae_last_error() gives the message
- *     (thread-local).  Nothing throws across the ABI.  No hidden global state.
+ *     (thread-local).  Nothing throws across the ABI.  Process state is limited to per-device set-up flags
+ *     (constant tables, kernel attributes), the launch counter and the thread-local arithmetic mode that an
+ *     entry point sets for its own duration.
  *   - model constants are fixed (7 nodes, X 27, X0 23, H 512, Z 128): kernels are
  *     specialised on them.
  *
@@ -38,7 +40,7 @@
 extern "C" {
 #endif
 
-#define DXVAE_ABI_VERSION 3
+#define DXVAE_ABI_VERSION 4
 #define DXVAE_N_NODES 7
 #define DXVAE_N_PARAMS 21
 #define DXVAE_SIZE_X 27
@@ -53,7 +55,7 @@ const char* dxvae_last_error(void);
 /* number of kernels this library has launched in this process (bench.py's gpu_launches) */
 long long dxvae_launch_count(void);
 /* per-launch CUDA-event timing of the GEMM kernel family (bench.py roofline): totals per tile
- * class (0: FP32 128x128 tiles, 1: FP32 64x64, 2: tcgen05 TF32) of device ms, executed flops
+ * class (0: FP32 128x128 tiles, 1: FP32 64x64, 2: tcgen05 TF32 / 3xTF32) of device ms, executed flops
  * (2MNK) and launches; each output array has 3 entries. */
 void dxvae_prof_begin(int max_launches);
 void dxvae_prof_end(double* ms3, double* flops3, long long* n3);
@@ -127,10 +129,12 @@ int dxvae_pack_syx(int64_t B, const float* Pg, uint8_t* voices, void* stream);
  * DXVAE_PREC_TF32: eligible products (rows >= 128, N >= 64, K >= 32, no row gather) run on the
  *                  tcgen05 tensor cores with TF32 inputs / FP32 accumulation; looser, stated
  *                  tolerance.
- * DXVAE_PREC_3XTF32: inference only (encode_fwd keep=0, decode_greedy).  FP32-accurate products on the
- *                  tensor cores: operands are split exactly into tf32 hi + lo parts and every k-step
- *                  issues hi*hi + hi*lo + lo*hi into the FP32 accumulator (error ~2^-21 per product,
- *                  the size of FP32 summation-order noise), so discrete decode outputs keep matching. */
+ * DXVAE_PREC_3XTF32: FP32-accurate products on the tensor cores, every entry point and every operand form (forward,
+ *                  dgrad, wgrad).  The kernel itself splits each landed operand tile into tf32 hi + lo parts in
+ *                  shared memory and issues hi*hi + hi*lo + lo*hi; the FP32 partial sums are drained from TMEM into
+ *                  registers every 32 k (the tensor core accumulates with truncation, which would otherwise bias a
+ *                  long reduction).  Measured product error 3e-7..6e-7 of max|C| (the FFMA kernels: ~1e-6);
+ *                  a training step meets the reference tolerances of DXVAE_PREC_FP32. */
 enum { DXVAE_PREC_FP32 = 0, DXVAE_PREC_TF32 = 1, DXVAE_PREC_3XTF32 = 2 };
 
 /* ---- workspace sizes ------------------------------------------------------------ */
@@ -154,10 +158,11 @@ int dxvae_encode_fwd(const float* weights, int64_t B, const float* Xn, const uin
 int dxvae_reparameterize(int64_t n, const float* mu, const float* std_, const float* eps, float* z, void* stream);
 
 /* ---- greedy decode (model.py:214-253, quantisers :87-149) ------------------------ *
- * z (B,128) -> Xg (B,7,27), Pg (B,7,21), adj (B).  logits_out (optional, may be NULL):
- * (B,34) fp32 decision logits [6 self-loop | 21 x (in,out) ... ] is NOT provided; use
- * margins (B) = min |logit| over the 48 edge decisions of each graph, for tie-aware
- * parity checks.  After each pair of edge decisions only the graphs that gained an edge
+ * z (B,128) -> Xg (B,7,27), Pg (B,7,21), adj (B).  margins (optional, may be NULL): (B,2) fp32,
+ * [b][0] = min |logit| over the 48 edge decisions of graph b (sigmoid > 0.5 flips at logit 0),
+ * [b][1] = min distance, in logit units, of any parameter logit to the point where its quantiser would decide
+ * otherwise (rounding tie of _q_lin / _q_log, sigmoid at 0.5 of _q_bool, arg-max gap of _q_prob; model.py:87-107),
+ * for tie-aware parity checks.  After each pair of edge decisions only the graphs that gained an edge
  * re-propagate; their count is read back to size the next launches, so this call
  * synchronises the stream (21 small copies per call) and must not be stream-captured. */
 int dxvae_decode_greedy(const float* weights, int64_t B, const float* z, float* Xg, float* Pg, uint64_t* adj,
@@ -166,17 +171,20 @@ int dxvae_decode_greedy(const float* weights, int64_t B, const float* z, float* 
 /* ---- teacher-forced ELBO (model.py:270-367) + backward (model.py:385) ------------ *
  * One call = encode_fwd + loss_fwd (+ backward of both when grads != NULL).
  * eps (B,128) is the injected N(0,1) noise.  loss5 (5 floats, device) receives
- * (total, loss_X0, loss_Xi, loss_E, kld*w_kld) of model.py:367 over the B graphs
- * scaled by loss_scale... see below.  `inv_batch` is 1/(global batch): every term is a
+ * (total, loss_X0, loss_Xi, loss_E, kld*w_kld) of model.py:367 over the B graphs,
+ * each scaled by inv_batch * B.  `inv_batch` is 1/(global batch): every term is a
  * batch mean (model.py:303-365), so data-parallel ranks pass 1/(B*world) and sum
  * loss5 / grads across ranks.  grads: flat blob, same layout as weights, ACCUMULATED
- * into (caller zeroes it). */
+ * into (caller zeroes it).  decoder_done_event (cudaEvent_t or NULL) is recorded on the stream once the decoder's
+ * backward has been issued: the gradient range of the decoder-only tensors (combin_decode.weight_ih up to, not
+ * including, gate.0.weight) is final from then on, so a data-parallel caller can reduce it while the encoder's
+ * backward still runs. */
 int dxvae_elbo_step(const float* weights, int64_t B, const float* Xn, const int32_t* cls, const uint64_t* adj,
                     int32_t n_levels, const int32_t* level_ptr_host, const int32_t* level_rows,
                     const int32_t* level_rare_host, const float* eps,
                     float w_env, float w_frq, float w_kld, float inv_batch, float* loss5, float* mu_out,
                     float* std_out, float* grads, void* workspace, size_t workspace_bytes, int precision,
-                    const int32_t* step_ptr_host, const int32_t* step_rows, void* stream);
+                    const int32_t* step_ptr_host, const int32_t* step_rows, void* decoder_done_event, void* stream);
 
 /* Split form of dxvae_elbo_step, for DXVAE.encode(G) followed by DXVAE.loss(q, G)
  * (model.py:370-371).  encode_fwd(keep=1, workspace of DXVAE_OP_ENCODE_TRAIN) leaves the
@@ -201,7 +209,8 @@ int dxvae_adamw_step(int64_t n, float* weights, const float* grads, float* exp_a
 
 /* ---- low-level pieces exported for unit tests ------------------------------------ *
  * variant 0: C[M,N] = act(A[M,K] W[N,K]^T + bias) (act: 0 none, 1 relu, 2 tanh, 4 softplus);
- * 1: dgrad C[M,K] (+)= A[M,N] W[N,K]; 2: wgrad C[N,K] += A[M,N]^T B[M,K]; +16: TF32 tensor-core path */
+ * 1: dgrad C[M,K] (+)= A[M,N] W[N,K]; 2: wgrad C[N,K] += A[M,N]^T B[M,K]; +16: TF32 tensor-core path; +32: 3xTF32;
+ * 64: forward with bf16 operands (A, Bm point at bf16 data) */
 int dxvae_test_gemm(int variant, int64_t M, int64_t N, int64_t K, const float* A, int64_t lda, const float* Bm,
                     int64_t ldb, float* C, int64_t ldc, const float* bias, int act, int accumulate, void* stream);
 

@@ -108,7 +108,7 @@ class Emu:
         _abi.check(L, L.dxvae_elbo_step(ptr(self.blob), B, ptr(bt["Xn"]), ptr(bt["cls"]), ptr(bt["adj"]),
                                         bt["n_levels"], ptr(bt["level_ptr"]), ptr(bt["level_rows"]), ptr(bt["level_ptr"][8:]), ptr(eps),
                                         w[0], w[1], w[2], inv_batch or 1.0 / B, ptr(loss5), ptr(mu), ptr(sd), ptr(g),
-                                        ptr(ws), ws.nbytes, 0, ptr(sp), ptr(sr), None), "elbo")
+                                        ptr(ws), ws.nbytes, 0, ptr(sp), ptr(sr), None, None), "elbo")
         return loss5, mu, sd, g
 
     def decode(self, z):
@@ -117,7 +117,7 @@ class Emu:
         B = z.shape[0]
         ws = np.full(L.dxvae_workspace_bytes(_abi.OP_DECODE, B), 0xFF, np.uint8)   # NaN-poisoned: a read of workspace that was never written shows up in the outputs
         Xg = np.zeros((B, 7, 27), np.float32); Pg = np.zeros((B, 7, 21), np.float32)
-        adj = np.zeros(B, np.uint64); mg = np.zeros(B, np.float32)
+        adj = np.zeros(B, np.uint64); mg = np.zeros((B, 2), np.float32)
         _abi.check(L, L.dxvae_decode_greedy(ptr(self.blob), B, ptr(z), ptr(Xg), ptr(Pg), ptr(adj), ptr(mg), ptr(ws),
                                             ws.nbytes, 0, None), "decode")
         return Xg, Pg, adj, mg

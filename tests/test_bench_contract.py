@@ -9,14 +9,18 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 def test_reference_arm_prints_one_json_line_with_the_contract_keys():
     out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0",
-                          "--cpu-patches", "8"], capture_output=True, text=True, timeout=600, cwd=ROOT)
+                          "--cpu-patches", "8", "--ref-patches", "4"], capture_output=True, text=True, timeout=600, cwd=ROOT)
     assert out.returncode == 0, out.stderr[-2000:]
     lines = [l for l in out.stdout.splitlines() if l.strip()]
     assert len(lines) == 1
     d = json.loads(lines[0])
     assert d["impl"] == "reference" and d["metric"] == "patches/sec ELBO train step" and d["unit"] == "patches/s"
     assert d["higher_is_better"] is True and d["n_gpus"] == 1 and d["steps"] == 1 and d["value"] > 0
-    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
+    # the unmodified reference when baseline/_ref is staged (build container, GPU box), else the oracle port
+    staged = os.path.isfile(os.path.join(ROOT, "baseline", "_ref", "model.py"))
+    assert d["cpu_baseline"]["kind"] == ("reference" if staged else "port")
+    assert d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
+    assert d["extra"]["oracle_port"]["kind"] == "port" and d["extra"]["oracle_port"]["value"] > 0
     assert d["e2e"] == {"value": d["value"], "unit": "patches/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
 
 

@@ -304,14 +304,23 @@ def test_trainer_trajectory_matches_oracle(lib):
 
 
 # --------------------------------------------------------------------------- greedy decode
+@pytest.mark.parametrize("prec", ["fp32", "3xtf32"])
 @pytest.mark.parametrize("tag,gain", [("init", 1.0), ("stress", 3.0)])
-def test_decode_matches_oracle_and_reference_golden(lib, golden, tag, gain):
+def test_decode_matches_oracle_and_reference_golden(lib, golden, tag, gain, prec):
+    """Greedy decode against the reference's own outputs, in both FP32-accurate arithmetics (FFMA and 3xTF32 on the
+    tensor cores).  Tie-aware on EVERY discrete decision: a graph is compared when its smallest edge-logit margin (from
+    the reference run) and its smallest quantiser margin (reported by the kernel: distance of a parameter logit to a
+    rounding / sigmoid / arg-max tie) both exceed MARGIN."""
     m, o = make_model(0, gain)
+    m.decode_precision = prec
     for zt in ("mu", "prior"):
         z = torch.from_numpy(golden["%s_dec_%s_z" % (tag, zt)])
         gb = m.decode(z)
         Xo, Po, Ao, mg = o.decode(z, return_margins=True)
-        ok = golden["%s_dec_%s_minmargin" % (tag, zt)] > MARGIN          # tie-aware
+        qm = m.last_quant_margins.cpu().numpy()
+        assert (qm > 0).all() and (qm < 10).all()
+        ok = (golden["%s_dec_%s_minmargin" % (tag, zt)] > MARGIN) & (qm > MARGIN)          # tie-aware
+        print(tag, zt, prec, "compared %d of %d graphs; min quantiser margin %.2e" % (ok.sum(), len(ok), qm.min()))
         assert ok.sum() >= 0.5 * len(ok)
         A = util.adj_from_masks(gb.adj.cpu().numpy().view(np.uint64))
         Pd = gb.params.cpu().numpy().astype(np.int32)

@@ -153,7 +153,8 @@ def test_tc_gemm_x3_dgrad_wgrad(lib, M, N, K):
 
 def test_3xtf32_training_step_meets_the_fp32_tolerance(lib):
     """precision="3xtf32": the whole fused ELBO step on the tensor cores within the REFERENCE (fp32) tolerances of
-    tests/test_gpu_parity.py: each loss term rel <= 1e-5, every gradient tensor max-norm-relative <= 1e-4.
+    tests/test_gpu_parity.py: each loss term rel <= 1e-5, every gradient tensor max-norm-relative <= 1e-4 (see the kink
+    clause below).
 
     The yardstick is the oracle evaluated in FLOAT64: with the gain-3 "stress" weights the fp32 oracle itself is 5.4e-4
     away from its float64 evaluation on h_to_edge.0.weight for this batch (one relu of the edge head sits on its kink, and
@@ -188,7 +189,11 @@ def test_3xtf32_training_step_meets_the_fp32_tolerance(lib):
         print("3xtf32 vs float64 oracle: loss rel", rel, "worst grad rel %.2e (%s); fp32 oracle vs float64: worst %.2e (%s)"
               % (ours[wn], wn, max(ref32.values()), max(ref32, key=ref32.get)))
         assert max(rel) <= 1e-5, rel
-        assert max(ours.values()) <= 1e-4, sorted(ours.items(), key=lambda kv: -kv[1])[:5]
+        # per tensor: within the reference tolerance, or (where a relu kink makes the reference's own fp32 evaluation noisier
+        # than that) within twice the fp32 oracle's own distance to float64
+        bad = {n: (e, ref32[n]) for n, e in ours.items() if e > max(1e-4, 2 * ref32[n])}
+        assert not bad, bad
+        assert sorted(ours.values())[-3] <= 1e-4         # and at most two tensors may lean on the kink clause
 
 
 def test_3xtf32_encode_within_fp32_tolerance(lib):
