@@ -511,10 +511,16 @@ __device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity)
       "}" ::"r"(bar), "r"(parity) : "memory");
 }
 // arrive on the LEADER CTA's copy of a barrier (remote arrive from the peer, local from the leader itself)
+// Default semantics (.release.cta), as cutlass::arch::ClusterBarrier::arrive(cta_id): the explicit `.release.cluster` form
+// compiles to MEMBAR.ALL.CTA + MEMBAR.ALL.GPU + ERRBAR + CGAERRBAR in front of the arrive, and ncu's source view put 43 % of
+// the epilogue warps' samples of k_tc_gemm_x3w on that ERRBAR (profiles/r02a): the "accumulator drained" signal, sent once
+// per k-block by 16 warps, was the critical path of the chunk ping-pong.  What the signals order is covered without it:
+// TMEM reads by tcgen05.wait::ld + tcgen05.fence::before_thread_sync, the converters' shared-memory writes by
+// fence.proxy.async (both issued before the arrive).
 __device__ __forceinline__ void mbar_arrive_leader(uint32_t bar) {
   uint32_t ra;
   asm volatile("mapa.shared::cluster.u32 %0, %1, 0;" : "=r"(ra) : "r"(bar));
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(ra) : "memory");
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(ra) : "memory");
 }
 // TMA load whose completion bytes go to the LEADER CTA's mbarrier (peer bit cleared: cute Sm100MmaPeerBitMask)
 __device__ __forceinline__ void tma_load_2d_2sm(const CUtensorMap* map, uint32_t dst, uint32_t bar, int c0, int c1) {

@@ -1,0 +1,145 @@
+"""BASELINE config 1 pinned with a TRAINED model: the reference's `checkpoints/dx_1024.chk` (README.md:23) is absent from
+the reference tree, so this script makes a substitute with the UNMODIFIED reference and records the reference's own
+outputs for it on ALL 1024 graphs of DX_data/DXDataset.bin.  Build container only (needs /root/reference):
+
+    python oracle/make_trained_golden.py [--epochs 39] [--chk /tmp/cfg1/dx_trained.chk]
+
+TEST INFRASTRUCTURE ONLY.
+
+1. trains `DXVAE().train(G, epochs, size_batch=128)` (model.py:374-391; main.py:24-32 is the README's recipe with
+   size_batch 32 / 500 epochs) on the dataset with torch / random seeds 0 — unless --chk names a state_dict that an
+   earlier run of this script saved;
+2. quantises every weight matrix to int8 with one fp32 scale per output row (biases stay fp32), so that the fixture is
+   12 MB instead of 48 MB; the DEQUANTISED weights (q * scale in fp32, bit-reproducible) are the pinned model — it is
+   a weight setting like any other for the reference, and it keeps the trained model's behaviour (checked below:
+   reconstruction loss within a few percent of the fp32 checkpoint, decodes spread over many topologies);
+3. runs the reference with those weights: encode of all 1024 graphs (mu, std), greedy decode of z = mu, the five loss
+   terms for a seeded eps and the gradient fingerprints of all 53 tensors — and asserts, before writing anything, that
+   oracle/dxvae_oracle.py reproduces every one of them.
+
+Fixtures: tests/golden/trained_q8.npz (the model), tests/golden/trained_golden.npz (the reference's outputs).
+"""
+import argparse
+import os
+import random
+import sys
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, HERE)
+import dxvae_oracle as O  # noqa: E402
+import ref_loader  # noqa: E402
+from make_golden import grad_fingerprint  # noqa: E402
+
+OUT = os.path.join(os.path.dirname(HERE), "tests", "golden")
+
+
+def quantise(sd):
+    """state_dict -> dict of arrays: '<name>.q' int8 + '<name>.s' fp32 row scales for matrices, '<name>' fp32 otherwise."""
+    out = {}
+    for n, t in sd.items():
+        a = t.detach().numpy().astype(np.float32)
+        if a.ndim == 2:
+            s = (np.abs(a).max(1) / 127.0).astype(np.float32)
+            s[s == 0] = 1.0
+            out[n + ".q"] = np.clip(np.rint(a / s[:, None]), -127, 127).astype(np.int8)
+            out[n + ".s"] = s
+        else:
+            out[n] = a
+    return out
+
+
+def dequantise(z):
+    """The pinned weights: q * scale evaluated in fp32 (one IEEE multiply per element: the same bits everywhere)."""
+    sd = {}
+    for k in z.keys():
+        if k.endswith(".q"):
+            n = k[:-2]
+            sd[n] = torch.from_numpy(z[k].astype(np.float32) * z[n + ".s"][:, None].astype(np.float32))
+        elif not k.endswith(".s"):
+            sd[k] = torch.from_numpy(np.asarray(z[k], np.float32))
+    return sd
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--epochs", type=int, default=39)
+    ap.add_argument("--chk", default=None)
+    args = ap.parse_args()
+    assert ref_loader.available(), "needs /root/reference"
+    torch.set_num_threads(os.cpu_count())
+    model_mod, _ = ref_loader.load_reference()
+    G = ref_loader.load_dataset_graphs()
+    m = model_mod.DXVAE()
+    if args.chk and os.path.isfile(args.chk):
+        m.load_state_dict(torch.load(args.chk, map_location="cpu"))
+    else:
+        torch.manual_seed(0); random.seed(0)
+        m = model_mod.DXVAE()
+        m.train(list(G), args.epochs, 128, 0.001, args.chk or "/tmp/dx_trained.chk")
+    q = quantise(m.state_dict())
+    sd = dequantise(q)
+    mq = model_mod.DXVAE(); mq.load_state_dict(sd)
+    o = O.OracleDXVAE(); o.load_state_dict(sd)
+
+    X = torch.stack([g.ndata["X"] for g in G]); P = torch.stack([g.ndata["params"] for g in G])
+    A = torch.stack([g.adj().to_dense() for g in G])
+    out = {}
+    with torch.no_grad():
+        torch.manual_seed(77)
+        l_fp = [t.item() for t in m.forward(G)]
+        torch.manual_seed(77)
+        l_q = [t.item() for t in mq.forward(G)]
+    print("loss (fp32 checkpoint)", l_fp, "\nloss (q8 model)       ", l_q)
+    assert abs(l_q[0] - l_fp[0]) <= 0.1 * abs(l_fp[0]), "quantisation changed the model too much"
+    # ---- encode, all 1024 graphs
+    qd = mq.encode(G)
+    mu_o, sd_o = o.encode(X, A)
+    assert (qd.loc - mu_o).abs().max() < 1e-6 and (qd.scale - sd_o).abs().max() < 1e-6
+    out["mu"] = qd.loc.detach().numpy(); out["std"] = qd.scale.detach().numpy()
+    # ---- loss + gradients with injected noise
+    torch.manual_seed(2024)
+    lr = mq.loss(qd, G)
+    torch.manual_seed(2024)
+    eps = torch.randn(len(G), 128)
+    lo = o.loss(mu_o, sd_o, X, P, A, eps)
+    for a, b in zip(lr, lo):
+        assert abs(a.item() - b.item()) <= 1e-5 * abs(a.item()), (a.item(), b.item())
+    mq.zero_grad(); o.zero_grad()
+    lr[0].backward(); lo[0].backward()
+    fr, fo = grad_fingerprint(mq), grad_fingerprint(o)
+    rel = np.abs(fr["vals"] - fo["vals"]).max(1) / (np.abs(fr["vals"]).max(1) + 1e-30)
+    assert rel.max() < 1e-4, rel.max()
+    out["loss"] = np.array([t.item() for t in lr], np.float64)
+    out["eps_seed"] = np.int64(2024)
+    for k, v in fr.items():
+        out["grad_" + k] = v
+    # ---- greedy decode of z = mu (encode_decode, model.py:255-262, non-stochastic)
+    z = qd.loc.detach()
+    with torch.no_grad():
+        mq.hidden = [[None] * 7 for _ in range(len(z))]
+        D = mq.decode(z)
+    Xr = torch.stack([g.ndata["X"] for g in D]); Pr = torch.stack([g.ndata["params"] for g in D])
+    Ar = torch.stack([g.adj().to_dense() for g in D]).to(torch.uint8)
+    Xo, Po, Ao, mg = o.decode(z, return_margins=True)
+    assert torch.equal(Pr.int(), Po.int()) and torch.equal(Ar, Ao)
+    assert (Xr - Xo).abs().max() <= 1e-6
+    lg = torch.cat([l.flatten(1) for l in mg["edge"] + mg["self"]], 1)
+    out["dec_X"] = Xr.numpy(); out["dec_params"] = Pr.numpy().astype(np.int16); out["dec_adj"] = Ar.numpy()
+    out["dec_minmargin"] = lg.abs().min(1).values.numpy()
+    same_topo = (Ar == A.to(torch.uint8)).flatten(1).all(1).float().mean().item()
+    same_par = (Pr.int() == P.int()).float().mean().item()
+    ntopo = len({bytes(a.numpy().tobytes()) for a in Ar})
+    print("decode(mu): %d distinct topologies, %.1f%% of the graphs reconstruct their topology, %.1f%% of all parameters exact"
+          % (ntopo, 100 * same_topo, 100 * same_par))
+    out["recon_topology_frac"] = np.float64(same_topo); out["recon_param_frac"] = np.float64(same_par)
+    np.savez_compressed(os.path.join(OUT, "trained_q8.npz"), **q)
+    np.savez_compressed(os.path.join(OUT, "trained_golden.npz"), **out)
+    print("written:", os.path.getsize(os.path.join(OUT, "trained_q8.npz")) / 1e6, "MB model,",
+          os.path.getsize(os.path.join(OUT, "trained_golden.npz")) / 1e6, "MB outputs")
+
+
+if __name__ == "__main__":
+    main()
