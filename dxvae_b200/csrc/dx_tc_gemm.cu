@@ -723,21 +723,24 @@ k_tc_gemm2(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
 }
 
 // =============================================================================================
-// 3xTF32 with chunked accumulation ("x3c"): FP32-accurate products on the tensor cores.
+// 3xTF32 with chunked accumulation: FP32-accurate products on the tensor cores.
 //
 // Measured on B200 (tools/x3_bias_probe.py): tcgen05 adds each MMA's partial product into the FP32 TMEM
 // accumulator with TRUNCATION toward zero, about one ulp per instruction, so a K = 1024 reduction issued as
 // 3 x 128 MMAs into one accumulator comes out 2e-5 short — a bias that is coherent across the 40 dependent
 // products of a training step (gradients off by 5e-4).  The error is proportional to the number of MMAs
-// accumulated in TMEM, so this kernel keeps that number small:
-//   * the hi*hi terms of x3c_chunk k-blocks (default 2 = 8 MMAs) go into a "chunk" accumulator that the epilogue
-//     warps drain into FP32 REGISTERS (round-to-nearest adds) while the next chunk runs in the other buffer;
-//   * the hi*lo / lo*hi cross terms (2^-11 of the result) go into their own accumulator for the whole tile:
-//     their truncation is relative to that small magnitude.
-// Tile: 128 rows x 128 columns per CTA (a pair of CTAs forms 256 x 128 with cta_group::2, each staging its 128
-// rows of A and 64 of the 128 B rows).  TMEM: 2 chunk buffers + 2 cross buffers (tile double buffering) x 128
-// columns = 512.  Warps: 0 TMA, 1 MMA issue, 2-9 epilogue (64 columns of one lane quadrant each: 64 running
-// sums per thread), 10-13 converters (lo = v - tf32(v) over each landed stage, see x3_split_stage).
+// accumulated in TMEM at full magnitude, so the kernels keep that number at FOUR:
+//   * a "chunk" is ONE k-block (32 k): its 8 cross-term MMAs (hi*lo, lo*hi) are issued FIRST into the fresh chunk
+//     accumulator, while it only holds values 2^-11 of the final size (their truncation is then negligible),
+//     followed by the 4 hi*hi MMAs;
+//   * the epilogue warps drain every finished chunk into FP32 REGISTERS (round-to-nearest adds) while the next
+//     chunk runs in the other TMEM buffer.
+// k_tc_gemm_x3 (this kernel, 128-column tiles: 128 x 128 per CTA, or 256 x 128 per CTA pair with cta_group::2) and
+// k_tc_gemm_x3w (256 x 256 pair tiles, below) issue the SAME instruction sequence per output element, so a
+// product's value does not depend on which of them the row count selects: a patch's result is bit-identical
+// wherever it sits in a batch (tests/test_gpu_scale.py).
+// TMEM: 2 chunk buffers x 128 columns.  Warps: 0 TMA, 1 MMA issue, 2-9 epilogue (64 columns of one lane quadrant
+// each: 64 running sums per thread), 10-13 converters (lo = v - tf32(v) over each landed stage, see x3_split_stage).
 // =============================================================================================
 template <bool CTA2> struct X3Cfg {
   static constexpr int BN = 128;
@@ -761,16 +764,14 @@ k_tc_gemm_x3(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t stg_base = base + S * STAGE;
   const uint32_t bars = stg_base + 8 * 4096;
-  // full[S] empty[S] conv[S] | cfull[2] cempty[2] xfull[2] xempty[2] | tmem slot | add[8]
+  // full[S] empty[S] conv[S] | cfull[2] cempty[2] | tmem slot | add[8]
   auto full_bar = [&](int s) { return bars + 8u * s; };
   auto empty_bar = [&](int s) { return bars + 8u * (S + s); };
   auto conv_bar = [&](int s) { return bars + 8u * (2 * S + s); };
   auto cfull_bar = [&](int b) { return bars + 8u * (3 * S + b); };
   auto cempty_bar = [&](int b) { return bars + 8u * (3 * S + 2 + b); };
-  auto xfull_bar = [&](int b) { return bars + 8u * (3 * S + 4 + b); };
-  auto xempty_bar = [&](int b) { return bars + 8u * (3 * S + 6 + b); };
-  const uint32_t tmem_slot = bars + 8u * (3 * S + 8);
-  const uint32_t add_bar0 = bars + 8u * (3 * S + 9);
+  const uint32_t tmem_slot = bars + 8u * (3 * S + 4);
+  const uint32_t add_bar0 = bars + 8u * (3 * S + 5);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = CTA2 ? cluster_ctarank() : 0u;
@@ -779,23 +780,22 @@ k_tc_gemm_x3(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   const int splits = (p.K + p.k_chunk - 1) / p.k_chunk;
   const int total = gm * gn * splits;
   const int cid = CTA2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x, ncl = CTA2 ? (int)(gridDim.x >> 1) : (int)gridDim.x;
-  const int CH = p.x3_chunk;                                       // k-blocks per chunk accumulator
   const int dbg = p.x3_inplace;                                    // DX_X3_DBG experiment switches (results are wrong when set)
   const bool trace = p.dbg && blockIdx.x == 0;                     // DX_TC_DEBUG: clock64() stamps of the first 40 k-blocks of CTA 0
   if (trace && threadIdx.x == 0) p.dbg[250] = clock64();
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < S; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); mbar_init(conv_bar(s), (CTA2 ? 2 : 1) * X3_WARPS); }
-    for (int b = 0; b < 2; ++b) { mbar_init(cfull_bar(b), 1); mbar_init(cempty_bar(b), NEPI); mbar_init(xfull_bar(b), 1); mbar_init(xempty_bar(b), NEPI); }
+    for (int b = 0; b < 2; ++b) { mbar_init(cfull_bar(b), 1); mbar_init(cempty_bar(b), NEPI); }
     for (int w = 0; w < 8; ++w) mbar_init(add_bar0 + 8u * w, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
     if (CTA2) {
-      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(512) : "memory");
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(256) : "memory");
       asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
     } else {
-      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(512) : "memory");
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(256) : "memory");
       asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
   }
@@ -849,44 +849,40 @@ k_tc_gemm_x3(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       auto mma = [&](uint32_t d, uint64_t ad, uint64_t bd, uint32_t acc) {
         if (CTA2) umma_tf32_2sm(d, ad, bd, idesc, acc); else umma_tf32(d, ad, bd, idesc, acc);
       };
-      uint32_t it = 0, lt = 0, gc = 0;                             // stage, tile and chunk counters
-      for (int t = cid; t < total; t += ncl, ++lt) {
+      uint32_t it = 0;                                             // k-block counter: stage it % S, chunk buffer it & 1
+      for (int t = cid; t < total; t += ncl) {
         int m0, n0, kbeg, nkb; tile_coords(t, m0, n0, kbeg, nkb);
-        const uint32_t xb = lt & 1;
-        wait_leader(xempty_bar(xb), ((lt >> 1) & 1) ^ 1);          // cross accumulator of tile lt-2 has been read
-        const uint32_t tcross = tmem_base + 256 + xb * BN;
-        for (int kb0 = 0; kb0 < nkb; kb0 += CH, ++gc) {
-          const uint32_t cb = gc & 1;
-          wait_leader(cempty_bar(cb), ((gc >> 1) & 1) ^ 1);        // chunk accumulator drained
+        for (int kb = 0; kb < nkb; ++kb, ++it) {
+          const int s = it % S;
+          const uint32_t cb = it & 1;
+          wait_leader(cempty_bar(cb), ((it >> 1) & 1) ^ 1);        // chunk accumulator drained
+          wait_leader(conv_bar(s), (it / S) & 1);                  // raw tiles landed and lo tiles written, both CTAs
+          if (trace && it < 40) p.dbg[120 + it] = clock64();
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-          const uint32_t tmain = tmem_base + cb * BN;
-          const int kb1 = min(nkb, kb0 + CH);
-          for (int kb = kb0; kb < kb1; ++kb, ++it) {
-            const int s = it % S;
-            wait_leader(conv_bar(s), (it / S) & 1);                // raw tiles landed and lo tiles written, both CTAs
-            if (trace && it < 40) p.dbg[120 + it] = clock64();
-            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            const uint32_t sa = base + s * STAGE, sb = sa + A_BYTES;
+          const uint32_t tacc = tmem_base + cb * BN;
+          const uint32_t sa = base + s * STAGE, sb = sa + A_BYTES;
+          uint64_t ad[4], bd[4];
 #pragma unroll
-            for (int k = 0; k < TBK / 8; ++k) {
-              const uint32_t oa = A_MN ? sa + k * 1024 : sa + k * 32, ob = B_MN ? sb + k * 1024 : sb + k * 32;
-              const uint64_t ad = A_MN ? umma_desc(oa, 4096, 512, 1) : umma_desc(oa, 16, 1024, 2);
-              const uint64_t bd = B_MN ? umma_desc(ob, 4096, 512, 1) : umma_desc(ob, 16, 1024, 2);
-              const uint64_t adl = A_MN ? umma_desc(oa + RAW, 4096, 512, 1) : umma_desc(oa + RAW, 16, 1024, 2);
-              const uint64_t bdl = B_MN ? umma_desc(ob + RAW, 4096, 512, 1) : umma_desc(ob + RAW, 16, 1024, 2);
-              if (dbg & 16) continue;
-              if (!(dbg & 2)) {
-                mma((dbg & 4) ? tmain : tcross, ad, bdl, ((dbg & 4) ? (kb != kb0 || k != 0) : (kb | k) != 0) ? 1u : 0u);   // hi * lo
-                mma((dbg & 4) ? tmain : tcross, adl, bd, 1u);      // lo * hi
-                mma(tmain, ad, bd, ((dbg & 4) || kb != kb0 || k != 0) ? 1u : 0u);   // hi * hi, fresh accumulator per chunk
-              } else
-              mma(tmain, ad, bd, (kb != kb0 || k != 0) ? 1u : 0u); // hi * hi, fresh accumulator per chunk
-            }
-            commit(empty_bar(s));
+          for (int k = 0; k < 4; ++k) {
+            const uint32_t oa = A_MN ? sa + k * 1024 : sa + k * 32, ob = B_MN ? sb + k * 1024 : sb + k * 32;
+            ad[k] = A_MN ? umma_desc(oa, 4096, 512, 1) : umma_desc(oa, 16, 1024, 2);
+            bd[k] = B_MN ? umma_desc(ob, 4096, 512, 1) : umma_desc(ob, 16, 1024, 2);
           }
+          constexpr uint64_t LO = (uint64_t)(RAW >> 4);            // the lo tiles sit RAW bytes after the raw ones (16-byte units)
+          if (!(dbg & 16)) {
+            if (!(dbg & 2)) {
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {                        // cross terms first, into the still tiny accumulator
+                mma(tacc, ad[k], bd[k] + LO, k != 0 ? 1u : 0u);    // hi * lo
+                mma(tacc, ad[k] + LO, bd[k], 1u);                  // lo * hi
+              }
+            }
+#pragma unroll
+            for (int k = 0; k < 4; ++k) mma(tacc, ad[k], bd[k], ((dbg & 2) && k == 0) ? 0u : 1u);   // hi * hi
+          }
+          commit(empty_bar(s));
           commit(cfull_bar(cb));
         }
-        commit(xfull_bar(xb));
       }
     }
   } else if (warp < 10) {                                          // ---- epilogue: warps 2..9
@@ -894,16 +890,16 @@ k_tc_gemm_x3(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     EpiWarp w{stg_base + (uint32_t)ew * 4096u, add_bar0 + 8u * ew, 0u, lane, lane >> 3, lane & 7,
               ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0) && (p.ldc % 4 == 0)};
     const uint32_t tlane = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(half * 64);
-    uint32_t lt = 0, gc = 0;
-    for (int t = cid; t < total; t += ncl, ++lt) {
+    uint32_t it = 0;
+    for (int t = cid; t < total; t += ncl) {
       int m0, n0, kbeg, nkb; tile_coords(t, m0, n0, kbeg, nkb);
       float a0[32], a1[32];
 #pragma unroll
       for (int j = 0; j < 32; ++j) { a0[j] = 0.f; a1[j] = 0.f; }
-      for (int kb0 = 0; kb0 < nkb; kb0 += CH, ++gc) {
-        const uint32_t cb = gc & 1;
-        mbar_wait(cfull_bar(cb), (gc >> 1) & 1);
-        if (trace && threadIdx.x == 64 && gc < 20) p.dbg[160 + gc] = clock64();
+      for (int kb = 0; kb < nkb; ++kb, ++it) {
+        const uint32_t cb = it & 1;
+        mbar_wait(cfull_bar(cb), (it >> 1) & 1);
+        if (trace && threadIdx.x == 64 && it < 20) p.dbg[160 + it] = clock64();
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         if (!(dbg & 8)) {
           float v[32];                                             // (32 columns at a time: 64 sums + 32 loaded values live)
@@ -917,24 +913,7 @@ k_tc_gemm_x3(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         __syncwarp();
         if (lane == 0) arrive_leader(cempty_bar(cb));
-        if (trace && threadIdx.x == 64 && gc < 20) p.dbg[180 + gc] = clock64();
-      }
-      {
-        const uint32_t xb = lt & 1;
-        mbar_wait(xfull_bar(xb), (lt >> 1) & 1);
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        {
-          float v[32];
-          tmem_ld32(tlane + 256 + xb * BN, v);
-#pragma unroll
-          for (int j = 0; j < 32; ++j) a0[j] += v[j];
-          tmem_ld32(tlane + 256 + xb * BN + 32, v);
-#pragma unroll
-          for (int j = 0; j < 32; ++j) a1[j] += v[j];
-        }
-        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-        __syncwarp();
-        if (lane == 0) arrive_leader(xempty_bar(xb));
+        if (trace && threadIdx.x == 64 && it < 20) p.dbg[180 + it] = clock64();
       }
       const int gj = n0 + half * 64;
       if (gj < p.N) epi_cols32(p, &tmC, &tmAdd, a0, gj, m0 + q * 32, w);
@@ -963,8 +942,8 @@ k_tc_gemm_x3(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   if (CTA2) cluster_sync_all(); else __syncthreads();
   if (warp == 1) {
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    if (CTA2) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
-    else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+    if (CTA2) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(256) : "memory");
+    else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(256) : "memory");
   }
 }
 
@@ -1290,7 +1269,9 @@ bool launch_tc(dx_stream_t s, const GemmP& g) {
   // out through TMA reduce-add; a plain store becomes zero-fill + reduce-add.  (No bias / added matrix: they would be
   // applied once per split; the relu gate is a 0/1 factor and distributes over the partial sums.)
   int accum = g.accum;
-  if (g.accum != ACC_ATOMIC && tma_store && gm * gn < 48 && g.K >= 512 && !g.bias && (!g.add || g.act == ACT_GATE) &&
+  // Forward products (both operands K-major) are never split: the split count depends on the row count, and a patch's
+  // inference result must not depend on how many other patches share its batch.
+  if (g.accum != ACC_ATOMIC && !(g.a_kc && g.b_kc) && tma_store && gm * gn < 48 && g.K >= 512 && !g.bias && (!g.add || g.act == ACT_GATE) &&
       (g.act == ACT_NONE || g.act == ACT_GATE) && !getenv("DX_TC_NO_SMALL_SPLIT")) {
     const int want = 96 / (gm * gn), maxs = g.K / 256;
     splits = want < 1 ? 1 : (want > maxs ? maxs : want);
@@ -1424,9 +1405,9 @@ bool launch_x3(dx_stream_t s, const GemmP& g) {
     const int want = (2 * ncta) / (gm * gn);                    // two rounds of the persistent grid
     const int maxs = (g.K + TBK * 16 - 1) / (TBK * 16);        // >= 512 reduction rows per split
     splits = want < 1 ? 1 : (want > maxs ? maxs : want);
-  } else if (!CTA2 && tma_store && gm * gn < 48 && g.K >= 512 && !g.bias && (!g.add || g.act == ACT_GATE) &&
+  } else if (!CTA2 && !(g.a_kc && g.b_kc) && tma_store && gm * gn < 48 && g.K >= 512 && !g.bias && (!g.add || g.act == ACT_GATE) &&
              (g.act == ACT_NONE || g.act == ACT_GATE)) {
-    // few-row products with a long reduction: split it so that more SMs stream the weight matrix (see launch_tc)
+    // few-row dgrads with a long reduction: split it so that more SMs stream the weight matrix (see launch_tc)
     const int want = 96 / (gm * gn), maxs = g.K / 256;
     splits = want < 1 ? 1 : (want > maxs ? maxs : want);
     if (splits > 1) {

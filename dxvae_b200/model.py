@@ -73,15 +73,13 @@ class DXVAE(nn.Module):
         self.last_quant_margins = None
         self.last_loss5 = None      # device tensor (total, x0, xi, e, kld*w) of the latest forward()
         self._last_gflat = None     # flat gradient blob the latest backward() handed out views of
-        # arithmetic of the training products: "fp32" (FFMA), "3xtf32" (tcgen05 tensor cores with
-        # error-compensated hi/lo operands: FP32-accurate, meets the reference tolerance) or "tf32"
-        # (plain tensor-core TF32, looser stated tolerance)
-        self.precision = "fp32"
-        # inference encode: "fp32" (default, reference-tolerance latents) or "tf32" (tensor cores,
-        # latents within the looser TF32 bound of tests/test_gpu_tf32.py); greedy decode is always fp32
-        self.encode_precision = "fp32"
-        # greedy decode: "fp32" (FFMA) or "3xtf32" (error-compensated tensor-core products, FP32-accurate)
-        self.decode_precision = "fp32"
+        # arithmetic of the dense products, per entry point: "3xtf32" (default: tcgen05 tensor cores with error-compensated
+        # hi/lo operand splits and chunked FP32 accumulation — FP32-accurate, meets the reference tolerances of
+        # tests/test_gpu_parity.py), "fp32" (FFMA kernels) or, for training and encode only, "tf32" (plain tensor-core
+        # TF32 under the looser stated bounds of tests/test_gpu_tf32.py)
+        self.precision = "3xtf32"          # forward / loss / backward (training)
+        self.encode_precision = "3xtf32"   # inference encode
+        self.decode_precision = "3xtf32"   # greedy decode ("fp32" or "3xtf32": its discrete outputs need FP32 accuracy)
         # skip teacher-forced re-propagates that add no edge (exact; see dxvae_batch_steps)
         self.compact_steps = True
         if checkpoint is not None:

@@ -1,0 +1,116 @@
+"""BASELINE config 1 (encode + decode of DX_data/DXDataset.bin with a TRAINED model) against the reference's own outputs.
+
+`checkpoints/dx_1024.chk` is not in the reference tree; oracle/make_trained_golden.py trains the unmodified reference,
+stores the model as tests/golden/trained_q8.npz (int8 rows + fp32 scales; the dequantised weights are the pinned model)
+and the reference's outputs for it on all 1024 dataset graphs as tests/golden/trained_golden.npz.
+
+  not gpu: the oracle reproduces the reference's outputs on a subset (keeps the oracle pinned on trained weights)
+  gpu:     the CUDA path on ALL 1024 graphs, FFMA and 3xTF32 arithmetic: latents <= 1e-5, the five loss terms rel <= 1e-5,
+           all 53 gradient tensors (sampled entries <= 1e-4 of the float64 evaluation, relu-kink aware; norms), greedy decode of z = mu exact on every graph whose decision margins
+           exceed MARGIN and at most one quantisation step away on a handful of parameters elsewhere.
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import dxvae_oracle as O
+from tests import util
+
+TOL_LAT, TOL_LOSS, TOL_GRAD, MARGIN = 1e-5, 1e-5, 1e-4, 2e-5
+
+
+def trained_state_dict():
+    z = np.load(os.path.join(util.GOLDEN, "trained_q8.npz"))
+    sd = {}
+    for k in z.keys():
+        if k.endswith(".q"):
+            sd[k[:-2]] = torch.from_numpy(z[k].astype(np.float32) * z[k[:-2] + ".s"][:, None].astype(np.float32))
+        elif not k.endswith(".s"):
+            sd[k] = torch.from_numpy(np.asarray(z[k], np.float32))
+    return sd
+
+
+@pytest.fixture(scope="module")
+def tg():
+    return np.load(os.path.join(util.GOLDEN, "trained_golden.npz"))
+
+
+def test_oracle_reproduces_the_reference_on_trained_weights(tg):
+    idx = list(range(0, 1024, 32))
+    X, P, E, A = util.dataset_graphs(idx)
+    o = O.OracleDXVAE(); o.load_state_dict(trained_state_dict())
+    with torch.no_grad():
+        mu, sd = o.encode(X, A)
+        assert np.abs(mu.numpy() - tg["mu"][idx]).max() <= 1e-6 and np.abs(sd.numpy() - tg["std"][idx]).max() <= 1e-6
+        Xo, Po, Ao, mg = o.decode(torch.from_numpy(tg["mu"][idx]), return_margins=True)
+    ok = tg["dec_minmargin"][idx] > MARGIN
+    assert ok.sum() >= 0.9 * len(idx)
+    assert np.array_equal(Ao.numpy()[ok], tg["dec_adj"][idx][ok])
+    assert np.array_equal(Po.numpy().astype(np.int32)[ok], tg["dec_params"][idx].astype(np.int32)[ok])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("prec", ["fp32", "3xtf32"])
+def test_cfg1_all_1024_graphs_match_the_reference(tg, prec):
+    from dxvae_b200 import DXVAE
+    from dxvae_b200.dxdata import DXGraph
+    idx = list(range(1024))
+    X, P, E, A = util.dataset_graphs(idx)
+    G = [DXGraph(X[i], P[i], *E[i]) for i in idx]
+    m = DXVAE(); m.load_state_dict(trained_state_dict()); m.verbose = False
+    m.precision = prec; m.encode_precision = prec; m.decode_precision = prec
+    # ---- encode (model.py:200-212)
+    with torch.no_grad():
+        q = m.encode(G)
+    mu, sd = q.loc.cpu().numpy(), q.scale.cpu().numpy()
+    print(prec, "latent err", np.abs(mu - tg["mu"]).max(), np.abs(sd - tg["std"]).max())
+    assert np.abs(mu - tg["mu"]).max() <= TOL_LAT and np.abs(sd - tg["std"]).max() <= TOL_LAT
+    # ---- greedy decode of z = mu (model.py:214-253), tie-aware on every discrete decision
+    gb = m.decode(torch.from_numpy(tg["mu"]))
+    qm = m.last_quant_margins.cpu().numpy()
+    ok = (tg["dec_minmargin"] > MARGIN) & (qm > MARGIN)
+    # (a graph has ~140 quantised parameters, so its smallest distance to a rounding tie is often below MARGIN)
+    print(prec, "decode: compared %d of 1024 graphs exactly" % ok.sum())
+    assert ok.sum() >= 0.6 * 1024
+    Ad = util.adj_from_masks(gb.adj.cpu().numpy().view(np.uint64))
+    Pd = gb.params.cpu().numpy().astype(np.int32)
+    assert np.array_equal(Ad[ok], tg["dec_adj"][ok])
+    assert np.array_equal(Pd[ok], tg["dec_params"].astype(np.int32)[ok])
+    assert np.abs(gb.X.cpu().numpy() - tg["dec_X"])[ok].max() <= 1e-6
+    # the graphs left out sit on a tie somewhere: where their topology agrees, a parameter may land on the other side
+    # of its tie (one quantisation step), nothing more
+    same = (Ad == tg["dec_adj"]).reshape(1024, -1).all(1)
+    assert same.mean() >= 0.995
+    dP = np.abs(Pd - tg["dec_params"].astype(np.int32))[same]
+    print(prec, "decode: %d of %d parameters differ over all graphs with the reference's topology, max step %d"
+          % ((dP > 0).sum(), dP.size, dP.max()))
+    assert (dP > 0).mean() <= 1e-3
+    # ---- ELBO terms and gradients for the reference's noise (model.py:270-372, :385)
+    torch.manual_seed(int(tg["eps_seed"]))
+    eps = torch.randn(1024, 128)
+    m.zero_grad()
+    out = m.forward(G, eps=eps)
+    for a, c in zip(out, tg["loss"]):
+        assert abs(a.item() - c) <= TOL_LOSS * abs(c) + 1e-7, (a.item(), c)
+    out[0].backward()
+    # Yardstick: the float64 evaluation of the same function (the fp32 reference is within grad_ref_noise ~ 3e-6 of it).
+    # Relu kinks: the batch holds 1024 x 21 x 2048 edge-head units, and a unit whose pre-activation is within rounding of
+    # zero contributes or not depending on the last bit — a step of one graph's share (~1/1024 of an entry) that is not
+    # an arithmetic error.  So per tensor: all sampled entries within TOL_GRAD except at most two, and those within a
+    # few graphs' shares; the tensor norm within 3e-4.
+    named = dict(m.named_parameters())
+    worst, kinks = 0.0, 0
+    for k, n in enumerate(tg["grad_names"]):
+        g = named[str(n)].grad.cpu().flatten()
+        vals = g[torch.from_numpy(tg["grad_idx"][k])].double().numpy()
+        scale = np.abs(g.numpy()).max() + 1e-30
+        errs = np.sort(np.abs(vals - tg["grad64_vals"][k]) / scale)
+        worst = max(worst, errs[-3])
+        kinks += int((errs > TOL_GRAD).sum())
+        assert errs[-3] <= TOL_GRAD and errs[-1] <= 4.0 / 1024, (n, errs[-3:])
+        assert abs(g.double().norm().item() - tg["grad64_norms"][k]) <= 3e-4 * tg["grad64_norms"][k] + 1e-12, n
+    print(prec, "gradients vs float64: worst (third-largest per tensor) %.2e, entries on a relu kink %d of %d"
+          % (worst, kinks, 48 * len(tg["grad_names"])))
+    assert kinks <= 6

@@ -33,12 +33,16 @@ def golden():
     return np.load(os.path.join(util.GOLDEN, "model_golden.npz"))
 
 
-def make_model(seed, gain):
+def make_model(seed, gain, prec="fp32"):
+    """The tests of this file pin the FFMA arithmetic unless they say otherwise (the class default is the FP32-accurate
+    tensor-core mode "3xtf32": covered here where a test is parametrised over `prec`, by tests/test_gpu_tf32.py,
+    tests/test_cfg1_trained.py, the 1 M-patch tests of tests/test_gpu_scale.py and smoke())."""
     from dxvae_b200 import DXVAE
     o = O.make_weights(seed, gain)
     m = DXVAE()
     m.load_state_dict(o.state_dict())
     m.verbose = False
+    m.precision = m.encode_precision = m.decode_precision = prec
     return m, o
 
 
@@ -157,11 +161,18 @@ def _graphs(X, P, E):
     return [DXGraph(X[i], P[i], *E[i]) for i in range(len(E))]
 
 
+def test_class_defaults_are_the_fp32_accurate_tensor_core_mode(lib):
+    from dxvae_b200 import DXVAE
+    m = DXVAE()
+    assert (m.precision, m.encode_precision, m.decode_precision) == ("3xtf32", "3xtf32", "3xtf32")
+
+
+@pytest.mark.parametrize("prec", ["fp32", "3xtf32"])
 @pytest.mark.parametrize("tag,gain", [("init", 1.0), ("stress", 3.0)])
-def test_encode_matches_oracle_and_reference_golden(lib, golden, tag, gain):
+def test_encode_matches_oracle_and_reference_golden(lib, golden, tag, gain, prec):
     idx, X, P, E, A = _encode_cases()
     assert list(golden["subset"]) == idx
-    m, o = make_model(0, gain)
+    m, o = make_model(0, gain, prec)
     with torch.no_grad():
         q = m.encode(_graphs(X, P, E))
         mu_o, sd_o = o.encode(X, A)
@@ -311,8 +322,7 @@ def test_decode_matches_oracle_and_reference_golden(lib, golden, tag, gain, prec
     tensor cores).  Tie-aware on EVERY discrete decision: a graph is compared when its smallest edge-logit margin (from
     the reference run) and its smallest quantiser margin (reported by the kernel: distance of a parameter logit to a
     rounding / sigmoid / arg-max tie) both exceed MARGIN."""
-    m, o = make_model(0, gain)
-    m.decode_precision = prec
+    m, o = make_model(0, gain, prec)
     for zt in ("mu", "prior"):
         z = torch.from_numpy(golden["%s_dec_%s_z" % (tag, zt)])
         gb = m.decode(z)
