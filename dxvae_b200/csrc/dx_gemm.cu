@@ -289,6 +289,66 @@ __global__ void __launch_bounds__(256) k_colsum(int M, int N, const float* __res
   }
 }
 
+// dW[MO, N] += dy[:, :MO]^T x  for MO = 1 or 2 output rows (the second layer of the edge heads: h_to_edge_self.2 is
+// (1, 1024), h_to_edge.2 is (2, 2048)): a dy-weighted column sum of x.  A GEMM tile would run 1 or 2 of its 128 rows;
+// this streams x once (HBM-bound).  Thread = 4 consecutive columns x 4 row lanes; grid.y splits the rows.
+template <int MO>
+__global__ void __launch_bounds__(256) k_wcolsum(int M, int N, const float* __restrict__ dy, int64_t lddy,
+                                                 const float* __restrict__ x, int64_t ldx, float* __restrict__ dW, int64_t lddw,
+                                                 int rows_per) {
+  __shared__ float4 red[3][MO][64];
+  const int tc = threadIdx.x & 63, lane_r = threadIdx.x >> 6;
+  const int c = (blockIdx.x * 64 + tc) * 4;
+  const int r0 = blockIdx.y * rows_per, r1 = min(M, r0 + rows_per);
+  float4 acc[MO];
+#pragma unroll
+  for (int o = 0; o < MO; ++o) acc[o] = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (c < N) {
+#pragma unroll 4
+    for (int r = r0 + lane_r; r < r1; r += 4) {
+      const float4 v = *reinterpret_cast<const float4*>(x + (int64_t)r * ldx + c);
+#pragma unroll
+      for (int o = 0; o < MO; ++o) {
+        const float d = __ldg(dy + (int64_t)r * lddy + o);
+        acc[o].x = fmaf(d, v.x, acc[o].x); acc[o].y = fmaf(d, v.y, acc[o].y);
+        acc[o].z = fmaf(d, v.z, acc[o].z); acc[o].w = fmaf(d, v.w, acc[o].w);
+      }
+    }
+  }
+  if (lane_r > 0) {
+#pragma unroll
+    for (int o = 0; o < MO; ++o) red[lane_r - 1][o][tc] = acc[o];
+  }
+  __syncthreads();
+  if (lane_r == 0 && c < N) {
+#pragma unroll
+    for (int o = 0; o < MO; ++o) {
+      const float4 a = red[0][o][tc], b = red[1][o][tc], d = red[2][o][tc];
+      float* dst = dW + (int64_t)o * lddw + c;
+      atomicAdd(dst, acc[o].x + a.x + b.x + d.x); atomicAdd(dst + 1, acc[o].y + a.y + b.y + d.y);
+      atomicAdd(dst + 2, acc[o].z + a.z + b.z + d.z); atomicAdd(dst + 3, acc[o].w + a.w + b.w + d.w);
+    }
+  }
+}
+// eligible: wgrad form without row lists, 1 or 2 output rows, 16-byte aligned x rows, N a multiple of 4
+bool wcolsum(dx_stream_t s, const GemmP& p) {
+  if (p.a_kc || p.b_kc || p.accum != ACC_ATOMIC || p.M > 2 || p.a_idx || p.b_idx || p.c_idx || p.bias || p.add || p.act != ACT_NONE)
+    return false;
+  if (!aligned16(p.B) || (p.ldb % 4) || (p.N % 4)) return false;
+  const int rows = p.K;                                        // the reduction runs over the batch rows
+  const int gx = (p.N / 4 + 63) / 64;
+  int gy = (148 * 8 + gx - 1) / gx;
+  const int maxy = (rows + 63) / 64;
+  if (gy > maxy) gy = maxy;
+  if (gy < 1) gy = 1;
+  const int rows_per = (rows + gy - 1) / gy;
+  gy = (rows + rows_per - 1) / rows_per;
+  if (p.M == 1) k_wcolsum<1><<<dim3(gx, gy), 256, 0, s>>>(rows, p.N, p.A, p.lda, p.B, p.ldb, p.C, p.ldc, rows_per);
+  else k_wcolsum<2><<<dim3(gx, gy), 256, 0, s>>>(rows, p.N, p.A, p.lda, p.B, p.ldb, p.C, p.ldc, rows_per);
+  ++g_launches;
+  return true;
+}
+
 }  // namespace
 
 void prof_begin(int max_launches) {
@@ -340,7 +400,8 @@ void gemm(dx_stream_t s, const GemmP& p) {
   // Large tile when both output extents fill it; otherwise 64x64 so small batches
   // (B=128) and narrow heads (N=27/55/2/1) still spread over the SMs.
   const bool big = (p.M >= 512 && p.N >= 96);
-  if (g_precision == PREC_3XTF32 && tc_gemm(s, p, nullptr, true)) cls = 2;
+  if (g_precision != PREC_FP32 && wcolsum(s, p)) cls = 1;        // (the FFMA mode keeps its one kernel family: bit-stable parity path)
+  else if (g_precision == PREC_3XTF32 && tc_gemm(s, p, nullptr, true)) cls = 2;
   else if (g_precision == PREC_TF32 && tc_gemm(s, p, nullptr)) cls = 2;
   else if (big) { launch_tile<128, 128, 8, 8>(s, p); cls = 0; }
   else { launch_tile<64, 64, 4, 4>(s, p); cls = 1; }

@@ -742,22 +742,26 @@ k_tc_gemm2(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
 // TMEM: 2 chunk buffers x 128 columns.  Warps: 0 TMA, 1 MMA issue, 2-9 epilogue (64 columns of one lane quadrant
 // each: 64 running sums per thread), 10-13 converters (lo = v - tf32(v) over each landed stage, see x3_split_stage).
 // =============================================================================================
-template <bool CTA2> struct X3Cfg {
-  static constexpr int BN = 128;
-  static constexpr int BROWS = CTA2 ? 64 : 128;                    // B rows staged by one CTA
-  static constexpr int RAW = A_BYTES + BROWS * TBK * 4;            // 24 KB / 32 KB
+// BNT = 32: narrow tiles for the thin products of the path (the 27 / 55-column parameter heads, the 32-column padded
+// weight_ih gradients): a 128-column tile spends 3/4 of its MMAs on padding there.
+template <bool CTA2, int BNT = 128> struct X3Cfg {
+  static_assert(BNT == 128 || (BNT == 32 && !CTA2), "tile widths: 128, or 32 on single CTAs");
+  static constexpr int BN = BNT;
+  static constexpr int BROWS = CTA2 ? BN / 2 : BN;                 // B rows staged by one CTA
+  static constexpr int RAW = A_BYTES + BROWS * TBK * 4;            // 24 KB / 32 KB (20 KB for the narrow tile)
   static constexpr int STAGE = 2 * RAW;
-  static constexpr int S = CTA2 ? 4 : 3;
+  static constexpr int S = (BNT == 32 || CTA2) ? 4 : 3;
   static constexpr int THREADS = 320 + 32 * X3_WARPS;
   static constexpr int SMEM = S * STAGE + 1024 + 8 * 4096 + 256;
 };
 
-template <bool A_MN, bool B_MN, bool CTA2>
-__global__ void __launch_bounds__(X3Cfg<CTA2>::THREADS, 1)
+template <bool A_MN, bool B_MN, bool CTA2, int BNT = 128>
+__global__ void __launch_bounds__(X3Cfg<CTA2, BNT>::THREADS, 1)
 k_tc_gemm_x3(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
              const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmAdd, const TcParams p) {
-  using Cfg = X3Cfg<CTA2>;
+  using Cfg = X3Cfg<CTA2, BNT>;
   constexpr int BN = Cfg::BN, S = Cfg::S, RAW = Cfg::RAW, STAGE = Cfg::STAGE, BROWS = Cfg::BROWS;
+  constexpr int WC = BN == 128 ? 64 : 32;                          // columns drained by one epilogue warp (narrow tile: warps 2-5 only)
   constexpr int TM = CTA2 ? 256 : 128;                             // rows of the (pair) tile
   constexpr uint32_t NEPI = CTA2 ? 16 : 8;                         // epilogue warps reporting to a leader barrier
   extern __shared__ uint8_t smem_raw[];
@@ -889,7 +893,8 @@ k_tc_gemm_x3(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     const int ew = warp - 2, q = warp & 3, half = ew >> 2;
     EpiWarp w{stg_base + (uint32_t)ew * 4096u, add_bar0 + 8u * ew, 0u, lane, lane >> 3, lane & 7,
               ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0) && (p.ldc % 4 == 0)};
-    const uint32_t tlane = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(half * 64);
+    const uint32_t tlane = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(half * WC);
+    const bool drains = BN == 128 || half == 0;                    // narrow tile: the second column half does not exist
     uint32_t it = 0;
     for (int t = cid; t < total; t += ncl) {
       int m0, n0, kbeg, nkb; tile_coords(t, m0, n0, kbeg, nkb);
@@ -901,23 +906,25 @@ k_tc_gemm_x3(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         mbar_wait(cfull_bar(cb), (it >> 1) & 1);
         if (trace && threadIdx.x == 64 && it < 20) p.dbg[160 + it] = clock64();
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        if (!(dbg & 8)) {
+        if (!(dbg & 8) && drains) {
           float v[32];                                             // (32 columns at a time: 64 sums + 32 loaded values live)
           tmem_ld32(tlane + cb * BN, v);
 #pragma unroll
           for (int j = 0; j < 32; ++j) a0[j] += v[j];
-          tmem_ld32(tlane + cb * BN + 32, v);
+          if (BN == 128) {
+            tmem_ld32(tlane + cb * BN + 32, v);
 #pragma unroll
-          for (int j = 0; j < 32; ++j) a1[j] += v[j];
+            for (int j = 0; j < 32; ++j) a1[j] += v[j];
+          }
         }
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         __syncwarp();
         if (lane == 0) arrive_leader(cempty_bar(cb));
         if (trace && threadIdx.x == 64 && it < 20) p.dbg[180 + it] = clock64();
       }
-      const int gj = n0 + half * 64;
-      if (gj < p.N) epi_cols32(p, &tmC, &tmAdd, a0, gj, m0 + q * 32, w);
-      if (gj + 32 < p.N) epi_cols32(p, &tmC, &tmAdd, a1, gj + 32, m0 + q * 32, w);
+      const int gj = n0 + half * WC;
+      if (drains && gj < p.N) epi_cols32(p, &tmC, &tmAdd, a0, gj, m0 + q * 32, w);
+      if (BN == 128 && gj + 32 < p.N) epi_cols32(p, &tmC, &tmAdd, a1, gj + 32, m0 + q * 32, w);
     }
     if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
     __syncwarp();
@@ -1391,9 +1398,9 @@ bool launch_tc2(dx_stream_t s, const GemmP& g) {
 }
 
 // Chunked 3xTF32 launch (k_tc_gemm_x3): CTA2 = pair tiles 256 x 128, else 128 x 128.  Returns false if not applicable.
-template <bool CTA2>
+template <bool CTA2, int BNT = 128>
 bool launch_x3(dx_stream_t s, const GemmP& g) {
-  using Cfg = X3Cfg<CTA2>;
+  using Cfg = X3Cfg<CTA2, BNT>;
   constexpr int TM = CTA2 ? 256 : 128, BN = Cfg::BN;
   const int num_sms = sm_count();
   const int ncta = CTA2 ? num_sms / 2 : num_sms;               // concurrent tiles
@@ -1440,10 +1447,10 @@ bool launch_x3(dx_stream_t s, const GemmP& g) {
              m_fast ? 0 : 1, x3_dbg(), x3_chunk(), tc_prefetch(), want_dbg ? dbg : nullptr};
   static AttrOnce attr;
   attr([] {
-    cudaFuncSetAttribute(k_tc_gemm_x3<false, false, CTA2>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM);
-    cudaFuncSetAttribute(k_tc_gemm_x3<false, true, CTA2>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM);
-    cudaFuncSetAttribute(k_tc_gemm_x3<true, true, CTA2>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM);
-    cudaFuncSetAttribute(k_tc_gemm_x3<true, false, CTA2>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM);
+    cudaFuncSetAttribute(k_tc_gemm_x3<false, false, CTA2, BNT>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM);
+    cudaFuncSetAttribute(k_tc_gemm_x3<false, true, CTA2, BNT>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM);
+    cudaFuncSetAttribute(k_tc_gemm_x3<true, true, CTA2, BNT>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM);
+    cudaFuncSetAttribute(k_tc_gemm_x3<true, false, CTA2, BNT>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM);
   });
   const int nt = total < ncta ? total : ncta;
   dim3 grid(CTA2 ? 2 * nt : nt);
@@ -1459,10 +1466,10 @@ bool launch_x3(dx_stream_t s, const GemmP& g) {
       kern<<<grid, Cfg::THREADS, Cfg::SMEM, s>>>(ta, tb, tc, tadd, p);
     }
   };
-  if (g.a_kc && g.b_kc) run(k_tc_gemm_x3<false, false, CTA2>);
-  else if (g.a_kc && !g.b_kc) run(k_tc_gemm_x3<false, true, CTA2>);
-  else if (!g.a_kc && !g.b_kc) run(k_tc_gemm_x3<true, true, CTA2>);
-  else run(k_tc_gemm_x3<true, false, CTA2>);
+  if (g.a_kc && g.b_kc) run(k_tc_gemm_x3<false, false, CTA2, BNT>);
+  else if (g.a_kc && !g.b_kc) run(k_tc_gemm_x3<false, true, CTA2, BNT>);
+  else if (!g.a_kc && !g.b_kc) run(k_tc_gemm_x3<true, true, CTA2, BNT>);
+  else run(k_tc_gemm_x3<true, false, CTA2, BNT>);
   ++g_launches;
   if (want_dbg) {
     long long h[256];
@@ -1587,6 +1594,8 @@ bool tc_gemm(dx_stream_t s, const GemmP& g, int* tile_n, bool x3) {
       return bn == 256 ? launch_tc<256, true>(s, g) : (bn == 128 ? launch_tc<128, true>(s, g) : launch_tc<64, true>(s, g));
     }
     if (bn == 256 && launch_x3w(s, g)) return true;
+    static const bool no_narrow = getenv("DX_X3_NO_NARROW") != nullptr;
+    if (g.N <= 64 && !no_narrow) return launch_x3<false, 32>(s, g);   // thin outputs: 32-column tiles
     if (launch_x3<true>(s, g)) return true;
     return launch_x3<false>(s, g);
   }

@@ -133,7 +133,8 @@ def test_tc_gemm_x3_forward(lib, M, N, K):
 
 
 @pytest.mark.parametrize("M,N,K", [(128, 256, 64), (8192, 1536, 512), (1000, 1024, 1024), (300, 2048, 512), (4096, 512, 128),
-                                   (8192, 4, 2048), (4096, 56, 1024), (2048, 28, 1024), (32768, 1536, 32), (77, 1536, 512)])
+                                   (8192, 4, 2048), (4096, 56, 1024), (2048, 28, 1024), (32768, 1536, 32), (77, 1536, 512),
+                                   (4096, 1, 1024), (3000, 2, 2048), (5000, 27, 1024)])
 def test_tc_gemm_x3_dgrad_wgrad(lib, M, N, K):
     from dxvae_b200 import _lib
     g = torch.Generator().manual_seed(M + N + K)
