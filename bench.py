@@ -520,7 +520,7 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--micro-batch", type=int, default=32768)
+    ap.add_argument("--micro-batch", type=int, default=65536)
     ap.add_argument("--cpu-patches", type=int, default=2048, help="patches per step of the oracle-port CPU sample")
     ap.add_argument("--ref-patches", type=int, default=128, help="patches per step of the unmodified-reference CPU sample")
     ap.add_argument("--no-cpu", action="store_true")

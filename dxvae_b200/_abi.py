@@ -31,6 +31,7 @@ SIGNATURES = {
     "dxvae_voices_to_graphs": (C.c_int, [I64, P, P, P, P, P, P, P]),
     "dxvae_pack_syx": (C.c_int, [I64, P, P, P]),
     "dxvae_workspace_bytes": (SZ, [C.c_int, I64]),
+    "dxvae_workspace_bytes_sched": (SZ, [C.c_int, I64, I32, P, P]),
     "dxvae_encode_fwd": (C.c_int, [P, I64, P, P, I32, P, P, P, P, P, P, SZ, C.c_int, C.c_int, P]),
     "dxvae_reparameterize": (C.c_int, [I64, P, P, P, P, P]),
     "dxvae_decode_greedy": (C.c_int, [P, I64, P, P, P, P, P, P, SZ, C.c_int, P]),

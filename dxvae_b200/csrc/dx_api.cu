@@ -18,24 +18,24 @@ void set_error(const char* fmt, ...) {
 
 struct TrainWs { EncWs e; DecWs d; float *mu, *sd, *dmu, *dsd; };
 
-static TrainWs carve_train(Arena& ar, int64_t B) {
+static TrainWs carve_train(Arena& ar, int64_t B, int n_levels, const int32_t* level_ptr, const int32_t* step_ptr) {
   TrainWs t;
-  t.e = carve_enc(ar, B, true);
-  t.d = carve_dec(ar, B, true);
+  t.e = carve_enc(ar, B, true, n_levels, level_ptr);
+  t.d = carve_dec(ar, B, true, step_ptr);
   t.mu = ar.take<float>((size_t)B * Z); t.sd = ar.take<float>((size_t)B * Z);
   t.dmu = ar.take<float>((size_t)B * Z); t.dsd = ar.take<float>((size_t)B * Z);
   return t;
 }
 
-size_t workspace_bytes(int op, int64_t B) {
+size_t workspace_bytes(int op, int64_t B, int n_levels, const int32_t* level_ptr, const int32_t* step_ptr) {
   Arena ar(nullptr, (size_t)-1);
   switch (op) {
-    case DXVAE_OP_ENCODE: carve_enc(ar, B, false); break;
+    case DXVAE_OP_ENCODE: carve_enc(ar, B, false, n_levels, level_ptr); break;
     case DXVAE_OP_DECODE: carve_dec(ar, B, false); break;
-    case DXVAE_OP_TRAIN: carve_train(ar, B); break;
+    case DXVAE_OP_TRAIN: carve_train(ar, B, n_levels, level_ptr, step_ptr); break;
     case DXVAE_OP_SCHEDULE: ar.take<int32_t>((size_t)72 * ((B + 1023) / 1024)); break;
-    case DXVAE_OP_ENCODE_TRAIN: carve_enc(ar, B, true); break;
-    case DXVAE_OP_LOSS: carve_dec(ar, B, true); break;
+    case DXVAE_OP_ENCODE_TRAIN: carve_enc(ar, B, true, n_levels, level_ptr); break;
+    case DXVAE_OP_LOSS: carve_dec(ar, B, true, step_ptr); break;
     default: return 0;
   }
   return ar.off + 256;
@@ -47,7 +47,7 @@ int elbo_step(dx_stream_t st, const float* weights, const Batch& bt, const float
   const int B = (int)bt.B;
   PrecisionScope prec(precision);
   Arena ar(ws, ws_bytes);
-  TrainWs t = carve_train(ar, bt.B);
+  TrainWs t = carve_train(ar, bt.B, bt.n_levels, bt.level_ptr, bt.step_ptr);
   DX_CHECK(!ar.overflow, "elbo_step: workspace too small (%zu < %zu bytes)", ws_bytes, ar.off);
   Weights W(weights);
   encode_fwd_impl(st, W, bt, t.e, t.mu, t.sd, true);
@@ -81,7 +81,7 @@ int loss_step(dx_stream_t st, const float* weights, const Batch& bt, const float
   const int B = (int)bt.B;
   PrecisionScope prec(precision);
   Arena ar(ws, ws_bytes);
-  DecWs d = carve_dec(ar, bt.B, true);
+  DecWs d = carve_dec(ar, bt.B, true, bt.step_ptr);
   DX_CHECK(!ar.overflow, "loss_step: workspace too small (%zu < %zu bytes)", ws_bytes, ar.off);
   Weights W(weights);
   reparameterize(st, (int64_t)B * Z, mu, sd, eps, d.z);
@@ -104,7 +104,7 @@ int encode_bwd(dx_stream_t st, const float* weights, const Batch& bt, const floa
                const float* dsd, float* grads, void* ws, size_t ws_bytes, int precision) {
   PrecisionScope prec(precision);
   Arena ar(ws, ws_bytes);
-  EncWs e = carve_enc(ar, bt.B, true);
+  EncWs e = carve_enc(ar, bt.B, true, bt.n_levels, bt.level_ptr);
   DX_CHECK(!ar.overflow, "encode_bwd: workspace too small (%zu < %zu bytes)", ws_bytes, ar.off);
   Weights W(weights), G(grads);
   encode_bwd_impl(st, W, G, bt, e, dmu, dsd, sd);
@@ -191,6 +191,9 @@ int dxvae_pack_syx(int64_t B, const float* Pg, uint8_t* voices, void* stream) {
   return pack_syx(DX_ST(stream), B, Pg, voices);
 }
 size_t dxvae_workspace_bytes(int op, int64_t B) { return workspace_bytes(op, B); }
+size_t dxvae_workspace_bytes_sched(int op, int64_t B, int32_t n_levels, const int32_t* level_ptr_host, const int32_t* step_ptr_host) {
+  return workspace_bytes(op, B, n_levels, level_ptr_host, step_ptr_host);
+}
 
 int dxvae_encode_fwd(const float* weights, int64_t B, const float* Xn, const uint64_t* adj, int32_t n_levels,
                      const int32_t* level_ptr_host, const int32_t* level_rows, const int32_t* level_rare_host, float* mu,

@@ -16,9 +16,19 @@
 
 namespace dx {
 
-DecWs carve_dec(Arena& ar, int64_t B, bool train) {
+// step_ptr (HOST, NLIST+1; training with the compacted step schedule): the per-step buffers hold one row per ACTIVE graph
+// of the step, so they are sized by the schedule's row counts instead of B (about 30 % of the (graph, step) pairs on
+// dataset-like topologies), the self-loop propagate's gates by the self-loop rows, and a step's E1 only holds the
+// 256-byte relu bit-mask of the fused edge head.  Without it (dense replay, greedy decode) every buffer has B rows.
+DecWs carve_dec(Arena& ar, int64_t B, bool train, const int32_t* step_ptr) {
   DecWs w{};
   const size_t b = (size_t)B;
+  const bool compact = train && step_ptr != nullptr;
+  auto list_rows = [&](int list) -> size_t {
+    if (!compact) return b;
+    const size_t n = (size_t)(step_ptr[list + 1] - step_ptr[list]);
+    return n > 0 ? n : 1;
+  };
   w.z = ar.take<float>(b * Z); w.Hinit = ar.take<float>(b * H); w.Hd = ar.take<float>(7 * b * H);
   w.Pg = ar.take<float>(6 * b * 2 * H); w.Pm = ar.take<float>(6 * b * 2 * H); w.Q = ar.take<float>(6 * b * 4 * H);
   w.gh = ar.take<float>(b * G3); w.ghl0 = ar.take<float>(b * G3); w.Hrun = ar.take<float>(b * H);
@@ -32,20 +42,22 @@ DecWs carve_dec(Arena& ar, int64_t B, bool train) {
     float* shared = need ? nullptr : ar.take<float>(b * cols);
     for (int v = 0; v < 7; ++v) arr[v] = need ? ar.take<float>(b * cols) : shared;
   };
-  auto per_step = [&](float** arr, size_t cols, bool need) {
+  auto per_step = [&](float** arr, size_t cols, bool need, bool by_rows = false) {
     float* shared = need ? nullptr : ar.take<float>(b * cols);
-    for (int t = 0; t < NSTEP; ++t) arr[t] = need ? ar.take<float>(b * cols) : shared;
+    for (int t = 0; t < NSTEP; ++t) arr[t] = need ? ar.take<float>((by_rows ? list_rows(t) : b) * cols) : shared;
   };
   per_node(w.A1, 2 * H, train); per_node(w.A2, 2 * H, train); per_node(w.L, LD_L, train);
   per_node(w.gxc, G3, train); per_node(w.gxl, G3, train); per_node(w.Hc0, H, train);
   per_node(w.Hi_p1, H, train); per_node(w.Hi_p2, H, train); per_node(w.ES1, 2 * H, train); per_node(w.ls, LD_E, train);
-  per_step(w.E1, 4 * H, train); per_step(w.l2, LD_E, train); per_step(w.Hin, H, train); per_step(w.Hc, H, train);
-  per_step(w.Hi, H, train);
+  per_step(w.E1, compact ? 64 : 4 * H, train); per_step(w.l2, LD_E, train);
+  per_step(w.Hin, H, train, true); per_step(w.Hc, H, train, true); per_step(w.Hi, H, train, true);
   if (train) {
     w.g_root = ar.take<float>(b * 4 * H);
     per_node(w.dL, LD_L, true); per_node(w.g_c0, 4 * H, true); per_node(w.g_p1, 4 * H, true);
-    per_node(w.g_p2, 4 * H, true); per_node(w.dls, LD_E, true);
-    per_step(w.dl2, LD_E, true); per_step(w.g_c, 4 * H, true); per_step(w.g_l, 4 * H, true);
+    for (int v = 0; v < 7; ++v)   // second propagate: self-loop rows only when compacted (list NSTEP + v - 1)
+      w.g_p2[v] = ar.take<float>((v == 0 ? (size_t)1 : (compact ? list_rows(NSTEP + v - 1) : b)) * 4 * H);
+    per_node(w.dls, LD_E, true);
+    per_step(w.dl2, LD_E, true); per_step(w.g_c, 4 * H, true, true); per_step(w.g_l, 4 * H, true, true);
     w.rowloss = ar.take<float>(4 * b);
     w.dHd = ar.take<float>(7 * b * H); w.dPg = ar.take<float>(6 * b * 2 * H); w.dPm = ar.take<float>(6 * b * 2 * H);
     w.dQ = ar.take<float>(6 * b * 4 * H); w.dgb = nullptr;   // (gate-bias gradient: summed inside msg_bwd)

@@ -13,12 +13,19 @@
 
 namespace dx {
 
-EncWs carve_enc(Arena& ar, int64_t B, bool train) {
+// level_ptr (HOST, n_levels + 1; optional): the per-level temporaries (input / hidden gate products, gate gradients) are
+// then sized for the largest level of THIS schedule (and the B rows of the root step) instead of the 6B-row worst case.
+EncWs carve_enc(Arena& ar, int64_t B, bool train, int n_levels, const int32_t* level_ptr) {
   EncWs w{};
   const size_t R7 = (size_t)7 * B, R6 = (size_t)6 * B;
+  size_t RT = R6;                                                   // rows of a per-level temporary
+  if (level_ptr && n_levels > 0) {
+    RT = (size_t)B;
+    for (int L = 0; L < n_levels; ++L) { const size_t m = (size_t)(level_ptr[L + 1] - level_ptr[L]); if (m > RT) RT = m; }
+  }
   w.Hin = ar.take<float>(R7 * H); w.Hc = ar.take<float>(R7 * H); w.Hv = ar.take<float>(R7 * H);
   w.Pg = ar.take<float>(R7 * 2 * H); w.Pm = ar.take<float>(R7 * 2 * H);
-  w.gxc = ar.take<float>(R6 * G3); w.gxl = ar.take<float>(R6 * G3); w.gh = ar.take<float>(R6 * G3);
+  w.gxc = ar.take<float>(RT * G3); w.gxl = ar.take<float>(RT * G3); w.gh = ar.take<float>(RT * G3);
   w.XnS = ar.take<float>(R6 * XP); w.pos = ar.take<int>(R7);
   for (int k = 0; k < 3; ++k) w.WihP[k] = ar.take<float>((size_t)G3 * XP);
   if (train) {
@@ -27,8 +34,8 @@ EncWs carve_enc(Arena& ar, int64_t B, bool train) {
     w.gc = ar.take<float>(R7 * 4 * H); w.gl = ar.take<float>(R7 * 4 * H);
     w.dH = ar.take<float>(R7 * H); w.dHin = ar.take<float>(R7 * H);
     w.dPg = ar.take<float>(R6 * 2 * H); w.dPm = ar.take<float>(R6 * 2 * H); w.dgb = nullptr;
-    w.dgx = ar.take<float>(R6 * 4 * H); w.dgh = w.dgx + H; w.dgxs = nullptr;   // one D4 buffer, two views (CellBwd)
-    w.dHc = ar.take<float>(R6 * H); w.dsraw = ar.take<float>((size_t)B * Z);
+    w.dgx = ar.take<float>(RT * 4 * H); w.dgh = w.dgx + H; w.dgxs = nullptr;   // one D4 buffer, two views (CellBwd)
+    w.dHc = ar.take<float>(RT * H); w.dsraw = ar.take<float>((size_t)B * Z);
   }
   return w;
 }
@@ -178,7 +185,7 @@ void encode_bwd_impl(dx_stream_t st, const Weights& W, const Weights& G, const B
 int encode_fwd(dx_stream_t st, const float* weights, const Batch& bt, float* mu, float* std_, void* ws,
                size_t ws_bytes, int keep) {
   Arena ar(ws, ws_bytes);
-  EncWs w = carve_enc(ar, bt.B, keep != 0);
+  EncWs w = carve_enc(ar, bt.B, keep != 0, bt.n_levels, bt.level_ptr);
   DX_CHECK(!ar.overflow, "encode_fwd: workspace too small (%zu < %zu bytes)", ws_bytes, ar.off);
   Weights W(weights);
   encode_fwd_impl(st, W, bt, w, mu, std_, keep != 0);

@@ -91,8 +91,8 @@ inline void proj_wgrad(dx_stream_t st, int M, const float* dP, const float* h, f
   linear_wgrad(st, M, H, H, dP + half * H, 2 * H, h, H, dWp + half * H, 2 * H);
 }
 
-EncWs carve_enc(Arena& ar, int64_t B, bool train);
-DecWs carve_dec(Arena& ar, int64_t B, bool train);
+EncWs carve_enc(Arena& ar, int64_t B, bool train, int n_levels = 0, const int32_t* level_ptr = nullptr);
+DecWs carve_dec(Arena& ar, int64_t B, bool train, const int32_t* step_ptr = nullptr);
 void encode_fwd_impl(dx_stream_t st, const Weights& W, const Batch& bt, const EncWs& w, float* mu, float* sd, bool train);
 void encode_bwd_impl(dx_stream_t st, const Weights& W, const Weights& G, const Batch& bt, const EncWs& w,
                      const float* dmu, const float* dstd, const float* sd);
@@ -110,7 +110,7 @@ void unpad_add_wih(dx_stream_t st, const float* dWp, int K, float* dW);      // 
 void mask_features(dx_stream_t st, int64_t rows, int B, const int* row_ids, int row_base, const uint64_t* adj,
                    const float* X, float* XL);                                // XL[m] = selfloop(row) * X[m]
 
-size_t workspace_bytes(int op, int64_t B);
+size_t workspace_bytes(int op, int64_t B, int n_levels = 0, const int32_t* level_ptr = nullptr, const int32_t* step_ptr = nullptr);
 
 int encode_fwd(dx_stream_t st, const float* weights, const Batch& bt, float* mu, float* std_, void* ws, size_t ws_bytes,
                int keep);

@@ -116,9 +116,15 @@ class DXVAE(nn.Module):
             raise ValueError("precision must be 'fp32', '3xtf32' or 'tf32'")
         return self._PREC[self.precision]
 
-    def _workspace(self, op, B, fresh=False):
+    def _workspace(self, op, B, fresh=False, d=None):
+        """Caller-owned scratch for one native call.  d (a prepared batch): sized for ITS schedules — the largest encoder
+        level, the active rows of the teacher-forced steps (dxvae_workspace_bytes_sched) — instead of the worst case."""
         L = _lib.lib()
-        n = int(L.dxvae_workspace_bytes(op, B))
+        if d is not None:
+            n = int(L.dxvae_workspace_bytes_sched(op, B, d.n_levels, d.level_ptr.ctypes.data,
+                                                  None if d.step_ptr is None else d.step_ptr.ctypes.data))
+        else:
+            n = int(L.dxvae_workspace_bytes(op, B))
         if fresh:
             return torch.empty(n, dtype=torch.uint8, device="cuda")
         key = (op,)
@@ -336,7 +342,7 @@ class DXVAE(nn.Module):
         L = _lib.lib()
         if loss5 is None:
             loss5 = torch.empty(5, device="cuda")
-        ws = self._workspace(_abi.OP_TRAIN, d.B)
+        ws = self._workspace(_abi.OP_TRAIN, d.B, d=d)
         _lib.check(L.dxvae_elbo_step(
             self._flat.data_ptr(), d.B, d.Xn.data_ptr(), d.cls.data_ptr(), d.adj.data_ptr(), d.n_levels,
             d.level_ptr.ctypes.data, d.level_rows.data_ptr(), d.level_ptr[8:].ctypes.data, eps.data_ptr(), w[0], w[1], w[2],
@@ -453,7 +459,7 @@ class _LossFn(torch.autograd.Function):
         dmu = torch.empty(d.B, 128, device="cuda") if need else None
         dsd = torch.empty(d.B, 128, device="cuda") if need else None
         loss5 = torch.empty(5, device="cuda")
-        ws = model._workspace(_abi.OP_LOSS, d.B)
+        ws = model._workspace(_abi.OP_LOSS, d.B, d=d)
         _lib.check(L.dxvae_loss_step(
             model._flat.data_ptr(), d.B, d.Xn.data_ptr(), d.cls.data_ptr(), d.adj.data_ptr(), mu.data_ptr(),
             sd.data_ptr(), eps.data_ptr(), w[0], w[1], w[2], 1.0 / d.B, loss5.data_ptr(),

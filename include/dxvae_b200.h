@@ -141,6 +141,15 @@ enum { DXVAE_PREC_FP32 = 0, DXVAE_PREC_TF32 = 1, DXVAE_PREC_3XTF32 = 2 };
 enum { DXVAE_OP_ENCODE = 0, DXVAE_OP_DECODE = 1, DXVAE_OP_TRAIN = 2, DXVAE_OP_SCHEDULE = 3,
        DXVAE_OP_ENCODE_TRAIN = 4, DXVAE_OP_LOSS = 5 };
 size_t dxvae_workspace_bytes(int op, int64_t B);
+/* The same for a batch whose schedules are known (all host arrays, either may be NULL = worst case):
+ *   level_ptr_host (n_levels + 1, dxvae_batch_build_host / dxvae_batch_schedule): the encoder's per-level temporaries
+ *     are sized for the largest level instead of 6B rows;
+ *   step_ptr_host (dxvae_batch_steps*, DXVAE_OP_TRAIN / DXVAE_OP_LOSS): the per-step activations of the teacher-forced
+ *     decoder are kept for the ACTIVE graphs of each step only.
+ * Never more than dxvae_workspace_bytes; about 0.65x for training on Dexed-like topologies.  Entry points called with
+ * those schedules accept either size. */
+size_t dxvae_workspace_bytes_sched(int op, int64_t B, int32_t n_levels, const int32_t* level_ptr_host,
+                                   const int32_t* step_ptr_host);
 
 /* ---- encode (model.py:200-212; _propagate :151-198 with encode=True) ------------- *
  * level_ptr_host (n_levels+1 ints, HOST) and level_rows (DEVICE) come from the batcher.

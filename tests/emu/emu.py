@@ -100,7 +100,11 @@ class Emu:
         if compact:
             sp = np.zeros(34, np.int32); sr = np.zeros(33 * B, np.int32)
             _abi.check(L, L.dxvae_batch_steps_host(B, ptr(bt["adj"]), ptr(sp), ptr(sr)), "steps")
-        ws = np.full(L.dxvae_workspace_bytes(_abi.OP_TRAIN, B), 0xFF, np.uint8)   # NaN-poisoned: a read of workspace that was never written shows up in the outputs
+        # NaN-poisoned: a read of workspace that was never written shows up in the outputs.  Compacted steps: the
+        # schedule-sized workspace (per-step buffers hold the active rows only), exactly as large as the library asks for
+        nws = L.dxvae_workspace_bytes_sched(_abi.OP_TRAIN, B, bt["n_levels"], ptr(bt["level_ptr"]), ptr(sp)) if compact else L.dxvae_workspace_bytes(_abi.OP_TRAIN, B)
+        assert nws <= L.dxvae_workspace_bytes(_abi.OP_TRAIN, B)
+        ws = np.full(nws, 0xFF, np.uint8)
         loss5 = np.zeros(5, np.float32)
         mu = np.zeros((B, 128), np.float32); sd = np.zeros((B, 128), np.float32)
         g = np.zeros(self.total, np.float32) if grads else None

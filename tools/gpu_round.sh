@@ -17,4 +17,12 @@ $CMD > gpurun_out/prof_plain2_$TAG.log 2>&1 &&
 timeout 1200 ncu --set full --clock-control none --import-source on -k regex:k_tc_gemm -s ${GSKIP:-600} -c ${GCOUNT:-12} \
     -o gpurun_out/prof_tc_$TAG -f $CMD > gpurun_out/ncu_full_$TAG.log 2>&1
 echo "full rc=$?"
+# designated products (forward / dgrad / wgrad of M=32768 N=1536 K=512, cold L2) for the traffic-vs-algorithmic-bytes figure,
+# the L2-feed counters and the source-level stall view: 3xTF32 and plain TF32
+for VB in 32 16; do
+  ONE="python tools/x3_probe.py one 32768 1536 512 $VB"
+  $ONE > gpurun_out/one_plain_${VB}_$TAG.log 2>&1 &&
+  timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_tc_gemm -o gpurun_out/prof_one_${VB}_$TAG -f $ONE > gpurun_out/ncu_one_${VB}_$TAG.log 2>&1
+  echo "one $VB rc=$?"
+done
 fi

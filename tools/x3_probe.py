@@ -62,6 +62,25 @@ def probe(M, N, K, timing=True):
 
 
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "one":
+        # one designated product per operand form, twice each (the second launch is the one to capture under ncu):
+        #   python tools/x3_probe.py one M N K [variant-base: 32 = 3xTF32 (default), 16 = TF32]
+        M, N, K = (int(a) for a in sys.argv[2:5])
+        vb = int(sys.argv[5]) if len(sys.argv) > 5 else 32
+        g = torch.Generator().manual_seed(1)
+        A = torch.randn(M, K, generator=g).cuda(); W = torch.randn(N, K, generator=g).cuda(); dY = torch.randn(M, N, generator=g).cuda()
+        C = torch.empty(M, N, device="cuda"); dX = torch.empty(M, K, device="cuda"); dW = torch.zeros(N, K, device="cuda")
+        flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+        for _ in range(2):
+            flush.zero_()                                   # the operands do not sit in L2 from the previous launch
+            run(vb, M, N, K, A, K, W, K, C, N)
+            flush.zero_()
+            run(vb + 1, M, N, K, dY, N, W, K, dX, K)
+            flush.zero_()
+            run(vb + 2, M, N, K, dY, N, A, K, dW, K)
+        torch.cuda.synchronize()
+        print("one", M, N, K, vb)
+        sys.exit(0)
     quick = len(sys.argv) > 1 and sys.argv[1] == "quick"
     print("DX_X3_INPLACE =", os.environ.get("DX_X3_INPLACE"))
     shapes = [(256, 256, 64), (1000, 1024, 1024), (300, 2048, 512)] if quick else \
