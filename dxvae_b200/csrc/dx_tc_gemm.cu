@@ -1493,6 +1493,23 @@ bool launch_x3(dx_stream_t s, const GemmP& g) {
 }
 
 // Wide chunked 3xTF32 launch (k_tc_gemm_x3w, pair tiles 256 x 256).  Returns false if not applicable.
+// Reduction splits for the persistent pair-tile kernels.  `tiles` output tiles run on `ncl` clusters in waves, and a
+// last wave that is nearly empty costs as much as a full one (80 tiles on 74 clusters: 54 % of the machine), while
+// every tile pays about 3 k-block times of pipeline fill and epilogue.  Modelled efficiency of s splits:
+// occupancy of the waves x kb / (kb + 3) with kb k-blocks per tile; the smallest s within 4 % of the best wins.
+inline int choose_splits(int tiles, int K, int ncl, int max_splits) {
+  int best = 1; double best_e = 0.0;
+  const int kbs = (K + TBK - 1) / TBK;
+  for (int sp = 1; sp <= max_splits && sp <= 16; ++sp) {
+    const int kb = (kbs + sp - 1) / sp;
+    if (sp > 1 && kb < 8) break;                                  // >= 256 reduction rows per split
+    const int total = tiles * sp, waves = (total + ncl - 1) / ncl;
+    const double e = (double)total / ((double)waves * ncl) * kb / (kb + 3.0);
+    if (e > best_e * 1.04) { best_e = e; best = sp; }
+  }
+  return best;
+}
+
 bool launch_x3w(dx_stream_t s, const GemmP& g) {
   using Cfg = X3wCfg;
   static const bool off = getenv("DX_X3_NO_WIDE") != nullptr;
@@ -1501,11 +1518,20 @@ bool launch_x3w(dx_stream_t s, const GemmP& g) {
   const int gm = (g.M + 255) / 256, gn = (g.N + 255) / 256;
   const bool tma_store = !g.c_idx && ((reinterpret_cast<uintptr_t>(g.C) & 15) == 0) && (g.ldc % 4 == 0);
   if (!tma_store || g.N < 192 || (!g.a_kc && g.b_kc)) return false;
-  int splits = 1;
+  int splits = 1, accum = g.accum;
+  static const bool no_model = getenv("DX_X3_NO_SPLIT_MODEL") != nullptr;
   if (g.accum == ACC_ATOMIC) {
     const int want = (2 * ncl) / (gm * gn);
     const int maxs = (g.K + TBK * 16 - 1) / (TBK * 16);
     splits = want < 1 ? 1 : (want > maxs ? maxs : want);
+    if (!no_model) splits = choose_splits(gm * gn, g.K, ncl, maxs);
+  } else if (!no_model && !(g.a_kc && g.b_kc) && !g.bias && (!g.add || g.act == ACT_GATE) && (g.act == ACT_NONE || g.act == ACT_GATE)) {
+    // dgrads (never the forward products: their value must not depend on the row count): partial sums leave through
+    // TMA reduce-add; a plain store becomes zero-fill + reduce-add; the relu gate is a 0/1 factor and distributes
+    // (only under one wave of tiles: measured on B200, splitting an 80-tile dgrad over 74 clusters buys nothing — the
+    // zero fill and the reduce-adds cost what the better last wave saves — while 16 tiles -> 64 runs 1.56x faster)
+    if (gm * gn < ncl) splits = choose_splits(gm * gn, g.K, ncl, g.K / 256);
+    if (splits > 1) accum = ACC_ADD;                              // (zero fill just before the launch, below)
   }
   int k_chunk = (g.K + splits - 1) / splits;
   k_chunk = (k_chunk + TBK - 1) / TBK * TBK;
@@ -1523,7 +1549,7 @@ bool launch_x3w(dx_stream_t s, const GemmP& g) {
   if (add_tma) { if (!make_map(&tadd, g.add, g.M, g.N, g.ldadd, 32, 32, false, true)) return false; }
   else tadd = ta;
   static const bool m_fast = getenv("DX_TC_M_FAST") != nullptr;
-  TcParams p{g.M, g.N, g.K, g.C, g.ldc, g.c_idx, g.bias, g.add, g.ldadd, g.act, g.accum, k_chunk, 1, add_tma ? 1 : 0,
+  TcParams p{g.M, g.N, g.K, g.C, g.ldc, g.c_idx, g.bias, g.add, g.ldadd, g.act, accum, k_chunk, 1, add_tma ? 1 : 0,
              m_fast ? 0 : 1, 0, 1, tc_prefetch(), nullptr};
   static AttrOnce attr;
   attr([] {
@@ -1532,6 +1558,7 @@ bool launch_x3w(dx_stream_t s, const GemmP& g) {
     cudaFuncSetAttribute(k_tc_gemm_x3w<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM);
   });
   const int nt = total < ncl ? total : ncl;
+  if (accum != g.accum && g.accum == ACC_STORE) cudaMemset2DAsync(g.C, (size_t)g.ldc * 4, 0, (size_t)g.N * 4, (size_t)g.M, s);
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(2 * nt); cfg.blockDim = dim3(Cfg::THREADS); cfg.dynamicSmemBytes = Cfg::SMEM; cfg.stream = s;
   cudaLaunchAttribute at[1];
@@ -1593,9 +1620,15 @@ bool tc_gemm(dx_stream_t s, const GemmP& g, int* tile_n, bool x3) {
       if (bn == 256 && launch_tc2<true>(s, g)) return true;
       return bn == 256 ? launch_tc<256, true>(s, g) : (bn == 128 ? launch_tc<128, true>(s, g) : launch_tc<64, true>(s, g));
     }
-    if (bn == 256 && launch_x3w(s, g)) return true;
+    static const char* force = getenv("DX_X3_FORCE");           // experiments: w = wide pair tile, p = pair 256x128, s = single 128x128
+    if (force && force[0] == 'w' && launch_x3w(s, g)) return true;
+    if (force && force[0] == 'p' && launch_x3<true>(s, g)) return true;
+    if (force && force[0] == 's') return launch_x3<false>(s, g);
     static const bool no_narrow = getenv("DX_X3_NO_NARROW") != nullptr;
     if (g.N <= 64 && !no_narrow) return launch_x3<false, 32>(s, g);   // thin outputs: 32-column tiles
+    // wide pair tiles whenever the output is wide enough: for dgrads / wgrads launch_x3w splits the reduction until the
+    // machine is filled (choose_splits), forward products need >= 37 tiles of their own
+    if (g.N >= 192 && launch_x3w(s, g)) return true;
     if (launch_x3<true>(s, g)) return true;
     return launch_x3<false>(s, g);
   }

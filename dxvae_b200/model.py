@@ -123,6 +123,11 @@ class DXVAE(nn.Module):
         if d is not None:
             n = int(L.dxvae_workspace_bytes_sched(op, B, d.n_levels, d.level_ptr.ctypes.data,
                                                   None if d.step_ptr is None else d.step_ptr.ctypes.data))
+            ws = self._ws.get((op,))
+            if not fresh and (ws is None or ws.numel() < n):
+                # the need follows the batch's topologies: leave 6 % of headroom (never above the worst case) so that
+                # the next batches of the same size do not reallocate tens of GB
+                n = min(int(L.dxvae_workspace_bytes(op, B)), n + n // 16)
         else:
             n = int(L.dxvae_workspace_bytes(op, B))
         if fresh:

@@ -95,22 +95,25 @@ def test_cfg1_all_1024_graphs_match_the_reference(tg, prec):
     for a, c in zip(out, tg["loss"]):
         assert abs(a.item() - c) <= TOL_LOSS * abs(c) + 1e-7, (a.item(), c)
     out[0].backward()
-    # Yardstick: the float64 evaluation of the same function (the fp32 reference is within grad_ref_noise ~ 3e-6 of it).
-    # Relu kinks: the batch holds 1024 x 21 x 2048 edge-head units, and a unit whose pre-activation is within rounding of
-    # zero contributes or not depending on the last bit — a step of one graph's share (~1/1024 of an entry) that is not
-    # an arithmetic error.  So per tensor: all sampled entries within TOL_GRAD except at most two, and those within a
-    # few graphs' shares; the tensor norm within 3e-4.
+    # Yardstick: the float64 evaluation of the same function.  Relu kinks: the batch evaluates 1024 x 21 x 2048 edge-head
+    # units and 1024 x 7 x 2048 parameter-head units, and a unit whose pre-activation is within rounding of zero
+    # contributes or not depending on the last bit — a step of one graph's share (~1/1024 of an entry, a whole weight row
+    # for a hidden unit of an MLP) that is not an arithmetic error; the fp32 REFERENCE is itself up to 4.6e-4 away from
+    # float64 on this model (grad_ref_noise, per tensor).  So per tensor: band = max(TOL_GRAD, 2 x the reference's own
+    # distance); all sampled entries within the band except at most two, and those within a few graphs' shares; the
+    # tensor norm within 3 x band.
     named = dict(m.named_parameters())
-    worst, kinks = 0.0, 0
+    worst, outside = 0.0, 0
     for k, n in enumerate(tg["grad_names"]):
         g = named[str(n)].grad.cpu().flatten()
         vals = g[torch.from_numpy(tg["grad_idx"][k])].double().numpy()
         scale = np.abs(g.numpy()).max() + 1e-30
+        band = max(TOL_GRAD, 2.0 * float(tg["grad_ref_noise"][k]))
         errs = np.sort(np.abs(vals - tg["grad64_vals"][k]) / scale)
         worst = max(worst, errs[-3])
-        kinks += int((errs > TOL_GRAD).sum())
-        assert errs[-3] <= TOL_GRAD and errs[-1] <= 4.0 / 1024, (n, errs[-3:])
-        assert abs(g.double().norm().item() - tg["grad64_norms"][k]) <= 3e-4 * tg["grad64_norms"][k] + 1e-12, n
-    print(prec, "gradients vs float64: worst (third-largest per tensor) %.2e, entries on a relu kink %d of %d"
-          % (worst, kinks, 48 * len(tg["grad_names"])))
-    assert kinks <= 6
+        outside += int((errs > band).sum())
+        assert errs[-3] <= band and errs[-1] <= max(band, 4.0 / 1024), (n, errs[-3:], band)
+        assert abs(g.double().norm().item() - tg["grad64_norms"][k]) <= 3 * band * tg["grad64_norms"][k] + 1e-12, n
+    print(prec, "gradients vs float64: worst (third-largest per tensor) %.2e, entries outside their band %d of %d"
+          % (worst, outside, 48 * len(tg["grad_names"])))
+    assert outside <= 6

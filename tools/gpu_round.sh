@@ -14,7 +14,7 @@ timeout 1200 ncu --metrics gpu__time_duration.sum --clock-control none -s ${SKIP
     --log-file gpurun_out/launches_$TAG.csv $CMD > gpurun_out/ncu_launches_$TAG.log 2>&1
 echo "launch list rc=$?"
 $CMD > gpurun_out/prof_plain2_$TAG.log 2>&1 &&
-timeout 1200 ncu --set full --clock-control none --import-source on -k regex:k_tc_gemm -s ${GSKIP:-600} -c ${GCOUNT:-12} \
+timeout 1200 ncu --set full --clock-control none --import-source on -k regex:k_tc_gemm -s ${GSKIP:-600} -c ${GCOUNT:-4} \
     -o gpurun_out/prof_tc_$TAG -f $CMD > gpurun_out/ncu_full_$TAG.log 2>&1
 echo "full rc=$?"
 # designated products (forward / dgrad / wgrad of M=32768 N=1536 K=512, cold L2) for the traffic-vs-algorithmic-bytes figure,
@@ -22,7 +22,9 @@ echo "full rc=$?"
 for VB in 32 16; do
   ONE="python tools/x3_probe.py one 32768 1536 512 $VB"
   $ONE > gpurun_out/one_plain_${VB}_$TAG.log 2>&1 &&
-  timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_tc_gemm -o gpurun_out/prof_one_${VB}_$TAG -f $ONE > gpurun_out/ncu_one_${VB}_$TAG.log 2>&1
+  SRC=""; if [ $VB = 32 ]; then SRC="--import-source on"; fi
+  timeout 900 ncu --set full --clock-control none $SRC -k regex:k_tc_gemm -s 3 -c 3 -o gpurun_out/prof_one_${VB}_$TAG -f $ONE > gpurun_out/ncu_one_${VB}_$TAG.log 2>&1
   echo "one $VB rc=$?"
 done
 fi
+du -sh gpurun_out | tail -1   # (gpurun copies back at most 64 MiB)

@@ -25,13 +25,14 @@ def val(r, name, scale=True):
 
 
 gemm = [r for r in body if "k_tc_gemm" in r[hdr.index("Kernel Name")]]
-assert len(gemm) >= 6, "expected forward, dgrad, wgrad x 2 launches, got %d" % len(gemm)
+assert len(gemm) >= 3, "expected the forward, dgrad, wgrad launches of the second round, got %d" % len(gemm)
+gemm = gemm[-3:]
 forms = ["forward  y = x W^T", "dgrad    dx = dy W", "wgrad    dW += dy^T x"]
 alg = [4.0 * (M * K + N * K + M * N), 4.0 * (M * N + N * K + M * K), 4.0 * (M * N + M * K + N * K)]
 out = {"shape": [M, N, K], "precision": prec, "source": "ncu --set full --clock-control none of tools/x3_probe.py one %d %d %d" % (M, N, K),
        "launches": []}
 for f in range(3):
-    r = gemm[3 + f]                                        # second round
+    r = gemm[f]                                            # second round (captured with -s 3 -c 3)
     rd, wr, t = val(r, "dram__bytes_read.sum"), val(r, "dram__bytes_write.sum"), val(r, "gpu__time_duration.sum")
     out["launches"].append({"form": forms[f], "kernel": r[hdr.index("Kernel Name")][:60], "dram_read_bytes": rd, "dram_write_bytes": wr,
                             "algorithmic_bytes": alg[f], "dram_over_algorithmic": (rd + wr) / alg[f], "duration_us_under_ncu": t * 1e6,

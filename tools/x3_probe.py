@@ -85,6 +85,7 @@ if __name__ == "__main__":
     print("DX_X3_INPLACE =", os.environ.get("DX_X3_INPLACE"))
     shapes = [(256, 256, 64), (1000, 1024, 1024), (300, 2048, 512)] if quick else \
         [(32768, 1536, 512), (32768, 2048, 512), (32768, 1024, 1024), (32768, 512, 512), (32768, 1536, 32), (8192, 1536, 512),
-         (4096, 512, 512), (128, 1536, 512), (32768, 27, 1024), (32768, 1, 1024), (2000, 1536, 512), (4000, 512, 1536)]
+         (4096, 512, 512), (128, 1536, 512), (32768, 27, 1024), (32768, 1, 1024), (2000, 1536, 512), (4000, 512, 1536), (10000, 1536, 512), (10000, 2048, 512),
+         (14000, 1536, 512), (20000, 1536, 512)]
     for s in shapes:
         probe(*s, timing=not quick)
