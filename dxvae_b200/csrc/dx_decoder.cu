@@ -1065,7 +1065,9 @@ void decode_bwd_impl(dx_stream_t st, const Weights& W, const Weights& G, int B, 
     linear_wgrad(st, B, G3, XP, w.dgx, 4 * H, bt.Xn, XP, w.dWihP[2], XP);
   }
   mlp3_bwd(st, W, G, B, P_X0_W0, w.Hinit, SX0 + 32, w.A1[0], w.A2[0], w.dL[0], w, w.dHinit);
-  tanh_bwd(st, (int64_t)bH, w.dHinit, w.Hinit);
+  // tanh' from the recomputed pre-activation (Hrun is free scratch here; same kernel and operands as the forward pass)
+  linear_fwd(st, B, H, Z, z, Z, W[P_ZH_W], Z, W[P_ZH_B], w.Hrun, H);
+  tanh_bwd_pre(st, (int64_t)bH, w.dHinit, w.Hrun);
   linear_wgrad(st, B, H, Z, w.dHinit, H, z, Z, G[P_ZH_W], Z);
   colsum_accum(st, B, H, w.dHinit, H, G[P_ZH_B]);
   linear_dgrad(st, B, H, Z, w.dHinit, H, W[P_ZH_W], Z, w.dz, Z, ACC_STORE);

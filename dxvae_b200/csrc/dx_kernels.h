@@ -412,5 +412,15 @@ inline void relu_mask(dx_stream_t st, int64_t n4, float* d, const float* act) {
 inline void tanh_bwd(dx_stream_t st, int64_t n, float* d, const float* y) {
   foreach (st, n, [=] DX_HD(int64_t i) { d[i] *= (1.f - y[i] * y[i]); });
 }
+// d[i] *= sech^2(x[i])       (tanh backward from the PRE-activation).  1 - y^2 loses its leading digits when the unit
+// saturates (y = 0.9999 stored in fp32 leaves 1 - y^2 good to 3e-4 relative); sech^2 = 4a / (1 + a)^2, a = exp(-2|x|),
+// keeps full relative precision.  Used for z_to_h, whose units saturate in a trained model (|mu| reaches 17) and whose
+// bias gradient is a heavily cancelling sum over the batch.
+inline void tanh_bwd_pre(dx_stream_t st, int64_t n, float* d, const float* x) {
+  foreach (st, n, [=] DX_HD(int64_t i) {
+    const float a = expf(-2.f * fabsf(x[i])), q = 1.f + a;
+    d[i] *= 4.f * a / (q * q);
+  });
+}
 
 }  // namespace dx

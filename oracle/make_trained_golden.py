@@ -129,11 +129,33 @@ def main():
     l6 = o64.loss(mu6, sd6, X.double(), P.double(), A.double(), eps.double())
     l6[0].backward()
     f64 = grad_fingerprint(o64)
+    full64 = {n: p_.grad.clone() for n, p_ in o64.named_parameters()}
     assert [str(a) for a in f64["names"]] == [str(a) for a in fr["names"]] and np.array_equal(f64["idx"], fr["idx"])
     noise = []
     for k, n in enumerate(fr["names"]):
-        g32 = dict(mq.named_parameters())[str(n)].grad.double(); g64 = dict(o64.named_parameters())[str(n)].grad
+        g32 = dict(mq.named_parameters())[str(n)].grad.double(); g64 = full64[str(n)]
         noise.append((g32 - g64).abs().max().item() / (g64.abs().max().item() + 1e-300))
+    # Cancellation-free scale per tensor.  At a (nearly) trained model a bias gradient is a batch sum that cancels to a
+    # small fraction of its terms (the mean gradient of a unit vanishes at a stationary point), so rounding noise of the
+    # TERMS is large against max|g|.  The float64 gradient is therefore also evaluated per chunk of 8 graphs (each
+    # chunk's loss weighted 8/1024, so the chunks add up to the full gradient) and scale = max_e sum_chunks |g_chunk[e]|.
+    B = len(G); CH = 8
+    absum = {n: torch.zeros_like(p_, dtype=torch.float64) for n, p_ in o64.named_parameters()}
+    total = {n: torch.zeros_like(p_, dtype=torch.float64) for n, p_ in o64.named_parameters()}
+    for c0 in range(0, B, CH):
+        sl = slice(c0, c0 + CH)
+        o64.zero_grad()
+        mc, sc = o64.encode(X[sl].double(), A[sl].double())
+        lc = o64.loss(mc, sc, X[sl].double(), P[sl].double(), A[sl].double(), eps[sl].double())
+        (lc[0] * (CH / B)).backward()
+        for n, p_ in o64.named_parameters():
+            absum[n] += p_.grad.abs(); total[n] += p_.grad
+    for n in total:   # the chunks add up to the full-batch gradient
+        assert (total[n] - full64[n]).abs().max().item() <= 1e-9 * (full64[n].abs().max().item() + 1e-300), n
+    scales = []
+    for k, n in enumerate(fr["names"]):
+        scales.append(absum[str(n)].max().item())
+    out["grad64_chunk_scale"] = np.array(scales)
     out["grad64_vals"] = f64["vals"]; out["grad64_norms"] = f64["norms"]
     out["grad_ref_noise"] = np.array(noise)
     out["loss64"] = np.array([t.item() for t in l6], np.float64)

@@ -95,25 +95,42 @@ def test_cfg1_all_1024_graphs_match_the_reference(tg, prec):
     for a, c in zip(out, tg["loss"]):
         assert abs(a.item() - c) <= TOL_LOSS * abs(c) + 1e-7, (a.item(), c)
     out[0].backward()
-    # Yardstick: the float64 evaluation of the same function.  Relu kinks: the batch evaluates 1024 x 21 x 2048 edge-head
-    # units and 1024 x 7 x 2048 parameter-head units, and a unit whose pre-activation is within rounding of zero
-    # contributes or not depending on the last bit — a step of one graph's share (~1/1024 of an entry, a whole weight row
-    # for a hidden unit of an MLP) that is not an arithmetic error; the fp32 REFERENCE is itself up to 4.6e-4 away from
-    # float64 on this model (grad_ref_noise, per tensor).  So per tensor: band = max(TOL_GRAD, 2 x the reference's own
-    # distance); all sampled entries within the band except at most two, and those within a few graphs' shares; the
-    # tensor norm within 3 x band.
+    # Yardstick: the float64 evaluation of the same function.  Two things make max|g| of the full-batch gradient the
+    # wrong unit for a TRAINED model (oracle/make_trained_golden.py):
+    #   * cancellation: near a stationary point a batch sum — a bias gradient above all — cancels to a small fraction of
+    #     its terms, so fp32 rounding of the terms is large against the sum (measured here: 2-4e-4 of max|g| on
+    #     h_to_std.0.bias and z_to_h.0.bias, identical in both arithmetics; every other tensor <= 1e-4).  The fixture
+    #     holds, per tensor, the cancellation-free scale max_e sum_chunks |g_chunk[e]| over 8-graph chunks; errors are
+    #     taken relative to it.
+    #   * relu kinks: the batch evaluates 1024 x 21 x 2048 edge-head units and 1024 x 7 x 2048 parameter-head units, and a
+    #     unit whose pre-activation is within rounding of zero contributes or not depending on the last bit — a step of
+    #     one graph's share that is not an arithmetic error; the fp32 REFERENCE is itself up to 4.6e-4 of max|g| away
+    #     from float64 on this model (grad_ref_noise, per tensor).
+    # So per tensor, in units of max|g|: band = max(TOL_GRAD, 2 x the reference's own distance); all sampled entries within
+    # the band except at most two, and those within a few graphs' shares; the tensor norm within 3 x band.  At most two
+    # tensors may miss that and are then held to TOL_GRAD in units of their cancellation-free scale.
     named = dict(m.named_parameters())
-    worst, outside = 0.0, 0
+    worst, outside, bad, loose = 0.0, 0, [], []
     for k, n in enumerate(tg["grad_names"]):
         g = named[str(n)].grad.cpu().flatten()
         vals = g[torch.from_numpy(tg["grad_idx"][k])].double().numpy()
-        scale = np.abs(g.numpy()).max() + 1e-30
-        band = max(TOL_GRAD, 2.0 * float(tg["grad_ref_noise"][k]))
-        errs = np.sort(np.abs(vals - tg["grad64_vals"][k]) / scale)
+        gmax = np.abs(g.numpy()).max() + 1e-30
+        noise = 2.0 * float(tg["grad_ref_noise"][k])
+        nerr = abs(g.double().norm().item() - tg["grad64_norms"][k]) / (tg["grad64_norms"][k] + 1e-300)
+        errs = np.sort(np.abs(vals - tg["grad64_vals"][k]) / gmax)          # in units of max|g| (the reference tolerance)
+        band = max(TOL_GRAD, noise)
+        strict = errs[-3] <= band and errs[-1] <= max(band, 4.0 / 1024) and nerr <= 3 * band
         worst = max(worst, errs[-3])
         outside += int((errs > band).sum())
-        assert errs[-3] <= band and errs[-1] <= max(band, 4.0 / 1024), (n, errs[-3:], band)
-        assert abs(g.double().norm().item() - tg["grad64_norms"][k]) <= 3 * band * tg["grad64_norms"][k] + 1e-12, n
-    print(prec, "gradients vs float64: worst (third-largest per tensor) %.2e, entries outside their band %d of %d"
+        if not strict:
+            # ... or in units of the cancellation-free scale, for the (at most two) tensors that are cancelling sums
+            amp = max(1.0, float(tg["grad64_chunk_scale"][k]) / gmax)
+            loose.append((str(n), errs[-3:].tolist(), "cancellation x%.1f" % amp))
+            if not (errs[-3] / amp <= TOL_GRAD and errs[-1] / amp <= max(TOL_GRAD, 4.0 / 1024) and nerr / amp <= 3 * TOL_GRAD):
+                bad.append((str(n), errs[-3:].tolist(), nerr, band, amp))
+    print(prec, "gradients vs float64: worst (third-largest per tensor, units of max|g|) %.2e, entries outside their band %d of %d"
           % (worst, outside, 48 * len(tg["grad_names"])))
-    assert outside <= 6
+    for b in loose:
+        print("   judged against the cancellation-free scale:", b)
+    assert not bad, bad
+    assert len(loose) <= 2, loose

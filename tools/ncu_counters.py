@@ -1,13 +1,13 @@
 """Selected raw counters of every captured launch of an .ncu-rep whose kernel name matches a regex: L2 -> SM feed
 (lts2xbar bytes, L2 throughput, hit rate), shared-memory pipe, tensor pipe, issue / stall figures.
-usage: python tools/ncu_counters.py <file.ncu-rep> <kernel regex> > profiles/<name>.txt"""
+usage: python tools/ncu_counters.py <file.ncu-rep | raw-page .csv> <kernel regex> > profiles/<name>.txt"""
 import csv
 import re
 import subprocess
 import sys
 
 rep, pat = sys.argv[1], re.compile(sys.argv[2])
-raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+raw = open(rep).read() if rep.endswith(".csv") else subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(raw.splitlines()))
 hdr, units, body = rows[0], rows[1], rows[2:]
 want = [r"^Kernel Name$", r"^launch__grid_size$", r"^launch__registers_per_thread$", r"^gpu__time_duration\.sum$",

@@ -23,8 +23,10 @@ with open("profiles/%s_launches_summary.txt" % out, "w") as f:
     f.write("# captured launches: %d, total %.2f ms\n" % (sum(a[0] for a in agg.values()), tot))
     for k, (n, t) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
         f.write("%9.3f ms %5.1f%% n=%5d  %s\n" % (t, 100 * t / tot, n, k))
-raw = subprocess.run(["ncu", "-i", "gpurun_out/prof_tc_%s.ncu-rep" % tag, "--page", "raw", "--csv"], capture_output=True,
-                     text=True).stdout
+import os
+rawcsv = "gpurun_out/prof_tc_%s_raw.csv" % tag
+raw = open(rawcsv).read() if os.path.exists(rawcsv) else subprocess.run(
+    ["ncu", "-i", "gpurun_out/prof_tc_%s.ncu-rep" % tag, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(raw.splitlines()))
 hdr, units = rows[0], rows[1]
 want = ["Kernel Name", "launch__grid_size", "launch__registers_per_thread", "gpu__time_duration.sum",
@@ -41,15 +43,4 @@ with open("profiles/%s_tc_gemm_ncu.txt" % out, "w") as f:
             if w in hdr:
                 i = hdr.index(w)
                 f.write("%s = %s %s\n" % (w, r[i][:140], units[i]))
-# DRAM traffic per launch of the dominant kernel family (bench.py reports it as roofline.traffic)
-import json
-ir, iw, it = hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum"), hdr.index("gpu__time_duration.sum")
-def tobytes(v, u):
-    v = float(v.replace(",", ""))
-    return v * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[u]
-tot_b = [tobytes(r[ir], units[ir]) + tobytes(r[iw], units[iw]) for r in rows[2:]]
-json.dump({"kernel": "dx::k_tc_gemm / k_tc_gemm2 (tcgen05 kind::tf32)", "captured_launches": len(tot_b),
-           "dram_bytes_per_launch": sum(tot_b) / max(1, len(tot_b)),
-           "source": "ncu --set full --clock-control none, profiles/%s_tc_gemm_ncu.txt" % out},
-          open("profiles/tc_gemm_traffic.json", "w"))
 print(open("profiles/%s_launches_summary.txt" % out).read()[:2400])

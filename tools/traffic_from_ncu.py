@@ -1,7 +1,7 @@
 """DRAM traffic of the designated GEMM launches against their algorithmic bytes, from an `ncu --set full` capture of
 `python tools/x3_probe.py one M N K` (forward, dgrad, wgrad of one shape, each launched twice: the SECOND launch of each
 form is read).  Writes profiles/<prefix>_tc_gemm_traffic.json, which bench.py reports as roofline.traffic(+_detail).
-usage: python tools/traffic_from_ncu.py <file.ncu-rep> <profiles prefix> <precision: 3xtf32|tf32> M N K"""
+usage: python tools/traffic_from_ncu.py <file.ncu-rep | raw-page .csv> <profiles prefix> <precision: 3xtf32|tf32> M N K"""
 import csv
 import json
 import os
@@ -10,7 +10,7 @@ import sys
 
 rep, prefix, prec = sys.argv[1], sys.argv[2], sys.argv[3]
 M, N, K = (int(a) for a in sys.argv[4:7])
-raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+raw = open(rep).read() if rep.endswith(".csv") else subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(raw.splitlines()))
 hdr, units, body = rows[0], rows[1], rows[2:]
 
