@@ -524,8 +524,8 @@ def run_ours(args):
                            "precision": args.precision,
                            "micro_batch_per_gpu": M, "global_batch": M * world, "parallelism": "dp%d" % world,
                            "optimizer": "AdamW lr=1e-3", "l2": "inputs cycle over a %d-graph pool; the step's %.1f GB "
-                           "activation workspace is far larger than L2" %
-                           (NPOOL * M, L.dxvae_workspace_bytes(2, M) / 1e9)},
+                           "activation workspace (schedule-sized; %.1f GB worst case) is far larger than L2" %
+                           (NPOOL * M, model._ws[(_abi.OP_TRAIN,)].numel() / 1e9, L.dxvae_workspace_bytes(2, M) / 1e9)},
                 "clocks": clocks, "gpu_launches": int(launches),
                 "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 20,
                         "ms_per_step": ms_e2e / K,
