@@ -1,24 +1,29 @@
-// tcgen05 / TMA GEMM for sm_100a: the large dense contractions of the TRAINING path
-// (GRU gate products, gate/mapper and edge-head projections, MLP layers and their
-// dgrad / wgrad) on the 5th-generation tensor cores with TF32 inputs and FP32
-// accumulation in TMEM.
+// tcgen05 / TMA GEMMs for sm_100a: the dense contractions of the path (GRU gate products, gate / mapper and
+// edge-head projections, MLP layers and their dgrad / wgrad) on the 5th-generation tensor cores, FP32 accumulation in
+// TMEM, operands fp32 in HBM.
 //
 //   C[M,N] (op)= act( sum_r Aop(i,r) Bop(r,j) + bias[j] + add[i,j] )      (same contract as dx_gemm.h)
 //
-// Persistent CTAs (one per SM) walk the 128 x BN output tiles (BN = 256 / 128 / 64); two TMEM
-// accumulators let the epilogue of one tile overlap the main loop of the next.  320 threads:
-//   warp 0   : TMA producer  (cp.async.bulk.tensor, 128B swizzle, mbarrier complete_tx)
+// Three kernel families (dispatch: tc_gemm() at the end of the file):
+//   k_tc_gemm_x3w / k_tc_gemm_x3   PREC_3XTF32 (the default arithmetic): FP32-accurate products — operands split
+//                                  hi/lo in shared memory by converter warps, hi*lo + lo*hi + hi*hi per k-step,
+//                                  chunked accumulation drained into FP32 registers (see the comment above
+//                                  k_tc_gemm_x3).  256x256 pair tiles (cta_group::2), 128- and 32-column tiles.
+//   k_tc_gemm2 / k_tc_gemm<BN>     PREC_TF32: plain kind::tf32 (the tensor map's TFLOAT32 type rounds on load); pair
+//                                  tiles 256x256 and single-CTA 128 x {256,128,64} tiles, double-buffered TMEM
+//                                  accumulator so that the epilogue of one tile overlaps the main loop of the next.
+//   k_tc_gemm2<.., BF16>           bf16 K-major operands (unit-tested groundwork, not on the product path).
+// Common structure: persistent CTAs (one per SM) walk the output tiles;
+//   warp 0   : TMA producer  (cp.async.bulk.tensor, 128B swizzle, mbarrier complete_tx, L2 prefetch of the next tile)
 //   warp 1   : TMEM allocation + single-thread tcgen05.mma issue, tcgen05.commit -> mbarriers
-//   warps 2-9: epilogue (tcgen05.ld 32x32b -> registers -> bias/add/act -> swizzled smem slab -> TMA bulk
-//              store / reduce-add), two warps per TMEM lane quadrant, half of the columns each
-// Operands stay fp32 in HBM; the tensor map's TFLOAT32 type rounds on load.  Both operand
-// majors are native (no physical transposes): K-major tiles are one 2-D box of
-// [rows x 32 floats]; MN-major tiles (dgrad's W, wgrad's dy and x) are 32x32 boxes laid out as
-// SWIZZLE_128B_BASE32B MN-major atoms (TMA swizzle 128B_ATOM_32B; SBO = 512 B between 4-row k
-// groups, LBO = 4096 B between 32-element MN groups) — the only MN-major layout tf32 accepts.  Reduction splits (wgrad) use blockIdx.z + atomic epilogue.
+//   epilogue warps: tcgen05.ld 32x32b -> registers -> bias/add/act -> swizzled smem slab -> TMA bulk store / reduce-add,
+//              two warps per TMEM lane quadrant, half of the columns each
+// Both operand majors are native (no physical transposes): K-major tiles are one 2-D box of [rows x 32 floats];
+// MN-major tiles (dgrad's W, wgrad's dy and x) are 32x32 boxes laid out as SWIZZLE_128B_BASE32B MN-major atoms (TMA
+// swizzle 128B_ATOM_32B; SBO = 512 B between 4-row k groups, LBO = 4096 B between 32-element MN groups) — the only
+// MN-major layout tf32 accepts.  Reduction splits (wgrad, sub-wave dgrads) leave through TMA reduce-add.
 //
-// Roofline: tensor pipe (kind::tf32 = 1/2 of the bf16 rate), fed from L2: a 128x256x32 stage is
-// 48 KB per 512 MMA cycles.
+// Roofline: the tensor pipe (kind::tf32 = 1/2 of the bf16 rate; 1/6 per algorithmic flop in the 3xTF32 mode).
 #include "dx_gemm.h"
 
 #ifndef DX_EMU
@@ -31,20 +36,19 @@ namespace {
 constexpr int TBM = 128, TBK = 32;           // 32 fp32 = one 128-byte swizzle row
 constexpr int A_BYTES = TBM * TBK * 4;       // 16 KB
 
-// X3: error-compensated "3xTF32" mode for FP32-accurate results on the tensor cores.  kind::tf32 reads the top
-// 19 bits of each 32-bit operand word, so the raw fp32 tile TMA delivers IS the hi part (hi = v with the low 13
-// mantissa bits dropped).  Four extra "converter" warps (10..13) write lo = v - hi (exact in fp32) for every
-// element of a landed stage into a second buffer of the same layout — element-wise, so it is valid for K-major
-// and MN-major tiles alike — and each k-step issues hi*hi + hi*lo + lo*hi into the same FP32 accumulator (the
-// dropped lo*lo term is ~2^-22 relative).  No operand copies in HBM, no extra L2 traffic: the mode costs 3x the
-// MMA issue and one shared-memory read + write of the stage.
+// 3xTF32 converter warps of the chunked kernels below (k_tc_gemm_x3 / k_tc_gemm_x3w): kind::tf32 reads the top 19 bits of
+// each 32-bit operand word, so the raw fp32 tile TMA delivers IS the hi part (hi = v with the low 13 mantissa bits
+// dropped).  Converter warps write lo = v - hi (exact in fp32, then rounded to tf32) for every element of a landed stage
+// into a second buffer of the same layout — element-wise, so it is valid for K-major and MN-major tiles alike.  No
+// operand copies in HBM, no extra L2 traffic: the mode costs 3x the MMA issue and one shared-memory read + write of the
+// stage.
 constexpr int X3_WARPS = 4;
-template <int BN, bool X3 = false> struct TcCfg {
+template <int BN> struct TcCfg {
   static constexpr int B_BYTES = BN * TBK * 4;
   static constexpr int RAW = A_BYTES + B_BYTES;                    // bytes TMA delivers per stage
-  static constexpr int STAGE = RAW * (X3 ? 2 : 1);                 // X3: [A|B] raw, then [A_lo|B_lo]
-  static constexpr int STAGES = X3 ? (BN == 256 ? 2 : (BN == 128 ? 3 : 4)) : ((BN == 256) ? 4 : (BN == 128 ? 6 : 8));
-  static constexpr int THREADS = 320 + (X3 ? 32 * X3_WARPS : 0);
+  static constexpr int STAGE = RAW;
+  static constexpr int STAGES = (BN == 256) ? 4 : (BN == 128 ? 6 : 8);
+  static constexpr int THREADS = 320;
   static constexpr int SMEM = STAGES * STAGE + 1024 /*align*/ + 8 * 4096 /*store staging*/ + 256 /*barriers*/;
 };
 
@@ -57,8 +61,8 @@ struct TcParams {
   int add_tma;      // 1: the `add` matrix tile is prefetched into the staging slab by TMA
   int n_fast;       // tile order: 1 = the N tiles of one M panel are adjacent (concurrent CTAs share the big A panel in L2;
                     //             the weight-side operand is small and L2-resident anyway), 0 = M fastest
-  int x3_inplace;   // 3xTF32 debug switch (DX_X3_INPLACE=1): converters also overwrite the raw tile with hi
-  int x3_chunk;     // k_tc_gemm_x3: k-blocks (of 32) accumulated in TMEM before the FP32 register drain
+  int x3_inplace;   // k_tc_gemm_x3: DX_X3_DBG experiment switches (results are wrong when set)
+  int x3_chunk;     // (unused)
   int prefetch;     // producers prefetch their next tile's operand boxes into L2 (DX_TC_NO_PREFETCH=1 turns it off)
   long long* dbg;   // optional per-phase clock64() trace of CTA (0,0,0): DX_TC_DEBUG=1
 };
@@ -333,25 +337,24 @@ __device__ __forceinline__ void tc_epilogue(const TcParams& p, const CUtensorMap
   __syncwarp();
 }
 
-template <int BN, bool A_MN, bool B_MN, bool X3 = false>
-__global__ void __launch_bounds__(TcCfg<BN, X3>::THREADS, 1) k_tc_gemm(const __grid_constant__ CUtensorMap tmA,
+template <int BN, bool A_MN, bool B_MN>
+__global__ void __launch_bounds__(TcCfg<BN>::THREADS, 1) k_tc_gemm(const __grid_constant__ CUtensorMap tmA,
                                                     const __grid_constant__ CUtensorMap tmB,
                                                     const __grid_constant__ CUtensorMap tmC,
                                                     const __grid_constant__ CUtensorMap tmAdd, const TcParams p) {
   // Persistent: CTA b processes tiles b, b+grid, ... ; two accumulators in TMEM so the epilogue of
   // tile i overlaps the main loop of tile i+1.
-  using Cfg = TcCfg<BN, X3>;
+  using Cfg = TcCfg<BN>;
   constexpr int S = Cfg::STAGES;
-  constexpr int RAW = Cfg::RAW;                                    // X3: [A|B] raw then [A_lo|B_lo]
+  constexpr int RAW = Cfg::RAW;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;       // swizzle atoms need 1024-byte alignment
   const uint32_t stg_base = base + S * Cfg::STAGE;                    // 4 warps x 2 x 4 KB store staging
-  const uint32_t bars = stg_base + 8 * 4096;                      // full[S], empty[S], tfull[2], tempty[2], slot, add[8], conv[S]
+  const uint32_t bars = stg_base + 8 * 4096;                      // full[S], empty[S], tfull[2], tempty[2], slot, add[8]
   auto full_bar = [&](int s) { return bars + 8u * s; };
   auto empty_bar = [&](int s) { return bars + 8u * (S + s); };
   auto tfull_bar = [&](int a) { return bars + 8u * (2 * S + a); };
   auto tempty_bar = [&](int a) { return bars + 8u * (2 * S + 2 + a); };
-  auto conv_bar = [&](int s) { return bars + 8u * (2 * S + 13 + s); };
   const uint32_t tmem_slot = bars + 8u * (2 * S + 4);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -362,7 +365,7 @@ __global__ void __launch_bounds__(TcCfg<BN, X3>::THREADS, 1) k_tc_gemm(const __g
   if (trace && threadIdx.x == 0) p.dbg[200] = clock64();
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < S; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); if (X3) mbar_init(conv_bar(s), X3_WARPS); }
+    for (int s = 0; s < S; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
     for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 8); }
     for (int w = 0; w < 8; ++w) mbar_init(bars + 8u * (2 * S + 5 + w), 1);   // per-warp `add` tile barriers
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -422,7 +425,7 @@ __global__ void __launch_bounds__(TcCfg<BN, X3>::THREADS, 1) k_tc_gemm(const __g
         const uint32_t tacc = tmem_base + as * BN;
         for (int kb = 0; kb < nkb; ++kb, ++it) {
           const int s = it % S;
-          mbar_wait(X3 ? conv_bar(s) : full_bar(s), (it / S) & 1); // X3: the converters have written the lo tiles
+          mbar_wait(full_bar(s), (it / S) & 1);
           if (trace && it < 32) p.dbg[64 + it] = clock64();
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
           const uint32_t sa = base + s * Cfg::STAGE, sb = sa + A_BYTES;
@@ -433,15 +436,7 @@ __global__ void __launch_bounds__(TcCfg<BN, X3>::THREADS, 1) k_tc_gemm(const __g
             const uint32_t oa = A_MN ? sa + k * 1024 : sa + k * 32, ob = B_MN ? sb + k * 1024 : sb + k * 32;
             const uint64_t ad = A_MN ? umma_desc(oa, 4096, 512, 1) : umma_desc(oa, 16, 1024, 2);
             const uint64_t bd = B_MN ? umma_desc(ob, 4096, 512, 1) : umma_desc(ob, 16, 1024, 2);
-            if (X3) {
-              const uint64_t adl = A_MN ? umma_desc(oa + RAW, 4096, 512, 1) : umma_desc(oa + RAW, 16, 1024, 2);
-              const uint64_t bdl = B_MN ? umma_desc(ob + RAW, 4096, 512, 1) : umma_desc(ob + RAW, 16, 1024, 2);
-              umma_tf32(tacc, ad, bdl, idesc, (kb | k) != 0 ? 1u : 0u);   // hi * lo   (small terms first)
-              umma_tf32(tacc, adl, bd, idesc, 1u);                        // lo * hi
-              umma_tf32(tacc, ad, bd, idesc, 1u);                         // hi * hi
-            } else {
-              umma_tf32(tacc, ad, bd, idesc, (kb | k) != 0 ? 1u : 0u);
-            }
+            umma_tf32(tacc, ad, bd, idesc, (kb | k) != 0 ? 1u : 0u);
           }
           umma_commit(empty_bar(s));                               // frees the smem stage when these MMAs retire
         }
@@ -453,20 +448,6 @@ __global__ void __launch_bounds__(TcCfg<BN, X3>::THREADS, 1) k_tc_gemm(const __g
                     (int)gridDim.x, total, tile_coords,
                     [&](uint32_t as) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tempty_bar(as)) : "memory"); },
                     trace);
-  } else if (X3) {                                                 // ---- 3xTF32 converters: warps 10..13
-    uint32_t it = 0;
-    const int ctid = threadIdx.x - 320;
-    for (int t = blockIdx.x; t < total; t += gridDim.x) {
-      int m0, n0, kbeg, nkb; tile_coords(t, m0, n0, kbeg, nkb);
-      for (int kb = 0; kb < nkb; ++kb, ++it) {
-        const int s = it % S;
-        mbar_wait(full_bar(s), (it / S) & 1);
-        const uint32_t sa = base + s * Cfg::STAGE;
-        x3_split_stage(sa, sa + RAW, RAW, ctid, p.x3_inplace != 0);
-        __syncwarp();
-        if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(conv_bar(s)) : "memory");
-      }
-    }
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
@@ -487,10 +468,10 @@ __global__ void __launch_bounds__(TcCfg<BN, X3>::THREADS, 1) k_tc_gemm(const __g
 // empty" barrier.
 // =============================================================================================
 constexpr int RAW2 = A_BYTES + 128 * TBK * 4;     // 32 KB per CTA per stage from TMA
-template <bool X3> struct Tc2Cfg {
-  static constexpr int S = X3 ? 3 : 6;
-  static constexpr int STAGE = RAW2 * (X3 ? 2 : 1);                // X3: raw [A|B half] then [A_lo|B_lo]
-  static constexpr int THREADS = 320 + (X3 ? 32 * X3_WARPS : 0);
+struct Tc2Cfg {
+  static constexpr int S = 6;
+  static constexpr int STAGE = RAW2;
+  static constexpr int THREADS = 320;
   static constexpr int SMEM = S * STAGE + 1024 + 8 * 4096 + 256;
 };
 
@@ -552,14 +533,12 @@ __device__ __forceinline__ void umma_commit_2sm(uint32_t bar) {   // arrives on 
 // BF16 (K-major operands only, groundwork for DESIGN.md §7 item 1): the operands are bf16 in HBM; a 128-byte tile row then
 // holds 64 k-values and one UMMA (kind::f16) covers K = 16 = the same 32 bytes, so stage bytes, swizzle, descriptors and
 // barriers are unchanged — only the k extent of a stage, the instruction kind and the format codes differ.
-// X3 (3xTF32, see TcCfg): each CTA's TMA signals its OWN "full" barrier; its converter warps (10..13) write the lo
-// tiles and report to the leader's "converted" barrier, which is what the MMA issuer waits on.
-template <bool A_MN, bool B_MN, bool BF16 = false, bool X3 = false>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(Tc2Cfg<X3>::THREADS, 1)
+template <bool A_MN, bool B_MN, bool BF16 = false>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(Tc2Cfg::THREADS, 1)
 k_tc_gemm2(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
            const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmAdd, const TcParams p) {
-  static_assert(!BF16 || (!A_MN && !B_MN && !X3), "bf16 operands: K-major only");
-  constexpr int BN = 256, S = Tc2Cfg<X3>::S, STAGE2 = Tc2Cfg<X3>::STAGE;
+  static_assert(!BF16 || (!A_MN && !B_MN), "bf16 operands: K-major only");
+  constexpr int BN = 256, S = Tc2Cfg::S, STAGE2 = Tc2Cfg::STAGE;
   constexpr int TKE = BF16 ? 64 : TBK;                              // k-values per stage
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -569,7 +548,6 @@ k_tc_gemm2(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
   auto empty_bar = [&](int s) { return bars + 8u * (S + s); };
   auto tfull_bar = [&](int a) { return bars + 8u * (2 * S + a); };
   auto tempty_bar = [&](int a) { return bars + 8u * (2 * S + 2 + a); };
-  auto conv_bar = [&](int s) { return bars + 8u * (2 * S + 13 + s); };
   const uint32_t tmem_slot = bars + 8u * (2 * S + 4);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -583,7 +561,7 @@ k_tc_gemm2(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
   if (trace && threadIdx.x == 0) p.dbg[200] = clock64();
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < S; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); if (X3) mbar_init(conv_bar(s), 2 * X3_WARPS); }
+    for (int s = 0; s < S; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
     for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 16); }   // 8 warps x 2 CTAs
     for (int w = 0; w < 8; ++w) mbar_init(bars + 8u * (2 * S + 5 + w), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -634,18 +612,6 @@ k_tc_gemm2(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
               for (int g = 0; g < 4; ++g) tma_prefetch_2d(&tmB, qn + g * 32, q0);
           }
           const uint32_t sa = base + s * STAGE2, sb = sa + A_BYTES;
-          if (X3) {                                                // bytes land on this CTA's own barrier (its converters wait there)
-            mbar_expect_tx(full_bar(s), RAW2);
-            if (!A_MN) tma_load_2d(&tmA, sa, full_bar(s), k0, m0);
-            else
-#pragma unroll
-              for (int g = 0; g < 4; ++g) tma_load_2d(&tmA, sa + g * 4096, full_bar(s), m0 + g * 32, k0);
-            if (!B_MN) tma_load_2d(&tmB, sb, full_bar(s), k0, nb0);
-            else
-#pragma unroll
-              for (int g = 0; g < 4; ++g) tma_load_2d(&tmB, sb + g * 4096, full_bar(s), nb0 + g * 32, k0);
-            continue;
-          }
           if (leader) mbar_expect_tx(full_bar(s), 2 * RAW2);       // bytes of both CTAs land on the leader's barrier
           if (!A_MN) tma_load_2d_2sm(&tmA, sa, full_bar(s), k0, m0);
           else
@@ -672,7 +638,7 @@ k_tc_gemm2(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
         const uint32_t tacc = tmem_base + as * BN;
         for (int kb = 0; kb < nkb; ++kb, ++it) {
           const int s = it % S;
-          mbar_wait_cluster(X3 ? conv_bar(s) : full_bar(s), (it / S) & 1);
+          mbar_wait_cluster(full_bar(s), (it / S) & 1);
           if (trace && it < 32) p.dbg[64 + it] = clock64();
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
           const uint32_t sa = base + s * STAGE2, sb = sa + A_BYTES;
@@ -682,13 +648,7 @@ k_tc_gemm2(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
             const uint64_t ad = A_MN ? umma_desc(oa, 4096, 512, 1) : umma_desc(oa, 16, 1024, 2);
             const uint64_t bd = B_MN ? umma_desc(ob, 4096, 512, 1) : umma_desc(ob, 16, 1024, 2);
             if (BF16) umma_f16_2sm(tacc, ad, bd, idesc, (kb | k) != 0 ? 1u : 0u);
-            else if (X3) {
-              const uint64_t adl = A_MN ? umma_desc(oa + RAW2, 4096, 512, 1) : umma_desc(oa + RAW2, 16, 1024, 2);
-              const uint64_t bdl = B_MN ? umma_desc(ob + RAW2, 4096, 512, 1) : umma_desc(ob + RAW2, 16, 1024, 2);
-              umma_tf32_2sm(tacc, ad, bdl, idesc, (kb | k) != 0 ? 1u : 0u);   // hi * lo   (small terms first)
-              umma_tf32_2sm(tacc, adl, bd, idesc, 1u);                        // lo * hi
-              umma_tf32_2sm(tacc, ad, bd, idesc, 1u);                         // hi * hi
-            } else umma_tf32_2sm(tacc, ad, bd, idesc, (kb | k) != 0 ? 1u : 0u);
+            else umma_tf32_2sm(tacc, ad, bd, idesc, (kb | k) != 0 ? 1u : 0u);
           }
           umma_commit_2sm(empty_bar(s));                           // frees the stage in both CTAs
         }
@@ -699,20 +659,6 @@ k_tc_gemm2(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
     tc_epilogue<BN>(p, &tmC, &tmAdd, tmem_base, stg_base, bars + 8u * (2 * S + 5), tfull_bar(0), cid, ncl, total, tile_coords,
                     [&](uint32_t as) { mbar_arrive_leader(tempty_bar(as)); },   // the LEADER's "accumulator empty" barrier
                     trace);
-  } else if (X3) {                                                 // ---- 3xTF32 converters: warps 10..13 of both CTAs
-    uint32_t it = 0;
-    const int ctid = threadIdx.x - 320;
-    for (int t = cid; t < total; t += ncl) {
-      int m0, n0, kbeg, nkb; tile_coords(t, m0, n0, kbeg, nkb);
-      for (int kb = 0; kb < nkb; ++kb, ++it) {
-        const int s = it % S;
-        mbar_wait(full_bar(s), (it / S) & 1);                      // this CTA's own tiles have landed
-        const uint32_t sa = base + s * STAGE2;
-        x3_split_stage(sa, sa + RAW2, RAW2, ctid, p.x3_inplace != 0);
-        __syncwarp();
-        if (lane == 0) mbar_arrive_leader(conv_bar(s));
-      }
-    }
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   cluster_sync_all();                                              // nobody may still address the peer's smem / TMEM
@@ -1233,24 +1179,18 @@ struct AttrOnce {
     if (!(done & bit)) { set(); done |= bit; }
   }
 };
-inline bool x3_inplace() { static const bool v = getenv("DX_X3_INPLACE") != nullptr; return v; }
 inline int tc_prefetch() { static const int v = getenv("DX_TC_NO_PREFETCH") ? 0 : 1; return v; }
 inline int x3_dbg() { static const int v = [] { const char* e = getenv("DX_X3_DBG"); return e ? atoi(e) : 0; }(); return v; }
-inline int x3_chunk() {   // k-blocks per chunk accumulator of k_tc_gemm_x3 (DX_X3_CHUNK overrides; see the kernel's header)
-  static const int v = [] { const char* e = getenv("DX_X3_CHUNK"); const int c = e ? atoi(e) : 2; return c < 1 ? 1 : c; }();
-  return v;
-}
 
-template <int BN, bool X3 = false>
+template <int BN>
 bool launch_tc(dx_stream_t s, const GemmP& g) {
-  using Cfg = TcCfg<BN, X3>;
+  using Cfg = TcCfg<BN>;
   CUtensorMap ta, tb;
-  // K-major: memory [MN rows][reduction cols]; MN-major: memory [reduction rows][MN cols].
-  // X3 reads the raw fp32 words (the converters need the exact value): plain FLOAT32 maps, no rounding on load.
-  if (g.a_kc) { if (!make_map(&ta, g.A, g.M, g.K, g.lda, TBK, TBM, false, X3)) return false; }
-  else        { if (!make_map(&ta, g.A, g.K, g.M, g.lda, 32, TBK, true, X3)) return false; }
-  if (g.b_kc) { if (!make_map(&tb, g.B, g.N, g.K, g.ldb, TBK, BN, false, X3)) return false; }
-  else        { if (!make_map(&tb, g.B, g.K, g.N, g.ldb, 32, TBK, true, X3)) return false; }
+  // K-major: memory [MN rows][reduction cols]; MN-major: memory [reduction rows][MN cols].  TFLOAT32 maps round on load.
+  if (g.a_kc) { if (!make_map(&ta, g.A, g.M, g.K, g.lda, TBK, TBM, false)) return false; }
+  else        { if (!make_map(&ta, g.A, g.K, g.M, g.lda, 32, TBK, true)) return false; }
+  if (g.b_kc) { if (!make_map(&tb, g.B, g.N, g.K, g.ldb, TBK, BN, false)) return false; }
+  else        { if (!make_map(&tb, g.B, g.K, g.N, g.ldb, 32, TBK, true)) return false; }
   // C through TMA when it is a plain strided matrix (no row scatter) with 16-byte aligned rows
   const bool tma_store = !g.c_idx && ((reinterpret_cast<uintptr_t>(g.C) & 15) == 0) && (g.ldc % 4 == 0) &&
                          !getenv("DX_TC_NO_TMA_STORE");
@@ -1296,29 +1236,29 @@ bool launch_tc(dx_stream_t s, const GemmP& g) {
   if (want_dbg) cudaMemsetAsync(dbg, 0, 256 * sizeof(long long), s);
   static const bool m_fast = getenv("DX_TC_M_FAST") != nullptr;
   TcParams p{g.M, g.N, g.K, g.C, g.ldc, g.c_idx, g.bias, g.add, g.ldadd, g.act, accum, k_chunk, tma_store ? 1 : 0, add_tma ? 1 : 0,
-             m_fast ? 0 : 1, x3_inplace() ? 1 : 0, x3_chunk(), tc_prefetch(), want_dbg ? dbg : nullptr};
+             m_fast ? 0 : 1, 0, 0, tc_prefetch(), want_dbg ? dbg : nullptr};
   const int total_tiles = gm * gn * splits;
   dim3 grid(total_tiles < num_sms ? total_tiles : num_sms);
-  static AttrOnce attr;   // per (BN, X3) instantiation; the operand-major variants share the footprint
+  static AttrOnce attr;   // per BN instantiation; the operand-major variants share the footprint
   attr([] {
-    cudaFuncSetAttribute(k_tc_gemm<BN, false, false, X3>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM);
-    cudaFuncSetAttribute(k_tc_gemm<BN, false, true, X3>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM);
-    cudaFuncSetAttribute(k_tc_gemm<BN, true, true, X3>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM);
-    cudaFuncSetAttribute(k_tc_gemm<BN, true, false, X3>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM);
+    cudaFuncSetAttribute(k_tc_gemm<BN, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM);
+    cudaFuncSetAttribute(k_tc_gemm<BN, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM);
+    cudaFuncSetAttribute(k_tc_gemm<BN, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM);
+    cudaFuncSetAttribute(k_tc_gemm<BN, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM);
   });
   auto run = [&](auto kern) { kern<<<grid, Cfg::THREADS, Cfg::SMEM, s>>>(ta, tb, tc, tadd, p); };
-  if (g.a_kc && g.b_kc) run(k_tc_gemm<BN, false, false, X3>);
-  else if (g.a_kc && !g.b_kc) run(k_tc_gemm<BN, false, true, X3>);
-  else if (!g.a_kc && !g.b_kc) run(k_tc_gemm<BN, true, true, X3>);
-  else run(k_tc_gemm<BN, true, false, X3>);
+  if (g.a_kc && g.b_kc) run(k_tc_gemm<BN, false, false>);
+  else if (g.a_kc && !g.b_kc) run(k_tc_gemm<BN, false, true>);
+  else if (!g.a_kc && !g.b_kc) run(k_tc_gemm<BN, true, true>);
+  else run(k_tc_gemm<BN, true, false>);
   ++g_launches;
   if (want_dbg) {
     long long h[256];
     cudaStreamSynchronize(s);
     cudaMemcpy(h, dbg, sizeof(h), cudaMemcpyDeviceToHost);
     const long long t0 = h[200];
-    fprintf(stderr, "[tc trace] M=%d N=%d K=%d BN=%d x3=%d splits=%d tiles=%d grid=%d | setup %lld | epilogues:", g.M, g.N, g.K, BN,
-            (int)X3, splits, total_tiles, (int)grid.x, h[201] - t0);
+    fprintf(stderr, "[tc trace] M=%d N=%d K=%d BN=%d splits=%d tiles=%d grid=%d | setup %lld | epilogues:", g.M, g.N, g.K, BN,
+            splits, total_tiles, (int)grid.x, h[201] - t0);
     for (int i = 0; i < 8 && h[208 + 2 * i]; ++i) fprintf(stderr, " [%lld..%lld]", h[208 + 2 * i] - t0, h[209 + 2 * i] - t0);
     fprintf(stderr, "\n");
     fprintf(stderr, "  producer(empty ok):");
@@ -1331,9 +1271,8 @@ bool launch_tc(dx_stream_t s, const GemmP& g) {
 }
 
 // 2-CTA launch (BN = 256).  Returns false if not applicable.
-template <bool X3>
 bool launch_tc2(dx_stream_t s, const GemmP& g) {
-  using Cfg = Tc2Cfg<X3>;
+  using Cfg = Tc2Cfg;
   static const bool disabled = getenv("DX_TC_NO_CG2") != nullptr;
   if (disabled) return false;
   const int num_sms = sm_count();
@@ -1354,10 +1293,10 @@ bool launch_tc2(dx_stream_t s, const GemmP& g) {
   if (!tma_store) return false;
   if (!g.a_kc && g.b_kc) return false;                          // (no product of the path has this form)
   CUtensorMap ta, tb, tc, tadd;
-  if (g.a_kc) { if (!make_map(&ta, g.A, g.M, g.K, g.lda, TBK, TBM, false, X3)) return false; }
-  else        { if (!make_map(&ta, g.A, g.K, g.M, g.lda, 32, TBK, true, X3)) return false; }
-  if (g.b_kc) { if (!make_map(&tb, g.B, g.N, g.K, g.ldb, TBK, 128, false, X3)) return false; }   // half of the B tile per CTA
-  else        { if (!make_map(&tb, g.B, g.K, g.N, g.ldb, 32, TBK, true, X3)) return false; }
+  if (g.a_kc) { if (!make_map(&ta, g.A, g.M, g.K, g.lda, TBK, TBM, false)) return false; }
+  else        { if (!make_map(&ta, g.A, g.K, g.M, g.lda, 32, TBK, true)) return false; }
+  if (g.b_kc) { if (!make_map(&tb, g.B, g.N, g.K, g.ldb, TBK, 128, false)) return false; }   // half of the B tile per CTA
+  else        { if (!make_map(&tb, g.B, g.K, g.N, g.ldb, 32, TBK, true)) return false; }
   if (!make_map(&tc, g.C, g.M, g.N, g.ldc, 32, 32, false, true)) return false;
   const bool add_tma = g.add && ((reinterpret_cast<uintptr_t>(g.add) & 15) == 0) && (g.ldadd % 4 == 0);
   if (g.add && !add_tma) return false;
@@ -1369,26 +1308,26 @@ bool launch_tc2(dx_stream_t s, const GemmP& g) {
   if (want_dbg) cudaMemsetAsync(dbg, 0, 256 * sizeof(long long), s);
   static const bool m_fast = getenv("DX_TC_M_FAST") != nullptr;
   TcParams p{g.M, g.N, g.K, g.C, g.ldc, g.c_idx, g.bias, g.add, g.ldadd, g.act, g.accum, k_chunk, 1, add_tma ? 1 : 0,
-             m_fast ? 0 : 1, x3_inplace() ? 1 : 0, x3_chunk(), tc_prefetch(), want_dbg ? dbg : nullptr};
+             m_fast ? 0 : 1, 0, 0, tc_prefetch(), want_dbg ? dbg : nullptr};
   const int ncl = total < num_sms / 2 ? total : num_sms / 2;
   static AttrOnce attr;
   attr([] {
-    cudaFuncSetAttribute(k_tc_gemm2<false, false, false, X3>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM);
-    cudaFuncSetAttribute(k_tc_gemm2<false, true, false, X3>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM);
-    cudaFuncSetAttribute(k_tc_gemm2<true, true, false, X3>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM);
+    cudaFuncSetAttribute(k_tc_gemm2<false, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM);
+    cudaFuncSetAttribute(k_tc_gemm2<false, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM);
+    cudaFuncSetAttribute(k_tc_gemm2<true, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM);
   });
   dim3 grid(2 * ncl);
-  if (g.a_kc && g.b_kc) k_tc_gemm2<false, false, false, X3><<<grid, Cfg::THREADS, Cfg::SMEM, s>>>(ta, tb, tc, tadd, p);
-  else if (g.a_kc && !g.b_kc) k_tc_gemm2<false, true, false, X3><<<grid, Cfg::THREADS, Cfg::SMEM, s>>>(ta, tb, tc, tadd, p);
-  else k_tc_gemm2<true, true, false, X3><<<grid, Cfg::THREADS, Cfg::SMEM, s>>>(ta, tb, tc, tadd, p);
+  if (g.a_kc && g.b_kc) k_tc_gemm2<false, false, false><<<grid, Cfg::THREADS, Cfg::SMEM, s>>>(ta, tb, tc, tadd, p);
+  else if (g.a_kc && !g.b_kc) k_tc_gemm2<false, true, false><<<grid, Cfg::THREADS, Cfg::SMEM, s>>>(ta, tb, tc, tadd, p);
+  else k_tc_gemm2<true, true, false><<<grid, Cfg::THREADS, Cfg::SMEM, s>>>(ta, tb, tc, tadd, p);
   ++g_launches;
   if (want_dbg) {
     long long h[256];
     cudaStreamSynchronize(s);
     cudaMemcpy(h, dbg, sizeof(h), cudaMemcpyDeviceToHost);
     const long long t0 = h[200];
-    fprintf(stderr, "[tc2 trace] M=%d N=%d K=%d x3=%d splits=%d pair-tiles=%d clusters=%d | setup %lld | epilogues:", g.M, g.N, g.K,
-            (int)X3, splits, total, ncl, h[201] - t0);
+    fprintf(stderr, "[tc2 trace] M=%d N=%d K=%d splits=%d pair-tiles=%d clusters=%d | setup %lld | epilogues:", g.M, g.N, g.K,
+            splits, total, ncl, h[201] - t0);
     for (int i = 0; i < 8 && h[208 + 2 * i]; ++i) fprintf(stderr, " [%lld..%lld]", h[208 + 2 * i] - t0, h[209 + 2 * i] - t0);
     fprintf(stderr, "\n  mma(full ok):");
     for (int i = 0; i < 20 && h[64 + i]; ++i) fprintf(stderr, " %lld", h[64 + i] - t0);
@@ -1444,7 +1383,7 @@ bool launch_x3(dx_stream_t s, const GemmP& g) {
   if (want_dbg && !dbg) cudaMalloc(&dbg, 256 * sizeof(long long));
   if (want_dbg) cudaMemsetAsync(dbg, 0, 256 * sizeof(long long), s);
   TcParams p{g.M, g.N, g.K, g.C, g.ldc, g.c_idx, g.bias, g.add, g.ldadd, g.act, accum, k_chunk, tma_store ? 1 : 0, add_tma ? 1 : 0,
-             m_fast ? 0 : 1, x3_dbg(), x3_chunk(), tc_prefetch(), want_dbg ? dbg : nullptr};
+             m_fast ? 0 : 1, x3_dbg(), 0, tc_prefetch(), want_dbg ? dbg : nullptr};
   static AttrOnce attr;
   attr([] {
     cudaFuncSetAttribute(k_tc_gemm_x3<false, false, CTA2, BNT>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM);
@@ -1587,8 +1526,8 @@ bool launch_tc2_bf16(dx_stream_t s, const GemmP& g, const void* A16, const void*
   const int num_sms = sm_count();
   const int total = gm2 * gn, ncl = total < num_sms / 2 ? total : num_sms / 2;
   static AttrOnce attr;
-  attr([] { cudaFuncSetAttribute(k_tc_gemm2<false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Tc2Cfg<false>::SMEM); });
-  k_tc_gemm2<false, false, true><<<dim3(2 * ncl), 320, Tc2Cfg<false>::SMEM, s>>>(ta, tb, tc, ta, p);
+  attr([] { cudaFuncSetAttribute(k_tc_gemm2<false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Tc2Cfg::SMEM); });
+  k_tc_gemm2<false, false, true><<<dim3(2 * ncl), 320, Tc2Cfg::SMEM, s>>>(ta, tb, tc, ta, p);
   ++g_launches;
   return true;
 }
@@ -1615,15 +1554,6 @@ bool tc_gemm(dx_stream_t s, const GemmP& g, int* tile_n, bool x3) {
   }
   if (tile_n) *tile_n = bn;
   if (x3) {
-    static const bool v1 = getenv("DX_X3_V1") != nullptr;      // first version: single accumulator, no chunked drain
-    if (v1) {
-      if (bn == 256 && launch_tc2<true>(s, g)) return true;
-      return bn == 256 ? launch_tc<256, true>(s, g) : (bn == 128 ? launch_tc<128, true>(s, g) : launch_tc<64, true>(s, g));
-    }
-    static const char* force = getenv("DX_X3_FORCE");           // experiments: w = wide pair tile, p = pair 256x128, s = single 128x128
-    if (force && force[0] == 'w' && launch_x3w(s, g)) return true;
-    if (force && force[0] == 'p' && launch_x3<true>(s, g)) return true;
-    if (force && force[0] == 's') return launch_x3<false>(s, g);
     static const bool no_narrow = getenv("DX_X3_NO_NARROW") != nullptr;
     if (g.N <= 64 && !no_narrow) return launch_x3<false, 32>(s, g);   // thin outputs: 32-column tiles
     // wide pair tiles whenever the output is wide enough: for dgrads / wgrads launch_x3w splits the reduction until the
@@ -1632,7 +1562,7 @@ bool tc_gemm(dx_stream_t s, const GemmP& g, int* tile_n, bool x3) {
     if (launch_x3<true>(s, g)) return true;
     return launch_x3<false>(s, g);
   }
-  if (bn == 256 && launch_tc2<false>(s, g)) return true;
+  if (bn == 256 && launch_tc2(s, g)) return true;
   return bn == 256 ? launch_tc<256>(s, g) : (bn == 128 ? launch_tc<128>(s, g) : launch_tc<64>(s, g));
 }
 

@@ -1,0 +1,83 @@
+"""Edge cases of the hot path on the GPU, default arithmetic (3xTF32) and the FFMA path: batches of one graph, batch
+sizes that straddle the 128-row tensor-core tiles, graphs with no edges at all and with all 49 directed edges (every
+self-loop and every feedback back-edge: what a decoded graph may contain), empty input."""
+import numpy as np
+import pytest
+import torch
+
+import dxvae_oracle as O
+from tests import util
+
+pytestmark = pytest.mark.gpu
+
+
+def _model(prec):
+    from dxvae_b200 import DXVAE
+    o = O.make_weights(2, 1.0)
+    m = DXVAE(); m.load_state_dict(o.state_dict()); m.verbose = False
+    m.precision = m.encode_precision = m.decode_precision = prec
+    return m, o
+
+
+def _batch(n, seed):
+    from dxvae_b200.dxdata import DXGraph
+    idx = list(np.random.default_rng(seed).integers(0, 1024, n))
+    X, P, _, _ = util.dataset_graphs(idx)
+    full = (list(np.repeat(np.arange(7), 7)), list(np.tile(np.arange(7), 7)))       # all 49 edges
+    E = []
+    for b in range(n):
+        if b % 3 == 0:
+            E.append(([], []))                                                          # no edges: every node is its own level
+        elif b % 3 == 1:
+            E.append(([int(s) for s in full[0]], [int(d) for d in full[1]]))
+        else:
+            E.append(util.random_edge_lists(1, 0.5, seed * 1000 + b)[0])
+    return X, P, E, util.adj_dense(E), [DXGraph(X[i], P[i], *E[i]) for i in range(n)]
+
+
+@pytest.mark.parametrize("prec", ["3xtf32", "fp32"])
+@pytest.mark.parametrize("n", [1, 2, 129, 257])
+def test_extreme_topologies_and_ragged_batch_sizes(prec, n):
+    m, o = _model(prec)
+    X, P, E, A, G = _batch(n, n)
+    with torch.no_grad():
+        q = m.encode(G)
+        mu_o, sd_o = o.encode(X, A)
+    assert (q.loc.cpu() - mu_o).abs().max().item() <= 1e-5 and (q.scale.cpu() - sd_o).abs().max().item() <= 1e-5
+    eps = torch.randn(n, 128, generator=torch.Generator().manual_seed(n))
+    out = m.forward(G, eps=eps)
+    # yardstick: the oracle in float64.  A third of these graphs have all 49 edges: six saturating neighbour messages
+    # per node amplify fp32 rounding of the gate functions, and the fp32 oracle itself sits ~1e-4 from float64 on the
+    # input-weight gradients; both arithmetics land within 1.04e-4 of float64 there (identical to three digits: the
+    # element-wise kernels are shared), so this test allows 2e-4 — the reference tolerance of 1e-4 is asserted on
+    # dataset topologies in test_gpu_parity / test_gpu_tf32 / test_cfg1_trained.
+    o64 = O.make_weights(2, 1.0).double()
+    mu6, sd6 = o64.encode(X.double(), A.double())
+    l6 = o64.loss(mu6, sd6, X.double(), P.double(), A.double(), eps.double())
+    for a, b in zip(out, l6):
+        assert abs(a.item() - b.item()) <= 1e-5 * abs(b.item()) + 1e-7, (a.item(), b.item())
+    out[0].backward(); l6[0].backward()
+    named = dict(m.named_parameters())
+    for name, p in o64.named_parameters():
+        rel = (p.grad - named[name].grad.cpu().double()).abs().max().item() / (p.grad.abs().max().item() + 1e-300)
+        assert rel <= 2e-4, (name, rel)
+    mu_o = mu_o.detach()
+    # greedy decode of the same latents: tie-aware comparison with the oracle
+    z = mu_o
+    gb = m.decode(z)
+    Xo, Po, Ao, mg = o.decode(z, return_margins=True)
+    em = torch.cat([l.flatten(1) for l in mg["edge"] + mg["self"]], 1).abs().min(1).values.numpy()
+    ok = (em > 2e-5) & (m.last_quant_margins.cpu().numpy() > 2e-5)
+    Ad = util.adj_from_masks(gb.adj.cpu().numpy().view(np.uint64))
+    assert np.array_equal(Ad[ok], Ao.numpy()[ok])
+    assert np.array_equal(gb.params.cpu().numpy().astype(np.int32)[ok], Po.numpy().astype(np.int32)[ok])
+
+
+def test_empty_input_raises():
+    from dxvae_b200 import DXVAE
+    m = DXVAE(); m.verbose = False
+    with pytest.raises((ValueError, RuntimeError)):
+        m.encode([])
+    with pytest.raises((ValueError, RuntimeError)):
+        m.forward([])
+    assert len(m.decode(torch.zeros(0, 128))) == 0          # nothing to decode: an empty batch comes back
