@@ -46,21 +46,28 @@ def test_extreme_topologies_and_ragged_batch_sizes(prec, n):
     assert (q.loc.cpu() - mu_o).abs().max().item() <= 1e-5 and (q.scale.cpu() - sd_o).abs().max().item() <= 1e-5
     eps = torch.randn(n, 128, generator=torch.Generator().manual_seed(n))
     out = m.forward(G, eps=eps)
-    # yardstick: the oracle in float64.  A third of these graphs have all 49 edges: six saturating neighbour messages
-    # per node amplify fp32 rounding of the gate functions, and the fp32 oracle itself sits ~1e-4 from float64 on the
-    # input-weight gradients; both arithmetics land within 1.04e-4 of float64 there (identical to three digits: the
-    # element-wise kernels are shared), so this test allows 2e-4 — the reference tolerance of 1e-4 is asserted on
-    # dataset topologies in test_gpu_parity / test_gpu_tf32 / test_cfg1_trained.
+    # Yardstick: the oracle in float64; band per tensor: the reference tolerance, or twice the fp32 oracle's own distance
+    # to float64 where that is larger.  A third of these graphs have all 49 edges: six saturating neighbour messages per
+    # node and ~90 k relu units per graph near their kinks make the fp32 evaluation itself noisy (the fp32 oracle is up
+    # to 1.5e-3 from float64 on single tensors at n = 257); the 1e-4 tolerance proper is asserted on dataset topologies
+    # in test_gpu_parity / test_gpu_tf32 / test_cfg1_trained.
     o64 = O.make_weights(2, 1.0).double()
     mu6, sd6 = o64.encode(X.double(), A.double())
     l6 = o64.loss(mu6, sd6, X.double(), P.double(), A.double(), eps.double())
+    mu3, sd3 = o.encode(X, A)
+    l3 = o.loss(mu3, sd3, X, P, A, eps)
     for a, b in zip(out, l6):
         assert abs(a.item() - b.item()) <= 1e-5 * abs(b.item()) + 1e-7, (a.item(), b.item())
-    out[0].backward(); l6[0].backward()
-    named = dict(m.named_parameters())
+    out[0].backward(); l6[0].backward(); l3[0].backward()
+    named = dict(m.named_parameters()); n32 = dict(o.named_parameters())
+    bad = []
     for name, p in o64.named_parameters():
-        rel = (p.grad - named[name].grad.cpu().double()).abs().max().item() / (p.grad.abs().max().item() + 1e-300)
-        assert rel <= 2e-4, (name, rel)
+        den = p.grad.abs().max().item() + 1e-300
+        rel = (p.grad - named[name].grad.cpu().double()).abs().max().item() / den
+        noise = (p.grad - n32[name].grad.double()).abs().max().item() / den
+        if rel > max(1e-4, 2.0 * noise):
+            bad.append((name, rel, noise))
+    assert not bad, bad
     mu_o = mu_o.detach()
     # greedy decode of the same latents: tie-aware comparison with the oracle
     z = mu_o

@@ -82,6 +82,17 @@ def test_decode_one_million_patches_to_syx_round_trip(lib):
     assert P.shape == (N_FULL, 7, 21)
     assert float(P.abs().min()) >= 0 and float(P[:, 1:, 0:9].max()) <= 99 and float(P[:, 0, 18].max()) <= 31
     assert float(P[:, 1:, 20].max()) <= 2 and float(P[:, 0, 8].max()) <= 48          # rc quirk, transpose
+    # the CPU oracle on a sample taken across the whole range: same topology and parameters wherever every discrete
+    # decision clears its tie margin (edge logits from the oracle run, quantiser margins reported by the kernel)
+    idx = torch.arange(0, N_FULL, N_FULL // 96)[:96]
+    Xo, Po, Ao, mgo = o.decode(z[idx], return_margins=True)
+    em = torch.cat([l.flatten(1) for l in mgo["edge"] + mgo["self"]], 1).abs().min(1).values.numpy()
+    ok = (em > 2e-5) & (m.last_quant_margins[idx.cuda()].cpu().numpy() > 2e-5)
+    assert ok.sum() >= 48
+    from tests import util
+    Ad = util.adj_from_masks(a.adj[idx.cuda()].cpu().numpy().view(np.uint64))
+    assert np.array_equal(Ad[ok], Ao.numpy()[ok])
+    assert np.array_equal(P[idx.cuda()].cpu().numpy().astype(np.int32)[ok], Po.numpy().astype(np.int32)[ok])
     # position / chunk invariance on a shuffled subset
     pick = torch.randperm(N_FULL, generator=torch.Generator().manual_seed(2))[:30000]
     m.max_chunk = 4096
