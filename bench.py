@@ -284,6 +284,9 @@ def run_ours(args):
 
     # ---- the public API: lists of host graph objects through DXVAE.forward / backward / optimiser step
     glists = [list(host[k * M:(k + 1) * M]) for k in range(NPOOL)]       # the user's data: Python lists of graph objects
+    import random as _random
+    for k, gl in enumerate(glists):                                      # in epoch order, as DXVAE.train leaves them (model.py:380
+        _random.Random(100 + k).shuffle(gl)                              # random.shuffle): the batcher gathers, it cannot slice
     opt = FusedAdamW(model, lr=1e-3)
     loss_host = torch.empty(max(K, W, 1), 5).pin_memory()
 
@@ -530,7 +533,8 @@ def run_ours(args):
                 "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 20,
                         "ms_per_step": ms_e2e / K,
                         "api": "opt.zero_grad(); loss = model(list_of_graphs)[0]; loss.backward(); opt.step()  "
-                               "(DXVAE.forward on a Python list of host graph objects, FusedAdamW)",
+                               "(DXVAE.forward on a shuffled Python list of host graph objects — row views of a pinned "
+                               "DXGraphBatch, what DXDataset / a decoded batch hand out — FusedAdamW)",
                         "tensor_input": {"value": e2e_tensor, "ms_per_step": ms_t / K,
                                          "note": "same step fed pre-batched pinned tensors (Trainer.grad_step)"}},
                 "roofline": roof, "roofline_encode": roof_enc, "roofline_decode": roof_dec,

@@ -136,12 +136,16 @@ class DXGraphBatch:
             return None
         base = own[0]
         idx = []
-        for g in graphs:
-            o = getattr(g, "_owner", None)
-            if o is None or o[0] is not base or g.ndata.get("X") is not o[2] or g.ndata.get("params") is not o[3] \
-                    or g._edges is not o[4]:
-                return None
-            idx.append(o[1])
+        add = idx.append
+        try:                                    # (tight loop: this runs once per graph of every training batch)
+            for g in graphs:
+                o = g._owner
+                nd = g.ndata
+                if o[0] is not base or nd["X"] is not o[2] or nd["params"] is not o[3] or g._edges is not o[4]:
+                    return None
+                add(o[1])
+        except (TypeError, KeyError, AttributeError):    # a foreign graph object, or one whose ndata was replaced
+            return None
         n = len(idx)
         el = base._edge_lists
         if idx[-1] - idx[0] == n - 1 and all(idx[k + 1] - idx[k] == 1 for k in range(n - 1)):

@@ -1,4 +1,4 @@
-"""B=128 train step (BASELINE config 2 shape): eager vs CUDA-graph replay, fp32 vs tf32."""
+"""B=128 train step (BASELINE config 2 shape): eager vs CUDA-graph replay in every arithmetic."""
 import sys, time, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
@@ -9,7 +9,7 @@ from dxvae_b200.train import Trainer
 
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 128
 pool = voices_to_batch(random_voices(1024, seed=3))
-for prec in ("tf32", "fp32"):
+for prec in ("3xtf32", "tf32", "fp32"):
     for gmax in (0, 1024):
         torch.manual_seed(0)
         m = DXVAE(); m.verbose = False; m.precision = prec
