@@ -340,7 +340,7 @@ def run_ours(args):
         tensor_step(i)
     ms_t, _, _ = timed(tensor_step, K)
     e2e_tensor = M * world * K / (ms_t * 1e-3)
-    h2d = M * (7 * 27 * 4 + 7 * 21 * 4 + 8)
+    h2d = M * (7 * 27 * 4 + 7 * 21 * 4 + 8 + 8)      # X, params, adjacency rows (read by the device out of pinned memory) + the index list
 
     # ---- roofline of the dominant kernel family: per-launch events on the launching stream
     # (every rank runs the pass so the collectives inside the step stay matched; rank 0 reports)

@@ -27,6 +27,7 @@ SIGNATURES = {
     "dxvae_batch_steps": (C.c_int, [I64, P, P, P, P, P, SZ, P]),
     "dxvae_batch_steps_host": (C.c_int, [I64, P, P, P]),
     "dxvae_pack_graphs": (C.c_int, [I64, P, P, P, P, P]),
+    "dxvae_pack_graphs_indexed": (C.c_int, [I64, P, P, P, P, P, P, P, P]),
     "dxvae_unpack_graphs": (C.c_int, [I64, P, P, P, P, P]),
     "dxvae_voices_to_graphs": (C.c_int, [I64, P, P, P, P, P, P, P]),
     "dxvae_pack_syx": (C.c_int, [I64, P, P, P]),

@@ -177,6 +177,11 @@ int dxvae_pack_graphs(int64_t B, const float* Xg, const float* Pg, float* Xn, in
   DX_CHECK(B > 0, "pack_graphs: empty batch");
   return pack_graphs(DX_ST(stream), B, Xg, Pg, Xn, cls);
 }
+int dxvae_pack_graphs_indexed(int64_t B, const int64_t* idx, const float* Xg, const float* Pg, const uint64_t* adj_g,
+                              float* Xn, int32_t* cls, uint64_t* adj, void* stream) {
+  DX_CHECK(B > 0, "pack_graphs_indexed: empty batch");
+  return pack_graphs_indexed(DX_ST(stream), B, idx, Xg, Pg, adj_g, Xn, cls, adj);
+}
 int dxvae_unpack_graphs(int64_t B, const float* Xn, const float* Pn, float* Xg, float* Pg, void* stream) {
   DX_CHECK(B > 0, "unpack_graphs: empty batch");
   return unpack_graphs(DX_ST(stream), B, Xn, Pn, Xg, Pg);

@@ -130,6 +130,8 @@ int batch_steps(dx_stream_t st, int64_t B, const uint64_t* adj, int32_t* step_pt
                 int32_t* step_ptr_host, void* ws, size_t ws_bytes);
 int batch_steps_host(int64_t B, const uint64_t* adj, int32_t* step_ptr, int32_t* step_rows);
 int pack_graphs(dx_stream_t st, int64_t B, const float* Xg, const float* Pg, float* Xn, int32_t* cls);
+int pack_graphs_indexed(dx_stream_t st, int64_t B, const int64_t* idx, const float* Xg, const float* Pg,
+                        const uint64_t* adjg, float* Xn, int32_t* cls, uint64_t* adj);
 int unpack_graphs(dx_stream_t st, int64_t B, const float* Xn, const float* Pn, float* Xg, float* Pg);
 int voices_to_graphs(dx_stream_t st, int64_t B, const uint8_t* voices, float* Xn, int32_t* cls, uint64_t* adj,
                      float* Xg, float* Pg);

@@ -1543,7 +1543,10 @@ bool tc_gemm(dx_stream_t s, const GemmP& g, int* tile_n, bool x3) {
   // TMA needs 16-byte aligned bases and row pitches; everything else (ragged M/N/K) is handled by
   // the tensor maps' out-of-bounds zero fill / clipping.
   if (!al16(g.A) || !al16(g.B) || (g.lda % 4) || (g.ldb % 4)) return false;
-  if ((double)g.M * g.N * g.K < 1.0e6) return false;          // launch-bound anyway
+  // Products with a tiny weight side go to the FFMA kernels.  The rule looks at N x K only, never at the row count: which
+  // kernel family computes a forward product must not depend on how many patches share the batch (a one-graph batch
+  // and a 32768-graph batch give a patch the same bits).
+  if ((double)g.N * g.K < 4096.0) return false;
   int bn = g.N >= 192 ? 256 : (g.N >= 96 ? 128 : 64);
   // Small batches (M of a few hundred rows): a 128 x 256 tiling leaves most SMs idle and each CTA streams a large
   // slice of the weight matrix alone; narrower tiles spread that stream over more SMs (latency, not throughput).

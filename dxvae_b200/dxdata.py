@@ -16,6 +16,9 @@ import os
 import struct
 from pathlib import Path
 
+import operator
+import weakref
+
 import numpy as np
 import torch
 
@@ -64,13 +67,43 @@ class _Adj:
         return a
 
 
+class _ViewData(dict):
+    """ndata of a graph that is a row view of a DXGraphBatch: replacing or removing an entry detaches the graph from its
+    batch (the batcher's fast path then treats it as a foreign graph), so the fast path needs no per-graph comparison."""
+    __slots__ = ("_g",)
+
+    def _detach(self):
+        self._g._oid = None
+
+    def __setitem__(self, k, v):
+        self._detach(); dict.__setitem__(self, k, v)
+
+    def __delitem__(self, k):
+        self._detach(); dict.__delitem__(self, k)
+
+    def pop(self, *a):
+        self._detach(); return dict.pop(self, *a)
+
+    def popitem(self):
+        self._detach(); return dict.popitem(self)
+
+    def update(self, *a, **kw):
+        self._detach(); dict.update(self, *a, **kw)
+
+    def clear(self):
+        self._detach(); dict.clear(self)
+
+    def setdefault(self, *a):
+        self._detach(); return dict.setdefault(self, *a)
+
+
 class DXGraph:
     """One 7-node patch graph: the subset of the DGLGraph API the reference touches."""
 
     def __init__(self, X, params, src, dst):
         self.ndata = {"X": X, "params": params}
         self._edges = ([int(s) for s in src], [int(d) for d in dst])
-        self._owner = None      # (DXGraphBatch, index, X view, params view, edge tuple) when this graph is a row view of a batch
+        self._oid = None        # (batch token << 32 | row) while this graph is an untouched row view of a DXGraphBatch
 
     def edges(self):
         return (torch.tensor(self._edges[0], dtype=torch.int64), torch.tensor(self._edges[1], dtype=torch.int64))
@@ -101,6 +134,35 @@ def _graph_edges(g):
     return s.tolist(), d.tolist()
 
 
+_GET_OID = operator.attrgetter("_oid")
+_BATCHES = weakref.WeakValueDictionary()      # batch token -> DXGraphBatch that handed out row views
+_next_token = [1]
+
+
+class _LazyEdgeLists:
+    """Edge lists of a gathered sub-batch, materialised on first use (only the host batcher and graph views need them)."""
+
+    def __init__(self, base, idx):
+        self._base, self._idx, self._lists = base, idx, None
+
+    def _get(self):
+        if self._lists is None:
+            b = self._base
+            self._lists = [b[int(i)] for i in self._idx]
+        return self._lists
+
+    def __len__(self):
+        return len(self._idx)
+
+    def __getitem__(self, i):
+        if isinstance(i, slice):
+            return self._get()[i]
+        return self._base[int(self._idx[i])]
+
+    def __iter__(self):
+        return iter(self._get())
+
+
 class DXGraphBatch:
     """B graphs as three arrays: X (B,7,27) f32, params (B,7,21) f32, adj (B,) int64 masks
     (bit src*7+dst).  Indexing / iteration yields DXGraph views, so it can be passed anywhere
@@ -111,13 +173,16 @@ class DXGraphBatch:
         self._edge_lists = edge_lists          # original insertion order when known
 
     @classmethod
-    def from_graphs(cls, graphs):
+    def from_graphs(cls, graphs, staging=False):
+        """staging=True (the batcher's own call, DXVAE._prepare): rows drawn from a PINNED host batch come back as an
+        IndexedBatch — the parent plus an index list — which the device gathers straight out of the pinned memory
+        (dxvae_pack_graphs_indexed); nothing is gathered or staged on the host."""
         if isinstance(graphs, DXGraphBatch):
             return graphs
         graphs = list(graphs)
         if not graphs:
             raise ValueError("empty batch")
-        fast = cls._from_views(graphs)
+        fast = cls._from_views(graphs, staging)
         if fast is not None:
             return fast
         X = torch.stack([g.ndata["X"].detach().to("cpu", torch.float32) for g in graphs])
@@ -127,34 +192,39 @@ class DXGraphBatch:
         return cls(X, P, adj, edges)
 
     @classmethod
-    def _from_views(cls, graphs):
+    def _from_views(cls, graphs, staging=False):
         """Batcher fast path: graphs that are untouched row views of ONE DXGraphBatch (what iterating / indexing a batch or
         a DXDataset hands out) are re-batched by index — one gather (a plain slice when the rows are consecutive) instead
-        of stacking thousands of (7,27) tensors.  Returns None when any graph is foreign or was modified."""
-        own = getattr(graphs[0], "_owner", None)
-        if own is None:
+        of stacking thousands of (7,27) tensors.  Returns None when any graph is foreign or was modified (a view whose
+        ndata was touched has detached itself, see _ViewData).  With staging=True rows of a pinned host batch are not
+        gathered at all: the result is an IndexedBatch (parent + index list) for the device to gather."""
+        try:                                                    # ONE pass over the (scattered) graph objects, at C speed: this
+            oid = np.fromiter(map(_GET_OID, graphs), np.int64, count=len(graphs))   # runs once per graph of every training batch
+        except (TypeError, AttributeError):                     # a foreign graph object or a detached view (_oid None)
             return None
-        base = own[0]
-        idx = []
-        add = idx.append
-        try:                                    # (tight loop: this runs once per graph of every training batch)
-            for g in graphs:
-                o = g._owner
-                nd = g.ndata
-                if o[0] is not base or nd["X"] is not o[2] or nd["params"] is not o[3] or g._edges is not o[4]:
-                    return None
-                add(o[1])
-        except (TypeError, KeyError, AttributeError):    # a foreign graph object, or one whose ndata was replaced
+        tok = oid >> 32
+        if not bool(np.all(tok == tok[0])):
             return None
-        n = len(idx)
+        base = _BATCHES.get(int(tok[0]))
+        if base is None:
+            return None
+        idx_np = oid & 0xFFFFFFFF
+        owners = graphs
+        n = len(owners)
         el = base._edge_lists
-        if idx[-1] - idx[0] == n - 1 and all(idx[k + 1] - idx[k] == 1 for k in range(n - 1)):
-            sl = slice(idx[0], idx[0] + n)
+        if n == 1 or bool(np.all(np.diff(idx_np) == 1)):
+            sl = slice(int(idx_np[0]), int(idx_np[0]) + n)
             return cls(base.X[sl], base.params[sl], base.adj[sl], el[sl] if el is not None else None)
-        ii = torch.as_tensor(idx, dtype=torch.int64, device=base.X.device)
-        pin = (not base.X.is_cuda) and base.X.is_pinned()
-        take = lambda t: (t.index_select(0, ii).pin_memory() if pin else t.index_select(0, ii))
-        return cls(take(base.X), take(base.params), take(base.adj), [el[i] for i in idx] if el is not None else None)
+        idx = idx_np
+        ii = torch.from_numpy(idx_np)
+        if base.X.is_cuda:
+            ii = ii.to(base.X.device)
+        sub_el = _LazyEdgeLists(el, idx) if el is not None else None
+        pinned = (not base.X.is_cuda) and base.X.is_pinned()
+        if pinned and staging:
+            return IndexedBatch(base, idx_np, sub_el)
+        take = (lambda t: t.index_select(0, ii).pin_memory()) if pinned else (lambda t: t.index_select(0, ii))
+        return cls(take(base.X), take(base.params), take(base.adj), sub_el)
 
     def __len__(self):
         return self.X.shape[0]
@@ -175,9 +245,16 @@ class DXGraphBatch:
         if X.is_cuda:
             return DXGraph(X.cpu(), P.cpu(), e[0], e[1])
         g = DXGraph.__new__(DXGraph)
-        g.ndata = {"X": X, "params": P}
+        nd = _ViewData(); dict.__setitem__(nd, "X", X); dict.__setitem__(nd, "params", P); nd._g = g
+        g.ndata = nd
         g._edges = (list(e[0]), list(e[1]))
-        g._owner = (self, i, X, P, g._edges)
+        tok = self.__dict__.get("_token")
+        if tok is None:
+            tok = self._token = _next_token[0]
+            _next_token[0] += 1
+            _BATCHES[tok] = self
+        g._oid = (tok << 32) | i
+        g._ob = self                      # (keeps the batch alive as long as one of its views is)
         return g
 
     def __iter__(self):
@@ -195,6 +272,32 @@ class DXGraphBatch:
 
     def cpu(self):
         return DXGraphBatch(self.X.cpu(), self.params.cpu(), self.adj.cpu(), self._edge_lists)
+
+
+class IndexedBatch(DXGraphBatch):
+    """Rows `index` of a pinned host DXGraphBatch, not gathered: what the batcher hands the device when a training loop
+    draws a shuffled batch from its dataset.  X / params / adj materialise (host gather) only if somebody asks for them."""
+
+    def __init__(self, base, index, edge_lists=None):
+        self.base, self.index = base, index
+        self._edge_lists = edge_lists
+        self._mat = None
+
+    def _m(self):
+        if self._mat is None:
+            ii = torch.from_numpy(self.index)
+            self._mat = (self.base.X.index_select(0, ii), self.base.params.index_select(0, ii), self.base.adj.index_select(0, ii))
+        return self._mat
+
+    X = property(lambda self: self._m()[0])
+    params = property(lambda self: self._m()[1])
+    adj = property(lambda self: self._m()[2])
+
+    def __len__(self):
+        return len(self.index)
+
+    def materialise(self):
+        return DXGraphBatch(self.X, self.params, self.adj, self._edge_lists)
 
 
 def _to_i64(m):

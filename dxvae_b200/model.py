@@ -16,7 +16,7 @@ import torch.nn as nn
 from torch.distributions.normal import Normal
 
 from . import _abi, _lib
-from .dxdata import DXGraphBatch
+from .dxdata import DXGraphBatch, IndexedBatch
 from .params import param_table
 
 _FIXED = dict(n_nodes=7, n_params=21, size_X=27, size_X0=23, size_H=512, size_Z=128)
@@ -72,6 +72,8 @@ class DXVAE(nn.Module):
         self.last_margins = None
         self.last_quant_margins = None
         self.last_loss5 = None      # device tensor (total, x0, xi, e, kld*w) of the latest forward()
+        self._prep_tag = None       # workspace tag of the batcher (set while it runs on the upload stream)
+        self._upload_stream = None
         self._last_gflat = None     # flat gradient blob the latest backward() handed out views of
         # arithmetic of the dense products, per entry point: "3xtf32" (default: tcgen05 tensor cores with error-compensated
         # hi/lo operand splits and chunked FP32 accumulation — FP32-accurate, meets the reference tolerances of
@@ -116,7 +118,7 @@ class DXVAE(nn.Module):
             raise ValueError("precision must be 'fp32', '3xtf32' or 'tf32'")
         return self._PREC[self.precision]
 
-    def _workspace(self, op, B, fresh=False, d=None):
+    def _workspace(self, op, B, fresh=False, d=None, tag=None):
         """Caller-owned scratch for one native call.  d (a prepared batch): sized for ITS schedules — the largest encoder
         level, the active rows of the teacher-forced steps (dxvae_workspace_bytes_sched) — instead of the worst case."""
         L = _lib.lib()
@@ -132,7 +134,7 @@ class DXVAE(nn.Module):
             n = int(L.dxvae_workspace_bytes(op, B))
         if fresh:
             return torch.empty(n, dtype=torch.uint8, device="cuda")
-        key = (op,)
+        key = (op,) if tag is None else (op, tag)
         ws = self._ws.get(key)
         if ws is None or ws.numel() < n:
             self._ws[key] = None
@@ -146,22 +148,35 @@ class DXVAE(nn.Module):
         Host lists go through the C++ host batcher (flat CSR + level schedule + feedback
         marks); device-resident batches through the device scheduler."""
         L = _lib.require_cuda()
-        gb = DXGraphBatch.from_graphs(G)
+        gb = DXGraphBatch.from_graphs(G, staging=True)
         B = len(gb)
         if B == 0:
             raise ValueError("empty batch")
         st = _stream()
         d = _DevBatch()
         d.B = B
-        Xg = gb.X.to("cuda", torch.float32, non_blocking=True).contiguous()
-        Pg = gb.params.to("cuda", torch.float32, non_blocking=True).contiguous()
         d.Xn = torch.empty(7, B, 32, device="cuda")
         d.cls = torch.empty(14, B, dtype=torch.int32, device="cuda")
-        _lib.check(L.dxvae_pack_graphs(B, Xg.data_ptr(), Pg.data_ptr(), d.Xn.data_ptr(), d.cls.data_ptr(), st),
-                   "dxvae_pack_graphs")
+        indexed = isinstance(gb, IndexedBatch)
+        if indexed and B <= self.host_batcher_max and host_batcher is not False:
+            gb, indexed = gb.materialise(), False        # small batches take the host batcher (explicit CSR): gather on the host
+        if indexed:
+            # rows of a pinned host batch: upload the index list, the device gathers X / params / adjacency straight out of
+            # the pinned memory into the kernels' layout (this IS the step's host-to-device transfer)
+            base = gb.base
+            ii = torch.from_numpy(gb.index).to("cuda", non_blocking=True)
+            d.adj = torch.empty(B, dtype=torch.int64, device="cuda")
+            _lib.check(L.dxvae_pack_graphs_indexed(B, ii.data_ptr(), base.X.data_ptr(), base.params.data_ptr(), base.adj.data_ptr(),
+                                                   d.Xn.data_ptr(), d.cls.data_ptr(), d.adj.data_ptr(), st),
+                       "dxvae_pack_graphs_indexed")
+        else:
+            Xg = gb.X.to("cuda", torch.float32, non_blocking=True).contiguous()
+            Pg = gb.params.to("cuda", torch.float32, non_blocking=True).contiguous()
+            _lib.check(L.dxvae_pack_graphs(B, Xg.data_ptr(), Pg.data_ptr(), d.Xn.data_ptr(), d.cls.data_ptr(), st),
+                       "dxvae_pack_graphs")
         # host-resident batches of a few thousand graphs go through the C++ host batcher (explicit CSR, no device round
         # trip); larger ones are uploaded and scheduled on the device (same result, bit for bit)
-        use_host = (not gb.adj.is_cuda and B <= self.host_batcher_max) if host_batcher is None else host_batcher
+        use_host = False if indexed else ((not gb.adj.is_cuda and B <= self.host_batcher_max) if host_batcher is None else host_batcher)
         d.level_ptr = np.zeros(16, np.int32)       # 8 level offsets, then per-level counts of back-edge-target rows
         d.csr = None
         if use_host:
@@ -191,16 +206,40 @@ class DXVAE(nn.Module):
                 _lib.check(L.dxvae_batch_steps_host(B, pv(adj), pv(d.step_ptr), pv(srows)), "dxvae_batch_steps_host")
                 d.step_rows = torch.from_numpy(srows[:max(1, int(d.step_ptr[33]))]).to("cuda")
         else:
-            d.adj = gb.adj.to("cuda", torch.int64).contiguous()
+            if not indexed:
+                d.adj = gb.adj.to("cuda", torch.int64, non_blocking=True).contiguous()
             self._schedule(d)
             d.step_ptr = d.step_rows = None
             if need_cls and self.compact_steps:
                 d.step_ptr = np.zeros(34, np.int32)
                 d.step_rows = torch.empty(33 * B, dtype=torch.int32, device="cuda")
                 sp_dev = torch.empty(34, dtype=torch.int32, device="cuda")
-                ws = self._workspace(_abi.OP_SCHEDULE, B)
+                ws = self._workspace(_abi.OP_SCHEDULE, B, tag=self._prep_tag)
                 _lib.check(L.dxvae_batch_steps(B, d.adj.data_ptr(), sp_dev.data_ptr(), d.step_rows.data_ptr(),
                                                d.step_ptr.ctypes.data, ws.data_ptr(), ws.numel(), st), "dxvae_batch_steps")
+        return d
+
+    def _prepare_uploading(self, G):
+        """_prepare for HOST-resident graphs on a side stream: the batcher's H2D copies, its pack / schedule kernels and the
+        two small read-backs that size the schedule (which synchronise their stream) then overlap the compute the caller
+        has already queued — typically the previous training step — instead of waiting behind it.  The compute stream
+        picks the batch up through an event."""
+        if isinstance(G, DXGraphBatch) and G.X.is_cuda:
+            return self._prepare(G, need_cls=True)       # device-resident input: stay ordered with its producer
+        cur = torch.cuda.current_stream()
+        if self._upload_stream is None:
+            self._upload_stream = torch.cuda.Stream()
+        side = self._upload_stream
+        self._prep_tag = "upload"
+        try:
+            with torch.cuda.stream(side):
+                d = self._prepare(G, need_cls=True)
+        finally:
+            self._prep_tag = None
+        for t in (d.Xn, d.cls, d.adj, d.level_rows, d.step_rows, d.level):
+            if isinstance(t, torch.Tensor) and t.is_cuda:
+                t.record_stream(cur)                     # allocated on the upload stream, consumed on the compute stream
+        cur.wait_stream(side)
         return d
 
     def _schedule(self, d):
@@ -209,7 +248,7 @@ class DXVAE(nn.Module):
         d.level = torch.empty(B, 7, dtype=torch.uint8, device="cuda")
         d.level_rows = torch.empty(6 * B, dtype=torch.int32, device="cuda")
         lp_dev = torch.empty(16, dtype=torch.int32, device="cuda")     # 8 offsets + 8 per-level prefix sizes (ABI: 16 ints)
-        ws = self._workspace(_abi.OP_SCHEDULE, B)
+        ws = self._workspace(_abi.OP_SCHEDULE, B, tag=self._prep_tag)
         _lib.check(L.dxvae_batch_schedule(B, d.adj.data_ptr(), d.level.data_ptr(), lp_dev.data_ptr(),
                                           d.level_rows.data_ptr(), d.level_ptr.ctypes.data, ws.data_ptr(), ws.numel(),
                                           _stream()), "dxvae_batch_schedule")
@@ -330,7 +369,7 @@ class DXVAE(nn.Module):
     def forward(self, G_true, w_env=2, w_frq=5, w_kld=0.01, eps=None):
         """model.py:369-372: encode + loss, fused into one native call (dxvae_elbo_step)."""
         self._ensure_flat()
-        d = self._prepare(G_true, need_cls=True)
+        d = self._prepare_uploading(G_true)
         self.hidden = d.B
         if eps is None:
             eps = torch.empty(d.B, 128, device="cuda").normal_()

@@ -111,6 +111,12 @@ int dxvae_batch_steps_host(int64_t B, const uint64_t* adj_host, int32_t* step_pt
 
 /* Graph-major reference tensors -> what the kernels read. */
 int dxvae_pack_graphs(int64_t B, const float* Xg, const float* Pg, float* Xn, int32_t* cls, void* stream);
+/* The same for the B rows idx[b] (device int64 list; NULL = identity) of a larger graph-major store Xg / Pg / adj_g — how
+ * a training loop draws a shuffled batch from its dataset (model.py:380-382).  Xg, Pg and adj_g may point to PINNED HOST
+ * memory (cudaHostAlloc / torch pin_memory: mapped into the device's address space): the gather then is the host-to-device
+ * transfer of the batch.  cls and adj may be NULL. */
+int dxvae_pack_graphs_indexed(int64_t B, const int64_t* idx, const float* Xg, const float* Pg, const uint64_t* adj_g,
+                              float* Xn, int32_t* cls, uint64_t* adj, void* stream);
 /* Node-major decode outputs -> graph-major (B,7,27) / (B,7,21). */
 int dxvae_unpack_graphs(int64_t B, const float* Xn, const float* Pn, float* Xg, float* Pg, void* stream);
 

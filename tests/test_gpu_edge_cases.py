@@ -88,3 +88,20 @@ def test_empty_input_raises():
     with pytest.raises((ValueError, RuntimeError)):
         m.forward([])
     assert len(m.decode(torch.zeros(0, 128))) == 0          # nothing to decode: an empty batch comes back
+
+
+def test_a_patch_alone_equals_the_patch_in_a_batch():
+    """Default arithmetic: encode and greedy decode of ONE graph give the same bits as the same graph inside a batch of
+    300 (the kernel family of a product is chosen from the weight shape, never from the row count)."""
+    m, o = _model("3xtf32")
+    X, P, E, A, G = _batch(300, 5)
+    with torch.no_grad():
+        q = m.encode(G)
+        for k in (0, 1, 2, 151, 299):
+            q1 = m.encode([G[k]])
+            assert torch.equal(q1.loc[0], q.loc[k]) and torch.equal(q1.scale[0], q.scale[k]), k
+    z = torch.randn(300, 128, generator=torch.Generator().manual_seed(3))
+    gb = m.decode(z)
+    for k in (0, 7, 299):
+        g1 = m.decode(z[k:k + 1])
+        assert torch.equal(g1.params[0], gb.params[k]) and torch.equal(g1.adj[0], gb.adj[k]) and torch.equal(g1.X[0], gb.X[k]), k

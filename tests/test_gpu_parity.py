@@ -118,6 +118,38 @@ def test_host_batcher_matches_set_logic(lib):
     assert np.array_equal(d.level_rows.cpu().numpy(), ob["level_rows"])
 
 
+def test_shuffled_views_of_a_pinned_batch_are_gathered_by_the_device(lib):
+    """A training loop hands forward() a shuffled Python list of graph objects that are row views of one pinned host batch
+    (what DXDataset / DXGraphBatch iteration give out).  The batcher then ships an index list and the device gathers the
+    rows out of the pinned memory (dxvae_pack_graphs_indexed): same batch, bit for bit, as stacking the graphs on the host;
+    a modified or foreign graph in the list falls back to stacking."""
+    import random
+    from dxvae_b200.dxdata import DXGraph, DXGraphBatch, IndexedBatch
+    idx = list(range(0, 1024, 2))
+    X, P, E, A = util.dataset_graphs(idx)
+    m, _ = make_model(0, 1.0, "3xtf32")
+    m.host_batcher_max = 0                                    # (small batches would otherwise take the host batcher)
+    host = DXGraphBatch.from_graphs(_graphs(X, P, E)).pin_memory()
+    views = list(host)
+    random.Random(4).shuffle(views)
+    gb = DXGraphBatch.from_graphs(views, staging=True)
+    assert isinstance(gb, IndexedBatch) and len(gb) == len(idx)
+    order = [int(i) for i in gb.index]
+    plain = DXGraphBatch(host.X[order], host.params[order], host.adj[order])
+    d1, d2 = m._prepare(views), m._prepare(plain)
+    assert torch.equal(d1.Xn, d2.Xn) and torch.equal(d1.cls, d2.cls) and torch.equal(d1.adj, d2.adj)
+    assert torch.equal(d1.level_rows, d2.level_rows) and np.array_equal(d1.level_ptr, d2.level_ptr)
+    eps = torch.randn(len(idx), 128, generator=torch.Generator().manual_seed(1))
+    with torch.no_grad():
+        a = m.forward(views, eps=eps); b = m.forward(plain, eps=eps)
+    assert all(torch.equal(x, y) for x, y in zip(a, b))
+    views[5].ndata["X"] = views[5].ndata["X"].clone()         # touching a view detaches it: the list is stacked instead
+    gb2 = DXGraphBatch.from_graphs(views, staging=True)
+    assert not isinstance(gb2, IndexedBatch) and torch.equal(gb2.X, plain.X)
+    views[6] = DXGraph(X[0], P[0], *E[0])                      # ... and so does a foreign graph
+    assert not isinstance(DXGraphBatch.from_graphs(views, staging=True), IndexedBatch)
+
+
 def test_make_graph_matches_dataset_bin_bit_exact(lib):
     """dxdata.py:_make_graph on the device == DX_data/DXDataset.bin (golden: SHA-256 of the
     bin's X / params tensors + its edge lists, written by oracle/make_golden.py)."""
