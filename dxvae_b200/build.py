@@ -13,7 +13,7 @@ OUT = os.path.join(HERE, "libdxvae_b200.so")
 OBJ = os.path.join(os.path.dirname(HERE), "build", "obj")
 FILES = ["dx_gemm.cu", "dx_tc_gemm.cu", "dx_encoder.cu", "dx_decoder.cu", "dx_data.cu", "dx_api.cu", "dx_small.cu"]
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
-NVCC_FLAGS = ARCH + ["-lineinfo", "-O3", "-std=c++17", "--extended-lambda", "-Xcompiler", "-fPIC"]
+NVCC_FLAGS = ARCH + ["-lineinfo", "-O3", "-std=c++17", "--extended-lambda", "-Xcompiler", "-fPIC"] + os.environ.get("DX_NVCC_EXTRA", "").split()   # (experiments: extra -D switches)
 
 
 def _nvcc():

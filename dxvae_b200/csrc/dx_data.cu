@@ -108,6 +108,7 @@ constexpr int NBIN = 72;     // (level 0..5) x (back-edge target first, others s
 __global__ void __launch_bounds__(SCH_T) k_levels_count(int64_t B, const uint64_t* __restrict__ adj,
                                                         uint8_t* __restrict__ level, int32_t* __restrict__ counts,
                                                         int nblk) {
+  pdl_wait();
   __shared__ int cnt[NBIN];
   if (threadIdx.x < NBIN) cnt[threadIdx.x] = 0;
   __syncthreads();
@@ -123,6 +124,7 @@ __global__ void __launch_bounds__(SCH_T) k_levels_count(int64_t B, const uint64_
 }
 // exclusive scan of counts in (bin, block) order -> offsets; level_ptr[L] = start of bin (L,1)
 __global__ void k_scan_bins(int32_t* __restrict__ counts, int nblk, int32_t* __restrict__ level_ptr) {
+  pdl_wait();
   __shared__ int tot[NBIN];
   const int bin = threadIdx.x;
   if (bin < NBIN) {
@@ -149,6 +151,7 @@ __global__ void __launch_bounds__(SCH_T) k_scatter_rows(int64_t B, const uint8_t
                                                         const uint64_t* __restrict__ adj,
                                                         const int32_t* __restrict__ offsets, int nblk,
                                                         int32_t* __restrict__ level_rows) {
+  pdl_wait();
   __shared__ int wsum[32];
   const int64_t b = (int64_t)blockIdx.x * SCH_T + threadIdx.x;
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -179,9 +182,9 @@ int batch_schedule(dx_stream_t st, int64_t B, const uint64_t* adj, uint8_t* leve
   Arena ar(ws, ws_bytes);
   int32_t* counts = ar.take<int32_t>((size_t)NBIN * nblk);
   DX_CHECK(!ar.overflow, "batch_schedule: workspace too small (%zu < %zu)", ws_bytes, ar.off);
-  k_levels_count<<<nblk, SCH_T, 0, st>>>(B, adj, level, counts, nblk);
-  k_scan_bins<<<1, 96, 0, st>>>(counts, nblk, level_ptr);
-  k_scatter_rows<<<nblk, SCH_T, 0, st>>>(B, level, adj, counts, nblk, level_rows);
+  launch_k(k_levels_count, dim3(nblk), dim3(SCH_T), 0, st, 1, B, adj, level, counts, nblk);
+  launch_k(k_scan_bins, dim3(1), dim3(96), 0, st, 1, counts, nblk, level_ptr);
+  launch_k(k_scatter_rows, dim3(nblk), dim3(SCH_T), 0, st, 1, B, level, adj, counts, nblk, level_rows);
   g_launches += 3;
   cudaMemcpyAsync(level_ptr_host, level_ptr, 16 * sizeof(int32_t), cudaMemcpyDeviceToHost, st);
   cudaStreamSynchronize(st);
@@ -231,6 +234,7 @@ namespace {
 constexpr int NSTEPB = NLIST;
 __global__ void __launch_bounds__(SCH_T) k_steps_count(int64_t B, const uint64_t* __restrict__ adj,
                                                        int32_t* __restrict__ counts, int nblk) {
+  pdl_wait();
   __shared__ int cnt[NSTEPB];
   if (threadIdx.x < NSTEPB) cnt[threadIdx.x] = 0;
   __syncthreads();
@@ -243,6 +247,7 @@ __global__ void __launch_bounds__(SCH_T) k_steps_count(int64_t B, const uint64_t
   if (threadIdx.x < NSTEPB) counts[threadIdx.x * nblk + blockIdx.x] = cnt[threadIdx.x];
 }
 __global__ void k_steps_scan(int32_t* __restrict__ counts, int nblk, int32_t* __restrict__ step_ptr) {
+  pdl_wait();
   __shared__ int tot[NSTEPB];
   const int bin = threadIdx.x;
   if (bin < NSTEPB) {
@@ -263,6 +268,7 @@ __global__ void k_steps_scan(int32_t* __restrict__ counts, int nblk, int32_t* __
 __global__ void __launch_bounds__(SCH_T) k_steps_scatter(int64_t B, const uint64_t* __restrict__ adj,
                                                          const int32_t* __restrict__ offsets, int nblk,
                                                          int32_t* __restrict__ step_rows) {
+  pdl_wait();
   __shared__ int wsum[32];
   const int64_t b = (int64_t)blockIdx.x * SCH_T + threadIdx.x;
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -288,9 +294,9 @@ int batch_steps(dx_stream_t st, int64_t B, const uint64_t* adj, int32_t* step_pt
   Arena ar(ws, ws_bytes);
   int32_t* counts = ar.take<int32_t>((size_t)NSTEPB * nblk);
   DX_CHECK(!ar.overflow, "batch_steps: workspace too small (%zu < %zu)", ws_bytes, ar.off);
-  k_steps_count<<<nblk, SCH_T, 0, st>>>(B, adj, counts, nblk);
-  k_steps_scan<<<1, 64, 0, st>>>(counts, nblk, step_ptr);
-  k_steps_scatter<<<nblk, SCH_T, 0, st>>>(B, adj, counts, nblk, step_rows);
+  launch_k(k_steps_count, dim3(nblk), dim3(SCH_T), 0, st, 1, B, adj, counts, nblk);
+  launch_k(k_steps_scan, dim3(1), dim3(64), 0, st, 1, counts, nblk, step_ptr);
+  launch_k(k_steps_scatter, dim3(nblk), dim3(SCH_T), 0, st, 1, B, adj, counts, nblk, step_rows);
   g_launches += 3;
   cudaMemcpyAsync(step_ptr_host, step_ptr, (NLIST + 1) * sizeof(int32_t), cudaMemcpyDeviceToHost, st);
   cudaStreamSynchronize(st);

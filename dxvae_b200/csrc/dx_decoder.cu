@@ -176,6 +176,7 @@ void latent_bwd(dx_stream_t st, int B, const float* mu, const float* sd, const f
 // loss5 = (sum, x0, xi, e, kld_w): deterministic two-level sum over the B rows of each slot.
 #ifndef DX_EMU
 __global__ void __launch_bounds__(1024) k_loss_reduce(int B, const float* __restrict__ rowloss, float* __restrict__ out) {
+  pdl_wait();
   __shared__ double red[32];
   __shared__ double tot[4];
   for (int k = 0; k < 4; ++k) {
@@ -197,7 +198,7 @@ __global__ void __launch_bounds__(1024) k_loss_reduce(int B, const float* __rest
   }
 }
 void loss_reduce(dx_stream_t st, int B, const float* rowloss, float* out) {
-  k_loss_reduce<<<1, 1024, 0, st>>>(B, rowloss, out);
+  launch_k(k_loss_reduce, dim3(1), dim3(1024), 0, st, 1, B, rowloss, out);
   ++g_launches;
 }
 #else
@@ -367,6 +368,7 @@ constexpr int EH_R = 4;   // rows per block iteration
 // finishes the EH_R rows redundantly in its first 2*EH_R lanes (lane = 2*row + output), so no thread
 // waits on a serial tail; warp 0 alone writes the row outputs.
 static __global__ void __launch_bounds__(256, 2) k_edge_head_fwd(const EdgeHeadP a) {
+  pdl_wait();
   __shared__ float red[2][8][2 * EH_R];
   const int t = threadIdx.x, lane = t & 31, wid = t >> 5;
   const int c0 = t * 8;
@@ -482,7 +484,7 @@ static __global__ void __launch_bounds__(256, 2) k_edge_head_fwd(const EdgeHeadP
 static void edge_head_fwd(dx_stream_t st, const EdgeHeadP& a) {
   int blocks = (a.B + EH_R - 1) / EH_R;
   if (blocks > 148 * 2) blocks = 148 * 2;
-  k_edge_head_fwd<<<blocks, 256, 0, st>>>(a);
+  launch_k(k_edge_head_fwd, dim3(blocks), dim3(256), 0, st, 1, a);
   ++g_launches;
 }
 #else
@@ -556,6 +558,7 @@ DX_HD DX_INLINE void head_sum_item(const HeadSumP& a, int m, int tc, const float
 #ifndef DX_EMU
 // thread = one group of 8 columns (its two W2 slices stay in registers), blocks stride over the rows
 static __global__ void __launch_bounds__(256, 4) k_head_sum(const HeadSumP a) {
+  pdl_wait();
   const int tc = threadIdx.x, c0 = tc * 8;
   float w0[8], w1[8];
   {
@@ -567,7 +570,7 @@ static __global__ void __launch_bounds__(256, 4) k_head_sum(const HeadSumP a) {
 }
 static void head_sum(dx_stream_t st, const HeadSumP& a) {
   if (a.M <= 0) return;
-  k_head_sum<<<a.M < 148 * 8 ? a.M : 148 * 8, 256, 0, st>>>(a);
+  launch_k(k_head_sum, dim3(a.M < 148 * 8 ? a.M : 148 * 8), dim3(256), 0, st, 1, a);
   ++g_launches;
 }
 #else
@@ -584,6 +587,7 @@ static void head_sum(dx_stream_t, const HeadSumP& a) {
 static __global__ void __launch_bounds__(256) k_rowdot(int M, int K, const float* __restrict__ A, int64_t lda,
                                                        const float* __restrict__ w, const float* __restrict__ b,
                                                        float* __restrict__ out, int64_t ldo) {
+  pdl_wait();
   const int lane = threadIdx.x & 31;
   const int warp = (int)((blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5), nw = (int)((gridDim.x * (int64_t)blockDim.x) >> 5);
   for (int m = warp; m < M; m += nw) {
@@ -602,7 +606,7 @@ static __global__ void __launch_bounds__(256) k_rowdot(int M, int K, const float
 static void rowdot(dx_stream_t st, int M, int K, const float* A, int64_t lda, const float* w, const float* b, float* out, int64_t ldo) {
   int blocks = (M + 7) / 8;
   if (blocks > 148 * 8) blocks = 148 * 8;
-  k_rowdot<<<blocks, 256, 0, st>>>(M, K, A, lda, w, b, out, ldo);
+  launch_k(k_rowdot, dim3(blocks), dim3(256), 0, st, 1, M, K, A, lda, w, b, out, ldo);
   ++g_launches;
 }
 #else

@@ -42,6 +42,7 @@ __device__ __forceinline__ float4 ld4(const float* p, int nvalid, bool vec) {
 template <int BM, int BN, int TM, int TN, bool AKC, bool BKC>
 __global__ void __launch_bounds__(256, (BM >= 128 ? 2 : 3)) k_gemm(const GemmP p, const int k_chunk, const bool vecA, const bool vecB,
                                               const bool vecC) {
+  pdl_wait();
   static_assert((BM / TM) * (BN / TN) == 256, "256 threads");
   static_assert(TM % 4 == 0 && TN % 4 == 0, "4x4 sub-blocks");
   constexpr int LA = BM * BK / 4 / 256;  // float4 loads per thread for the A tile
@@ -261,15 +262,16 @@ void launch_tile(dx_stream_t s, const GemmP& p) {
   const bool vecB = aligned16(p.B) && (p.ldb % 4 == 0);
   const bool vecC = aligned16(p.C) && (p.ldc % 4 == 0);
   dim3 grid(gn, gm, splits);
-  if (p.a_kc && p.b_kc) k_gemm<BM, BN, TM, TN, true, true><<<grid, 256, 0, s>>>(p, k_chunk, vecA, vecB, vecC);
-  else if (p.a_kc && !p.b_kc) k_gemm<BM, BN, TM, TN, true, false><<<grid, 256, 0, s>>>(p, k_chunk, vecA, vecB, vecC);
-  else if (!p.a_kc && !p.b_kc) k_gemm<BM, BN, TM, TN, false, false><<<grid, 256, 0, s>>>(p, k_chunk, vecA, vecB, vecC);
-  else k_gemm<BM, BN, TM, TN, false, true><<<grid, 256, 0, s>>>(p, k_chunk, vecA, vecB, vecC);
+  if (p.a_kc && p.b_kc) launch_k(k_gemm<BM, BN, TM, TN, true, true>, grid, dim3(256), 0, s, 1, p, k_chunk, vecA, vecB, vecC);
+  else if (p.a_kc && !p.b_kc) launch_k(k_gemm<BM, BN, TM, TN, true, false>, grid, dim3(256), 0, s, 1, p, k_chunk, vecA, vecB, vecC);
+  else if (!p.a_kc && !p.b_kc) launch_k(k_gemm<BM, BN, TM, TN, false, false>, grid, dim3(256), 0, s, 1, p, k_chunk, vecA, vecB, vecC);
+  else launch_k(k_gemm<BM, BN, TM, TN, false, true>, grid, dim3(256), 0, s, 1, p, k_chunk, vecA, vecB, vecC);
   ++g_launches;
 }
 
 __global__ void __launch_bounds__(256) k_colsum(int M, int N, const float* __restrict__ dy, int64_t ld,
                                                 float* __restrict__ db, const int* __restrict__ idx, int rows_per) {
+  pdl_wait();
   // block (x: 64 columns as 64 threads) x (4 row lanes); grid.y splits the rows
   __shared__ float red[4][64];
   const int c = blockIdx.x * 64 + (threadIdx.x & 63);
@@ -296,6 +298,7 @@ template <int MO>
 __global__ void __launch_bounds__(256) k_wcolsum(int M, int N, const float* __restrict__ dy, int64_t lddy,
                                                  const float* __restrict__ x, int64_t ldx, float* __restrict__ dW, int64_t lddw,
                                                  int rows_per) {
+  pdl_wait();
   __shared__ float4 red[3][MO][64];
   const int tc = threadIdx.x & 63, lane_r = threadIdx.x >> 6;
   const int c = (blockIdx.x * 64 + tc) * 4;
@@ -343,8 +346,8 @@ bool wcolsum(dx_stream_t s, const GemmP& p) {
   if (gy < 1) gy = 1;
   const int rows_per = (rows + gy - 1) / gy;
   gy = (rows + rows_per - 1) / rows_per;
-  if (p.M == 1) k_wcolsum<1><<<dim3(gx, gy), 256, 0, s>>>(rows, p.N, p.A, p.lda, p.B, p.ldb, p.C, p.ldc, rows_per);
-  else k_wcolsum<2><<<dim3(gx, gy), 256, 0, s>>>(rows, p.N, p.A, p.lda, p.B, p.ldb, p.C, p.ldc, rows_per);
+  if (p.M == 1) launch_k(k_wcolsum<1>, dim3(gx, gy), dim3(256), 0, s, 1, rows, p.N, p.A, p.lda, p.B, p.ldb, p.C, p.ldc, rows_per);
+  else launch_k(k_wcolsum<2>, dim3(gx, gy), dim3(256), 0, s, 1, rows, p.N, p.A, p.lda, p.B, p.ldb, p.C, p.ldc, rows_per);
   ++g_launches;
   return true;
 }
@@ -417,7 +420,7 @@ void colsum_accum(dx_stream_t s, int M, int N, const float* dy, int64_t lddy, fl
   if (gy < 1) gy = 1;
   const int rows_per = (M + gy - 1) / gy;
   gy = (M + rows_per - 1) / rows_per;
-  k_colsum<<<dim3(gx, gy), 256, 0, s>>>(M, N, dy, lddy, db, dy_idx, rows_per);
+  launch_k(k_colsum, dim3(gx, gy), dim3(256), 0, s, 1, M, N, dy, lddy, db, dy_idx, rows_per);
   ++g_launches;
 }
 

@@ -131,6 +131,7 @@ DX_HD DX_INLINE void cell_bwd_elem(const CellBwd& a, int m, int n, float4& ar, f
 // dgx / dgh), the 4 row groups are folded through shared memory, and 128 threads issue the atomics:
 // no second pass over 12 KB/row, and only 2 blocks/SM worth of atomics per address.
 static __global__ void __launch_bounds__(512) k_cell_bwd(const CellBwd a, float* __restrict__ dbih, float* __restrict__ dbhh) {
+  pdl_wait();
   __shared__ float red[3][16][128];
   const int q = threadIdx.x & 127, rg = threadIdx.x >> 7;
   const int n = q * 4;
@@ -171,7 +172,7 @@ inline void cell_bwd(dx_stream_t st, const CellBwd& a, float* dbih = nullptr, fl
 #ifndef DX_EMU
   int blocks = (a.rm.M + 3) / 4;
   if (blocks > 148 * 2) blocks = 148 * 2;
-  k_cell_bwd<<<blocks, 512, 0, st>>>(a, dbih, dbhh);
+  launch_k(k_cell_bwd, dim3(blocks), dim3(512), 0, st, 1, a, dbih, dbhh);
   ++g_launches;
 #else
   for (int m = 0; m < a.rm.M; ++m)
@@ -304,6 +305,7 @@ DX_HD DX_INLINE float4 msg_bwd_elem(const MsgBwd& a, int m, int n) {
 #ifndef DX_EMU
 // Block = 4 row groups x 128 threads (the 512 hidden units, 4 per thread); blocks stride over the rows (as k_cell_bwd).
 static __global__ void __launch_bounds__(512, 2) k_msg_bwd(const MsgBwd a) {
+  pdl_wait();
   __shared__ float red[3][4][128];
   const int q = threadIdx.x & 127, rg = threadIdx.x >> 7;
   float4 s = f4zero();
@@ -328,7 +330,7 @@ inline void msg_bwd(dx_stream_t st, const MsgBwd& a) {
 #ifndef DX_EMU
   int blocks = (a.rm.M + 3) / 4;
   if (blocks > 148 * 2) blocks = 148 * 2;
-  k_msg_bwd<<<blocks, 512, 0, st>>>(a);
+  launch_k(k_msg_bwd, dim3(blocks), dim3(512), 0, st, 1, a);
   ++g_launches;
 #else
   for (int m = 0; m < a.rm.M; ++m)

@@ -379,6 +379,7 @@ __global__ void __launch_bounds__(TcCfg<BN>::THREADS, 1) k_tc_gemm(const __grid_
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   uint32_t tmem_base;
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+  pdl_wait();                                                      // set-up above overlapped the previous kernel; its results are visible from here on
   if (trace && threadIdx.x == 0) p.dbg[201] = clock64();
 
   auto tile_coords = [&](int t, int& m0, int& n0, int& kbeg, int& nkb) {
@@ -575,6 +576,7 @@ k_tc_gemm2(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   uint32_t tmem_base;
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+  pdl_wait();                                                      // set-up above overlapped the previous kernel; its results are visible from here on
   if (trace && threadIdx.x == 0) p.dbg[201] = clock64();
 
   auto tile_coords = [&](int t, int& m0, int& n0, int& kbeg, int& nkb) {
@@ -754,6 +756,7 @@ k_tc_gemm_x3(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   uint32_t tmem_base;
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+  pdl_wait();                                                      // set-up above overlapped the previous kernel; its results are visible from here on
 
   auto tile_coords = [&](int t, int& m0, int& n0, int& kbeg, int& nkb) {
     const int mt = p.n_fast ? (t / gn) % gm : t % gm, nt = p.n_fast ? t % gn : (t / gm) % gn, z = t / (gm * gn);
@@ -962,6 +965,7 @@ k_tc_gemm_x3w(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   uint32_t tmem_base;
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+  pdl_wait();                                                      // set-up above overlapped the previous kernel; its results are visible from here on
 
   auto tile_coords = [&](int t, int& m0, int& n0, int& kbeg, int& nkb) {
     const int mt = p.n_fast ? (t / gn) % gm : t % gm, nt = p.n_fast ? t % gn : (t / gm) % gn, z = t / (gm * gn);
@@ -1139,14 +1143,36 @@ bool make_map(CUtensorMap* m, const float* ptr, int64_t rows, int64_t cols, int6
               bool mn_major, bool plain_f32 = false) {
   EncodeTiledFn enc = get_encode();
   if (!enc) return false;
+  // A tensor map is a pure function of (address, extents, pitch, box, flags): a training step re-issues the same few
+  // hundred products every iteration, so the encoded maps are kept in a small direct-mapped per-thread table (4-6 driver
+  // calls per product launch otherwise: host time that matters when a step is ~850 short dependent launches).
+  struct Slot { const float* ptr; int64_t rows, cols, ld; uint32_t box, flags; bool used; CUtensorMap map; };
+  constexpr int NSLOT = 2048;
+  static thread_local Slot* table = nullptr;
+  if (!table) table = static_cast<Slot*>(calloc(NSLOT, sizeof(Slot)));
+  const uint32_t boxk = ((uint32_t)box_cols << 16) | (uint32_t)box_rows;
+  const uint32_t flags = (mn_major ? 1u : 0u) | (plain_f32 ? 2u : 0u);
+  Slot* sl = nullptr;
+  if (table) {
+    uint64_t h = reinterpret_cast<uintptr_t>(ptr) * 0x9E3779B97F4A7C15ull;
+    h ^= ((uint64_t)rows * 0xC2B2AE3D27D4EB4Full) ^ ((uint64_t)cols << 21) ^ ((uint64_t)ld << 42) ^ ((uint64_t)boxk << 7) ^ flags;
+    h ^= h >> 29;
+    sl = table + (h & (NSLOT - 1));
+    if (sl->used && sl->ptr == ptr && sl->rows == rows && sl->cols == cols && sl->ld == ld && sl->box == boxk && sl->flags == flags) {
+      *m = sl->map;
+      return true;
+    }
+  }
   cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
   cuuint64_t gstr[1] = {(cuuint64_t)ld * 4};
   cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1, 1};
-  return enc(m, plain_f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_TFLOAT32, 2, const_cast<float*>(ptr), gdim, gstr, box, estr,
+  const bool ok = enc(m, plain_f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_TFLOAT32, 2, const_cast<float*>(ptr), gdim, gstr, box, estr,
              CU_TENSOR_MAP_INTERLEAVE_NONE, mn_major ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
              l2_promo(),
              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+  if (ok && sl) { sl->ptr = ptr; sl->rows = rows; sl->cols = cols; sl->ld = ld; sl->box = boxk; sl->flags = flags; sl->map = *m; sl->used = true; }
+  return ok;
 }
 
 // 2-D bf16 tensor [rows][cols] with row pitch ld (elements); box = 64 columns (128 bytes) x box_rows, 128-byte swizzle
@@ -1246,7 +1272,7 @@ bool launch_tc(dx_stream_t s, const GemmP& g) {
     cudaFuncSetAttribute(k_tc_gemm<BN, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM);
     cudaFuncSetAttribute(k_tc_gemm<BN, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM);
   });
-  auto run = [&](auto kern) { kern<<<grid, Cfg::THREADS, Cfg::SMEM, s>>>(ta, tb, tc, tadd, p); };
+  auto run = [&](auto kern) { launch_k(kern, grid, dim3(Cfg::THREADS), Cfg::SMEM, s, 1, ta, tb, tc, tadd, p); };
   if (g.a_kc && g.b_kc) run(k_tc_gemm<BN, false, false>);
   else if (g.a_kc && !g.b_kc) run(k_tc_gemm<BN, false, true>);
   else if (!g.a_kc && !g.b_kc) run(k_tc_gemm<BN, true, true>);
@@ -1317,9 +1343,9 @@ bool launch_tc2(dx_stream_t s, const GemmP& g) {
     cudaFuncSetAttribute(k_tc_gemm2<true, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM);
   });
   dim3 grid(2 * ncl);
-  if (g.a_kc && g.b_kc) k_tc_gemm2<false, false, false><<<grid, Cfg::THREADS, Cfg::SMEM, s>>>(ta, tb, tc, tadd, p);
-  else if (g.a_kc && !g.b_kc) k_tc_gemm2<false, true, false><<<grid, Cfg::THREADS, Cfg::SMEM, s>>>(ta, tb, tc, tadd, p);
-  else k_tc_gemm2<true, true, false><<<grid, Cfg::THREADS, Cfg::SMEM, s>>>(ta, tb, tc, tadd, p);
+  if (g.a_kc && g.b_kc) launch_k(k_tc_gemm2<false, false, false>, grid, dim3(Cfg::THREADS), Cfg::SMEM, s, 1, ta, tb, tc, tadd, p);
+  else if (g.a_kc && !g.b_kc) launch_k(k_tc_gemm2<false, true, false>, grid, dim3(Cfg::THREADS), Cfg::SMEM, s, 1, ta, tb, tc, tadd, p);
+  else launch_k(k_tc_gemm2<true, true, false>, grid, dim3(Cfg::THREADS), Cfg::SMEM, s, 1, ta, tb, tc, tadd, p);
   ++g_launches;
   if (want_dbg) {
     long long h[256];
@@ -1394,16 +1420,7 @@ bool launch_x3(dx_stream_t s, const GemmP& g) {
   const int nt = total < ncta ? total : ncta;
   dim3 grid(CTA2 ? 2 * nt : nt);
   auto run = [&](auto kern) {
-    if (CTA2) {
-      cudaLaunchConfig_t cfg = {};
-      cfg.gridDim = grid; cfg.blockDim = dim3(Cfg::THREADS); cfg.dynamicSmemBytes = Cfg::SMEM; cfg.stream = s;
-      cudaLaunchAttribute at[1];
-      at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-      cfg.attrs = at; cfg.numAttrs = 1;
-      cudaLaunchKernelEx(&cfg, kern, ta, tb, tc, tadd, p);
-    } else {
-      kern<<<grid, Cfg::THREADS, Cfg::SMEM, s>>>(ta, tb, tc, tadd, p);
-    }
+    launch_k(kern, grid, dim3(Cfg::THREADS), Cfg::SMEM, s, CTA2 ? 2 : 1, ta, tb, tc, tadd, p);
   };
   if (g.a_kc && g.b_kc) run(k_tc_gemm_x3<false, false, CTA2, BNT>);
   else if (g.a_kc && !g.b_kc) run(k_tc_gemm_x3<false, true, CTA2, BNT>);
@@ -1498,14 +1515,10 @@ bool launch_x3w(dx_stream_t s, const GemmP& g) {
   });
   const int nt = total < ncl ? total : ncl;
   if (accum != g.accum && g.accum == ACC_STORE) cudaMemset2DAsync(g.C, (size_t)g.ldc * 4, 0, (size_t)g.N * 4, (size_t)g.M, s);
-  cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(2 * nt); cfg.blockDim = dim3(Cfg::THREADS); cfg.dynamicSmemBytes = Cfg::SMEM; cfg.stream = s;
-  cudaLaunchAttribute at[1];
-  at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-  cfg.attrs = at; cfg.numAttrs = 1;
-  if (g.a_kc && g.b_kc) cudaLaunchKernelEx(&cfg, k_tc_gemm_x3w<false, false>, ta, tb, tc, tadd, p);
-  else if (g.a_kc && !g.b_kc) cudaLaunchKernelEx(&cfg, k_tc_gemm_x3w<false, true>, ta, tb, tc, tadd, p);
-  else cudaLaunchKernelEx(&cfg, k_tc_gemm_x3w<true, true>, ta, tb, tc, tadd, p);
+  const dim3 grid(2 * nt), block(Cfg::THREADS);
+  if (g.a_kc && g.b_kc) launch_k(k_tc_gemm_x3w<false, false>, grid, block, Cfg::SMEM, s, 2, ta, tb, tc, tadd, p);
+  else if (g.a_kc && !g.b_kc) launch_k(k_tc_gemm_x3w<false, true>, grid, block, Cfg::SMEM, s, 2, ta, tb, tc, tadd, p);
+  else launch_k(k_tc_gemm_x3w<true, true>, grid, block, Cfg::SMEM, s, 2, ta, tb, tc, tadd, p);
   ++g_launches;
   return true;
 }
@@ -1527,7 +1540,7 @@ bool launch_tc2_bf16(dx_stream_t s, const GemmP& g, const void* A16, const void*
   const int total = gm2 * gn, ncl = total < num_sms / 2 ? total : num_sms / 2;
   static AttrOnce attr;
   attr([] { cudaFuncSetAttribute(k_tc_gemm2<false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Tc2Cfg::SMEM); });
-  k_tc_gemm2<false, false, true><<<dim3(2 * ncl), 320, Tc2Cfg::SMEM, s>>>(ta, tb, tc, ta, p);
+  launch_k(k_tc_gemm2<false, false, true>, dim3(2 * ncl), dim3(320), Tc2Cfg::SMEM, s, 1, ta, tb, tc, ta, p);
   ++g_launches;
   return true;
 }
@@ -1559,6 +1572,11 @@ bool tc_gemm(dx_stream_t s, const GemmP& g, int* tile_n, bool x3) {
   if (x3) {
     static const bool no_narrow = getenv("DX_X3_NO_NARROW") != nullptr;
     if (g.N <= 64 && !no_narrow) return launch_x3<false, 32>(s, g);   // thin outputs: 32-column tiles
+    // Few-row products (small training batches, M <= 256): a 128-column tiling runs N/128 CTAs whose k-blocks are a serial
+    // load -> convert -> MMA -> drain chain; 32-column tiles put 4x as many SMs on the weight stream and shorten every link
+    // of the chain.  Same per-element instruction sequence as the other tile shapes, so forward results keep their bits.
+    static const int few_rows = [] { const char* e = getenv("DX_X3_FEW_ROWS"); return e ? atoi(e) : 256; }();   // (0 disables)
+    if (few_rows > 0 && g.accum != ACC_ATOMIC && g.M <= few_rows && !no_narrow) return launch_x3<false, 32>(s, g);
     // wide pair tiles whenever the output is wide enough: for dgrads / wgrads launch_x3w splits the reduction until the
     // machine is filled (choose_splits), forward products need >= 37 tiles of their own
     if (g.N >= 192 && launch_x3w(s, g)) return true;
