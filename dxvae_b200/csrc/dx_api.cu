@@ -46,6 +46,7 @@ int elbo_step(dx_stream_t st, const float* weights, const Batch& bt, const float
               float* mu_out, float* std_out, float* grads, void* ws, size_t ws_bytes, int precision, void* dec_done_event) {
   const int B = (int)bt.B;
   PrecisionScope prec(precision);
+  FwdSplitScope fsplit(true);   // training: few-row forward products may split their reduction (dx_gemm.h)
   Arena ar(ws, ws_bytes);
   TrainWs t = carve_train(ar, bt.B, bt.n_levels, bt.level_ptr, bt.step_ptr);
   DX_CHECK(!ar.overflow, "elbo_step: workspace too small (%zu < %zu bytes)", ws_bytes, ar.off);
@@ -80,6 +81,7 @@ int loss_step(dx_stream_t st, const float* weights, const Batch& bt, const float
               LossW lw, float* loss5, float* grads, float* dmu, float* dsd, void* ws, size_t ws_bytes, int precision) {
   const int B = (int)bt.B;
   PrecisionScope prec(precision);
+  FwdSplitScope fsplit(true);   // training: few-row forward products may split their reduction (dx_gemm.h)
   Arena ar(ws, ws_bytes);
   DecWs d = carve_dec(ar, bt.B, true, bt.step_ptr);
   DX_CHECK(!ar.overflow, "loss_step: workspace too small (%zu < %zu bytes)", ws_bytes, ar.off);
@@ -103,6 +105,7 @@ int loss_step(dx_stream_t st, const float* weights, const Batch& bt, const float
 int encode_bwd(dx_stream_t st, const float* weights, const Batch& bt, const float* sd, const float* dmu,
                const float* dsd, float* grads, void* ws, size_t ws_bytes, int precision) {
   PrecisionScope prec(precision);
+  FwdSplitScope fsplit(true);   // training: few-row forward products may split their reduction (dx_gemm.h)
   Arena ar(ws, ws_bytes);
   EncWs e = carve_enc(ar, bt.B, true, bt.n_levels, bt.level_ptr);
   DX_CHECK(!ar.overflow, "encode_bwd: workspace too small (%zu < %zu bytes)", ws_bytes, ar.off);
@@ -272,7 +275,7 @@ int dxvae_adamw_step(int64_t n, float* weights, const float* grads, float* exp_a
 }
 int dxvae_test_gemm(int variant, int64_t M, int64_t N, int64_t K, const float* A, int64_t lda, const float* Bm,
                     int64_t ldb, float* C, int64_t ldc, const float* bias, int act, int accumulate, void* stream) {
-  // variant 0: y = act(x W^T + b) ; 1: dx (+)= dy W ; 2: dW += dy^T x ; +16: tcgen05 TF32 path ; +32: 3xTF32
+  // variant 0: y = act(x W^T + b) ; 1: dx (+)= dy W ; 2: dW += dy^T x ; +16: tcgen05 TF32 path ; +32: 3xTF32 ; +128: training scope
   // variant 64: y = act(x W^T + b) with A and Bm pointing at BF16 data (pitches in elements), tcgen05 kind::f16
   if (variant == 64) {
     GemmP g; g.M = (int)M; g.N = (int)N; g.K = (int)K; g.lda = lda; g.ldb = ldb; g.C = C; g.ldc = ldc; g.bias = bias; g.act = act;
@@ -280,6 +283,7 @@ int dxvae_test_gemm(int variant, int64_t M, int64_t N, int64_t K, const float* A
     return check_launch("test_gemm_bf16");
   }
   PrecisionScope prec((variant & 32) ? PREC_3XTF32 : ((variant & 16) ? PREC_TF32 : PREC_FP32));
+  FwdSplitScope fsplit((variant & 128) != 0);   // +128: as inside the training entry points (few-row forward products may split)
   variant &= 15;
   DX_CHECK(variant >= 0 && variant <= 2, "test_gemm: unknown variant %d", variant);
   if (variant == 0) linear_fwd(DX_ST(stream), (int)M, (int)N, (int)K, A, lda, Bm, ldb, bias, C, ldc, act);

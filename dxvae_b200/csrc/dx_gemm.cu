@@ -388,6 +388,9 @@ void prof_end(double* ms, double* flops, long long* n) {
 thread_local int g_precision = PREC_FP32;
 void set_precision(int prec) { g_precision = prec; }
 int get_precision() { return g_precision; }
+thread_local bool g_fwd_split = false;
+void set_fwd_split(bool on) { g_fwd_split = on; }
+bool get_fwd_split() { return g_fwd_split; }
 
 void gemm(dx_stream_t s, const GemmP& p) {
   if (p.M <= 0 || p.N <= 0 || p.K <= 0) return;
@@ -459,6 +462,9 @@ void prof_end(double* ms, double* flops, long long* n) {
 static thread_local int g_precision = PREC_FP32;
 void set_precision(int prec) { g_precision = prec; }
 int get_precision() { return g_precision; }
+static thread_local bool g_fwd_split = false;
+void set_fwd_split(bool on) { g_fwd_split = on; }
+bool get_fwd_split() { return g_fwd_split; }
 
 void colsum_accum(dx_stream_t, int M, int N, const float* dy, int64_t lddy, float* db, const int* dy_idx) {
   for (int j = 0; j < N; ++j) {

@@ -42,6 +42,16 @@ struct PrecisionScope {
   explicit PrecisionScope(int p) : prev(get_precision()) { set_precision(p); }
   ~PrecisionScope() { set_precision(prev); }
 };
+// Training entry points allow FORWARD products of a few rows (M <= 256) to split their reduction over a thread-block
+// cluster (dx_tc_gemm.cu, launch_x3k): deterministic, but the summation order differs from the unsplit kernels, and an
+// inference result must not depend on how many patches share the batch — so it is scoped, per thread, like the precision.
+void set_fwd_split(bool on);
+bool get_fwd_split();
+struct FwdSplitScope {
+  bool prev;
+  explicit FwdSplitScope(bool on) : prev(get_fwd_split()) { set_fwd_split(on); }
+  ~FwdSplitScope() { set_fwd_split(prev); }
+};
 bool tc_gemm(dx_stream_t s, const GemmP& p, int* tile_n, bool x3 = false);   // dx_tc_gemm.cu; false = not eligible
 // PREC_3XTF32: the same kernels with the operand hi/lo split done inside the kernel (shared memory), three MMAs per
 // k-step: FP32-accurate products for every operand form (forward, dgrad, wgrad), no operand copies in HBM.

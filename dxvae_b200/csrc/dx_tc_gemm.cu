@@ -477,6 +477,7 @@ struct Tc2Cfg {
 };
 
 __device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ uint32_t cluster_nctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r)); return r; }
 __device__ __forceinline__ void cluster_sync_all() {
   asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
   asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
@@ -703,7 +704,11 @@ template <bool CTA2, int BNT = 128> struct X3Cfg {
   static constexpr int SMEM = S * STAGE + 1024 + 8 * 4096 + 256;
 };
 
-template <bool A_MN, bool B_MN, bool CTA2, int BNT = 128>
+// KSP (few-row products, M <= 256: see launch_x3k): the reduction is split over the CTAs of a thread-block cluster
+// (rank = split index, one output tile per cluster); every CTA runs the unchanged main loop on its k range, parks its
+// FP32 partial tile in its own shared memory, and after a cluster barrier each CTA sums a 128/KS-row slice of the tile
+// over all ranks through distributed shared memory IN RANK ORDER (deterministic), applies the epilogue and stores it.
+template <bool A_MN, bool B_MN, bool CTA2, int BNT = 128, bool KSP = false>
 __global__ void __launch_bounds__(X3Cfg<CTA2, BNT>::THREADS, 1)
 k_tc_gemm_x3(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
              const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmAdd, const TcParams p) {
@@ -726,12 +731,15 @@ k_tc_gemm_x3(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   const uint32_t add_bar0 = bars + 8u * (3 * S + 5);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  static_assert(!KSP || (!CTA2 && BNT == 128), "cluster split-K: single-CTA 128 x 128 tiles");
   const uint32_t rank = CTA2 ? cluster_ctarank() : 0u;
   const bool leader = rank == 0;
   const int gm = (p.M + TM - 1) / TM, gn = (p.N + BN - 1) / BN;
-  const int splits = (p.K + p.k_chunk - 1) / p.k_chunk;
+  const uint32_t ks_rank = KSP ? cluster_ctarank() : 0u, ks_n = KSP ? cluster_nctarank() : 1u;   // split index / splits
+  const int splits = KSP ? 1 : (p.K + p.k_chunk - 1) / p.k_chunk;
   const int total = gm * gn * splits;
-  const int cid = CTA2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x, ncl = CTA2 ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+  const int cid = KSP ? (int)(blockIdx.x / ks_n) : (CTA2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x);
+  const int ncl = KSP ? (int)(gridDim.x / ks_n) : (CTA2 ? (int)(gridDim.x >> 1) : (int)gridDim.x);   // (KSP: ncl == total, one tile per cluster)
   const int dbg = p.x3_inplace;                                    // DX_X3_DBG experiment switches (results are wrong when set)
   const bool trace = p.dbg && blockIdx.x == 0;                     // DX_TC_DEBUG: clock64() stamps of the first 40 k-blocks of CTA 0
   if (trace && threadIdx.x == 0) p.dbg[250] = clock64();
@@ -759,10 +767,11 @@ k_tc_gemm_x3(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   pdl_wait();                                                      // set-up above overlapped the previous kernel; its results are visible from here on
 
   auto tile_coords = [&](int t, int& m0, int& n0, int& kbeg, int& nkb) {
-    const int mt = p.n_fast ? (t / gn) % gm : t % gm, nt = p.n_fast ? t % gn : (t / gm) % gn, z = t / (gm * gn);
+    const int mt = p.n_fast ? (t / gn) % gm : t % gm, nt = p.n_fast ? t % gn : (t / gm) % gn;
+    const int z = KSP ? (int)ks_rank : t / (gm * gn);
     m0 = mt * TM + (int)rank * TBM; n0 = nt * BN; kbeg = z * p.k_chunk;   // this CTA's 128 rows
     const int kend = min(p.K, kbeg + p.k_chunk);
-    nkb = (kend - kbeg + TBK - 1) / TBK;
+    nkb = kend > kbeg ? (kend - kbeg + TBK - 1) / TBK : 0;               // (KSP: the last ranks of a short reduction may have none)
   };
   auto wait_leader = [&](uint32_t bar, uint32_t parity) { if (CTA2) mbar_wait_cluster(bar, parity); else mbar_wait(bar, parity); };
   auto arrive_leader = [&](uint32_t bar) {
@@ -871,9 +880,25 @@ k_tc_gemm_x3(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         if (lane == 0) arrive_leader(cempty_bar(cb));
         if (trace && threadIdx.x == 64 && it < 20) p.dbg[180 + it] = clock64();
       }
+      if (KSP) {
+        // park the partial tile in this CTA's shared memory (stage 0 is free: every MMA that read it has completed):
+        // row r at r * 512 B, its 16-byte chunk c at position c ^ (r & 31) — conflict-free for these row-per-lane
+        // writes and for the row-per-warp reads of the reduction below
+        const int r = q * 32 + lane;
+        const uint32_t prow = base + (uint32_t)r * 512u;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const uint32_t c0 = (uint32_t)(half * 16 + j), c1 = c0 + 8u;
+          asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(prow + ((c0 ^ (uint32_t)(r & 31)) << 4)), "f"(a0[4 * j]),
+                       "f"(a0[4 * j + 1]), "f"(a0[4 * j + 2]), "f"(a0[4 * j + 3]) : "memory");
+          asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(prow + ((c1 ^ (uint32_t)(r & 31)) << 4)), "f"(a1[4 * j]),
+                       "f"(a1[4 * j + 1]), "f"(a1[4 * j + 2]), "f"(a1[4 * j + 3]) : "memory");
+        }
+      } else {
       const int gj = n0 + half * WC;
       if (drains && gj < p.N) epi_cols32(p, &tmC, &tmAdd, a0, gj, m0 + q * 32, w);
       if (BN == 128 && gj + 32 < p.N) epi_cols32(p, &tmC, &tmAdd, a1, gj + 32, m0 + q * 32, w);
+      }
     }
     if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
     __syncwarp();
@@ -895,7 +920,51 @@ k_tc_gemm_x3(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     }
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-  if (CTA2) cluster_sync_all(); else __syncthreads();
+  if (KSP) {
+    __syncwarp();
+    cluster_sync_all();                                            // every rank's partial tile is in its shared memory
+    int m0, n0, kbeg, nkb; tile_coords(cid, m0, n0, kbeg, nkb);
+    const int rp = TBM / (int)ks_n;                                // rows of the tile this CTA reduces and stores
+    const bool vec_c = ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0) && (p.ldc % 4 == 0);
+    const bool vec_add = p.add && ((reinterpret_cast<uintptr_t>(p.add) & 15) == 0) && (p.ldadd % 4 == 0);
+    for (int i = threadIdx.x; i < rp * 32; i += Cfg::THREADS) {
+      const int r = (int)ks_rank * rp + (i >> 5), c = i & 31;
+      const int gi = m0 + r, gj = n0 + 4 * c;
+      if (gi >= p.M || gj >= p.N) continue;
+      const uint32_t local = base + (uint32_t)r * 512u + (((uint32_t)c ^ (uint32_t)(r & 31)) << 4);
+      float v[4] = {0.f, 0.f, 0.f, 0.f};
+      for (uint32_t z = 0; z < ks_n; ++z) {                        // rank order: the sum does not depend on timing
+        uint32_t ra; float x0, x1, x2, x3;
+        asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(local), "r"(z));
+        asm volatile("ld.shared::cluster.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(x0), "=f"(x1), "=f"(x2), "=f"(x3) : "r"(ra) : "memory");
+        v[0] += x0; v[1] += x1; v[2] += x2; v[3] += x3;
+      }
+      const int nv = min(4, p.N - gj);
+      if (p.add) {
+        const float* ar = p.add + (int64_t)gi * p.ldadd + gj;
+        float a[4] = {0.f, 0.f, 0.f, 0.f};
+        if (vec_add && nv == 4) { const float4 a4 = __ldg(reinterpret_cast<const float4*>(ar)); a[0] = a4.x; a[1] = a4.y; a[2] = a4.z; a[3] = a4.w; }
+        else for (int e = 0; e < nv; ++e) a[e] = __ldg(ar + e);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) v[e] = p.act == ACT_GATE ? (a[e] > 0.f ? v[e] : 0.f) : v[e] + a[e];
+      }
+      if (p.bias) for (int e = 0; e < nv; ++e) v[e] += __ldg(p.bias + gj + e);
+      if (p.act != ACT_NONE && p.act != ACT_GATE) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) v[e] = tc_act(v[e], p.act);
+      }
+      float* cr = p.C + (int64_t)(p.c_idx ? p.c_idx[gi] : gi) * p.ldc + gj;
+      if (p.accum == ACC_ATOMIC) { for (int e = 0; e < nv; ++e) atomicAdd(cr + e, v[e]); }
+      else if (vec_c && nv == 4) {
+        float4 o = make_float4(v[0], v[1], v[2], v[3]);
+        if (p.accum == ACC_ADD) { const float4 c4 = *reinterpret_cast<const float4*>(cr); o.x += c4.x; o.y += c4.y; o.z += c4.z; o.w += c4.w; }
+        *reinterpret_cast<float4*>(cr) = o;
+      } else {
+        for (int e = 0; e < nv; ++e) cr[e] = p.accum == ACC_ADD ? cr[e] + v[e] : v[e];
+      }
+    }
+    cluster_sync_all();                                            // no rank leaves while its partial tile may still be read
+  } else if (CTA2) cluster_sync_all(); else __syncthreads();
   if (warp == 1) {
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     if (CTA2) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(256) : "memory");
@@ -1448,6 +1517,47 @@ bool launch_x3(dx_stream_t s, const GemmP& g) {
   return true;
 }
 
+// Few-row products (M <= 256: the training step of a small batch, BASELINE config 2) on thread-block clusters:
+// k_tc_gemm_x3<.., KSP>.  Measured on B200 (DX_TC_DEBUG clock trace of M = 128, N = 1536, K = 512): a CTA's k-blocks
+// are a serial chain of ~1400 clocks each — the 12 MMAs of a 3xTF32 k-block cost ~80-100 clocks apiece whether the tile
+// is 32 or 128 columns wide — behind ~5000 clocks of set-up, first TMA, first conversion and the first (slow) MMA
+// chunk, so a 16-k-block product takes 14 us on 12 SMs.  Splitting the reduction over the KS CTAs of a cluster makes
+// the chain KS times shorter on KS times as many SMs; the partial tiles are summed through distributed shared memory
+// in rank order, so the result is deterministic and bias / activation / gate / accumulate epilogues all work (no
+// zero fill, no reduce-add).  Forward products take this path only inside the training entry points (FwdSplitScope):
+// the split changes the summation order, and inference results must not depend on the batch size.
+bool launch_x3k(dx_stream_t s, const GemmP& g) {
+  using Cfg = X3Cfg<false, 128>;
+  static const bool off = getenv("DX_X3_NO_KSPLIT") != nullptr;
+  if (off || g.accum == ACC_ATOMIC || g.M > 256) return false;
+  if (g.a_kc && g.b_kc && !get_fwd_split()) return false;
+  if (!g.a_kc && g.b_kc) return false;
+  const int nkb = (g.K + TBK - 1) / TBK;
+  const int tiles = ((g.M + TBM - 1) / TBM) * ((g.N + 127) / 128);
+  int ks = 8;
+  while (ks > 1 && (tiles * ks > sm_count() || nkb < 2 * ks)) ks >>= 1;   // at least two k-blocks per rank, one wave of CTAs
+  if (ks < 2) return false;
+  const int k_chunk = (nkb + ks - 1) / ks * TBK;
+  CUtensorMap ta, tb;
+  if (g.a_kc) { if (!make_map(&ta, g.A, g.M, g.K, g.lda, TBK, TBM, false, true)) return false; }
+  else        { if (!make_map(&ta, g.A, g.K, g.M, g.lda, 32, TBK, true, true)) return false; }
+  if (g.b_kc) { if (!make_map(&tb, g.B, g.N, g.K, g.ldb, TBK, 128, false, true)) return false; }
+  else        { if (!make_map(&tb, g.B, g.K, g.N, g.ldb, 32, TBK, true, true)) return false; }
+  TcParams p{g.M, g.N, g.K, g.C, g.ldc, g.c_idx, g.bias, g.add, g.ldadd, g.act, g.accum, k_chunk, 0, 0, 1, 0, 0, 0, nullptr};
+  static AttrOnce attr;
+  attr([] {
+    cudaFuncSetAttribute(k_tc_gemm_x3<false, false, false, 128, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM);
+    cudaFuncSetAttribute(k_tc_gemm_x3<false, true, false, 128, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM);
+    cudaFuncSetAttribute(k_tc_gemm_x3<true, true, false, 128, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM);
+  });
+  const dim3 grid(tiles * ks), block(Cfg::THREADS);
+  if (g.a_kc && g.b_kc) launch_k(k_tc_gemm_x3<false, false, false, 128, true>, grid, block, Cfg::SMEM, s, ks, ta, tb, ta, ta, p);
+  else if (g.a_kc && !g.b_kc) launch_k(k_tc_gemm_x3<false, true, false, 128, true>, grid, block, Cfg::SMEM, s, ks, ta, tb, ta, ta, p);
+  else launch_k(k_tc_gemm_x3<true, true, false, 128, true>, grid, block, Cfg::SMEM, s, ks, ta, tb, ta, ta, p);
+  ++g_launches;
+  return true;
+}
+
 // Wide chunked 3xTF32 launch (k_tc_gemm_x3w, pair tiles 256 x 256).  Returns false if not applicable.
 // Reduction splits for the persistent pair-tile kernels.  `tiles` output tiles run on `ncl` clusters in waves, and a
 // last wave that is nearly empty costs as much as a full one (80 tiles on 74 clusters: 54 % of the machine), while
@@ -1571,6 +1681,7 @@ bool tc_gemm(dx_stream_t s, const GemmP& g, int* tile_n, bool x3) {
   if (tile_n) *tile_n = bn;
   if (x3) {
     static const bool no_narrow = getenv("DX_X3_NO_NARROW") != nullptr;
+    if (launch_x3k(s, g)) return true;                                // few rows, long reduction: cluster split-K
     if (g.N <= 64 && !no_narrow) return launch_x3<false, 32>(s, g);   // thin outputs: 32-column tiles
     // Few-row products (small training batches, M <= 256): a 128-column tiling runs N/128 CTAs whose k-blocks are a serial
     // load -> convert -> MMA -> drain chain; 32-column tiles put 4x as many SMs on the weight stream and shorten every link

@@ -152,6 +152,44 @@ def test_tc_gemm_x3_dgrad_wgrad(lib, M, N, K):
     assert (dW.double() - refw).abs().max().item() <= X3_GEMM * refw.abs().max().item()
 
 
+# Few-row products (M <= 256, the small-batch training regime): the reduction is split over a thread-block cluster and
+# the partial tiles are summed through distributed shared memory in rank order (k_tc_gemm_x3<.., KSP>).  Same accuracy
+# bound as the unsplit kernels, every epilogue form, ragged extents, and bit-identical from run to run.
+@pytest.mark.parametrize("M,N,K", [(128, 1536, 512), (128, 512, 512), (128, 2048, 512), (128, 1024, 1024), (128, 27, 1024),
+                                   (128, 55, 1024), (77, 1536, 512), (5, 512, 512), (200, 1000, 520), (256, 2048, 512),
+                                   (128, 128, 128), (1, 1536, 512), (129, 130, 136)])
+def test_tc_gemm_x3_cluster_split_k(lib, M, N, K):
+    from dxvae_b200 import _lib
+    g = torch.Generator().manual_seed(7 * M + 3 * N + K)
+    A = torch.randn(M, K, generator=g).cuda(); W = torch.randn(N, K, generator=g).cuda()
+    b = torch.randn(N, generator=g).cuda()
+    ref0 = A.double() @ W.double().t() + b.double()
+    scale = max(1.0, ref0.abs().max().item())
+    outs = []
+    for act, fn in ((0, lambda t: t), (1, torch.relu), (2, torch.tanh)):
+        for rep in range(2):
+            C = torch.full((M, N), float("nan"), device="cuda")
+            _lib.check(lib.dxvae_test_gemm(32 + 128, M, N, K, A.data_ptr(), K, W.data_ptr(), K, C.data_ptr(), N, b.data_ptr(),
+                                           act, 0, st()), "x3 split-k forward")
+            outs.append(C)
+        assert torch.equal(outs[-1], outs[-2]), "the cluster reduction must be deterministic"
+        err = (outs[-1].double() - fn(ref0)).abs().max().item()
+        assert err <= X3_GEMM * scale, (act, err, scale)
+    # outside the training scope the forward product keeps the unsplit kernels' summation order (inference invariant);
+    # both are FP32-accurate, so they agree to the same bound
+    C0 = torch.full((M, N), float("nan"), device="cuda")
+    _lib.check(lib.dxvae_test_gemm(32, M, N, K, A.data_ptr(), K, W.data_ptr(), K, C0.data_ptr(), N, b.data_ptr(), 0, 0, st()), "x3")
+    assert (C0.double() - outs[0].double()).abs().max().item() <= 2 * X3_GEMM * scale
+    # dgrad: plain store, then accumulate on top
+    dY = torch.randn(M, N, generator=g).cuda()
+    dX = torch.full((M, K), float("nan"), device="cuda")
+    _lib.check(lib.dxvae_test_gemm(33, M, N, K, dY.data_ptr(), N, W.data_ptr(), K, dX.data_ptr(), K, None, 0, 0, st()), "dgrad")
+    ref = dY.double() @ W.double()
+    assert (dX.double() - ref).abs().max().item() <= X3_GEMM * max(1.0, ref.abs().max().item())
+    _lib.check(lib.dxvae_test_gemm(33, M, N, K, dY.data_ptr(), N, W.data_ptr(), K, dX.data_ptr(), K, None, 0, 1, st()), "dgrad+")
+    assert (dX.double() - 2 * ref).abs().max().item() <= 2 * X3_GEMM * max(1.0, ref.abs().max().item())
+
+
 def test_3xtf32_training_step_meets_the_fp32_tolerance(lib):
     """precision="3xtf32": the whole fused ELBO step on the tensor cores within the REFERENCE (fp32) tolerances of
     tests/test_gpu_parity.py: each loss term rel <= 1e-5, every gradient tensor max-norm-relative <= 1e-4 (see the kink
