@@ -1669,7 +1669,10 @@ bool tc_gemm(dx_stream_t s, const GemmP& g, int* tile_n, bool x3) {
   // Products with a tiny weight side go to the FFMA kernels.  The rule looks at N x K only, never at the row count: which
   // kernel family computes a forward product must not depend on how many patches share the batch (a one-graph batch
   // and a 32768-graph batch give a patch the same bits).
-  if ((double)g.N * g.K < 4096.0) return false;
+  // (Weight gradients — ACC_ATOMIC, K = the batch rows of the step — are exempt: a 512 x 512 gradient over the 2-12 active
+  // rows of a small step is 16 short tiles here, but 262 k atomic adds in the FFMA kernel: 34 us against ~10.)
+  if (g.accum != ACC_ATOMIC && (double)g.N * g.K < 4096.0) return false;
+  if (g.accum == ACC_ATOMIC && (double)g.M * g.N < 4096.0) return false;
   int bn = g.N >= 192 ? 256 : (g.N >= 96 ? 128 : 64);
   // Small batches (M of a few hundred rows): a 128 x 256 tiling leaves most SMs idle and each CTA streams a large
   // slice of the weight matrix alone; narrower tiles spread that stream over more SMs (latency, not throughput).
