@@ -14,8 +14,13 @@
  *     nothing synchronises unless stated;
  *   - return 0 = ok, non-zero = error; dxvae_last_error() gives the message
  *     (thread-local).  Nothing throws across the ABI.  Process state is limited to per-device set-up flags
- *     (constant tables, kernel attributes), the launch counter and the thread-local arithmetic mode that an
- *     entry point sets for its own duration.
+ *     (constant tables, kernel attributes), the launch counter, a per-thread table of encoded TMA tensor maps
+ *     (a pure function of address / extents / pitch: cached instead of re-encoded per launch) and the thread-local
+ *     arithmetic mode / training scope that an entry point sets for its own duration;
+ *   - every kernel is launched with programmatic stream serialization and waits (griddepcontrol.wait) before its
+ *     first global access, so back-to-back entry points on one stream overlap launch latency, never data
+ *     (DX_NO_PDL=1 in the environment launches plainly).  Work enqueued by OTHER code on the same stream keeps the
+ *     usual stream order.
  *   - model constants are fixed (7 nodes, X 27, X0 23, H 512, Z 128): kernels are
  *     specialised on them.
  *
