@@ -363,7 +363,7 @@ def run_ours(args):
         traffic, tnote = None, None
         try:    # DRAM bytes of a designated large launch of this kernel family against its algorithmic bytes, from the
                 # committed ncu --set full capture of this round (tools/traffic_from_ncu.py writes the json)
-            tj = json.load(open(os.path.join(ROOT, "profiles", "r02_tc_gemm_traffic.json")))
+            tj = json.load(open(os.path.join(ROOT, "profiles", "r02c_tc_gemm_traffic.json")))   # (captured at the final kernel set of round 2)
             if dom == 2 and args.precision in tj:
                 traffic = tj[args.precision]["dram_bytes_per_launch"]
                 tnote = dict(tj[args.precision], note="DRAM bytes (read + write) of ONE designated launch of this kernel family "
