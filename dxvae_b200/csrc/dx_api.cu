@@ -6,7 +6,7 @@
 
 namespace dx {
 
-long long g_launches = 0;
+std::atomic<long long> g_launches{0};
 static thread_local char g_err[512] = "";
 
 void set_error(const char* fmt, ...) {
@@ -141,7 +141,7 @@ extern "C" {
 
 int dxvae_abi_version(void) { return DXVAE_ABI_VERSION; }
 const char* dxvae_last_error(void) { return g_err; }
-long long dxvae_launch_count(void) { return g_launches; }
+long long dxvae_launch_count(void) { return g_launches.load(); }
 void dxvae_prof_begin(int max_launches) { prof_begin(max_launches); }
 void dxvae_prof_end(double* ms, double* flops, long long* n) { prof_end(ms, flops, n); }
 

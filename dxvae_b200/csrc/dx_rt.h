@@ -2,11 +2,12 @@
 // GPU build: real kernels.  DX_EMU build (tests only): serial CPU loops.
 #pragma once
 #include "dx_common.h"
+#include <atomic>
 #include <stdlib.h>
 
 namespace dx {
 
-extern long long g_launches;  // kernels launched by this library (bench.py reports it)
+extern std::atomic<long long> g_launches;  // kernels launched by this library (bench.py reports it); entry points may run on several host threads
 
 #ifndef DX_EMU
 // ---- programmatic dependent launch --------------------------------------------------------
