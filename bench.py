@@ -475,6 +475,19 @@ def run_ours(args):
                     assert len(syx) == 8 + 128 * nfull
                 model.decode_precision = DXVAE().decode_precision
             del hv, hz, q, mu_h, sd_h, syx
+        # cfg1 shape: encode + greedy decode(mu) of 1024 graphs handed over as a Python list of host graph objects, decoded
+        # graphs read back to the host (the reference's main.py:24-32 flow; random-init weights, so timing only — parity of
+        # this config with a trained model is tests/test_cfg1_trained.py)
+        with torch.no_grad():
+            g1024 = list(host[:1024])
+            for _ in range(2):
+                out1 = model.encode_decode(g1024); out1.params.cpu()
+            torch.cuda.synchronize(); t0 = time.perf_counter()
+            for _ in range(5):
+                out1 = model.encode_decode(g1024); out1.params.cpu(); out1.adj.cpu()
+            torch.cuda.synchronize()
+            extra["cfg1_encode_decode_1024_patches_per_s"] = 5 * 1024 / (time.perf_counter() - t0)
+            del g1024, out1
         idx = list(range(128))
         for _ in range(3):
             tr.step(pool, idx)
