@@ -36,7 +36,7 @@ def _batch(n, seed):
 
 
 @pytest.mark.parametrize("prec", ["3xtf32", "fp32"])
-@pytest.mark.parametrize("n", [1, 2, 129, 257])
+@pytest.mark.parametrize("n", [1, 2, 129, 256, 257])   # (<= 256 rows: the cluster split-K products; 257: the unsplit ones)
 def test_extreme_topologies_and_ragged_batch_sizes(prec, n):
     m, o = _model(prec)
     X, P, E, A, G = _batch(n, n)
