@@ -29,6 +29,11 @@ DecWs carve_dec(Arena& ar, int64_t B, bool train, const int32_t* step_ptr) {
     const size_t n = (size_t)(step_ptr[list + 1] - step_ptr[list]);
     return n > 0 ? n : 1;
   };
+  // The per-step state / gate buffers of the compacted schedule take EXACTLY their active rows (an empty step takes
+  // none; rows are 2 KB / 8 KB, so no alignment padding either): the 21 steps' buffers are then one contiguous matrix
+  // in step order, which is what lets the backward pass form each cell's weight gradients as ONE product over all
+  // active (graph, step) pairs instead of one per step (decode_bwd_impl).
+  auto step_rows_exact = [&](int t) -> size_t { return compact ? (size_t)(step_ptr[t + 1] - step_ptr[t]) : b; };
   w.z = ar.take<float>(b * Z); w.Hinit = ar.take<float>(b * H); w.Hd = ar.take<float>(7 * b * H);
   w.Pg = ar.take<float>(6 * b * 2 * H); w.Pm = ar.take<float>(6 * b * 2 * H); w.Q = ar.take<float>(6 * b * 4 * H);
   w.gh = ar.take<float>(b * G3); w.ghl0 = ar.take<float>(b * G3); w.Hrun = ar.take<float>(b * H);
@@ -37,6 +42,8 @@ DecWs carve_dec(Arena& ar, int64_t B, bool train, const int32_t* step_ptr) {
     w.U = ar.take<float>(b * 4 * H); w.UC = ar.take<float>(b * 4 * H); w.dHiC = ar.take<float>(b * H);
     for (int k = 0; k < 3; ++k) w.dWihP[k] = ar.take<float>((size_t)G3 * XP);
     w.XL = ar.take<float>(7 * b * XP); w.xc = ar.take<float>(b * XP);
+    const size_t nact = compact ? (size_t)(step_ptr[NSTEP] - step_ptr[0]) : 0;
+    w.xlS = ar.take<float>((nact ? nact : 1) * XP); w.xiS = ar.take<float>((nact ? nact : 1) * XP);
   }
   auto per_node = [&](float** arr, size_t cols, bool need) {
     float* shared = need ? nullptr : ar.take<float>(b * cols);
@@ -44,7 +51,7 @@ DecWs carve_dec(Arena& ar, int64_t B, bool train, const int32_t* step_ptr) {
   };
   auto per_step = [&](float** arr, size_t cols, bool need, bool by_rows = false) {
     float* shared = need ? nullptr : ar.take<float>(b * cols);
-    for (int t = 0; t < NSTEP; ++t) arr[t] = need ? ar.take<float>((by_rows ? list_rows(t) : b) * cols) : shared;
+    for (int t = 0; t < NSTEP; ++t) arr[t] = need ? ar.take<float>((by_rows ? step_rows_exact(t) : b) * cols) : shared;
   };
   per_node(w.A1, 2 * H, train); per_node(w.A2, 2 * H, train); per_node(w.L, LD_L, train);
   per_node(w.gxc, G3, train); per_node(w.gxl, G3, train); per_node(w.Hc0, H, train);
@@ -845,22 +852,31 @@ static void mlp3_bwd(dx_stream_t st, const Weights& W, const Weights& G, int B, 
 }
 
 // looper cell backward for one propagate: dHi -> (dHc += ..., weight grads)
+// x_stash != NULL (a compacted step): the gate gradients are written IN PLACE over the step's saved gates (each thread
+// reads its four gate values before it stores the four gradients at the same addresses; nothing reads the gates
+// again) and the masked x rows go to x_stash — both weight gradients of the cell are then formed ONCE for all steps at
+// the end of decode_bwd_impl from the concatenated buffers instead of two products per step.
 static void looper_bwd(dx_stream_t st, const Weights& W, const Weights& G, int B, int vi, const RowMap& rm,   // rm.M rows
                        const float* dHi, const float* gates, const float* Hc, int smode, const uint64_t* adj,
-                       const float* Xi, const DecWs& w, float* dHc, bool dHc_accum) {
+                       const float* Xi, const DecWs& w, float* dHc, bool dHc_accum, float* x_stash = nullptr) {
   // dHc (+)= dHi*z + dgh W_hh            (rm.M rows: all B graphs, or the active rows of a compacted step)
   const int M = rm.M;
   float* direct = dHc_accum ? w.dHin : dHc;  // dHin is free scratch at this point
-  CellBwd cb{rm, dHi, 0, gates, 0, Hc, 0, w.dgx, nullptr, w.dgh, direct, smode, adj};
+  float* d4 = x_stash ? const_cast<float*>(gates) : w.dgx;
+  float* dgh = d4 + H;
+  CellBwd cb{rm, dHi, 0, gates, 0, Hc, 0, d4, nullptr, dgh, direct, smode, adj};
   cell_bwd(st, cb, G[P_LD_BIH], G[P_LD_BHH]);
   if (dHc_accum) add_inplace(st, (int64_t)M * H / 4, dHc, direct);
-  linear_dgrad(st, M, G3, H, w.dgh, 4 * H, W[P_LD_WHH], H, dHc, H, ACC_ADD);
-  linear_wgrad(st, M, G3, H, w.dgh, 4 * H, Hc, H, G[P_LD_WHH], H);
+  linear_dgrad(st, M, G3, H, dgh, 4 * H, W[P_LD_WHH], H, dHc, H, ACC_ADD);
+  if (!x_stash) linear_wgrad(st, M, G3, H, dgh, 4 * H, Hc, H, G[P_LD_WHH], H);
   // weight_ih gradient: x masked by the self-loop flag (XL), gathered to the active rows when compacted
   if (smode != S_ZERO) {
     const float* xl = w.XL + (size_t)vi * B * XP;
-    if (rm.rows) { gather_rows(st, M, XP, rm.rows, const_cast<float*>(xl), w.xc, 0); xl = w.xc; }
-    linear_wgrad(st, M, G3, XP, w.dgx, 4 * H, xl, XP, w.dWihP[1], XP);
+    if (x_stash) { gather_rows(st, M, XP, rm.rows, const_cast<float*>(xl), x_stash, 0); }
+    else {
+      if (rm.rows) { gather_rows(st, M, XP, rm.rows, const_cast<float*>(xl), w.xc, 0); xl = w.xc; }
+      linear_wgrad(st, M, G3, XP, d4, 4 * H, xl, XP, w.dWihP[1], XP);
+    }
   }
   (void)Xi; (void)G;
 }
@@ -869,6 +885,10 @@ void decode_bwd_impl(dx_stream_t st, const Weights& W, const Weights& G, int B, 
                      const Batch& bt, LossW lw) {
   const uint64_t* adj = bt.adj;
   const size_t bH = (size_t)B * H;
+  // weight gradients of the re-propagates: one product per tensor over all active (graph, step) pairs at the end
+  // (DX_DEFER_WGRAD=0: two products per step, for A/B)
+  static const bool defer_env = [] { const char* e = getenv("DX_DEFER_WGRAD"); return !(e && e[0] == '0'); }();
+  const bool defer = defer_env;
   zero_async(st, w.dHd + 6 * bH, sizeof(float) * bH);   // nothing reads the last node's state: its gradient is zero
   if (bt.step_ptr) {
     // compacted steps: msg_bwd accumulates the "out" halves for every graph, the "in" halves only on the rows of the
@@ -927,6 +947,15 @@ void decode_bwd_impl(dx_stream_t st, const Weights& W, const Weights& G, int B, 
           linear_dgrad(st, n, 4 * H, H, w.UC, 4 * H, W[P_E_W0], 2 * H, w.dHiC, H, ACC_ADD);
           linear_wgrad(st, n, 4 * H, H, w.UC, 4 * H, w.Hi[t], H, G[P_E_W0], 2 * H);
         }
+        const size_t soff = (size_t)(bt.step_ptr[t] - bt.step_ptr[0]) * XP;   // this step's rows in the concatenated x stashes
+        if (defer) {
+        looper_bwd(st, W, G, B, vi, rc, w.dHiC, w.g_l[t], w.Hc[t], S_SELF, adj, Xi, w, w.dHc, false, w.xlS + soff);
+        // combiner: gate gradients in place over g_c[t]; its two weight gradients are deferred like the looper's
+        CellBwd cc{rc, w.dHc, 0, w.g_c[t], 0, w.Hin[t], 0, w.g_c[t], nullptr, w.g_c[t] + H, w.dHin, S_ONE, adj};
+        cell_bwd(st, cc, G[P_CD_BIH], G[P_CD_BHH]);
+        linear_dgrad(st, n, G3, H, w.g_c[t] + H, 4 * H, W[P_CD_WHH], H, w.dHin, H, ACC_ADD);
+        gather_rows(st, n, XP, rows, const_cast<float*>(Xi), w.xiS + soff, 0);
+        } else {
         looper_bwd(st, W, G, B, vi, rc, w.dHiC, w.g_l[t], w.Hc[t], S_SELF, adj, Xi, w, w.dHc, false);
         CellBwd cc{rc, w.dHc, 0, w.g_c[t], 0, w.Hin[t], 0, w.dgx, nullptr, w.dgh, w.dHin, S_ONE, adj};
         cell_bwd(st, cc, G[P_CD_BIH], G[P_CD_BHH]);
@@ -934,6 +963,7 @@ void decode_bwd_impl(dx_stream_t st, const Weights& W, const Weights& G, int B, 
         linear_wgrad(st, n, G3, H, w.dgh, 4 * H, w.Hin[t], H, G[P_CD_WHH], H);
         gather_rows(st, n, XP, rows, const_cast<float*>(Xi), w.xc, 0);
         linear_wgrad(st, n, G3, XP, w.dgx, 4 * H, w.xc, XP, w.dWihP[0], XP);
+        }
         {
           // dHrun[b] += dHin[m]: the running gradient of the aggregate.  Steps are walked with vj ascending, so a row was
           // written before iff the graph has an edge between vi and some node below vj: first touch stores (no zero fill)
@@ -1075,6 +1105,17 @@ void decode_bwd_impl(dx_stream_t st, const Weights& W, const Weights& G, int B, 
   linear_wgrad(st, B, H, Z, w.dHinit, H, z, Z, G[P_ZH_W], Z);
   colsum_accum(st, B, H, w.dHinit, H, G[P_ZH_B]);
   linear_dgrad(st, B, H, Z, w.dHinit, H, W[P_ZH_W], Z, w.dz, Z, ACC_STORE);
+  if (bt.step_ptr && defer) {
+    // the deferred weight gradients of the 21 re-propagates: ONE product per tensor over every active (graph, step) pair
+    // (the per-step gate-gradient, state and x buffers are contiguous in step order, see carve_dec)
+    const int nact = bt.step_ptr[NSTEP] - bt.step_ptr[0];
+    if (nact > 0) {
+      linear_wgrad(st, nact, G3, H, w.g_l[0] + H, 4 * H, w.Hc[0], H, G[P_LD_WHH], H);
+      linear_wgrad(st, nact, G3, XP, w.g_l[0], 4 * H, w.xlS, XP, w.dWihP[1], XP);
+      linear_wgrad(st, nact, G3, H, w.g_c[0] + H, 4 * H, w.Hin[0], H, G[P_CD_WHH], H);
+      linear_wgrad(st, nact, G3, XP, w.g_c[0], 4 * H, w.xiS, XP, w.dWihP[0], XP);
+    }
+  }
   unpad_add_wih(st, w.dWihP[0], SX, G[P_CD_WIH]);
   unpad_add_wih(st, w.dWihP[1], SX, G[P_LD_WIH]);
   unpad_add_wih(st, w.dWihP[2], SX0, G[P_RD_WIH]);

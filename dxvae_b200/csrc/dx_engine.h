@@ -58,6 +58,8 @@ struct DecWs {
   float *gh, *ghl0, *Hrun, *rowloss;
   float *U, *UC, *dHiC;    // compacted teacher forcing: running edge-head product, compact temp, compact dHi
   float *WihP[3], *dWihP[3], *XL, *xc;   // padded input weights / grads (comb, loop, root), masked features (7B,32), compact x rows
+  float *xlS, *xiS;     // compacted teacher forcing, backward: the x rows of every active (graph, step) pair, concatenated in step order
+                        // (masked by the self-loop flag / plain): the operands of the ONE deferred weight_ih gradient per cell
   // greedy only
   float *Xd, *Pn;
   int *act_rows, *act_cnt; uint8_t* act_flag;   // graphs that gained an edge at the current step (device-compacted)
