@@ -858,17 +858,19 @@ static void mlp3_bwd(dx_stream_t st, const Weights& W, const Weights& G, int B, 
 // the end of decode_bwd_impl from the concatenated buffers instead of two products per step.
 static void looper_bwd(dx_stream_t st, const Weights& W, const Weights& G, int B, int vi, const RowMap& rm,   // rm.M rows
                        const float* dHi, const float* gates, const float* Hc, int smode, const uint64_t* adj,
-                       const float* Xi, const DecWs& w, float* dHc, bool dHc_accum, float* x_stash = nullptr) {
+                       const float* Xi, const DecWs& w, float* dHc, bool dHc_accum, float* x_stash = nullptr,
+                       bool defer = false) {                        // defer without x_stash: the S_ZERO propagate (no x term)
   // dHc (+)= dHi*z + dgh W_hh            (rm.M rows: all B graphs, or the active rows of a compacted step)
   const int M = rm.M;
   float* direct = dHc_accum ? w.dHin : dHc;  // dHin is free scratch at this point
-  float* d4 = x_stash ? const_cast<float*>(gates) : w.dgx;
+  defer = defer || x_stash != nullptr;
+  float* d4 = defer ? const_cast<float*>(gates) : w.dgx;
   float* dgh = d4 + H;
   CellBwd cb{rm, dHi, 0, gates, 0, Hc, 0, d4, nullptr, dgh, direct, smode, adj};
   cell_bwd(st, cb, G[P_LD_BIH], G[P_LD_BHH]);
   if (dHc_accum) add_inplace(st, (int64_t)M * H / 4, dHc, direct);
   linear_dgrad(st, M, G3, H, dgh, 4 * H, W[P_LD_WHH], H, dHc, H, ACC_ADD);
-  if (!x_stash) linear_wgrad(st, M, G3, H, dgh, 4 * H, Hc, H, G[P_LD_WHH], H);
+  if (!defer) linear_wgrad(st, M, G3, H, dgh, 4 * H, Hc, H, G[P_LD_WHH], H);
   // weight_ih gradient: x masked by the self-loop flag (XL), gathered to the active rows when compacted
   if (smode != S_ZERO) {
     const float* xl = w.XL + (size_t)vi * B * XP;
@@ -1047,12 +1049,15 @@ void decode_bwd_impl(dx_stream_t st, const Weights& W, const Weights& G, int B, 
     linear_wgrad(st, B, 2 * H, H, w.dES1, 2 * H, w.Hi_p1[vi], H, G[P_ES_W0], H);
     colsum_accum(st, B, 2 * H, w.dES1, 2 * H, G[P_ES_B0]);
     linear_dgrad(st, B, 2 * H, H, w.dES1, 2 * H, W[P_ES_W0], H, dHi, H, compact ? ACC_ADD : ACC_STORE);
-    looper_bwd(st, W, G, B, vi, rm, dHi, w.g_p1[vi], w.Hc0[vi], S_ZERO, adj, Xi, w, w.dHc0, !compact);
+    // first propagate of the node (all B graphs): gate gradients in place over g_p1[vi] / g_c0[vi]; the per-node buffers
+    // of nodes 1..6 are contiguous, so both weight gradients are formed once over 6B rows after the node loop
+    looper_bwd(st, W, G, B, vi, rm, dHi, w.g_p1[vi], w.Hc0[vi], S_ZERO, adj, Xi, w, w.dHc0, !compact, nullptr, defer);
     if (ns > 0) scatter_rows(st, ns, H, rows_s, w.dHc, w.dHc0, 1);
     // combiner with H_in = 0: only input weights / biases receive gradient
-    CellBwd c0{rm, w.dHc0, 0, w.g_c0[vi], 0, nullptr, 0, w.dgx, nullptr, w.dgh, nullptr, S_ONE, adj};
+    float* d0 = defer ? w.g_c0[vi] : w.dgx;
+    CellBwd c0{rm, w.dHc0, 0, w.g_c0[vi], 0, nullptr, 0, d0, nullptr, d0 + H, nullptr, S_ONE, adj};
     cell_bwd(st, c0, G[P_CD_BIH], G[P_CD_BHH]);
-    linear_wgrad(st, B, G3, XP, w.dgx, 4 * H, Xi, XP, w.dWihP[0], XP);
+    if (!defer) linear_wgrad(st, B, G3, XP, w.dgx, 4 * H, Xi, XP, w.dWihP[0], XP);
     // parameter head of node vi read h_{vi-1}
     float* dprev = w.dHd + (size_t)(vi - 1) * bH;
     const float* hprev = w.Hd + (size_t)(vi - 1) * bH;
@@ -1105,6 +1110,11 @@ void decode_bwd_impl(dx_stream_t st, const Weights& W, const Weights& G, int B, 
   linear_wgrad(st, B, H, Z, w.dHinit, H, z, Z, G[P_ZH_W], Z);
   colsum_accum(st, B, H, w.dHinit, H, G[P_ZH_B]);
   linear_dgrad(st, B, H, Z, w.dHinit, H, W[P_ZH_W], Z, w.dz, Z, ACC_STORE);
+  if (defer) {
+    // first propagates of nodes 1..6 (g_p1 / g_c0 / Hc0 are per-node buffers carved back to back; Xn is node-major)
+    linear_wgrad(st, 6 * B, G3, H, w.g_p1[1] + H, 4 * H, w.Hc0[1], H, G[P_LD_WHH], H);
+    linear_wgrad(st, 6 * B, G3, XP, w.g_c0[1], 4 * H, bt.Xn + (size_t)B * XP, XP, w.dWihP[0], XP);
+  }
   if (bt.step_ptr && defer) {
     // the deferred weight gradients of the 21 re-propagates: ONE product per tensor over every active (graph, step) pair
     // (the per-step gate-gradient, state and x buffers are contiguous in step order, see carve_dec)

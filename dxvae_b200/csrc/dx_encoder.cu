@@ -161,21 +161,28 @@ void encode_bwd_impl(dx_stream_t st, const Weights& W, const Weights& G, const B
       proj_wgrad(st, Mh, w.dPg, Hv, G[P_G_W], half);
       proj_wgrad(st, Mh, w.dPm, Hv, G[P_M_W], half);
     }
-    // looper
-    CellBwd cl{rm, dH, 0, w.gl + (size_t)base * 4 * H, 0, Hc, 0, w.dgx, nullptr, w.dgh, w.dHc, S_SELF, bt.adj};
+    // looper: the gate gradients are written IN PLACE over the level's saved gates (schedule order: the levels are one
+    // contiguous matrix), the cells' weight gradients are formed once over all levels after the loop
+    float* gl = w.gl + (size_t)base * 4 * H;
+    CellBwd cl{rm, dH, 0, gl, 0, Hc, 0, gl, nullptr, gl + H, w.dHc, S_SELF, bt.adj};
     cell_bwd(st, cl, G[P_LE_BIH], G[P_LE_BHH]);
-    linear_dgrad(st, M, G3, H, w.dgh, 4 * H, W[P_LE_WHH], H, w.dHc, H, ACC_ADD);
-    linear_wgrad(st, M, G3, H, w.dgh, 4 * H, Hc, H, G[P_LE_WHH], H);
-    linear_wgrad(st, M, G3, XP, w.dgx, 4 * H, w.XnSL + (size_t)base * XP, XP, w.dWihP[1], XP);   // x masked by the self-loop flag
+    linear_dgrad(st, M, G3, H, gl + H, 4 * H, W[P_LE_WHH], H, w.dHc, H, ACC_ADD);
     // combiner
-    CellBwd cc{rm, w.dHc, 0, w.gc + (size_t)base * 4 * H, 0, L > 0 ? Hin : nullptr, 0, w.dgx, nullptr, w.dgh,
-               L > 0 ? dHin : nullptr, S_ONE, bt.adj};
+    float* gc = w.gc + (size_t)base * 4 * H;
+    CellBwd cc{rm, w.dHc, 0, gc, 0, L > 0 ? Hin : nullptr, 0, gc, nullptr, gc + H, L > 0 ? dHin : nullptr, S_ONE, bt.adj};
     cell_bwd(st, cc, G[P_CE_BIH], G[P_CE_BHH]);
-    if (L > 0) {
-      linear_dgrad(st, M, G3, H, w.dgh, 4 * H, W[P_CE_WHH], H, dHin, H, ACC_ADD);
-      linear_wgrad(st, M, G3, H, w.dgh, 4 * H, Hin, H, G[P_CE_WHH], H);
-    }
-    linear_wgrad(st, M, G3, XP, w.dgx, 4 * H, Xs, XP, w.dWihP[0], XP);
+    if (L > 0) linear_dgrad(st, M, G3, H, gc + H, 4 * H, W[P_CE_WHH], H, dHin, H, ACC_ADD);
+    (void)Xs;
+  }
+  {
+    // one weight-gradient product per tensor over the 6B operator rows (x masked by the self-loop flag for the looper;
+    // the combiner's hidden product exists from level 1 on: level-0 rows have H_in = 0 and no saved input state)
+    const int n_op = (int)R6;
+    const int b1 = bt.n_levels > 1 ? bt.level_ptr[1] : n_op;
+    linear_wgrad(st, n_op, G3, H, w.gl + H, 4 * H, w.Hc, H, G[P_LE_WHH], H);
+    linear_wgrad(st, n_op, G3, XP, w.gl, 4 * H, w.XnSL, XP, w.dWihP[1], XP);
+    if (n_op > b1) linear_wgrad(st, n_op - b1, G3, H, w.gc + (size_t)b1 * 4 * H + H, 4 * H, w.Hin + (size_t)b1 * H, H, G[P_CE_WHH], H);
+    linear_wgrad(st, n_op, G3, XP, w.gc, 4 * H, w.XnS, XP, w.dWihP[0], XP);
   }
   unpad_add_wih(st, w.dWihP[0], SX, G[P_CE_WIH]);
   unpad_add_wih(st, w.dWihP[1], SX, G[P_LE_WIH]);

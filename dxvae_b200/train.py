@@ -9,7 +9,7 @@ over the flat blob) is replicated.  No other collective is on the path.
 
 Small batches (the reference's own regime: size_batch 32..128, BASELINE config 2) are bound by the
 latency of ~900 dependent kernels; the native side answers with programmatic dependent launch and
-cluster split-K products (DESIGN.md §5 "Small batches": 5.95 ms per batch-128 step).  Optionally
+cluster split-K products (DESIGN.md §5 "Small batches": 5.75 ms per batch-128 step).  Optionally
 (graph_max_batch > 0) the step is captured ONCE into a CUDA graph over static buffers and replayed:
 the schedule is made batch-independent (encoder levels = the reference's node order 6..1, every
 teacher-forcing step on every graph — both are valid schedules of the same function), so one graph
