@@ -46,7 +46,7 @@ int elbo_step(dx_stream_t st, const float* weights, const Batch& bt, const float
               float* mu_out, float* std_out, float* grads, void* ws, size_t ws_bytes, int precision, void* dec_done_event) {
   const int B = (int)bt.B;
   PrecisionScope prec(precision);
-  FwdSplitScope fsplit(true);   // training: few-row forward products may split their reduction (dx_gemm.h)
+  FwdSplitScope fsplit(true, few_rows_for_batch(bt.B));   // training: few-row forward products may split their reduction (dx_gemm.h)
   Arena ar(ws, ws_bytes);
   TrainWs t = carve_train(ar, bt.B, bt.n_levels, bt.level_ptr, bt.step_ptr);
   DX_CHECK(!ar.overflow, "elbo_step: workspace too small (%zu < %zu bytes)", ws_bytes, ar.off);
@@ -81,7 +81,7 @@ int loss_step(dx_stream_t st, const float* weights, const Batch& bt, const float
               LossW lw, float* loss5, float* grads, float* dmu, float* dsd, void* ws, size_t ws_bytes, int precision) {
   const int B = (int)bt.B;
   PrecisionScope prec(precision);
-  FwdSplitScope fsplit(true);   // training: few-row forward products may split their reduction (dx_gemm.h)
+  FwdSplitScope fsplit(true, few_rows_for_batch(bt.B));   // training: few-row forward products may split their reduction (dx_gemm.h)
   Arena ar(ws, ws_bytes);
   DecWs d = carve_dec(ar, bt.B, true, bt.step_ptr);
   DX_CHECK(!ar.overflow, "loss_step: workspace too small (%zu < %zu bytes)", ws_bytes, ar.off);
@@ -105,7 +105,7 @@ int loss_step(dx_stream_t st, const float* weights, const Batch& bt, const float
 int encode_bwd(dx_stream_t st, const float* weights, const Batch& bt, const float* sd, const float* dmu,
                const float* dsd, float* grads, void* ws, size_t ws_bytes, int precision) {
   PrecisionScope prec(precision);
-  FwdSplitScope fsplit(true);   // training: few-row forward products may split their reduction (dx_gemm.h)
+  FwdSplitScope fsplit(true, few_rows_for_batch(bt.B));   // training: few-row forward products may split their reduction (dx_gemm.h)
   Arena ar(ws, ws_bytes);
   EncWs e = carve_enc(ar, bt.B, true, bt.n_levels, bt.level_ptr);
   DX_CHECK(!ar.overflow, "encode_bwd: workspace too small (%zu < %zu bytes)", ws_bytes, ar.off);
@@ -283,7 +283,7 @@ int dxvae_test_gemm(int variant, int64_t M, int64_t N, int64_t K, const float* A
     return check_launch("test_gemm_bf16");
   }
   PrecisionScope prec((variant & 32) ? PREC_3XTF32 : ((variant & 16) ? PREC_TF32 : PREC_FP32));
-  FwdSplitScope fsplit((variant & 128) != 0);   // +128: as inside the training entry points (few-row forward products may split)
+  FwdSplitScope fsplit((variant & 128) != 0, (variant & 128) ? 1024 : 256);   // +128: as inside the training entry points (few-row forward products may split)
   variant &= 15;
   DX_CHECK(variant >= 0 && variant <= 2, "test_gemm: unknown variant %d", variant);
   if (variant == 0) linear_fwd(DX_ST(stream), (int)M, (int)N, (int)K, A, lda, Bm, ldb, bias, C, ldc, act);

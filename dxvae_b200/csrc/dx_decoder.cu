@@ -20,6 +20,13 @@ namespace dx {
 // of the step, so they are sized by the schedule's row counts instead of B (about 30 % of the (graph, step) pairs on
 // dataset-like topologies), the self-loop propagate's gates by the self-loop rows, and a step's E1 only holds the
 // 256-byte relu bit-mask of the fused edge head.  Without it (dense replay, greedy decode) every buffer has B rows.
+// Teacher forcing never feeds a parameter head's output back (x_vi is the true X), so the heads of nodes 1..6 can run as
+// ONE 3-layer pass over the 6B finished node states after the node loop, and their backward as one pass before it
+// (18 + 54 product launches become 3 + 9).  It needs the two relu-gradient scratch matrices at 6B rows instead of B
+// (+80 KB per patch), so it is used for batches up to DX_HEADS_BATCH_MAX graphs (default 4096: the small-batch regime,
+// where the step is bound by the number of dependent launches); larger batches keep one pass per node.
+static bool heads_batched(int64_t B, bool train) { return train && B <= small_batch_max(); }   // (dx_gemm.h)
+
 DecWs carve_dec(Arena& ar, int64_t B, bool train, const int32_t* step_ptr) {
   DecWs w{};
   const size_t b = (size_t)B;
@@ -71,7 +78,7 @@ DecWs carve_dec(Arena& ar, int64_t B, bool train, const int32_t* step_ptr) {
     w.dHi = ar.take<float>(b * H); w.dHc = ar.take<float>(b * H); w.dHin = ar.take<float>(b * H);
     w.dHrun = ar.take<float>(b * H); w.dHc0 = ar.take<float>(b * H);
     w.dgx = ar.take<float>(b * 4 * H); w.dgh = w.dgx + H; w.dgxs = nullptr;   // one D4 buffer, two views (CellBwd)
-    w.dE1 = ar.take<float>(b * 4 * H); w.dA1 = ar.take<float>(b * 2 * H); w.dA2 = ar.take<float>(b * 2 * H);
+    w.dE1 = ar.take<float>(b * 4 * H); { const size_t hb = heads_batched(B, train) ? 6 * b : b; w.dA1 = ar.take<float>(hb * 2 * H); w.dA2 = ar.take<float>(hb * 2 * H); }
     w.dES1 = ar.take<float>(b * 2 * H); w.dHinit = ar.take<float>(b * H); w.dz = ar.take<float>(b * Z);
   } else {
     w.U = ar.take<float>(b * 4 * H); w.UC = ar.take<float>(b * 4 * H);
@@ -141,6 +148,40 @@ static void loss_xi(dx_stream_t st, int B, int vi, const float* Li, const float*
     }
     for (int c = 27; c < LD_L; ++c) d[c] = 0.f;
     rowloss[(int64_t)B + b] += acc * ib;  // slot 1: loss_Xi
+  });
+}
+// the same for nodes 1..6 in one launch (batched parameter heads): thread per graph walks its six operators in node
+// order, so the row's loss_Xi sum is formed exactly as six consecutive loss_xi launches form it
+static void loss_xi_all(dx_stream_t st, int B, const float* L1, const float* Xn, const int32_t* cls, LossW lw,
+                        float* rowloss, float* dL1) {
+  foreach (st, B, [=] DX_HD(int64_t b) {
+    const float ib = lw.inv_batch;
+    float tot = rowloss[(int64_t)B + b];
+    for (int vi = 1; vi < NN; ++vi) {
+      const float* l = L1 + ((int64_t)(vi - 1) * B + b) * LD_L; const float* x = Xn + ((int64_t)vi * B + b) * XP;
+      float* d = dL1 + ((int64_t)(vi - 1) * B + b) * LD_L;
+      float acc = 0.f;
+      for (int c = 0; c < 18; ++c) {
+        const float w = c < 9 ? lw.w_env : (c == 9 ? lw.w_frq : 1.f);
+        const float df = l[c] * w - x[c] * w;
+        acc += df * df; d[c] = 2.f * df * w * ib;
+      }
+      acc += bce_logits(l[18], x[18]); d[18] = (sigmoidf_(l[18]) - x[18]) * ib;
+      for (int seg = 0; seg < 2; ++seg) {
+        const int lo = 19 + 4 * seg;
+        const int tgt = cls[(int64_t)(2 + 6 * seg + (vi - 1)) * B + b];
+        float mx = l[lo];
+        for (int c = 1; c < 4; ++c) mx = fmaxf(mx, l[lo + c]);
+        float se = 0.f;
+        for (int c = 0; c < 4; ++c) se += expf(l[lo + c] - mx);
+        const float lse = mx + logf(se);
+        acc += lse - l[lo + tgt];
+        for (int c = 0; c < 4; ++c) d[lo + c] = (expf(l[lo + c] - lse) - (c == tgt ? 1.f : 0.f)) * ib;
+      }
+      for (int c = 27; c < LD_L; ++c) d[c] = 0.f;
+      tot += acc * ib;
+    }
+    rowloss[(int64_t)B + b] = tot;  // slot 1: loss_Xi
   });
 }
 // edge heads: model.py:339 (self loop, n=1: target A[vi,vi]) and :363 (n=2: A[vj,vi], A[vi,vj])
@@ -697,9 +738,13 @@ void decode_fwd_impl(dx_stream_t st, const Weights& W, int B, const float* z, co
     const float* hprev_node = w.Hd + (size_t)(vi - 1) * B * H;
     float* Xi = const_cast<float*>(Xsrc) + (size_t)vi * B * XP;
     RowMap rm{B, B, nullptr, vi * B};
-    mlp3_fwd(st, W, B, P_X_W0, hprev_node, SX, w.A1[vi], w.A2[vi], w.L[vi]);
-    if (train) loss_xi(st, B, vi, w.L[vi], Xi, io.bt->cls, io.lw, w.rowloss, w.dL[vi]);
-    else reg_xi(st, B, w.L[vi], w.Xd + (size_t)vi * B * XP, w.Pn + (size_t)vi * B * XP, io.margins);
+    if (!train) {
+      mlp3_fwd(st, W, B, P_X_W0, hprev_node, SX, w.A1[vi], w.A2[vi], w.L[vi]);
+      reg_xi(st, B, w.L[vi], w.Xd + (size_t)vi * B * XP, w.Pn + (size_t)vi * B * XP, io.margins);
+    } else if (!heads_batched(B, train)) {                         // (batched heads: one pass after the node loop)
+      mlp3_fwd(st, W, B, P_X_W0, hprev_node, SX, w.A1[vi], w.A2[vi], w.L[vi]);
+      loss_xi(st, B, vi, w.L[vi], Xi, io.bt->cls, io.lw, w.rowloss, w.dL[vi]);
+    }
     linear_fwd(st, B, G3, Kx, Xi, XP, Wc, ldx, nullptr, w.gxc[vi], G3);
     linear_fwd(st, B, G3, Kx, Xi, XP, Wl, ldx, nullptr, w.gxl[vi], G3);
     // P1 (model.py:234/320): no edges yet -> H_in = 0, x_loop = 0
@@ -833,6 +878,12 @@ void decode_fwd_impl(dx_stream_t st, const Weights& W, int B, const float* z, co
     }
     if (vi < NN - 1) node_projections(st, W, B, vi, w);
   }
+  if (heads_batched(B, train)) {
+    // parameter heads of nodes 1..6 (model.py:318/323-328) on the finished states h_0..h_5: Hd, A1, A2, L, dL are
+    // node-major and carved back to back, so rows [0,6B) of Hd map to rows [0,6B) of the node-1 buffers
+    mlp3_fwd(st, W, 6 * B, P_X_W0, w.Hd, SX, w.A1[1], w.A2[1], w.L[1]);
+    loss_xi_all(st, B, w.L[1], Xsrc, io.bt->cls, io.lw, w.rowloss, w.dL[1]);
+  }
 }
 
 // =============================================================================================
@@ -915,6 +966,12 @@ void decode_bwd_impl(dx_stream_t st, const Weights& W, const Weights& G, int B, 
   for (int k = 0; k < 3; ++k) zero_async(st, w.dWihP[k], sizeof(float) * G3 * XP);
   mask_features(st, (int64_t)7 * B, B, nullptr, 0, adj, bt.Xn, w.XL);
 
+  const bool hbatch = heads_batched(B, true);
+  if (hbatch) {
+    // backward of the batched parameter heads: the FIRST writer of dh_0..dh_5 (stores; every other consumer of a node
+    // state accumulates on top, below)
+    mlp3_bwd(st, W, G, 6 * B, P_X_W0, w.Hd, SX, w.A1[1], w.A2[1], w.dL[1], w, w.dHd, ACC_STORE);
+  }
   int t_end = NSTEP;  // steps of node vi occupy [t_end - vi, t_end)
   for (int vi = NN - 1; vi >= 1; --vi) {
     const float* Xi = bt.Xn + (size_t)vi * B * XP;
@@ -1062,7 +1119,7 @@ void decode_bwd_impl(dx_stream_t st, const Weights& W, const Weights& G, int B, 
     float* dprev = w.dHd + (size_t)(vi - 1) * bH;
     const float* hprev = w.Hd + (size_t)(vi - 1) * bH;
     // first writer of dh_{vi-1} (its other consumers are folded in just below): stores, so dHd needs no zero fill
-    mlp3_bwd(st, W, G, B, P_X_W0, hprev, SX, w.A1[vi], w.A2[vi], w.dL[vi], w, dprev, ACC_STORE);
+    if (!hbatch) mlp3_bwd(st, W, G, B, P_X_W0, hprev, SX, w.A1[vi], w.A2[vi], w.dL[vi], w, dprev, ACC_STORE);
     // every consumer of node vi-1 is done: fold its projection gradients into dh_{vi-1}
     const int j = vi - 1;
     const float* dPg = w.dPg + (size_t)j * B * 2 * H; const float* dPm = w.dPm + (size_t)j * B * 2 * H;

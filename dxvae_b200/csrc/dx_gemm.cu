@@ -391,6 +391,9 @@ int get_precision() { return g_precision; }
 thread_local bool g_fwd_split = false;
 void set_fwd_split(bool on) { g_fwd_split = on; }
 bool get_fwd_split() { return g_fwd_split; }
+static thread_local int g_few_rows = 256;
+void set_few_rows(int rows) { g_few_rows = rows; }
+int get_few_rows() { return g_few_rows; }
 
 void gemm(dx_stream_t s, const GemmP& p) {
   if (p.M <= 0 || p.N <= 0 || p.K <= 0) return;
@@ -465,6 +468,9 @@ int get_precision() { return g_precision; }
 static thread_local bool g_fwd_split = false;
 void set_fwd_split(bool on) { g_fwd_split = on; }
 bool get_fwd_split() { return g_fwd_split; }
+static thread_local int g_few_rows = 256;
+void set_few_rows(int rows) { g_few_rows = rows; }
+int get_few_rows() { return g_few_rows; }
 
 void colsum_accum(dx_stream_t, int M, int N, const float* dy, int64_t lddy, float* db, const int* dy_idx) {
   for (int j = 0; j < N; ++j) {

@@ -12,6 +12,7 @@
 //   dgrad    dx = dy W     : a_kc=1, b_kc=0
 //   wgrad    dW += dy^T x  : a_kc=0, b_kc=0, accum=ACC_ATOMIC (split along the batch)
 #pragma once
+#include <cstdlib>
 #include "dx_rt.h"
 
 namespace dx {
@@ -45,12 +46,25 @@ struct PrecisionScope {
 // Training entry points allow FORWARD products of a few rows (M <= 256) to split their reduction over a thread-block
 // cluster (dx_tc_gemm.cu, launch_x3k): deterministic, but the summation order differs from the unsplit kernels, and an
 // inference result must not depend on how many patches share the batch — so it is scoped, per thread, like the precision.
+// The row limit of that path is scoped the same way: 256 by default, 1024 inside a training step of a SMALL batch
+// (B <= small_batch_max(): the launch-bound regime, where the batched parameter heads run 6B rows per product).  A large
+// batch keeps 256, so which kernel a compacted step of a few hundred rows takes does not change with this switch.
 void set_fwd_split(bool on);
 bool get_fwd_split();
+void set_few_rows(int rows);
+int get_few_rows();
+inline int small_batch_max() {
+  static const int v = [] { const char* e = getenv("DX_HEADS_BATCH_MAX"); return e ? atoi(e) : 4096; }();
+  return v;
+}
+inline int few_rows_for_batch(int64_t B) {
+  static const int forced = [] { const char* e = getenv("DX_X3K_ROWS"); return e ? atoi(e) : 0; }();   // (experiments)
+  return forced > 0 ? forced : (B <= small_batch_max() ? 1024 : 256);
+}
 struct FwdSplitScope {
-  bool prev;
-  explicit FwdSplitScope(bool on) : prev(get_fwd_split()) { set_fwd_split(on); }
-  ~FwdSplitScope() { set_fwd_split(prev); }
+  bool prev; int prev_rows;
+  explicit FwdSplitScope(bool on, int few_rows = 256) : prev(get_fwd_split()), prev_rows(get_few_rows()) { set_fwd_split(on); set_few_rows(few_rows); }
+  ~FwdSplitScope() { set_fwd_split(prev); set_few_rows(prev_rows); }
 };
 bool tc_gemm(dx_stream_t s, const GemmP& p, int* tile_n, bool x3 = false);   // dx_tc_gemm.cu; false = not eligible
 // PREC_3XTF32: the same kernels with the operand hi/lo split done inside the kernel (shared memory), three MMAs per

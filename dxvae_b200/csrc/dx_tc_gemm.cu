@@ -1529,7 +1529,7 @@ bool launch_x3(dx_stream_t s, const GemmP& g) {
 bool launch_x3k(dx_stream_t s, const GemmP& g) {
   using Cfg = X3Cfg<false, 128>;
   static const bool off = getenv("DX_X3_NO_KSPLIT") != nullptr;
-  if (off || g.accum == ACC_ATOMIC || g.M > 256) return false;
+  if (off || g.accum == ACC_ATOMIC || g.M > get_few_rows()) return false;   // (256 rows, 1024 inside a small-batch training step: dx_gemm.h)
   if (g.a_kc && g.b_kc && !get_fwd_split()) return false;
   if (!g.a_kc && g.b_kc) return false;
   const int nkb = (g.K + TBK - 1) / TBK;
