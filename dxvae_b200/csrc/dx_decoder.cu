@@ -26,6 +26,15 @@ namespace dx {
 // (+80 KB per patch), so it is used for batches up to DX_HEADS_BATCH_MAX graphs (default 4096: the small-batch regime,
 // where the step is bound by the number of dependent launches); larger batches keep one pass per node.
 static bool heads_batched(int64_t B, bool train) { return train && B <= small_batch_max(); }   // (dx_gemm.h)
+// Likewise the FIRST propagates of nodes 1..6 (model.py:234-240 / 320-337: no edges yet, H_in = 0): under teacher forcing
+// they depend on the true features of the node only, not on the nodes before it, so in the same small-batch regime the
+// input products, the combiner / looper cells, the self-loop head and their backward run once over 6B rows (the per-node
+// buffers are carved back to back) instead of once per node; only the second propagate (self-loop rows) and the loss of
+// the self-loop head stay in the node loop.  Compacted schedules only (the dense replay keeps the per-node form).
+static bool p1_batched(int64_t B, bool train, const int32_t* step_ptr) {
+  static const bool off = getenv("DX_NO_P1_BATCH") != nullptr;
+  return !off && heads_batched(B, train) && step_ptr != nullptr;
+}
 
 DecWs carve_dec(Arena& ar, int64_t B, bool train, const int32_t* step_ptr) {
   DecWs w{};
@@ -43,7 +52,7 @@ DecWs carve_dec(Arena& ar, int64_t B, bool train, const int32_t* step_ptr) {
   auto step_rows_exact = [&](int t) -> size_t { return compact ? (size_t)(step_ptr[t + 1] - step_ptr[t]) : b; };
   w.z = ar.take<float>(b * Z); w.Hinit = ar.take<float>(b * H); w.Hd = ar.take<float>(7 * b * H);
   w.Pg = ar.take<float>(6 * b * 2 * H); w.Pm = ar.take<float>(6 * b * 2 * H); w.Q = ar.take<float>(6 * b * 4 * H);
-  w.gh = ar.take<float>(b * G3); w.ghl0 = ar.take<float>(b * G3); w.Hrun = ar.take<float>(b * H);
+  w.gh = ar.take<float>(b * G3); w.ghl0 = ar.take<float>((p1_batched(B, train, step_ptr) ? 6 * b : b) * G3); w.Hrun = ar.take<float>(b * H);
   for (int k = 0; k < 3; ++k) w.WihP[k] = ar.take<float>((size_t)G3 * XP);
   if (train) {
     w.U = ar.take<float>(b * 4 * H); w.UC = ar.take<float>(b * 4 * H); w.dHiC = ar.take<float>(b * H);
@@ -80,6 +89,7 @@ DecWs carve_dec(Arena& ar, int64_t B, bool train, const int32_t* step_ptr) {
     w.dgx = ar.take<float>(b * 4 * H); w.dgh = w.dgx + H; w.dgxs = nullptr;   // one D4 buffer, two views (CellBwd)
     w.dE1 = ar.take<float>(b * 4 * H); { const size_t hb = heads_batched(B, train) ? 6 * b : b; w.dA1 = ar.take<float>(hb * 2 * H); w.dA2 = ar.take<float>(hb * 2 * H); }
     w.dES1 = ar.take<float>(b * 2 * H); w.dHinit = ar.take<float>(b * H); w.dz = ar.take<float>(b * Z);
+    if (p1_batched(B, train, step_ptr)) { w.dHc06 = ar.take<float>(6 * b * H); w.dir6 = ar.take<float>(6 * b * H); w.dES16 = ar.take<float>(6 * b * 2 * H); }
   } else {
     w.U = ar.take<float>(b * 4 * H); w.UC = ar.take<float>(b * 4 * H);
     w.act_rows = ar.take<int>(b); w.act_cnt = ar.take<int>(64); w.act_flag = ar.take<uint8_t>(b);
@@ -733,6 +743,24 @@ void decode_fwd_impl(dx_stream_t st, const Weights& W, int B, const float* z, co
   }
   node_projections(st, W, B, 0, w, train ? io.bt : nullptr);
 
+  const bool p1b = p1_batched(B, train, train ? io.bt->step_ptr : nullptr);
+  if (p1b) {
+    // first propagates of nodes 1..6 in one pass over 6B rows (see p1_batched): row m of every buffer below is graph
+    // m % B of node 1 + m / B
+    const int B6 = 6 * B;
+    const float* X1 = Xsrc + (size_t)B * XP;
+    RowMap rm6{B6, B, nullptr, B};
+    linear_fwd(st, B6, G3, Kx, X1, XP, Wc, ldx, nullptr, w.gxc[1], G3);
+    linear_fwd(st, B6, G3, Kx, X1, XP, Wl, ldx, nullptr, w.gxl[1], G3);
+    CellFwd c0{rm6, w.gxc[1], nullptr, W[P_CD_BIH], W[P_CD_BHH], nullptr, 0, w.Hc0[1], 0, w.g_c0[1], 0, S_ONE, adj};
+    cell_fwd(st, c0);
+    linear_fwd(st, B6, G3, H, w.Hc0[1], H, W[P_LD_WHH], H, nullptr, w.ghl0, G3);
+    CellFwd p1{rm6, w.gxl[1], w.ghl0, W[P_LD_BIH], W[P_LD_BHH], w.Hc0[1], 0, w.Hi_p1[1], 0, w.g_p1[1], 0, S_ZERO, adj};
+    p1.hout2 = w.Hi_p2[1]; p1.hout3 = w.Hd + (size_t)B * H; p1.hout23_local = 1;   // P2 state and current state start as P1's
+    cell_fwd(st, p1);
+    linear_fwd(st, B6, 2 * H, H, w.Hi_p1[1], H, W[P_ES_W0], H, W[P_ES_B0], w.ES1[1], 2 * H, ACT_RELU);
+    rowdot(st, B6, 2 * H, w.ES1[1], 2 * H, W[P_ES_W2], W[P_ES_B2], w.ls[1], LD_E);
+  }
   int t = 0;
   for (int vi = 1; vi < NN; ++vi) {
     const float* hprev_node = w.Hd + (size_t)(vi - 1) * B * H;
@@ -745,6 +773,10 @@ void decode_fwd_impl(dx_stream_t st, const Weights& W, int B, const float* z, co
       mlp3_fwd(st, W, B, P_X_W0, hprev_node, SX, w.A1[vi], w.A2[vi], w.L[vi]);
       loss_xi(st, B, vi, w.L[vi], Xi, io.bt->cls, io.lw, w.rowloss, w.dL[vi]);
     }
+    const float* const ghl0 = p1b ? w.ghl0 + (size_t)(vi - 1) * B * G3 : w.ghl0;
+    const bool compact = train && io.bt->step_ptr != nullptr;
+    float* const Hcur = w.Hd + (size_t)vi * B * H;   // compacted steps / greedy: the CURRENT state of node vi for every graph
+    if (!p1b) {
     linear_fwd(st, B, G3, Kx, Xi, XP, Wc, ldx, nullptr, w.gxc[vi], G3);
     linear_fwd(st, B, G3, Kx, Xi, XP, Wl, ldx, nullptr, w.gxl[vi], G3);
     // P1 (model.py:234/320): no edges yet -> H_in = 0, x_loop = 0
@@ -752,8 +784,6 @@ void decode_fwd_impl(dx_stream_t st, const Weights& W, int B, const float* z, co
                S_ONE, adj};
     cell_fwd(st, c0);
     linear_fwd(st, B, G3, H, w.Hc0[vi], H, W[P_LD_WHH], H, nullptr, w.ghl0, G3);
-    const bool compact = train && io.bt->step_ptr != nullptr;
-    float* const Hcur = w.Hd + (size_t)vi * B * H;   // compacted steps / greedy: the CURRENT state of node vi for every graph
     CellFwd p1{rm, w.gxl[vi], w.ghl0, W[P_LD_BIH], W[P_LD_BHH], w.Hc0[vi], 0, w.Hi_p1[vi], 0, train ? w.g_p1[vi] : nullptr,
                0, S_ZERO, adj};
     // compacted steps: P2 equals P1 except on the self-loop rows, so P1 also fills the P2 state and the current state
@@ -763,7 +793,11 @@ void decode_fwd_impl(dx_stream_t st, const Weights& W, int B, const float* z, co
     // self-loop head (model.py:236/331)
     linear_fwd(st, B, 2 * H, H, w.Hi_p1[vi], H, W[P_ES_W0], H, W[P_ES_B0], w.ES1[vi], 2 * H, ACT_RELU);
     rowdot(st, B, 2 * H, w.ES1[vi], 2 * H, W[P_ES_W2], W[P_ES_B2], w.ls[vi], LD_E);
-    if (train) loss_edge(st, B, vi, vi, w.ls[vi], 1, adj, io.lw, w.rowloss, w.dls[vi]);
+    }
+    // (batched first propagates address ls / dls as ONE [6B, LD_E] matrix from the node-1 buffer: 16-byte rows, so the
+    // arena's 256-byte alignment may pad between the per-node pointers)
+    if (train) loss_edge(st, B, vi, vi, p1b ? w.ls[1] + (size_t)(vi - 1) * B * LD_E : w.ls[vi], 1, adj, io.lw, w.rowloss,
+                         p1b ? w.dls[1] + (size_t)(vi - 1) * B * LD_E : w.dls[vi]);
     else decide_edges(st, B, vi, vi, w.ls[vi], 1, io.adj_out, io.margins);
     // P2 (model.py:240/337): same H_in = 0, x_loop = s*x
     if (compact) {
@@ -772,7 +806,7 @@ void decode_fwd_impl(dx_stream_t st, const Weights& W, int B, const float* z, co
       const int ts = NSTEP + vi - 1, ns = io.bt->step_ptr[ts + 1] - io.bt->step_ptr[ts];
       if (ns > 0) {
         RowMap rs{ns, B, io.bt->step_rows + io.bt->step_ptr[ts], vi * B};
-        CellFwd p2{rs, w.gxl[vi], w.ghl0, W[P_LD_BIH], W[P_LD_BHH], w.Hc0[vi], 0, w.UC, 0, w.g_p2[vi], 0, S_SELF, adj};
+        CellFwd p2{rs, w.gxl[vi], ghl0, W[P_LD_BIH], W[P_LD_BHH], w.Hc0[vi], 0, w.UC, 0, w.g_p2[vi], 0, S_SELF, adj};
         p2.gx_by_graph = 1; p2.gh_by_graph = 1; p2.hprev_by_graph = 1; p2.hout2 = w.Hi_p2[vi]; p2.hout3 = Hcur;
         cell_fwd(st, p2);
       }
@@ -972,6 +1006,9 @@ void decode_bwd_impl(dx_stream_t st, const Weights& W, const Weights& G, int B, 
     // state accumulates on top, below)
     mlp3_bwd(st, W, G, 6 * B, P_X_W0, w.Hd, SX, w.A1[1], w.A2[1], w.dL[1], w, w.dHd, ACC_STORE);
   }
+  // first propagates of nodes 1..6 as one 6B-row pass after the node loop (p1_batched; needs the in-place gate gradients)
+  const bool p1b = defer && p1_batched(B, true, bt.step_ptr);
+  if (p1b) zero_async(st, w.dHc06, sizeof(float) * 6 * bH);   // the second propagates (self-loop rows) add into it first
   int t_end = NSTEP;  // steps of node vi occupy [t_end - vi, t_end)
   for (int vi = NN - 1; vi >= 1; --vi) {
     const float* Xi = bt.Xn + (size_t)vi * B * XP;
@@ -1099,6 +1136,11 @@ void decode_bwd_impl(dx_stream_t st, const Weights& W, const Weights& G, int B, 
     } else {
       looper_bwd(st, W, G, B, vi, rm, dHi, w.g_p2[vi], w.Hc0[vi], S_SELF, adj, Xi, w, w.dHc0, false);
     }
+    if (p1b) {
+      // the rest of the node's first propagate runs for all six nodes at once after the loop: dHd[vi] keeps the gradient of
+      // Hi_p2 (nothing touches it again), the second propagate's combiner-state gradient waits in dHc06[vi]
+      if (ns > 0) scatter_rows(st, ns, H, rows_s, w.dHc, w.dHc06 + (size_t)(vi - 1) * bH, 1);
+    } else {
     // self-loop head consumed Hi_p1
     linear_wgrad(st, B, 1, 2 * H, w.dls[vi], LD_E, w.ES1[vi], 2 * H, G[P_ES_W2], 2 * H);
     colsum_accum(st, B, 1, w.dls[vi], LD_E, G[P_ES_B2]);
@@ -1115,6 +1157,7 @@ void decode_bwd_impl(dx_stream_t st, const Weights& W, const Weights& G, int B, 
     CellBwd c0{rm, w.dHc0, 0, w.g_c0[vi], 0, nullptr, 0, d0, nullptr, d0 + H, nullptr, S_ONE, adj};
     cell_bwd(st, c0, G[P_CD_BIH], G[P_CD_BHH]);
     if (!defer) linear_wgrad(st, B, G3, XP, w.dgx, 4 * H, Xi, XP, w.dWihP[0], XP);
+    }
     // parameter head of node vi read h_{vi-1}
     float* dprev = w.dHd + (size_t)(vi - 1) * bH;
     const float* hprev = w.Hd + (size_t)(vi - 1) * bH;
@@ -1143,11 +1186,12 @@ void decode_bwd_impl(dx_stream_t st, const Weights& W, const Weights& G, int B, 
       }
       proj_dgrad(st, B, dPg, W[P_G_W], dprev, half, ACC_ADD);
       proj_dgrad(st, B, dPm, W[P_M_W], dprev, half, ACC_ADD);
+      if (p1b) continue;                                          // (weight gradients: once over 6B rows after the loop)
       proj_wgrad(st, B, dPg, hprev, G[P_G_W], half);
       proj_wgrad(st, B, dPm, hprev, G[P_M_W], half);
     }
     linear_dgrad(st, B, 4 * H, H, dQ, 4 * H, W[P_E_W0] + H, 2 * H, dprev, H, ACC_ADD);
-    linear_wgrad(st, B, 4 * H, H, dQ, 4 * H, hprev, H, G[P_E_W0] + H, 2 * H);
+    if (!p1b) linear_wgrad(st, B, 4 * H, H, dQ, 4 * H, hprev, H, G[P_E_W0] + H, 2 * H);
     if (!compact) colsum_accum(st, B, 4 * H, dQ, 4 * H, G[P_E_B0]);   // (compacted steps: the fused forward head summed it)
     t_end = t0;
   }
@@ -1167,6 +1211,32 @@ void decode_bwd_impl(dx_stream_t st, const Weights& W, const Weights& G, int B, 
   linear_wgrad(st, B, H, Z, w.dHinit, H, z, Z, G[P_ZH_W], Z);
   colsum_accum(st, B, H, w.dHinit, H, G[P_ZH_B]);
   linear_dgrad(st, B, H, Z, w.dHinit, H, W[P_ZH_W], Z, w.dz, Z, ACC_STORE);
+  if (p1b) {
+    // self-loop heads, looper and combiner of the first propagates of nodes 1..6: one pass over 6B rows (rows [B, 7B) of
+    // dHd hold the gradients of Hi_p2; every per-node buffer below is carved back to back)
+    const int B6 = 6 * B;
+    float* dH6 = w.dHd + bH;
+    RowMap rm6{B6, B, nullptr, B};
+    linear_wgrad(st, B6, 1, 2 * H, w.dls[1], LD_E, w.ES1[1], 2 * H, G[P_ES_W2], 2 * H);
+    colsum_accum(st, B6, 1, w.dls[1], LD_E, G[P_ES_B2]);
+    relu_head_bwd(st, B6, 2 * H, 1, w.ES1[1], w.dls[1], LD_E, W[P_ES_W2], w.dES16, nullptr);
+    linear_wgrad(st, B6, 2 * H, H, w.dES16, 2 * H, w.Hi_p1[1], H, G[P_ES_W0], H);
+    colsum_accum(st, B6, 2 * H, w.dES16, 2 * H, G[P_ES_B0]);
+    linear_dgrad(st, B6, 2 * H, H, w.dES16, 2 * H, W[P_ES_W0], H, dH6, H, ACC_ADD);
+    // looper (x_loop = 0): gate gradients in place over g_p1, dHc0 += dHi * z + dgh W_hh
+    CellBwd cb{rm6, dH6, 0, w.g_p1[1], 0, w.Hc0[1], 0, w.g_p1[1], nullptr, w.g_p1[1] + H, w.dir6, S_ZERO, adj};
+    cell_bwd(st, cb, G[P_LD_BIH], G[P_LD_BHH]);
+    add_inplace(st, (int64_t)B6 * H / 4, w.dHc06, w.dir6);
+    linear_dgrad(st, B6, G3, H, w.g_p1[1] + H, 4 * H, W[P_LD_WHH], H, w.dHc06, H, ACC_ADD);
+    // combiner with H_in = 0: only input weights / biases receive gradient
+    CellBwd c0{rm6, w.dHc06, 0, w.g_c0[1], 0, nullptr, 0, w.g_c0[1], nullptr, w.g_c0[1] + H, nullptr, S_ONE, adj};
+    cell_bwd(st, c0, G[P_CD_BIH], G[P_CD_BHH]);
+    // weight gradients of what reads the finished node states h_0..h_5 (the "out" halves of the gate / mapper projections
+    // and the Hj half of the edge head's first layer): dPg / dPm / dQ and Hd are node-major, one product each over 6B rows
+    proj_wgrad(st, B6, w.dPg, w.Hd, G[P_G_W], HALF_OUT);
+    proj_wgrad(st, B6, w.dPm, w.Hd, G[P_M_W], HALF_OUT);
+    linear_wgrad(st, B6, 4 * H, H, w.dQ, 4 * H, w.Hd, H, G[P_E_W0] + H, 2 * H);
+  }
   if (defer) {
     // first propagates of nodes 1..6 (g_p1 / g_c0 / Hc0 are per-node buffers carved back to back; Xn is node-major)
     linear_wgrad(st, 6 * B, G3, H, w.g_p1[1] + H, 4 * H, w.Hc0[1], H, G[P_LD_WHH], H);

@@ -41,6 +41,7 @@ struct CellFwd {
   float* hout3 = nullptr;     // optional third copy, likewise
   int gh_by_graph = 0;        // 1: gh is [B,1536] indexed by the row's graph b
   int hprev_by_graph = 0;     // 1: hprev is [B,512] indexed by the row's graph b
+  int hout23_local = 0;       // 1: hout2 / hout3 are [M,512] indexed by m like hout (all nodes' first propagates in one launch)
 };
 
 inline void cell_fwd(dx_stream_t st, const CellFwd& a) {
@@ -75,8 +76,9 @@ inline void cell_fwd(dx_stream_t st, const CellFwd& a) {
     DX_CELL(x) DX_CELL(y) DX_CELL(z) DX_CELL(w)
 #undef DX_CELL
     st4f(a.hout + (int64_t)(a.hout_global ? r : m) * H + n, O);
-    if (a.hout2) st4f(a.hout2 + (int64_t)(r % a.rm.B) * H + n, O);
-    if (a.hout3) st4f(a.hout3 + (int64_t)(r % a.rm.B) * H + n, O);
+    const int64_t o23 = a.hout23_local ? m : r % a.rm.B;
+    if (a.hout2) st4f(a.hout2 + o23 * H + n, O);
+    if (a.hout3) st4f(a.hout3 + o23 * H + n, O);
     if (a.gates) {
       float* g = a.gates + (int64_t)(a.gates_global ? r : m) * (4 * H) + n;
       st4f(g, R); st4f(g + H, Zg); st4f(g + 2 * H, Ng); st4f(g + 3 * H, NH);

@@ -8,7 +8,7 @@ from dxvae_b200.synth import random_voices
 from dxvae_b200.train import Trainer
 
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 128
-pool = voices_to_batch(random_voices(1024, seed=3))
+pool = voices_to_batch(random_voices(max(1024, B), seed=3))
 for prec in (sys.argv[2:] or ["3xtf32", "tf32", "fp32"]):
     for gmax in (0, 1024):
         torch.manual_seed(0)
