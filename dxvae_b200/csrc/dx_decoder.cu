@@ -89,7 +89,9 @@ DecWs carve_dec(Arena& ar, int64_t B, bool train, const int32_t* step_ptr) {
     w.dgx = ar.take<float>(b * 4 * H); w.dgh = w.dgx + H; w.dgxs = nullptr;   // one D4 buffer, two views (CellBwd)
     w.dE1 = ar.take<float>(b * 4 * H); { const size_t hb = heads_batched(B, train) ? 6 * b : b; w.dA1 = ar.take<float>(hb * 2 * H); w.dA2 = ar.take<float>(hb * 2 * H); }
     w.dES1 = ar.take<float>(b * 2 * H); w.dHinit = ar.take<float>(b * H); w.dz = ar.take<float>(b * Z);
-    if (p1_batched(B, train, step_ptr)) { w.dHc06 = ar.take<float>(6 * b * H); w.dir6 = ar.take<float>(6 * b * H); w.dES16 = ar.take<float>(6 * b * 2 * H); }
+    if (p1_batched(B, train, step_ptr)) { w.dHc06 = ar.take<float>(6 * b * H); w.dir6 = ar.take<float>(6 * b * H); w.dES16 = ar.take<float>(6 * b * 2 * H);
+      const size_t na = (size_t)(step_ptr[NSTEP] - step_ptr[0]); w.UCS = ar.take<float>((na ? na : 1) * 4 * H);
+      w.dU6 = ar.take<float>(6 * b * 4 * H); w.U6 = ar.take<float>(6 * b * 4 * H); }
   } else {
     w.U = ar.take<float>(b * 4 * H); w.UC = ar.take<float>(b * 4 * H);
     w.act_rows = ar.take<int>(b); w.act_cnt = ar.take<int>(64); w.act_flag = ar.take<uint8_t>(b);
@@ -760,6 +762,18 @@ void decode_fwd_impl(dx_stream_t st, const Weights& W, int B, const float* z, co
     cell_fwd(st, p1);
     linear_fwd(st, B6, 2 * H, H, w.Hi_p1[1], H, W[P_ES_W0], H, W[P_ES_B0], w.ES1[1], 2 * H, ACT_RELU);
     rowdot(st, B6, 2 * H, w.ES1[1], 2 * H, W[P_ES_W2], W[P_ES_B2], w.ls[1], LD_E);
+    // second propagates (x_loop = s*x): the self-loop rows of each node (schedule list NSTEP+vi-1), gates stored compactly
+    for (int vi = 1; vi < NN; ++vi) {
+      const int ts = NSTEP + vi - 1, ns = io.bt->step_ptr[ts + 1] - io.bt->step_ptr[ts];
+      if (ns <= 0) continue;
+      RowMap rs{ns, B, io.bt->step_rows + io.bt->step_ptr[ts], vi * B};
+      CellFwd p2{rs, w.gxl[vi], w.ghl0 + (size_t)(vi - 1) * B * G3, W[P_LD_BIH], W[P_LD_BHH], w.Hc0[vi], 0, w.UC, 0, w.g_p2[vi], 0,
+                 S_SELF, adj};
+      p2.gx_by_graph = 1; p2.gh_by_graph = 1; p2.hprev_by_graph = 1; p2.hout2 = w.Hi_p2[vi]; p2.hout3 = w.Hd + (size_t)vi * B * H;
+      cell_fwd(st, p2);
+    }
+    // U = Hi_p2 W_e0[:, :512]^T of every node: the running edge-head product each node's steps start from
+    linear_fwd(st, B6, 4 * H, H, w.Hi_p2[1], H, W[P_E_W0], 2 * H, nullptr, w.U6, 4 * H);
   }
   int t = 0;
   for (int vi = 1; vi < NN; ++vi) {
@@ -800,7 +814,9 @@ void decode_fwd_impl(dx_stream_t st, const Weights& W, int B, const float* z, co
                          p1b ? w.dls[1] + (size_t)(vi - 1) * B * LD_E : w.dls[vi]);
     else decide_edges(st, B, vi, vi, w.ls[vi], 1, io.adj_out, io.margins);
     // P2 (model.py:240/337): same H_in = 0, x_loop = s*x
-    if (compact) {
+    if (p1b) {
+      // (done for all nodes ahead of the loop)
+    } else if (compact) {
       // x_loop = s*x: P2 repeats P1 exactly on graphs without a self-loop on vi, so it is computed on the
       // self-loop rows only (schedule list NSTEP+vi-1); their gates are stored compactly.
       const int ts = NSTEP + vi - 1, ns = io.bt->step_ptr[ts + 1] - io.bt->step_ptr[ts];
@@ -822,10 +838,11 @@ void decode_fwd_impl(dx_stream_t st, const Weights& W, int B, const float* z, co
       // graphs where the step adds an edge.  Hd[vi] holds the CURRENT state of node vi for every
       // graph and U = Hd[vi] W_e0[:, :512]^T is kept consistent with it, so the edge head of a step is
       // element-wise for all graphs and the GRU / projection products run on the active rows only.
-      linear_fwd(st, B, 4 * H, H, w.Hi_p2[vi], H, W[P_E_W0], 2 * H, nullptr, w.U, 4 * H);
+      float* const Ucur = p1b ? w.U6 + (size_t)(vi - 1) * B * 4 * H : w.U;
+      if (!p1b) linear_fwd(st, B, 4 * H, H, w.Hi_p2[vi], H, W[P_E_W0], 2 * H, nullptr, Ucur, 4 * H);
       for (int vj = vi - 1; vj >= 0; --vj, ++t) {
         // fused edge head: the E1 buffer of the step only stores the relu bit-mask (256 B/row)
-        EdgeHeadP eh{B, vi, vj, w.U, w.Q + (size_t)vj * B * 4 * H, W[P_E_W2], W[P_E_B2], adj, io.lw.inv_batch, w.l2[t], w.dl2[t],
+        EdgeHeadP eh{B, vi, vj, Ucur, w.Q + (size_t)vj * B * 4 * H, W[P_E_W2], W[P_E_B2], adj, io.lw.inv_batch, w.l2[t], w.dl2[t],
                      w.rowloss, reinterpret_cast<uint8_t*>(w.E1[t]), io.dW2, io.db2};
         eh.db0 = io.db0;
         edge_head_fwd(st, eh);
@@ -846,7 +863,7 @@ void decode_fwd_impl(dx_stream_t st, const Weights& W, int B, const float* z, co
         cell_fwd(st, cl);
         if (vj > 0) {                                          // (no head reads U after the node's last step)
           linear_fwd(st, n, 4 * H, H, w.Hi[t], H, W[P_E_W0], 2 * H, nullptr, w.UC, 4 * H);
-          scatter_rows(st, n, 4 * H, rows, w.UC, w.U, 0);
+          scatter_rows(st, n, 4 * H, rows, w.UC, Ucur, 0);
         }
       }
       if (vi < NN - 1) node_projections(st, W, B, vi, w, io.bt);
@@ -944,7 +961,7 @@ static void mlp3_bwd(dx_stream_t st, const Weights& W, const Weights& G, int B, 
 static void looper_bwd(dx_stream_t st, const Weights& W, const Weights& G, int B, int vi, const RowMap& rm,   // rm.M rows
                        const float* dHi, const float* gates, const float* Hc, int smode, const uint64_t* adj,
                        const float* Xi, const DecWs& w, float* dHc, bool dHc_accum, float* x_stash = nullptr,
-                       bool defer = false) {                        // defer without x_stash: the S_ZERO propagate (no x term)
+                       bool defer = false, bool x_stashed = false) {   // x_stashed: stash_step_x already filled x_stash                        // defer without x_stash: the S_ZERO propagate (no x term)
   // dHc (+)= dHi*z + dgh W_hh            (rm.M rows: all B graphs, or the active rows of a compacted step)
   const int M = rm.M;
   float* direct = dHc_accum ? w.dHin : dHc;  // dHin is free scratch at this point
@@ -959,13 +976,36 @@ static void looper_bwd(dx_stream_t st, const Weights& W, const Weights& G, int B
   // weight_ih gradient: x masked by the self-loop flag (XL), gathered to the active rows when compacted
   if (smode != S_ZERO) {
     const float* xl = w.XL + (size_t)vi * B * XP;
-    if (x_stash) { gather_rows(st, M, XP, rm.rows, const_cast<float*>(xl), x_stash, 0); }
+    if (x_stash) { if (!x_stashed) gather_rows(st, M, XP, rm.rows, const_cast<float*>(xl), x_stash, 0); }
     else {
       if (rm.rows) { gather_rows(st, M, XP, rm.rows, const_cast<float*>(xl), w.xc, 0); xl = w.xc; }
       linear_wgrad(st, M, G3, XP, d4, 4 * H, xl, XP, w.dWihP[1], XP);
     }
   }
   (void)Xi; (void)G;
+}
+
+// The x rows of every active (graph, step) pair of the compacted schedule, plain (xiS: combiner input) and masked by
+// the self-loop flag (xlS: looper input), concatenated in step order — the operands of the deferred weight_ih gradients.
+// They depend on the schedule and the true features only, so one launch fills both stashes for all 21 steps (it replaces
+// two row gathers per step).  Step t belongs to node vi with vi(vi-1)/2 <= t < vi(vi+1)/2 (decode_fwd_impl's step order).
+struct StepPtrV { int p[NSTEP + 1]; };
+static void stash_step_x(dx_stream_t st, int B, const int32_t* step_ptr, const int* step_rows, const float* Xn,
+                         const float* XL, float* xiS, float* xlS) {
+  StepPtrV sp;
+  for (int t = 0; t <= NSTEP; ++t) sp.p[t] = step_ptr[t];
+  const int64_t nact = sp.p[NSTEP] - sp.p[0];
+  if (nact <= 0) return;
+  foreach (st, nact * (XP / 4), [=] DX_HD(int64_t idx) {
+    const int pos = (int)(idx / (XP / 4)) + sp.p[0], c = (int)(idx % (XP / 4)) * 4;
+    int t = 0;
+    while (t + 1 < NSTEP && pos >= sp.p[t + 1]) ++t;
+    int vi = 1;
+    while ((vi + 1) * vi / 2 <= t) ++vi;
+    const int64_t src = ((int64_t)vi * B + step_rows[pos]) * XP + c;
+    const int64_t dst = (int64_t)(pos - sp.p[0]) * XP + c;
+    st4f(xiS + dst, ld4f(Xn + src)); st4f(xlS + dst, ld4f(XL + src));
+  });
 }
 
 void decode_bwd_impl(dx_stream_t st, const Weights& W, const Weights& G, int B, const float* z, const DecWs& w,
@@ -1009,6 +1049,16 @@ void decode_bwd_impl(dx_stream_t st, const Weights& W, const Weights& G, int B, 
   // first propagates of nodes 1..6 as one 6B-row pass after the node loop (p1_batched; needs the in-place gate gradients)
   const bool p1b = defer && p1_batched(B, true, bt.step_ptr);
   if (p1b) zero_async(st, w.dHc06, sizeof(float) * 6 * bH);   // the second propagates (self-loop rows) add into it first
+  static const bool one_stash = getenv("DX_NO_XSTASH_ONE") == nullptr;
+  const bool xst = defer && bt.step_ptr && one_stash;
+  if (xst) stash_step_x(st, B, bt.step_ptr, bt.step_rows, bt.Xn, w.XL, w.xiS, w.xlS);
+  // small batches: the head gradients dU of the steps are kept, concatenated in step order like the states Hi, and the
+  // first-layer weight gradient of the edge head (its Hi half) is ONE product over all active rows after the loop; the
+  // last step of a node feeds no later head: its rows stay zero
+  if (p1b) {
+    const size_t na = (size_t)(bt.step_ptr[NSTEP] - bt.step_ptr[0]);
+    if (na) zero_async(st, w.UCS, sizeof(float) * na * 4 * H);
+  }
   int t_end = NSTEP;  // steps of node vi occupy [t_end - vi, t_end)
   for (int vi = NN - 1; vi >= 1; --vi) {
     const float* Xi = bt.Xn + (size_t)vi * B * XP;
@@ -1037,20 +1087,21 @@ void decode_bwd_impl(dx_stream_t st, const Weights& W, const Weights& G, int B, 
         RowMap rc{n, B, rows, vi * B};
         gather_rows(st, n, H, rows, dHi, w.dHiC, 1);
         if (vj > 0) {                                        // (the last step's state feeds no later head)
-          HeadSumP hs{n, rows, adj, vi, 0, 1, {}, {}, {}, W[P_E_W2], w.UC};
+          float* const dUs = p1b ? w.UCS + (size_t)(bt.step_ptr[t] - bt.step_ptr[0]) * 4 * H : w.UC;
+          HeadSumP hs{n, rows, adj, vi, 0, 1, {}, {}, {}, W[P_E_W2], dUs};
           head_list(hs, vj - 1);
           head_sum(st, hs);
-          linear_dgrad(st, n, 4 * H, H, w.UC, 4 * H, W[P_E_W0], 2 * H, w.dHiC, H, ACC_ADD);
-          linear_wgrad(st, n, 4 * H, H, w.UC, 4 * H, w.Hi[t], H, G[P_E_W0], 2 * H);
+          linear_dgrad(st, n, 4 * H, H, dUs, 4 * H, W[P_E_W0], 2 * H, w.dHiC, H, ACC_ADD);
+          if (!p1b) linear_wgrad(st, n, 4 * H, H, dUs, 4 * H, w.Hi[t], H, G[P_E_W0], 2 * H);
         }
         const size_t soff = (size_t)(bt.step_ptr[t] - bt.step_ptr[0]) * XP;   // this step's rows in the concatenated x stashes
         if (defer) {
-        looper_bwd(st, W, G, B, vi, rc, w.dHiC, w.g_l[t], w.Hc[t], S_SELF, adj, Xi, w, w.dHc, false, w.xlS + soff);
+        looper_bwd(st, W, G, B, vi, rc, w.dHiC, w.g_l[t], w.Hc[t], S_SELF, adj, Xi, w, w.dHc, false, w.xlS + soff, false, xst);
         // combiner: gate gradients in place over g_c[t]; its two weight gradients are deferred like the looper's
         CellBwd cc{rc, w.dHc, 0, w.g_c[t], 0, w.Hin[t], 0, w.g_c[t], nullptr, w.g_c[t] + H, w.dHin, S_ONE, adj};
         cell_bwd(st, cc, G[P_CD_BIH], G[P_CD_BHH]);
         linear_dgrad(st, n, G3, H, w.g_c[t] + H, 4 * H, W[P_CD_WHH], H, w.dHin, H, ACC_ADD);
-        gather_rows(st, n, XP, rows, const_cast<float*>(Xi), w.xiS + soff, 0);
+        if (!xst) gather_rows(st, n, XP, rows, const_cast<float*>(Xi), w.xiS + soff, 0);
         } else {
         looper_bwd(st, W, G, B, vi, rc, w.dHiC, w.g_l[t], w.Hc[t], S_SELF, adj, Xi, w, w.dHc, false);
         CellBwd cc{rc, w.dHc, 0, w.g_c[t], 0, w.Hin[t], 0, w.dgx, nullptr, w.dgh, w.dHin, S_ONE, adj};
@@ -1081,12 +1132,14 @@ void decode_bwd_impl(dx_stream_t st, const Weights& W, const Weights& G, int B, 
         msg_bwd(st, mb);
       }
       // U = Hi_p2 W^T (the state every graph had before its first edge): read by the heads up to the first active step
-      float* dU = w.dE1;
+      float* dU = p1b ? w.dU6 + (size_t)(vi - 1) * B * 4 * H : w.dE1;
       HeadSumP hs{B, nullptr, adj, vi, 0, 1, {}, {}, {}, W[P_E_W2], dU};
       head_list(hs, vi - 1);
       head_sum(st, hs);
+      if (!p1b) {                                                // (small batches: both products once over 6B rows after the loop)
       linear_wgrad(st, B, 4 * H, H, dU, 4 * H, w.Hi_p2[vi], H, G[P_E_W0], 2 * H);
       linear_dgrad(st, B, 4 * H, H, dU, 4 * H, W[P_E_W0], 2 * H, dHi, H, ACC_ADD);
+      }
       // dQ of node j = vi-1 (consumed below): heads (vi', j) of every later node vi' (all of them are done)
       {
         const int j = vi - 1;
@@ -1122,7 +1175,10 @@ void decode_bwd_impl(dx_stream_t st, const Weights& W, const Weights& G, int B, 
     }
     // dHi now holds the gradient of Hi_p2.  P2 and P1 share Hc0.
     int ns = 0; const int* rows_s = nullptr;
-    if (compact) {
+    if (p1b) {
+      // small batches: dHd[vi] is left as it is (the gradient of Hi_p2 but for the product U = Hi_p2 W^T, added for all six
+      // nodes at once after the loop); the second and first propagates of all nodes follow there
+    } else if (compact) {
       // P2 ran on the self-loop rows only: their gradient goes through P2's looper (compact), every other
       // row's gradient passes straight to Hi_p1 (Hi_p2 == Hi_p1 there) and joins the self-loop head's.
       const int ts = NSTEP + vi - 1;
@@ -1136,11 +1192,7 @@ void decode_bwd_impl(dx_stream_t st, const Weights& W, const Weights& G, int B, 
     } else {
       looper_bwd(st, W, G, B, vi, rm, dHi, w.g_p2[vi], w.Hc0[vi], S_SELF, adj, Xi, w, w.dHc0, false);
     }
-    if (p1b) {
-      // the rest of the node's first propagate runs for all six nodes at once after the loop: dHd[vi] keeps the gradient of
-      // Hi_p2 (nothing touches it again), the second propagate's combiner-state gradient waits in dHc06[vi]
-      if (ns > 0) scatter_rows(st, ns, H, rows_s, w.dHc, w.dHc06 + (size_t)(vi - 1) * bH, 1);
-    } else {
+    if (!p1b) {
     // self-loop head consumed Hi_p1
     linear_wgrad(st, B, 1, 2 * H, w.dls[vi], LD_E, w.ES1[vi], 2 * H, G[P_ES_W2], 2 * H);
     colsum_accum(st, B, 1, w.dls[vi], LD_E, G[P_ES_B2]);
@@ -1217,6 +1269,21 @@ void decode_bwd_impl(dx_stream_t st, const Weights& W, const Weights& G, int B, 
     const int B6 = 6 * B;
     float* dH6 = w.dHd + bH;
     RowMap rm6{B6, B, nullptr, B};
+    // U = Hi_p2 W^T of every node (the state each graph had before its first edge): head gradients kept in dU6
+    linear_wgrad(st, B6, 4 * H, H, w.dU6, 4 * H, w.Hi_p2[1], H, G[P_E_W0], 2 * H);
+    linear_dgrad(st, B6, 4 * H, H, w.dU6, 4 * H, W[P_E_W0], 2 * H, dH6, H, ACC_ADD);
+    // second propagates (self-loop rows of each node, compact): their gradient goes through P2's looper, every other row's
+    // passes straight to Hi_p1 (Hi_p2 == Hi_p1 there); the combiner-state gradient waits in dHc06[vi]
+    for (int vi = NN - 1; vi >= 1; --vi) {
+      const int ts = NSTEP + vi - 1, ns = bt.step_ptr[ts + 1] - bt.step_ptr[ts];
+      if (ns <= 0) continue;
+      const int* rows_s = bt.step_rows + bt.step_ptr[ts];
+      RowMap rs{ns, B, rows_s, vi * B};
+      gather_rows(st, ns, H, rows_s, w.dHd + (size_t)vi * bH, w.dHiC, 1);
+      gather_rows(st, ns, H, rows_s, w.Hc0[vi], w.Hrun, 0);            // (Hrun is free scratch in the backward pass)
+      looper_bwd(st, W, G, B, vi, rs, w.dHiC, w.g_p2[vi], w.Hrun, S_SELF, adj, bt.Xn + (size_t)vi * B * XP, w, w.dHc, false);
+      scatter_rows(st, ns, H, rows_s, w.dHc, w.dHc06 + (size_t)(vi - 1) * bH, 1);
+    }
     linear_wgrad(st, B6, 1, 2 * H, w.dls[1], LD_E, w.ES1[1], 2 * H, G[P_ES_W2], 2 * H);
     colsum_accum(st, B6, 1, w.dls[1], LD_E, G[P_ES_B2]);
     relu_head_bwd(st, B6, 2 * H, 1, w.ES1[1], w.dls[1], LD_E, W[P_ES_W2], w.dES16, nullptr);
@@ -1251,6 +1318,7 @@ void decode_bwd_impl(dx_stream_t st, const Weights& W, const Weights& G, int B, 
       linear_wgrad(st, nact, G3, XP, w.g_l[0], 4 * H, w.xlS, XP, w.dWihP[1], XP);
       linear_wgrad(st, nact, G3, H, w.g_c[0] + H, 4 * H, w.Hin[0], H, G[P_CD_WHH], H);
       linear_wgrad(st, nact, G3, XP, w.g_c[0], 4 * H, w.xiS, XP, w.dWihP[0], XP);
+      if (p1b) linear_wgrad(st, nact, 4 * H, H, w.UCS, 4 * H, w.Hi[0], H, G[P_E_W0], 2 * H);
     }
   }
   unpad_add_wih(st, w.dWihP[0], SX, G[P_CD_WIH]);

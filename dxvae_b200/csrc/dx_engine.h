@@ -66,7 +66,7 @@ struct DecWs {
   // backward temporaries
   float *dHd, *dPg, *dPm, *dQ, *dgb, *dHi, *dHc, *dHin, *dHrun, *dHc0, *dgx, *dgxs, *dgh, *dE1, *dA1, *dA2, *dES1,
       *dHinit, *dz;
-  float *dHc06, *dir6, *dES16;   // small batches: first propagates of nodes 1..6 as one 6B-row pass (decode_bwd_impl)
+  float *dHc06, *dir6, *dES16, *UCS, *dU6, *U6;   // small batches: first propagates of nodes 1..6 as one 6B-row pass (decode_bwd_impl)
 };
 
 struct DecIO {
