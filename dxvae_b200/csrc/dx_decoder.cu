@@ -23,7 +23,7 @@ namespace dx {
 // Teacher forcing never feeds a parameter head's output back (x_vi is the true X), so the heads of nodes 1..6 can run as
 // ONE 3-layer pass over the 6B finished node states after the node loop, and their backward as one pass before it
 // (18 + 54 product launches become 3 + 9).  It needs the two relu-gradient scratch matrices at 6B rows instead of B
-// (+80 KB per patch), so it is used for batches up to DX_HEADS_BATCH_MAX graphs (default 4096: the small-batch regime,
+// (+40 KB per patch), so it is used for batches up to DX_HEADS_BATCH_MAX graphs (default 4096: the small-batch regime,
 // where the step is bound by the number of dependent launches); larger batches keep one pass per node.
 static bool heads_batched(int64_t B, bool train) { return train && B <= small_batch_max(); }   // (dx_gemm.h)
 // Likewise the FIRST propagates of nodes 1..6 (model.py:234-240 / 320-337: no edges yet, H_in = 0): under teacher forcing

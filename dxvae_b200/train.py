@@ -8,13 +8,14 @@ every rank hold the single-GPU gradient; the AdamW update (torch.optim.AdamW def
 over the flat blob) is replicated.  No other collective is on the path.
 
 Small batches (the reference's own regime: size_batch 32..128, BASELINE config 2) are bound by the
-latency of ~900 dependent kernels; the native side answers with programmatic dependent launch and
-cluster split-K products (DESIGN.md §5 "Small batches": 5.75 ms per batch-128 step).  Optionally
+latency of several hundred dependent kernels; the native side answers with programmatic dependent launch,
+cluster split-K products and one pass over all six decoder nodes for the work that does not depend on the
+nodes in front (DESIGN.md §5 "Small batches": 4.49 ms per batch-128 step).  Optionally
 (graph_max_batch > 0) the step is captured ONCE into a CUDA graph over static buffers and replayed:
 the schedule is made batch-independent (encoder levels = the reference's node order 6..1, every
 teacher-forcing step on every graph — both are valid schedules of the same function), so one graph
 serves every batch of that size.  Measured on B200 the replay is SLOWER than the eager step
-(8.1 vs 6.5 ms at batch 128: the dense schedule does more work and the graph serialises what the
+(7.3 vs 4.5 ms at batch 128: the dense schedule does more work and the graph serialises what the
 stream overlaps), so it stays off by default."""
 import numpy as np
 import torch
