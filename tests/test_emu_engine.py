@@ -132,3 +132,21 @@ def test_greedy_decode_matches_oracle(setup):
     assert np.array_equal(util.adj_from_masks(adj)[ok], Ao.numpy()[ok])
     assert np.array_equal(Pd.astype(np.int32)[ok], Po.numpy().astype(np.int32)[ok])
     assert np.abs(Xd - Xo.numpy())[ok].max() <= 1e-6
+
+
+def test_per_node_decoder_schedule_matches_oracle_too():
+    """Training steps of <= 4096 graphs take the small-batch schedule of the teacher-forced decoder (node-independent work
+    once over 6B rows: csrc/dx_decoder.cu heads_batched / p1_batched), so the tests above pin THAT schedule to the oracle.
+    Larger batches — the benchmark's — take the per-node schedule; the switch is read once per process, so the same
+    loss / gradient comparisons are repeated in a child process with DX_HEADS_BATCH_MAX=0."""
+    import os
+    import subprocess
+    import sys
+    if os.environ.get("DX_EMU_NESTED"):
+        pytest.skip("already the child run")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, DX_HEADS_BATCH_MAX="0", DX_EMU_NESTED="1")
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(root, "tests", "test_emu_engine.py"), "-x", "-q", "-k", "elbo",
+                        "-p", "no:cacheprovider"], capture_output=True, text=True, timeout=900, env=env, cwd=root)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
+    assert "5 passed" in r.stdout, r.stdout[-500:]
