@@ -38,7 +38,18 @@ size_t workspace_bytes(int op, int64_t B, int n_levels, const int32_t* level_ptr
     case DXVAE_OP_LOSS: carve_dec(ar, B, true, step_ptr); break;
     default: return 0;
   }
-  return ar.off + 256;
+  size_t need = ar.off;
+  if ((op == DXVAE_OP_TRAIN || op == DXVAE_OP_LOSS) && step_ptr == nullptr && B > 0 && B <= small_batch_max()) {
+    // Worst case over schedules: the small-batch schedule of the decoder (dx_decoder.cu, p1_batched) keeps extra per-node /
+    // per-step buffers, and only when it runs on a compacted schedule — so the bound is the larger of the dense replay
+    // (above) and a compacted schedule with every graph in every list (carve_dec grows with every list's row count).
+    int32_t dense[NLIST + 1];
+    for (int i = 0; i <= NLIST; ++i) dense[i] = (int32_t)(i * B);
+    Arena ad(nullptr, (size_t)-1);
+    if (op == DXVAE_OP_TRAIN) carve_train(ad, B, n_levels, level_ptr, dense); else carve_dec(ad, B, true, dense);
+    if (ad.off > need) need = ad.off;
+  }
+  return need + 256;
 }
 
 // model.py:369-372 forward (= encode + loss) and model.py:385 backward, one call.

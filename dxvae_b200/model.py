@@ -129,7 +129,7 @@ class DXVAE(nn.Module):
             if not fresh and (ws is None or ws.numel() < n):
                 # the need follows the batch's topologies: leave 6 % of headroom (never above the worst case) so that
                 # the next batches of the same size do not reallocate tens of GB
-                n = min(int(L.dxvae_workspace_bytes(op, B)), n + n // 16)
+                n = max(n, min(int(L.dxvae_workspace_bytes(op, B)), n + n // 16))
         else:
             n = int(L.dxvae_workspace_bytes(op, B))
         if fresh:

@@ -150,3 +150,20 @@ def test_per_node_decoder_schedule_matches_oracle_too():
                         "-p", "no:cacheprovider"], capture_output=True, text=True, timeout=900, env=env, cwd=root)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
     assert "5 passed" in r.stdout, r.stdout[-500:]
+
+
+@pytest.mark.parametrize("B,density", [(8, 1.0), (128, 1.0), (128, 0.3), (512, 1.0)])
+def test_worst_case_workspace_bounds_every_schedule(setup, B, density):
+    """include/dxvae_b200.h: dxvae_workspace_bytes_sched is never more than dxvae_workspace_bytes — also for the small-batch
+    schedule of the decoder, whose extra per-node / per-step buffers only exist on compacted schedules (a batch with
+    every graph active at every step is the worst case there)."""
+    from dxvae_b200 import _abi
+    from tests.emu.emu import ptr
+    emu = setup[-1]
+    L = emu.lib
+    bt = emu.batch(None, None, util.random_edge_lists(B, density, 3))
+    sp = np.zeros(34, np.int32); sr = np.zeros(33 * B, np.int32)
+    _abi.check(L, L.dxvae_batch_steps_host(B, ptr(bt["adj"]), ptr(sp), ptr(sr)), "steps")
+    for op in (_abi.OP_TRAIN, _abi.OP_LOSS):
+        ns = L.dxvae_workspace_bytes_sched(op, B, bt["n_levels"], ptr(bt["level_ptr"]), ptr(sp))
+        assert 0 < ns <= L.dxvae_workspace_bytes(op, B), (op, ns)
